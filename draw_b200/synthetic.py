@@ -1,0 +1,147 @@
+"""Procedural inputs for the configs that have no asset in the reference tree.
+
+  - `torus(n_theta, n_phi)`     C5: the donut.obj generator scaled up: same
+                                vertex and face enumeration as models/donut/donut.obj
+                                (R=9, r=4), then the loader's post-processing — rescale to
+                                radius 100 (object.rs:159-170) and smooth normals as the
+                                normalised sum of un-normalised face normals (object.rs:394-411).
+  - `checker_texture()`         C5: 1024x1024 RGB checker, per-cell tint from splitmix64.
+  - `airplane_standin(...)`     C1: models/airplane/*.obj is missing from the reference tree
+                                (.MISSING_LARGE_BLOBS); a two-material ellipsoid + canopy bound
+                                to the airplane's MTL coefficients and JPG exercises the same
+                                code (textured opaque body + `d 0.7` glass, transparent pass).
+  - `flythrough_camera(k)`      C4: the 120-frame clipping-heavy camera path.
+Everything is deterministic; nothing here is timed.
+"""
+import numpy as np
+
+from .model import IndexedMesh, Object, Texture
+
+F = np.float32
+
+
+def _norm_rows(a):
+    s = (a[:, 0] * a[:, 0] + a[:, 1] * a[:, 1]).astype(F) + a[:, 2] * a[:, 2]
+    return np.sqrt(s.astype(F)).astype(F)
+
+
+def _rescale_100(v):
+    """object.rs:159-170: v * (100 / max |v|), float32."""
+    factor = F(100.0) / F(_norm_rows(v).max())
+    return (v * factor).astype(F)
+
+
+def _smooth_normals(vertices, tri_v):
+    """object.rs:394-411 in the reference's accumulation order (face-major, corner-minor)."""
+    a, b, c = vertices[tri_v[:, 0]], vertices[tri_v[:, 1]], vertices[tri_v[:, 2]]
+    p, q = (b - a).astype(F), (c - b).astype(F)
+    n = np.stack([(p[:, 1] * q[:, 2]).astype(F) - (p[:, 2] * q[:, 1]).astype(F),
+                  (p[:, 2] * q[:, 0]).astype(F) - (p[:, 0] * q[:, 2]).astype(F),
+                  (p[:, 0] * q[:, 1]).astype(F) - (p[:, 1] * q[:, 0]).astype(F)], 1).astype(F)
+    gen = np.zeros_like(vertices, dtype=F)
+    np.add.at(gen, tri_v.reshape(-1), np.repeat(n, 3, axis=0))  # sequential, in index order
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return (gen / _norm_rows(gen)[:, None]).astype(F)
+
+
+def torus(n_theta=32, n_phi=32, R=9.0, r=4.0, texture=None, name="torus"):
+    """v[j*n_phi+i] = ((R + r cos phi_i) cos theta_j, (R + r cos phi_i) sin theta_j, r sin phi_i);
+    faces (j,i),(j+1,i),(j+1,i+1) and (j,i),(j+1,i+1),(j,i+1), indices wrapping in both directions
+    (the enumeration of models/donut/donut.obj)."""
+    th = 2.0 * np.pi * np.arange(n_theta, dtype=np.float64) / n_theta
+    ph = 2.0 * np.pi * np.arange(n_phi, dtype=np.float64) / n_phi
+    ring = R + r * np.cos(ph)
+    v = np.stack([np.outer(np.cos(th), ring), np.outer(np.sin(th), ring),
+                  np.outer(np.ones_like(th), r * np.sin(ph))], -1).reshape(-1, 3).astype(F)
+    j, i = np.meshgrid(np.arange(n_theta), np.arange(n_phi), indexing="ij")
+    j1, i1 = (j + 1) % n_theta, (i + 1) % n_phi
+    idx = lambda jj, ii: (jj * n_phi + ii).reshape(-1)
+    t0 = np.stack([idx(j, i), idx(j1, i), idx(j1, i1)], 1)
+    t1 = np.stack([idx(j, i), idx(j1, i1), idx(j, i1)], 1)
+    tri_v = np.stack([t0, t1], 1).reshape(-1, 3).astype(np.uint32)
+
+    v = _rescale_100(v)
+    normals = _smooth_normals(v, tri_v)
+    uv = np.stack([(j / n_theta).reshape(-1), (i / n_phi).reshape(-1), np.zeros(j.size)], 1).astype(F)
+    tris = np.concatenate([tri_v, tri_v, tri_v], 1).astype(np.uint32)  # v, t, n share the vertex index
+    textures = [Texture()]
+    tex_idx = 0
+    if texture is not None:
+        textures.append(texture)
+        tex_idx = 1
+    return Object(name, v, normals, uv, [IndexedMesh("default", tris, tex_idx)], textures)
+
+
+def _splitmix64(x):
+    x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    z = x
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return x, z ^ (z >> 31)
+
+
+def checker_texture(size=1024, cells=32, seed=0xD0A7):
+    """RGB checker: two base colours, each cell XOR'd with a 3x5-bit tint from splitmix64(seed)."""
+    base = np.array([[200, 72, 40], [40, 96, 208]], np.uint8)
+    img = np.zeros((size, size, 3), np.uint8)
+    step = size // cells
+    state = seed
+    for cy in range(cells):
+        for cx in range(cells):
+            state, rnd = _splitmix64(state)
+            tint = np.array([rnd & 31, (rnd >> 5) & 31, (rnd >> 10) & 31], np.uint8)
+            img[cy * step:(cy + 1) * step, cx * step:(cx + 1) * step] = base[(cx + cy) & 1] ^ tint
+    return img
+
+
+def checker_material():
+    """C5 material: ka = kd = (1,1,1), ks = (.5,.5,.5), both maps = the checker."""
+    img = checker_texture()
+    return Texture("checker", np.ones(3, F), np.ones(3, F), np.full(3, 0.5, F), 1.0, img, img)
+
+
+def _ellipsoid(n_lon, n_lat, radii, center, flip=False):
+    lon = 2.0 * np.pi * np.arange(n_lon + 1) / n_lon
+    lat = np.pi * (np.arange(n_lat + 1) / n_lat - 0.5)
+    LO, LA = np.meshgrid(lon, lat, indexing="ij")
+    unit = np.stack([np.cos(LA) * np.cos(LO), np.sin(LA), np.cos(LA) * np.sin(LO)], -1).reshape(-1, 3)
+    v = (unit * np.array(radii) + np.array(center)).astype(F)
+    n = unit / np.array(radii)
+    n = (n / np.linalg.norm(n, axis=1, keepdims=True)).astype(F)
+    uv = np.stack([(LO / (2 * np.pi)).reshape(-1), (LA / np.pi + 0.5).reshape(-1), np.zeros(LO.size)], 1).astype(F)
+    a = (np.arange(n_lon)[:, None] * (n_lat + 1) + np.arange(n_lat)[None, :]).reshape(-1)
+    b, c, d = a + (n_lat + 1), a + (n_lat + 1) + 1, a + 1
+    tri = np.concatenate([np.stack([a, c, b], 1), np.stack([a, d, c], 1)], 0)
+    if flip:
+        tri = tri[:, ::-1]
+    return v, n, uv, tri.astype(np.uint32)
+
+
+def airplane_standin(diffuse_map, body_coef=None, glass_coef=None):
+    """Stand-in for the missing airplane mesh: fuselage ellipsoid (opaque, textured) plus a canopy
+    ellipsoid (glass, alpha 0.7) sharing the airplane's JPG, coefficients from its MTL
+    (models/airplane/11804_Airplane_v2_l2.mtl: Ka 1 1 1, Kd 1 1 1, Ks .54 .54 .54, d 1.0 / 0.7)."""
+    bv, bn, buv, bt = _ellipsoid(32, 16, (3.0, 0.6, 0.6), (0.0, 0.0, 0.0))
+    gv, gn, guv, gt = _ellipsoid(20, 10, (0.9, 0.5, 0.45), (1.2, 0.45, 0.0))
+    off = bv.shape[0]
+    v = _rescale_100(np.concatenate([bv, gv], 0))
+    n = np.concatenate([bn, gn], 0)
+    uv = np.concatenate([buv, guv], 0)
+    body = np.concatenate([bt, bt, bt], 1)
+    glass = np.concatenate([gt + off, gt + off, gt + off], 1).astype(np.uint32)
+    one, ks = np.ones(3, F), np.full(3, 0.54, F)
+    textures = [Texture(),
+                Texture("01___11804_Airplane_body", one, one, ks, 1.0, diffuse_map, diffuse_map),
+                Texture("02___11804_Airplane_glass", one, one, ks, float(F(0.7)), diffuse_map, diffuse_map)]
+    return Object("airplane_standin", v, n, uv,
+                  [IndexedMesh("body", body, 1), IndexedMesh("glass", glass, 2)], textures)
+
+
+def flythrough_camera(n_frames=120):
+    """C4 camera path: frame k -> Camera::new(pos_k, dir_k, W/H) with
+    pos_k = (30 sin(2 pi k/120), 10, 150 - 2.5 k), dir_k = (0.3 sin(2 pi k/60), -0.05, -1),
+    evaluated in float64 and rounded once to float32.  Returns float32 [n_frames, 6]."""
+    k = np.arange(n_frames, dtype=np.float64)
+    pos = np.stack([30.0 * np.sin(2 * np.pi * k / 120.0), np.full_like(k, 10.0), 150.0 - 2.5 * k], 1)
+    dr = np.stack([0.3 * np.sin(2 * np.pi * k / 60.0), np.full_like(k, -0.05), np.full_like(k, -1.0)], 1)
+    return np.concatenate([pos, dr], 1).astype(F)
