@@ -1,0 +1,270 @@
+"""Scene / Camera / Canvas with the reference's names and verbs, over the C ABI.
+
+Reads like code written against mororo18/draw's `renderer` module:
+
+    scene = Scene(width, height)            # Scene::new            scene/mod.rs:760
+    canvas = Canvas(width, height)          # Canvas::new           canvas.rs:366
+    canvas.init_depth(100000.0)             #                       canvas.rs:403
+    canvas.apply_offset(0, 0)               #                       canvas.rs:382
+    scene.add_obj(obj)                      # Scene::add_obj        scene/mod.rs:788
+    scene.camera = Camera.new(pos, dir)     # Camera::new           scene/mod.rs:297
+    scene.render(canvas)                    # Scene::render         scene/mod.rs:901
+    frame = canvas.as_bytes_slice()         # Canvas::as_bytes_slice canvas.rs:974
+
+Everything executes in libdraw_b200.so on the GPU; this file only marshals arguments.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from .model import Object
+
+DEPTH_MAX_DEFAULT = 100000.0  # Application::run, src/app/mod.rs:80
+
+
+def _vec3(v):
+    a = np.asarray(v, dtype=np.float32).reshape(3)
+    return (C.c_float * 3)(float(a[0]), float(a[1]), float(a[2]))
+
+
+class Camera:
+    """Camera handle of a scene (scene/mod.rs:282-594).  `Camera.new(pos, dir)` builds a value that
+    can be assigned to `scene.camera`, like `scene.camera = Camera::new(pos, dir, ratio)`; the
+    aspect ratio is always the scene's width/height (scene/mod.rs:768)."""
+
+    def __init__(self, scene):
+        self._scene = scene
+
+    @staticmethod
+    def new(pos, direction):
+        return ("camera", np.asarray(pos, np.float32).copy(), np.asarray(direction, np.float32).copy())
+
+    def _h(self):
+        return self._scene._h
+
+    def get_pos(self):
+        p, d = (C.c_float * 3)(), (C.c_float * 3)()
+        N.check(N.lib().draw_scene_get_camera(self._h(), p, d))
+        return np.array(p, np.float32)
+
+    def get_direction(self):
+        p, d = (C.c_float * 3)(), (C.c_float * 3)()
+        N.check(N.lib().draw_scene_get_camera(self._h(), p, d))
+        return np.array(d, np.float32)
+
+    def set_pos(self, pos):
+        N.check(N.lib().draw_scene_set_camera_pos(self._h(), _vec3(pos)))
+
+    def _move(self, which, dist):
+        N.check(N.lib().draw_scene_camera_move(self._h(), which, float(dist)))
+
+    def move_up(self, dist): self._move(0, dist)
+    def move_down(self, dist): self._move(1, dist)
+    def move_left(self, dist): self._move(2, dist)
+    def move_right(self, dist): self._move(3, dist)
+    def move_foward(self, dist): self._move(4, dist)
+    def move_backward(self, dist): self._move(5, dist)
+
+
+class Canvas:
+    """canvas.rs:353-983."""
+
+    def __init__(self, width, height):
+        h = C.c_void_p()
+        N.check(N.lib().draw_canvas_create(width, height, C.byref(h)))
+        self._h = h
+        self.width, self.height = int(width), int(height)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            N.lib().draw_canvas_destroy(h)
+
+    def init_depth(self, depth=DEPTH_MAX_DEFAULT):
+        N.check(N.lib().draw_canvas_init_depth(self._h, float(depth)))
+
+    def apply_offset(self, x, y):
+        N.check(N.lib().draw_canvas_apply_offset(self._h, int(x), int(y)))
+
+    def resize(self, width, height):
+        N.check(N.lib().draw_canvas_resize(self._h, width, height))
+        self.width, self.height = int(width), int(height)
+
+    def clear(self):
+        N.check(N.lib().draw_canvas_clear(self._h))
+
+    def enable_depth_update(self):
+        N.check(N.lib().draw_canvas_enable_depth_update(self._h))
+
+    def disable_depth_update(self):
+        N.check(N.lib().draw_canvas_disable_depth_update(self._h))
+
+    @staticmethod
+    def pixel_bytes():
+        return 4  # size_of::<Pixel>(), canvas.rs:966
+
+    def size_bytes(self):
+        return self.width * self.height * 4
+
+    def as_bytes_slice(self, copy=True):
+        """uint8 [H, W, 4], B,G,R,pad per pixel, row 0 = top (canvas.rs:974).  Waits for the frame.
+        copy=False returns a view of the library's pinned mirror, valid until the next render."""
+        p, n = C.c_void_p(), C.c_size_t()
+        N.check(N.lib().draw_canvas_map_host(self._h, C.byref(p), C.byref(n)))
+        buf = (C.c_uint8 * n.value).from_address(p.value)
+        a = np.frombuffer(buf, dtype=np.uint8).reshape(self.height, self.width, 4)
+        return a.copy() if copy else a
+
+    def depth(self):
+        """float32 [H, W]; row = canvas y, not flipped (get_pixel_depth, canvas.rs:413)."""
+        out = np.empty((self.height, self.width), np.float32)
+        N.check(N.lib().draw_canvas_read_depth(self._h, out.ctypes.data, out.size))
+        return out
+
+    def get_pixel_depth(self, x, y):
+        return float(self.depth()[y, x])
+
+    def sync(self):
+        N.check(N.lib().draw_canvas_sync(self._h))
+
+    def last_frame_stats(self):
+        s = N.FrameStats()
+        N.check(N.lib().draw_canvas_last_frame_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    # ---- device-side plumbing (multi-GPU drivers, torch interop)
+    def device_ptrs(self):
+        c, d = C.c_void_p(), C.c_void_p()
+        N.check(N.lib().draw_canvas_device_ptrs(self._h, C.byref(c), C.byref(d)))
+        return c.value, d.value
+
+    def bind_external(self, color_ptr, depth_ptr):
+        N.check(N.lib().draw_canvas_bind_external(self._h, color_ptr, depth_ptr))
+
+    def set_stream(self, cuda_stream):
+        N.check(N.lib().draw_canvas_set_stream(self._h, cuda_stream))
+
+    def set_stripe(self, y0, y1):
+        N.check(N.lib().draw_canvas_set_stripe(self._h, y0, y1))
+
+
+class ObjectInfo:
+    """scene/object.rs:12-16."""
+
+    def __init__(self, id_, name, mesh_info_list):
+        self.id, self.name, self.mesh_info_list = id_, name, mesh_info_list
+
+
+class Scene:
+    """scene/mod.rs:749-1252."""
+
+    def __init__(self, width, height):
+        h = C.c_void_p()
+        N.check(N.lib().draw_scene_create(width, height, C.byref(h)))
+        self._h = h
+        self.width, self.height = int(width), int(height)
+        self._camera = Camera(self)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            N.lib().draw_scene_destroy(h)
+
+    @property
+    def camera(self):
+        return self._camera
+
+    @camera.setter
+    def camera(self, value):
+        if not (isinstance(value, tuple) and value and value[0] == "camera"):
+            raise TypeError("assign Camera.new(pos, direction)")
+        N.check(N.lib().draw_scene_set_camera(self._h, _vec3(value[1]), _vec3(value[2])))
+
+    def set_light(self, pos):
+        N.check(N.lib().draw_scene_set_light(self._h, _vec3(pos)))
+
+    def add_obj(self, obj: Object):
+        pos = np.ascontiguousarray(obj.vertices, np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(obj.normals_vertices, np.float32).reshape(-1, 3)
+        uv = np.ascontiguousarray(obj.texture_vertices, np.float32).reshape(-1, 3)
+        keep = [pos, nrm, uv]
+        mats = (N.Material * max(1, len(obj.textures)))()
+        for i, t in enumerate(obj.textures):
+            m = mats[i]
+            m.name = t.name.encode()
+            for j in range(3):
+                m.ka[j], m.kd[j], m.ks[j] = float(np.float32(t.ka[j])), float(np.float32(t.kd[j])), float(np.float32(t.ks[j]))
+            m.alpha = float(np.float32(t.alpha))
+            for field, img in (("map_ka", t.map_ka), ("map_kd", t.map_kd)):
+                tm = getattr(m, field)
+                if img is None:
+                    tm.pixels = None
+                    continue
+                img = np.ascontiguousarray(img, np.uint8)
+                if img.ndim != 3:
+                    raise ValueError("texture maps are uint8 [height, width, components]")
+                same = [k for k in keep if k is img or (k.dtype == np.uint8 and k.shape == img.shape
+                                                        and k.ctypes.data == img.ctypes.data)]
+                if not same:
+                    keep.append(img)
+                tm.pixels = img.ctypes.data
+                tm.height, tm.width, tm.components = img.shape
+        meshes = (N.Mesh * max(1, len(obj.meshes)))()
+        for i, me in enumerate(obj.meshes):
+            tris = np.ascontiguousarray(me.triangles, np.uint32).reshape(-1, 9)
+            keep.append(tris)
+            meshes[i].name = me.name.encode()
+            meshes[i].triangles = tris.ctypes.data
+            meshes[i].n_triangles = tris.shape[0]
+            meshes[i].material_idx = int(me.texture_idx)
+        desc = N.ObjectDesc(obj.name.encode(), pos.ctypes.data, pos.shape[0], nrm.ctypes.data, nrm.shape[0],
+                            uv.ctypes.data, uv.shape[0], C.addressof(meshes), len(obj.meshes),
+                            C.addressof(mats), len(obj.textures))
+        out = C.c_uint32()
+        N.check(N.lib().draw_scene_add_object(self._h, C.byref(desc), C.byref(out)))
+        del keep
+        infos = [(m.name, int(np.asarray(m.triangles).reshape(-1, 9).shape[0]),
+                  obj.textures[m.texture_idx].name) for m in obj.meshes]
+        return ObjectInfo(int(out.value), obj.name, infos)
+
+    def move_camera_direction(self, dx, dy):
+        N.check(N.lib().draw_scene_move_camera_direction(self._h, int(dx), int(dy)))
+
+    def render(self, canvas: Canvas):
+        N.check(N.lib().draw_scene_render(self._h, canvas._h))
+
+    # ---- parity / measurement taps
+    def uniforms(self):
+        m, p = (C.c_float * 16)(), (C.c_float * 24)()
+        N.check(N.lib().draw_scene_get_uniforms(self._h, m, p))
+        return np.array(m, np.float32).reshape(4, 4), np.array(p, np.float32).reshape(6, 4)
+
+    def vertex_visual(self, canvas, first, count):
+        out = np.empty((count, 7), np.float32)
+        N.check(N.lib().draw_scene_read_vertex_visual(self._h, canvas._h, first, count, out.ctypes.data))
+        return out
+
+    def counts(self):
+        a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        N.check(N.lib().draw_scene_counts(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"objects": a.value, "triangles": b.value, "vertices": c.value}
+
+    def launch_count(self):
+        n = C.c_uint64()
+        N.check(N.lib().draw_scene_launch_count(self._h, C.byref(n)))
+        return int(n.value)
+
+
+def device_count():
+    n = C.c_int()
+    N.check(N.lib().draw_device_count(C.byref(n)))
+    return n.value
+
+
+def set_device(index):
+    N.check(N.lib().draw_set_device(int(index)))
+
+
+def tile_size():
+    return N.lib().draw_tile_size()

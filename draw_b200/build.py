@@ -1,0 +1,67 @@
+"""Builds libdraw_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m draw_b200.build [--force] [--verbose]
+
+Device code: -gencode arch=compute_100a,code=sm_100a -fmad=false (the reference never fuses
+a*b+c; all parity-critical arithmetic additionally uses the __f*_rn intrinsics), -lineinfo so
+ncu's source page maps to kernels.cu.  Host code: -ffp-contract=off for the per-frame uniforms.
+The CUDA runtime is linked statically, so the .so only needs the driver on the GPU box.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libdraw_b200.so")
+SOURCES = ["kernels.cu", "scene.cpp", "obj_loader.cpp"]
+HEADERS = ["device_types.h", "host_math.hpp", os.path.join("..", "..", "include", "draw_b200.h")]
+
+NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
+              "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall", "-cudart", "static"]
+
+
+def nvcc_path():
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(p):
+        raise RuntimeError("nvcc not found; libdraw_b200.so cannot be built")
+    return p
+
+
+def up_to_date():
+    if not os.path.exists(LIB):
+        return False
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return all(os.path.getmtime(d) <= t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and up_to_date():
+        return LIB
+    objs = []
+    build_dir = os.path.join(HERE, "build")
+    os.makedirs(build_dir, exist_ok=True)
+    for src in SOURCES:
+        obj = os.path.join(build_dir, src + ".o")
+        cmd = [nvcc_path(), *NVCC_FLAGS, "-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose and src.endswith(".cu"):
+            cmd.insert(1, "-Xptxas=-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode:
+            sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if r.returncode:
+            raise RuntimeError(f"nvcc failed on {src}")
+        objs.append(obj)
+    cmd = [nvcc_path(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
+           "-o", LIB, *objs]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode:
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

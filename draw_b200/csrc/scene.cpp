@@ -1,0 +1,930 @@
+// scene.cpp — host side of libdraw_b200.so: the C ABI of include/draw_b200.h.
+//
+// Mirrors the reference's Scene / Canvas / Camera verbs (mororo18/draw src/renderer/scene/mod.rs,
+// canvas.rs) and owns the device memory: scene geometry as SoA arrays uploaded once per
+// add_object, per-frame work buffers, and the canvas' colour + depth buffers with a pinned
+// host mirror.  Per-frame uniforms are computed here in the reference's float32 operation
+// order (host_math.hpp) and handed to the kernels by value.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/draw_b200.h"
+#include "device_types.h"
+#include "host_math.hpp"
+
+namespace drawb200 {
+cudaError_t launch_frame(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, uint8_t *color, float *depth,
+                         cudaStream_t stream, uint64_t *launches);
+cudaError_t launch_clear(uint8_t *color, float *depth, size_t n_pixels, float depth_max, cudaStream_t stream,
+                         uint64_t *launches);
+cudaError_t launch_fill_u32(uint32_t *dst, size_t n, uint32_t value, cudaStream_t stream, uint64_t *launches);
+} // namespace drawb200
+
+using namespace drawb200;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_error = "";
+int g_device = -1; // device for *_create; -1 = whatever is current
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            const int code_ = (e_ == cudaErrorMemoryAllocation) ? DRAW_ERR_OUT_OF_MEMORY           \
+                              : (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver)     \
+                                  ? DRAW_ERR_NO_DEVICE                                             \
+                                  : DRAW_ERR_CUDA;                                                 \
+            return fail(code_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                          \
+    } while (0)
+
+#define TRY(expr)             \
+    do {                      \
+        int rc_ = (expr);     \
+        if (rc_ != DRAW_OK) return rc_; \
+    } while (0)
+
+// Growable device array.
+template <typename T> struct DevBuf {
+    T *ptr = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { release(); }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+    int reserve(size_t n) {
+        if (n <= cap && ptr) return DRAW_OK;
+        release();
+        if (n == 0) n = 1;
+        CU(cudaMalloc(&ptr, n * sizeof(T)));
+        cap = n;
+        return DRAW_OK;
+    }
+    int upload(const std::vector<T> &host, cudaStream_t st = nullptr) {
+        TRY(reserve(host.size()));
+        if (!host.empty()) CU(cudaMemcpyAsync(ptr, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+        return DRAW_OK;
+    }
+};
+
+struct HostMesh {
+    std::vector<uint32_t> tris; // 9 per triangle, object-local indices
+    uint32_t material;          // object-local
+};
+struct HostObject {
+    std::string name;
+    std::vector<float> pos, nrm, uv; // 3 floats each
+    std::vector<HostMesh> opaque, transparent; // Object::new split, object.rs:45-53
+    std::vector<MaterialDev> materials;        // offsets relative to this object's texel block
+    std::vector<uint8_t> texels;
+};
+
+std::mutex g_registry_mutex;
+std::set<draw_scene *> g_live_scenes;
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------
+struct draw_scene {
+    int device = 0;
+    size_t width = 0, height = 0;
+    CameraState camera;
+    f3 light{0.0f, 300.0f, 300.0f};
+    std::vector<HostObject> objects;
+    bool geometry_dirty = true;
+    uint64_t launches = 0;
+
+    // device geometry
+    DevBuf<float> d_pos[3], d_nrm[3], d_uv[2];
+    DevBuf<uint32_t> d_idx[9], d_mat, d_tslot;
+    DevBuf<MaterialDev> d_materials;
+    DevBuf<uint8_t> d_texels;
+    SceneDev dev{};
+    // host copy of the draw-order index streams of transparent meshes (re-sorted every frame)
+    struct TransparentRange {
+        size_t object, mesh, first_tri; // first_tri = position in the global draw order
+    };
+    std::vector<TransparentRange> transparent_ranges;
+
+    // per-frame work buffers
+    DevBuf<float> w_vert[9];
+    DevBuf<uint32_t> w_flags, w_tile_count, w_tile_offset, w_refs, w_counters;
+    DevBuf<RasterRec> w_rrec, w_trrec;
+    DevBuf<ShadeRec> w_srec, w_tsrec;
+    size_t rec_cap = 0, refs_cap = 0;
+    FrameDev work{};
+    cudaStream_t last_stream = nullptr;
+    cudaEvent_t last_done = nullptr;
+    bool has_last = false;
+};
+
+struct draw_canvas {
+    int device = 0;
+    size_t width = 0, height = 0;
+    int off_x = 0, off_y = 0;
+    float depth_max = 0.0f;
+    bool has_depth = false;
+    bool depth_update = false;
+    DevBuf<uint8_t> d_color;
+    DevBuf<float> d_depth;
+    uint8_t *ext_color = nullptr;
+    float *ext_depth = nullptr;
+    uint8_t *h_color = nullptr; // pinned mirror
+    size_t h_color_cap = 0;
+    bool host_dirty = true;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    size_t stripe_y0 = 0, stripe_y1 = 0; // rows; y1 == 0 means whole canvas
+    uint32_t *h_status = nullptr;        // pinned: counters of the last frame
+    bool frame_pending = false;
+    draw_scene *last_scene = nullptr;
+    draw_frame_stats stats{};
+    uint64_t launches = 0;
+
+    uint8_t *color() { return ext_color ? ext_color : d_color.ptr; }
+    float *depth() { return ext_depth ? ext_depth : d_depth.ptr; }
+};
+
+namespace {
+
+int ensure_device(int device) {
+    int cur = -1;
+    CU(cudaGetDevice(&cur));
+    if (cur != device) CU(cudaSetDevice(device));
+    return DRAW_OK;
+}
+
+int pick_device(int *out) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(DRAW_ERR_NO_DEVICE, "no usable CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (g_device >= 0) {
+        if (g_device >= n) return fail(DRAW_ERR_INVALID_ARGUMENT, "device %d out of range (%d devices)", g_device, n);
+        *out = g_device;
+        CU(cudaSetDevice(g_device));
+    } else {
+        CU(cudaGetDevice(out));
+    }
+    return DRAW_OK;
+}
+
+// Rebuilds the device geometry from the host objects: SoA, all objects concatenated, triangles
+// in the reference's draw order (per object: opaque meshes, then transparent meshes).
+int upload_geometry(draw_scene *s) {
+    std::vector<float> pos[3], nrm[3], uv[2];
+    std::vector<uint32_t> idx[9], mat, tslot;
+    std::vector<MaterialDev> materials;
+    std::vector<uint8_t> texels;
+    s->transparent_ranges.clear();
+    uint32_t n_transparent = 0;
+    bool any_transparent = false;
+    for (const HostObject &o : s->objects)
+        if (!o.transparent.empty()) any_transparent = true;
+
+    for (size_t oi = 0; oi < s->objects.size(); oi++) {
+        const HostObject &o = s->objects[oi];
+        const uint32_t vbase = (uint32_t)pos[0].size(), nbase = (uint32_t)nrm[0].size(), tbase = (uint32_t)uv[0].size();
+        const uint32_t mbase = (uint32_t)materials.size(), xbase = (uint32_t)texels.size();
+        for (size_t i = 0; i < o.pos.size() / 3; i++)
+            for (int c = 0; c < 3; c++) pos[c].push_back(o.pos[3 * i + c]);
+        for (size_t i = 0; i < o.nrm.size() / 3; i++)
+            for (int c = 0; c < 3; c++) nrm[c].push_back(o.nrm[3 * i + c]);
+        for (size_t i = 0; i < o.uv.size() / 3; i++)
+            for (int c = 0; c < 2; c++) uv[c].push_back(o.uv[3 * i + c]);
+        for (MaterialDev m : o.materials) {
+            m.ka_off += xbase;
+            m.kd_off += xbase;
+            materials.push_back(m);
+        }
+        texels.insert(texels.end(), o.texels.begin(), o.texels.end());
+        auto push_mesh = [&](const HostMesh &m, bool transparent) {
+            const size_t n = m.tris.size() / 9;
+            for (size_t t = 0; t < n; t++) {
+                const uint32_t *p = &m.tris[9 * t];
+                for (int c = 0; c < 3; c++) {
+                    idx[c].push_back(p[c] + vbase);
+                    idx[3 + c].push_back(p[3 + c] + tbase);
+                    idx[6 + c].push_back(p[6 + c] + nbase);
+                }
+                mat.push_back((m.material + mbase) | (transparent ? 0x80000000u : 0u));
+                if (any_transparent) tslot.push_back(transparent ? n_transparent++ : 0u);
+            }
+        };
+        for (const HostMesh &m : o.opaque) push_mesh(m, false);
+        for (size_t mi = 0; mi < o.transparent.size(); mi++) {
+            s->transparent_ranges.push_back({oi, mi, mat.size()});
+            push_mesh(o.transparent[mi], true);
+        }
+    }
+    if (mat.size() >= (1u << 30)) return fail(DRAW_ERR_INVALID_ARGUMENT, "too many triangles (%zu)", mat.size());
+
+    for (int c = 0; c < 3; c++) TRY(s->d_pos[c].upload(pos[c]));
+    for (int c = 0; c < 3; c++) TRY(s->d_nrm[c].upload(nrm[c]));
+    for (int c = 0; c < 2; c++) TRY(s->d_uv[c].upload(uv[c]));
+    for (int c = 0; c < 9; c++) TRY(s->d_idx[c].upload(idx[c]));
+    TRY(s->d_mat.upload(mat));
+    TRY(s->d_tslot.upload(tslot));
+    TRY(s->d_materials.upload(materials));
+    TRY(s->d_texels.upload(texels));
+    CU(cudaDeviceSynchronize()); // the host vectors above are about to go away
+
+    SceneDev &d = s->dev;
+    d.px = s->d_pos[0].ptr; d.py = s->d_pos[1].ptr; d.pz = s->d_pos[2].ptr;
+    d.nx = s->d_nrm[0].ptr; d.ny = s->d_nrm[1].ptr; d.nz = s->d_nrm[2].ptr;
+    d.tu = s->d_uv[0].ptr; d.tv = s->d_uv[1].ptr;
+    for (int c = 0; c < 9; c++) d.idx[c] = s->d_idx[c].ptr;
+    d.tri_mat = s->d_mat.ptr;
+    d.tri_tslot = any_transparent ? s->d_tslot.ptr : nullptr;
+    d.materials = s->d_materials.ptr;
+    d.texels = s->d_texels.ptr;
+    d.n_vertices = (uint32_t)pos[0].size();
+    d.n_triangles = (uint32_t)mat.size();
+    d.n_transparent = n_transparent;
+    s->geometry_dirty = false;
+    return DRAW_OK;
+}
+
+int ensure_work_buffers(draw_scene *s, size_t n_tiles) {
+    const SceneDev &d = s->dev;
+    for (int i = 0; i < 9; i++) TRY(s->w_vert[i].reserve(d.n_vertices));
+    TRY(s->w_flags.reserve(d.n_vertices));
+    if (s->rec_cap == 0) s->rec_cap = 2 * (size_t)d.n_triangles + 1024;
+    if (s->refs_cap == 0) s->refs_cap = std::max<size_t>((size_t)1 << 22, 4 * (size_t)d.n_triangles);
+    TRY(s->w_rrec.reserve(s->rec_cap));
+    TRY(s->w_srec.reserve(s->rec_cap));
+    TRY(s->w_trrec.reserve(4 * (size_t)d.n_transparent));
+    TRY(s->w_tsrec.reserve(4 * (size_t)d.n_transparent));
+    TRY(s->w_tile_count.reserve(n_tiles));
+    TRY(s->w_tile_offset.reserve(n_tiles + 1));
+    TRY(s->w_refs.reserve(s->refs_cap));
+    TRY(s->w_counters.reserve(4));
+    FrameDev &w = s->work;
+    w.v_lx = s->w_vert[0].ptr; w.v_ly = s->w_vert[1].ptr; w.v_lz = s->w_vert[2].ptr;
+    w.v_hx = s->w_vert[3].ptr; w.v_hy = s->w_vert[4].ptr; w.v_hz = s->w_vert[5].ptr;
+    w.v_depth = s->w_vert[6].ptr; w.v_sx = s->w_vert[7].ptr; w.v_sy = s->w_vert[8].ptr;
+    w.v_flags = s->w_flags.ptr;
+    w.rrec = s->w_rrec.ptr; w.srec = s->w_srec.ptr;
+    w.t_rrec = s->w_trrec.ptr; w.t_srec = s->w_tsrec.ptr;
+    w.tile_count = s->w_tile_count.ptr; w.tile_offset = s->w_tile_offset.ptr; w.tile_refs = s->w_refs.ptr;
+    w.counters = s->w_counters.ptr;
+    w.rec_cap = (uint32_t)s->rec_cap;
+    w.refs_cap = (uint32_t)s->refs_cap;
+    return DRAW_OK;
+}
+
+// Painter sort of every transparent mesh (scene/mod.rs:1100-1115): stable, far to near by
+// f32::total_cmp of the centroid distance, persistent across frames; re-uploads the index
+// streams of meshes whose order changed.
+int sort_transparent(draw_scene *s, cudaStream_t stream) {
+    const f3 cam = s->camera.position;
+    for (const draw_scene::TransparentRange &tr : s->transparent_ranges) {
+        HostObject &o = s->objects[tr.object];
+        HostMesh &m = o.transparent[tr.mesh];
+        const size_t n = m.tris.size() / 9;
+        std::vector<int32_t> key(n);
+        for (size_t t = 0; t < n; t++) {
+            const uint32_t *p = &m.tris[9 * t];
+            auto vert = [&](uint32_t v) { return f3{o.pos[3 * v], o.pos[3 * v + 1], o.pos[3 * v + 2]}; };
+            const f3 center = divide(add(add(vert(p[0]), vert(p[1])), vert(p[2])), 3.0f); // :1108
+            key[t] = total_order_key(length(sub(center, cam)));                           // Vec3::dist
+        }
+        std::vector<uint32_t> order(n);
+        for (size_t t = 0; t < n; t++) order[t] = (uint32_t)t;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] > key[b]; });
+        bool changed = false;
+        for (size_t t = 0; t < n; t++)
+            if (order[t] != t) { changed = true; break; }
+        if (!changed) continue;
+        std::vector<uint32_t> sorted(m.tris.size());
+        for (size_t t = 0; t < n; t++) std::memcpy(&sorted[9 * t], &m.tris[9 * order[t]], 9 * sizeof(uint32_t));
+        m.tris.swap(sorted);
+        // global index bases of this object
+        uint32_t vbase = 0, nbase = 0, tbase = 0;
+        for (size_t oi = 0; oi < tr.object; oi++) {
+            vbase += (uint32_t)(s->objects[oi].pos.size() / 3);
+            nbase += (uint32_t)(s->objects[oi].nrm.size() / 3);
+            tbase += (uint32_t)(s->objects[oi].uv.size() / 3);
+        }
+        std::vector<uint32_t> stream_host(n);
+        for (int c = 0; c < 9; c++) {
+            const uint32_t base = c < 3 ? vbase : (c < 6 ? tbase : nbase);
+            for (size_t t = 0; t < n; t++) stream_host[t] = m.tris[9 * t + c] + base;
+            // pageable source: the call returns once the data is staged, so the vector may be reused
+            CU(cudaMemcpyAsync(s->d_idx[c].ptr + tr.first_tri, stream_host.data(), n * sizeof(uint32_t),
+                               cudaMemcpyHostToDevice, stream));
+        }
+    }
+    return DRAW_OK;
+}
+
+int enqueue_frame(draw_scene *s, draw_canvas *c) {
+    TRY(ensure_device(s->device));
+    if (s->geometry_dirty) TRY(upload_geometry(s));
+    const uint32_t tiles_x = (uint32_t)((c->width + TILE - 1) / TILE), tiles_y = (uint32_t)((c->height + TILE - 1) / TILE);
+    TRY(ensure_work_buffers(s, (size_t)tiles_x * tiles_y));
+
+    // serialise frames that share this scene's work buffers across different streams
+    if (s->has_last && s->last_stream != c->stream) CU(cudaStreamWaitEvent(c->stream, s->last_done, 0));
+
+    FrameUniforms U{};
+    const m4 m = transformation_matrix(s->camera, s->width, s->height); // :904
+    std::memcpy(U.m, m.v, sizeof U.m);
+    plane4 planes[6];
+    s->camera.view_planes(planes); // :908
+    for (int i = 0; i < 6; i++) {
+        U.planes[i][0] = planes[i].nx; U.planes[i][1] = planes[i].ny;
+        U.planes[i][2] = planes[i].nz; U.planes[i][3] = planes[i].k;
+    }
+    U.cam[0] = s->camera.position.x; U.cam[1] = s->camera.position.y; U.cam[2] = s->camera.position.z;
+    U.light[0] = s->light.x; U.light[1] = s->light.y; U.light[2] = s->light.z;
+    U.off_x = (float)c->off_x;
+    U.off_y = (float)c->off_y;
+    U.depth_max = c->depth_max;
+    U.canvas_w = (uint32_t)c->width;
+    U.canvas_h = (uint32_t)c->height;
+    U.tiles_x = tiles_x;
+    U.tiles_y = tiles_y;
+    const size_t y0 = c->stripe_y1 ? c->stripe_y0 : 0, y1 = c->stripe_y1 ? c->stripe_y1 : c->height;
+    U.tile_y_begin = (uint32_t)(y0 / TILE);
+    U.tile_y_end = (uint32_t)((y1 + TILE - 1) / TILE);
+
+    if (s->dev.n_transparent) TRY(sort_transparent(s, c->stream));
+
+    CU(launch_frame(U, s->dev, s->work, c->color(), c->depth(), c->stream, &s->launches));
+    CU(cudaMemcpyAsync(c->h_status, s->work.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (!s->last_done) CU(cudaEventCreateWithFlags(&s->last_done, cudaEventDisableTiming));
+    CU(cudaEventRecord(s->last_done, c->stream));
+    s->last_stream = c->stream;
+    s->has_last = true;
+    c->frame_pending = true;
+    c->host_dirty = true;
+    c->last_scene = s;
+    return DRAW_OK;
+}
+
+// Waits for the canvas' stream; if the last frame overflowed a work buffer, grows it and
+// renders the frame again (so what the host reads is always a complete frame).
+int finish_frame(draw_canvas *c) {
+    TRY(ensure_device(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    int guard = 0;
+    while (c->frame_pending) {
+        c->frame_pending = false;
+        draw_scene *s = c->last_scene;
+        bool alive;
+        {
+            std::lock_guard<std::mutex> lk(g_registry_mutex);
+            alive = g_live_scenes.count(s) != 0;
+        }
+        const uint32_t n_rec = c->h_status[0], n_refs = c->h_status[1], overflow = c->h_status[2];
+        c->stats.setup_records = n_rec;
+        c->stats.tile_refs = n_refs;
+        if (alive) {
+            c->stats.input_triangles = s->dev.n_triangles;
+            c->stats.transparent_slots = s->dev.n_transparent * 4;
+        }
+        if (!overflow) break;
+        c->stats.overflow = overflow;
+        if (!alive) return fail(DRAW_ERR_INTERNAL, "frame overflowed a work buffer and its scene is gone");
+        if (++guard > 4) return fail(DRAW_ERR_INTERNAL, "work buffers keep overflowing");
+        if (overflow & OVERFLOW_RECORDS)
+            s->rec_cap = std::max<size_t>((size_t)n_rec + n_rec / 4 + 1024, 4 * (size_t)s->dev.n_triangles + 1024);
+        if (overflow & OVERFLOW_REFS) s->refs_cap = (size_t)n_refs + n_refs / 4 + 4096;
+        else if (overflow & OVERFLOW_RECORDS) s->refs_cap = std::max(s->refs_cap, 4 * s->rec_cap);
+        TRY(enqueue_frame(s, c));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return DRAW_OK;
+}
+
+int fill_color_black(draw_canvas *c, size_t first, size_t count) {
+    if (!count) return DRAW_OK;
+    // Pixel::black(): b=0 g=0 r=0 pad=255 (canvas.rs:63-70,128-130)
+    CU(launch_fill_u32(reinterpret_cast<uint32_t *>(c->d_color.ptr) + first, count, 0xFF000000u, c->stream, &c->launches));
+    return DRAW_OK;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+#define GUARD_BEGIN try {
+#define GUARD_END                                                                  \
+    }                                                                              \
+    catch (const std::bad_alloc &) { return fail(DRAW_ERR_OUT_OF_MEMORY, "host allocation failed"); } \
+    catch (const std::exception &e) { return fail(DRAW_ERR_INTERNAL, "internal error: %s", e.what()); } \
+    catch (...) { return fail(DRAW_ERR_INTERNAL, "internal error"); }
+
+extern "C" {
+
+int draw_version(void) { return DRAW_B200_VERSION; }
+const char *draw_last_error(void) { return g_error.c_str(); }
+
+int draw_device_count(int *out_count) {
+    if (!out_count) return fail(DRAW_ERR_INVALID_ARGUMENT, "out_count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    *out_count = n;
+    return DRAW_OK;
+}
+
+int draw_set_device(int device) {
+    if (device < 0) return fail(DRAW_ERR_INVALID_ARGUMENT, "negative device index");
+    g_device = device;
+    return DRAW_OK;
+}
+
+int draw_tile_size(void) { return TILE; }
+
+// ---- Scene ---------------------------------------------------------------------------------
+
+int draw_scene_create(size_t width, size_t height, draw_scene **out) {
+    GUARD_BEGIN
+    if (!out) return fail(DRAW_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (width == 0 || height == 0) return fail(DRAW_ERR_INVALID_ARGUMENT, "scene size must be non-zero");
+    int dev = 0;
+    TRY(pick_device(&dev));
+    draw_scene *s = new draw_scene();
+    s->device = dev;
+    s->width = width;
+    s->height = height;
+    // Scene::new, scene/mod.rs:760-786
+    const f3 pos{0.0f, 0.0f, 150.0f};
+    const f3 dir = scale(pos, -1.0f);
+    const float ratio = (float)width / (float)height;
+    s->camera = CameraState::make(pos, dir, ratio);
+    {
+        std::lock_guard<std::mutex> lk(g_registry_mutex);
+        g_live_scenes.insert(s);
+    }
+    *out = s;
+    return DRAW_OK;
+    GUARD_END
+}
+
+void draw_scene_destroy(draw_scene *scene) {
+    if (!scene) return;
+    {
+        std::lock_guard<std::mutex> lk(g_registry_mutex);
+        g_live_scenes.erase(scene);
+    }
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess) {
+        if (cur != scene->device) cudaSetDevice(scene->device);
+        cudaDeviceSynchronize();
+        if (scene->last_done) cudaEventDestroy(scene->last_done);
+    }
+    delete scene;
+}
+
+int draw_scene_add_object(draw_scene *scene, const draw_object_desc *desc, uint32_t *out_id) {
+    GUARD_BEGIN
+    if (!scene || !desc) return fail(DRAW_ERR_INVALID_ARGUMENT, "scene or desc is NULL");
+    if ((desc->n_positions && !desc->positions) || (desc->n_normals && !desc->normals) || (desc->n_uvs && !desc->uvs) ||
+        (desc->n_meshes && !desc->meshes) || (desc->n_materials && !desc->materials))
+        return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL array with non-zero count");
+    HostObject o;
+    o.name = desc->name ? desc->name : "";
+    o.pos.assign(desc->positions, desc->positions + 3 * desc->n_positions);
+    o.nrm.assign(desc->normals, desc->normals + 3 * desc->n_normals);
+    o.uv.assign(desc->uvs, desc->uvs + 3 * desc->n_uvs);
+    // texel block of this object; offset 0 holds the 1x1 white default map (scene/mod.rs:128-135)
+    o.texels = {255, 255, 255, 255};
+    auto add_map = [&](const draw_texture_map &m, uint32_t &off, uint32_t &w, uint32_t &h, uint32_t &comp) -> int {
+        if (!m.pixels) {
+            off = 0; w = 1; h = 1; comp = 3;
+            return DRAW_OK;
+        }
+        if (m.width == 0 || m.height == 0 || (m.components != 3 && m.components != 4))
+            return fail(DRAW_ERR_INVALID_ARGUMENT, "texture map must be non-empty with 3 or 4 components");
+        const size_t bytes = (size_t)m.width * m.height * m.components;
+        // identical images inside one object (map_Ka == map_Kd is common) share storage
+        off = (uint32_t)o.texels.size();
+        o.texels.insert(o.texels.end(), m.pixels, m.pixels + bytes);
+        while (o.texels.size() % 4) o.texels.push_back(0);
+        w = m.width; h = m.height; comp = m.components;
+        return DRAW_OK;
+    };
+    std::vector<std::pair<const uint8_t *, uint32_t>> seen; // pointer -> offset, dedupe by pointer
+    for (size_t i = 0; i < desc->n_materials; i++) {
+        const draw_material &m = desc->materials[i];
+        MaterialDev d{};
+        for (int c = 0; c < 3; c++) { d.ka[c] = m.ka[c]; d.kd[c] = m.kd[c]; d.ks[c] = m.ks[c]; }
+        d.alpha = m.alpha;
+        auto add_dedup = [&](const draw_texture_map &tm, uint32_t &off, uint32_t &w, uint32_t &h, uint32_t &comp) -> int {
+            for (auto &pr : seen)
+                if (tm.pixels && pr.first == tm.pixels) {
+                    off = pr.second; w = tm.width; h = tm.height; comp = tm.components;
+                    return DRAW_OK;
+                }
+            TRY(add_map(tm, off, w, h, comp));
+            if (tm.pixels) seen.push_back({tm.pixels, off});
+            return DRAW_OK;
+        };
+        TRY(add_dedup(m.map_ka, d.ka_off, d.ka_w, d.ka_h, d.ka_comp));
+        TRY(add_dedup(m.map_kd, d.kd_off, d.kd_w, d.kd_h, d.kd_comp));
+        o.materials.push_back(d);
+    }
+    for (size_t i = 0; i < desc->n_meshes; i++) {
+        const draw_mesh &dm = desc->meshes[i];
+        if (dm.n_triangles && !dm.triangles) return fail(DRAW_ERR_INVALID_ARGUMENT, "mesh %zu: NULL triangles", i);
+        // Object::new indexes textures[texture_idx] (object.rs:46-48) and would panic
+        if (dm.material_idx >= desc->n_materials)
+            return fail(DRAW_ERR_INVALID_ARGUMENT, "mesh %zu: material index %u out of range (%zu materials)", i,
+                        dm.material_idx, desc->n_materials);
+        HostMesh hm;
+        hm.material = dm.material_idx;
+        hm.tris.assign(dm.triangles, dm.triangles + 9 * dm.n_triangles);
+        for (size_t t = 0; t < dm.n_triangles; t++) {
+            const uint32_t *p = &hm.tris[9 * t];
+            for (int c = 0; c < 3; c++)
+                if (p[c] >= desc->n_positions || p[3 + c] >= desc->n_uvs || p[6 + c] >= desc->n_normals)
+                    return fail(DRAW_ERR_INVALID_ARGUMENT, "mesh %zu triangle %zu: index out of range", i, t); // mesh.rs:46-48
+        }
+        if (desc->materials[dm.material_idx].alpha < 1.0f) o.transparent.push_back(std::move(hm)); // object.rs:48-52
+        else o.opaque.push_back(std::move(hm));
+    }
+    scene->objects.push_back(std::move(o));
+    scene->geometry_dirty = true;
+    scene->rec_cap = scene->refs_cap = 0; // re-derive capacities for the new triangle count
+    if (out_id) *out_id = (uint32_t)scene->objects.size() - 1;
+    return DRAW_OK;
+    GUARD_END
+}
+
+int draw_scene_set_camera(draw_scene *scene, const float pos[3], const float dir[3]) {
+    if (!scene || !pos || !dir) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    const float ratio = (float)scene->width / (float)scene->height; // scene/mod.rs:768
+    scene->camera = CameraState::make(f3{pos[0], pos[1], pos[2]}, f3{dir[0], dir[1], dir[2]}, ratio);
+    return DRAW_OK;
+}
+
+int draw_scene_get_camera(const draw_scene *scene, float pos[3], float dir[3]) {
+    if (!scene || !pos || !dir) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    pos[0] = scene->camera.position.x; pos[1] = scene->camera.position.y; pos[2] = scene->camera.position.z;
+    dir[0] = scene->camera.direction.x; dir[1] = scene->camera.direction.y; dir[2] = scene->camera.direction.z;
+    return DRAW_OK;
+}
+
+int draw_scene_set_camera_pos(draw_scene *scene, const float pos[3]) {
+    if (!scene || !pos) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    scene->camera.position = f3{pos[0], pos[1], pos[2]};
+    return DRAW_OK;
+}
+
+int draw_scene_camera_move(draw_scene *scene, draw_camera_dir dir, float dist) {
+    if (!scene) return fail(DRAW_ERR_INVALID_ARGUMENT, "scene is NULL");
+    CameraState &c = scene->camera;
+    switch (dir) { // scene/mod.rs:381-405
+    case DRAW_CAMERA_UP: c.position = add(c.position, scale(c.up, dist)); break;
+    case DRAW_CAMERA_DOWN: c.position = add(c.position, scale(c.up, -dist)); break;
+    case DRAW_CAMERA_LEFT: c.position = add(c.position, scale(c.u, -dist)); break;
+    case DRAW_CAMERA_RIGHT: c.position = add(c.position, scale(c.u, dist)); break;
+    case DRAW_CAMERA_FOWARD: c.position = add(c.position, scale(unit(cross3(c.up, c.u)), dist)); break;
+    case DRAW_CAMERA_BACKWARD: c.position = add(c.position, scale(unit(cross3(c.u, c.up)), dist)); break;
+    default: return fail(DRAW_ERR_INVALID_ARGUMENT, "unknown camera direction %d", (int)dir);
+    }
+    return DRAW_OK;
+}
+
+int draw_scene_move_camera_direction(draw_scene *scene, int dx, int dy) {
+    if (!scene) return fail(DRAW_ERR_INVALID_ARGUMENT, "scene is NULL");
+    // the reference asserts dx < width and dy < height (scene/mod.rs:804-805)
+    if (dx >= (long long)scene->width || dy >= (long long)scene->height)
+        return fail(DRAW_ERR_INVALID_ARGUMENT, "dx/dy must be smaller than the scene size");
+    CameraState &c = scene->camera;
+    const float fx = (float)dx / (float)scene->width, fy = (float)dy / (float)scene->height;
+    c.direction = unit(add(add(c.direction, scale(c.u, fx)), scale(c.v, fy))); // :430-432
+    c.update_basis();
+    return DRAW_OK;
+}
+
+int draw_scene_set_light(draw_scene *scene, const float pos[3]) {
+    if (!scene || !pos) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    scene->light = f3{pos[0], pos[1], pos[2]};
+    return DRAW_OK;
+}
+
+int draw_scene_render(draw_scene *scene, draw_canvas *canvas) {
+    GUARD_BEGIN
+    if (!scene || !canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "scene or canvas is NULL");
+    if (scene->device != canvas->device)
+        return fail(DRAW_ERR_INVALID_ARGUMENT, "scene (device %d) and canvas (device %d) live on different devices",
+                    scene->device, canvas->device);
+    if (!canvas->has_depth) return fail(DRAW_ERR_INVALID_ARGUMENT, "Depth not initialized"); // canvas.rs:914
+    if (canvas->frame_pending) {
+        // settle the previous frame's status first (grows buffers if it overflowed)
+        TRY(ensure_device(canvas->device));
+        if (cudaStreamQuery(canvas->stream) == cudaSuccess) TRY(finish_frame(canvas));
+    }
+    canvas->stats.overflow = 0;
+    return enqueue_frame(scene, canvas);
+    GUARD_END
+}
+
+int draw_scene_get_uniforms(draw_scene *scene, float matrix[16], float planes[24]) {
+    if (!scene || !matrix || !planes) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    const m4 m = transformation_matrix(scene->camera, scene->width, scene->height);
+    std::memcpy(matrix, m.v, 16 * sizeof(float));
+    plane4 p[6];
+    scene->camera.view_planes(p);
+    for (int i = 0; i < 6; i++) {
+        planes[4 * i] = p[i].nx; planes[4 * i + 1] = p[i].ny; planes[4 * i + 2] = p[i].nz; planes[4 * i + 3] = p[i].k;
+    }
+    return DRAW_OK;
+}
+
+int draw_scene_read_vertex_visual(draw_scene *scene, draw_canvas *canvas, size_t first, size_t count, float *out) {
+    GUARD_BEGIN
+    if (!scene || !canvas || !out) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    TRY(finish_frame(canvas));
+    if (first + count > scene->dev.n_vertices) return fail(DRAW_ERR_INVALID_ARGUMENT, "vertex range out of bounds");
+    std::vector<float> tmp(count);
+    const int order[7] = {0, 1, 2, 3, 4, 5, 6}; // light xyz, halfway xyz, depth
+    for (int k = 0; k < 7; k++) {
+        CU(cudaMemcpy(tmp.data(), scene->w_vert[order[k]].ptr + first, count * sizeof(float), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < count; i++) out[7 * i + k] = tmp[i];
+    }
+    return DRAW_OK;
+    GUARD_END
+}
+
+int draw_scene_counts(const draw_scene *scene, size_t *n_objects, size_t *n_triangles, size_t *n_vertices) {
+    if (!scene) return fail(DRAW_ERR_INVALID_ARGUMENT, "scene is NULL");
+    size_t t = 0, v = 0;
+    for (const HostObject &o : scene->objects) {
+        v += o.pos.size() / 3;
+        for (const HostMesh &m : o.opaque) t += m.tris.size() / 9;
+        for (const HostMesh &m : o.transparent) t += m.tris.size() / 9;
+    }
+    if (n_objects) *n_objects = scene->objects.size();
+    if (n_triangles) *n_triangles = t;
+    if (n_vertices) *n_vertices = v;
+    return DRAW_OK;
+}
+
+int draw_scene_launch_count(const draw_scene *scene, uint64_t *out) {
+    if (!scene || !out) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = scene->launches;
+    return DRAW_OK;
+}
+
+// ---- Canvas --------------------------------------------------------------------------------
+
+int draw_canvas_create(size_t width, size_t height, draw_canvas **out) {
+    GUARD_BEGIN
+    if (!out) return fail(DRAW_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (width == 0 || height == 0 || width > 65535 || height > 65535)
+        return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas size must be in 1..65535");
+    int dev = 0;
+    TRY(pick_device(&dev));
+    draw_canvas *c = new draw_canvas();
+    c->device = dev;
+    c->width = width;
+    c->height = height;
+    auto cleanup = [&](int rc) {
+        draw_canvas_destroy(c);
+        return rc;
+    };
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return cleanup(fail(DRAW_ERR_CUDA, "cudaStreamCreate failed"));
+    c->stream = c->own_stream;
+    if (cudaMallocHost(&c->h_status, 4 * sizeof(uint32_t)) != cudaSuccess)
+        return cleanup(fail(DRAW_ERR_OUT_OF_MEMORY, "cudaMallocHost failed"));
+    std::memset(c->h_status, 0, 4 * sizeof(uint32_t));
+    int rc = c->d_color.reserve(width * height * 4);
+    if (rc) return cleanup(rc);
+    rc = fill_color_black(c, 0, width * height); // vec![Pixel::black(); len], canvas.rs:368
+    if (rc) return cleanup(rc);
+    *out = c;
+    return DRAW_OK;
+    GUARD_END
+}
+
+void draw_canvas_destroy(draw_canvas *canvas) {
+    if (!canvas) return;
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess) {
+        if (cur != canvas->device) cudaSetDevice(canvas->device);
+        if (canvas->stream) cudaStreamSynchronize(canvas->stream);
+        if (canvas->own_stream) cudaStreamDestroy(canvas->own_stream);
+        if (canvas->h_color) cudaFreeHost(canvas->h_color);
+        if (canvas->h_status) cudaFreeHost(canvas->h_status);
+    }
+    delete canvas;
+}
+
+int draw_canvas_init_depth(draw_canvas *canvas, float depth) {
+    GUARD_BEGIN
+    if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas is NULL");
+    TRY(ensure_device(canvas->device));
+    canvas->depth_max = depth;
+    TRY(canvas->d_depth.reserve(canvas->width * canvas->height));
+    canvas->has_depth = true;
+    uint32_t bits;
+    std::memcpy(&bits, &depth, 4);
+    CU(launch_fill_u32(reinterpret_cast<uint32_t *>(canvas->depth()), canvas->width * canvas->height, bits,
+                       canvas->stream, &canvas->launches));
+    return DRAW_OK;
+    GUARD_END
+}
+
+int draw_canvas_apply_offset(draw_canvas *canvas, int x, int y) {
+    if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas is NULL");
+    canvas->off_x = x;
+    canvas->off_y = y;
+    return DRAW_OK;
+}
+
+int draw_canvas_resize(draw_canvas *canvas, size_t width, size_t height) {
+    GUARD_BEGIN
+    if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas is NULL");
+    if (width == 0 || height == 0 || width > 65535 || height > 65535)
+        return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas size must be in 1..65535");
+    if (canvas->ext_color || canvas->ext_depth)
+        return fail(DRAW_ERR_INVALID_ARGUMENT, "cannot resize a canvas bound to external memory");
+    TRY(finish_frame(canvas));
+    // Vec::resize on the flat pixel vector (canvas.rs:390): keep the first min(old,new) pixels
+    const size_t old_n = canvas->width * canvas->height, new_n = width * height;
+    DevBuf<uint8_t> fresh;
+    TRY(fresh.reserve(new_n * 4));
+    const size_t keep = std::min(old_n, new_n);
+    CU(cudaMemcpyAsync(fresh.ptr, canvas->d_color.ptr, keep * 4, cudaMemcpyDeviceToDevice, canvas->stream));
+    CU(cudaStreamSynchronize(canvas->stream));
+    std::swap(fresh.ptr, canvas->d_color.ptr);
+    std::swap(fresh.cap, canvas->d_color.cap);
+    canvas->width = width;
+    canvas->height = height;
+    TRY(fill_color_black(canvas, keep, new_n - keep));
+    canvas->stripe_y0 = canvas->stripe_y1 = 0;
+    canvas->host_dirty = true;
+    // self.init_depth(self.depth_max), canvas.rs:392 — allocates the depth buffer even if none existed
+    return draw_canvas_init_depth(canvas, canvas->depth_max);
+    GUARD_END
+}
+
+int draw_canvas_clear(draw_canvas *canvas) {
+    GUARD_BEGIN
+    if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas is NULL");
+    TRY(ensure_device(canvas->device));
+    CU(launch_clear(canvas->color(), canvas->has_depth ? canvas->depth() : nullptr, canvas->width * canvas->height,
+                    canvas->depth_max, canvas->stream, &canvas->launches));
+    canvas->host_dirty = true;
+    return DRAW_OK;
+    GUARD_END
+}
+
+int draw_canvas_enable_depth_update(draw_canvas *canvas) {
+    if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas is NULL");
+    canvas->depth_update = true;
+    return DRAW_OK;
+}
+int draw_canvas_disable_depth_update(draw_canvas *canvas) {
+    if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas is NULL");
+    canvas->depth_update = false;
+    return DRAW_OK;
+}
+
+int draw_canvas_size(const draw_canvas *canvas, size_t *width, size_t *height) {
+    if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas is NULL");
+    if (width) *width = canvas->width;
+    if (height) *height = canvas->height;
+    return DRAW_OK;
+}
+
+int draw_canvas_map_host(draw_canvas *canvas, const uint8_t **out_bytes, size_t *out_len) {
+    GUARD_BEGIN
+    if (!canvas || !out_bytes) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    TRY(finish_frame(canvas));
+    const size_t bytes = canvas->width * canvas->height * 4;
+    if (canvas->h_color_cap < bytes) {
+        if (canvas->h_color) cudaFreeHost(canvas->h_color);
+        canvas->h_color = nullptr;
+        canvas->h_color_cap = 0;
+        CU(cudaMallocHost(&canvas->h_color, bytes));
+        canvas->h_color_cap = bytes;
+        canvas->host_dirty = true;
+    }
+    if (canvas->host_dirty) {
+        CU(cudaMemcpyAsync(canvas->h_color, canvas->color(), bytes, cudaMemcpyDeviceToHost, canvas->stream));
+        CU(cudaStreamSynchronize(canvas->stream));
+        canvas->host_dirty = false;
+    }
+    *out_bytes = canvas->h_color;
+    if (out_len) *out_len = bytes;
+    return DRAW_OK;
+    GUARD_END
+}
+
+int draw_canvas_read_depth(draw_canvas *canvas, float *dst, size_t n_floats) {
+    GUARD_BEGIN
+    if (!canvas || !dst) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!canvas->has_depth) return fail(DRAW_ERR_INVALID_ARGUMENT, "Depth not initialized");
+    if (n_floats != canvas->width * canvas->height)
+        return fail(DRAW_ERR_INVALID_ARGUMENT, "n_floats must be width*height");
+    TRY(finish_frame(canvas));
+    CU(cudaMemcpyAsync(dst, canvas->depth(), n_floats * sizeof(float), cudaMemcpyDeviceToHost, canvas->stream));
+    CU(cudaStreamSynchronize(canvas->stream));
+    return DRAW_OK;
+    GUARD_END
+}
+
+int draw_canvas_sync(draw_canvas *canvas) {
+    GUARD_BEGIN
+    if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas is NULL");
+    return finish_frame(canvas);
+    GUARD_END
+}
+
+int draw_canvas_last_frame_stats(draw_canvas *canvas, draw_frame_stats *out) {
+    GUARD_BEGIN
+    if (!canvas || !out) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    TRY(finish_frame(canvas));
+    *out = canvas->stats;
+    return DRAW_OK;
+    GUARD_END
+}
+
+int draw_canvas_device_ptrs(draw_canvas *canvas, void **out_color, void **out_depth) {
+    if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas is NULL");
+    if (out_color) *out_color = canvas->color();
+    if (out_depth) *out_depth = canvas->has_depth ? canvas->depth() : nullptr;
+    return DRAW_OK;
+}
+
+int draw_canvas_bind_external(draw_canvas *canvas, void *color_dev, void *depth_dev) {
+    GUARD_BEGIN
+    if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas is NULL");
+    TRY(finish_frame(canvas));
+    canvas->ext_color = static_cast<uint8_t *>(color_dev);
+    canvas->ext_depth = static_cast<float *>(depth_dev);
+    if (depth_dev) canvas->has_depth = true;
+    canvas->host_dirty = true;
+    return DRAW_OK;
+    GUARD_END
+}
+
+int draw_canvas_set_stream(draw_canvas *canvas, void *cuda_stream) {
+    GUARD_BEGIN
+    if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas is NULL");
+    TRY(finish_frame(canvas));
+    canvas->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : canvas->own_stream;
+    return DRAW_OK;
+    GUARD_END
+}
+
+int draw_canvas_set_stripe(draw_canvas *canvas, size_t y0, size_t y1) {
+    if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas is NULL");
+    if (y0 >= y1 || y1 > canvas->height) return fail(DRAW_ERR_INVALID_ARGUMENT, "stripe must satisfy y0 < y1 <= height");
+    if (y0 % TILE || (y1 % TILE && y1 != canvas->height))
+        return fail(DRAW_ERR_INVALID_ARGUMENT, "stripe bounds must be multiples of the tile size %d (or the canvas height)", TILE);
+    if (y0 == 0 && y1 == canvas->height) canvas->stripe_y0 = canvas->stripe_y1 = 0;
+    else {
+        canvas->stripe_y0 = y0;
+        canvas->stripe_y1 = y1;
+    }
+    return DRAW_OK;
+}
+
+} // extern "C"
+
+namespace drawb200 {
+int loader_fail(int code, const char *msg) { return fail(code, "%s", msg); }
+} // namespace drawb200

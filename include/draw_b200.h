@@ -1,0 +1,194 @@
+/*
+ * draw_b200.h — C ABI of the B200-native renderer (libdraw_b200.so).
+ *
+ * This is the drop-in boundary for the one hot path of mororo18/draw: everything under
+ * `Scene::render(&mut Canvas)` (src/renderer/scene/mod.rs:901) up to the bytes returned by
+ * `Canvas::as_bytes_slice()` (src/renderer/canvas.rs:974).  The reference has no FFI of its
+ * own; the seam is the pair of public Rust types `Scene` / `Canvas` used by
+ * `Application` (src/app/mod.rs:44-45,65-84,196-202).  Each entry point below names the
+ * reference item it replaces.  INTEGRATION.md shows the Rust `extern "C"` block a maintainer
+ * would add to bind them.
+ *
+ * Conventions
+ *   - Plain C: opaque handles, pointers and sizes.  No C++ or torch types cross the boundary.
+ *   - Every function returns a draw_status (0 = ok, negative = error) unless noted; on error
+ *     `draw_last_error()` returns a thread-local message.  The reference panics instead
+ *     (assert!/unwrap/expect); no exception or abort crosses this boundary.
+ *   - Inputs are borrowed for the duration of the call and copied (to device memory where
+ *     needed); the caller keeps ownership of every array it passes in.
+ *   - Handles are not thread-safe (the reference is single-threaded, `&mut` everywhere);
+ *     distinct handles may be used from distinct threads.
+ *   - A scene and a canvas live on the CUDA device that was current when they were created
+ *     and must be used together on that device.  There is no CPU fallback: every compute
+ *     entry point fails with DRAW_ERR_NO_DEVICE when no CUDA device is usable.
+ *   - float arrays are IEEE binary32; positions / normals / uvs are 3 floats per element
+ *     (uv as the reference's Vec3, z is ignored by the renderer, object.rs:151-155).
+ */
+#ifndef DRAW_B200_H
+#define DRAW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRAW_B200_VERSION 100 /* 0.1.0 */
+
+typedef enum draw_status {
+    DRAW_OK = 0,
+    DRAW_ERR_INVALID_ARGUMENT = -1,
+    DRAW_ERR_NO_DEVICE = -2,
+    DRAW_ERR_CUDA = -3,
+    DRAW_ERR_OUT_OF_MEMORY = -4,
+    DRAW_ERR_IO = -5,
+    DRAW_ERR_INTERNAL = -6
+} draw_status;
+
+typedef struct draw_scene draw_scene;   /* Scene  (scene/mod.rs:749-757) */
+typedef struct draw_canvas draw_canvas; /* Canvas (canvas.rs:353-363)    */
+typedef struct draw_object draw_object; /* Object (object.rs:18-31), host-side, from the loader */
+
+/* TextureMap (scene/mod.rs:102-110).  pixels == NULL means TextureMap::default(): 1x1x3 white
+ * (scene/mod.rs:128-135).  components is 3 or 4; row 0 is the top of the image. */
+typedef struct draw_texture_map {
+    const uint8_t *pixels;
+    uint32_t width, height, components;
+} draw_texture_map;
+
+/* Texture (scene/mod.rs:206-216): Phong coefficients, opacity and the two maps. */
+typedef struct draw_material {
+    const char *name; /* may be NULL */
+    float ka[3], kd[3], ks[3];
+    float alpha; /* < 1 puts the mesh in the transparent pass (object.rs:45-53) */
+    draw_texture_map map_ka, map_kd;
+} draw_material;
+
+/* IndexedMesh (mesh.rs:31-35).  triangles holds 9 indices per triangle:
+ * (v0 v1 v2, t0 t1 t2, n0 n1 n2) = the reference's (vertex, texture, normal) index triples. */
+typedef struct draw_mesh {
+    const char *name; /* may be NULL */
+    const uint32_t *triangles;
+    size_t n_triangles;
+    uint32_t material_idx; /* index into draw_object_desc.materials (IndexedMesh.texture_idx) */
+} draw_mesh;
+
+/* The arguments of Object::new (object.rs:34-41). */
+typedef struct draw_object_desc {
+    const char *name; /* may be NULL */
+    const float *positions; size_t n_positions;
+    const float *normals;   size_t n_normals;
+    const float *uvs;       size_t n_uvs;
+    const draw_mesh *meshes;         size_t n_meshes;
+    const draw_material *materials;  size_t n_materials;
+} draw_object_desc;
+
+/* Camera::move_* (scene/mod.rs:381-405) */
+typedef enum draw_camera_dir {
+    DRAW_CAMERA_UP = 0, DRAW_CAMERA_DOWN = 1, DRAW_CAMERA_LEFT = 2,
+    DRAW_CAMERA_RIGHT = 3, DRAW_CAMERA_FOWARD = 4, DRAW_CAMERA_BACKWARD = 5
+} draw_camera_dir;
+
+/* Counters of the last completed frame (device-side bookkeeping, read back at sync). */
+typedef struct draw_frame_stats {
+    uint32_t input_triangles;   /* triangles in the scene's draw list */
+    uint32_t setup_records;     /* triangles that survived cull / reject / clip / zero-area */
+    uint32_t tile_refs;         /* (tile, triangle) pairs produced by binning */
+    uint32_t transparent_slots; /* slots scanned by the ordered transparent pass */
+    uint32_t overflow;          /* non-zero: a device buffer was too small, frame was re-rendered */
+    uint32_t reserved[3];
+} draw_frame_stats;
+
+/* ---- library ------------------------------------------------------------------------ */
+int draw_version(void);                 /* returns DRAW_B200_VERSION */
+const char *draw_last_error(void);      /* thread-local, never NULL */
+int draw_device_count(int *out_count);  /* CUDA devices visible to this process */
+int draw_set_device(int device);        /* device used by subsequent *_create calls */
+
+/* ---- Scene (scene/mod.rs) ------------------------------------------------------------ */
+/* Scene::new(width, height) :760 — default camera (0,0,150) looking at the origin, light at
+ * (0,300,300).  width/height size the viewport transform (:818-819, :889-894). */
+int draw_scene_create(size_t width, size_t height, draw_scene **out);
+void draw_scene_destroy(draw_scene *scene);
+/* Object::new :34 + Scene::add_obj :788.  Copies the geometry to the device.  out_id may be
+ * NULL; ids count up from 0 like ObjectInfo.id. */
+int draw_scene_add_object(draw_scene *scene, const draw_object_desc *desc, uint32_t *out_id);
+/* scene.camera = Camera::new(pos, dir, ratio) :297, ratio = scene width / height (:768). */
+int draw_scene_set_camera(draw_scene *scene, const float pos[3], const float dir[3]);
+int draw_scene_get_camera(const draw_scene *scene, float pos[3], float dir[3]);
+/* Camera::set_pos :377 */
+int draw_scene_set_camera_pos(draw_scene *scene, const float pos[3]);
+/* Camera::move_up/down/left/right/foward/backward :381-405 */
+int draw_scene_camera_move(draw_scene *scene, draw_camera_dir dir, float dist);
+/* Scene::move_camera_direction(dx, dy) :803 */
+int draw_scene_move_camera_direction(draw_scene *scene, int dx, int dy);
+/* light_source is a private field initialised at :766; settable here for completeness */
+int draw_scene_set_light(draw_scene *scene, const float pos[3]);
+/* Scene::render(&mut Canvas) :901 — THE hot path.  Enqueues the frame on the canvas' stream
+ * and returns without waiting; the first host read (map_host / read_depth / sync) waits. */
+int draw_scene_render(draw_scene *scene, draw_canvas *canvas);
+/* Debug / parity taps: matrix_transf (:817-899, row-major 16 floats) and the six view planes
+ * (:481-593) as near, far, right, left, top, bottom, each (nx, ny, nz, k). */
+int draw_scene_get_uniforms(draw_scene *scene, float matrix[16], float planes[24]);
+/* Per-vertex visual info of the last rendered frame (:917-926) for vertices
+ * [first, first+count) of the scene's concatenated vertex list: 7 floats per vertex
+ * (light3, halfway3, depth).  Waits for the frame. */
+int draw_scene_read_vertex_visual(draw_scene *scene, draw_canvas *canvas, size_t first, size_t count,
+                                  float *out);
+int draw_scene_counts(const draw_scene *scene, size_t *n_objects, size_t *n_triangles,
+                      size_t *n_vertices);
+/* Kernels launched by this scene so far (bench.py reports the delta over the timed region). */
+int draw_scene_launch_count(const draw_scene *scene, uint64_t *out);
+
+/* ---- Canvas (canvas.rs) -------------------------------------------------------------- */
+/* Canvas::new(width, height) :366 — colour BGRA8 (Pixel, :51-59), black; no depth yet. */
+int draw_canvas_create(size_t width, size_t height, draw_canvas **out);
+void draw_canvas_destroy(draw_canvas *canvas);
+int draw_canvas_init_depth(draw_canvas *canvas, float depth);     /* :403 */
+int draw_canvas_apply_offset(draw_canvas *canvas, int x, int y);  /* :382 */
+int draw_canvas_resize(draw_canvas *canvas, size_t width, size_t height); /* :387 */
+int draw_canvas_clear(draw_canvas *canvas);                       /* :425 */
+int draw_canvas_enable_depth_update(draw_canvas *canvas);         /* :399 (render sets it itself) */
+int draw_canvas_disable_depth_update(draw_canvas *canvas);        /* :395 */
+int draw_canvas_size(const draw_canvas *canvas, size_t *width, size_t *height);
+/* Canvas::as_bytes_slice / as_ptr / size_bytes :966-982.  Waits for the frame, copies it to a
+ * pinned host mirror if it changed, and returns that mirror: width*height*4 bytes, B,G,R,pad
+ * per pixel, row 0 = top.  Valid until the next render / resize / destroy on this canvas. */
+int draw_canvas_map_host(draw_canvas *canvas, const uint8_t **out_bytes, size_t *out_len);
+/* depth_frame (get_pixel_depth :413): width*height floats, row index = canvas y (not flipped). */
+int draw_canvas_read_depth(draw_canvas *canvas, float *dst, size_t n_floats);
+/* Wait for everything enqueued on the canvas' stream. */
+int draw_canvas_sync(draw_canvas *canvas);
+int draw_canvas_last_frame_stats(draw_canvas *canvas, draw_frame_stats *out);
+
+/* ---- device-side plumbing (not in the reference; used by the multi-GPU drivers) ------ */
+/* Device pointers of the colour (BGRA8, y-flipped rows) and depth (f32) buffers. */
+int draw_canvas_device_ptrs(draw_canvas *canvas, void **out_color, void **out_depth);
+/* Render into caller-owned device memory instead (e.g. a torch tensor, or a peer GPU's
+ * framebuffer opened through CUDA IPC).  NULL restores the canvas' own buffer.  The colour
+ * buffer must hold width*height*4 bytes; depth width*height floats. */
+int draw_canvas_bind_external(draw_canvas *canvas, void *color_dev, void *depth_dev);
+/* Enqueue on an existing CUDA stream (a cudaStream_t passed as void*); NULL = own stream. */
+int draw_canvas_set_stream(draw_canvas *canvas, void *cuda_stream);
+/* Sort-first partition: render only canvas rows y in [y0, y1) (canvas y = depth-buffer row;
+ * colour row = height-1-y).  Rows outside are left untouched.  (0, height) = whole frame.
+ * y0 and y1 must be multiples of the tile height (draw_tile_size) or equal to height. */
+int draw_canvas_set_stripe(draw_canvas *canvas, size_t y0, size_t y1);
+int draw_tile_size(void);
+
+/* ---- Object loader (object.rs:73-454), host only ------------------------------------- */
+/* Object::load_from_file :106.  Texture images referenced by the MTL are decoded by the
+ * caller-supplied callback (the reference uses stb_image, scene/mod.rs:174-202, which is not
+ * part of this library); a NULL callback leaves maps at the 1x1 default. */
+typedef int (*draw_image_loader)(const char *path, void *user, uint8_t **out_pixels, uint32_t *out_w,
+                                 uint32_t *out_h, uint32_t *out_components);
+int draw_object_load_obj(const char *path, draw_image_loader loader, void *user, draw_object **out);
+void draw_object_free(draw_object *obj);
+/* Borrow the loaded object as a desc (valid until draw_object_free). */
+int draw_object_desc_of(const draw_object *obj, draw_object_desc *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRAW_B200_H */

@@ -1,0 +1,63 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every symbol that
+include/draw_b200.h declares, and fails loudly (no CPU fallback) when there is no GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "draw_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = set(re.findall(r"\b(draw_[a-z0-9_]+)\s*\(", text))
+    names.discard("draw_image_loader")
+    return names
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from draw_b200 import build
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    declared = _declared_symbols()
+    assert len(declared) >= 35
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, f"declared in include/draw_b200.h but not exported: {missing}"
+
+
+def test_binding_covers_the_header():
+    from draw_b200 import _native
+    assert set(_native.SIGNATURES) == _declared_symbols()
+
+
+def test_version_and_error_string():
+    from draw_b200 import _native
+    L = _native.lib()
+    assert L.draw_version() == 100
+    assert isinstance(L.draw_last_error(), bytes)
+    assert L.draw_tile_size() == 64
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import draw_b200
+    with pytest.raises(draw_b200.DrawError) as e:
+        draw_b200.Scene(64, 48)
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+    with pytest.raises(draw_b200.DrawError):
+        draw_b200.Canvas(64, 48)
+
+
+def test_product_does_not_import_the_oracle():
+    """The oracle is test infrastructure: nothing under draw_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "draw_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".h", ".hpp")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "oracle/" not in src and "liboracle" not in src, f
