@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py — frames/s and Mtri/s of the draw hot path at 3840x2160 Phong+texture on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c3|c2|c4|c5]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      (N > 1)
+
+One "step" is one frame: Scene::render of the whole scene into a 4K canvas (BASELINE.json
+configs[2], "C3": soldier1 + skeleton + lemur, 20 697 triangles, Phong + texture).  Rank 0 prints
+ONE JSON line.  Keys beyond the base contract:
+
+  value / ms_per_step   frames already resident in HBM, K frames back to back on one stream,
+                        CUDA events around the K steps, max over ranks.  Frames rotate over a ring
+                        of canvases larger than L2 so no step finds its framebuffer in L2.
+  e2e                   the same metric through the public API with host buffers: every step sets
+                        the camera (host), renders, and reads the BGRA frame back into pinned host
+                        memory (Canvas::as_bytes_slice), host clock around the K steps.
+  roofline              k_tile (the dominant kernel): algorithmic bytes per launch / its mean
+                        device time from CUDA events recorded around it on the launching stream,
+                        against MEASURED_PEAKS.json's HBM copy bandwidth.
+  cpu_baseline          the CPU oracle (C++ restatement of the reference renderer, 1 thread) on a
+                        bounded number of frames of the same workload, rank 0, N = 1 only.
+  sort_first            (N > 1) one frame partitioned into tile-row stripes across the ranks and
+                        gathered on rank 0 over NCCL; reported beside the frame-parallel `value`.
+
+--impl reference times the reference's CPU implementation of the path.  The reference is a Rust
+program; no Rust toolchain exists in this image, so the arm runs the C++ oracle port
+(oracle/oracle.cpp), single-threaded like the reference (it has no threads anywhere in src/).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+DEPTH_MAX = 100000.0
+
+CONFIGS = {
+    "c2": dict(scene="c2_donut", W=1920, H=1080, label="C2 donut 1920x1080 Phong only"),
+    "c3": dict(scene="c3_trio", W=3840, H=2160, label="C3 soldier1+skeleton+lemur 3840x2160 Phong+texture"),
+    "c4": dict(scene="c4_dungeon", W=3840, H=2160, label="C4 dungeon_set 120-frame fly-through 3840x2160", path=True),
+    "c5": dict(scene=None, W=7680, H=4320, label="C5 synthetic 10M-triangle torus 7680x4320 Phong+checker texture"),
+}
+
+
+def load_workload(name):
+    from draw_b200 import scene_cache, synthetic
+    cfg = dict(CONFIGS[name])
+    if name == "c5":
+        n_theta, n_phi = int(os.environ.get("DRAW_C5_NTHETA", 2500)), int(os.environ.get("DRAW_C5_NPHI", 2000))
+        cfg["objects"] = [synthetic.torus(n_theta, n_phi, texture=synthetic.checker_material())]
+    else:
+        cfg["objects"] = scene_cache.load(os.path.join(GOLDEN, "scenes", cfg["scene"] + ".npz"))
+    cfg["cameras"] = (np.load(os.path.join(GOLDEN, "c4_camera_path.npy")) if cfg.get("path") else None)
+    objs = cfg["objects"]
+    cfg["triangles"] = int(sum(o.triangle_count() for o in objs))
+    n_pos = sum(o.vertices.shape[0] for o in objs)
+    n_nrm = sum(o.normals_vertices.shape[0] for o in objs)
+    n_uv = sum(o.texture_vertices.shape[0] for o in objs)
+    tex_bytes = 0
+    for o in objs:
+        used = {m.texture_idx for m in o.meshes}
+        seen = set()
+        for i in used:
+            for img in (o.textures[i].map_ka, o.textures[i].map_kd):
+                if img is None:
+                    tex_bytes += 3 if "default" not in seen else 0
+                    seen.add("default")
+                elif id(img) not in seen:
+                    seen.add(id(img))
+                    tex_bytes += int(np.asarray(img).size)
+    # ALGO_BYTES(frame) = 8 W H + 36 T + 12 (Np + Nn + Nuv) + bound texture bytes
+    cfg["tex_bytes"] = tex_bytes
+    cfg["algo_bytes_frame"] = 8 * cfg["W"] * cfg["H"] + 36 * cfg["triangles"] + 12 * (n_pos + n_nrm + n_uv) + tex_bytes
+    cfg["algo_bytes_tile_kernel"] = 8 * cfg["W"] * cfg["H"] + tex_bytes
+    return cfg
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc = gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side: the oracle as cpu_baseline and as the reference arm
+# ------------------------------------------------------------------------------------------------
+def oracle_scene(cfg):
+    from oracle import pyoracle
+    s, c = pyoracle.Scene(cfg["W"], cfg["H"]), pyoracle.Canvas(cfg["W"], cfg["H"])
+    c.init_depth(DEPTH_MAX)
+    c.apply_offset(0, 0)
+    for o in cfg["objects"]:
+        s.add_obj(o)
+    return s, c
+
+
+def oracle_frame(s, c, cfg, k):
+    if cfg["cameras"] is not None:
+        cam = cfg["cameras"][k % len(cfg["cameras"])]
+        s.set_camera(cam[:3], cam[3:])
+    s.render(c)
+
+
+def cpu_baseline(cfg, budget_s=12.0, max_frames=400):
+    s, c = oracle_scene(cfg)
+    oracle_frame(s, c, cfg, 0)  # warm-up (page faults, caches)
+    t0, n = time.perf_counter(), 0
+    while n < max_frames and (n < 3 or time.perf_counter() - t0 < budget_s):
+        oracle_frame(s, c, cfg, n)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "frames/s", "cores": 1, "kind": "port",
+            "mtri_per_s": cfg["triangles"] * n / dt / 1e6,
+            "sample": f"{n} frames of the {cfg['label']} workload in {dt:.1f} s, C++ oracle port "
+                      f"(oracle/oracle.cpp, -O3, -ffp-contract=off), 1 thread of {os.cpu_count()} host cores; "
+                      "the reference renderer is single-threaded"}
+
+
+def run_reference(args, cfg):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    s, c = oracle_scene(cfg)
+    # bounded sample: at most ~60 s of CPU work overall
+    oracle_frame(s, c, cfg, 0)
+    t0 = time.perf_counter()
+    oracle_frame(s, c, cfg, 0)
+    per = time.perf_counter() - t0
+    steps = max(1, min(args.steps, int(45.0 / max(per, 1e-6))))
+    warm = max(0, min(args.warmup, int(10.0 / max(per, 1e-6))))
+    for k in range(warm):
+        oracle_frame(s, c, cfg, k)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        oracle_frame(s, c, cfg, k)
+    dt = time.perf_counter() - t0
+    fps = steps / dt
+    line = {
+        "impl": "reference", "metric": "frames/s at 3840x2160 (Phong+texture)", "value": fps, "unit": "frames/s",
+        "mtri_per_s": cfg["triangles"] * fps / 1e6, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "reference model assets (committed scene cache), default camera",
+        "config": {"workload": cfg["label"], "triangles": cfg["triangles"], "width": cfg["W"], "height": cfg["H"]},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port",
+                         "sample": f"{steps} frames ({args.steps} requested) of {cfg['label']}; C++ oracle port of the "
+                                   f"single-threaded Rust reference (no Rust toolchain in this image), 1 of "
+                                   f"{os.cpu_count()} host cores"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, cfg):
+    import torch
+    import draw_b200
+
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the draw_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    draw_b200.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        dist = None
+    # a real (non-default) stream: the library enqueues on it and torch's events are recorded on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    W, H = cfg["W"], cfg["H"]
+
+    scene = draw_b200.Scene(W, H)
+    for o in cfg["objects"]:
+        scene.add_obj(o)
+    # ring of canvases: working set of framebuffers larger than the 126 MB L2
+    n_ring = max(2, int(np.ceil(160e6 / (8 * W * H))) + 1)
+    ring = []
+    for _ in range(n_ring):
+        c = draw_b200.Canvas(W, H)
+        c.init_depth(DEPTH_MAX)
+        c.apply_offset(0, 0)
+        c.set_stream(stream.cuda_stream)
+        ring.append(c)
+    cams = cfg["cameras"]
+
+    def frame(k, canvas):
+        if cams is not None:
+            cam = cams[k % len(cams)]
+            scene.camera = draw_b200.Camera.new(cam[:3], cam[3:])
+        scene.render(canvas)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # settle work-buffer capacities over the whole camera path before anything is timed
+    for k in range(len(cams) if cams is not None else 1):
+        frame(k, ring[0])
+        ring[0].sync()
+    for k in range(args.warmup):
+        frame(k, ring[k % n_ring])
+    barrier()
+
+    # ---- timed region: K frames back to back ------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = scene.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for k in range(args.steps):
+        frame(k, ring[k % n_ring])
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = scene.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    for c in ring:
+        st = c.last_frame_stats()
+        if st["overflow"]:
+            raise SystemExit(f"bench.py: a timed frame overflowed a work buffer ({st}); timing invalid")
+    if dist is not None:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    frames_total = args.steps * world
+    fps = frames_total / (ms_total * 1e-3)
+
+    # ---- per-kernel times (separate pass, same workload, events around each kernel) -----------
+    scene.set_kernel_timing(True)
+    ktimes = {k: [] for k in scene.KERNELS}
+    n_prof = min(args.steps, 50)
+    for k in range(n_prof):
+        frame(k, ring[k % n_ring])
+        for name, ms in scene.last_kernel_times(ring[k % n_ring]).items():
+            ktimes[name].append(ms)
+    scene.set_kernel_timing(False)
+    kmean = {k: float(np.mean(v)) for k, v in ktimes.items()}
+
+    # ---- L2-flushed per-step timing (second protocol, reported beside the ring number) ---------
+    flush = torch.empty(int(256e6) // 4, dtype=torch.float32, device="cuda")
+    per_step = []
+    for k in range(min(args.steps, 30)):
+        flush.fill_(float(k))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        frame(k, ring[0])
+        b.record(stream)
+        torch.cuda.synchronize()
+        per_step.append(a.elapsed_time(b))
+    del flush
+
+    # ---- e2e: public API, host in / host out ----------------------------------------------------
+    canvas = ring[0]
+    for k in range(3):
+        frame(k, canvas)
+        canvas.as_bytes_slice(copy=False)
+    barrier()
+    t0 = time.perf_counter()
+    checksum = 0
+    for k in range(args.steps):
+        if cams is None:  # the per-step host input: the camera (scene.camera = Camera::new(...))
+            scene.camera = draw_b200.Camera.new([0.0, 0.0, 150.0], [0.0, 0.0, -150.0])
+        frame(k, canvas)
+        host = canvas.as_bytes_slice(copy=False)
+        checksum ^= int(host[H // 2, W // 2, 0])
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_fps = frames_total / e2e_s
+
+    sort_first = None
+    if dist is not None:
+        from draw_b200 import multi
+        sort_first = multi.bench_sort_first(scene, cfg, dist, steps=min(args.steps, 100), warmup=args.warmup)
+
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        t_tile = kmean["k_tile"] * 1e-3
+        achieved = cfg["algo_bytes_tile_kernel"] / t_tile / 1e9
+        frame_gbs = cfg["algo_bytes_frame"] / (ms_total * 1e-3 / args.steps) / 1e9
+        line = {
+            "metric": "frames/s at 3840x2160 (Phong+texture)", "value": fps, "unit": "frames/s",
+            "mtri_per_s": cfg["triangles"] * fps / 1e6,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "reference model assets (committed scene cache), default camera; no published baseline",
+            "config": {"workload": cfg["label"], "triangles": cfg["triangles"], "width": W, "height": H,
+                       "parallelism": "single GPU" if world == 1 else f"frame-parallel x{world} (no collective)",
+                       "l2": f"ring of {n_ring} canvases x {8 * W * H / 1e6:.0f} MB (colour+depth) = "
+                             f"{n_ring * 8 * W * H / 1e6:.0f} MB > 126 MB L2, rotated every step",
+                       "ms_per_step_l2_flushed": float(np.median(per_step)),
+                       "l2_flushed_protocol": "256 MB fill between steps, CUDA events per step, median"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 220,
+                    "d2h_bytes_per_step": 4 * W * H + 12,
+                    "note": "per step: camera set on host, Scene::render, Canvas::as_bytes_slice into pinned "
+                            "host memory; geometry is uploaded once by add_obj like the reference's Scene owns "
+                            "its objects"},
+            "gpu_launches": launches,
+            "kernel_ms": kmean,
+            "roofline": {"bound": "hbm", "kernel": "k_tile", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algo_bytes_per_launch": cfg["algo_bytes_tile_kernel"],
+                         "frame_algo_bytes": cfg["algo_bytes_frame"], "frame_achieved": frame_gbs,
+                         "frame_frac": frame_gbs / peak},
+        }
+        if sort_first is not None:
+            line["sort_first"] = sort_first
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(cfg)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    cfg = load_workload(args.config)
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,145 @@
+// device_math.cuh — strict float32 device arithmetic shared by all kernels.
+//
+// Numerical contract: every float operation is a single
+// round-to-nearest binary32 operation in the reference's evaluation order (mororo18/draw
+// src/renderer/linalg.rs).  Everything goes through __fadd_rn/__fsub_rn/__fmul_rn/__fdiv_rn/
+// __fsqrt_rn, which ptxas never fuses into FMAs or reassociates; the .cu files are also
+// compiled with -fmad=false.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_types.h"
+
+namespace drawb200 {
+
+#define FADD(a, b) __fadd_rn((a), (b))
+#define FSUB(a, b) __fsub_rn((a), (b))
+#define FMUL(a, b) __fmul_rn((a), (b))
+#define FDIV(a, b) __fdiv_rn((a), (b))
+
+struct v3 {
+    float x, y, z;
+};
+__device__ __forceinline__ v3 v_add(v3 a, v3 b) { return {FADD(a.x, b.x), FADD(a.y, b.y), FADD(a.z, b.z)}; }
+__device__ __forceinline__ v3 v_sub(v3 a, v3 b) { return {FSUB(a.x, b.x), FSUB(a.y, b.y), FSUB(a.z, b.z)}; }
+__device__ __forceinline__ v3 v_div(v3 a, float s) { return {FDIV(a.x, s), FDIV(a.y, s), FDIV(a.z, s)}; }
+// linalg.rs:182-184
+__device__ __forceinline__ float v_dot(v3 a, v3 b) {
+    return FADD(FADD(FMUL(a.x, b.x), FMUL(a.y, b.y)), FMUL(a.z, b.z));
+}
+// linalg.rs:167-171
+__device__ __forceinline__ float v_norm(v3 a) {
+    return __fsqrt_rn(FADD(FADD(FMUL(a.x, a.x), FMUL(a.y, a.y)), FMUL(a.z, a.z)));
+}
+// linalg.rs:186-200
+__device__ __forceinline__ v3 v_cross(v3 a, v3 b) {
+    return {FSUB(FMUL(a.y, b.z), FMUL(a.z, b.y)), FSUB(FMUL(a.z, b.x), FMUL(a.x, b.z)),
+            FSUB(FMUL(a.x, b.y), FMUL(a.y, b.x))};
+}
+// ViewPlane::func, scene/mod.rs:634-636
+__device__ __forceinline__ float plane_eval(const float *pl, v3 p) {
+    return FADD(v_dot(v3{pl[0], pl[1], pl[2]}, p), pl[3]);
+}
+// One row of Matrix4 * Vec4 with w = 1 (linalg.rs:346-360): (((0 + m0*x) + m1*y) + m2*z) + m3*1
+__device__ __forceinline__ float mat_row(const float *m, v3 p) {
+    return FADD(FADD(FADD(FADD(0.0f, FMUL(m[0], p.x)), FMUL(m[1], p.y)), FMUL(m[2], p.z)), m[3]);
+}
+
+// canvas.rs:597-616 : f(x,y) = (((P.y-Q.y)*x + (Q.x-P.x)*y) + P.x*Q.y) - Q.x*P.y
+struct Edge {
+    float cx, cy, k1, k2;
+};
+__device__ __forceinline__ Edge make_edge(float px, float py, float qx, float qy) {
+    return {FSUB(py, qy), FSUB(qx, px), FMUL(px, qy), FMUL(qx, py)};
+}
+__device__ __forceinline__ float edge_eval(const Edge &e, float x, float y) {
+    return FSUB(FADD(FADD(FMUL(e.cx, x), FMUL(e.cy, y)), e.k1), e.k2);
+}
+
+// Rust `f32 as usize`: saturating, NaN -> 0 (cvt.rzi.u64.f32 has exactly these semantics)
+__device__ __forceinline__ unsigned long long sat_usize(float v) { return __float2ull_rz(v); }
+// Rust `f32 as u8` (saturating, NaN -> 0)
+__device__ __forceinline__ uint32_t sat_u8(float v) {
+    const uint32_t u = __float2uint_rz(v);
+    return u > 255u ? 255u : u;
+}
+
+__device__ __forceinline__ void store_raster(RasterRec *dst, const RasterRec &r) {
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+    d[0] = make_uint4(__float_as_uint(r.ax), __float_as_uint(r.ay), __float_as_uint(r.bx), __float_as_uint(r.by));
+    d[1] = make_uint4(__float_as_uint(r.cx), __float_as_uint(r.cy), __float_as_uint(r.da), __float_as_uint(r.db));
+    d[2] = make_uint4(__float_as_uint(r.dc), r.id, r.bbx, r.bby);
+}
+__device__ __forceinline__ RasterRec load_raster(const RasterRec *src) {
+    const uint4 *s = reinterpret_cast<const uint4 *>(src);
+    const uint4 a = __ldg(s), b = __ldg(s + 1), c = __ldg(s + 2);
+    RasterRec r;
+    r.ax = __uint_as_float(a.x); r.ay = __uint_as_float(a.y); r.bx = __uint_as_float(a.z); r.by = __uint_as_float(a.w);
+    r.cx = __uint_as_float(b.x); r.cy = __uint_as_float(b.y); r.da = __uint_as_float(b.z); r.db = __uint_as_float(b.w);
+    r.dc = __uint_as_float(c.x); r.id = c.y; r.bbx = c.z; r.bby = c.w;
+    return r;
+}
+
+// The three edge functions of a screen triangle prepared for coverage tests.
+//   edge 0 = bc (alpha, opposite vertex a), 1 = ca (beta, b), 2 = ab (gama, c)   canvas.rs:660-666
+// "Tame" triangles (all coefficients finite and < 1e30, so no product with a pixel coordinate can
+// overflow and every edge value is an exact-or-rounded integer) are sign-normalised: when f < 0
+// every coefficient of that edge is negated.  Negation commutes with round-to-nearest, so the
+// edge value e' is exactly -e, f' = -f > 0, the quotient e'/f' is bit-identical to e/f, and
+//   e/f >= 0  <=>  e' >= 0        e/f > 0  <=>  e' > 0
+// (|e'| >= 1 when non-zero, f' < 2^100: the quotient cannot underflow to zero).
+// Other triangles keep the literal coefficients and are evaluated with the reference's division
+// ("slow" mode, flag bit 3).
+struct TriEdges {
+    float ecx[3], ecy[3], ek1[3], ek2[3], f[3];
+    uint32_t flags; // bit e: f_e * f_e(-1,-1) > 0, the tie rule admits e == 0 (canvas.rs:678-680); bit 3: slow
+};
+constexpr uint32_t TRI_SLOW = 8u;
+
+__device__ __forceinline__ TriEdges prepare_edges(const RasterRec &r) {
+    const Edge e[3] = {make_edge(r.bx, r.by, r.cx, r.cy), make_edge(r.cx, r.cy, r.ax, r.ay),
+                       make_edge(r.ax, r.ay, r.bx, r.by)};
+    const float vx[3] = {r.ax, r.bx, r.cx}, vy[3] = {r.ay, r.by, r.cy};
+    TriEdges t;
+    t.flags = 0;
+    bool tame = true;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        t.f[i] = edge_eval(e[i], vx[i], vy[i]);
+        const float f_out = edge_eval(e[i], -1.0f, -1.0f);
+        if (FMUL(t.f[i], f_out) > 0.0f) t.flags |= 1u << i;
+        const float lim = 1e30f;
+        tame = tame && fabsf(e[i].cx) < lim && fabsf(e[i].cy) < lim && fabsf(e[i].k1) < lim &&
+               fabsf(e[i].k2) < lim && fabsf(t.f[i]) < lim;
+    }
+    if (!tame) t.flags |= TRI_SLOW;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const bool neg = tame && t.f[i] < 0.0f;
+        t.ecx[i] = neg ? -e[i].cx : e[i].cx;
+        t.ecy[i] = neg ? -e[i].cy : e[i].cy;
+        t.ek1[i] = neg ? -e[i].k1 : e[i].k1;
+        t.ek2[i] = neg ? -e[i].k2 : e[i].k2;
+        t.f[i] = neg ? -t.f[i] : t.f[i];
+    }
+    return t;
+}
+
+// Can any pixel of the rectangle [lx,hx] x [ly,hy] be covered?  Exact, not heuristic: each edge
+// value fl(fl(fl(cx*x + cy*y) + k1) - k2) is a monotone function of x and of y because every
+// rounding step is monotone, so its maximum over the rectangle sits at the corner selected by
+// the coefficient signs; if that corner fails an edge test, every pixel of the rectangle fails.
+__device__ __forceinline__ bool rect_may_cover(const TriEdges &t, int lx, int hx, int ly, int hy) {
+    if (t.flags & TRI_SLOW) return true;
+    bool any = true;
+#pragma unroll
+    for (int e = 0; e < 3; e++) {
+        const float xm = (float)(t.ecx[e] >= 0.0f ? hx : lx), ym = (float)(t.ecy[e] >= 0.0f ? hy : ly);
+        const float em = FSUB(FADD(FADD(FMUL(t.ecx[e], xm), FMUL(t.ecy[e], ym)), t.ek1[e]), t.ek2[e]);
+        any = any && (em > 0.0f || (em == 0.0f && (t.flags & (1u << e))));
+    }
+    return any;
+}
+
+} // namespace drawb200

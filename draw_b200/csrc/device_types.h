@@ -4,7 +4,12 @@
 
 namespace drawb200 {
 
-constexpr int TILE = 64;            // screen tile edge in pixels (one CTA per tile)
+// Two-level screen partition.  A CTA of k_tile owns one coarse tile (TILE_W x TILE_H pixels);
+// each of its 8 warps owns one fine tile (FINE x FINE pixels, 8 pixels per lane).  Triangles
+// whose bbox spans at most 2x2 fine tiles are binned into fine-tile lists (only the owning warp
+// looks at them); larger ones go to coarse-tile lists (all 8 warps look at them).
+constexpr int TILE_W = 64, TILE_H = 32, FINE = 16;
+constexpr int FINE_PER_TILE_X = TILE_W / FINE, FINE_PER_TILE_Y = TILE_H / FINE;
 constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
 
 // Per-frame constants, passed to every kernel by value (__grid_constant__): no upload, no sync.
@@ -16,8 +21,11 @@ struct FrameUniforms {
     float off_x, off_y; // canvas offset (canvas.rs:382-385)
     float depth_max;    // canvas.rs:403
     uint32_t canvas_w, canvas_h;
-    uint32_t tiles_x, tiles_y;      // whole canvas, in tiles
-    uint32_t tile_y_begin, tile_y_end; // stripe rendered by this launch (sort-first partition)
+    uint32_t tiles_x, tiles_y;         // whole canvas, in coarse tiles
+    uint32_t tile_y_begin, tile_y_end; // coarse tile rows rendered by this launch (sort-first stripe)
+    uint32_t n_coarse;                 // tiles_x * tiles_y ; list ids [0, n_coarse) are coarse tiles
+    uint32_t fine_nx;                  // tiles_x * FINE_PER_TILE_X ; list id of fine tile (gx,gy) = n_coarse + gy*fine_nx + gx
+    uint32_t n_lists;                  // n_coarse + fine tiles
 };
 
 // Texture (scene/mod.rs:206-216) with both TextureMaps flattened into the texel pool.
@@ -71,13 +79,15 @@ struct FrameDev {
     ShadeRec *srec;
     RasterRec *t_rrec;          // transparent records, slot = 4*ordinal + k, in draw order [4*n_transparent]
     ShadeRec *t_srec;
-    uint32_t *tile_count;       // per tile: count, then fill cursor [n_tiles]
-    uint32_t *tile_offset;      // exclusive scan [n_tiles + 1]
-    uint32_t *tile_refs;        // record slots grouped by tile [refs_cap]
+    uint32_t *list_count;       // per list (coarse tiles, then fine tiles): count, then fill cursor [n_lists]
+    uint32_t *list_offset;      // exclusive scan [n_lists + 1]
+    uint32_t *list_refs;        // record slots grouped by list [refs_cap]
     uint32_t *counters;         // [0] records  [1] refs  [2] overflow bits
     uint32_t rec_cap, refs_cap;
 };
 
 enum : uint32_t { OVERFLOW_RECORDS = 1u, OVERFLOW_REFS = 2u };
+
+constexpr int N_FRAME_KERNELS = 6; // k_vertex k_setup k_bin<count> k_scan k_bin<fill> k_tile
 
 } // namespace drawb200

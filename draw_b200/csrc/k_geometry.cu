@@ -1,0 +1,425 @@
+// k_geometry.cu — per-vertex and per-triangle stages of the frame (mororo18/draw scene/mod.rs:901).
+//
+//   k_vertex   per vertex   light / halfway / depth (scene/mod.rs:917-926), screen xy of the
+//                           unclipped vertex (:1047-1058), view-plane side flags (:634-660)
+//   k_setup    per triangle gather, back-face cull (:1016-1027), lateral reject + near/far clip
+//                           (:43-90, :662-746), snap + bbox + zero-area cull (canvas.rs:585-666),
+//                           record allocation by ballot / popc prefix sums, record write
+//
+// Arithmetic contract: see device_math.cuh.
+#include "device_math.cuh"
+
+namespace drawb200 {
+
+// ------------------------------------------------------------------------------------------
+// k_vertex
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FrameUniforms U, const SceneDev S,
+                                                const FrameDev W) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    // per-frame reset of the binning state (the binning kernels run after this one on the same stream)
+    for (uint32_t t = i; t < U.n_lists; t += gridDim.x * blockDim.x) W.list_count[t] = 0;
+    if (i < 3) W.counters[i] = 0;
+    if (i >= S.n_vertices) return;
+
+    const v3 p{S.px[i], S.py[i], S.pz[i]};
+    const v3 cam{U.cam[0], U.cam[1], U.cam[2]};
+    const v3 lsrc{U.light[0], U.light[1], U.light[2]};
+
+    // scene/mod.rs:920-925
+    const v3 eye_dir = v_sub(p, cam);
+    const v3 lvec = v_sub(p, lsrc);
+    const v3 light = v_div(lvec, v_norm(lvec));
+    const float eye_len = v_norm(eye_dir);
+    const v3 eye = v_div(eye_dir, eye_len);
+    const v3 hsum = v_add(light, eye);
+    const v3 halfway = v_div(hsum, v_norm(hsum));
+
+    W.v_lx[i] = light.x; W.v_ly[i] = light.y; W.v_lz[i] = light.z;
+    W.v_hx[i] = halfway.x; W.v_hy[i] = halfway.y; W.v_hz[i] = halfway.z;
+    W.v_depth[i] = eye_len;
+
+    // scene/mod.rs:1047-1058 for an unclipped corner: rows x, y, w of matrix_transf, then x/w, y/w
+    const float cx = mat_row(&U.m[0], p);
+    const float cy = mat_row(&U.m[4], p);
+    const float cw = mat_row(&U.m[12], p);
+    W.v_sx[i] = FDIV(cx, cw);
+    W.v_sy[i] = FDIV(cy, cw);
+
+    uint32_t flags = 0;
+#pragma unroll
+    for (int pl = 0; pl < 6; pl++) {
+        const float f = plane_eval(U.planes[pl], p);
+        flags |= (f > 0.0f ? 1u : 0u) << (2 * pl);
+        flags |= (f <= 0.0f ? 1u : 0u) << (2 * pl + 1);
+    }
+    W.v_flags[i] = flags;
+}
+
+// ------------------------------------------------------------------------------------------
+// triangle setup helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float min3_ref(float a, float b, float c) { // canvas.rs:618-627
+    float r = __int_as_float(0x7f800000);
+    if (a < r) r = a;
+    if (b < r) r = b;
+    if (c < r) r = c;
+    return r;
+}
+__device__ __forceinline__ float max3_ref(float a, float b, float c) { // canvas.rs:629-638
+    float r = __int_as_float(0xff800000);
+    if (a > r) r = a;
+    if (b > r) r = b;
+    if (c > r) r = c;
+    return r;
+}
+
+// Rectangle::clip of two [min,max] ranges (canvas.rs:332-350), one axis.
+__device__ __forceinline__ void clip_axis(unsigned long long a0, unsigned long long a1, unsigned long long b0,
+                                          unsigned long long b1, unsigned long long &o0, unsigned long long &o1) {
+    unsigned long long lo = a0 > b0 ? a0 : b0;
+    unsigned long long hi = a1 < b1 ? a1 : b1;
+    if (lo > hi) lo = hi = 0;
+    o0 = lo < hi ? lo : hi; // from_coords normalisation (canvas.rs:315-330)
+    o1 = lo < hi ? hi : lo;
+}
+
+// canvas.rs:585-666.  Builds the raster record of one screen triangle; returns false when the
+// triangle provably writes nothing: one of f_alpha/f_beta/f_gama is zero or NaN, so every
+// barycentric is +-inf or NaN, the interpolated depth is inf/NaN and `depth < stored` fails.
+__device__ __forceinline__ bool setup_raster(const FrameUniforms &U, const float sx[3], const float sy[3],
+                                             const float dep[3], uint32_t id, RasterRec &r) {
+    // Vec2 sub is add of the negation (linalg.rs:37-43), then pos_map_center (canvas.rs:896-904)
+    const float ax = floorf(FADD(FADD(sx[0], -U.off_x), 0.5f)), ay = floorf(FADD(FADD(sy[0], -U.off_y), 0.5f));
+    const float bx = floorf(FADD(FADD(sx[1], -U.off_x), 0.5f)), by = floorf(FADD(FADD(sy[1], -U.off_y), 0.5f));
+    const float cx = floorf(FADD(FADD(sx[2], -U.off_x), 0.5f)), cy = floorf(FADD(FADD(sy[2], -U.off_y), 0.5f));
+
+    const Edge e_bc = make_edge(bx, by, cx, cy), e_ca = make_edge(cx, cy, ax, ay), e_ab = make_edge(ax, ay, bx, by);
+    const float f_alpha = edge_eval(e_bc, ax, ay);
+    const float f_beta = edge_eval(e_ca, bx, by);
+    const float f_gama = edge_eval(e_ab, cx, cy);
+    const bool nonzero = (f_alpha < 0.0f || f_alpha > 0.0f) && (f_beta < 0.0f || f_beta > 0.0f) &&
+                         (f_gama < 0.0f || f_gama > 0.0f);
+    if (!nonzero) return false;
+
+    // canvas.rs:640-658
+    unsigned long long x0 = sat_usize(min3_ref(ax, bx, cx)), y0 = sat_usize(min3_ref(ay, by, cy));
+    unsigned long long x1 = sat_usize(max3_ref(ax, bx, cx)), y1 = sat_usize(max3_ref(ay, by, cy));
+    if (x0 > x1) { unsigned long long t = x0; x0 = x1; x1 = t; }
+    if (y0 > y1) { unsigned long long t = y0; y0 = y1; y1 = t; }
+    const unsigned long long sw = U.canvas_w - 1, sh = U.canvas_h - 1;
+    unsigned long long dx0, dx1, dy0, dy1;
+    clip_axis(x0, x1, 0, sw, dx0, dx1); // clip(drawable, screen)
+    clip_axis(y0, y1, 0, sh, dy0, dy1);
+    clip_axis(0, sw, dx0, dx1, x0, x1); // clip(screen, drawable)
+    clip_axis(0, sh, dy0, dy1, y0, y1);
+
+    r.ax = ax; r.ay = ay; r.bx = bx; r.by = by; r.cx = cx; r.cy = cy;
+    r.da = dep[0]; r.db = dep[1]; r.dc = dep[2];
+    r.id = id;
+    r.bbx = (uint32_t)x0 | ((uint32_t)x1 << 16);
+    r.bby = (uint32_t)y0 | ((uint32_t)y1 << 16);
+    return true;
+}
+
+// Does the bbox reach any coarse tile row of this launch's stripe?  (Records that do not are dropped.)
+__device__ __forceinline__ bool touches_stripe(const FrameUniforms &U, const RasterRec &r) {
+    const uint32_t ty0 = (r.bby & 0xFFFF) / TILE_H, ty1 = (r.bby >> 16) / TILE_H;
+    return ty1 >= U.tile_y_begin && ty0 < U.tile_y_end;
+}
+
+// ------------------------------------------------------------------------------------------
+// clip path (rare): world-space near/far clipping, scene/mod.rs:43-90 and :662-746
+// ------------------------------------------------------------------------------------------
+constexpr int NATTR = 12; // depth, normal3, light3, halfway3, uv2 (uv.z and screen_coord are dead)
+struct ClipVert {
+    float p[3];
+    float a[NATTR];
+};
+struct ClipTri {
+    ClipVert v[3];
+};
+
+__device__ __forceinline__ v3 cv_pos(const ClipVert &v) { return v3{v.p[0], v.p[1], v.p[2]}; }
+
+// a + (c - a) * t, component-wise, positions and attributes (scene/mod.rs:716-720, canvas.rs:242-291)
+__device__ __forceinline__ void cv_lerp(const ClipVert &a, const ClipVert &c, float t, ClipVert &o) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) o.p[i] = FADD(a.p[i], FMUL(FSUB(c.p[i], a.p[i]), t));
+#pragma unroll
+    for (int i = 0; i < NATTR; i++) o.a[i] = FADD(a.a[i], FMUL(FSUB(c.a[i], a.a[i]), t));
+}
+
+// ViewPlane::clip, scene/mod.rs:662-746
+__device__ __noinline__ int clip_plane(const float *pl, const ClipTri &tri, ClipTri *out) {
+    ClipVert a = tri.v[0], b = tri.v[1], c = tri.v[2];
+    float f_a = plane_eval(pl, cv_pos(a)), f_b = plane_eval(pl, cv_pos(b)), f_c = plane_eval(pl, cv_pos(c));
+    if (f_a > 0.0f && f_b > 0.0f && f_c > 0.0f) {
+        out[0] = tri;
+        return 1;
+    }
+    if (f_a <= 0.0f && f_b <= 0.0f && f_c <= 0.0f) return 0;
+    if (FMUL(f_a, f_c) >= 0.0f) { // (a,b,c) <- (c,a,b)  :691-700
+        ClipVert t = b; b = c; c = t;
+        float ft = f_b; f_b = f_c; f_c = ft;
+        t = a; a = b; b = t;
+        ft = f_a; f_a = f_b; f_b = ft;
+    } else if (FMUL(f_b, f_c) >= 0.0f) { // (a,b,c) <- (b,c,a)  :701-711
+        ClipVert t = a; a = c; c = t;
+        float ft = f_a; f_a = f_c; f_c = ft;
+        t = a; a = b; b = t;
+        ft = f_a; f_a = f_b; f_b = ft;
+    }
+    const v3 n{pl[0], pl[1], pl[2]};
+    const float eps = 0.0000001f; // linalg.rs:6
+    const float t_a = FSUB(FDIV(plane_eval(pl, cv_pos(a)), v_dot(n, v_sub(cv_pos(a), cv_pos(c)))), eps);
+    ClipVert na;
+    cv_lerp(a, c, t_a, na);
+    const float t_b = FSUB(FDIV(plane_eval(pl, cv_pos(b)), v_dot(n, v_sub(cv_pos(b), cv_pos(c)))), eps);
+    ClipVert nb;
+    cv_lerp(b, c, t_b, nb);
+    if (f_c <= 0.0f) { // :723-736
+        out[0].v[0] = a; out[0].v[1] = na; out[0].v[2] = nb;
+        out[1].v[0] = a; out[1].v[1] = b;  out[1].v[2] = nb;
+        return 2;
+    }
+    out[0].v[0] = c; out[0].v[1] = na; out[0].v[2] = nb; // :737-745
+    return 1;
+}
+
+__device__ __forceinline__ void shade_from_clip(const ClipTri &t, uint32_t material, ShadeRec &s) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            s.n[c][k] = t.v[c].a[1 + k];
+            s.l[c][k] = t.v[c].a[4 + k];
+            s.h[c][k] = t.v[c].a[7 + k];
+        }
+        s.uv[c][0] = t.v[c].a[10];
+        s.uv[c][1] = t.v[c].a[11];
+    }
+    s.material = material;
+    s.pad[0] = s.pad[1] = 0;
+}
+
+__device__ __forceinline__ void store_shade(ShadeRec *dst, const ShadeRec &s) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(&s);
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(ShadeRec) / 16); i++) d[i] = src[i];
+}
+
+// Gathers a vertex' clip-space inputs (scene/mod.rs:938-1008).
+__device__ __forceinline__ void gather_clip_vert(const SceneDev &S, const FrameDev &W, uint32_t v, uint32_t t,
+                                                 uint32_t n, ClipVert &o) {
+    o.p[0] = S.px[v]; o.p[1] = S.py[v]; o.p[2] = S.pz[v];
+    o.a[0] = W.v_depth[v];
+    o.a[1] = S.nx[n]; o.a[2] = S.ny[n]; o.a[3] = S.nz[n];
+    o.a[4] = W.v_lx[v]; o.a[5] = W.v_ly[v]; o.a[6] = W.v_lz[v];
+    o.a[7] = W.v_hx[v]; o.a[8] = W.v_hy[v]; o.a[9] = W.v_hz[v];
+    o.a[10] = S.tu[t]; o.a[11] = S.tv[t];
+}
+
+// The full clip path for one triangle that straddles the near or far plane: up to 4 outputs,
+// each projected (:1047-1063), set up, and written.  Opaque outputs take slots with a plain
+// atomic (this path is rare); transparent outputs go to their ordered slots 4*ordinal + k.
+__device__ __noinline__ void clip_and_emit(const FrameUniforms &U, const SceneDev &S, const FrameDev &W,
+                                           uint32_t tri, const uint32_t vi[3], uint32_t material, bool transparent,
+                                           uint32_t tslot) {
+    ClipTri in;
+#pragma unroll
+    for (int c = 0; c < 3; c++) gather_clip_vert(S, W, vi[c], S.idx[3 + c][tri], S.idx[6 + c][tri], in.v[c]);
+
+    ClipTri near_out[2], out[4];
+    const int n_near = clip_plane(U.planes[0], in, near_out);
+    int n_out = 0;
+    for (int i = 0; i < n_near; i++) n_out += clip_plane(U.planes[1], near_out[i], out + n_out);
+
+    for (int k = 0; k < 4; k++) {
+        RasterRec r;
+        bool keep = false;
+        if (k < n_out) {
+            float sx[3], sy[3], dep[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const v3 p = cv_pos(out[k].v[c]);
+                const float w = mat_row(&U.m[12], p);
+                sx[c] = FDIV(mat_row(&U.m[0], p), w);
+                sy[c] = FDIV(mat_row(&U.m[4], p), w);
+                dep[c] = out[k].v[c].a[0];
+            }
+            keep = setup_raster(U, sx, sy, dep, tri * 4u + (uint32_t)k, r);
+        }
+        if (transparent) {
+            RasterRec *dst = W.t_rrec + (size_t)tslot * 4 + k;
+            if (keep) {
+                ShadeRec s;
+                shade_from_clip(out[k], material, s);
+                store_raster(dst, r);
+                store_shade(W.t_srec + (size_t)tslot * 4 + k, s);
+            } else {
+                r.id = NO_SLOT;
+                r.bbx = r.bby = 0;
+                r.ax = r.ay = r.bx = r.by = r.cx = r.cy = r.da = r.db = r.dc = 0.0f;
+                store_raster(dst, r);
+            }
+        } else if (keep && touches_stripe(U, r)) {
+            const uint32_t slot = atomicAdd(&W.counters[0], 1u);
+            if (slot >= W.rec_cap) {
+                atomicOr(&W.counters[2], OVERFLOW_RECORDS);
+                continue;
+            }
+            ShadeRec s;
+            shade_from_clip(out[k], material, s);
+            store_raster(W.rrec + slot, r);
+            store_shade(W.srec + slot, s);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_setup
+// ------------------------------------------------------------------------------------------
+constexpr int SETUP_THREADS = 256;
+
+__global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__ FrameUniforms U, const SceneDev S,
+                                                         const FrameDev W) {
+    __shared__ uint32_t warp_tot[SETUP_THREADS / 32];
+    __shared__ uint32_t block_base;
+
+    const uint32_t tri = blockIdx.x * SETUP_THREADS + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    bool emit = false;        // this thread has one unclipped opaque record to place
+    bool transparent = false;
+    uint32_t tslot = 0, material = 0;
+    uint32_t vi[3] = {0, 0, 0};
+    RasterRec r;
+    r.id = NO_SLOT;
+
+    if (tri < S.n_triangles) {
+        vi[0] = S.idx[0][tri]; vi[1] = S.idx[1][tri]; vi[2] = S.idx[2][tri];
+        const uint32_t mat = S.tri_mat[tri];
+        material = mat & 0x7FFFFFFFu;
+        transparent = (mat >> 31) != 0;
+        if (transparent) tslot = S.tri_tslot[tri];
+
+        bool alive = true;
+        if (!transparent) {
+            // back-face cull, scene/mod.rs:1016-1027 with calc_normal :30-41 and get_center :92-99
+            const v3 a{S.px[vi[0]], S.py[vi[0]], S.pz[vi[0]]};
+            const v3 b{S.px[vi[1]], S.py[vi[1]], S.pz[vi[1]]};
+            const v3 c{S.px[vi[2]], S.py[vi[2]], S.pz[vi[2]]};
+            const v3 nrm = v_cross(v_sub(b, a), v_sub(c, b));
+            v3 sum{0.0f, 0.0f, 0.0f};
+            sum = v_add(sum, a);
+            sum = v_add(sum, b);
+            sum = v_add(sum, c);
+            const v3 center = v_div(sum, 3.0f);
+            const v3 eye = v_sub(v3{U.cam[0], U.cam[1], U.cam[2]}, center);
+            if (v_dot(eye, nrm) <= 0.0f) alive = false;
+        }
+        bool clip = false;
+        if (alive) {
+            const uint32_t fa = W.v_flags[vi[0]], fb = W.v_flags[vi[1]], fc = W.v_flags[vi[2]];
+            const uint32_t all_nonpos = fa & fb & fc & 0xAAAu; // bit 2p+1 : f <= 0 on all three
+            const uint32_t all_pos = fa & fb & fc & 0x555u;    // bit 2p   : f > 0 on all three
+            // lateral planes 2..5: reject only if completely outside one of them (:59-66, :641-660)
+            if (all_nonpos & 0xAA0u) alive = false;
+            else if ((all_pos & 0x5u) == 0x5u) clip = false;   // inside near and far: passes through (:677-681)
+            else if (all_nonpos & 0x2u) alive = false;          // completely behind the near plane (:682-686)
+            else if ((all_pos & 0x1u) && (all_nonpos & 0x8u)) alive = false; // untouched by near, beyond far
+            else clip = true;
+        }
+        if (alive && clip) {
+            clip_and_emit(U, S, W, tri, vi, material, transparent, tslot);
+            alive = false;
+            if (transparent) transparent = false; // its four ordered slots were written by clip_and_emit
+        } else if (alive) {
+            const float sx[3] = {W.v_sx[vi[0]], W.v_sx[vi[1]], W.v_sx[vi[2]]};
+            const float sy[3] = {W.v_sy[vi[0]], W.v_sy[vi[1]], W.v_sy[vi[2]]};
+            const float dep[3] = {W.v_depth[vi[0]], W.v_depth[vi[1]], W.v_depth[vi[2]]};
+            alive = setup_raster(U, sx, sy, dep, tri * 4u, r);
+            if (!alive) r.id = NO_SLOT;
+        }
+        emit = alive && !transparent && touches_stripe(U, r);
+        if (transparent) emit = false;
+        if (transparent && !alive) r.id = NO_SLOT;
+    }
+
+    // block-wide slot allocation: ballot + popc inside the warp, one atomic per block
+    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, emit);
+    const uint32_t warp_rank = __popc(ballot & ((1u << lane) - 1u));
+    if (lane == 0) warp_tot[warp] = __popc(ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (int w = 0; w < SETUP_THREADS / 32; w++) {
+            const uint32_t c = warp_tot[w];
+            warp_tot[w] = total;
+            total += c;
+        }
+        block_base = total ? atomicAdd(&W.counters[0], total) : 0u;
+    }
+    __syncthreads();
+
+    RasterRec *rdst = nullptr;
+    ShadeRec *sdst = nullptr;
+    if (emit) {
+        const uint32_t slot = block_base + warp_tot[warp] + warp_rank;
+        if (slot < W.rec_cap) {
+            rdst = W.rrec + slot;
+            sdst = W.srec + slot;
+        } else {
+            atomicOr(&W.counters[2], OVERFLOW_RECORDS);
+        }
+    } else if (transparent) {
+        // unclipped transparent triangle: ordered slot 4*ordinal, the other three are empty
+        RasterRec empty;
+        empty.id = NO_SLOT;
+        empty.bbx = empty.bby = 0;
+        empty.ax = empty.ay = empty.bx = empty.by = empty.cx = empty.cy = empty.da = empty.db = empty.dc = 0.0f;
+        for (int k = 1; k < 4; k++) store_raster(W.t_rrec + (size_t)tslot * 4 + k, empty);
+        rdst = W.t_rrec + (size_t)tslot * 4;
+        if (r.id == NO_SLOT) {
+            store_raster(rdst, empty);
+            rdst = nullptr;
+        } else {
+            sdst = W.t_srec + (size_t)tslot * 4;
+        }
+    }
+    if (rdst) {
+        store_raster(rdst, r);
+        // attribute gather for the shading record (scene/mod.rs:938-1008)
+        ShadeRec s;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const uint32_t v = vi[c], t = S.idx[3 + c][tri], n = S.idx[6 + c][tri];
+            s.n[c][0] = S.nx[n]; s.n[c][1] = S.ny[n]; s.n[c][2] = S.nz[n];
+            s.l[c][0] = W.v_lx[v]; s.l[c][1] = W.v_ly[v]; s.l[c][2] = W.v_lz[v];
+            s.h[c][0] = W.v_hx[v]; s.h[c][1] = W.v_hy[v]; s.h[c][2] = W.v_hz[v];
+            s.uv[c][0] = S.tu[t]; s.uv[c][1] = S.tv[t];
+        }
+        s.material = material;
+        s.pad[0] = s.pad[1] = 0;
+        store_shade(sdst, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+void launch_vertex(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, cudaStream_t stream) {
+    const uint32_t by_vertex = (S.n_vertices + 255) / 256, by_list = (U.n_lists + 255) / 256;
+    uint32_t blocks = by_vertex > 1 ? by_vertex : 1;
+    if (blocks < by_list && blocks < 148 * 4) blocks = by_list < 148 * 4 ? by_list : 148 * 4;
+    k_vertex<<<blocks, 256, 0, stream>>>(U, S, W);
+}
+
+void launch_setup(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, cudaStream_t stream) {
+    if (!S.n_triangles) return;
+    k_setup<<<(S.n_triangles + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, stream>>>(U, S, W);
+}
+
+} // namespace drawb200

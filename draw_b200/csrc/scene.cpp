@@ -22,8 +22,14 @@
 #include "host_math.hpp"
 
 namespace drawb200 {
-cudaError_t launch_frame(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, uint8_t *color, float *depth,
-                         cudaStream_t stream, uint64_t *launches);
+// k_geometry.cu / k_binning.cu / k_tile.cu
+void launch_vertex(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
+void launch_setup(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
+void launch_bin_count(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream);
+void launch_scan(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream);
+void launch_bin_fill(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream);
+void launch_tile(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, uint8_t *color, float *depth,
+                 cudaStream_t stream);
 cudaError_t launch_clear(uint8_t *color, float *depth, size_t n_pixels, float depth_max, cudaStream_t stream,
                          uint64_t *launches);
 cudaError_t launch_fill_u32(uint32_t *dst, size_t n, uint32_t value, cudaStream_t stream, uint64_t *launches);
@@ -135,7 +141,7 @@ struct draw_scene {
 
     // per-frame work buffers
     DevBuf<float> w_vert[9];
-    DevBuf<uint32_t> w_flags, w_tile_count, w_tile_offset, w_refs, w_counters;
+    DevBuf<uint32_t> w_flags, w_list_count, w_list_offset, w_refs, w_counters;
     DevBuf<RasterRec> w_rrec, w_trrec;
     DevBuf<ShadeRec> w_srec, w_tsrec;
     size_t rec_cap = 0, refs_cap = 0;
@@ -143,6 +149,10 @@ struct draw_scene {
     cudaStream_t last_stream = nullptr;
     cudaEvent_t last_done = nullptr;
     bool has_last = false;
+    // optional per-kernel timing (draw_scene_set_kernel_timing)
+    bool kernel_timing = false;
+    cudaEvent_t kev[N_FRAME_KERNELS + 1] = {};
+    bool kev_recorded = false;
 };
 
 struct draw_canvas {
@@ -274,7 +284,7 @@ int upload_geometry(draw_scene *s) {
     return DRAW_OK;
 }
 
-int ensure_work_buffers(draw_scene *s, size_t n_tiles) {
+int ensure_work_buffers(draw_scene *s, size_t n_lists) {
     const SceneDev &d = s->dev;
     for (int i = 0; i < 9; i++) TRY(s->w_vert[i].reserve(d.n_vertices));
     TRY(s->w_flags.reserve(d.n_vertices));
@@ -284,8 +294,8 @@ int ensure_work_buffers(draw_scene *s, size_t n_tiles) {
     TRY(s->w_srec.reserve(s->rec_cap));
     TRY(s->w_trrec.reserve(4 * (size_t)d.n_transparent));
     TRY(s->w_tsrec.reserve(4 * (size_t)d.n_transparent));
-    TRY(s->w_tile_count.reserve(n_tiles));
-    TRY(s->w_tile_offset.reserve(n_tiles + 1));
+    TRY(s->w_list_count.reserve(n_lists));
+    TRY(s->w_list_offset.reserve(n_lists + 1));
     TRY(s->w_refs.reserve(s->refs_cap));
     TRY(s->w_counters.reserve(4));
     FrameDev &w = s->work;
@@ -295,7 +305,7 @@ int ensure_work_buffers(draw_scene *s, size_t n_tiles) {
     w.v_flags = s->w_flags.ptr;
     w.rrec = s->w_rrec.ptr; w.srec = s->w_srec.ptr;
     w.t_rrec = s->w_trrec.ptr; w.t_srec = s->w_tsrec.ptr;
-    w.tile_count = s->w_tile_count.ptr; w.tile_offset = s->w_tile_offset.ptr; w.tile_refs = s->w_refs.ptr;
+    w.list_count = s->w_list_count.ptr; w.list_offset = s->w_list_offset.ptr; w.list_refs = s->w_refs.ptr;
     w.counters = s->w_counters.ptr;
     w.rec_cap = (uint32_t)s->rec_cap;
     w.refs_cap = (uint32_t)s->refs_cap;
@@ -350,8 +360,10 @@ int sort_transparent(draw_scene *s, cudaStream_t stream) {
 int enqueue_frame(draw_scene *s, draw_canvas *c) {
     TRY(ensure_device(s->device));
     if (s->geometry_dirty) TRY(upload_geometry(s));
-    const uint32_t tiles_x = (uint32_t)((c->width + TILE - 1) / TILE), tiles_y = (uint32_t)((c->height + TILE - 1) / TILE);
-    TRY(ensure_work_buffers(s, (size_t)tiles_x * tiles_y));
+    const uint32_t tiles_x = (uint32_t)((c->width + TILE_W - 1) / TILE_W), tiles_y = (uint32_t)((c->height + TILE_H - 1) / TILE_H);
+    const uint32_t n_coarse = tiles_x * tiles_y;
+    const uint32_t n_lists = n_coarse + n_coarse * FINE_PER_TILE_X * FINE_PER_TILE_Y;
+    TRY(ensure_work_buffers(s, n_lists));
 
     // serialise frames that share this scene's work buffers across different streams
     if (s->has_last && s->last_stream != c->stream) CU(cudaStreamWaitEvent(c->stream, s->last_done, 0));
@@ -374,13 +386,39 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     U.canvas_h = (uint32_t)c->height;
     U.tiles_x = tiles_x;
     U.tiles_y = tiles_y;
+    U.n_coarse = n_coarse;
+    U.fine_nx = tiles_x * FINE_PER_TILE_X;
+    U.n_lists = n_lists;
     const size_t y0 = c->stripe_y1 ? c->stripe_y0 : 0, y1 = c->stripe_y1 ? c->stripe_y1 : c->height;
-    U.tile_y_begin = (uint32_t)(y0 / TILE);
-    U.tile_y_end = (uint32_t)((y1 + TILE - 1) / TILE);
+    U.tile_y_begin = (uint32_t)(y0 / TILE_H);
+    U.tile_y_end = (uint32_t)((y1 + TILE_H - 1) / TILE_H);
 
     if (s->dev.n_transparent) TRY(sort_transparent(s, c->stream));
 
-    CU(launch_frame(U, s->dev, s->work, c->color(), c->depth(), c->stream, &s->launches));
+    cudaEvent_t *ev = nullptr;
+    if (s->kernel_timing) {
+        for (int i = 0; i <= N_FRAME_KERNELS; i++)
+            if (!s->kev[i]) CU(cudaEventCreate(&s->kev[i]));
+        ev = s->kev;
+        s->kev_recorded = true;
+    }
+    // the frame: six kernels back to back on the canvas' stream (optional events between them)
+    cudaStream_t st = c->stream;
+    if (ev) cudaEventRecord(ev[0], st);
+    launch_vertex(U, s->dev, s->work, st);
+    if (ev) cudaEventRecord(ev[1], st);
+    launch_setup(U, s->dev, s->work, st);
+    if (ev) cudaEventRecord(ev[2], st);
+    launch_bin_count(U, s->work, st);
+    if (ev) cudaEventRecord(ev[3], st);
+    launch_scan(U, s->work, st);
+    if (ev) cudaEventRecord(ev[4], st);
+    launch_bin_fill(U, s->work, st);
+    if (ev) cudaEventRecord(ev[5], st);
+    launch_tile(U, s->dev, s->work, c->color(), c->depth(), st);
+    if (ev) cudaEventRecord(ev[6], st);
+    s->launches += 4 + (s->dev.n_triangles ? 1 : 0) + (U.tile_y_end > U.tile_y_begin ? 1 : 0);
+    CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_status, s->work.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     if (!s->last_done) CU(cudaEventCreateWithFlags(&s->last_done, cudaEventDisableTiming));
     CU(cudaEventRecord(s->last_done, c->stream));
@@ -469,7 +507,7 @@ int draw_set_device(int device) {
     return DRAW_OK;
 }
 
-int draw_tile_size(void) { return TILE; }
+int draw_tile_size(void) { return TILE_H; }
 
 // ---- Scene ---------------------------------------------------------------------------------
 
@@ -509,6 +547,8 @@ void draw_scene_destroy(draw_scene *scene) {
         if (cur != scene->device) cudaSetDevice(scene->device);
         cudaDeviceSynchronize();
         if (scene->last_done) cudaEventDestroy(scene->last_done);
+        for (int i = 0; i <= N_FRAME_KERNELS; i++)
+            if (scene->kev[i]) cudaEventDestroy(scene->kev[i]);
     }
     delete scene;
 }
@@ -703,6 +743,23 @@ int draw_scene_launch_count(const draw_scene *scene, uint64_t *out) {
     if (!scene || !out) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
     *out = scene->launches;
     return DRAW_OK;
+}
+
+int draw_scene_set_kernel_timing(draw_scene *scene, int enabled) {
+    if (!scene) return fail(DRAW_ERR_INVALID_ARGUMENT, "scene is NULL");
+    scene->kernel_timing = enabled != 0;
+    if (!enabled) scene->kev_recorded = false;
+    return DRAW_OK;
+}
+
+int draw_scene_last_kernel_times(draw_scene *scene, draw_canvas *canvas, float ms[6]) {
+    GUARD_BEGIN
+    if (!scene || !canvas || !ms) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!scene->kev_recorded) return fail(DRAW_ERR_INVALID_ARGUMENT, "kernel timing was not enabled for the last frame");
+    TRY(finish_frame(canvas));
+    for (int i = 0; i < N_FRAME_KERNELS; i++) CU(cudaEventElapsedTime(&ms[i], scene->kev[i], scene->kev[i + 1]));
+    return DRAW_OK;
+    GUARD_END
 }
 
 // ---- Canvas --------------------------------------------------------------------------------
@@ -913,8 +970,8 @@ int draw_canvas_set_stream(draw_canvas *canvas, void *cuda_stream) {
 int draw_canvas_set_stripe(draw_canvas *canvas, size_t y0, size_t y1) {
     if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas is NULL");
     if (y0 >= y1 || y1 > canvas->height) return fail(DRAW_ERR_INVALID_ARGUMENT, "stripe must satisfy y0 < y1 <= height");
-    if (y0 % TILE || (y1 % TILE && y1 != canvas->height))
-        return fail(DRAW_ERR_INVALID_ARGUMENT, "stripe bounds must be multiples of the tile size %d (or the canvas height)", TILE);
+    if (y0 % TILE_H || (y1 % TILE_H && y1 != canvas->height))
+        return fail(DRAW_ERR_INVALID_ARGUMENT, "stripe bounds must be multiples of the tile height %d (or the canvas height)", TILE_H);
     if (y0 == 0 && y1 == canvas->height) canvas->stripe_y0 = canvas->stripe_y1 = 0;
     else {
         canvas->stripe_y0 = y0;

@@ -141,6 +141,12 @@ int draw_scene_counts(const draw_scene *scene, size_t *n_objects, size_t *n_tria
 /* Kernels launched by this scene so far (bench.py reports the delta over the timed region). */
 int draw_scene_launch_count(const draw_scene *scene, uint64_t *out);
 
+/* Measurement tap: when enabled, every frame records CUDA events between its kernels on the
+ * canvas' stream; last_kernel_times waits for the frame and returns the device time in ms of
+ * k_vertex, k_setup, k_bin<count>, k_scan, k_bin<fill>, k_tile (DESIGN.md describes them). */
+int draw_scene_set_kernel_timing(draw_scene *scene, int enabled);
+int draw_scene_last_kernel_times(draw_scene *scene, draw_canvas *canvas, float ms[6]);
+
 /* ---- Canvas (canvas.rs) -------------------------------------------------------------- */
 /* Canvas::new(width, height) :366 — colour BGRA8 (Pixel, :51-59), black; no depth yet. */
 int draw_canvas_create(size_t width, size_t height, draw_canvas **out);
@@ -173,7 +179,7 @@ int draw_canvas_bind_external(draw_canvas *canvas, void *color_dev, void *depth_
 int draw_canvas_set_stream(draw_canvas *canvas, void *cuda_stream);
 /* Sort-first partition: render only canvas rows y in [y0, y1) (canvas y = depth-buffer row;
  * colour row = height-1-y).  Rows outside are left untouched.  (0, height) = whole frame.
- * y0 and y1 must be multiples of the tile height (draw_tile_size) or equal to height. */
+ * y0 and y1 must be multiples of the tile height (draw_tile_size, 32) or equal to height. */
 int draw_canvas_set_stripe(draw_canvas *canvas, size_t y0, size_t y1);
 int draw_tile_size(void);
 

@@ -37,7 +37,7 @@ def test_version_and_error_string():
     L = _native.lib()
     assert L.draw_version() == 100
     assert isinstance(L.draw_last_error(), bytes)
-    assert L.draw_tile_size() == 64
+    assert L.draw_tile_size() == 32
 
 
 def test_no_cpu_fallback_without_a_gpu():

@@ -22,7 +22,7 @@ def _both(objs, W, H, **kw):
 def test_library_loaded_and_device_present():
     import draw_b200
     assert draw_b200.device_count() >= 1
-    assert draw_b200.tile_size() == 64
+    assert draw_b200.tile_size() == 32
 
 
 def test_uniforms_match_oracle():
