@@ -74,6 +74,8 @@ SIGNATURES = {
     "draw_scene_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "draw_scene_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "draw_scene_last_kernel_times": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),
+    "draw_scene_debug_list_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "draw_scene_debug_tile_cycles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "draw_canvas_create": (C.c_int, [C.c_size_t, C.c_size_t, C.POINTER(C.c_void_p)]),
     "draw_canvas_destroy": (None, [C.c_void_p]),
     "draw_canvas_init_depth": (C.c_int, [C.c_void_p, C.c_float]),

@@ -245,7 +245,7 @@ class Scene:
         N.check(N.lib().draw_scene_read_vertex_visual(self._h, canvas._h, first, count, out.ctypes.data))
         return out
 
-    KERNELS = ("k_vertex", "k_setup", "k_bin_count", "k_scan", "k_bin_fill", "k_tile")
+    KERNELS = ("k_vertex", "k_setup", "k_bin_count", "k_alloc", "k_bin_fill", "k_tile")
 
     def set_kernel_timing(self, enabled):
         N.check(N.lib().draw_scene_set_kernel_timing(self._h, 1 if enabled else 0))
@@ -255,6 +255,26 @@ class Scene:
         ms = (C.c_float * 6)()
         N.check(N.lib().draw_scene_last_kernel_times(self._h, canvas._h, ms))
         return dict(zip(self.KERNELS, (float(x) for x in ms)))
+
+    def debug_list_counts(self, canvas):
+        """(large list sizes, small list sizes) per tile of the last frame, as uint32 arrays."""
+        nc = C.c_size_t()
+        N.check(N.lib().draw_scene_debug_list_counts(self._h, canvas._h, None, 0, C.byref(nc)))
+        n = nc.value * 2
+        out = np.empty(n, np.uint32)
+        N.check(N.lib().draw_scene_debug_list_counts(self._h, canvas._h, out.ctypes.data, n, C.byref(nc)))
+        return out[:nc.value], out[nc.value:]
+
+    def debug_tile_cycles(self, canvas=None, enable=True):
+        """Toggle per-tile cycle recording; with a canvas, return the last frame's cycles per coarse tile."""
+        if canvas is None:
+            N.check(N.lib().draw_scene_debug_tile_cycles(self._h, None, 1 if enable else 0, None, 0))
+            return None
+        nc = C.c_size_t()
+        N.check(N.lib().draw_scene_debug_list_counts(self._h, canvas._h, None, 0, C.byref(nc)))
+        out = np.empty(nc.value, np.uint32)
+        N.check(N.lib().draw_scene_debug_tile_cycles(self._h, canvas._h, 1 if enable else 0, out.ctypes.data, nc.value))
+        return out
 
     def counts(self):
         a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()

@@ -4,12 +4,12 @@
 
 namespace drawb200 {
 
-// Two-level screen partition.  A CTA of k_tile owns one coarse tile (TILE_W x TILE_H pixels);
-// each of its 8 warps owns one fine tile (FINE x FINE pixels, 8 pixels per lane).  Triangles
-// whose bbox spans at most 2x2 fine tiles are binned into fine-tile lists (only the owning warp
-// looks at them); larger ones go to coarse-tile lists (all 8 warps look at them).
-constexpr int TILE_W = 64, TILE_H = 32, FINE = 16;
-constexpr int FINE_PER_TILE_X = TILE_W / FINE, FINE_PER_TILE_Y = TILE_H / FINE;
+// Screen partition.  A CTA of k_tile owns one tile of TILE_W x TILE_H pixels and keeps its depth /
+// winner / colour on chip.  Each tile has two lists of raster records: "large" (list id = tile) and
+// "small" (list id = n_coarse + tile; bbox of at most SMALL_AREA pixels).  REGION is the square each
+// warp owns during the large-record phase (8 pixels per lane).
+constexpr int TILE_W = 64, TILE_H = 32, REGION = 16;
+constexpr int SMALL_AREA = 64;
 constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
 
 // Per-frame constants, passed to every kernel by value (__grid_constant__): no upload, no sync.
@@ -23,9 +23,8 @@ struct FrameUniforms {
     uint32_t canvas_w, canvas_h;
     uint32_t tiles_x, tiles_y;         // whole canvas, in coarse tiles
     uint32_t tile_y_begin, tile_y_end; // coarse tile rows rendered by this launch (sort-first stripe)
-    uint32_t n_coarse;                 // tiles_x * tiles_y ; list ids [0, n_coarse) are coarse tiles
-    uint32_t fine_nx;                  // tiles_x * FINE_PER_TILE_X ; list id of fine tile (gx,gy) = n_coarse + gy*fine_nx + gx
-    uint32_t n_lists;                  // n_coarse + fine tiles
+    uint32_t n_coarse;                 // tiles_x * tiles_y
+    uint32_t n_lists;                  // 2 * n_coarse: large lists, then small lists
 };
 
 // Texture (scene/mod.rs:206-216) with both TextureMaps flattened into the texel pool.
@@ -79,15 +78,17 @@ struct FrameDev {
     ShadeRec *srec;
     RasterRec *t_rrec;          // transparent records, slot = 4*ordinal + k, in draw order [4*n_transparent]
     ShadeRec *t_srec;
-    uint32_t *list_count;       // per list (coarse tiles, then fine tiles): count, then fill cursor [n_lists]
-    uint32_t *list_offset;      // exclusive scan [n_lists + 1]
+    uint32_t *list_count;       // per list (large lists, then small lists): count, then fill cursor [n_lists]
+    uint32_t *list_offset;      // first entry of each list in list_refs [n_lists + 1]
     uint32_t *list_refs;        // record slots grouped by list [refs_cap]
-    uint32_t *counters;         // [0] records  [1] refs  [2] overflow bits
+    uint32_t *counters;         // [0] records  [1] refs  [2] overflow bits  [3] k_setup CTA ticket
+    unsigned long long *scan_desc; // k_setup chained-scan descriptors [ceil(n_triangles / 256)]
     uint32_t rec_cap, refs_cap;
+    uint32_t *tile_cycles;      // debug: SM cycles spent by each coarse tile's CTA (null = off) [n_coarse]
 };
 
 enum : uint32_t { OVERFLOW_RECORDS = 1u, OVERFLOW_REFS = 2u };
 
-constexpr int N_FRAME_KERNELS = 6; // k_vertex k_setup k_bin<count> k_scan k_bin<fill> k_tile
+constexpr int N_FRAME_KERNELS = 6; // k_vertex k_setup k_bin<count> k_alloc k_bin<fill> k_tile
 
 } // namespace drawb200

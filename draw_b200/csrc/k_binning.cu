@@ -4,16 +4,16 @@
 // it exists so that k_tile can keep a tile's colour and depth on chip and write HBM once.
 //
 //   k_bin<false>  per record  count the lists it belongs to
-//   k_scan        one CTA     exclusive scan of the counts -> list offsets
+//   k_alloc       per list    reserve a contiguous range of list_refs for every list
 //   k_bin<true>   per record  scatter its slot into those lists
 //
-// Two list classes (device_types.h): a record whose bbox spans at most 2x2 fine tiles (16x16 px)
-// goes to fine-tile lists, read by one warp of k_tile each; any larger record goes to the lists
-// of the coarse tiles (64x32 px) it overlaps, read by all 8 warps of that tile's CTA.  A tile is
-// only referenced if the triangle can actually cover a pixel in it (exact corner test,
-// rect_may_cover), not merely because its bbox touches it.  Records covering many coarse tiles
-// are binned by the whole warp (ballot picks them, lanes stride over the tiles).
-// Order inside a list is irrelevant: k_tile resolves fragments by (depth, draw id).
+// Every tile (64x32 px) has two lists (device_types.h): "large" records are rasterised by k_tile
+// with every lane testing its own pixels, "small" records (bbox <= SMALL_AREA px) one record per
+// lane.  A tile is only referenced if the triangle can actually cover a pixel in it (exact corner
+// test, rect_may_cover), not merely because its bbox touches it.  Records covering many tiles are
+// binned by the whole warp (ballot picks them, lanes stride over the tiles).
+// Order inside a list is irrelevant: k_tile resolves fragments by (depth, record slot), and slots
+// are allocated in draw order.
 #include "device_math.cuh"
 
 namespace drawb200 {
@@ -42,36 +42,26 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const __grid_constant__ Fra
         else { r.bbx = r.bby = 0; r.ax = r.ay = r.bx = r.by = r.cx = r.cy = 0.0f; }
         const int x0 = (int)(r.bbx & 0xFFFF), x1 = (int)(r.bbx >> 16);
         const int y0 = (int)(r.bby & 0xFFFF), y1 = (int)(r.bby >> 16);
-        const int gx0 = x0 / FINE, gx1 = x1 / FINE, gy0 = y0 / FINE, gy1 = y1 / FINE;
-        const bool small = (gx1 - gx0 <= 1) && (gy1 - gy0 <= 1);
+        // small: bbox of at most SMALL_AREA pixels -> the tile's "small" list (one lane of k_tile walks it);
+        // anything else -> the tile's "large" list (all lanes of k_tile test their own pixels against it)
+        const bool small = (x1 - x0 + 1) * (y1 - y0 + 1) <= SMALL_AREA;
         const int tx0 = x0 / TILE_W, tx1 = x1 / TILE_W;
         int ty0 = y0 / TILE_H, ty1 = y1 / TILE_H;
         if (ty0 < (int)U.tile_y_begin) ty0 = (int)U.tile_y_begin;
         if (ty1 > (int)U.tile_y_end - 1) ty1 = (int)U.tile_y_end - 1;
         const int n_coarse_hit = ty0 <= ty1 ? (tx1 - tx0 + 1) * (ty1 - ty0 + 1) : 0;
-        const bool wide = valid && !small && n_coarse_hit > WIDE_TILES;
+        const bool wide = valid && n_coarse_hit > WIDE_TILES;
 
         if (valid && !wide) {
             const TriEdges t = prepare_edges(r);
-            if (small) {
-                for (int gy = gy0; gy <= gy1; gy++) {
-                    const int trow = gy / FINE_PER_TILE_Y;
-                    if (trow < (int)U.tile_y_begin || trow >= (int)U.tile_y_end) continue;
-                    for (int gx = gx0; gx <= gx1; gx++) {
-                        const int lx = max(x0, gx * FINE), hx = min(x1, gx * FINE + FINE - 1);
-                        const int ly = max(y0, gy * FINE), hy = min(y1, gy * FINE + FINE - 1);
-                        if (rect_may_cover(t, lx, hx, ly, hy))
-                            bin_hit<FILL>(W, U.n_coarse + (uint32_t)gy * U.fine_nx + (uint32_t)gx, slot);
-                    }
+            const uint32_t list_base = small ? U.n_coarse : 0u;
+            for (int ty = ty0; ty <= ty1; ty++)
+                for (int tx = tx0; tx <= tx1; tx++) {
+                    const int lx = max(x0, tx * TILE_W), hx = min(x1, tx * TILE_W + TILE_W - 1);
+                    const int ly = max(y0, ty * TILE_H), hy = min(y1, ty * TILE_H + TILE_H - 1);
+                    if (rect_may_cover(t, lx, hx, ly, hy))
+                        bin_hit<FILL>(W, list_base + (uint32_t)ty * U.tiles_x + (uint32_t)tx, slot);
                 }
-            } else {
-                for (int ty = ty0; ty <= ty1; ty++)
-                    for (int tx = tx0; tx <= tx1; tx++) {
-                        const int lx = max(x0, tx * TILE_W), hx = min(x1, tx * TILE_W + TILE_W - 1);
-                        const int ly = max(y0, ty * TILE_H), hy = min(y1, ty * TILE_H + TILE_H - 1);
-                        if (rect_may_cover(t, lx, hx, ly, hy)) bin_hit<FILL>(W, (uint32_t)ty * U.tiles_x + (uint32_t)tx, slot);
-                    }
-            }
         }
 
         // wide records: one at a time, all 32 lanes stride over its coarse tiles
@@ -101,21 +91,21 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const __grid_constant__ Fra
 }
 
 // ------------------------------------------------------------------------------------------
-// k_scan : exclusive scan of list_count -> list_offset, cursors reset, total -> counters[1]
+// k_alloc : gives every list a contiguous range of list_refs.  Lists need not be laid out in
+// list order, so instead of a global scan each CTA scans its 256 counts locally and reserves its
+// total with one atomicAdd; list_count is reset to serve as the fill cursor (after k_bin<true> it
+// holds the count again, which is what k_tile reads).  total -> counters[1].
 // ------------------------------------------------------------------------------------------
-constexpr int SCAN_THREADS = 1024;
+constexpr int ALLOC_THREADS = 256;
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan(const FrameDev W, const uint32_t n_lists) {
-    __shared__ uint32_t warp_sum[SCAN_THREADS / 32];
+__global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const FrameDev W, const uint32_t n_lists) {
+    __shared__ uint32_t warp_sum[ALLOC_THREADS / 32];
+    __shared__ uint32_t block_base;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t per = (n_lists + SCAN_THREADS - 1) / SCAN_THREADS;
-    const uint32_t begin = tid * per < n_lists ? tid * per : n_lists;
-    const uint32_t end = begin + per < n_lists ? begin + per : n_lists;
+    const uint32_t i = blockIdx.x * ALLOC_THREADS + tid;
+    const uint32_t c = i < n_lists ? W.list_count[i] : 0u;
 
-    uint32_t local = 0;
-    for (uint32_t i = begin; i < end; i++) local += W.list_count[i];
-
-    uint32_t incl = local;
+    uint32_t incl = c;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
@@ -123,28 +113,21 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(const FrameDev W, const u
     }
     if (lane == 31) warp_sum[warp] = incl;
     __syncthreads();
-    if (warp == 0) {
-        const uint32_t w = warp_sum[lane];
-        uint32_t wi = w;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, wi, d);
-            if (lane >= (uint32_t)d) wi += up;
+    if (tid == 0) {
+        uint32_t total = 0;
+        for (int w = 0; w < ALLOC_THREADS / 32; w++) {
+            const uint32_t t = warp_sum[w];
+            warp_sum[w] = total;
+            total += t;
         }
-        warp_sum[lane] = wi - w; // exclusive
+        const uint32_t base = total ? atomicAdd(&W.counters[1], total) : 0u;
+        if (total && base + total > W.refs_cap) atomicOr(&W.counters[2], OVERFLOW_REFS);
+        block_base = base;
     }
     __syncthreads();
-    uint32_t run = warp_sum[warp] + incl - local;
-    for (uint32_t i = begin; i < end; i++) {
-        const uint32_t c = W.list_count[i];
-        W.list_offset[i] = run;
+    if (i < n_lists) {
+        W.list_offset[i] = block_base + warp_sum[warp] + incl - c;
         W.list_count[i] = 0; // becomes the fill cursor
-        run += c;
-    }
-    if (tid == SCAN_THREADS - 1) {
-        W.list_offset[n_lists] = run;
-        W.counters[1] = run;
-        if (run > W.refs_cap) atomicOr(&W.counters[2], OVERFLOW_REFS);
     }
 }
 
@@ -160,8 +143,8 @@ static int bin_blocks(const FrameDev &W) {
 void launch_bin_count(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream) {
     k_bin<false><<<bin_blocks(W), BIN_THREADS, 0, stream>>>(U, W);
 }
-void launch_scan(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream) {
-    k_scan<<<1, SCAN_THREADS, 0, stream>>>(W, U.n_lists);
+void launch_alloc(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream) {
+    k_alloc<<<(U.n_lists + ALLOC_THREADS - 1) / ALLOC_THREADS, ALLOC_THREADS, 0, stream>>>(W, U.n_lists);
 }
 void launch_bin_fill(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream) {
     k_bin<true><<<bin_blocks(W), BIN_THREADS, 0, stream>>>(U, W);

@@ -4,7 +4,8 @@
 //                           unclipped vertex (:1047-1058), view-plane side flags (:634-660)
 //   k_setup    per triangle gather, back-face cull (:1016-1027), lateral reject + near/far clip
 //                           (:43-90, :662-746), snap + bbox + zero-area cull (canvas.rs:585-666),
-//                           record allocation by ballot / popc prefix sums, record write
+//                           draw-order-preserving record allocation (warp prefix sums + chained
+//                           scan across CTAs), record write
 //
 // Arithmetic contract: see device_math.cuh.
 #include "device_math.cuh"
@@ -19,7 +20,9 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FrameUni
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     // per-frame reset of the binning state (the binning kernels run after this one on the same stream)
     for (uint32_t t = i; t < U.n_lists; t += gridDim.x * blockDim.x) W.list_count[t] = 0;
-    if (i < 3) W.counters[i] = 0;
+    if (i < 4) W.counters[i] = 0;
+    const uint32_t n_desc = (S.n_triangles + 255) / 256;
+    for (uint32_t t = i; t < n_desc; t += gridDim.x * blockDim.x) W.scan_desc[t] = 0ull;
     if (i >= S.n_vertices) return;
 
     const v3 p{S.px[i], S.py[i], S.pz[i]};
@@ -221,12 +224,13 @@ __device__ __forceinline__ void gather_clip_vert(const SceneDev &S, const FrameD
     o.a[10] = S.tu[t]; o.a[11] = S.tv[t];
 }
 
-// The full clip path for one triangle that straddles the near or far plane: up to 4 outputs,
-// each projected (:1047-1063), set up, and written.  Opaque outputs take slots with a plain
-// atomic (this path is rare); transparent outputs go to their ordered slots 4*ordinal + k.
-__device__ __noinline__ void clip_and_emit(const FrameUniforms &U, const SceneDev &S, const FrameDev &W,
-                                           uint32_t tri, const uint32_t vi[3], uint32_t material, bool transparent,
-                                           uint32_t tslot) {
+// The full clip path for one triangle that straddles the near or far plane: up to 4 outputs, each
+// projected (:1047-1063) and set up.  Transparent outputs are written straight to their ordered
+// slots 4*ordinal + k (empty slots are marked).  Opaque outputs that survive are returned
+// compacted in out_r / out_s (in emission order) for the caller to place once its slots are known.
+__device__ __noinline__ int clip_triangle(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, uint32_t tri,
+                                          const uint32_t vi[3], uint32_t material, bool transparent, uint32_t tslot,
+                                          RasterRec *out_r, ShadeRec *out_s) {
     ClipTri in;
 #pragma unroll
     for (int c = 0; c < 3; c++) gather_clip_vert(S, W, vi[c], S.idx[3 + c][tri], S.idx[6 + c][tri], in.v[c]);
@@ -236,6 +240,7 @@ __device__ __noinline__ void clip_and_emit(const FrameUniforms &U, const SceneDe
     int n_out = 0;
     for (int i = 0; i < n_near; i++) n_out += clip_plane(U.planes[1], near_out[i], out + n_out);
 
+    int n_keep = 0;
     for (int k = 0; k < 4; k++) {
         RasterRec r;
         bool keep = false;
@@ -265,17 +270,12 @@ __device__ __noinline__ void clip_and_emit(const FrameUniforms &U, const SceneDe
                 store_raster(dst, r);
             }
         } else if (keep && touches_stripe(U, r)) {
-            const uint32_t slot = atomicAdd(&W.counters[0], 1u);
-            if (slot >= W.rec_cap) {
-                atomicOr(&W.counters[2], OVERFLOW_RECORDS);
-                continue;
-            }
-            ShadeRec s;
-            shade_from_clip(out[k], material, s);
-            store_raster(W.rrec + slot, r);
-            store_shade(W.srec + slot, s);
+            out_r[n_keep] = r;
+            shade_from_clip(out[k], material, out_s[n_keep]);
+            n_keep++;
         }
     }
+    return n_keep;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -283,20 +283,35 @@ __device__ __noinline__ void clip_and_emit(const FrameUniforms &U, const SceneDe
 // ------------------------------------------------------------------------------------------
 constexpr int SETUP_THREADS = 256;
 
+// Descriptor of the chained scan over CTAs: status in the top 2 bits, count in the rest.
+#define DESC_AGGREGATE (1ull << 62)
+#define DESC_PREFIX (2ull << 62)
+#define DESC_VALUE ((1ull << 62) - 1)
+
+// Record slots are handed out in draw order (stable compaction): slot order == draw order, which is
+// what lets k_tile break depth ties by comparing slots.  Inside a CTA: ballot/popc-style prefix sums
+// over the per-thread output counts (0..4).  Across CTAs: single-pass chained scan with decoupled
+// look-back; CTAs take a ticket so that the chain follows launch order and cannot deadlock.
 __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__ FrameUniforms U, const SceneDev S,
                                                          const FrameDev W) {
     __shared__ uint32_t warp_tot[SETUP_THREADS / 32];
-    __shared__ uint32_t block_base;
+    __shared__ uint32_t s_ticket, s_base;
 
-    const uint32_t tri = blockIdx.x * SETUP_THREADS + threadIdx.x;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&W.counters[3], 1u);
+    __syncthreads();
+    const uint32_t bid = s_ticket;
+    const uint32_t tri = bid * SETUP_THREADS + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    bool emit = false;        // this thread has one unclipped opaque record to place
-    bool transparent = false;
+    uint32_t n_out = 0;       // opaque records this thread places (0..4)
+    bool clipped = false;     // they come from the clip path (held in clip_r / clip_s)
+    bool transparent = false; // unclipped transparent triangle: writes its own ordered slots
     uint32_t tslot = 0, material = 0;
     uint32_t vi[3] = {0, 0, 0};
     RasterRec r;
     r.id = NO_SLOT;
+    RasterRec clip_r[4];
+    ShadeRec clip_s[4];
 
     if (tri < S.n_triangles) {
         vi[0] = S.idx[0][tri]; vi[1] = S.idx[1][tri]; vi[2] = S.idx[2][tri];
@@ -333,9 +348,10 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
             else clip = true;
         }
         if (alive && clip) {
-            clip_and_emit(U, S, W, tri, vi, material, transparent, tslot);
+            n_out = (uint32_t)clip_triangle(U, S, W, tri, vi, material, transparent, tslot, clip_r, clip_s);
+            clipped = true;
             alive = false;
-            if (transparent) transparent = false; // its four ordered slots were written by clip_and_emit
+            transparent = false; // a clipped transparent triangle wrote its four ordered slots already
         } else if (alive) {
             const float sx[3] = {W.v_sx[vi[0]], W.v_sx[vi[1]], W.v_sx[vi[2]]};
             const float sy[3] = {W.v_sy[vi[0]], W.v_sy[vi[1]], W.v_sy[vi[2]]};
@@ -343,37 +359,81 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
             alive = setup_raster(U, sx, sy, dep, tri * 4u, r);
             if (!alive) r.id = NO_SLOT;
         }
-        emit = alive && !transparent && touches_stripe(U, r);
-        if (transparent) emit = false;
-        if (transparent && !alive) r.id = NO_SLOT;
+        if (!clipped) n_out = (alive && !transparent && touches_stripe(U, r)) ? 1u : 0u;
     }
 
-    // block-wide slot allocation: ballot + popc inside the warp, one atomic per block
-    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, emit);
-    const uint32_t warp_rank = __popc(ballot & ((1u << lane) - 1u));
-    if (lane == 0) warp_tot[warp] = __popc(ballot);
+    // ---- CTA-wide exclusive prefix of n_out -------------------------------------------------
+    uint32_t incl = n_out;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= (uint32_t)d) incl += up;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t total = 0;
-        for (int w = 0; w < SETUP_THREADS / 32; w++) {
-            const uint32_t c = warp_tot[w];
-            warp_tot[w] = total;
-            total += c;
+    // ---- chained scan across CTAs (warp 0) ----------------------------------------------------
+    if (warp == 0) {
+        uint32_t wt = lane < SETUP_THREADS / 32 ? warp_tot[lane] : 0u;
+        uint32_t wi = wt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+            if (lane >= (uint32_t)d) wi += up;
         }
-        block_base = total ? atomicAdd(&W.counters[0], total) : 0u;
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, wi, 31);
+        if (lane < SETUP_THREADS / 32) warp_tot[lane] = wi - wt; // exclusive offset of each warp
+        volatile unsigned long long *desc = reinterpret_cast<volatile unsigned long long *>(W.scan_desc);
+        uint32_t base = 0;
+        if (bid == 0) {
+            if (lane == 0) desc[0] = DESC_PREFIX | total;
+        } else {
+            if (lane == 0) desc[bid] = DESC_AGGREGATE | total;
+            // look back 32 predecessors at a time until one of them has its inclusive prefix
+            int look = (int)bid - 1;
+            while (true) {
+                const int j = look - (int)lane;
+                unsigned long long d = j >= 0 ? desc[j] : DESC_PREFIX;
+                // wait until every descriptor in the window up to the first PREFIX is published
+                const uint32_t is_prefix = __ballot_sync(0xFFFFFFFFu, (d >> 62) == 2);
+                const uint32_t not_ready = __ballot_sync(0xFFFFFFFFu, (d >> 62) == 0);
+                const int first_prefix = is_prefix ? __ffs(is_prefix) - 1 : 32;
+                const uint32_t window = first_prefix >= 31 ? 0xFFFFFFFFu : ((2u << first_prefix) - 1u);
+                if (not_ready & window) continue; // spin
+                uint32_t v = (lane <= (uint32_t)first_prefix && j >= 0) ? (uint32_t)(d & DESC_VALUE) : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+                base += v;
+                if (first_prefix < 32) break;
+                look -= 32;
+            }
+            if (lane == 0) desc[bid] = DESC_PREFIX | (unsigned long long)(base + total);
+        }
+        if (lane == 0) {
+            s_base = base;
+            if (bid == gridDim.x - 1) W.counters[0] = base + total; // total record count of the frame
+        }
     }
     __syncthreads();
+
+    const uint32_t slot0 = s_base + warp_tot[warp] + incl - n_out;
+    if (n_out && slot0 + n_out > W.rec_cap) {
+        atomicOr(&W.counters[2], OVERFLOW_RECORDS);
+        n_out = 0;
+        clipped = true; // nothing to write
+    }
+    if (clipped) {
+        for (uint32_t k = 0; k < n_out; k++) {
+            store_raster(W.rrec + slot0 + k, clip_r[k]);
+            store_shade(W.srec + slot0 + k, clip_s[k]);
+        }
+        return;
+    }
 
     RasterRec *rdst = nullptr;
     ShadeRec *sdst = nullptr;
-    if (emit) {
-        const uint32_t slot = block_base + warp_tot[warp] + warp_rank;
-        if (slot < W.rec_cap) {
-            rdst = W.rrec + slot;
-            sdst = W.srec + slot;
-        } else {
-            atomicOr(&W.counters[2], OVERFLOW_RECORDS);
-        }
+    if (n_out) {
+        rdst = W.rrec + slot0;
+        sdst = W.srec + slot0;
     } else if (transparent) {
         // unclipped transparent triangle: ordered slot 4*ordinal, the other three are empty
         RasterRec empty;

@@ -1,284 +1,316 @@
 // k_tile.cu — per-tile raster / depth / shade kernel (mororo18/draw canvas.rs:577-750, 906-960).
 //
-// One CTA per coarse tile (64x32 px), 8 warps; warp w owns the fine tile (w & 3, w >> 2) of 16x16
-// px and lane l owns the 4x2 pixel block at (4 * (l & 3), 2 * (l >> 2)) inside it.  Depth and the
-// winning record of every pixel live in registers for the whole kernel; colour and depth are
-// written to HBM exactly once at the end (clear fused in).  No atomics and no tensor cores.
+// One CTA (256 threads) per 64x32-pixel tile.  The tile's depth, winning record and colour stay on
+// chip (registers, then shared memory) for the whole kernel; colour and depth go to HBM exactly
+// once at the end, with the clear fused in.  No tensor cores: nothing here is a contraction.
 //
-//   phase 1a  coarse-tile list   staged through shared memory 64 triangles at a time, all warps
-//   phase 1b  fine-tile list     each warp stages and consumes its own list, 32 at a time
-//   shading   deferred: only the winning triangle of a pixel is shaded (canvas.rs:685-743)
-//   phase 2   transparent triangles, in draw order, blended over the shaded colour
-//   write     colour rows y-flipped (canvas.rs:955-956), depth rows not (canvas.rs:413-423)
+//   phase A  "large" list: triangles are staged through shared memory 64 at a time; every lane owns
+//            a 4x2 pixel block (warp = 16x16 region) and tests it against each triangle, after a
+//            warp-level bbox reject and an exact block-level edge reject.  Depth/winner in registers.
+//   merge    each lane publishes its 8 pixels as 64-bit keys (depth, slot) in shared memory.
+//   phase B  "small" list (bbox <= 64 px): one triangle per lane; the lane walks the bbox and
+//            commits covered fragments with a shared-memory atomicMin on the key.
+//   phase C  deferred shading, one pixel per lane per step: only the winner of a pixel is shaded
+//            (canvas.rs:685-743); the key becomes (exact depth, draw id), colour goes to smem.
+//   phase D  transparent triangles in draw order, blended over the shaded colour (rare).
+//   phase E  write-back, 128 B per warp store: colour rows y-flipped (canvas.rs:955-956), depth
+//            rows not (canvas.rs:413-423).
 //
 // Draw-order semantics without ordered lists: the reference draws triangles sequentially with a
-// strict `<` depth test, so for opaque triangles the surviving fragment of a pixel is the
-// minimum of (depth, draw id) — ties go to the earlier triangle.  Lists are therefore consumed
-// in any order and depth ties are broken by draw id.  Transparent triangles (depth test on,
-// depth write off, blend with the current colour, scene/mod.rs:1088) are only visible over the
-// final opaque winner W of their pixel if drawn after it: fragment T is blended iff
-// id(T) > id(W) and depth(T) < depth(W), in draw order.
+// strict `<` depth test (canvas.rs:923), so for opaque triangles the surviving fragment of a pixel
+// is the minimum of (depth, draw order) — ties go to the earlier triangle.  Record slots are
+// allocated in draw order by k_setup, so the key (depth, slot) ordered as an unsigned 64-bit
+// integer is exactly that minimum, and lists can be consumed in any order by any lane.
+// Transparent triangles (depth test on, depth write off, blend with the current colour,
+// scene/mod.rs:1088) are only visible over the final opaque winner W of their pixel if drawn after
+// it: fragment T is blended iff id(T) > id(W) and depth(T) < depth(W), in draw order.
 #include "shading.cuh"
 
 namespace drawb200 {
 
 constexpr int TILE_THREADS = 256;
-constexpr int TILE_WARPS = TILE_THREADS / 32;
-constexpr int CHUNK = 64;  // coarse-list triangles staged per round (whole CTA)
-constexpr int FCHUNK = 32; // fine-list triangles staged per round (per warp)
-constexpr int PX = 8;      // pixels per lane: 4 wide x 2 tall
+constexpr int CHUNK = 64; // large-list triangles staged per round
+constexpr int PX = 8;     // pixels per lane in phase A: 4 wide x 2 tall
+constexpr int TILE_PIXELS = TILE_W * TILE_H;
 
-// One triangle prepared for the pixel loop (25 words; stride 25 is conflict-free for staging writes,
-// and every read in the pixel loop is a broadcast).
+// One triangle prepared for the phase-A pixel loop (25 words; stride 25 is conflict-free for the
+// staging writes, and every read in the pixel loop is a broadcast).  The bbox is kept as floats
+// (exact: < 65536) so the loop does no int->float conversions (those run on the slow XU pipe).
 struct StagedTri {
     float ecx[3], ecy[3], ek1[3], ek2[3], f[3];
     float da, db, dc;
-    int x0, x1, y0, y1;
+    float x0, x1, y0, y1;
     uint32_t flags, id, slot;
 };
 
-__device__ __forceinline__ void stage_triangle(StagedTri &s, const RasterRec &r, uint32_t slot) {
+__device__ __forceinline__ void stage_triangle(StagedTri *dst, const RasterRec *src, uint32_t slot) {
+    RasterRec r = load_raster(src);
+    if (r.id == NO_SLOT) { // empty transparent slot: an empty bbox makes every lane skip it
+        r.bbx = 1u;        // x_min = 1 > x_max = 0
+        r.bby = 1u;
+    }
     const TriEdges t = prepare_edges(r);
+    StagedTri &s = *dst;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         s.ecx[i] = t.ecx[i]; s.ecy[i] = t.ecy[i]; s.ek1[i] = t.ek1[i]; s.ek2[i] = t.ek2[i]; s.f[i] = t.f[i];
     }
     s.da = r.da; s.db = r.db; s.dc = r.dc;
-    s.x0 = (int)(r.bbx & 0xFFFF); s.x1 = (int)(r.bbx >> 16);
-    s.y0 = (int)(r.bby & 0xFFFF); s.y1 = (int)(r.bby >> 16);
+    s.x0 = (float)(r.bbx & 0xFFFF); s.x1 = (float)(r.bbx >> 16);
+    s.y0 = (float)(r.bby & 0xFFFF); s.y1 = (float)(r.bby >> 16);
     s.flags = t.flags;
     s.id = r.id;
     s.slot = slot;
 }
 
-// Literal coverage + depth of one pixel (canvas.rs:673-682) with the reference's divisions.  Used
-// for non-tame triangles and for the transparent phase.  Staged coefficients may be
-// sign-normalised; the quotients e/f are unchanged by that.
-__device__ __noinline__ bool cover_literal(const StagedTri &s, float x, float y, float &depth) {
-    float bary[3];
+// Coverage + depth of one pixel (canvas.rs:673-682).  Tame triangles: sign tests on the
+// sign-normalised edge values, divisions only for covered pixels.  Others: the reference's literal
+// divide-then-compare.  The quotients e/f are the same either way.
+__device__ __forceinline__ bool cover_pixel(const float (&ecx)[3], const float (&ecy)[3], const float (&ek1)[3],
+                                            const float (&ek2)[3], const float (&f)[3], uint32_t flags, float da,
+                                            float db, float dc, float x, float y, float &depth) {
+    float e[3];
 #pragma unroll
-    for (int i = 0; i < 3; i++) {
-        const float e = FSUB(FADD(FADD(FMUL(s.ecx[i], x), FMUL(s.ecy[i], y)), s.ek1[i]), s.ek2[i]);
-        bary[i] = FDIV(e, s.f[i]);
+    for (int i = 0; i < 3; i++) e[i] = FSUB(FADD(FADD(FMUL(ecx[i], x), FMUL(ecy[i], y)), ek1[i]), ek2[i]);
+    float bary[3];
+    if (!(flags & TRI_SLOW)) {
+        const bool in = (e[0] > 0.0f || (e[0] == 0.0f && (flags & 1u))) && (e[1] > 0.0f || (e[1] == 0.0f && (flags & 2u))) &&
+                        (e[2] > 0.0f || (e[2] == 0.0f && (flags & 4u)));
+        if (!in) return false;
+#pragma unroll
+        for (int i = 0; i < 3; i++) bary[i] = FDIV(e[i], f[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; i++) bary[i] = FDIV(e[i], f[i]);
+        if (!(bary[0] >= 0.0f && bary[1] >= 0.0f && bary[2] >= 0.0f)) return false;
+        if (!((bary[0] > 0.0f || (flags & 1u)) && (bary[1] > 0.0f || (flags & 2u)) && (bary[2] > 0.0f || (flags & 4u))))
+            return false;
     }
-    if (!(bary[0] >= 0.0f && bary[1] >= 0.0f && bary[2] >= 0.0f)) return false;
-    if (!((bary[0] > 0.0f || (s.flags & 1u)) && (bary[1] > 0.0f || (s.flags & 2u)) && (bary[2] > 0.0f || (s.flags & 4u))))
-        return false;
-    depth = FADD(FADD(FMUL(bary[0], s.da), FMUL(bary[1], s.db)), FMUL(bary[2], s.dc));
+    depth = FADD(FADD(FMUL(bary[0], da), FMUL(bary[1], db)), FMUL(bary[2], dc)); // canvas.rs:682
     return true;
 }
 
-// Depth test with the draw-order tie rule.
-__device__ __forceinline__ void depth_update(float d, uint32_t id, uint32_t slot, float &zb, uint32_t &sl,
-                                             const RasterRec *__restrict__ rrec) {
-    if (d < zb) {
-        zb = d;
-        sl = slot;
-    } else if (d == zb && sl != NO_SLOT) {
-        if (id < __ldg(&rrec[sl].id)) { // equal depth: the earlier draw wins (strict `<`, canvas.rs:923)
-            zb = d;
-            sl = slot;
-        }
-    }
+// Order-preserving map float -> uint32 (-0 is folded onto +0: the reference's `<` treats them as
+// equal, so the earlier draw must win between them).
+__device__ __forceinline__ uint32_t depth_key(float d) {
+    const uint32_t b = __float_as_uint(FADD(d, 0.0f));
+    return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
 }
-
-// Rasterises staged triangle s against this lane's 4x2 block at (bx0, by0) inside the warp's fine
-// tile at (fx0, fy0).
-__device__ __forceinline__ void raster_triangle(const StagedTri &s, int fx0, int fy0, int bx0, int by0,
-                                                float (&zb)[PX], uint32_t (&sl)[PX],
-                                                const RasterRec *__restrict__ rrec) {
-    if (s.x1 < fx0 || s.x0 > fx0 + FINE - 1 || s.y1 < fy0 || s.y0 > fy0 + FINE - 1) return; // warp-uniform
-    const int lo_x = max(s.x0, bx0), hi_x = min(s.x1, bx0 + 3);
-    const int lo_y = max(s.y0, by0), hi_y = min(s.y1, by0 + 1);
-    if (lo_x > hi_x || lo_y > hi_y) return;
-    const uint32_t flags = s.flags, id = s.id, slot = s.slot;
-    if (!(flags & TRI_SLOW)) {
-        // block-level reject at the best corner of the clipped block (exact, see rect_may_cover)
-        bool any = true;
-#pragma unroll
-        for (int e = 0; e < 3; e++) {
-            const float cx = s.ecx[e], cy = s.ecy[e];
-            const float xm = (float)(cx >= 0.0f ? hi_x : lo_x), ym = (float)(cy >= 0.0f ? hi_y : lo_y);
-            const float em = FSUB(FADD(FADD(FMUL(cx, xm), FMUL(cy, ym)), s.ek1[e]), s.ek2[e]);
-            any = any && (em > 0.0f || (em == 0.0f && (flags & (1u << e))));
-        }
-        if (!any) return;
-        float pxs[3][4], pys[3][2];
-#pragma unroll
-        for (int e = 0; e < 3; e++) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) pxs[e][i] = FMUL(s.ecx[e], (float)(bx0 + i));
-#pragma unroll
-            for (int j = 0; j < 2; j++) pys[e][j] = FMUL(s.ecy[e], (float)(by0 + j));
-        }
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int x = bx0 + i, y = by0 + j;
-                if (x < lo_x || x > hi_x || y < lo_y || y > hi_y) continue;
-                // f > 0 after sign normalisation: alpha >= 0 <=> e >= 0, alpha > 0 <=> e > 0
-                const float e0 = FSUB(FADD(FADD(pxs[0][i], pys[0][j]), s.ek1[0]), s.ek2[0]);
-                const float e1 = FSUB(FADD(FADD(pxs[1][i], pys[1][j]), s.ek1[1]), s.ek2[1]);
-                const float e2 = FSUB(FADD(FADD(pxs[2][i], pys[2][j]), s.ek1[2]), s.ek2[2]);
-                const bool in = (e0 > 0.0f || (e0 == 0.0f && (flags & 1u))) &&
-                                (e1 > 0.0f || (e1 == 0.0f && (flags & 2u))) &&
-                                (e2 > 0.0f || (e2 == 0.0f && (flags & 4u)));
-                if (!in) continue;
-                const float alpha = FDIV(e0, s.f[0]), beta = FDIV(e1, s.f[1]), gama = FDIV(e2, s.f[2]);
-                const float d = FADD(FADD(FMUL(alpha, s.da), FMUL(beta, s.db)), FMUL(gama, s.dc)); // canvas.rs:682
-                depth_update(d, id, slot, zb[j * 4 + i], sl[j * 4 + i], rrec);
-            }
-        }
-    } else {
-#pragma unroll
-        for (int p = 0; p < PX; p++) {
-            const int x = bx0 + (p & 3), y = by0 + (p >> 2);
-            if (x < lo_x || x > hi_x || y < lo_y || y > hi_y) continue;
-            float d;
-            if (!cover_literal(s, (float)x, (float)y, d)) continue;
-            depth_update(d, id, slot, zb[p], sl[p], rrec);
-        }
-    }
+__device__ __forceinline__ unsigned long long make_key(float d, uint32_t slot) {
+    return ((unsigned long long)depth_key(d) << 32) | slot;
 }
 
 __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ FrameUniforms U, const SceneDev S,
                                                        const FrameDev W, uint8_t *__restrict__ color,
                                                        float *__restrict__ depth) {
-    __shared__ StagedTri st_coarse[CHUNK];
-    __shared__ StagedTri st_fine[TILE_WARPS][FCHUNK];
+    __shared__ unsigned long long keys[TILE_PIXELS]; // (depth key, slot), later (depth bits, draw id)
+    __shared__ uint32_t colour[TILE_PIXELS];         // r | g << 8 | b << 16 | pad << 24
+    __shared__ StagedTri staged[CHUNK];
 
     const uint32_t tile_x = blockIdx.x % U.tiles_x;
     const uint32_t tile_y = U.tile_y_begin + blockIdx.x / U.tiles_x;
     const uint32_t tile = tile_y * U.tiles_x + tile_x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    // warp -> fine tile, lane -> 4x2 block (canvas coordinates: x right, y = depth-buffer row)
-    const int gx = (int)tile_x * FINE_PER_TILE_X + (warp & 3), gy = (int)tile_y * FINE_PER_TILE_Y + (warp >> 2);
-    const int fx0 = gx * FINE, fy0 = gy * FINE;
-    const int bx0 = fx0 + (lane & 3) * 4, by0 = fy0 + (lane >> 2) * 2;
-
-    float zb[PX];
-    uint32_t sl[PX];
-#pragma unroll
-    for (int i = 0; i < PX; i++) {
-        zb[i] = U.depth_max;
-        sl[i] = NO_SLOT;
-    }
+    const long long t_start = W.tile_cycles ? clock64() : 0;
+    const int tx0 = (int)tile_x * TILE_W, ty0 = (int)tile_y * TILE_H;
 
     const bool usable = W.counters[2] == 0;
+    const uint32_t l_begin = usable ? W.list_offset[tile] : 0u;
+    const uint32_t l_count = usable ? W.list_count[tile] : 0u; // the fill cursor ends at the count
+    const uint32_t s_begin = usable ? W.list_offset[U.n_coarse + tile] : 0u;
+    const uint32_t s_count = usable ? W.list_count[U.n_coarse + tile] : 0u;
+    const RasterRec *__restrict__ rrec = W.rrec;
+    const float depth_max = U.depth_max;
 
-    // ---- phase 1a: the coarse tile's list, all warps --------------------------------------------
+    // ---- phase A: large triangles, every lane tests its own 4x2 block ------------------------------
     {
-        const uint32_t begin = usable ? W.list_offset[tile] : 0u, end = usable ? W.list_offset[tile + 1] : 0u;
-        for (uint32_t base = begin; base < end; base += CHUNK) {
-            const int n = (int)min((uint32_t)CHUNK, end - base);
+        // warp -> 16x16 region, lane -> 4x2 block (canvas coordinates: x right, y = depth-buffer row)
+        const int rx0 = tx0 + (warp & 3) * REGION, ry0 = ty0 + (warp >> 2) * REGION;
+        const int bx0 = rx0 + (lane & 3) * 4, by0 = ry0 + (lane >> 2) * 2;
+        const float fx0 = (float)rx0, fy0 = (float)ry0, fx1 = fx0 + (float)(REGION - 1), fy1 = fy0 + (float)(REGION - 1);
+        float xf[4], yf[2];
+#pragma unroll
+        for (int i = 0; i < 4; i++) xf[i] = (float)(bx0 + i);
+#pragma unroll
+        for (int j = 0; j < 2; j++) yf[j] = (float)(by0 + j);
+        float zb[PX];
+        uint32_t sl[PX];
+#pragma unroll
+        for (int i = 0; i < PX; i++) {
+            zb[i] = depth_max;
+            sl[i] = NO_SLOT;
+        }
+#pragma unroll 1
+        for (uint32_t base = 0; base < l_count; base += CHUNK) {
+            const uint32_t n = min((uint32_t)CHUNK, l_count - base);
             __syncthreads();
-            if (tid < n) {
-                const uint32_t slot = W.list_refs[base + tid];
-                stage_triangle(st_coarse[tid], load_raster(W.rrec + slot), slot);
+            if ((uint32_t)tid < n) {
+                const uint32_t slot = W.list_refs[l_begin + base + tid];
+                stage_triangle(staged + tid, rrec + slot, slot);
             }
             __syncthreads();
-            for (int k = 0; k < n; k++) raster_triangle(st_coarse[k], fx0, fy0, bx0, by0, zb, sl, W.rrec);
-        }
-    }
-    // ---- phase 1b: this warp's fine-tile list ---------------------------------------------------
-    {
-        const uint32_t list = U.n_coarse + (uint32_t)gy * U.fine_nx + (uint32_t)gx;
-        const uint32_t begin = usable ? W.list_offset[list] : 0u, end = usable ? W.list_offset[list + 1] : 0u;
-        StagedTri *mine = st_fine[warp];
-        for (uint32_t base = begin; base < end; base += FCHUNK) {
-            const int n = (int)min((uint32_t)FCHUNK, end - base);
-            __syncwarp();
-            if (lane < n) {
-                const uint32_t slot = W.list_refs[base + lane];
-                stage_triangle(mine[lane], load_raster(W.rrec + slot), slot);
-            }
-            __syncwarp();
-            for (int k = 0; k < n; k++) raster_triangle(mine[k], fx0, fy0, bx0, by0, zb, sl, W.rrec);
-        }
-    }
-
-    // ---- deferred shading of the opaque winners, fused clear ------------------------------------
-    // colour as r | g << 8 | b << 16 | pad << 24 ; clear = azul_bb (155,186,255), pad 255 (canvas.rs:131)
-    uint32_t col[PX];
-    uint32_t wid[PX]; // draw id of the opaque winner (for the transparent phase), NO_SLOT = none
+#pragma unroll 1
+            for (uint32_t k = 0; k < n; k++) {
+                const StagedTri &s = staged[k];
+                if (s.x1 < fx0 || s.x0 > fx1 || s.y1 < fy0 || s.y0 > fy1) continue; // warp-uniform
+                const float lo_x = fmaxf(s.x0, xf[0]), hi_x = fminf(s.x1, xf[3]);
+                const float lo_y = fmaxf(s.y0, yf[0]), hi_y = fminf(s.y1, yf[1]);
+                if (lo_x > hi_x || lo_y > hi_y) continue;
+                const uint32_t flags = s.flags, slot = s.slot;
+                if (!(flags & TRI_SLOW)) {
+                    // block-level reject at the best corner of the clipped block (exact, see rect_may_cover)
+                    bool any = true;
 #pragma unroll
-    for (int p = 0; p < PX; p++) {
-        col[p] = 155u | (186u << 8) | (255u << 16) | (255u << 24);
-        wid[p] = NO_SLOT;
-        if (sl[p] != NO_SLOT) {
-            const RasterRec r = load_raster(W.rrec + sl[p]);
-            float d, op;
-            const uint32_t rgb = shade_pixel(S, r, W.srec + sl[p], (float)(bx0 + (p & 3)), (float)(by0 + (p >> 2)), &d, &op);
-            col[p] = rgb | (255u << 24);
-            wid[p] = r.id;
-        }
-    }
-
-    // ---- phase 2: transparent triangles in draw order (scene/mod.rs:1088-1246) ------------------
-    const uint32_t n_tslots = usable ? S.n_transparent * 4u : 0u;
-    for (uint32_t base = 0; base < n_tslots; base += CHUNK) {
-        const int n = (int)min((uint32_t)CHUNK, n_tslots - base);
-        __syncthreads();
-        if (tid < n) {
-            RasterRec r = load_raster(W.t_rrec + base + tid);
-            if (r.id == NO_SLOT) { // empty slot: an empty bbox makes every lane skip it
-                r.bbx = 1u;        // x_min = 1 > x_max = 0
-                r.bby = 1u;
-            }
-            stage_triangle(st_coarse[tid], r, base + tid);
-        }
-        __syncthreads();
-        for (int k = 0; k < n; k++) {
-            const StagedTri &s = st_coarse[k];
-            if (s.x1 < fx0 || s.x0 > fx0 + FINE - 1 || s.y1 < fy0 || s.y0 > fy0 + FINE - 1) continue;
-            const int lo_x = max(s.x0, bx0), hi_x = min(s.x1, bx0 + 3);
-            const int lo_y = max(s.y0, by0), hi_y = min(s.y1, by0 + 1);
-            if (lo_x > hi_x || lo_y > hi_y) continue;
+                    for (int e = 0; e < 3; e++) {
+                        const float cx = s.ecx[e], cy = s.ecy[e];
+                        const float xm = cx >= 0.0f ? hi_x : lo_x, ym = cy >= 0.0f ? hi_y : lo_y;
+                        const float em = FSUB(FADD(FADD(FMUL(cx, xm), FMUL(cy, ym)), s.ek1[e]), s.ek2[e]);
+                        any = any && (em > 0.0f || (em == 0.0f && (flags & (1u << e))));
+                    }
+                    if (!any) continue;
+                    float pxs[3][4], pys[3][2];
 #pragma unroll
-            for (int p = 0; p < PX; p++) {
-                const int x = bx0 + (p & 3), y = by0 + (p >> 2);
-                if (x < lo_x || x > hi_x || y < lo_y || y > hi_y) continue;
-                float d;
-                if (!cover_literal(s, (float)x, (float)y, d)) continue;
-                if (!(wid[p] == NO_SLOT || s.id > wid[p])) continue; // drawn before the opaque winner: overwritten
-                if (!(d < zb[p])) continue;                          // canvas.rs:923, depth write is off
-                const RasterRec r = load_raster(W.t_rrec + s.slot);
-                float d2, op;
-                const uint32_t rgb = shade_pixel(S, r, W.t_srec + s.slot, (float)x, (float)y, &d2, &op);
-                // canvas.rs:916-921: opacity < 1 blends with the stored colour, else replaces it
-                col[p] = op < 1.0f ? blend_rgb(col[p], rgb, op) : (rgb | (255u << 24));
-            }
-        }
-    }
-
-    // ---- single write-back ------------------------------------------------------------------------
-    const int W_ = (int)U.canvas_w, H_ = (int)U.canvas_h;
-    const bool vec_ok = (W_ & 3) == 0;
+                    for (int e = 0; e < 3; e++) {
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
-        const int y = by0 + j;
-        if (y >= H_ || bx0 >= W_) continue;
-        uint32_t px[4];
+                        for (int i = 0; i < 4; i++) pxs[e][i] = FMUL(s.ecx[e], xf[i]);
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const uint32_t c = col[j * 4 + i]; // r g b pad -> memory order b g r pad
-            px[i] = ((c >> 16) & 255u) | (c & 0x0000FF00u) | ((c & 255u) << 16) | (c & 0xFF000000u);
-        }
-        const size_t crow = (size_t)(H_ - 1 - y) * W_ + bx0, drow = (size_t)y * W_ + bx0;
-        if (vec_ok) {
-            *reinterpret_cast<uint4 *>(color + crow * 4) = make_uint4(px[0], px[1], px[2], px[3]);
-            *reinterpret_cast<float4 *>(depth + drow) = make_float4(zb[j * 4], zb[j * 4 + 1], zb[j * 4 + 2], zb[j * 4 + 3]);
-        } else {
+                        for (int j = 0; j < 2; j++) pys[e][j] = FMUL(s.ecy[e], yf[j]);
+                    }
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                if (bx0 + i < W_) {
-                    reinterpret_cast<uint32_t *>(color)[crow + i] = px[i];
-                    depth[drow + i] = zb[j * 4 + i];
+                    for (int j = 0; j < 2; j++) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            if (xf[i] < lo_x || xf[i] > hi_x || yf[j] < lo_y || yf[j] > hi_y) continue;
+                            // f > 0 after sign normalisation: alpha >= 0 <=> e >= 0, alpha > 0 <=> e > 0
+                            const float e0 = FSUB(FADD(FADD(pxs[0][i], pys[0][j]), s.ek1[0]), s.ek2[0]);
+                            const float e1 = FSUB(FADD(FADD(pxs[1][i], pys[1][j]), s.ek1[1]), s.ek2[1]);
+                            const float e2 = FSUB(FADD(FADD(pxs[2][i], pys[2][j]), s.ek1[2]), s.ek2[2]);
+                            const bool in = (e0 > 0.0f || (e0 == 0.0f && (flags & 1u))) &&
+                                            (e1 > 0.0f || (e1 == 0.0f && (flags & 2u))) &&
+                                            (e2 > 0.0f || (e2 == 0.0f && (flags & 4u)));
+                            if (!in) continue;
+                            const float alpha = FDIV(e0, s.f[0]), beta = FDIV(e1, s.f[1]), gama = FDIV(e2, s.f[2]);
+                            const float d = FADD(FADD(FMUL(alpha, s.da), FMUL(beta, s.db)), FMUL(gama, s.dc)); // canvas.rs:682
+                            const int p = j * 4 + i;
+                            // strict `<` (canvas.rs:923); on equal depth the earlier draw (smaller slot) stays
+                            if (d < zb[p] || (d == zb[p] && slot < sl[p] && sl[p] != NO_SLOT)) {
+                                zb[p] = d;
+                                sl[p] = slot;
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int p = 0; p < PX; p++) {
+                        const float x = xf[p & 3], y = yf[p >> 2];
+                        if (x < lo_x || x > hi_x || y < lo_y || y > hi_y) continue;
+                        float d;
+                        if (!cover_pixel(s.ecx, s.ecy, s.ek1, s.ek2, s.f, flags, s.da, s.db, s.dc, x, y, d)) continue;
+                        if (d < zb[p] || (d == zb[p] && slot < sl[p] && sl[p] != NO_SLOT)) {
+                            zb[p] = d;
+                            sl[p] = slot;
+                        }
+                    }
                 }
             }
         }
+        // ---- merge: publish the block as keys --------------------------------------------------------
+#pragma unroll
+        for (int p = 0; p < PX; p++) {
+            const int lxp = bx0 - tx0 + (p & 3), lyp = by0 - ty0 + (p >> 2);
+            keys[lyp * TILE_W + lxp] = sl[p] != NO_SLOT ? make_key(zb[p], sl[p]) : make_key(depth_max, NO_SLOT);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: small triangles, one per lane, atomicMin on the key ---------------------------
+    for (uint32_t i = (uint32_t)tid; i < s_count; i += TILE_THREADS) {
+        const uint32_t slot = W.list_refs[s_begin + i];
+        const RasterRec r = load_raster(rrec + slot);
+        const TriEdges t = prepare_edges(r);
+        const int lx = max((int)(r.bbx & 0xFFFF), tx0), hx = min((int)(r.bbx >> 16), tx0 + TILE_W - 1);
+        const int ly = max((int)(r.bby & 0xFFFF), ty0), hy = min((int)(r.bby >> 16), ty0 + TILE_H - 1);
+        float y = (float)ly;
+        for (int yi = ly; yi <= hy; yi++, y = FADD(y, 1.0f)) {
+            float x = (float)lx;
+            for (int xi = lx; xi <= hx; xi++, x = FADD(x, 1.0f)) {
+                float d;
+                if (!cover_pixel(t.ecx, t.ecy, t.ek1, t.ek2, t.f, t.flags, r.da, r.db, r.dc, x, y, d)) continue;
+                if (!(d < depth_max)) continue; // also rejects NaN; equality with the clear depth fails `<`
+                const unsigned long long key = make_key(d, slot);
+                unsigned long long *cell = &keys[(yi - ty0) * TILE_W + (xi - tx0)];
+                if (key < *cell) atomicMin(cell, key);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: deferred shading, fused clear ----------------------------------------------------
+#pragma unroll 1
+    for (int it = 0; it < TILE_PIXELS / TILE_THREADS; it++) {
+        const int p = it * TILE_THREADS + tid;
+        const uint32_t slot = (uint32_t)keys[p];
+        uint32_t c = 155u | (186u << 8) | (255u << 16) | (255u << 24); // azul_bb, pad 255 (canvas.rs:131)
+        float d = depth_max;
+        uint32_t id = NO_SLOT;
+        if (slot != NO_SLOT) {
+            const RasterRec r = load_raster(rrec + slot);
+            float op;
+            c = shade_pixel(S, r, W.srec + slot, (float)(tx0 + (p & (TILE_W - 1))), (float)(ty0 + p / TILE_W), &d, &op) | (255u << 24);
+            id = r.id;
+        }
+        colour[p] = c;
+        keys[p] = ((unsigned long long)__float_as_uint(d) << 32) | id; // own pixel: no sync needed
+    }
+
+    // ---- phase D: transparent triangles in draw order (scene/mod.rs:1088-1246) -------------------
+    const uint32_t n_tslots = usable ? S.n_transparent * 4u : 0u;
+#pragma unroll 1
+    for (uint32_t base = 0; base < n_tslots; base += CHUNK) {
+        const uint32_t n = min((uint32_t)CHUNK, n_tslots - base);
+        __syncthreads();
+        if ((uint32_t)tid < n) stage_triangle(staged + tid, W.t_rrec + base + tid, base + tid);
+        __syncthreads();
+#pragma unroll 1
+        for (uint32_t k = 0; k < n; k++) {
+            const StagedTri &s = staged[k];
+            if (s.x1 < (float)tx0 || s.x0 > (float)(tx0 + TILE_W - 1) || s.y1 < (float)ty0 || s.y0 > (float)(ty0 + TILE_H - 1))
+                continue;
+#pragma unroll 1
+            for (int it = 0; it < TILE_PIXELS / TILE_THREADS; it++) {
+                const int p = it * TILE_THREADS + tid;
+                const float x = (float)(tx0 + (p & (TILE_W - 1))), y = (float)(ty0 + p / TILE_W);
+                if (x < s.x0 || x > s.x1 || y < s.y0 || y > s.y1) continue;
+                float d;
+                if (!cover_pixel(s.ecx, s.ecy, s.ek1, s.ek2, s.f, s.flags | TRI_SLOW, s.da, s.db, s.dc, x, y, d)) continue;
+                const unsigned long long key = keys[p];
+                const uint32_t wid = (uint32_t)key;
+                if (!(wid == NO_SLOT || s.id > wid)) continue;            // drawn before the opaque winner: overwritten
+                if (!(d < __uint_as_float((uint32_t)(key >> 32)))) continue; // canvas.rs:923, depth write is off
+                const RasterRec r = load_raster(W.t_rrec + s.slot);
+                float d2, op;
+                const uint32_t rgb = shade_pixel(S, r, W.t_srec + s.slot, x, y, &d2, &op);
+                // canvas.rs:916-921: opacity < 1 blends with the stored colour, else replaces it
+                colour[p] = op < 1.0f ? blend_rgb(colour[p], rgb, op) : (rgb | (255u << 24));
+            }
+        }
+    }
+
+    // ---- phase E: single write-back -------------------------------------------------------------
+    const int W_ = (int)U.canvas_w, H_ = (int)U.canvas_h;
+#pragma unroll
+    for (int it = 0; it < TILE_PIXELS / TILE_THREADS; it++) {
+        const int p = it * TILE_THREADS + tid;
+        const int x = tx0 + (p & (TILE_W - 1)), y = ty0 + p / TILE_W;
+        if (x >= W_ || y >= H_) continue;
+        const uint32_t c = colour[p]; // r g b pad -> memory order b g r pad
+        reinterpret_cast<uint32_t *>(color)[(size_t)(H_ - 1 - y) * W_ + x] =
+            ((c >> 16) & 255u) | (c & 0x0000FF00u) | ((c & 255u) << 16) | (c & 0xFF000000u);
+        depth[(size_t)y * W_ + x] = __uint_as_float((uint32_t)(keys[p] >> 32));
+    }
+    if (W.tile_cycles) {
+        __syncthreads();
+        if (tid == 0) W.tile_cycles[tile] = (uint32_t)(clock64() - t_start);
     }
 }
 

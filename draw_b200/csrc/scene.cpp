@@ -26,7 +26,7 @@ namespace drawb200 {
 void launch_vertex(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
 void launch_setup(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
 void launch_bin_count(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream);
-void launch_scan(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream);
+void launch_alloc(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream);
 void launch_bin_fill(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream);
 void launch_tile(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, uint8_t *color, float *depth,
                  cudaStream_t stream);
@@ -141,7 +141,9 @@ struct draw_scene {
 
     // per-frame work buffers
     DevBuf<float> w_vert[9];
-    DevBuf<uint32_t> w_flags, w_list_count, w_list_offset, w_refs, w_counters;
+    DevBuf<uint32_t> w_flags, w_list_count, w_list_offset, w_refs, w_counters, w_tile_cycles;
+    bool debug_tile_cycles = false;
+    DevBuf<unsigned long long> w_scan_desc;
     DevBuf<RasterRec> w_rrec, w_trrec;
     DevBuf<ShadeRec> w_srec, w_tsrec;
     size_t rec_cap = 0, refs_cap = 0;
@@ -298,6 +300,7 @@ int ensure_work_buffers(draw_scene *s, size_t n_lists) {
     TRY(s->w_list_offset.reserve(n_lists + 1));
     TRY(s->w_refs.reserve(s->refs_cap));
     TRY(s->w_counters.reserve(4));
+    TRY(s->w_scan_desc.reserve((size_t)d.n_triangles / 256 + 2));
     FrameDev &w = s->work;
     w.v_lx = s->w_vert[0].ptr; w.v_ly = s->w_vert[1].ptr; w.v_lz = s->w_vert[2].ptr;
     w.v_hx = s->w_vert[3].ptr; w.v_hy = s->w_vert[4].ptr; w.v_hz = s->w_vert[5].ptr;
@@ -307,8 +310,14 @@ int ensure_work_buffers(draw_scene *s, size_t n_lists) {
     w.t_rrec = s->w_trrec.ptr; w.t_srec = s->w_tsrec.ptr;
     w.list_count = s->w_list_count.ptr; w.list_offset = s->w_list_offset.ptr; w.list_refs = s->w_refs.ptr;
     w.counters = s->w_counters.ptr;
+    w.scan_desc = s->w_scan_desc.ptr;
     w.rec_cap = (uint32_t)s->rec_cap;
     w.refs_cap = (uint32_t)s->refs_cap;
+    w.tile_cycles = nullptr;
+    if (s->debug_tile_cycles) {
+        TRY(s->w_tile_cycles.reserve(n_lists));
+        w.tile_cycles = s->w_tile_cycles.ptr;
+    }
     return DRAW_OK;
 }
 
@@ -362,7 +371,7 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     if (s->geometry_dirty) TRY(upload_geometry(s));
     const uint32_t tiles_x = (uint32_t)((c->width + TILE_W - 1) / TILE_W), tiles_y = (uint32_t)((c->height + TILE_H - 1) / TILE_H);
     const uint32_t n_coarse = tiles_x * tiles_y;
-    const uint32_t n_lists = n_coarse + n_coarse * FINE_PER_TILE_X * FINE_PER_TILE_Y;
+    const uint32_t n_lists = 2 * n_coarse;
     TRY(ensure_work_buffers(s, n_lists));
 
     // serialise frames that share this scene's work buffers across different streams
@@ -387,7 +396,6 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     U.tiles_x = tiles_x;
     U.tiles_y = tiles_y;
     U.n_coarse = n_coarse;
-    U.fine_nx = tiles_x * FINE_PER_TILE_X;
     U.n_lists = n_lists;
     const size_t y0 = c->stripe_y1 ? c->stripe_y0 : 0, y1 = c->stripe_y1 ? c->stripe_y1 : c->height;
     U.tile_y_begin = (uint32_t)(y0 / TILE_H);
@@ -411,7 +419,7 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     if (ev) cudaEventRecord(ev[2], st);
     launch_bin_count(U, s->work, st);
     if (ev) cudaEventRecord(ev[3], st);
-    launch_scan(U, s->work, st);
+    launch_alloc(U, s->work, st);
     if (ev) cudaEventRecord(ev[4], st);
     launch_bin_fill(U, s->work, st);
     if (ev) cudaEventRecord(ev[5], st);
@@ -758,6 +766,33 @@ int draw_scene_last_kernel_times(draw_scene *scene, draw_canvas *canvas, float m
     if (!scene->kev_recorded) return fail(DRAW_ERR_INVALID_ARGUMENT, "kernel timing was not enabled for the last frame");
     TRY(finish_frame(canvas));
     for (int i = 0; i < N_FRAME_KERNELS; i++) CU(cudaEventElapsedTime(&ms[i], scene->kev[i], scene->kev[i + 1]));
+    return DRAW_OK;
+    GUARD_END
+}
+
+int draw_scene_debug_tile_cycles(draw_scene *scene, draw_canvas *canvas, int enable, uint32_t *out, size_t n) {
+    GUARD_BEGIN
+    if (!scene) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    scene->debug_tile_cycles = enable != 0;
+    if (!out) return DRAW_OK;
+    if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    TRY(finish_frame(canvas));
+    if (!scene->w_tile_cycles.ptr || n > scene->w_tile_cycles.cap) return fail(DRAW_ERR_INVALID_ARGUMENT, "no tile cycles recorded");
+    CU(cudaMemcpy(out, scene->w_tile_cycles.ptr, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return DRAW_OK;
+    GUARD_END
+}
+
+int draw_scene_debug_list_counts(draw_scene *scene, draw_canvas *canvas, uint32_t *out, size_t n, size_t *n_coarse) {
+    GUARD_BEGIN
+    if (!scene || !canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    TRY(finish_frame(canvas));
+    const size_t tiles_x = (canvas->width + TILE_W - 1) / TILE_W, tiles_y = (canvas->height + TILE_H - 1) / TILE_H;
+    const size_t coarse = tiles_x * tiles_y, lists = coarse * 2;
+    if (n_coarse) *n_coarse = coarse;
+    if (!out) return DRAW_OK;
+    if (n != lists) return fail(DRAW_ERR_INVALID_ARGUMENT, "n must be %zu", lists);
+    CU(cudaMemcpy(out, scene->w_list_count.ptr, lists * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return DRAW_OK;
     GUARD_END
 }

@@ -143,9 +143,17 @@ int draw_scene_launch_count(const draw_scene *scene, uint64_t *out);
 
 /* Measurement tap: when enabled, every frame records CUDA events between its kernels on the
  * canvas' stream; last_kernel_times waits for the frame and returns the device time in ms of
- * k_vertex, k_setup, k_bin<count>, k_scan, k_bin<fill>, k_tile (DESIGN.md describes them). */
+ * k_vertex, k_setup, k_bin<count>, k_alloc, k_bin<fill>, k_tile (DESIGN.md describes them). */
 int draw_scene_set_kernel_timing(draw_scene *scene, int enabled);
 int draw_scene_last_kernel_times(draw_scene *scene, draw_canvas *canvas, float ms[6]);
+
+/* Debug tap: sizes of the last frame's tile lists (coarse tiles first, then fine tiles, see
+ * DESIGN.md).  out == NULL only returns the number of coarse tiles. */
+int draw_scene_debug_list_counts(draw_scene *scene, draw_canvas *canvas, uint32_t *out, size_t n, size_t *n_coarse);
+
+/* Debug tap: enable != 0 makes later frames record the SM cycles each coarse tile's CTA spent in
+ * k_tile; out (n = number of coarse tiles) receives the last frame's values, or NULL to only toggle. */
+int draw_scene_debug_tile_cycles(draw_scene *scene, draw_canvas *canvas, int enable, uint32_t *out, size_t n);
 
 /* ---- Canvas (canvas.rs) -------------------------------------------------------------- */
 /* Canvas::new(width, height) :366 — colour BGRA8 (Pixel, :51-59), black; no depth yet. */
