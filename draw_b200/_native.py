@@ -94,6 +94,9 @@ SIGNATURES = {
     "draw_canvas_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "draw_canvas_set_stripe": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t]),
     "draw_tile_size": (C.c_int, []),
+    "draw_canvas_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "draw_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "draw_ipc_close": (C.c_int, [C.c_void_p]),
     "draw_object_load_obj": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "draw_object_free": (None, [C.c_void_p]),
     "draw_object_desc_of": (C.c_int, [C.c_void_p, C.POINTER(ObjectDesc)]),

@@ -257,13 +257,13 @@ class Scene:
         return dict(zip(self.KERNELS, (float(x) for x in ms)))
 
     def debug_list_counts(self, canvas):
-        """(large list sizes, small list sizes) per tile of the last frame, as uint32 arrays."""
+        """(large, medium, small) list sizes per tile of the last frame, as uint32 arrays."""
         nc = C.c_size_t()
         N.check(N.lib().draw_scene_debug_list_counts(self._h, canvas._h, None, 0, C.byref(nc)))
-        n = nc.value * 2
+        n = nc.value * 3
         out = np.empty(n, np.uint32)
         N.check(N.lib().draw_scene_debug_list_counts(self._h, canvas._h, out.ctypes.data, n, C.byref(nc)))
-        return out[:nc.value], out[nc.value:]
+        return out[:nc.value], out[nc.value:2 * nc.value], out[2 * nc.value:]
 
     def debug_tile_cycles(self, canvas=None, enable=True):
         """Toggle per-tile cycle recording; with a canvas, return the last frame's cycles per coarse tile."""

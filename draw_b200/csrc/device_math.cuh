@@ -130,16 +130,19 @@ __device__ __forceinline__ TriEdges prepare_edges(const RasterRec &r) {
 // value fl(fl(fl(cx*x + cy*y) + k1) - k2) is a monotone function of x and of y because every
 // rounding step is monotone, so its maximum over the rectangle sits at the corner selected by
 // the coefficient signs; if that corner fails an edge test, every pixel of the rectangle fails.
-__device__ __forceinline__ bool rect_may_cover(const TriEdges &t, int lx, int hx, int ly, int hy) {
+__device__ __forceinline__ bool rect_may_cover(const TriEdges &t, float lx, float hx, float ly, float hy) {
     if (t.flags & TRI_SLOW) return true;
     bool any = true;
 #pragma unroll
     for (int e = 0; e < 3; e++) {
-        const float xm = (float)(t.ecx[e] >= 0.0f ? hx : lx), ym = (float)(t.ecy[e] >= 0.0f ? hy : ly);
+        const float xm = t.ecx[e] >= 0.0f ? hx : lx, ym = t.ecy[e] >= 0.0f ? hy : ly;
         const float em = FSUB(FADD(FADD(FMUL(t.ecx[e], xm), FMUL(t.ecy[e], ym)), t.ek1[e]), t.ek2[e]);
         any = any && (em > 0.0f || (em == 0.0f && (t.flags & (1u << e))));
     }
     return any;
+}
+__device__ __forceinline__ bool rect_may_cover(const TriEdges &t, int lx, int hx, int ly, int hy) {
+    return rect_may_cover(t, (float)lx, (float)hx, (float)ly, (float)hy);
 }
 
 } // namespace drawb200

@@ -5,11 +5,15 @@
 namespace drawb200 {
 
 // Screen partition.  A CTA of k_tile owns one tile of TILE_W x TILE_H pixels and keeps its depth /
-// winner / colour on chip.  Each tile has two lists of raster records: "large" (list id = tile) and
-// "small" (list id = n_coarse + tile; bbox of at most SMALL_AREA pixels).  REGION is the square each
-// warp owns during the large-record phase (8 pixels per lane).
+// winner / colour on chip.  Each tile has three lists of raster records, classed by the area of
+// (record bbox intersected with the tile):
+//   large   list id = tile                  > MEDIUM_AREA px : every lane tests its own pixels
+//   medium  list id = n_coarse + tile       <= MEDIUM_AREA px: one record per warp, lane per pixel
+//   small   list id = 2 * n_coarse + tile   <= SMALL_AREA px : one record per lane
+// REGION is the square each warp owns during the large-record phase (8 pixels per lane).
 constexpr int TILE_W = 64, TILE_H = 32, REGION = 16;
-constexpr int SMALL_AREA = 64;
+constexpr int SMALL_AREA = 64, MEDIUM_AREA = 1024;
+constexpr int LISTS_PER_TILE = 3;
 constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
 
 // Per-frame constants, passed to every kernel by value (__grid_constant__): no upload, no sync.
@@ -24,16 +28,19 @@ struct FrameUniforms {
     uint32_t tiles_x, tiles_y;         // whole canvas, in coarse tiles
     uint32_t tile_y_begin, tile_y_end; // coarse tile rows rendered by this launch (sort-first stripe)
     uint32_t n_coarse;                 // tiles_x * tiles_y
-    uint32_t n_lists;                  // 2 * n_coarse: large lists, then small lists
+    uint32_t n_lists;                  // LISTS_PER_TILE * n_coarse: large, medium, small lists
 };
 
-// Texture (scene/mod.rs:206-216) with both TextureMaps flattened into the texel pool.
-struct MaterialDev {
+// Texture (scene/mod.rs:206-216) with both TextureMaps flattened into the texel pool.  Maps are
+// stored with 4 bytes per texel (3-component images are padded at upload) so that a texel is one
+// aligned 32-bit load; offsets are byte offsets into the pool, multiples of 4.  64 bytes, read by
+// shade_pixel as four uint4 — keep the field order.
+struct alignas(16) MaterialDev {
     float ka[3], kd[3], ks[3];
     float alpha;
-    uint32_t ka_off, ka_w, ka_h, ka_comp;
-    uint32_t kd_off, kd_w, kd_h, kd_comp;
-    uint32_t pad[2];
+    uint32_t ka_off, ka_w;
+    uint32_t kd_off, kd_w, kd_h;
+    uint32_t ka_h;
 };
 
 // Scene geometry, SoA, all objects concatenated (indices are global after upload).
@@ -78,7 +85,7 @@ struct FrameDev {
     ShadeRec *srec;
     RasterRec *t_rrec;          // transparent records, slot = 4*ordinal + k, in draw order [4*n_transparent]
     ShadeRec *t_srec;
-    uint32_t *list_count;       // per list (large lists, then small lists): count, then fill cursor [n_lists]
+    uint32_t *list_count;       // per list (large, medium, small per tile): count, then fill cursor [n_lists]
     uint32_t *list_offset;      // first entry of each list in list_refs [n_lists + 1]
     uint32_t *list_refs;        // record slots grouped by list [refs_cap]
     uint32_t *counters;         // [0] records  [1] refs  [2] overflow bits  [3] k_setup CTA ticket

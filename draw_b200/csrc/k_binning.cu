@@ -7,9 +7,10 @@
 //   k_alloc       per list    reserve a contiguous range of list_refs for every list
 //   k_bin<true>   per record  scatter its slot into those lists
 //
-// Every tile (64x32 px) has two lists (device_types.h): "large" records are rasterised by k_tile
-// with every lane testing its own pixels, "small" records (bbox <= SMALL_AREA px) one record per
-// lane.  A tile is only referenced if the triangle can actually cover a pixel in it (exact corner
+// Every tile (64x32 px) has three lists (device_types.h), classed by the area of the record's bbox
+// inside the tile: "large" records are rasterised by k_tile with every lane testing its own pixels,
+// "medium" ones one record per warp, "small" ones one record per lane.
+// A tile is only referenced if the triangle can actually cover a pixel in it (exact corner
 // test, rect_may_cover), not merely because its bbox touches it.  Records covering many tiles are
 // binned by the whole warp (ballot picks them, lanes stride over the tiles).
 // Order inside a list is irrelevant: k_tile resolves fragments by (depth, record slot), and slots
@@ -24,8 +25,38 @@ __device__ __forceinline__ void bin_hit(const FrameDev &W, uint32_t list, uint32
     if (FILL) W.list_refs[W.list_offset[list] + pos] = slot;
 }
 
+// Reference one tile from a record if the triangle can cover a pixel of it; the list class follows
+// the area of the bbox clipped to the tile.
+template <bool FILL>
+__device__ __forceinline__ void bin_tile(const FrameUniforms &U, const FrameDev &W, const TriEdges &t, int x0, int x1,
+                                         int y0, int y1, int tx, int ty, uint32_t slot) {
+    const int lx = max(x0, tx * TILE_W), hx = min(x1, tx * TILE_W + TILE_W - 1);
+    const int ly = max(y0, ty * TILE_H), hy = min(y1, ty * TILE_H + TILE_H - 1);
+    if (!rect_may_cover(t, lx, hx, ly, hy)) return;
+    const int area = (hx - lx + 1) * (hy - ly + 1);
+    const uint32_t cls = area <= SMALL_AREA ? 2u : (area <= MEDIUM_AREA ? 1u : 0u);
+    bin_hit<FILL>(W, cls * U.n_coarse + (uint32_t)ty * U.tiles_x + (uint32_t)tx, slot);
+}
+
 constexpr int BIN_THREADS = 256;
-constexpr int WIDE_TILES = 16; // records covering more coarse tiles than this are binned warp-cooperatively
+constexpr int WIDE_TILES = 8;        // thread-per-record mode: records covering more tiles are binned by the whole warp
+constexpr int RECORDS_PER_WARP = 8;  // up to this many records per warp of the grid: one warp per record
+
+// Tile range of a record's bbox, clipped to this launch's stripe.
+struct TileRange {
+    int x0, x1, y0, y1;     // bbox in pixels
+    int tx0, tx1, ty0, ty1; // tiles
+    __device__ __forceinline__ int count() const { return ty0 <= ty1 ? (tx1 - tx0 + 1) * (ty1 - ty0 + 1) : 0; }
+};
+__device__ __forceinline__ TileRange tile_range(const FrameUniforms &U, uint32_t bbx, uint32_t bby) {
+    TileRange t;
+    t.x0 = (int)(bbx & 0xFFFF); t.x1 = (int)(bbx >> 16);
+    t.y0 = (int)(bby & 0xFFFF); t.y1 = (int)(bby >> 16);
+    t.tx0 = t.x0 / TILE_W; t.tx1 = t.x1 / TILE_W;
+    t.ty0 = max(t.y0 / TILE_H, (int)U.tile_y_begin);
+    t.ty1 = min(t.y1 / TILE_H, (int)U.tile_y_end - 1);
+    return t;
+}
 
 template <bool FILL>
 __global__ void __launch_bounds__(BIN_THREADS) k_bin(const __grid_constant__ FrameUniforms U, const FrameDev W) {
@@ -33,38 +64,40 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const __grid_constant__ Fra
     uint32_t n = W.counters[0];
     if (n > W.rec_cap) n = W.rec_cap;
     const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n_warps = gridDim.x * (BIN_THREADS / 32);
 
+    if (n <= n_warps * RECORDS_PER_WARP) {
+        // Few records (they may each cover many tiles): one warp per record, lanes stride over its
+        // tiles so that the atomics of one record are in flight together.
+        for (uint32_t slot = blockIdx.x * (BIN_THREADS / 32) + (threadIdx.x >> 5); slot < n; slot += n_warps) {
+            const RasterRec r = load_raster(W.rrec + slot); // same address in every lane: one broadcast load
+            const TileRange tr = tile_range(U, r.bbx, r.bby);
+            const int total = tr.count();
+            if (total == 0) continue;
+            const TriEdges t = prepare_edges(r);
+            const int cols = tr.tx1 - tr.tx0 + 1;
+            for (int i = (int)lane; i < total; i += 32)
+                bin_tile<FILL>(U, W, t, tr.x0, tr.x1, tr.y0, tr.y1, tr.tx0 + i % cols, tr.ty0 + i / cols, slot);
+        }
+        return;
+    }
+
+    // Many records: one thread per record; the rare record covering many tiles is handed to the warp.
     for (uint32_t base = blockIdx.x * BIN_THREADS; base < n; base += gridDim.x * BIN_THREADS) {
         const uint32_t slot = base + threadIdx.x;
         const bool valid = slot < n;
         RasterRec r;
         if (valid) r = load_raster(W.rrec + slot);
         else { r.bbx = r.bby = 0; r.ax = r.ay = r.bx = r.by = r.cx = r.cy = 0.0f; }
-        const int x0 = (int)(r.bbx & 0xFFFF), x1 = (int)(r.bbx >> 16);
-        const int y0 = (int)(r.bby & 0xFFFF), y1 = (int)(r.bby >> 16);
-        // small: bbox of at most SMALL_AREA pixels -> the tile's "small" list (one lane of k_tile walks it);
-        // anything else -> the tile's "large" list (all lanes of k_tile test their own pixels against it)
-        const bool small = (x1 - x0 + 1) * (y1 - y0 + 1) <= SMALL_AREA;
-        const int tx0 = x0 / TILE_W, tx1 = x1 / TILE_W;
-        int ty0 = y0 / TILE_H, ty1 = y1 / TILE_H;
-        if (ty0 < (int)U.tile_y_begin) ty0 = (int)U.tile_y_begin;
-        if (ty1 > (int)U.tile_y_end - 1) ty1 = (int)U.tile_y_end - 1;
-        const int n_coarse_hit = ty0 <= ty1 ? (tx1 - tx0 + 1) * (ty1 - ty0 + 1) : 0;
-        const bool wide = valid && n_coarse_hit > WIDE_TILES;
+        const TileRange tr = tile_range(U, r.bbx, r.bby);
+        const bool wide = valid && tr.count() > WIDE_TILES;
 
         if (valid && !wide) {
             const TriEdges t = prepare_edges(r);
-            const uint32_t list_base = small ? U.n_coarse : 0u;
-            for (int ty = ty0; ty <= ty1; ty++)
-                for (int tx = tx0; tx <= tx1; tx++) {
-                    const int lx = max(x0, tx * TILE_W), hx = min(x1, tx * TILE_W + TILE_W - 1);
-                    const int ly = max(y0, ty * TILE_H), hy = min(y1, ty * TILE_H + TILE_H - 1);
-                    if (rect_may_cover(t, lx, hx, ly, hy))
-                        bin_hit<FILL>(W, list_base + (uint32_t)ty * U.tiles_x + (uint32_t)tx, slot);
-                }
+            for (int ty = tr.ty0; ty <= tr.ty1; ty++)
+                for (int tx = tr.tx0; tx <= tr.tx1; tx++) bin_tile<FILL>(U, W, t, tr.x0, tr.x1, tr.y0, tr.y1, tx, ty, slot);
         }
 
-        // wide records: one at a time, all 32 lanes stride over its coarse tiles
         uint32_t pending = __ballot_sync(0xFFFFFFFFu, wide);
         while (pending) {
             const int src = __ffs(pending) - 1;
@@ -73,19 +106,12 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const __grid_constant__ Fra
             w.ax = __shfl_sync(0xFFFFFFFFu, r.ax, src); w.ay = __shfl_sync(0xFFFFFFFFu, r.ay, src);
             w.bx = __shfl_sync(0xFFFFFFFFu, r.bx, src); w.by = __shfl_sync(0xFFFFFFFFu, r.by, src);
             w.cx = __shfl_sync(0xFFFFFFFFu, r.cx, src); w.cy = __shfl_sync(0xFFFFFFFFu, r.cy, src);
-            const int wx0 = __shfl_sync(0xFFFFFFFFu, x0, src), wx1 = __shfl_sync(0xFFFFFFFFu, x1, src);
-            const int wy0 = __shfl_sync(0xFFFFFFFFu, y0, src), wy1 = __shfl_sync(0xFFFFFFFFu, y1, src);
-            const int wtx0 = __shfl_sync(0xFFFFFFFFu, tx0, src), wtx1 = __shfl_sync(0xFFFFFFFFu, tx1, src);
-            const int wty0 = __shfl_sync(0xFFFFFFFFu, ty0, src), wty1 = __shfl_sync(0xFFFFFFFFu, ty1, src);
+            const TileRange wt = tile_range(U, __shfl_sync(0xFFFFFFFFu, r.bbx, src), __shfl_sync(0xFFFFFFFFu, r.bby, src));
             const uint32_t wslot = __shfl_sync(0xFFFFFFFFu, slot, src);
             const TriEdges t = prepare_edges(w);
-            const int cols = wtx1 - wtx0 + 1, total = cols * (wty1 - wty0 + 1);
-            for (int i = (int)lane; i < total; i += 32) {
-                const int tx = wtx0 + i % cols, ty = wty0 + i / cols;
-                const int lx = max(wx0, tx * TILE_W), hx = min(wx1, tx * TILE_W + TILE_W - 1);
-                const int ly = max(wy0, ty * TILE_H), hy = min(wy1, ty * TILE_H + TILE_H - 1);
-                if (rect_may_cover(t, lx, hx, ly, hy)) bin_hit<FILL>(W, (uint32_t)ty * U.tiles_x + (uint32_t)tx, wslot);
-            }
+            const int cols = wt.tx1 - wt.tx0 + 1, total = wt.count();
+            for (int i = (int)lane; i < total; i += 32)
+                bin_tile<FILL>(U, W, t, wt.x0, wt.x1, wt.y0, wt.y1, wt.tx0 + i % cols, wt.ty0 + i / cols, wslot);
         }
     }
 }
@@ -134,12 +160,7 @@ __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const FrameDev W, const
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-static int bin_blocks(const FrameDev &W) {
-    long long b = ((long long)W.rec_cap + BIN_THREADS - 1) / BIN_THREADS;
-    if (b > 148 * 8) b = 148 * 8;
-    if (b < 1) b = 1;
-    return (int)b;
-}
+static int bin_blocks(const FrameDev &) { return 148 * 4; }
 void launch_bin_count(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream) {
     k_bin<false><<<bin_blocks(W), BIN_THREADS, 0, stream>>>(U, W);
 }

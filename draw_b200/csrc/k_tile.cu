@@ -1,15 +1,16 @@
 // k_tile.cu — per-tile raster / depth / shade kernel (mororo18/draw canvas.rs:577-750, 906-960).
 //
-// One CTA (256 threads) per 64x32-pixel tile.  The tile's depth, winning record and colour stay on
+// One CTA (512 threads) per 64x32-pixel tile.  The tile's depth, winning record and colour stay on
 // chip (registers, then shared memory) for the whole kernel; colour and depth go to HBM exactly
 // once at the end, with the clear fused in.  No tensor cores: nothing here is a contraction.
 //
 //   phase A  "large" list: triangles are staged through shared memory 64 at a time; every lane owns
-//            a 4x2 pixel block (warp = 16x16 region) and tests it against each triangle, after a
+//            a 4x1 pixel block (warp = 16x8 region) and tests it against each triangle, after a
 //            warp-level bbox reject and an exact block-level edge reject.  Depth/winner in registers.
 //   merge    each lane publishes its 8 pixels as 64-bit keys (depth, slot) in shared memory.
-//   phase B  "small" list (bbox <= 64 px): one triangle per lane; the lane walks the bbox and
-//            commits covered fragments with a shared-memory atomicMin on the key.
+//   phase B  "medium" list (bbox in the tile <= 1024 px): one triangle per warp, the lanes sweep the
+//            bbox in 8x4 blocks (exact block reject first); "small" list (<= 64 px): one triangle per
+//            lane.  Covered fragments are committed with a shared-memory atomicMin on the key.
 //   phase C  deferred shading, one pixel per lane per step: only the winner of a pixel is shaded
 //            (canvas.rs:685-743); the key becomes (exact depth, draw id), colour goes to smem.
 //   phase D  transparent triangles in draw order, blended over the shaded colour (rare).
@@ -28,10 +29,18 @@
 
 namespace drawb200 {
 
-constexpr int TILE_THREADS = 256;
+#ifndef DRAW_TILE_THREADS
+#define DRAW_TILE_THREADS 512
+#endif
+constexpr int TILE_THREADS = DRAW_TILE_THREADS;
 constexpr int CHUNK = 64; // large-list triangles staged per round
-constexpr int PX = 8;     // pixels per lane in phase A: 4 wide x 2 tall
 constexpr int TILE_PIXELS = TILE_W * TILE_H;
+// phase A geometry: a warp owns a REGION x REGION_H rectangle (4 lanes across, 8 down), a lane a
+// 4 x BLK_H block of it
+constexpr int BLK_H = TILE_PIXELS / TILE_THREADS / 4;
+constexpr int PX = 4 * BLK_H;
+constexpr int REGION_H = 8 * BLK_H;
+static_assert(BLK_H >= 1 && TILE_W / REGION * (TILE_H / REGION_H) * 32 == TILE_THREADS, "tile geometry");
 
 // One triangle prepared for the phase-A pixel loop (25 words; stride 25 is conflict-free for the
 // staging writes, and every read in the pixel loop is a broadcast).  The bbox is kept as floats
@@ -106,6 +115,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ F
     __shared__ unsigned long long keys[TILE_PIXELS]; // (depth key, slot), later (depth bits, draw id)
     __shared__ uint32_t colour[TILE_PIXELS];         // r | g << 8 | b << 16 | pad << 24
     __shared__ StagedTri staged[CHUNK];
+    __shared__ float u8tab[256]; // (u8 as f32) / 255.0
 
     const uint32_t tile_x = blockIdx.x % U.tiles_x;
     const uint32_t tile_y = U.tile_y_begin + blockIdx.x / U.tiles_x;
@@ -114,25 +124,29 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ F
     const long long t_start = W.tile_cycles ? clock64() : 0;
     const int tx0 = (int)tile_x * TILE_W, ty0 = (int)tile_y * TILE_H;
 
+    fill_u8_table(u8tab, tid, TILE_THREADS); // visible after the barrier that ends phase A
+
     const bool usable = W.counters[2] == 0;
     const uint32_t l_begin = usable ? W.list_offset[tile] : 0u;
     const uint32_t l_count = usable ? W.list_count[tile] : 0u; // the fill cursor ends at the count
-    const uint32_t s_begin = usable ? W.list_offset[U.n_coarse + tile] : 0u;
-    const uint32_t s_count = usable ? W.list_count[U.n_coarse + tile] : 0u;
+    const uint32_t m_begin = usable ? W.list_offset[U.n_coarse + tile] : 0u;
+    const uint32_t m_count = usable ? W.list_count[U.n_coarse + tile] : 0u;
+    const uint32_t s_begin = usable ? W.list_offset[2 * U.n_coarse + tile] : 0u;
+    const uint32_t s_count = usable ? W.list_count[2 * U.n_coarse + tile] : 0u;
     const RasterRec *__restrict__ rrec = W.rrec;
     const float depth_max = U.depth_max;
 
     // ---- phase A: large triangles, every lane tests its own 4x2 block ------------------------------
     {
         // warp -> 16x16 region, lane -> 4x2 block (canvas coordinates: x right, y = depth-buffer row)
-        const int rx0 = tx0 + (warp & 3) * REGION, ry0 = ty0 + (warp >> 2) * REGION;
-        const int bx0 = rx0 + (lane & 3) * 4, by0 = ry0 + (lane >> 2) * 2;
-        const float fx0 = (float)rx0, fy0 = (float)ry0, fx1 = fx0 + (float)(REGION - 1), fy1 = fy0 + (float)(REGION - 1);
-        float xf[4], yf[2];
+        const int rx0 = tx0 + (warp & 3) * REGION, ry0 = ty0 + (warp >> 2) * REGION_H;
+        const int bx0 = rx0 + (lane & 3) * 4, by0 = ry0 + (lane >> 2) * BLK_H;
+        const float fx0 = (float)rx0, fy0 = (float)ry0, fx1 = fx0 + (float)(REGION - 1), fy1 = fy0 + (float)(REGION_H - 1);
+        float xf[4], yf[BLK_H];
 #pragma unroll
         for (int i = 0; i < 4; i++) xf[i] = (float)(bx0 + i);
 #pragma unroll
-        for (int j = 0; j < 2; j++) yf[j] = (float)(by0 + j);
+        for (int j = 0; j < BLK_H; j++) yf[j] = (float)(by0 + j);
         float zb[PX];
         uint32_t sl[PX];
 #pragma unroll
@@ -154,7 +168,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ F
                 const StagedTri &s = staged[k];
                 if (s.x1 < fx0 || s.x0 > fx1 || s.y1 < fy0 || s.y0 > fy1) continue; // warp-uniform
                 const float lo_x = fmaxf(s.x0, xf[0]), hi_x = fminf(s.x1, xf[3]);
-                const float lo_y = fmaxf(s.y0, yf[0]), hi_y = fminf(s.y1, yf[1]);
+                const float lo_y = fmaxf(s.y0, yf[0]), hi_y = fminf(s.y1, yf[BLK_H - 1]);
                 if (lo_x > hi_x || lo_y > hi_y) continue;
                 const uint32_t flags = s.flags, slot = s.slot;
                 if (!(flags & TRI_SLOW)) {
@@ -168,16 +182,16 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ F
                         any = any && (em > 0.0f || (em == 0.0f && (flags & (1u << e))));
                     }
                     if (!any) continue;
-                    float pxs[3][4], pys[3][2];
+                    float pxs[3][4], pys[3][BLK_H];
 #pragma unroll
                     for (int e = 0; e < 3; e++) {
 #pragma unroll
                         for (int i = 0; i < 4; i++) pxs[e][i] = FMUL(s.ecx[e], xf[i]);
 #pragma unroll
-                        for (int j = 0; j < 2; j++) pys[e][j] = FMUL(s.ecy[e], yf[j]);
+                        for (int j = 0; j < BLK_H; j++) pys[e][j] = FMUL(s.ecy[e], yf[j]);
                     }
 #pragma unroll
-                    for (int j = 0; j < 2; j++) {
+                    for (int j = 0; j < BLK_H; j++) {
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
                             if (xf[i] < lo_x || xf[i] > hi_x || yf[j] < lo_y || yf[j] > hi_y) continue;
@@ -223,7 +237,38 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ F
     }
     __syncthreads();
 
-    // ---- phase B: small triangles, one per lane, atomicMin on the key ---------------------------
+    // ---- phase B1: medium triangles, one per warp; lanes sweep the bbox in 8x4 pixel blocks --------
+    {
+        const float dxf = (float)(lane & 7), dyf = (float)(lane >> 3);
+#pragma unroll 1
+        for (uint32_t i = (uint32_t)warp; i < m_count; i += TILE_THREADS / 32) {
+            const uint32_t slot = W.list_refs[m_begin + i];
+            const RasterRec r = load_raster(rrec + slot); // same address in every lane: one broadcast load
+            const TriEdges t = prepare_edges(r);
+            const int lx = max((int)(r.bbx & 0xFFFF), tx0), hx = min((int)(r.bbx >> 16), tx0 + TILE_W - 1);
+            const int ly = max((int)(r.bby & 0xFFFF), ty0), hy = min((int)(r.bby >> 16), ty0 + TILE_H - 1);
+            const float lxf = (float)lx, hxf = (float)hx, hyf = (float)hy;
+            float byf = (float)ly;
+#pragma unroll 1
+            for (int by = ly; by <= hy; by += 4, byf = FADD(byf, 4.0f)) {
+                float bxf = lxf;
+#pragma unroll 1
+                for (int bx = lx; bx <= hx; bx += 8, bxf = FADD(bxf, 8.0f)) {
+                    // exact block-level reject (warp-uniform)
+                    if (!rect_may_cover(t, bxf, fminf(FADD(bxf, 7.0f), hxf), byf, fminf(FADD(byf, 3.0f), hyf))) continue;
+                    const float x = FADD(bxf, dxf), y = FADD(byf, dyf);
+                    if (x > hxf || y > hyf) continue;
+                    float d;
+                    if (!cover_pixel(t.ecx, t.ecy, t.ek1, t.ek2, t.f, t.flags, r.da, r.db, r.dc, x, y, d)) continue;
+                    if (!(d < depth_max)) continue;
+                    const unsigned long long key = make_key(d, slot);
+                    unsigned long long *cell = &keys[(by + (lane >> 3) - ty0) * TILE_W + (bx + (lane & 7) - tx0)];
+                    if (key < *cell) atomicMin(cell, key);
+                }
+            }
+        }
+    }
+    // ---- phase B2: small triangles, one per lane, atomicMin on the key --------------------------
     for (uint32_t i = (uint32_t)tid; i < s_count; i += TILE_THREADS) {
         const uint32_t slot = W.list_refs[s_begin + i];
         const RasterRec r = load_raster(rrec + slot);
@@ -256,7 +301,8 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ F
         if (slot != NO_SLOT) {
             const RasterRec r = load_raster(rrec + slot);
             float op;
-            c = shade_pixel(S, r, W.srec + slot, (float)(tx0 + (p & (TILE_W - 1))), (float)(ty0 + p / TILE_W), &d, &op) | (255u << 24);
+            c = shade_pixel(S.materials, S.texels, u8tab, r, W.srec + slot, (float)(tx0 + (p & (TILE_W - 1))),
+                            (float)(ty0 + p / TILE_W), &d, &op) | (255u << 24);
             id = r.id;
         }
         colour[p] = c;
@@ -289,7 +335,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ F
                 if (!(d < __uint_as_float((uint32_t)(key >> 32)))) continue; // canvas.rs:923, depth write is off
                 const RasterRec r = load_raster(W.t_rrec + s.slot);
                 float d2, op;
-                const uint32_t rgb = shade_pixel(S, r, W.t_srec + s.slot, x, y, &d2, &op);
+                const uint32_t rgb = shade_pixel(S.materials, S.texels, u8tab, r, W.t_srec + s.slot, x, y, &d2, &op);
                 // canvas.rs:916-921: opacity < 1 blends with the stored colour, else replaces it
                 colour[p] = op < 1.0f ? blend_rgb(colour[p], rgb, op) : (rgb | (255u << 24));
             }

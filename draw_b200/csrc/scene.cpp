@@ -371,7 +371,7 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     if (s->geometry_dirty) TRY(upload_geometry(s));
     const uint32_t tiles_x = (uint32_t)((c->width + TILE_W - 1) / TILE_W), tiles_y = (uint32_t)((c->height + TILE_H - 1) / TILE_H);
     const uint32_t n_coarse = tiles_x * tiles_y;
-    const uint32_t n_lists = 2 * n_coarse;
+    const uint32_t n_lists = LISTS_PER_TILE * n_coarse;
     TRY(ensure_work_buffers(s, n_lists));
 
     // serialise frames that share this scene's work buffers across different streams
@@ -574,39 +574,45 @@ int draw_scene_add_object(draw_scene *scene, const draw_object_desc *desc, uint3
     o.uv.assign(desc->uvs, desc->uvs + 3 * desc->n_uvs);
     // texel block of this object; offset 0 holds the 1x1 white default map (scene/mod.rs:128-135)
     o.texels = {255, 255, 255, 255};
-    auto add_map = [&](const draw_texture_map &m, uint32_t &off, uint32_t &w, uint32_t &h, uint32_t &comp) -> int {
+    // maps are stored with 4 bytes per texel (r, g, b, x): 3-component images are padded
+    auto add_map = [&](const draw_texture_map &m, uint32_t &off, uint32_t &w, uint32_t &h) -> int {
         if (!m.pixels) {
-            off = 0; w = 1; h = 1; comp = 3;
+            off = 0; w = 1; h = 1;
             return DRAW_OK;
         }
         if (m.width == 0 || m.height == 0 || (m.components != 3 && m.components != 4))
             return fail(DRAW_ERR_INVALID_ARGUMENT, "texture map must be non-empty with 3 or 4 components");
-        const size_t bytes = (size_t)m.width * m.height * m.components;
-        // identical images inside one object (map_Ka == map_Kd is common) share storage
+        const size_t n = (size_t)m.width * m.height;
         off = (uint32_t)o.texels.size();
-        o.texels.insert(o.texels.end(), m.pixels, m.pixels + bytes);
-        while (o.texels.size() % 4) o.texels.push_back(0);
-        w = m.width; h = m.height; comp = m.components;
+        o.texels.resize(o.texels.size() + 4 * n);
+        uint8_t *dst = o.texels.data() + off;
+        if (m.components == 4) std::memcpy(dst, m.pixels, 4 * n);
+        else
+            for (size_t i = 0; i < n; i++) {
+                dst[4 * i] = m.pixels[3 * i]; dst[4 * i + 1] = m.pixels[3 * i + 1];
+                dst[4 * i + 2] = m.pixels[3 * i + 2]; dst[4 * i + 3] = 255;
+            }
+        w = m.width; h = m.height;
         return DRAW_OK;
     };
-    std::vector<std::pair<const uint8_t *, uint32_t>> seen; // pointer -> offset, dedupe by pointer
+    std::vector<std::pair<const uint8_t *, uint32_t>> seen; // identical images (map_Ka == map_Kd is common) share storage
     for (size_t i = 0; i < desc->n_materials; i++) {
         const draw_material &m = desc->materials[i];
         MaterialDev d{};
         for (int c = 0; c < 3; c++) { d.ka[c] = m.ka[c]; d.kd[c] = m.kd[c]; d.ks[c] = m.ks[c]; }
         d.alpha = m.alpha;
-        auto add_dedup = [&](const draw_texture_map &tm, uint32_t &off, uint32_t &w, uint32_t &h, uint32_t &comp) -> int {
+        auto add_dedup = [&](const draw_texture_map &tm, uint32_t &off, uint32_t &w, uint32_t &h) -> int {
             for (auto &pr : seen)
                 if (tm.pixels && pr.first == tm.pixels) {
-                    off = pr.second; w = tm.width; h = tm.height; comp = tm.components;
+                    off = pr.second; w = tm.width; h = tm.height;
                     return DRAW_OK;
                 }
-            TRY(add_map(tm, off, w, h, comp));
+            TRY(add_map(tm, off, w, h));
             if (tm.pixels) seen.push_back({tm.pixels, off});
             return DRAW_OK;
         };
-        TRY(add_dedup(m.map_ka, d.ka_off, d.ka_w, d.ka_h, d.ka_comp));
-        TRY(add_dedup(m.map_kd, d.kd_off, d.kd_w, d.kd_h, d.kd_comp));
+        TRY(add_dedup(m.map_ka, d.ka_off, d.ka_w, d.ka_h));
+        TRY(add_dedup(m.map_kd, d.kd_off, d.kd_w, d.kd_h));
         o.materials.push_back(d);
     }
     for (size_t i = 0; i < desc->n_meshes; i++) {
@@ -788,7 +794,7 @@ int draw_scene_debug_list_counts(draw_scene *scene, draw_canvas *canvas, uint32_
     if (!scene || !canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
     TRY(finish_frame(canvas));
     const size_t tiles_x = (canvas->width + TILE_W - 1) / TILE_W, tiles_y = (canvas->height + TILE_H - 1) / TILE_H;
-    const size_t coarse = tiles_x * tiles_y, lists = coarse * 2;
+    const size_t coarse = tiles_x * tiles_y, lists = coarse * LISTS_PER_TILE;
     if (n_coarse) *n_coarse = coarse;
     if (!out) return DRAW_OK;
     if (n != lists) return fail(DRAW_ERR_INVALID_ARGUMENT, "n must be %zu", lists);
@@ -989,6 +995,36 @@ int draw_canvas_bind_external(draw_canvas *canvas, void *color_dev, void *depth_
     canvas->ext_depth = static_cast<float *>(depth_dev);
     if (depth_dev) canvas->has_depth = true;
     canvas->host_dirty = true;
+    return DRAW_OK;
+    GUARD_END
+}
+
+int draw_canvas_ipc_export(draw_canvas *canvas, uint8_t handle[64]) {
+    GUARD_BEGIN
+    if (!canvas || !handle) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    TRY(ensure_device(canvas->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, canvas->d_color.ptr));
+    std::memcpy(handle, &h, 64);
+    return DRAW_OK;
+    GUARD_END
+}
+
+int draw_ipc_open(const uint8_t handle[64], void **out_dev_ptr) {
+    GUARD_BEGIN
+    if (!handle || !out_dev_ptr) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(out_dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return DRAW_OK;
+    GUARD_END
+}
+
+int draw_ipc_close(void *dev_ptr) {
+    GUARD_BEGIN
+    if (!dev_ptr) return DRAW_OK;
+    CU(cudaIpcCloseMemHandle(dev_ptr));
     return DRAW_OK;
     GUARD_END
 }

@@ -4,24 +4,33 @@
 
 namespace drawb200 {
 
+// u8 -> (u8 as f32) / 255.0 (Pixel::normalized_as_vec3, canvas.rs:81-87) as a 256-entry table that
+// each CTA fills in shared memory with the same IEEE division, so a lookup is bit-identical to the
+// reference's divide and six divisions per shaded pixel disappear.
+__device__ __forceinline__ void fill_u8_table(float *tab, int tid, int n_threads) {
+    for (int i = tid; i < 256; i += n_threads) tab[i] = FDIV((float)i, 255.0f);
+}
 
-// TextureMap::get_rgb_slice (scene/mod.rs:154-168) + Pixel::normalized_as_vec3 (canvas.rs:81-87).
-// Indices are clamped into the map (SURVEY.md §8c deviation 6; never triggers for uv in [0,1]).
-__device__ __forceinline__ v3 fetch_texel(const uint8_t *__restrict__ texels, uint32_t off, uint32_t w, uint32_t h,
-                                          uint32_t comp, float u, float v) {
+// TextureMap::get_rgb_slice (scene/mod.rs:154-168).  Maps are stored with 4 bytes per texel on the
+// device (3-component images are padded at upload), so a texel is one aligned 32-bit load through
+// the read-only path; only bytes 0..2 (r, g, b) are used, as in the reference.  Indices are clamped
+// into the map (SURVEY.md §8c deviation 6; never triggers for uv in [0,1]).
+__device__ __forceinline__ uint32_t fetch_texel(const uint8_t *__restrict__ texels, uint32_t off, uint32_t w, uint32_t h,
+                                                float u, float v) {
     unsigned long long ui = sat_usize(floorf(FMUL(u, FSUB((float)w, 1.0f))));
     unsigned long long vr = sat_usize(floorf(FMUL(v, FSUB((float)h, 1.0f))));
     if (ui > w - 1) ui = w - 1;
     if (vr > h - 1) vr = h - 1;
-    const uint8_t *p = texels + off + ((size_t)(h - 1 - (uint32_t)vr) * w + (uint32_t)ui) * comp;
-    return v3{FDIV((float)__ldg(p), 255.0f), FDIV((float)__ldg(p + 1), 255.0f), FDIV((float)__ldg(p + 2), 255.0f)};
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(texels + off) + ((size_t)(h - 1 - (uint32_t)vr) * w + (uint32_t)ui);
+    return __ldg(p);
 }
-
 
 // canvas.rs:673-743 for one covered pixel: literal barycentrics, interpolation, texel fetches and
 // Phong.  Returns r | g << 8 | b << 16; *depth_out gets the interpolated depth.
-__device__ __forceinline__ uint32_t shade_pixel(const SceneDev &S, const RasterRec &r, const ShadeRec *__restrict__ sp,
-                                                float x, float y, float *depth_out, float *opacity_out) {
+__device__ __forceinline__ uint32_t shade_pixel(const MaterialDev *__restrict__ materials,
+                                                const uint8_t *__restrict__ texels, const float *u8tab,
+                                                const RasterRec &r, const ShadeRec *__restrict__ sp, float x, float y,
+                                                float *depth_out, float *opacity_out) {
     const Edge e_bc = make_edge(r.bx, r.by, r.cx, r.cy), e_ca = make_edge(r.cx, r.cy, r.ax, r.ay),
                e_ab = make_edge(r.ax, r.ay, r.bx, r.by);
     const float alpha = FDIV(edge_eval(e_bc, x, y), edge_eval(e_bc, r.ax, r.ay));
@@ -47,15 +56,18 @@ __device__ __forceinline__ uint32_t shade_pixel(const SceneDev &S, const RasterR
     const v3 H{INTERP(18, 0, 3), INTERP(18, 1, 3), INTERP(18, 2, 3)};
     const float u = INTERP(27, 0, 2), v = INTERP(27, 1, 2);
 #undef INTERP
-    const uint32_t material = __float_as_uint(w[33]);
-    const MaterialDev *m = S.materials + material;
-    const v3 ka{__ldg(&m->ka[0]), __ldg(&m->ka[1]), __ldg(&m->ka[2])};
-    const v3 kd{__ldg(&m->kd[0]), __ldg(&m->kd[1]), __ldg(&m->kd[2])};
-    const v3 ks{__ldg(&m->ks[0]), __ldg(&m->ks[1]), __ldg(&m->ks[2])};
-    *opacity_out = __ldg(&m->alpha);
+    // MaterialDev as 4 x uint4: ka3 kd1 | kd2 ks3 | alpha ka_off ka_w ka_h | kd_off kd_w kd_h pad
+    const uint4 *mq = reinterpret_cast<const uint4 *>(materials + __float_as_uint(w[33]));
+    const uint4 m0 = __ldg(mq), m1 = __ldg(mq + 1), m2 = __ldg(mq + 2), m3 = __ldg(mq + 3);
+    const v3 ka{__uint_as_float(m0.x), __uint_as_float(m0.y), __uint_as_float(m0.z)};
+    const v3 kd{__uint_as_float(m0.w), __uint_as_float(m1.x), __uint_as_float(m1.y)};
+    const v3 ks{__uint_as_float(m1.z), __uint_as_float(m1.w), __uint_as_float(m2.x)};
+    *opacity_out = __uint_as_float(m2.y);
 
-    const v3 dcol = fetch_texel(S.texels, __ldg(&m->kd_off), __ldg(&m->kd_w), __ldg(&m->kd_h), __ldg(&m->kd_comp), u, v);
-    const v3 acol = fetch_texel(S.texels, __ldg(&m->ka_off), __ldg(&m->ka_w), __ldg(&m->ka_h), __ldg(&m->ka_comp), u, v);
+    const uint32_t dt = fetch_texel(texels, m3.x, m3.y, m3.z, u, v); // map_kd   canvas.rs:689-691
+    const uint32_t at = fetch_texel(texels, m2.z, m2.w, m3.w, u, v); // map_ka   canvas.rs:693-695
+    const v3 dcol{u8tab[dt & 255u], u8tab[(dt >> 8) & 255u], u8tab[(dt >> 16) & 255u]};
+    const v3 acol{u8tab[at & 255u], u8tab[(at >> 8) & 255u], u8tab[(at >> 16) & 255u]};
 
     // canvas.rs:732-739
     const v3 c_r{FMUL(dcol.x, kd.x), FMUL(dcol.y, kd.y), FMUL(dcol.z, kd.z)};

@@ -190,6 +190,13 @@ int draw_canvas_set_stream(draw_canvas *canvas, void *cuda_stream);
  * y0 and y1 must be multiples of the tile height (draw_tile_size, 32) or equal to height. */
 int draw_canvas_set_stripe(draw_canvas *canvas, size_t y0, size_t y1);
 int draw_tile_size(void);
+/* Peer access for the fused sort-first gather (one process per GPU): the owner exports its
+ * canvas' own colour buffer as a 64-byte CUDA IPC handle; another process on the same node opens
+ * it (peer access is enabled lazily) and passes the pointer to draw_canvas_bind_external, so that
+ * its tile kernel stores pixels straight into the owner's framebuffer over NVLink. */
+int draw_canvas_ipc_export(draw_canvas *canvas, uint8_t handle[64]);
+int draw_ipc_open(const uint8_t handle[64], void **out_dev_ptr);
+int draw_ipc_close(void *dev_ptr);
 
 /* ---- Object loader (object.rs:73-454), host only ------------------------------------- */
 /* Object::load_from_file :106.  Texture images referenced by the MTL are decoded by the

@@ -20,19 +20,14 @@ for name in sys.argv[1:] or ["c3"]:
         s.render(c)
         s.render(c)
         cyc = s.debug_tile_cycles(c)
-        coarse, fine = s.debug_list_counts(c)
-        tx = (cfg["W"] + 63) // 64
-        finemax = fine.reshape(-1, tx * 4)
+        coarse, medium, fine = s.debug_list_counts(c)
         order = np.argsort(cyc)[::-1][:8]
-        print("  slowest tiles (cycles, coarse n, fine n of its 8 warps):")
-        for t in order:
-            ty, txx = divmod(int(t), tx)
-            f = finemax[ty * 2:ty * 2 + 2, txx * 4:txx * 4 + 4].reshape(-1)
-            print("   ", int(cyc[t]), int(coarse[t]), f.tolist())
+        print("  slowest tiles (cycles, large n, medium n, small n):", [(int(cyc[t]), int(coarse[t]), int(medium[t]), int(fine[t])) for t in order])
         print("  cycles p50/p90/p99/max", [int(np.percentile(cyc, p)) for p in (50, 90, 99, 100)], "sum", int(cyc.sum()),
               "empty-tile median", int(np.median(cyc[(coarse == 0)])))
         st = c.last_frame_stats()
         q = lambda a: [int(np.percentile(a, p)) for p in (50, 90, 99, 100)]
         print(name, "records", st["setup_records"], "refs", st["tile_refs"],
+              "| medium lists: nonempty", int((medium > 0).sum()), "sum", int(medium.sum()), "max", int(medium.max()),
               "| coarse lists: nonempty", int((coarse > 0).sum()), "of", coarse.size, "sum", int(coarse.sum()), "p50/90/99/max", q(coarse[coarse > 0]) if (coarse > 0).any() else None,
               "| fine lists: nonempty", int((fine > 0).sum()), "of", fine.size, "sum", int(fine.sum()), "p50/90/99/max", q(fine[fine > 0]) if (fine > 0).any() else None)
