@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdraw_b200.so")
+# DRAW_B200_LIB selects an experimental build variant (python -m draw_b200.build -D... --out=...)
+LIB_PATH = os.environ.get("DRAW_B200_LIB") or os.path.join(_HERE, "libdraw_b200.so")
 
 
 class DrawError(RuntimeError):

@@ -272,9 +272,9 @@ class Scene:
             return None
         nc = C.c_size_t()
         N.check(N.lib().draw_scene_debug_list_counts(self._h, canvas._h, None, 0, C.byref(nc)))
-        out = np.empty(nc.value, np.uint32)
-        N.check(N.lib().draw_scene_debug_tile_cycles(self._h, canvas._h, 1 if enable else 0, out.ctypes.data, nc.value))
-        return out
+        out = np.zeros(nc.value * 3, np.uint32)
+        N.check(N.lib().draw_scene_debug_tile_cycles(self._h, canvas._h, 1 if enable else 0, out.ctypes.data, nc.value * 3))
+        return out.reshape(3, nc.value)  # rows: whole CTA, end of phase A, end of phase B (cycles since CTA start)
 
     def counts(self):
         a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()

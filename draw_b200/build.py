@@ -37,15 +37,18 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
-        return LIB
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines / out build an experimental variant (e.g. another tile size) next to the default library;
+    select it at run time with DRAW_B200_LIB=<path>."""
+    lib = out or LIB
+    if not force and not defines and up_to_date():
+        return lib
     objs = []
-    build_dir = os.path.join(HERE, "build")
+    build_dir = os.path.join(HERE, "build", os.path.basename(lib))
     os.makedirs(build_dir, exist_ok=True)
     for src in SOURCES:
         obj = os.path.join(build_dir, src + ".o")
-        cmd = [nvcc_path(), *NVCC_FLAGS, "-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc_path(), *NVCC_FLAGS, *defines, "-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose and src.endswith(".cu"):
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -55,13 +58,15 @@ def build(force=False, verbose=False):
             raise RuntimeError(f"nvcc failed on {src}")
         objs.append(obj)
     cmd = [nvcc_path(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
-           "-o", LIB, *objs]
+           "-o", lib, *objs]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:
         sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
         raise RuntimeError("link failed")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, out=outs[0] if outs else None))

@@ -130,7 +130,8 @@ __device__ __forceinline__ TriEdges prepare_edges(const RasterRec &r) {
 // value fl(fl(fl(cx*x + cy*y) + k1) - k2) is a monotone function of x and of y because every
 // rounding step is monotone, so its maximum over the rectangle sits at the corner selected by
 // the coefficient signs; if that corner fails an edge test, every pixel of the rectangle fails.
-__device__ __forceinline__ bool rect_may_cover(const TriEdges &t, float lx, float hx, float ly, float hy) {
+template <typename Tri> // TriEdges or any struct with the same ecx / ecy / ek1 / ek2 / flags members
+__device__ __forceinline__ bool rect_may_cover(const Tri &t, float lx, float hx, float ly, float hy) {
     if (t.flags & TRI_SLOW) return true;
     bool any = true;
 #pragma unroll

@@ -11,8 +11,14 @@ namespace drawb200 {
 //   medium  list id = n_coarse + tile       <= MEDIUM_AREA px: one record per warp, lane per pixel
 //   small   list id = 2 * n_coarse + tile   <= SMALL_AREA px : one record per lane
 // REGION is the square each warp owns during the large-record phase (8 pixels per lane).
-constexpr int TILE_W = 64, TILE_H = 32, REGION = 16;
-constexpr int SMALL_AREA = 64, MEDIUM_AREA = 1024;
+#ifndef DRAW_TILE_W
+#define DRAW_TILE_W 64
+#endif
+#ifndef DRAW_TILE_H
+#define DRAW_TILE_H 32
+#endif
+constexpr int TILE_W = DRAW_TILE_W, TILE_H = DRAW_TILE_H, REGION = 16;
+constexpr int SMALL_AREA = 8, MEDIUM_AREA = 1024;
 constexpr int LISTS_PER_TILE = 3;
 constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
 

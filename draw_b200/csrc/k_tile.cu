@@ -8,9 +8,10 @@
 //            a 4x1 pixel block (warp = 16x8 region) and tests it against each triangle, after a
 //            warp-level bbox reject and an exact block-level edge reject.  Depth/winner in registers.
 //   merge    each lane publishes its 8 pixels as 64-bit keys (depth, slot) in shared memory.
-//   phase B  "medium" list (bbox in the tile <= 1024 px): one triangle per warp, the lanes sweep the
-//            bbox in 8x4 blocks (exact block reject first); "small" list (<= 64 px): one triangle per
-//            lane.  Covered fragments are committed with a shared-memory atomicMin on the key.
+//   phase B  "medium" list (bbox in the tile <= 1024 px): a coarse pass tests every 8x4 block of every
+//            triangle's bbox (one thread per block, exact test) and queues the blocks that can be
+//            covered; a fine pass takes queued blocks, one pixel per lane.  "small" list (<= 8 px): one
+//            triangle per lane.  Covered fragments are committed with a shared-memory atomicMin on the key.
 //   phase C  deferred shading, one pixel per lane per step: only the winner of a pixel is shaded
 //            (canvas.rs:685-743); the key becomes (exact depth, draw id), colour goes to smem.
 //   phase D  transparent triangles in draw order, blended over the shaded colour (rare).
@@ -124,8 +125,6 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ F
     const long long t_start = W.tile_cycles ? clock64() : 0;
     const int tx0 = (int)tile_x * TILE_W, ty0 = (int)tile_y * TILE_H;
 
-    fill_u8_table(u8tab, tid, TILE_THREADS); // visible after the barrier that ends phase A
-
     const bool usable = W.counters[2] == 0;
     const uint32_t l_begin = usable ? W.list_offset[tile] : 0u;
     const uint32_t l_count = usable ? W.list_count[tile] : 0u; // the fill cursor ends at the count
@@ -136,10 +135,36 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ F
     const RasterRec *__restrict__ rrec = W.rrec;
     const float depth_max = U.depth_max;
 
+    // ---- empty tile: nothing to rasterise, write the clear colour and depth (canvas.rs:425-433) ----
+    if (l_count + m_count + s_count == 0 && (S.n_transparent == 0 || !usable)) {
+        const int W_ = (int)U.canvas_w, H_ = (int)U.canvas_h;
+        const uint32_t clear_px = 255u | (186u << 8) | (155u << 16) | (255u << 24); // memory order b g r pad
+        if ((W_ & 3) == 0) {
+            for (int q = tid; q < TILE_PIXELS / 4; q += TILE_THREADS) { // 4 pixels (16 B) per store
+                const int x = tx0 + (q & (TILE_W / 4 - 1)) * 4, y = ty0 + q / (TILE_W / 4);
+                if (x >= W_ || y >= H_) continue;
+                *reinterpret_cast<uint4 *>(color + ((size_t)(H_ - 1 - y) * W_ + x) * 4) =
+                    make_uint4(clear_px, clear_px, clear_px, clear_px);
+                *reinterpret_cast<float4 *>(depth + (size_t)y * W_ + x) = make_float4(depth_max, depth_max, depth_max, depth_max);
+            }
+        } else {
+            for (int p = tid; p < TILE_PIXELS; p += TILE_THREADS) {
+                const int x = tx0 + (p & (TILE_W - 1)), y = ty0 + p / TILE_W;
+                if (x >= W_ || y >= H_) continue;
+                reinterpret_cast<uint32_t *>(color)[(size_t)(H_ - 1 - y) * W_ + x] = clear_px;
+                depth[(size_t)y * W_ + x] = depth_max;
+            }
+        }
+        if (W.tile_cycles && tid == 0) W.tile_cycles[tile] = (uint32_t)(clock64() - t_start);
+        return;
+    }
+    fill_u8_table(u8tab, tid, TILE_THREADS); // visible after the barrier that ends phase A
+
     // ---- phase A: large triangles, every lane tests its own 4x2 block ------------------------------
     {
         // warp -> 16x16 region, lane -> 4x2 block (canvas coordinates: x right, y = depth-buffer row)
-        const int rx0 = tx0 + (warp & 3) * REGION, ry0 = ty0 + (warp >> 2) * REGION_H;
+        constexpr int WARPS_X = TILE_W / REGION;
+        const int rx0 = tx0 + (warp % WARPS_X) * REGION, ry0 = ty0 + (warp / WARPS_X) * REGION_H;
         const int bx0 = rx0 + (lane & 3) * 4, by0 = ry0 + (lane >> 2) * BLK_H;
         const float fx0 = (float)rx0, fy0 = (float)ry0, fx1 = fx0 + (float)(REGION - 1), fy1 = fy0 + (float)(REGION_H - 1);
         float xf[4], yf[BLK_H];
@@ -237,39 +262,96 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ F
     }
     __syncthreads();
 
-    // ---- phase B1: medium triangles, one per warp; lanes sweep the bbox in 8x4 pixel blocks --------
+    if (W.tile_cycles && tid == 0) W.tile_cycles[U.n_coarse + tile] = (uint32_t)(clock64() - t_start); // end of phase A
+    // ---- phase B1: medium triangles -------------------------------------------------------------------
+    // Per chunk of 64 triangles: (1) one thread per triangle stages it and counts the 8x4-pixel blocks of
+    // its bbox inside the tile; (2) coarse raster: one thread per (triangle, block) runs the exact block
+    // test and queues the blocks that can be covered; (3) fine raster: warps take queued blocks, one
+    // pixel per lane, and commit covered fragments with atomicMin on the key.
     {
-        const float dxf = (float)(lane & 7), dyf = (float)(lane >> 3);
+        __shared__ uint16_t queue[CHUNK * (TILE_W / 8) * (TILE_H / 4)]; // item = tri | bx << 6 | by << 9
+        __shared__ uint32_t blk_prefix[CHUNK + 1];
+        __shared__ uint32_t q_count;
+        const float tx0f = (float)tx0, ty0f = (float)ty0, tx1f = (float)(tx0 + TILE_W - 1), ty1f = (float)(ty0 + TILE_H - 1);
 #pragma unroll 1
-        for (uint32_t i = (uint32_t)warp; i < m_count; i += TILE_THREADS / 32) {
-            const uint32_t slot = W.list_refs[m_begin + i];
-            const RasterRec r = load_raster(rrec + slot); // same address in every lane: one broadcast load
-            const TriEdges t = prepare_edges(r);
-            const int lx = max((int)(r.bbx & 0xFFFF), tx0), hx = min((int)(r.bbx >> 16), tx0 + TILE_W - 1);
-            const int ly = max((int)(r.bby & 0xFFFF), ty0), hy = min((int)(r.bby >> 16), ty0 + TILE_H - 1);
-            const float lxf = (float)lx, hxf = (float)hx, hyf = (float)hy;
-            float byf = (float)ly;
-#pragma unroll 1
-            for (int by = ly; by <= hy; by += 4, byf = FADD(byf, 4.0f)) {
-                float bxf = lxf;
-#pragma unroll 1
-                for (int bx = lx; bx <= hx; bx += 8, bxf = FADD(bxf, 8.0f)) {
-                    // exact block-level reject (warp-uniform)
-                    if (!rect_may_cover(t, bxf, fminf(FADD(bxf, 7.0f), hxf), byf, fminf(FADD(byf, 3.0f), hyf))) continue;
-                    const float x = FADD(bxf, dxf), y = FADD(byf, dyf);
-                    if (x > hxf || y > hyf) continue;
-                    float d;
-                    if (!cover_pixel(t.ecx, t.ecy, t.ek1, t.ek2, t.f, t.flags, r.da, r.db, r.dc, x, y, d)) continue;
-                    if (!(d < depth_max)) continue;
-                    const unsigned long long key = make_key(d, slot);
-                    unsigned long long *cell = &keys[(by + (lane >> 3) - ty0) * TILE_W + (bx + (lane & 7) - tx0)];
-                    if (key < *cell) atomicMin(cell, key);
+        for (uint32_t base = 0; base < m_count; base += CHUNK) {
+            const uint32_t n = min((uint32_t)CHUNK, m_count - base);
+            __syncthreads();
+            if ((uint32_t)tid < n) {
+                const uint32_t slot = W.list_refs[m_begin + base + tid];
+                stage_triangle(staged + tid, rrec + slot, slot);
+                const StagedTri &t = staged[tid];
+                const float w = FSUB(fminf(t.x1, tx1f), fmaxf(t.x0, tx0f)), h = FSUB(fminf(t.y1, ty1f), fmaxf(t.y0, ty0f));
+                blk_prefix[tid + 1] = ((uint32_t)w / 8u + 1u) * ((uint32_t)h / 4u + 1u); // blocks of 8x4 from the bbox corner
+            }
+            if (tid == 0) {
+                blk_prefix[0] = 0;
+                q_count = 0;
+            }
+            __syncthreads();
+            if (warp == 0) { // inclusive scan of the (up to 64) block counts
+                uint32_t a = lane < n ? blk_prefix[lane + 1] : 0u, b = lane + 32 < n ? blk_prefix[lane + 33] : 0u;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t ua = __shfl_up_sync(0xFFFFFFFFu, a, d), ub = __shfl_up_sync(0xFFFFFFFFu, b, d);
+                    if (lane >= d) { a += ua; b += ub; }
                 }
+                b += __shfl_sync(0xFFFFFFFFu, a, 31);
+                if (lane < n) blk_prefix[lane + 1] = a;
+                if (lane + 32 < n) blk_prefix[lane + 33] = b;
+            }
+            __syncthreads();
+            // (2) coarse raster
+            const uint32_t total = blk_prefix[n];
+#pragma unroll 1
+            for (uint32_t pbase = 0; pbase < total; pbase += TILE_THREADS) {
+                const uint32_t p = pbase + tid;
+                bool hit = false;
+                uint32_t item = 0;
+                if (p < total) {
+                    uint32_t lo = 0, hi = n; // largest k with blk_prefix[k] <= p
+                    while (hi - lo > 1) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (blk_prefix[mid] <= p) lo = mid; else hi = mid;
+                    }
+                    const StagedTri &t = staged[lo];
+                    const float lx = fmaxf(t.x0, tx0f), hx = fminf(t.x1, tx1f), ly = fmaxf(t.y0, ty0f), hy = fminf(t.y1, ty1f);
+                    const uint32_t nbx = (uint32_t)FSUB(hx, lx) / 8u + 1u, local = p - blk_prefix[lo];
+                    const uint32_t bxi = local % nbx, byi = local / nbx;
+                    const float bx = FADD(lx, (float)(bxi * 8u)), by = FADD(ly, (float)(byi * 4u));
+                    hit = rect_may_cover(t, bx, fminf(FADD(bx, 7.0f), hx), by, fminf(FADD(by, 3.0f), hy));
+                    item = lo | (bxi << 6) | (byi << 9);
+                }
+                const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
+                uint32_t wbase = 0;
+                if (lane == 0 && ballot) wbase = atomicAdd(&q_count, (uint32_t)__popc(ballot));
+                wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+                if (hit) queue[wbase + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)item;
+            }
+            __syncthreads();
+            // (3) fine raster
+            const uint32_t nq = q_count;
+            const float dxf = (float)(lane & 7), dyf = (float)(lane >> 3);
+#pragma unroll 1
+            for (uint32_t j = (uint32_t)warp; j < nq; j += TILE_THREADS / 32) {
+                const uint32_t item = queue[j];
+                const StagedTri &t = staged[item & 63u];
+                const float lx = fmaxf(t.x0, tx0f), hx = fminf(t.x1, tx1f), ly = fmaxf(t.y0, ty0f), hy = fminf(t.y1, ty1f);
+                const float x = FADD(FADD(lx, (float)(((item >> 6) & 7u) * 8u)), dxf);
+                const float y = FADD(FADD(ly, (float)((item >> 9) * 4u)), dyf);
+                if (x > hx || y > hy) continue;
+                float d;
+                if (!cover_pixel(t.ecx, t.ecy, t.ek1, t.ek2, t.f, t.flags, t.da, t.db, t.dc, x, y, d)) continue;
+                if (!(d < depth_max)) continue;
+                const unsigned long long key = make_key(d, t.slot);
+                unsigned long long *cell = &keys[(int)FSUB(y, ty0f) * TILE_W + (int)FSUB(x, tx0f)];
+                if (key < *cell) atomicMin(cell, key);
             }
         }
     }
     // ---- phase B2: small triangles, one per lane, atomicMin on the key --------------------------
-    for (uint32_t i = (uint32_t)tid; i < s_count; i += TILE_THREADS) {
+    // (item j of a round goes to lane j / warps of warp j % warps, so a short list spreads over all warps)
+    for (uint32_t i = (uint32_t)(lane * (TILE_THREADS / 32) + warp); i < s_count; i += TILE_THREADS) {
         const uint32_t slot = W.list_refs[s_begin + i];
         const RasterRec r = load_raster(rrec + slot);
         const TriEdges t = prepare_edges(r);
@@ -290,6 +372,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ F
     }
     __syncthreads();
 
+    if (W.tile_cycles && tid == 0) W.tile_cycles[2 * U.n_coarse + tile] = (uint32_t)(clock64() - t_start); // end of phase B
     // ---- phase C: deferred shading, fused clear ----------------------------------------------------
 #pragma unroll 1
     for (int it = 0; it < TILE_PIXELS / TILE_THREADS; it++) {

@@ -784,6 +784,7 @@ int draw_scene_debug_tile_cycles(draw_scene *scene, draw_canvas *canvas, int ena
     if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
     TRY(finish_frame(canvas));
     if (!scene->w_tile_cycles.ptr || n > scene->w_tile_cycles.cap) return fail(DRAW_ERR_INVALID_ARGUMENT, "no tile cycles recorded");
+    // layout: [tile] whole CTA, [n_tiles + tile] end of phase A, [2 n_tiles + tile] end of phase B
     CU(cudaMemcpy(out, scene->w_tile_cycles.ptr, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return DRAW_OK;
     GUARD_END

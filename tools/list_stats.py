@@ -19,10 +19,11 @@ for name in sys.argv[1:] or ["c3"]:
         s.debug_tile_cycles(enable=True)
         s.render(c)
         s.render(c)
-        cyc = s.debug_tile_cycles(c)
+        cyc3 = s.debug_tile_cycles(c)
+        cyc = cyc3[0]
         coarse, medium, fine = s.debug_list_counts(c)
         order = np.argsort(cyc)[::-1][:8]
-        print("  slowest tiles (cycles, large n, medium n, small n):", [(int(cyc[t]), int(coarse[t]), int(medium[t]), int(fine[t])) for t in order])
+        print("  slowest tiles (cycles, large n, medium n, small n):", [(int(cyc[t]), int(coarse[t]), int(medium[t]), int(fine[t]), "A/B/rest", int(cyc3[1][t]), int(cyc3[2][t]) - int(cyc3[1][t]), int(cyc[t]) - int(cyc3[2][t])) for t in order])
         print("  cycles p50/p90/p99/max", [int(np.percentile(cyc, p)) for p in (50, 90, 99, 100)], "sum", int(cyc.sum()),
               "empty-tile median", int(np.median(cyc[(coarse == 0)])))
         st = c.last_frame_stats()
