@@ -13,6 +13,31 @@
 
 namespace drawb200 {
 
+// Programmatic dependent launch: the frame's kernels are launched back to back on one stream with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel's CTAs may become resident
+// while the previous kernel drains.  Every kernel calls pdl_prologue() first: it lets its own
+// dependents launch early and then waits until the kernels it depends on have completed and their
+// writes are visible (griddepcontrol.wait), which preserves plain stream-order semantics for data.
+__device__ __forceinline__ void pdl_prologue() {
+#if __CUDA_ARCH__ >= 900
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();
+#endif
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 #define FADD(a, b) __fadd_rn((a), (b))
 #define FSUB(a, b) __fsub_rn((a), (b))
 #define FMUL(a, b) __fmul_rn((a), (b))

@@ -94,7 +94,9 @@ struct FrameDev {
     uint32_t *list_count;       // per list (large, medium, small per tile): count, then fill cursor [n_lists]
     uint32_t *list_offset;      // first entry of each list in list_refs [n_lists + 1]
     uint32_t *list_refs;        // record slots grouped by list [refs_cap]
-    uint32_t *counters;         // [0] records  [1] refs  [2] overflow bits  [3] k_setup CTA ticket
+    uint32_t *counters;         // [0] records  [1] refs  [2] overflow bits  [3] k_setup CTA ticket  [4] k_alloc CTAs done  [8]
+    uint32_t *tile_cost;        // estimated k_tile work per tile [n_coarse]
+    uint32_t *tile_order;       // tiles of the stripe, heaviest first [n_coarse]
     unsigned long long *scan_desc; // k_setup chained-scan descriptors [ceil(n_triangles / 256)]
     uint32_t rec_cap, refs_cap;
     uint32_t *tile_cycles;      // debug: SM cycles spent by each coarse tile's CTA (null = off) [n_coarse]

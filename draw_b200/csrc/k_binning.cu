@@ -4,7 +4,8 @@
 // it exists so that k_tile can keep a tile's colour and depth on chip and write HBM once.
 //
 //   k_bin<false>  per record  count the lists it belongs to
-//   k_alloc       per list    reserve a contiguous range of list_refs for every list
+//   k_alloc       per tile    reserve a contiguous range of list_refs for every list; order the tiles
+//                             heaviest first for k_tile
 //   k_bin<true>   per record  scatter its slot into those lists
 //
 // Every tile (64x32 px) has three lists (device_types.h), classed by the area of the record's bbox
@@ -60,6 +61,7 @@ __device__ __forceinline__ TileRange tile_range(const FrameUniforms &U, uint32_t
 
 template <bool FILL>
 __global__ void __launch_bounds__(BIN_THREADS) k_bin(const __grid_constant__ FrameUniforms U, const FrameDev W) {
+    pdl_prologue();
     if (FILL && W.counters[2] != 0) return; // a buffer overflowed: the host re-renders with larger buffers
     uint32_t n = W.counters[0];
     if (n > W.rec_cap) n = W.rec_cap;
@@ -117,19 +119,34 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const __grid_constant__ Fra
 }
 
 // ------------------------------------------------------------------------------------------
-// k_alloc : gives every list a contiguous range of list_refs.  Lists need not be laid out in
-// list order, so instead of a global scan each CTA scans its 256 counts locally and reserves its
-// total with one atomicAdd; list_count is reset to serve as the fill cursor (after k_bin<true> it
-// holds the count again, which is what k_tile reads).  total -> counters[1].
+// k_alloc : one thread per tile.
+//  (1) gives the tile's three lists a contiguous range of list_refs.  Lists need not be laid out in
+//      tile order, so instead of a global scan each CTA scans its 256 sums locally and reserves its
+//      total with one atomicAdd; list_count is reset to serve as the fill cursor (after k_bin<true> it
+//      holds the count again, which is what k_tile reads).  total -> counters[1].
+//  (2) orders the stripe's tiles by estimated work, heaviest first, so that k_tile (whose CTAs are
+//      dispatched in index order) starts its long tiles first and ends with the empty ones: the last
+//      CTA to finish (1) bucket-sorts the per-tile costs by their log2.
 // ------------------------------------------------------------------------------------------
 constexpr int ALLOC_THREADS = 256;
+constexpr uint32_t COST_NOT_IN_STRIPE = 0xFFFFFFFFu;
+constexpr int COST_BUCKETS = 34;
 
-__global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const FrameDev W, const uint32_t n_lists) {
+__device__ __forceinline__ int cost_bucket(uint32_t cost) { // 0 = heaviest ... COST_BUCKETS-1 = empty tile
+    return cost == 0 ? COST_BUCKETS - 1 : __clz(cost);      // clz in 0..31 (larger cost -> smaller clz)
+}
+
+__global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const __grid_constant__ FrameUniforms U, const FrameDev W) {
     __shared__ uint32_t warp_sum[ALLOC_THREADS / 32];
-    __shared__ uint32_t block_base;
+    __shared__ uint32_t block_base, is_last;
+    __shared__ uint32_t bucket_start[COST_BUCKETS];
+    pdl_prologue();
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t i = blockIdx.x * ALLOC_THREADS + tid;
-    const uint32_t c = i < n_lists ? W.list_count[i] : 0u;
+    const uint32_t tile = blockIdx.x * ALLOC_THREADS + tid, nc = U.n_coarse;
+    const bool valid = tile < nc;
+    const uint32_t c0 = valid ? W.list_count[tile] : 0u, c1 = valid ? W.list_count[nc + tile] : 0u,
+                   c2 = valid ? W.list_count[2 * nc + tile] : 0u;
+    const uint32_t c = c0 + c1 + c2;
 
     uint32_t incl = c;
 #pragma unroll
@@ -151,9 +168,59 @@ __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const FrameDev W, const
         block_base = base;
     }
     __syncthreads();
-    if (i < n_lists) {
-        W.list_offset[i] = block_base + warp_sum[warp] + incl - c;
-        W.list_count[i] = 0; // becomes the fill cursor
+    if (valid) {
+        const uint32_t off = block_base + warp_sum[warp] + incl - c;
+        W.list_offset[tile] = off;
+        W.list_offset[nc + tile] = off + c0;
+        W.list_offset[2 * nc + tile] = off + c0 + c1;
+        W.list_count[tile] = 0; // become the fill cursors
+        W.list_count[nc + tile] = 0;
+        W.list_count[2 * nc + tile] = 0;
+        const uint32_t ty = tile / U.tiles_x;
+        // rough relative cost of a large / medium / small reference in k_tile
+        W.tile_cost[tile] = (ty >= U.tile_y_begin && ty < U.tile_y_end) ? 16u * c0 + 4u * c1 + c2 : COST_NOT_IN_STRIPE;
+    }
+    // ---- the last CTA orders the tiles ---------------------------------------------------------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = atomicAdd(&W.counters[4], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    for (int b = (int)tid; b < COST_BUCKETS; b += ALLOC_THREADS) bucket_start[b] = 0;
+    __syncthreads();
+    constexpr int BATCH = 8; // independent loads in flight per thread
+    for (uint32_t t0 = tid; t0 < nc; t0 += ALLOC_THREADS * BATCH) {
+        uint32_t cost[BATCH];
+#pragma unroll
+        for (int k = 0; k < BATCH; k++) {
+            const uint32_t t = t0 + k * ALLOC_THREADS;
+            cost[k] = t < nc ? __ldcg(&W.tile_cost[t]) : COST_NOT_IN_STRIPE;
+        }
+#pragma unroll
+        for (int k = 0; k < BATCH; k++)
+            if (cost[k] != COST_NOT_IN_STRIPE) atomicAdd(&bucket_start[cost_bucket(cost[k])], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (int b = 0; b < COST_BUCKETS; b++) {
+            const uint32_t n = bucket_start[b];
+            bucket_start[b] = run;
+            run += n;
+        }
+    }
+    __syncthreads();
+    for (uint32_t t0 = tid; t0 < nc; t0 += ALLOC_THREADS * BATCH) {
+        uint32_t cost[BATCH];
+#pragma unroll
+        for (int k = 0; k < BATCH; k++) {
+            const uint32_t t = t0 + k * ALLOC_THREADS;
+            cost[k] = t < nc ? __ldcg(&W.tile_cost[t]) : COST_NOT_IN_STRIPE;
+        }
+#pragma unroll
+        for (int k = 0; k < BATCH; k++)
+            if (cost[k] != COST_NOT_IN_STRIPE)
+                W.tile_order[atomicAdd(&bucket_start[cost_bucket(cost[k])], 1u)] = t0 + k * ALLOC_THREADS;
     }
 }
 
@@ -162,13 +229,13 @@ __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const FrameDev W, const
 // ------------------------------------------------------------------------------------------
 static int bin_blocks(const FrameDev &) { return 148 * 4; }
 void launch_bin_count(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream) {
-    k_bin<false><<<bin_blocks(W), BIN_THREADS, 0, stream>>>(U, W);
+    launch_pdl(k_bin<false>, bin_blocks(W), BIN_THREADS, stream, U, W);
 }
 void launch_alloc(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream) {
-    k_alloc<<<(U.n_lists + ALLOC_THREADS - 1) / ALLOC_THREADS, ALLOC_THREADS, 0, stream>>>(W, U.n_lists);
+    launch_pdl(k_alloc, (U.n_coarse + ALLOC_THREADS - 1) / ALLOC_THREADS, ALLOC_THREADS, stream, U, W);
 }
 void launch_bin_fill(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream) {
-    k_bin<true><<<bin_blocks(W), BIN_THREADS, 0, stream>>>(U, W);
+    launch_pdl(k_bin<true>, bin_blocks(W), BIN_THREADS, stream, U, W);
 }
 
 } // namespace drawb200

@@ -17,10 +17,11 @@ namespace drawb200 {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FrameUniforms U, const SceneDev S,
                                                 const FrameDev W) {
+    pdl_prologue();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     // per-frame reset of the binning state (the binning kernels run after this one on the same stream)
     for (uint32_t t = i; t < U.n_lists; t += gridDim.x * blockDim.x) W.list_count[t] = 0;
-    if (i < 4) W.counters[i] = 0;
+    if (i < 8) W.counters[i] = 0;
     const uint32_t n_desc = (S.n_triangles + 255) / 256;
     for (uint32_t t = i; t < n_desc; t += gridDim.x * blockDim.x) W.scan_desc[t] = 0ull;
     if (i >= S.n_vertices) return;
@@ -296,6 +297,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
                                                          const FrameDev W) {
     __shared__ uint32_t warp_tot[SETUP_THREADS / 32];
     __shared__ uint32_t s_ticket, s_base;
+    pdl_prologue();
 
     if (threadIdx.x == 0) s_ticket = atomicAdd(&W.counters[3], 1u);
     __syncthreads();
@@ -474,12 +476,12 @@ void launch_vertex(const FrameUniforms &U, const SceneDev &S, const FrameDev &W,
     const uint32_t by_vertex = (S.n_vertices + 255) / 256, by_list = (U.n_lists + 255) / 256;
     uint32_t blocks = by_vertex > 1 ? by_vertex : 1;
     if (blocks < by_list && blocks < 148 * 4) blocks = by_list < 148 * 4 ? by_list : 148 * 4;
-    k_vertex<<<blocks, 256, 0, stream>>>(U, S, W);
+    launch_pdl(k_vertex, blocks, 256, stream, U, S, W);
 }
 
 void launch_setup(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, cudaStream_t stream) {
     if (!S.n_triangles) return;
-    k_setup<<<(S.n_triangles + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, stream>>>(U, S, W);
+    launch_pdl(k_setup, (S.n_triangles + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, stream, U, S, W);
 }
 
 } // namespace drawb200

@@ -117,21 +117,22 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ F
     __shared__ uint32_t colour[TILE_PIXELS];         // r | g << 8 | b << 16 | pad << 24
     __shared__ StagedTri staged[CHUNK];
     __shared__ float u8tab[256]; // (u8 as f32) / 255.0
+    pdl_prologue();
 
-    const uint32_t tile_x = blockIdx.x % U.tiles_x;
-    const uint32_t tile_y = U.tile_y_begin + blockIdx.x / U.tiles_x;
-    const uint32_t tile = tile_y * U.tiles_x + tile_x;
+    const uint32_t tile = W.tile_order[blockIdx.x]; // heaviest tiles first (k_alloc)
+    const uint32_t tile_x = tile % U.tiles_x, tile_y = tile / U.tiles_x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long t_start = W.tile_cycles ? clock64() : 0;
     const int tx0 = (int)tile_x * TILE_W, ty0 = (int)tile_y * TILE_H;
 
-    const bool usable = W.counters[2] == 0;
-    const uint32_t l_begin = usable ? W.list_offset[tile] : 0u;
-    const uint32_t l_count = usable ? W.list_count[tile] : 0u; // the fill cursor ends at the count
-    const uint32_t m_begin = usable ? W.list_offset[U.n_coarse + tile] : 0u;
-    const uint32_t m_count = usable ? W.list_count[U.n_coarse + tile] : 0u;
-    const uint32_t s_begin = usable ? W.list_offset[2 * U.n_coarse + tile] : 0u;
-    const uint32_t s_count = usable ? W.list_count[2 * U.n_coarse + tile] : 0u;
+    // (loads issued together; masked afterwards so that they do not wait for the overflow flag)
+    const uint32_t overflow = W.counters[2];
+    const uint32_t l_begin = W.list_offset[tile], m_begin = W.list_offset[U.n_coarse + tile],
+                   s_begin = W.list_offset[2 * U.n_coarse + tile];
+    uint32_t l_count = W.list_count[tile], m_count = W.list_count[U.n_coarse + tile],
+             s_count = W.list_count[2 * U.n_coarse + tile]; // the fill cursors end at the counts
+    const bool usable = overflow == 0;
+    if (!usable) l_count = m_count = s_count = 0;
     const RasterRec *__restrict__ rrec = W.rrec;
     const float depth_max = U.depth_max;
 
@@ -463,7 +464,7 @@ __global__ void __launch_bounds__(256) k_fill_u32(uint32_t *__restrict__ dst, si
 void launch_tile(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, uint8_t *color, float *depth,
                  cudaStream_t stream) {
     const uint32_t stripe_tiles = (U.tile_y_end - U.tile_y_begin) * U.tiles_x;
-    if (stripe_tiles) k_tile<<<stripe_tiles, TILE_THREADS, 0, stream>>>(U, S, W, color, depth);
+    if (stripe_tiles) launch_pdl(k_tile, stripe_tiles, TILE_THREADS, stream, U, S, W, color, depth);
 }
 
 cudaError_t launch_clear(uint8_t *color, float *depth, size_t n_pixels, float depth_max, cudaStream_t stream,

@@ -141,7 +141,7 @@ struct draw_scene {
 
     // per-frame work buffers
     DevBuf<float> w_vert[9];
-    DevBuf<uint32_t> w_flags, w_list_count, w_list_offset, w_refs, w_counters, w_tile_cycles;
+    DevBuf<uint32_t> w_flags, w_list_count, w_list_offset, w_refs, w_counters, w_tile_cycles, w_tile_cost, w_tile_order;
     bool debug_tile_cycles = false;
     DevBuf<unsigned long long> w_scan_desc;
     DevBuf<RasterRec> w_rrec, w_trrec;
@@ -299,7 +299,9 @@ int ensure_work_buffers(draw_scene *s, size_t n_lists) {
     TRY(s->w_list_count.reserve(n_lists));
     TRY(s->w_list_offset.reserve(n_lists + 1));
     TRY(s->w_refs.reserve(s->refs_cap));
-    TRY(s->w_counters.reserve(4));
+    TRY(s->w_counters.reserve(8));
+    TRY(s->w_tile_cost.reserve(n_lists));
+    TRY(s->w_tile_order.reserve(n_lists));
     TRY(s->w_scan_desc.reserve((size_t)d.n_triangles / 256 + 2));
     FrameDev &w = s->work;
     w.v_lx = s->w_vert[0].ptr; w.v_ly = s->w_vert[1].ptr; w.v_lz = s->w_vert[2].ptr;
@@ -310,6 +312,8 @@ int ensure_work_buffers(draw_scene *s, size_t n_lists) {
     w.t_rrec = s->w_trrec.ptr; w.t_srec = s->w_tsrec.ptr;
     w.list_count = s->w_list_count.ptr; w.list_offset = s->w_list_offset.ptr; w.list_refs = s->w_refs.ptr;
     w.counters = s->w_counters.ptr;
+    w.tile_cost = s->w_tile_cost.ptr;
+    w.tile_order = s->w_tile_order.ptr;
     w.scan_desc = s->w_scan_desc.ptr;
     w.rec_cap = (uint32_t)s->rec_cap;
     w.refs_cap = (uint32_t)s->refs_cap;
