@@ -299,3 +299,63 @@ def set_device(index):
 
 def tile_size():
     return N.lib().draw_tile_size()
+
+
+def load_obj(path, decode_images=True):
+    """Object::load_from_file (scene/object.rs:106) through the library's C++ loader
+    (draw_object_load_obj).  Texture files named by the MTL are decoded with PIL when
+    decode_images is true (the reference uses stb_image), else maps stay at the 1x1 default."""
+    from .model import IndexedMesh, Texture
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.malloc.argtypes = [C.c_size_t]
+
+    def _decode(cpath, _user, out_pixels, out_w, out_h, out_comp):
+        try:
+            from PIL import Image
+            im = Image.open(cpath.decode())
+            if im.mode != "RGBA":
+                im = im.convert("RGB")
+            a = np.ascontiguousarray(np.asarray(im, dtype=np.uint8))
+            buf = libc.malloc(a.size)
+            C.memmove(buf, a.ctypes.data, a.size)
+            out_pixels[0] = buf
+            out_w[0], out_h[0], out_comp[0] = a.shape[1], a.shape[0], a.shape[2]
+            return 0
+        except Exception:
+            return 1
+
+    cb = N.IMAGE_LOADER(_decode) if decode_images else None
+    handle = C.c_void_p()
+    N.check(N.lib().draw_object_load_obj(str(path).encode(), cb, None, C.byref(handle)))
+    try:
+        d = N.ObjectDesc()
+        N.check(N.lib().draw_object_desc_of(handle, C.byref(d)))
+
+        def arr(ptr, n, ctype, dtype, cols):
+            if n == 0:
+                return np.zeros((0, cols), dtype)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n * cols,)).astype(dtype, copy=True).reshape(n, cols)
+
+        meshes_c = C.cast(d.meshes, C.POINTER(N.Mesh))
+        mats_c = C.cast(d.materials, C.POINTER(N.Material))
+        meshes = [IndexedMesh((meshes_c[i].name or b"").decode(), arr(meshes_c[i].triangles, meshes_c[i].n_triangles, C.c_uint32, np.uint32, 9),
+                              int(meshes_c[i].material_idx)) for i in range(d.n_meshes)]
+        images = {}
+
+        def img(tm):
+            if not tm.pixels:
+                return None
+            if tm.pixels not in images:
+                n = tm.width * tm.height * tm.components
+                images[tm.pixels] = np.ctypeslib.as_array(C.cast(tm.pixels, C.POINTER(C.c_uint8)), shape=(n,)).copy().reshape(tm.height, tm.width, tm.components)
+            return images[tm.pixels]
+
+        textures = [Texture((mats_c[i].name or b"").decode(), np.array(mats_c[i].ka, np.float32), np.array(mats_c[i].kd, np.float32),
+                            np.array(mats_c[i].ks, np.float32), float(mats_c[i].alpha), img(mats_c[i].map_ka), img(mats_c[i].map_kd))
+                    for i in range(d.n_materials)]
+        return Object((d.name or b"").decode(), arr(d.positions, d.n_positions, C.c_float, np.float32, 3),
+                      arr(d.normals, d.n_normals, C.c_float, np.float32, 3), arr(d.uvs, d.n_uvs, C.c_float, np.float32, 3),
+                      meshes, textures)
+    finally:
+        N.lib().draw_object_free(handle)

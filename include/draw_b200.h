@@ -201,7 +201,9 @@ int draw_ipc_close(void *dev_ptr);
 /* ---- Object loader (object.rs:73-454), host only ------------------------------------- */
 /* Object::load_from_file :106.  Texture images referenced by the MTL are decoded by the
  * caller-supplied callback (the reference uses stb_image, scene/mod.rs:174-202, which is not
- * part of this library); a NULL callback leaves maps at the 1x1 default. */
+ * part of this library); a NULL callback leaves maps at the 1x1 default.  The callback returns 0 on
+ * success and hands over a malloc()ed buffer of width*height*components bytes (components 3 or 4, row 0
+ * = top); the library free()s it. */
 typedef int (*draw_image_loader)(const char *path, void *user, uint8_t **out_pixels, uint32_t *out_w,
                                  uint32_t *out_h, uint32_t *out_components);
 int draw_object_load_obj(const char *path, draw_image_loader loader, void *user, draw_object **out);
