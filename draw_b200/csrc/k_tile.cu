@@ -49,9 +49,24 @@ static_assert(BLK_H >= 1 && TILE_W / REGION * (TILE_H / REGION_H) * 32 == TILE_T
 struct StagedTri {
     float ecx[3], ecy[3], ek1[3], ek2[3], f[3];
     float da, db, dc;
+    float g[3];   // early depth reject: depth_i / f_i (approximate), see TRI_EARLYZ
+    float thr[3]; // tame triangles: edge e passes  <=>  value > thr[e]  (0, or -0.5 when the tie rule admits 0)
     float x0, x1, y0, y1;
     uint32_t flags, id, slot;
 };
+static_assert(sizeof(StagedTri) == 31 * 4, "31 words: odd stride keeps the staging writes conflict-free");
+
+// Early depth reject.  For a covered pixel of a tame triangle with finite non-negative vertex depths,
+//   D = e0*da/f0 + e1*db/f1 + e2*dc/f2                       (real arithmetic, all terms >= 0)
+// and the reference's float depth d_ref = fl(fl(fl(e0/f0)*da + fl(e1/f1)*db) + fl(e2/f2)*dc) satisfies
+// |d_ref - D| <= 4.1 u D (u = 2^-24: one division, one product and two sums of non-negative terms),
+// while d_app = fma(e2, g2, fma(e1, g1, e0*g0)) with g_i = fl(d_i * fl(1/f_i)) satisfies
+// |d_app - D| <= 5.1 u D.  Hence d_ref >= d_app * (1 - 9.3u) > d_app * (1 - 2^-20), so
+//   d_app * (1 - 2^-20) > z   ==>   d_ref > z :  the fragment fails the strict `<` test and is not a tie,
+// and its three IEEE divisions can be skipped.  The bounds need normal (not denormal) products, so the
+// flag is only set when every g_i is 0 or >= 1e-30; NaN/inf make the comparison false or d_ref = inf.
+constexpr uint32_t TRI_EARLYZ = 16u;
+constexpr float EARLYZ_SCALE = 0.99999904632568359375f; // 1 - 2^-20
 
 __device__ __forceinline__ void stage_triangle(StagedTri *dst, const RasterRec *src, uint32_t slot) {
     RasterRec r = load_raster(src);
@@ -66,9 +81,18 @@ __device__ __forceinline__ void stage_triangle(StagedTri *dst, const RasterRec *
         s.ecx[i] = t.ecx[i]; s.ecy[i] = t.ecy[i]; s.ek1[i] = t.ek1[i]; s.ek2[i] = t.ek2[i]; s.f[i] = t.f[i];
     }
     s.da = r.da; s.db = r.db; s.dc = r.dc;
+    const float dep[3] = {r.da, r.db, r.dc};
+    bool earlyz = !(t.flags & TRI_SLOW);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        s.thr[i] = (t.flags & (1u << i)) ? -0.5f : 0.0f; // edge values are integers: e >= 0 <=> e > -0.5
+        const float g = dep[i] * __frcp_rn(t.f[i]);
+        s.g[i] = g;
+        earlyz = earlyz && dep[i] >= 0.0f && dep[i] < 3.0e38f && (g == 0.0f || g >= 1e-30f);
+    }
     s.x0 = (float)(r.bbx & 0xFFFF); s.x1 = (float)(r.bbx >> 16);
     s.y0 = (float)(r.bby & 0xFFFF); s.y1 = (float)(r.bby >> 16);
-    s.flags = t.flags;
+    s.flags = t.flags | (earlyz ? TRI_EARLYZ : 0u);
     s.id = r.id;
     s.slot = slot;
 }
@@ -205,7 +229,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ F
                         const float cx = s.ecx[e], cy = s.ecy[e];
                         const float xm = cx >= 0.0f ? hi_x : lo_x, ym = cy >= 0.0f ? hi_y : lo_y;
                         const float em = FSUB(FADD(FADD(FMUL(cx, xm), FMUL(cy, ym)), s.ek1[e]), s.ek2[e]);
-                        any = any && (em > 0.0f || (em == 0.0f && (flags & (1u << e))));
+                        any = any && em > s.thr[e];
                     }
                     if (!any) continue;
                     float pxs[3][4], pys[3][BLK_H];
@@ -225,13 +249,14 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ F
                             const float e0 = FSUB(FADD(FADD(pxs[0][i], pys[0][j]), s.ek1[0]), s.ek2[0]);
                             const float e1 = FSUB(FADD(FADD(pxs[1][i], pys[1][j]), s.ek1[1]), s.ek2[1]);
                             const float e2 = FSUB(FADD(FADD(pxs[2][i], pys[2][j]), s.ek1[2]), s.ek2[2]);
-                            const bool in = (e0 > 0.0f || (e0 == 0.0f && (flags & 1u))) &&
-                                            (e1 > 0.0f || (e1 == 0.0f && (flags & 2u))) &&
-                                            (e2 > 0.0f || (e2 == 0.0f && (flags & 4u)));
-                            if (!in) continue;
+                            if (!(e0 > s.thr[0] && e1 > s.thr[1] && e2 > s.thr[2])) continue;
+                            const int p = j * 4 + i;
+                            // early depth reject (exactly conservative, see TRI_EARLYZ): skip the divisions
+                            if ((flags & TRI_EARLYZ) &&
+                                fmaf(e2, s.g[2], fmaf(e1, s.g[1], e0 * s.g[0])) * EARLYZ_SCALE > zb[p])
+                                continue;
                             const float alpha = FDIV(e0, s.f[0]), beta = FDIV(e1, s.f[1]), gama = FDIV(e2, s.f[2]);
                             const float d = FADD(FADD(FMUL(alpha, s.da), FMUL(beta, s.db)), FMUL(gama, s.dc)); // canvas.rs:682
-                            const int p = j * 4 + i;
                             // strict `<` (canvas.rs:923); on equal depth the earlier draw (smaller slot) stays
                             if (d < zb[p] || (d == zb[p] && slot < sl[p] && sl[p] != NO_SLOT)) {
                                 zb[p] = d;
@@ -341,11 +366,24 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ F
                 const float x = FADD(FADD(lx, (float)(((item >> 6) & 7u) * 8u)), dxf);
                 const float y = FADD(FADD(ly, (float)((item >> 9) * 4u)), dyf);
                 if (x > hx || y > hy) continue;
+                unsigned long long *cell = &keys[(int)FSUB(y, ty0f) * TILE_W + (int)FSUB(x, tx0f)];
                 float d;
-                if (!cover_pixel(t.ecx, t.ecy, t.ek1, t.ek2, t.f, t.flags, t.da, t.db, t.dc, x, y, d)) continue;
+                if (!(t.flags & TRI_SLOW)) {
+                    const float e0 = FSUB(FADD(FADD(FMUL(t.ecx[0], x), FMUL(t.ecy[0], y)), t.ek1[0]), t.ek2[0]);
+                    const float e1 = FSUB(FADD(FADD(FMUL(t.ecx[1], x), FMUL(t.ecy[1], y)), t.ek1[1]), t.ek2[1]);
+                    const float e2 = FSUB(FADD(FADD(FMUL(t.ecx[2], x), FMUL(t.ecy[2], y)), t.ek1[2]), t.ek2[2]);
+                    if (!(e0 > t.thr[0] && e1 > t.thr[1] && e2 > t.thr[2])) continue;
+                    // early depth reject in key space (exactly conservative, see TRI_EARLYZ)
+                    if ((t.flags & TRI_EARLYZ) &&
+                        depth_key(fmaf(e2, t.g[2], fmaf(e1, t.g[1], e0 * t.g[0])) * EARLYZ_SCALE) > (uint32_t)(*cell >> 32))
+                        continue;
+                    const float alpha = FDIV(e0, t.f[0]), beta = FDIV(e1, t.f[1]), gama = FDIV(e2, t.f[2]);
+                    d = FADD(FADD(FMUL(alpha, t.da), FMUL(beta, t.db)), FMUL(gama, t.dc)); // canvas.rs:682
+                } else if (!cover_pixel(t.ecx, t.ecy, t.ek1, t.ek2, t.f, t.flags, t.da, t.db, t.dc, x, y, d)) {
+                    continue;
+                }
                 if (!(d < depth_max)) continue;
                 const unsigned long long key = make_key(d, t.slot);
-                unsigned long long *cell = &keys[(int)FSUB(y, ty0f) * TILE_W + (int)FSUB(x, tx0f)];
                 if (key < *cell) atomicMin(cell, key);
             }
         }
