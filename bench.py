@@ -82,6 +82,15 @@ def load_workload(name):
     return cfg
 
 
+def ncu_traffic(kernel, config):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(kernel, {}).get(config)
+    except Exception:
+        return None
+
+
 def measured_peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -93,48 +102,58 @@ def measured_peak_hbm():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md).  NVML is polled
+    from a thread every ~2 ms (the timed region can be a few tens of ms, too short for nvidia-smi's
+    loop mode); falls back to one nvidia-smi query if pynvml is unavailable."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+               "hw_power_brake_slowdown": 0x80}
 
     def __init__(self, gpu_index):
-        self.gpu, self.proc = gpu_index, None
+        self.gpu, self.samples, self.reasons, self._stop, self._thread, self.max_mhz = gpu_index, [], set(), False, None, None
+
+    def _run(self, nv, h):
+        while not self._stop:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
+            import threading
+
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML indexes physical devices; honour CUDA_VISIBLE_DEVICES if it lists plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [int(x) for x in vis.split(",") if x.strip().isdigit()]
+            h = nv.nvmlDeviceGetHandleByIndex(ids[self.gpu] if self.gpu < len(ids) else self.gpu)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self._thread = threading.Thread(target=self._run, args=(nv, h), daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
+            self._thread = None
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self._thread is not None:
+            self._stop = True
+            self._thread.join(timeout=2)
+            sm = self.samples
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                    "sm_max_mhz": self.max_mhz, "samples": len(sm), "reasons": sorted(self.reasons), "source": "nvml, 2 ms poll"}
         try:
-            out, _ = self.proc.communicate(timeout=5)
+            out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                                  "-i", str(self.gpu)], capture_output=True, text=True, timeout=10).stdout
+            a, b2 = [float(x) for x in out.strip().split(",")]
+            return {"sm_mhz": a, "sm_max_mhz": b2, "samples": 1, "reasons": [], "source": "nvidia-smi after the run"}
         except Exception:
-            self.proc.kill()
-            out = ""
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["clock query unavailable"]}
 
 
 def dist_env():
@@ -383,7 +402,7 @@ def run_ours(args, cfg):
             "gpu_launches": launches,
             "kernel_ms": kmean,
             "roofline": {"bound": "hbm", "kernel": "k_tile", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": ncu_traffic("k_tile", args.config), "peak_source": peak_src,
                          "algo_bytes_per_launch": cfg["algo_bytes_tile_kernel"],
                          "frame_algo_bytes": cfg["algo_bytes_frame"], "frame_achieved": frame_gbs,
                          "frame_frac": frame_gbs / peak},

@@ -139,21 +139,28 @@ struct draw_scene {
     };
     std::vector<TransparentRange> transparent_ranges;
 
-    // per-frame work buffers
-    DevBuf<float> w_vert[9];
-    DevBuf<uint32_t> w_flags, w_list_count, w_list_offset, w_refs, w_counters, w_tile_cycles, w_tile_cost, w_tile_order;
+    // Per-frame work buffers, double-buffered: the vertex / setup / binning kernels of frame k+1 run on
+    // the scene's side stream while k_tile of frame k still runs on its canvas' stream.
+    struct WorkSet {
+        DevBuf<float> vert[9];
+        DevBuf<uint32_t> flags, list_count, list_offset, refs, counters, tile_cycles, tile_cost, tile_order;
+        DevBuf<unsigned long long> scan_desc;
+        DevBuf<RasterRec> rrec, trrec;
+        DevBuf<ShadeRec> srec, tsrec;
+        FrameDev work{};
+        cudaEvent_t geo_done = nullptr;  // side stream: binning of the frame using this set has finished
+        cudaEvent_t tile_done = nullptr; // canvas stream: k_tile of the frame using this set has finished
+        bool tile_pending = false;
+    };
+    WorkSet sets[2];
+    int next_set = 0, last_set = 0;
+    cudaStream_t side_stream = nullptr;
     bool debug_tile_cycles = false;
-    DevBuf<unsigned long long> w_scan_desc;
-    DevBuf<RasterRec> w_rrec, w_trrec;
-    DevBuf<ShadeRec> w_srec, w_tsrec;
     size_t rec_cap = 0, refs_cap = 0;
-    FrameDev work{};
-    cudaStream_t last_stream = nullptr;
-    cudaEvent_t last_done = nullptr;
-    bool has_last = false;
-    // optional per-kernel timing (draw_scene_set_kernel_timing)
+    // optional per-kernel timing (draw_scene_set_kernel_timing): 0..5 around the five side-stream kernels,
+    // 6 / 7 around k_tile on the canvas stream
     bool kernel_timing = false;
-    cudaEvent_t kev[N_FRAME_KERNELS + 1] = {};
+    cudaEvent_t kev[N_FRAME_KERNELS + 2] = {};
     bool kev_recorded = false;
 };
 
@@ -286,42 +293,44 @@ int upload_geometry(draw_scene *s) {
     return DRAW_OK;
 }
 
-int ensure_work_buffers(draw_scene *s, size_t n_lists) {
+int ensure_work_buffers(draw_scene *s, draw_scene::WorkSet &ws, size_t n_lists) {
     const SceneDev &d = s->dev;
-    for (int i = 0; i < 9; i++) TRY(s->w_vert[i].reserve(d.n_vertices));
-    TRY(s->w_flags.reserve(d.n_vertices));
+    for (int i = 0; i < 9; i++) TRY(ws.vert[i].reserve(d.n_vertices));
+    TRY(ws.flags.reserve(d.n_vertices));
     if (s->rec_cap == 0) s->rec_cap = 2 * (size_t)d.n_triangles + 1024;
     if (s->refs_cap == 0) s->refs_cap = std::max<size_t>((size_t)1 << 22, 4 * (size_t)d.n_triangles);
-    TRY(s->w_rrec.reserve(s->rec_cap));
-    TRY(s->w_srec.reserve(s->rec_cap));
-    TRY(s->w_trrec.reserve(4 * (size_t)d.n_transparent));
-    TRY(s->w_tsrec.reserve(4 * (size_t)d.n_transparent));
-    TRY(s->w_list_count.reserve(n_lists));
-    TRY(s->w_list_offset.reserve(n_lists + 1));
-    TRY(s->w_refs.reserve(s->refs_cap));
-    TRY(s->w_counters.reserve(8));
-    TRY(s->w_tile_cost.reserve(n_lists));
-    TRY(s->w_tile_order.reserve(n_lists));
-    TRY(s->w_scan_desc.reserve((size_t)d.n_triangles / 256 + 2));
-    FrameDev &w = s->work;
-    w.v_lx = s->w_vert[0].ptr; w.v_ly = s->w_vert[1].ptr; w.v_lz = s->w_vert[2].ptr;
-    w.v_hx = s->w_vert[3].ptr; w.v_hy = s->w_vert[4].ptr; w.v_hz = s->w_vert[5].ptr;
-    w.v_depth = s->w_vert[6].ptr; w.v_sx = s->w_vert[7].ptr; w.v_sy = s->w_vert[8].ptr;
-    w.v_flags = s->w_flags.ptr;
-    w.rrec = s->w_rrec.ptr; w.srec = s->w_srec.ptr;
-    w.t_rrec = s->w_trrec.ptr; w.t_srec = s->w_tsrec.ptr;
-    w.list_count = s->w_list_count.ptr; w.list_offset = s->w_list_offset.ptr; w.list_refs = s->w_refs.ptr;
-    w.counters = s->w_counters.ptr;
-    w.tile_cost = s->w_tile_cost.ptr;
-    w.tile_order = s->w_tile_order.ptr;
-    w.scan_desc = s->w_scan_desc.ptr;
+    TRY(ws.rrec.reserve(s->rec_cap));
+    TRY(ws.srec.reserve(s->rec_cap));
+    TRY(ws.trrec.reserve(4 * (size_t)d.n_transparent));
+    TRY(ws.tsrec.reserve(4 * (size_t)d.n_transparent));
+    TRY(ws.list_count.reserve(n_lists));
+    TRY(ws.list_offset.reserve(n_lists + 1));
+    TRY(ws.refs.reserve(s->refs_cap));
+    TRY(ws.counters.reserve(8));
+    TRY(ws.tile_cost.reserve(n_lists));
+    TRY(ws.tile_order.reserve(n_lists));
+    TRY(ws.scan_desc.reserve((size_t)d.n_triangles / 256 + 2));
+    FrameDev &w = ws.work;
+    w.v_lx = ws.vert[0].ptr; w.v_ly = ws.vert[1].ptr; w.v_lz = ws.vert[2].ptr;
+    w.v_hx = ws.vert[3].ptr; w.v_hy = ws.vert[4].ptr; w.v_hz = ws.vert[5].ptr;
+    w.v_depth = ws.vert[6].ptr; w.v_sx = ws.vert[7].ptr; w.v_sy = ws.vert[8].ptr;
+    w.v_flags = ws.flags.ptr;
+    w.rrec = ws.rrec.ptr; w.srec = ws.srec.ptr;
+    w.t_rrec = ws.trrec.ptr; w.t_srec = ws.tsrec.ptr;
+    w.list_count = ws.list_count.ptr; w.list_offset = ws.list_offset.ptr; w.list_refs = ws.refs.ptr;
+    w.counters = ws.counters.ptr;
+    w.tile_cost = ws.tile_cost.ptr;
+    w.tile_order = ws.tile_order.ptr;
+    w.scan_desc = ws.scan_desc.ptr;
     w.rec_cap = (uint32_t)s->rec_cap;
     w.refs_cap = (uint32_t)s->refs_cap;
     w.tile_cycles = nullptr;
     if (s->debug_tile_cycles) {
-        TRY(s->w_tile_cycles.reserve(n_lists));
-        w.tile_cycles = s->w_tile_cycles.ptr;
+        TRY(ws.tile_cycles.reserve(n_lists));
+        w.tile_cycles = ws.tile_cycles.ptr;
     }
+    if (!ws.geo_done) CU(cudaEventCreateWithFlags(&ws.geo_done, cudaEventDisableTiming));
+    if (!ws.tile_done) CU(cudaEventCreateWithFlags(&ws.tile_done, cudaEventDisableTiming));
     return DRAW_OK;
 }
 
@@ -376,10 +385,11 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     const uint32_t tiles_x = (uint32_t)((c->width + TILE_W - 1) / TILE_W), tiles_y = (uint32_t)((c->height + TILE_H - 1) / TILE_H);
     const uint32_t n_coarse = tiles_x * tiles_y;
     const uint32_t n_lists = LISTS_PER_TILE * n_coarse;
-    TRY(ensure_work_buffers(s, n_lists));
-
-    // serialise frames that share this scene's work buffers across different streams
-    if (s->has_last && s->last_stream != c->stream) CU(cudaStreamWaitEvent(c->stream, s->last_done, 0));
+    draw_scene::WorkSet &ws = s->sets[s->next_set];
+    s->last_set = s->next_set;
+    s->next_set ^= 1;
+    TRY(ensure_work_buffers(s, ws, n_lists));
+    if (!s->side_stream) CU(cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking));
 
     FrameUniforms U{};
     const m4 m = transformation_matrix(s->camera, s->width, s->height); // :904
@@ -405,37 +415,41 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     U.tile_y_begin = (uint32_t)(y0 / TILE_H);
     U.tile_y_end = (uint32_t)((y1 + TILE_H - 1) / TILE_H);
 
-    if (s->dev.n_transparent) TRY(sort_transparent(s, c->stream));
+    // Side stream: geometry + binning.  It only waits for the tile kernel that last read this work set.
+    cudaStream_t side = s->side_stream;
+    if (ws.tile_pending) CU(cudaStreamWaitEvent(side, ws.tile_done, 0));
+    if (s->dev.n_transparent) TRY(sort_transparent(s, side));
 
     cudaEvent_t *ev = nullptr;
     if (s->kernel_timing) {
-        for (int i = 0; i <= N_FRAME_KERNELS; i++)
+        for (int i = 0; i < N_FRAME_KERNELS + 2; i++)
             if (!s->kev[i]) CU(cudaEventCreate(&s->kev[i]));
         ev = s->kev;
         s->kev_recorded = true;
     }
-    // the frame: six kernels back to back on the canvas' stream (optional events between them)
+    if (ev) cudaEventRecord(ev[0], side);
+    launch_vertex(U, s->dev, ws.work, side);
+    if (ev) cudaEventRecord(ev[1], side);
+    launch_setup(U, s->dev, ws.work, side);
+    if (ev) cudaEventRecord(ev[2], side);
+    launch_bin_count(U, ws.work, side);
+    if (ev) cudaEventRecord(ev[3], side);
+    launch_alloc(U, ws.work, side);
+    if (ev) cudaEventRecord(ev[4], side);
+    launch_bin_fill(U, ws.work, side);
+    if (ev) cudaEventRecord(ev[5], side);
+    CU(cudaEventRecord(ws.geo_done, side));
+    // Canvas stream: the tile kernel (the only stage that touches the canvas), then the frame's counters.
     cudaStream_t st = c->stream;
-    if (ev) cudaEventRecord(ev[0], st);
-    launch_vertex(U, s->dev, s->work, st);
-    if (ev) cudaEventRecord(ev[1], st);
-    launch_setup(U, s->dev, s->work, st);
-    if (ev) cudaEventRecord(ev[2], st);
-    launch_bin_count(U, s->work, st);
-    if (ev) cudaEventRecord(ev[3], st);
-    launch_alloc(U, s->work, st);
-    if (ev) cudaEventRecord(ev[4], st);
-    launch_bin_fill(U, s->work, st);
-    if (ev) cudaEventRecord(ev[5], st);
-    launch_tile(U, s->dev, s->work, c->color(), c->depth(), st);
+    CU(cudaStreamWaitEvent(st, ws.geo_done, 0));
     if (ev) cudaEventRecord(ev[6], st);
+    launch_tile(U, s->dev, ws.work, c->color(), c->depth(), st);
+    if (ev) cudaEventRecord(ev[7], st);
+    CU(cudaEventRecord(ws.tile_done, st));
+    ws.tile_pending = true;
     s->launches += 4 + (s->dev.n_triangles ? 1 : 0) + (U.tile_y_end > U.tile_y_begin ? 1 : 0);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(c->h_status, s->work.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    if (!s->last_done) CU(cudaEventCreateWithFlags(&s->last_done, cudaEventDisableTiming));
-    CU(cudaEventRecord(s->last_done, c->stream));
-    s->last_stream = c->stream;
-    s->has_last = true;
+    CU(cudaMemcpyAsync(c->h_status, ws.work.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     c->frame_pending = true;
     c->host_dirty = true;
     c->last_scene = s;
@@ -471,6 +485,7 @@ int finish_frame(draw_canvas *c) {
             s->rec_cap = std::max<size_t>((size_t)n_rec + n_rec / 4 + 1024, 4 * (size_t)s->dev.n_triangles + 1024);
         if (overflow & OVERFLOW_REFS) s->refs_cap = (size_t)n_refs + n_refs / 4 + 4096;
         else if (overflow & OVERFLOW_RECORDS) s->refs_cap = std::max(s->refs_cap, 4 * s->rec_cap);
+        CU(cudaDeviceSynchronize()); // both work sets are about to be reallocated
         TRY(enqueue_frame(s, c));
         CU(cudaStreamSynchronize(c->stream));
     }
@@ -558,9 +573,13 @@ void draw_scene_destroy(draw_scene *scene) {
     if (cudaGetDevice(&cur) == cudaSuccess) {
         if (cur != scene->device) cudaSetDevice(scene->device);
         cudaDeviceSynchronize();
-        if (scene->last_done) cudaEventDestroy(scene->last_done);
-        for (int i = 0; i <= N_FRAME_KERNELS; i++)
+        for (draw_scene::WorkSet &ws : scene->sets) {
+            if (ws.geo_done) cudaEventDestroy(ws.geo_done);
+            if (ws.tile_done) cudaEventDestroy(ws.tile_done);
+        }
+        for (int i = 0; i < N_FRAME_KERNELS + 2; i++)
             if (scene->kev[i]) cudaEventDestroy(scene->kev[i]);
+        if (scene->side_stream) cudaStreamDestroy(scene->side_stream);
     }
     delete scene;
 }
@@ -736,7 +755,7 @@ int draw_scene_read_vertex_visual(draw_scene *scene, draw_canvas *canvas, size_t
     std::vector<float> tmp(count);
     const int order[7] = {0, 1, 2, 3, 4, 5, 6}; // light xyz, halfway xyz, depth
     for (int k = 0; k < 7; k++) {
-        CU(cudaMemcpy(tmp.data(), scene->w_vert[order[k]].ptr + first, count * sizeof(float), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(tmp.data(), scene->sets[scene->last_set].vert[order[k]].ptr + first, count * sizeof(float), cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < count; i++) out[7 * i + k] = tmp[i];
     }
     return DRAW_OK;
@@ -775,7 +794,8 @@ int draw_scene_last_kernel_times(draw_scene *scene, draw_canvas *canvas, float m
     if (!scene || !canvas || !ms) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!scene->kev_recorded) return fail(DRAW_ERR_INVALID_ARGUMENT, "kernel timing was not enabled for the last frame");
     TRY(finish_frame(canvas));
-    for (int i = 0; i < N_FRAME_KERNELS; i++) CU(cudaEventElapsedTime(&ms[i], scene->kev[i], scene->kev[i + 1]));
+    for (int i = 0; i < N_FRAME_KERNELS - 1; i++) CU(cudaEventElapsedTime(&ms[i], scene->kev[i], scene->kev[i + 1]));
+    CU(cudaEventElapsedTime(&ms[N_FRAME_KERNELS - 1], scene->kev[6], scene->kev[7])); // k_tile, on the canvas stream
     return DRAW_OK;
     GUARD_END
 }
@@ -787,9 +807,10 @@ int draw_scene_debug_tile_cycles(draw_scene *scene, draw_canvas *canvas, int ena
     if (!out) return DRAW_OK;
     if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
     TRY(finish_frame(canvas));
-    if (!scene->w_tile_cycles.ptr || n > scene->w_tile_cycles.cap) return fail(DRAW_ERR_INVALID_ARGUMENT, "no tile cycles recorded");
+    DevBuf<uint32_t> &cyc = scene->sets[scene->last_set].tile_cycles;
+    if (!cyc.ptr || n > cyc.cap) return fail(DRAW_ERR_INVALID_ARGUMENT, "no tile cycles recorded");
     // layout: [tile] whole CTA, [n_tiles + tile] end of phase A, [2 n_tiles + tile] end of phase B
-    CU(cudaMemcpy(out, scene->w_tile_cycles.ptr, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out, cyc.ptr, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return DRAW_OK;
     GUARD_END
 }
@@ -803,7 +824,7 @@ int draw_scene_debug_list_counts(draw_scene *scene, draw_canvas *canvas, uint32_
     if (n_coarse) *n_coarse = coarse;
     if (!out) return DRAW_OK;
     if (n != lists) return fail(DRAW_ERR_INVALID_ARGUMENT, "n must be %zu", lists);
-    CU(cudaMemcpy(out, scene->w_list_count.ptr, lists * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out, scene->sets[scene->last_set].list_count.ptr, lists * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return DRAW_OK;
     GUARD_END
 }
