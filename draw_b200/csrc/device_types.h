@@ -1,6 +1,7 @@
 // device_types.h — plain structs shared by the host library (scene.cpp) and the kernels.
 #pragma once
 #include <stdint.h>
+#include <vector_types.h>
 
 namespace drawb200 {
 
@@ -94,16 +95,17 @@ struct FrameDev {
     uint32_t *list_count;       // per list (large, medium, small per tile): count, then fill cursor [n_lists]
     uint32_t *list_offset;      // first entry of each list in list_refs [n_lists + 1]
     uint32_t *list_refs;        // record slots grouped by list [refs_cap]
-    uint32_t *counters;         // [0] records  [1] refs  [2] overflow bits  [3] k_setup CTA ticket  [4] k_alloc CTAs done  [8]
+    uint32_t *counters;         // [0] records  [1] refs  [2] overflow bits  [3] k_setup CTA ticket  [4] k_alloc CTAs done  [5] clip queue length  [8]
     uint32_t *tile_cost;        // estimated k_tile work per tile [n_coarse]
     uint32_t *tile_order;       // tiles of the stripe, heaviest first [n_coarse]
     unsigned long long *scan_desc; // k_setup chained-scan descriptors [ceil(n_triangles / 256)]
+    uint2 *clip_queue;          // (triangle, first reserved slot | NO_SLOT) of triangles to clip [n_triangles]
     uint32_t rec_cap, refs_cap;
     uint32_t *tile_cycles;      // debug: SM cycles spent by each coarse tile's CTA (null = off) [n_coarse]
 };
 
 enum : uint32_t { OVERFLOW_RECORDS = 1u, OVERFLOW_REFS = 2u };
 
-constexpr int N_FRAME_KERNELS = 6; // k_vertex k_setup k_bin<count> k_alloc k_bin<fill> k_tile
+constexpr int N_FRAME_KERNELS = 7; // k_vertex k_setup k_clip k_bin<count> k_alloc k_bin<fill> k_tile
 
 } // namespace drawb200

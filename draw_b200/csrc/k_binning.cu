@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const __grid_constant__ Fra
             const RasterRec r = load_raster(W.rrec + slot); // same address in every lane: one broadcast load
             const TileRange tr = tile_range(U, r.bbx, r.bby);
             const int total = tr.count();
-            if (total == 0) continue;
+            if (total == 0 || r.id == NO_SLOT) continue; // NO_SLOT: reserved by k_setup, not used by k_clip
             const TriEdges t = prepare_edges(r);
             const int cols = tr.tx1 - tr.tx0 + 1;
             for (int i = (int)lane; i < total; i += 32)
@@ -87,10 +87,11 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const __grid_constant__ Fra
     // Many records: one thread per record; the rare record covering many tiles is handed to the warp.
     for (uint32_t base = blockIdx.x * BIN_THREADS; base < n; base += gridDim.x * BIN_THREADS) {
         const uint32_t slot = base + threadIdx.x;
-        const bool valid = slot < n;
+        bool valid = slot < n;
         RasterRec r;
         if (valid) r = load_raster(W.rrec + slot);
-        else { r.bbx = r.bby = 0; r.ax = r.ay = r.bx = r.by = r.cx = r.cy = 0.0f; }
+        else { r.id = NO_SLOT; r.bbx = r.bby = 0; r.ax = r.ay = r.bx = r.by = r.cx = r.cy = 0.0f; }
+        if (r.id == NO_SLOT) valid = false; // also: slots reserved by k_setup that k_clip did not use
         const TileRange tr = tile_range(U, r.bbx, r.bby);
         const bool wide = valid && tr.count() > WIDE_TILES;
 

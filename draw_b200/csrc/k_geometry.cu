@@ -5,7 +5,8 @@
 //   k_setup    per triangle gather, back-face cull (:1016-1027), lateral reject + near/far clip
 //                           (:43-90, :662-746), snap + bbox + zero-area cull (canvas.rs:585-666),
 //                           draw-order-preserving record allocation (warp prefix sums + chained
-//                           scan across CTAs), record write
+//                           scan across CTAs), record write; triangles that need clipping are queued
+//   k_clip     per queued triangle: the clip path (rare, register-hungry), fills the reserved slots
 //
 // Arithmetic contract: see device_math.cuh.
 #include "device_math.cuh"
@@ -305,15 +306,13 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
     const uint32_t tri = bid * SETUP_THREADS + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    uint32_t n_out = 0;       // opaque records this thread places (0..4)
-    bool clipped = false;     // they come from the clip path (held in clip_r / clip_s)
+    uint32_t n_out = 0;       // opaque record slots this thread reserves (0, 1, or 4 for a triangle to clip)
+    bool clipped = false;     // the triangle straddles the near or far plane: k_clip fills its four slots
     bool transparent = false; // unclipped transparent triangle: writes its own ordered slots
     uint32_t tslot = 0, material = 0;
     uint32_t vi[3] = {0, 0, 0};
     RasterRec r;
     r.id = NO_SLOT;
-    RasterRec clip_r[4];
-    ShadeRec clip_s[4];
 
     if (tri < S.n_triangles) {
         vi[0] = S.idx[0][tri]; vi[1] = S.idx[1][tri]; vi[2] = S.idx[2][tri];
@@ -350,7 +349,9 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
             else clip = true;
         }
         if (alive && clip) {
-            n_out = (uint32_t)clip_triangle(U, S, W, tri, vi, material, transparent, tslot, clip_r, clip_s);
+            // Rare and register-hungry: handed to k_clip through a queue.  An opaque triangle reserves the
+            // maximum of four consecutive slots here, so that slot order stays draw order.
+            n_out = transparent ? 0u : 4u;
             clipped = true;
             alive = false;
             transparent = false; // a clipped transparent triangle wrote its four ordered slots already
@@ -419,14 +420,18 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 
     const uint32_t slot0 = s_base + warp_tot[warp] + incl - n_out;
     if (n_out && slot0 + n_out > W.rec_cap) {
-        atomicOr(&W.counters[2], OVERFLOW_RECORDS);
-        n_out = 0;
-        clipped = true; // nothing to write
+        atomicOr(&W.counters[2], OVERFLOW_RECORDS); // the host re-renders the frame with larger buffers
+        return;
     }
     if (clipped) {
-        for (uint32_t k = 0; k < n_out; k++) {
-            store_raster(W.rrec + slot0 + k, clip_r[k]);
-            store_shade(W.srec + slot0 + k, clip_s[k]);
+        {
+            RasterRec empty;
+            empty.id = NO_SLOT;
+            empty.bbx = empty.bby = 0;
+            empty.ax = empty.ay = empty.bx = empty.by = empty.cx = empty.cy = empty.da = empty.db = empty.dc = 0.0f;
+            for (uint32_t k = 0; k < n_out; k++) store_raster(W.rrec + slot0 + k, empty); // k_clip overwrites the used ones
+            const uint32_t q = atomicAdd(&W.counters[5], 1u);
+            W.clip_queue[q] = make_uint2(tri, n_out ? slot0 : NO_SLOT);
         }
         return;
     }
@@ -470,8 +475,40 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------
+// k_clip : the triangles k_setup queued because they straddle the near or far plane
+// ------------------------------------------------------------------------------------------
+constexpr int CLIP_THREADS = 128;
+
+__global__ void __launch_bounds__(CLIP_THREADS) k_clip(const __grid_constant__ FrameUniforms U, const SceneDev S,
+                                                       const FrameDev W) {
+    pdl_prologue();
+    const uint32_t n = W.counters[5];
+    for (uint32_t q = blockIdx.x * CLIP_THREADS + threadIdx.x; q < n; q += gridDim.x * CLIP_THREADS) {
+        const uint2 item = W.clip_queue[q];
+        const uint32_t tri = item.x, slot0 = item.y;
+        const uint32_t vi[3] = {S.idx[0][tri], S.idx[1][tri], S.idx[2][tri]};
+        const uint32_t mat = S.tri_mat[tri];
+        const bool transparent = (mat >> 31) != 0;
+        RasterRec out_r[4];
+        ShadeRec out_s[4];
+        const int n_keep = clip_triangle(U, S, W, tri, vi, mat & 0x7FFFFFFFu, transparent, transparent ? S.tri_tslot[tri] : 0u,
+                                         out_r, out_s);
+        if (slot0 == NO_SLOT) continue; // transparent: clip_triangle wrote its ordered slots
+        for (int k = 0; k < n_keep; k++) {
+            store_raster(W.rrec + slot0 + k, out_r[k]);
+            store_shade(W.srec + slot0 + k, out_s[k]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+void launch_clip(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, cudaStream_t stream) {
+    if (!S.n_triangles) return;
+    launch_pdl(k_clip, 148u * 2u, CLIP_THREADS, stream, U, S, W);
+}
+
 void launch_vertex(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, cudaStream_t stream) {
     const uint32_t by_vertex = (S.n_vertices + 255) / 256, by_list = (U.n_lists + 255) / 256;
     uint32_t blocks = by_vertex > 1 ? by_vertex : 1;

@@ -25,6 +25,7 @@ namespace drawb200 {
 // k_geometry.cu / k_binning.cu / k_tile.cu
 void launch_vertex(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
 void launch_setup(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
+void launch_clip(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
 void launch_bin_count(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream);
 void launch_alloc(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream);
 void launch_bin_fill(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream);
@@ -145,6 +146,7 @@ struct draw_scene {
         DevBuf<float> vert[9];
         DevBuf<uint32_t> flags, list_count, list_offset, refs, counters, tile_cycles, tile_cost, tile_order;
         DevBuf<unsigned long long> scan_desc;
+        DevBuf<uint2> clip_queue;
         DevBuf<RasterRec> rrec, trrec;
         DevBuf<ShadeRec> srec, tsrec;
         FrameDev work{};
@@ -157,8 +159,8 @@ struct draw_scene {
     cudaStream_t side_stream = nullptr;
     bool debug_tile_cycles = false;
     size_t rec_cap = 0, refs_cap = 0;
-    // optional per-kernel timing (draw_scene_set_kernel_timing): 0..5 around the five side-stream kernels,
-    // 6 / 7 around k_tile on the canvas stream
+    // optional per-kernel timing (draw_scene_set_kernel_timing): 0..6 around the six side-stream kernels,
+    // 7 / 8 around k_tile on the canvas stream
     bool kernel_timing = false;
     cudaEvent_t kev[N_FRAME_KERNELS + 2] = {};
     bool kev_recorded = false;
@@ -297,7 +299,7 @@ int ensure_work_buffers(draw_scene *s, draw_scene::WorkSet &ws, size_t n_lists) 
     const SceneDev &d = s->dev;
     for (int i = 0; i < 9; i++) TRY(ws.vert[i].reserve(d.n_vertices));
     TRY(ws.flags.reserve(d.n_vertices));
-    if (s->rec_cap == 0) s->rec_cap = 2 * (size_t)d.n_triangles + 1024;
+    if (s->rec_cap == 0) s->rec_cap = 2 * (size_t)d.n_triangles + 4096;
     if (s->refs_cap == 0) s->refs_cap = std::max<size_t>((size_t)1 << 22, 4 * (size_t)d.n_triangles);
     TRY(ws.rrec.reserve(s->rec_cap));
     TRY(ws.srec.reserve(s->rec_cap));
@@ -310,6 +312,7 @@ int ensure_work_buffers(draw_scene *s, draw_scene::WorkSet &ws, size_t n_lists) 
     TRY(ws.tile_cost.reserve(n_lists));
     TRY(ws.tile_order.reserve(n_lists));
     TRY(ws.scan_desc.reserve((size_t)d.n_triangles / 256 + 2));
+    TRY(ws.clip_queue.reserve(d.n_triangles));
     FrameDev &w = ws.work;
     w.v_lx = ws.vert[0].ptr; w.v_ly = ws.vert[1].ptr; w.v_lz = ws.vert[2].ptr;
     w.v_hx = ws.vert[3].ptr; w.v_hy = ws.vert[4].ptr; w.v_hz = ws.vert[5].ptr;
@@ -322,6 +325,7 @@ int ensure_work_buffers(draw_scene *s, draw_scene::WorkSet &ws, size_t n_lists) 
     w.tile_cost = ws.tile_cost.ptr;
     w.tile_order = ws.tile_order.ptr;
     w.scan_desc = ws.scan_desc.ptr;
+    w.clip_queue = ws.clip_queue.ptr;
     w.rec_cap = (uint32_t)s->rec_cap;
     w.refs_cap = (uint32_t)s->refs_cap;
     w.tile_cycles = nullptr;
@@ -432,22 +436,24 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     if (ev) cudaEventRecord(ev[1], side);
     launch_setup(U, s->dev, ws.work, side);
     if (ev) cudaEventRecord(ev[2], side);
-    launch_bin_count(U, ws.work, side);
+    launch_clip(U, s->dev, ws.work, side);
     if (ev) cudaEventRecord(ev[3], side);
-    launch_alloc(U, ws.work, side);
+    launch_bin_count(U, ws.work, side);
     if (ev) cudaEventRecord(ev[4], side);
-    launch_bin_fill(U, ws.work, side);
+    launch_alloc(U, ws.work, side);
     if (ev) cudaEventRecord(ev[5], side);
+    launch_bin_fill(U, ws.work, side);
+    if (ev) cudaEventRecord(ev[6], side);
     CU(cudaEventRecord(ws.geo_done, side));
     // Canvas stream: the tile kernel (the only stage that touches the canvas), then the frame's counters.
     cudaStream_t st = c->stream;
     CU(cudaStreamWaitEvent(st, ws.geo_done, 0));
-    if (ev) cudaEventRecord(ev[6], st);
-    launch_tile(U, s->dev, ws.work, c->color(), c->depth(), st);
     if (ev) cudaEventRecord(ev[7], st);
+    launch_tile(U, s->dev, ws.work, c->color(), c->depth(), st);
+    if (ev) cudaEventRecord(ev[8], st);
     CU(cudaEventRecord(ws.tile_done, st));
     ws.tile_pending = true;
-    s->launches += 4 + (s->dev.n_triangles ? 1 : 0) + (U.tile_y_end > U.tile_y_begin ? 1 : 0);
+    s->launches += 4 + (s->dev.n_triangles ? 2 : 0) + (U.tile_y_end > U.tile_y_begin ? 1 : 0);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_status, ws.work.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     c->frame_pending = true;
@@ -789,13 +795,13 @@ int draw_scene_set_kernel_timing(draw_scene *scene, int enabled) {
     return DRAW_OK;
 }
 
-int draw_scene_last_kernel_times(draw_scene *scene, draw_canvas *canvas, float ms[6]) {
+int draw_scene_last_kernel_times(draw_scene *scene, draw_canvas *canvas, float ms[7]) {
     GUARD_BEGIN
     if (!scene || !canvas || !ms) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!scene->kev_recorded) return fail(DRAW_ERR_INVALID_ARGUMENT, "kernel timing was not enabled for the last frame");
     TRY(finish_frame(canvas));
     for (int i = 0; i < N_FRAME_KERNELS - 1; i++) CU(cudaEventElapsedTime(&ms[i], scene->kev[i], scene->kev[i + 1]));
-    CU(cudaEventElapsedTime(&ms[N_FRAME_KERNELS - 1], scene->kev[6], scene->kev[7])); // k_tile, on the canvas stream
+    CU(cudaEventElapsedTime(&ms[N_FRAME_KERNELS - 1], scene->kev[7], scene->kev[8])); // k_tile, on the canvas stream
     return DRAW_OK;
     GUARD_END
 }
