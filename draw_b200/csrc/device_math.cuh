@@ -18,12 +18,17 @@ namespace drawb200 {
 // while the previous kernel drains.  Every kernel calls pdl_prologue() first: it lets its own
 // dependents launch early and then waits until the kernels it depends on have completed and their
 // writes are visible (griddepcontrol.wait), which preserves plain stream-order semantics for data.
-__device__ __forceinline__ void pdl_prologue() {
+// `early` (FrameUniforms::pdl_early): trigger before doing any work, which hides the whole launch
+// latency of the dependent kernel but makes its CTAs resident (and idle) for the duration of this
+// kernel — right for a lone frame, wrong when several frames are in flight and those slots are
+// needed by another frame's kernels; otherwise dependents launch when this kernel's CTAs exit.
+__device__ __forceinline__ void pdl_prologue(bool early = true) {
 #if __CUDA_ARCH__ >= 900
-    cudaTriggerProgrammaticLaunchCompletion();
+    if (early) cudaTriggerProgrammaticLaunchCompletion();
     cudaGridDependencySynchronize();
 #endif
 }
+extern int g_pdl_enabled; // scene.cpp (DRAW_B200_PDL=0 launches without the attribute)
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t stream, Args... args) {
     cudaLaunchConfig_t cfg = {};
@@ -34,7 +39,7 @@ inline void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, 
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_pdl_enabled ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
@@ -149,6 +154,61 @@ __device__ __forceinline__ TriEdges prepare_edges(const RasterRec &r) {
         t.f[i] = neg ? -t.f[i] : t.f[i];
     }
     return t;
+}
+
+// ---- prepared records --------------------------------------------------------------------------
+// Early depth reject.  For a covered pixel of a tame triangle with finite non-negative vertex depths,
+//   D = e0*da/f0 + e1*db/f1 + e2*dc/f2                       (real arithmetic, all terms >= 0)
+// and the reference's float depth d_ref = fl(fl(fl(e0/f0)*da + fl(e1/f1)*db) + fl(e2/f2)*dc) satisfies
+// |d_ref - D| <= 4.1 u D (u = 2^-24: one division, one product and two sums of non-negative terms),
+// while d_app = fma(e2, g2, fma(e1, g1, e0*g0)) with g_i = fl(d_i * fl(1/f_i)) satisfies
+// |d_app - D| <= 5.1 u D.  Hence d_ref >= d_app * (1 - 9.3u) > d_app * (1 - 2^-20), so
+//   d_app * (1 - 2^-20) > z   ==>   d_ref > z :  the fragment fails the strict `<` test and is not a tie,
+// and its divisions can be skipped.  The bounds need normal (not denormal) products, so the
+// flag is only set when every g_i is 0 or >= 1e-30; NaN/inf make the comparison false or d_ref = inf.
+constexpr uint32_t TRI_EARLYZ = 16u;
+constexpr float EARLYZ_SCALE = 0.99999904632568359375f; // 1 - 2^-20
+// exact_div may replace the IEEE division e / f_i for this triangle (tame, 1 <= f_i <= 2^40)
+constexpr uint32_t TRI_FASTDIV = 32u;
+
+// Correctly rounded e / f from rf = RN(1/f) in three operations (Markstein's theorem: with a correctly
+// rounded reciprocal, q0 = RN(e*rf) is within one ulp of e/f, the remainder r = e - f*q0 is exact in
+// an FMA, and RN(q0 + r*rf) is the correctly rounded quotient).  No branches, so the three quotients
+// of a pixel — and those of neighbouring pixels — overlap in the pipeline, unlike __fdiv_rn's
+// subroutine.  Used only under TRI_FASTDIV (no overflow, underflow or special values in reach);
+// tests/test_fastdiv_cpu.py checks the identity on 10^8 near-midpoint quotients, and every GPU
+// parity test exercises it.  The FMAs here are deliberate and exact-result-preserving.
+__device__ __forceinline__ float exact_div(float e, float f, float rf) {
+    const float q0 = __fmul_rn(e, rf);
+    const float r = __fmaf_rn(-f, q0, e);
+    return __fmaf_rn(r, rf, q0);
+}
+
+__device__ __forceinline__ void make_prep(const RasterRec &r, PrepRec &p) {
+    const TriEdges t = prepare_edges(r);
+    const float dep[3] = {r.da, r.db, r.dc};
+    bool earlyz = !(t.flags & TRI_SLOW), fastdiv = earlyz;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        p.ecx[i] = t.ecx[i]; p.ecy[i] = t.ecy[i]; p.ek1[i] = t.ek1[i]; p.ek2[i] = t.ek2[i]; p.f[i] = t.f[i];
+        p.rf[i] = __frcp_rn(t.f[i]);
+        const float g = __fmul_rn(dep[i], p.rf[i]);
+        earlyz = earlyz && dep[i] >= 0.0f && dep[i] < 3.0e38f && (g == 0.0f || g >= 1e-30f);
+        fastdiv = fastdiv && t.f[i] >= 1.0f && t.f[i] <= 1099511627776.0f;
+    }
+    p.da = r.da; p.db = r.db; p.dc = r.dc;
+    p.x0 = (float)(r.bbx & 0xFFFF); p.x1 = (float)(r.bbx >> 16);
+    p.y0 = (float)(r.bby & 0xFFFF); p.y1 = (float)(r.bby >> 16);
+    p.flags = t.flags | (earlyz ? TRI_EARLYZ : 0u) | (fastdiv ? TRI_FASTDIV : 0u);
+    p.id = r.id;
+    p.slot = 0;
+    p.pad[0] = p.pad[1] = p.pad[2] = p.pad[3] = 0;
+}
+__device__ __forceinline__ void store_prep(PrepRec *dst, const PrepRec &p) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(&p);
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+    for (int i = 0; i < 7; i++) d[i] = src[i]; // the last quad is padding
 }
 
 // Can any pixel of the rectangle [lx,hx] x [ly,hy] be covered?  Exact, not heuristic: each edge

@@ -19,9 +19,57 @@ namespace drawb200 {
 #define DRAW_TILE_H 32
 #endif
 constexpr int TILE_W = DRAW_TILE_W, TILE_H = DRAW_TILE_H, REGION = 16;
-constexpr int SMALL_AREA = 8, MEDIUM_AREA = 1024;
+#ifndef DRAW_MEDIUM_AREA
+#define DRAW_MEDIUM_AREA 1024
+#endif
+#ifndef DRAW_SMALL_AREA
+#define DRAW_SMALL_AREA 8
+#endif
+constexpr int SMALL_AREA = DRAW_SMALL_AREA, MEDIUM_AREA = DRAW_MEDIUM_AREA;
 constexpr int LISTS_PER_TILE = 3;
 constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
+#ifndef DRAW_TILE_THREADS
+#define DRAW_TILE_THREADS 512
+#endif
+constexpr int TILE_THREADS = DRAW_TILE_THREADS;
+// k_tile phase A geometry: a warp owns a REGION x REGION_H rectangle (4 lanes across, 8 down), a lane
+// a 4 x BLK_H block of it.
+constexpr int BLK_H = TILE_W * TILE_H / TILE_THREADS / 4;
+constexpr int REGION_H = 8 * BLK_H;
+
+// k_tile work items, built by k_alloc (heaviest first).  An item is a tile plus a pixel window of it in
+// units of warp regions (a 4x4 grid of REGION x REGION_H rectangles): the whole tile, or one of the
+// 2 / 4 / 8 / 16 windows a dense tile is cut into.
+//   bits 0-9 tile x | 10-20 tile y | 21-22 window x0 | 23-24 window y0 | 25-26 window w-1 | 27-28 window h-1
+// Tiles with nothing binned to them are not items of their own: they are listed in FrameDev::empty_tiles
+// (as x | y << 10) and an item with ITEM_EMPTY set names a group of EMPTY_GROUP of them, one per warp
+// of the CTA (bits 0-28 = group index).
+constexpr int REGIONS_X = TILE_W / REGION, REGIONS_Y = TILE_H / REGION_H;
+constexpr bool TILE_SPLITTABLE = REGIONS_X == 4 && (REGIONS_Y == 4 || REGIONS_Y == 2);
+#ifndef DRAW_TILE_MAX_SPLIT
+#define DRAW_TILE_MAX_SPLIT 8
+#endif
+#ifndef DRAW_TILE_SPLIT_MIN_COST
+#define DRAW_TILE_SPLIT_MIN_COST 256
+#endif
+constexpr int TILE_MAX_SPLIT = DRAW_TILE_MAX_SPLIT < REGIONS_X * REGIONS_Y ? DRAW_TILE_MAX_SPLIT : REGIONS_X * REGIONS_Y; // 1, 2, 4, 8 or 16
+constexpr int TILE_SPLIT_MIN_COST = DRAW_TILE_SPLIT_MIN_COST; // windows are not made cheaper than this (k_alloc cost units)
+constexpr int TILE_EXTRA_ITEMS = 1024;                        // work-list slots beyond one per tile
+#ifndef DRAW_TILE_SPLIT_DIV
+#define DRAW_TILE_SPLIT_DIV 296
+#endif
+constexpr int TILE_SPLIT_DIV = DRAW_TILE_SPLIT_DIV;           // a window should cost about total / this (<= TILE_EXTRA_ITEMS)
+constexpr uint32_t ITEM_NONE = 0xFFFFFFFFu, ITEM_EMPTY = 1u << 29;
+constexpr int EMPTY_GROUP = TILE_THREADS / 32;
+constexpr uint32_t MAX_TILES_X = 1u << 10, MAX_TILES_Y = 1u << 11;
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline uint32_t make_item(uint32_t tx, uint32_t ty, uint32_t splits, uint32_t i) {
+    const uint32_t sx = splits >= 8 ? 4u : (splits >= 2 ? 2u : 1u), sy = splits / sx; // sy <= REGIONS_Y as splits <= TILE_MAX_SPLIT
+    const uint32_t rw = (uint32_t)REGIONS_X / sx, rh = (uint32_t)REGIONS_Y / sy, rx0 = (i % sx) * rw, ry0 = (i / sx) * rh;
+    return tx | ty << 10 | rx0 << 21 | ry0 << 23 | (rw - 1u) << 25 | (rh - 1u) << 27;
+}
 
 // Per-frame constants, passed to every kernel by value (__grid_constant__): no upload, no sync.
 struct FrameUniforms {
@@ -36,6 +84,9 @@ struct FrameUniforms {
     uint32_t tile_y_begin, tile_y_end; // coarse tile rows rendered by this launch (sort-first stripe)
     uint32_t n_coarse;                 // tiles_x * tiles_y
     uint32_t n_lists;                  // LISTS_PER_TILE * n_coarse: large, medium, small lists
+    uint32_t split_min_cost, split_div, split_max; // k_alloc's tile splitting policy (defaults: TILE_SPLIT_*)
+    uint32_t has_transparent;          // transparent triangles are not binned: no tile may take the empty-tile path
+    uint32_t pdl_early;                // geometry / binning kernels trigger their dependents at once (device_math.cuh)
 };
 
 // Texture (scene/mod.rs:206-216) with both TextureMaps flattened into the texel pool.  Maps are
@@ -71,6 +122,25 @@ struct alignas(16) RasterRec {
     uint32_t bbx, bby;            // x_min | x_max << 16, y_min | y_max << 16 (canvas.rs:640-658)
 };
 
+// A raster record prepared for coverage and depth tests (128 B = 8 x uint4, one per thread when a
+// tile CTA stages it).  Written once per record by k_bin<count>, read by every tile (and window) the
+// record is binned to, so the edge set-up is not repeated per reference.  Field order is fixed:
+// quad 5 (x0 x1 y0 y1) is what the window filter of k_tile reads on its own.
+struct alignas(16) PrepRec {
+    float ecx[3], ecy[3], ek1[3], ek2[3]; // sign-normalised edge functions (device_math.cuh: prepare_edges)
+    float f[3];                           // their values at the opposite vertex (> 0 when tame)
+    float rf[3];                          // RN(1 / f): exact_div, early depth reject
+    float da, db;
+    float x0, x1, y0, y1;                 // bbox as floats (exact: < 65536)
+    float dc;
+    uint32_t flags;                       // TRI_* bits
+    uint32_t id;                          // draw id
+    uint32_t slot;                        // record slot (filled in when staged)
+    uint32_t pad[4];
+};
+static_assert(sizeof(PrepRec) == 128, "PrepRec is staged as 8 uint4");
+constexpr int PREP_WORDS = 28; // meaningful words; shared-memory copies use this (odd-ish) stride + 1
+
 // What shading needs for the winning triangle of a pixel (144 B).
 struct alignas(16) ShadeRec {
     float n[3][3]; // normal    per corner
@@ -88,16 +158,18 @@ struct FrameDev {
     float *v_depth;             // :924
     float *v_sx, *v_sy;         // screen xy after the divide (:1047-1058), before the canvas offset
     uint32_t *v_flags;          // 2 bits per plane: bit 2p = f>0, bit 2p+1 = f<=0
-    RasterRec *rrec;            // opaque records, unordered slots [rec_cap]
+    RasterRec *rrec;            // opaque records, slots in draw order [rec_cap]
+    PrepRec *prep;              // the same records prepared for rasterisation (k_bin<count>) [rec_cap]
     ShadeRec *srec;
     RasterRec *t_rrec;          // transparent records, slot = 4*ordinal + k, in draw order [4*n_transparent]
     ShadeRec *t_srec;
     uint32_t *list_count;       // per list (large, medium, small per tile): count, then fill cursor [n_lists]
     uint32_t *list_offset;      // first entry of each list in list_refs [n_lists + 1]
     uint32_t *list_refs;        // record slots grouped by list [refs_cap]
-    uint32_t *counters;         // [0] records  [1] refs  [2] overflow bits  [3] k_setup CTA ticket  [4] k_alloc CTAs done  [5] clip queue length  [8]
+    uint32_t *counters;         // [0] records  [1] refs  [2] overflow bits  [3] k_setup CTA ticket  [4] k_alloc CTAs done  [5] clip queue length  [6] total tile cost  [8]
     uint32_t *tile_cost;        // estimated k_tile work per tile [n_coarse]
-    uint32_t *tile_order;       // tiles of the stripe, heaviest first [n_coarse]
+    uint32_t *tile_order;       // k_tile work items (make_item), heaviest first, padded with ITEM_NONE [n_coarse + TILE_EXTRA_ITEMS]
+    uint32_t *empty_tiles;      // tiles with empty lists as x | y << 10, padded with NO_SLOT to a multiple of EMPTY_GROUP [n_coarse + EMPTY_GROUP]
     unsigned long long *scan_desc; // k_setup chained-scan descriptors [ceil(n_triangles / 256)]
     uint2 *clip_queue;          // (triangle, first reserved slot | NO_SLOT) of triangles to clip [n_triangles]
     uint32_t rec_cap, refs_cap;

@@ -25,18 +25,55 @@ __device__ __forceinline__ void bin_hit(const FrameDev &W, uint32_t list, uint32
     const uint32_t pos = atomicAdd(&W.list_count[list], 1u);
     if (FILL) W.list_refs[W.list_offset[list] + pos] = slot;
 }
+// Estimated k_tile work of one reference, in quarter block-iterations (one iteration = a warp testing an
+// 8x4 block of a medium triangle, ~130 instructions): a large triangle costs every warp of the CTA a
+// pass, a medium one its 8x4 blocks, a small one a lane.  Summed per tile by k_bin<count> for k_alloc.
+constexpr uint32_t COST_LARGE = 80u, COST_MEDIUM_BLOCK = 4u, COST_SMALL = 1u;
 
 // Reference one tile from a record if the triangle can cover a pixel of it; the list class follows
 // the area of the bbox clipped to the tile.
-template <bool FILL>
-__device__ __forceinline__ void bin_tile(const FrameUniforms &U, const FrameDev &W, const TriEdges &t, int x0, int x1,
+template <bool FILL, typename Tri>
+__device__ __forceinline__ void bin_tile(const FrameUniforms &U, const FrameDev &W, const Tri &t, int x0, int x1,
                                          int y0, int y1, int tx, int ty, uint32_t slot) {
     const int lx = max(x0, tx * TILE_W), hx = min(x1, tx * TILE_W + TILE_W - 1);
     const int ly = max(y0, ty * TILE_H), hy = min(y1, ty * TILE_H + TILE_H - 1);
-    if (!rect_may_cover(t, lx, hx, ly, hy)) return;
+    if (!rect_may_cover(t, (float)lx, (float)hx, (float)ly, (float)hy)) return;
     const int area = (hx - lx + 1) * (hy - ly + 1);
     const uint32_t cls = area <= SMALL_AREA ? 2u : (area <= MEDIUM_AREA ? 1u : 0u);
-    bin_hit<FILL>(W, cls * U.n_coarse + (uint32_t)ty * U.tiles_x + (uint32_t)tx, slot);
+    const uint32_t tile = (uint32_t)ty * U.tiles_x + (uint32_t)tx;
+    bin_hit<FILL>(W, cls * U.n_coarse + tile, slot);
+    if (!FILL) {
+        const uint32_t blocks = (uint32_t)((hx - lx) / 8 + 1) * (uint32_t)((hy - ly) / 4 + 1);
+        atomicAdd(&W.tile_cost[tile], cls == 2u ? COST_SMALL : (cls == 1u ? COST_MEDIUM_BLOCK * blocks : COST_LARGE));
+    }
+}
+
+// The part of a prepared record binning needs.  k_bin<count> prepares every record once (make_prep)
+// and writes the PrepRec k_tile stages from; k_bin<fill> reads the edges back instead of redoing them.
+struct BinTri {
+    float ecx[3], ecy[3], ek1[3], ek2[3];
+    uint32_t flags;
+};
+template <bool FILL>
+__device__ __forceinline__ BinTri bin_prepare(const FrameDev &W, const RasterRec &r, uint32_t slot, bool store) {
+    BinTri b;
+    if (!FILL) {
+        PrepRec p;
+        make_prep(r, p);
+        if (store) store_prep(W.prep + slot, p);
+#pragma unroll
+        for (int i = 0; i < 3; i++) { b.ecx[i] = p.ecx[i]; b.ecy[i] = p.ecy[i]; b.ek1[i] = p.ek1[i]; b.ek2[i] = p.ek2[i]; }
+        b.flags = p.flags;
+    } else {
+        const uint4 *q = reinterpret_cast<const uint4 *>(W.prep + slot);
+        const uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q6 = __ldg(q + 6);
+        b.ecx[0] = __uint_as_float(q0.x); b.ecx[1] = __uint_as_float(q0.y); b.ecx[2] = __uint_as_float(q0.z);
+        b.ecy[0] = __uint_as_float(q0.w); b.ecy[1] = __uint_as_float(q1.x); b.ecy[2] = __uint_as_float(q1.y);
+        b.ek1[0] = __uint_as_float(q1.z); b.ek1[1] = __uint_as_float(q1.w); b.ek1[2] = __uint_as_float(q2.x);
+        b.ek2[0] = __uint_as_float(q2.y); b.ek2[1] = __uint_as_float(q2.z); b.ek2[2] = __uint_as_float(q2.w);
+        b.flags = q6.y;
+    }
+    return b;
 }
 
 constexpr int BIN_THREADS = 256;
@@ -61,7 +98,7 @@ __device__ __forceinline__ TileRange tile_range(const FrameUniforms &U, uint32_t
 
 template <bool FILL>
 __global__ void __launch_bounds__(BIN_THREADS) k_bin(const __grid_constant__ FrameUniforms U, const FrameDev W) {
-    pdl_prologue();
+    pdl_prologue(U.pdl_early != 0);
     if (FILL && W.counters[2] != 0) return; // a buffer overflowed: the host re-renders with larger buffers
     uint32_t n = W.counters[0];
     if (n > W.rec_cap) n = W.rec_cap;
@@ -75,8 +112,12 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const __grid_constant__ Fra
             const RasterRec r = load_raster(W.rrec + slot); // same address in every lane: one broadcast load
             const TileRange tr = tile_range(U, r.bbx, r.bby);
             const int total = tr.count();
-            if (total == 0 || r.id == NO_SLOT) continue; // NO_SLOT: reserved by k_setup, not used by k_clip
-            const TriEdges t = prepare_edges(r);
+            if (r.id == NO_SLOT) continue; // reserved by k_setup, not used by k_clip
+            if (total == 0) {              // outside the stripe: never referenced, but keep the PrepRec defined
+                if (!FILL && lane == 0) bin_prepare<FILL>(W, r, slot, true);
+                continue;
+            }
+            const BinTri t = bin_prepare<FILL>(W, r, slot, lane == 0);
             const int cols = tr.tx1 - tr.tx0 + 1;
             for (int i = (int)lane; i < total; i += 32)
                 bin_tile<FILL>(U, W, t, tr.x0, tr.x1, tr.y0, tr.y1, tr.tx0 + i % cols, tr.ty0 + i / cols, slot);
@@ -94,9 +135,10 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const __grid_constant__ Fra
         if (r.id == NO_SLOT) valid = false; // also: slots reserved by k_setup that k_clip did not use
         const TileRange tr = tile_range(U, r.bbx, r.bby);
         const bool wide = valid && tr.count() > WIDE_TILES;
+        BinTri t = {};
+        if (valid) t = bin_prepare<FILL>(W, r, slot, true);
 
         if (valid && !wide) {
-            const TriEdges t = prepare_edges(r);
             for (int ty = tr.ty0; ty <= tr.ty1; ty++)
                 for (int tx = tr.tx0; tx <= tr.tx1; tx++) bin_tile<FILL>(U, W, t, tr.x0, tr.x1, tr.y0, tr.y1, tx, ty, slot);
         }
@@ -105,16 +147,18 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const __grid_constant__ Fra
         while (pending) {
             const int src = __ffs(pending) - 1;
             pending &= pending - 1;
-            RasterRec w;
-            w.ax = __shfl_sync(0xFFFFFFFFu, r.ax, src); w.ay = __shfl_sync(0xFFFFFFFFu, r.ay, src);
-            w.bx = __shfl_sync(0xFFFFFFFFu, r.bx, src); w.by = __shfl_sync(0xFFFFFFFFu, r.by, src);
-            w.cx = __shfl_sync(0xFFFFFFFFu, r.cx, src); w.cy = __shfl_sync(0xFFFFFFFFu, r.cy, src);
+            BinTri w;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                w.ecx[i] = __shfl_sync(0xFFFFFFFFu, t.ecx[i], src); w.ecy[i] = __shfl_sync(0xFFFFFFFFu, t.ecy[i], src);
+                w.ek1[i] = __shfl_sync(0xFFFFFFFFu, t.ek1[i], src); w.ek2[i] = __shfl_sync(0xFFFFFFFFu, t.ek2[i], src);
+            }
+            w.flags = __shfl_sync(0xFFFFFFFFu, t.flags, src);
             const TileRange wt = tile_range(U, __shfl_sync(0xFFFFFFFFu, r.bbx, src), __shfl_sync(0xFFFFFFFFu, r.bby, src));
             const uint32_t wslot = __shfl_sync(0xFFFFFFFFu, slot, src);
-            const TriEdges t = prepare_edges(w);
             const int cols = wt.tx1 - wt.tx0 + 1, total = wt.count();
             for (int i = (int)lane; i < total; i += 32)
-                bin_tile<FILL>(U, W, t, wt.x0, wt.x1, wt.y0, wt.y1, wt.tx0 + i % cols, wt.ty0 + i / cols, wslot);
+                bin_tile<FILL>(U, W, w, wt.x0, wt.x1, wt.y0, wt.y1, wt.tx0 + i % cols, wt.ty0 + i / cols, wslot);
         }
     }
 }
@@ -125,9 +169,13 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const __grid_constant__ Fra
 //      tile order, so instead of a global scan each CTA scans its 256 sums locally and reserves its
 //      total with one atomicAdd; list_count is reset to serve as the fill cursor (after k_bin<true> it
 //      holds the count again, which is what k_tile reads).  total -> counters[1].
-//  (2) orders the stripe's tiles by estimated work, heaviest first, so that k_tile (whose CTAs are
-//      dispatched in index order) starts its long tiles first and ends with the empty ones: the last
-//      CTA to finish (1) bucket-sorts the per-tile costs by their log2.
+//  (2) builds k_tile's work list (the last CTA to finish (1) does it).  A work item is a tile or, for
+//      a tile whose estimated cost is far above the frame's average, one of 2/4/8/16 pixel windows of
+//      it (device_types.h: make_item): every window gets its own 512-thread CTA, walks the tile's
+//      lists and keeps only what falls inside its window, so that a few dense tiles do not decide
+//      the duration of the whole launch.  Items are bucket-sorted by the log2 of their cost, heaviest
+//      first (k_tile's CTAs are dispatched in index order); empty tiles carry a flag so that their
+//      CTA needs no further loads.  Unused slots up to the launch's grid size hold ITEM_NONE.
 // ------------------------------------------------------------------------------------------
 constexpr int ALLOC_THREADS = 256;
 constexpr uint32_t COST_NOT_IN_STRIPE = 0xFFFFFFFFu;
@@ -136,36 +184,50 @@ constexpr int COST_BUCKETS = 34;
 __device__ __forceinline__ int cost_bucket(uint32_t cost) { // 0 = heaviest ... COST_BUCKETS-1 = empty tile
     return cost == 0 ? COST_BUCKETS - 1 : __clz(cost);      // clz in 0..31 (larger cost -> smaller clz)
 }
+// Number of windows a tile of this cost is cut into: the largest power of two <= cost / target,
+// so that the sum over tiles stays <= total cost / target <= TILE_EXTRA_ITEMS.
+__device__ __forceinline__ uint32_t tile_splits(uint32_t cost, uint32_t target, uint32_t max_split) {
+    if (!TILE_SPLITTABLE || cost < 2u * target) return 1u;
+    const uint32_t q = cost / target;
+    return min(max_split, 1u << (31 - __clz(q)));
+}
 
 __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const __grid_constant__ FrameUniforms U, const FrameDev W) {
-    __shared__ uint32_t warp_sum[ALLOC_THREADS / 32];
+    __shared__ uint32_t warp_sum[ALLOC_THREADS / 32], warp_cost[ALLOC_THREADS / 32];
     __shared__ uint32_t block_base, is_last;
     __shared__ uint32_t bucket_start[COST_BUCKETS];
-    pdl_prologue();
+    pdl_prologue(U.pdl_early != 0);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.x * ALLOC_THREADS + tid, nc = U.n_coarse;
     const bool valid = tile < nc;
     const uint32_t c0 = valid ? W.list_count[tile] : 0u, c1 = valid ? W.list_count[nc + tile] : 0u,
                    c2 = valid ? W.list_count[2 * nc + tile] : 0u;
     const uint32_t c = c0 + c1 + c2;
+    const uint32_t ty = valid ? tile / U.tiles_x : 0u;
+    const bool in_stripe = valid && ty >= U.tile_y_begin && ty < U.tile_y_end;
+    const uint32_t cost = in_stripe ? W.tile_cost[tile] : 0u; // summed by k_bin<count> (COST_* above)
 
-    uint32_t incl = c;
+    uint32_t incl = c, cost_sum = cost;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
         if (lane >= (uint32_t)d) incl += up;
+        cost_sum += __shfl_xor_sync(0xFFFFFFFFu, cost_sum, d);
     }
     if (lane == 31) warp_sum[warp] = incl;
+    if (lane == 0) warp_cost[warp] = cost_sum;
     __syncthreads();
     if (tid == 0) {
-        uint32_t total = 0;
+        uint32_t total = 0, total_cost = 0;
         for (int w = 0; w < ALLOC_THREADS / 32; w++) {
             const uint32_t t = warp_sum[w];
             warp_sum[w] = total;
             total += t;
+            total_cost += warp_cost[w];
         }
         const uint32_t base = total ? atomicAdd(&W.counters[1], total) : 0u;
         if (total && base + total > W.refs_cap) atomicOr(&W.counters[2], OVERFLOW_REFS);
+        if (total_cost) atomicAdd(&W.counters[6], total_cost);
         block_base = base;
     }
     __syncthreads();
@@ -177,29 +239,41 @@ __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const __grid_constant__
         W.list_count[tile] = 0; // become the fill cursors
         W.list_count[nc + tile] = 0;
         W.list_count[2 * nc + tile] = 0;
-        const uint32_t ty = tile / U.tiles_x;
-        // rough relative cost of a large / medium / small reference in k_tile
-        W.tile_cost[tile] = (ty >= U.tile_y_begin && ty < U.tile_y_end) ? 16u * c0 + 4u * c1 + c2 : COST_NOT_IN_STRIPE;
+        W.tile_cost[tile] = in_stripe ? cost : COST_NOT_IN_STRIPE;
     }
-    // ---- the last CTA orders the tiles ---------------------------------------------------------
+    // ---- the last CTA builds the work list -------------------------------------------------------
     __threadfence();
     __syncthreads();
     if (tid == 0) is_last = atomicAdd(&W.counters[4], 1u) == gridDim.x - 1;
     __syncthreads();
     if (!is_last) return;
+    __shared__ uint32_t n_empty;
     for (int b = (int)tid; b < COST_BUCKETS; b += ALLOC_THREADS) bucket_start[b] = 0;
+    if (tid == 0) n_empty = 0;
     __syncthreads();
+    const uint32_t total_cost = __ldcg(&W.counters[6]);
+    const uint32_t target = max(U.split_min_cost, total_cost / U.split_div + 1u); // split_div <= TILE_EXTRA_ITEMS
+    const uint32_t max_split = U.split_max;
+    const bool group_empties = U.has_transparent == 0; // else every tile runs the full path (cost 0, last bucket)
     constexpr int BATCH = 8; // independent loads in flight per thread
     for (uint32_t t0 = tid; t0 < nc; t0 += ALLOC_THREADS * BATCH) {
-        uint32_t cost[BATCH];
+        uint32_t cost_k[BATCH];
 #pragma unroll
         for (int k = 0; k < BATCH; k++) {
             const uint32_t t = t0 + k * ALLOC_THREADS;
-            cost[k] = t < nc ? __ldcg(&W.tile_cost[t]) : COST_NOT_IN_STRIPE;
+            cost_k[k] = t < nc ? __ldcg(&W.tile_cost[t]) : COST_NOT_IN_STRIPE;
         }
 #pragma unroll
         for (int k = 0; k < BATCH; k++)
-            if (cost[k] != COST_NOT_IN_STRIPE) atomicAdd(&bucket_start[cost_bucket(cost[k])], 1u);
+            if (cost_k[k] != COST_NOT_IN_STRIPE) {
+                if (cost_k[k] == 0 && group_empties) { // listed on its own: one warp of a group CTA clears it
+                    const uint32_t t = t0 + k * ALLOC_THREADS;
+                    W.empty_tiles[atomicAdd(&n_empty, 1u)] = (t % U.tiles_x) | (t / U.tiles_x) << 10;
+                    continue;
+                }
+                const uint32_t s = tile_splits(cost_k[k], target, max_split);
+                atomicAdd(&bucket_start[cost_bucket(cost_k[k] / s)], s);
+            }
     }
     __syncthreads();
     if (tid == 0) {
@@ -209,19 +283,30 @@ __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const __grid_constant__
             bucket_start[b] = run;
             run += n;
         }
+        block_base = run; // number of tile / window items
     }
     __syncthreads();
+    const uint32_t n_dense = block_base, n_groups = (n_empty + EMPTY_GROUP - 1) / EMPTY_GROUP;
+    const uint32_t grid_items = (U.tile_y_end - U.tile_y_begin) * U.tiles_x + (TILE_SPLITTABLE ? TILE_EXTRA_ITEMS : 0);
+    // after the tile items: one item per group of empty tiles, then nothing
+    for (uint32_t i = tid; i < n_groups; i += ALLOC_THREADS) W.tile_order[n_dense + i] = ITEM_EMPTY | i;
+    for (uint32_t i = n_dense + n_groups + tid; i < grid_items; i += ALLOC_THREADS) W.tile_order[i] = ITEM_NONE;
+    for (uint32_t i = n_empty + tid; i < n_groups * EMPTY_GROUP; i += ALLOC_THREADS) W.empty_tiles[i] = NO_SLOT;
     for (uint32_t t0 = tid; t0 < nc; t0 += ALLOC_THREADS * BATCH) {
-        uint32_t cost[BATCH];
+        uint32_t cost_k[BATCH];
 #pragma unroll
         for (int k = 0; k < BATCH; k++) {
             const uint32_t t = t0 + k * ALLOC_THREADS;
-            cost[k] = t < nc ? __ldcg(&W.tile_cost[t]) : COST_NOT_IN_STRIPE;
+            cost_k[k] = t < nc ? __ldcg(&W.tile_cost[t]) : COST_NOT_IN_STRIPE;
         }
 #pragma unroll
         for (int k = 0; k < BATCH; k++)
-            if (cost[k] != COST_NOT_IN_STRIPE)
-                W.tile_order[atomicAdd(&bucket_start[cost_bucket(cost[k])], 1u)] = t0 + k * ALLOC_THREADS;
+            if (cost_k[k] != COST_NOT_IN_STRIPE && !(cost_k[k] == 0 && group_empties)) {
+                const uint32_t t = t0 + k * ALLOC_THREADS, s = tile_splits(cost_k[k], target, max_split);
+                const uint32_t tx = t % U.tiles_x, tyy = t / U.tiles_x;
+                const uint32_t at = atomicAdd(&bucket_start[cost_bucket(cost_k[k] / s)], s);
+                for (uint32_t i = 0; i < s; i++) W.tile_order[at + i] = make_item(tx, tyy, s, i);
+            }
     }
 }
 
@@ -231,6 +316,10 @@ __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const __grid_constant__
 static int bin_blocks(const FrameDev &) { return 148 * 4; }
 void launch_bin_count(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream) {
     launch_pdl(k_bin<false>, bin_blocks(W), BIN_THREADS, stream, U, W);
+}
+uint32_t tile_grid_items(const FrameUniforms &U) { // k_tile's grid: one CTA per work-list slot
+    const uint32_t stripe_tiles = (U.tile_y_end - U.tile_y_begin) * U.tiles_x;
+    return stripe_tiles ? stripe_tiles + (TILE_SPLITTABLE ? TILE_EXTRA_ITEMS : 0) : 0;
 }
 void launch_alloc(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream) {
     launch_pdl(k_alloc, (U.n_coarse + ALLOC_THREADS - 1) / ALLOC_THREADS, ALLOC_THREADS, stream, U, W);

@@ -18,10 +18,11 @@ namespace drawb200 {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FrameUniforms U, const SceneDev S,
                                                 const FrameDev W) {
-    pdl_prologue();
+    pdl_prologue(U.pdl_early != 0);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     // per-frame reset of the binning state (the binning kernels run after this one on the same stream)
     for (uint32_t t = i; t < U.n_lists; t += gridDim.x * blockDim.x) W.list_count[t] = 0;
+    for (uint32_t t = i; t < U.n_coarse; t += gridDim.x * blockDim.x) W.tile_cost[t] = 0;
     if (i < 8) W.counters[i] = 0;
     const uint32_t n_desc = (S.n_triangles + 255) / 256;
     for (uint32_t t = i; t < n_desc; t += gridDim.x * blockDim.x) W.scan_desc[t] = 0ull;
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
                                                          const FrameDev W) {
     __shared__ uint32_t warp_tot[SETUP_THREADS / 32];
     __shared__ uint32_t s_ticket, s_base;
-    pdl_prologue();
+    pdl_prologue(U.pdl_early != 0);
 
     if (threadIdx.x == 0) s_ticket = atomicAdd(&W.counters[3], 1u);
     __syncthreads();
@@ -481,7 +482,7 @@ constexpr int CLIP_THREADS = 128;
 
 __global__ void __launch_bounds__(CLIP_THREADS) k_clip(const __grid_constant__ FrameUniforms U, const SceneDev S,
                                                        const FrameDev W) {
-    pdl_prologue();
+    pdl_prologue(U.pdl_early != 0);
     const uint32_t n = W.counters[5];
     for (uint32_t q = blockIdx.x * CLIP_THREADS + threadIdx.x; q < n; q += gridDim.x * CLIP_THREADS) {
         const uint2 item = W.clip_queue[q];

@@ -30,98 +30,141 @@
 
 namespace drawb200 {
 
-#ifndef DRAW_TILE_THREADS
-#define DRAW_TILE_THREADS 512
-#endif
-constexpr int TILE_THREADS = DRAW_TILE_THREADS;
-constexpr int CHUNK = 64; // large-list triangles staged per round
+constexpr int CHUNK = 64;      // triangles staged per round
+constexpr int CAND_CAP = 1024; // window filter: list references examined per segment
 constexpr int TILE_PIXELS = TILE_W * TILE_H;
-// phase A geometry: a warp owns a REGION x REGION_H rectangle (4 lanes across, 8 down), a lane a
-// 4 x BLK_H block of it
-constexpr int BLK_H = TILE_PIXELS / TILE_THREADS / 4;
+// phase A geometry (device_types.h): a warp owns a REGION x REGION_H rectangle (4 lanes across, 8 down),
+// a lane a 4 x BLK_H block of it
 constexpr int PX = 4 * BLK_H;
-constexpr int REGION_H = 8 * BLK_H;
 static_assert(BLK_H >= 1 && TILE_W / REGION * (TILE_H / REGION_H) * 32 == TILE_THREADS, "tile geometry");
 
-// One triangle prepared for the phase-A pixel loop (25 words; stride 25 is conflict-free for the
-// staging writes, and every read in the pixel loop is a broadcast).  The bbox is kept as floats
-// (exact: < 65536) so the loop does no int->float conversions (those run on the slow XU pipe).
-struct StagedTri {
-    float ecx[3], ecy[3], ek1[3], ek2[3], f[3];
-    float da, db, dc;
-    float g[3];   // early depth reject: depth_i / f_i (approximate), see TRI_EARLYZ
-    float thr[3]; // tame triangles: edge e passes  <=>  value > thr[e]  (0, or -0.5 when the tie rule admits 0)
-    float x0, x1, y0, y1;
-    uint32_t flags, id, slot;
-};
-static_assert(sizeof(StagedTri) == 31 * 4, "31 words: odd stride keeps the staging writes conflict-free");
+// A staged triangle is the first PREP_WORDS words of its PrepRec (device_types.h) in shared memory, at an
+// odd stride so that threads reading the same field of different triangles hit different banks; reads in
+// the phase-A pixel loop are broadcasts.  Word offsets:
+enum : int { S_ECX = 0, S_ECY = 3, S_EK1 = 6, S_EK2 = 9, S_F = 12, S_RF = 15, S_DA = 18, S_DB = 19, S_X0 = 20, S_X1 = 21,
+             S_Y0 = 22, S_Y1 = 23, S_DC = 24, S_FLAGS = 25, S_ID = 26, S_SLOT = 27 };
+constexpr int STAGE_STRIDE = PREP_WORDS + 1;
+static_assert(PREP_WORDS == 28 && (STAGE_STRIDE & 1) == 1 && offsetof(PrepRec, x0) == 4 * S_X0 &&
+              offsetof(PrepRec, flags) == 4 * S_FLAGS && offsetof(PrepRec, slot) == 4 * S_SLOT, "PrepRec layout");
 
-// Early depth reject.  For a covered pixel of a tame triangle with finite non-negative vertex depths,
-//   D = e0*da/f0 + e1*db/f1 + e2*dc/f2                       (real arithmetic, all terms >= 0)
-// and the reference's float depth d_ref = fl(fl(fl(e0/f0)*da + fl(e1/f1)*db) + fl(e2/f2)*dc) satisfies
-// |d_ref - D| <= 4.1 u D (u = 2^-24: one division, one product and two sums of non-negative terms),
-// while d_app = fma(e2, g2, fma(e1, g1, e0*g0)) with g_i = fl(d_i * fl(1/f_i)) satisfies
-// |d_app - D| <= 5.1 u D.  Hence d_ref >= d_app * (1 - 9.3u) > d_app * (1 - 2^-20), so
-//   d_app * (1 - 2^-20) > z   ==>   d_ref > z :  the fragment fails the strict `<` test and is not a tie,
-// and its three IEEE divisions can be skipped.  The bounds need normal (not denormal) products, so the
-// flag is only set when every g_i is 0 or >= 1e-30; NaN/inf make the comparison false or d_ref = inf.
-constexpr uint32_t TRI_EARLYZ = 16u;
-constexpr float EARLYZ_SCALE = 0.99999904632568359375f; // 1 - 2^-20
-
-__device__ __forceinline__ void stage_triangle(StagedTri *dst, const RasterRec *src, uint32_t slot) {
+// Copies n prepared records into shared memory: one 16-byte load per thread (8 threads per record, the
+// eighth idle), so a chunk of 64 is a single load per thread of a 512-thread CTA.
+__device__ __forceinline__ void stage_copy(float (*staged)[STAGE_STRIDE], const PrepRec *__restrict__ prep,
+                                           const uint32_t *refs, uint32_t n, int tid) {
+    for (uint32_t i = (uint32_t)tid; i < n * 8u; i += TILE_THREADS) {
+        const uint32_t k = i >> 3, q = i & 7u;
+        if (q == 7u) continue;
+        const uint32_t slot = refs[k];
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(prep + slot) + q);
+        float *d = staged[k] + 4 * q;
+        d[0] = __uint_as_float(v.x); d[1] = __uint_as_float(v.y); d[2] = __uint_as_float(v.z);
+        d[3] = q == 6u ? __uint_as_float(slot) : __uint_as_float(v.w);
+    }
+}
+// Phase D only (transparent records are not binned and have no PrepRec): prepare in place.
+__device__ __forceinline__ void stage_triangle(float *dst, const RasterRec *src, uint32_t slot) {
     RasterRec r = load_raster(src);
     if (r.id == NO_SLOT) { // empty transparent slot: an empty bbox makes every lane skip it
         r.bbx = 1u;        // x_min = 1 > x_max = 0
         r.bby = 1u;
     }
-    const TriEdges t = prepare_edges(r);
-    StagedTri &s = *dst;
+    PrepRec p;
+    make_prep(r, p);
+    p.slot = slot;
+    const float *w = reinterpret_cast<const float *>(&p);
+#pragma unroll
+    for (int i = 0; i < PREP_WORDS; i++) dst[i] = w[i];
+}
+
+// Window filter: keeps the references whose bbox meets the window (only their bbox quad is read).
+// Returns the number kept; cand[] is valid after the call (ends with a barrier).
+__device__ __forceinline__ uint32_t filter_refs(const uint32_t *__restrict__ list, uint32_t count,
+                                                const PrepRec *__restrict__ prep, uint32_t *cand, uint32_t *s_count,
+                                                float wx0f, float wx1f, float wy0f, float wy1f, int tid) {
+    __syncthreads(); // cand / s_count may still be in use by the previous segment
+    if (tid == 0) *s_count = 0;
+    __syncthreads();
+    const int lane = tid & 31;
+    for (uint32_t base = 0; base < count; base += TILE_THREADS) {
+        const uint32_t i = base + (uint32_t)tid;
+        bool keep = false;
+        uint32_t slot = 0;
+        if (i < count) {
+            slot = list[i];
+            const uint4 bb = __ldg(reinterpret_cast<const uint4 *>(prep + slot) + 5); // x0 x1 y0 y1
+            keep = !(__uint_as_float(bb.y) < wx0f || __uint_as_float(bb.x) > wx1f || __uint_as_float(bb.w) < wy0f ||
+                     __uint_as_float(bb.z) > wy1f);
+        }
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, keep);
+        uint32_t wbase = 0;
+        if (lane == 0 && ballot) wbase = atomicAdd(s_count, (uint32_t)__popc(ballot));
+        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+        if (keep) cand[wbase + __popc(ballot & ((1u << lane) - 1u))] = slot;
+    }
+    __syncthreads();
+    return *s_count;
+}
+
+// One triangle in registers (phase B2, phase D).
+struct TriRegs {
+    float ecx[3], ecy[3], ek1[3], ek2[3], f[3], rf[3];
+    float da, db, dc;
+    uint32_t flags;
+};
+__device__ __forceinline__ TriRegs tri_from_words(const float *w) {
+    TriRegs t;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        s.ecx[i] = t.ecx[i]; s.ecy[i] = t.ecy[i]; s.ek1[i] = t.ek1[i]; s.ek2[i] = t.ek2[i]; s.f[i] = t.f[i];
+        t.ecx[i] = w[S_ECX + i]; t.ecy[i] = w[S_ECY + i]; t.ek1[i] = w[S_EK1 + i]; t.ek2[i] = w[S_EK2 + i];
+        t.f[i] = w[S_F + i]; t.rf[i] = w[S_RF + i];
     }
-    s.da = r.da; s.db = r.db; s.dc = r.dc;
-    const float dep[3] = {r.da, r.db, r.dc};
-    bool earlyz = !(t.flags & TRI_SLOW);
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        s.thr[i] = (t.flags & (1u << i)) ? -0.5f : 0.0f; // edge values are integers: e >= 0 <=> e > -0.5
-        const float g = dep[i] * __frcp_rn(t.f[i]);
-        s.g[i] = g;
-        earlyz = earlyz && dep[i] >= 0.0f && dep[i] < 3.0e38f && (g == 0.0f || g >= 1e-30f);
-    }
-    s.x0 = (float)(r.bbx & 0xFFFF); s.x1 = (float)(r.bbx >> 16);
-    s.y0 = (float)(r.bby & 0xFFFF); s.y1 = (float)(r.bby >> 16);
-    s.flags = t.flags | (earlyz ? TRI_EARLYZ : 0u);
-    s.id = r.id;
-    s.slot = slot;
+    t.da = w[S_DA]; t.db = w[S_DB]; t.dc = w[S_DC];
+    t.flags = __float_as_uint(w[S_FLAGS]);
+    return t;
 }
 
 // Coverage + depth of one pixel (canvas.rs:673-682).  Tame triangles: sign tests on the
 // sign-normalised edge values, divisions only for covered pixels.  Others: the reference's literal
 // divide-then-compare.  The quotients e/f are the same either way.
-__device__ __forceinline__ bool cover_pixel(const float (&ecx)[3], const float (&ecy)[3], const float (&ek1)[3],
-                                            const float (&ek2)[3], const float (&f)[3], uint32_t flags, float da,
-                                            float db, float dc, float x, float y, float &depth) {
+__device__ __forceinline__ bool cover_pixel(const TriRegs &t, uint32_t flags, float x, float y, float &depth) {
     float e[3];
 #pragma unroll
-    for (int i = 0; i < 3; i++) e[i] = FSUB(FADD(FADD(FMUL(ecx[i], x), FMUL(ecy[i], y)), ek1[i]), ek2[i]);
+    for (int i = 0; i < 3; i++) e[i] = FSUB(FADD(FADD(FMUL(t.ecx[i], x), FMUL(t.ecy[i], y)), t.ek1[i]), t.ek2[i]);
     float bary[3];
     if (!(flags & TRI_SLOW)) {
         const bool in = (e[0] > 0.0f || (e[0] == 0.0f && (flags & 1u))) && (e[1] > 0.0f || (e[1] == 0.0f && (flags & 2u))) &&
                         (e[2] > 0.0f || (e[2] == 0.0f && (flags & 4u)));
         if (!in) return false;
+        if (flags & TRI_FASTDIV) {
 #pragma unroll
-        for (int i = 0; i < 3; i++) bary[i] = FDIV(e[i], f[i]);
+            for (int i = 0; i < 3; i++) bary[i] = exact_div(e[i], t.f[i], t.rf[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 3; i++) bary[i] = FDIV(e[i], t.f[i]);
+        }
     } else {
 #pragma unroll
-        for (int i = 0; i < 3; i++) bary[i] = FDIV(e[i], f[i]);
+        for (int i = 0; i < 3; i++) bary[i] = FDIV(e[i], t.f[i]);
         if (!(bary[0] >= 0.0f && bary[1] >= 0.0f && bary[2] >= 0.0f)) return false;
         if (!((bary[0] > 0.0f || (flags & 1u)) && (bary[1] > 0.0f || (flags & 2u)) && (bary[2] > 0.0f || (flags & 4u))))
             return false;
     }
-    depth = FADD(FADD(FMUL(bary[0], da), FMUL(bary[1], db)), FMUL(bary[2], dc)); // canvas.rs:682
+    depth = FADD(FADD(FMUL(bary[0], t.da), FMUL(bary[1], t.db)), FMUL(bary[2], t.dc)); // canvas.rs:682
     return true;
+}
+
+// Exact block reject on a staged triangle (see rect_may_cover in device_math.cuh).
+__device__ __forceinline__ bool staged_may_cover(const float *s, uint32_t flags, float lx, float hx, float ly, float hy) {
+    if (flags & TRI_SLOW) return true;
+    bool any = true;
+#pragma unroll
+    for (int e = 0; e < 3; e++) {
+        const float cx = s[S_ECX + e], cy = s[S_ECY + e];
+        const float xm = cx >= 0.0f ? hx : lx, ym = cy >= 0.0f ? hy : ly;
+        const float em = FSUB(FADD(FADD(FMUL(cx, xm), FMUL(cy, ym)), s[S_EK1 + e]), s[S_EK2 + e]);
+        any = any && em > ((flags >> e) & 1u ? -0.5f : 0.0f); // edge values are integers: e >= 0 <=> e > -0.5
+    }
+    return any;
 }
 
 // Order-preserving map float -> uint32 (-0 is folded onto +0: the reference's `<` treats them as
@@ -134,20 +177,76 @@ __device__ __forceinline__ unsigned long long make_key(float d, uint32_t slot) {
     return ((unsigned long long)depth_key(d) << 32) | slot;
 }
 
-__global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ FrameUniforms U, const SceneDev S,
+__global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(const __grid_constant__ FrameUniforms U, const SceneDev S,
                                                        const FrameDev W, uint8_t *__restrict__ color,
                                                        float *__restrict__ depth) {
     __shared__ unsigned long long keys[TILE_PIXELS]; // (depth key, slot), later (depth bits, draw id)
     __shared__ uint32_t colour[TILE_PIXELS];         // r | g << 8 | b << 16 | pad << 24
-    __shared__ StagedTri staged[CHUNK];
+    __shared__ float staged[CHUNK][STAGE_STRIDE];
+    __shared__ uint32_t cand[CAND_CAP];
     __shared__ float u8tab[256]; // (u8 as f32) / 255.0
+    __shared__ uint32_t s_cand_count;
     pdl_prologue();
 
-    const uint32_t tile = W.tile_order[blockIdx.x]; // heaviest tiles first (k_alloc)
-    const uint32_t tile_x = tile % U.tiles_x, tile_y = tile / U.tiles_x;
+    // work item (k_alloc, device_types.h): a tile, one pixel window of a dense tile, or a group of empty
+    // tiles; heaviest first
+    const uint32_t item = W.tile_order[blockIdx.x];
+    if (item == ITEM_NONE) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W_ = (int)U.canvas_w, H_ = (int)U.canvas_h;
+    const float depth_max = U.depth_max;
+
+    // ---- empty tiles: nothing to rasterise, write the clear colour and depth (canvas.rs:425-433) ----
+    // One tile per warp, two 256-byte rows (colour) per store instruction, pointers stepped by a row pair.
+    if (item & ITEM_EMPTY) {
+        const uint32_t et = W.empty_tiles[(item & (ITEM_EMPTY - 1u)) * EMPTY_GROUP + (uint32_t)warp];
+        if (et == NO_SLOT) return;
+        const int ex0 = (int)(et & (MAX_TILES_X - 1)) * TILE_W, ey0 = (int)(et >> 10) * TILE_H;
+        const uint32_t clear_px = 255u | (186u << 8) | (155u << 16) | (255u << 24); // memory order b g r pad
+        if ((W_ & 3) == 0) {
+            constexpr int QPR = TILE_W / 4, RPI = 32 / QPR; // 16-byte quads per tile row, rows per warp store
+            const int x = ex0 + (lane % QPR) * 4, r0 = lane / QPR;
+            const int rows = min(TILE_H, H_ - ey0);
+            if (x < W_) {
+                uint4 *cp = reinterpret_cast<uint4 *>(color + ((size_t)(H_ - 1 - ey0 - r0) * W_ + x) * 4);
+                float4 *dp = reinterpret_cast<float4 *>(depth + (size_t)(ey0 + r0) * W_ + x);
+                const ptrdiff_t step = (ptrdiff_t)RPI * (W_ / 4); // in 16-byte units: colour rows go up, depth rows down
+                const uint4 cv = make_uint4(clear_px, clear_px, clear_px, clear_px);
+                const float4 dv = make_float4(depth_max, depth_max, depth_max, depth_max);
+#pragma unroll 4
+                for (int r = r0; r < rows; r += RPI, cp -= step, dp += step) {
+                    *cp = cv;
+                    *dp = dv;
+                }
+            }
+        } else {
+            for (int p = lane; p < TILE_PIXELS; p += 32) {
+                const int x = ex0 + (p & (TILE_W - 1)), y = ey0 + p / TILE_W;
+                if (x >= W_ || y >= H_) continue;
+                reinterpret_cast<uint32_t *>(color)[(size_t)(H_ - 1 - y) * W_ + x] = clear_px;
+                depth[(size_t)y * W_ + x] = depth_max;
+            }
+        }
+        if (W.tile_cycles && lane == 0) atomicMax(&W.tile_cycles[(et >> 10) * U.tiles_x + (et & (MAX_TILES_X - 1))], 1u);
+        return;
+    }
+    const uint32_t tile_x = item & (MAX_TILES_X - 1), tile_y = (item >> 10) & (MAX_TILES_Y - 1);
+    const uint32_t tile = tile_y * U.tiles_x + tile_x;
     const long long t_start = W.tile_cycles ? clock64() : 0;
     const int tx0 = (int)tile_x * TILE_W, ty0 = (int)tile_y * TILE_H;
+
+    // pixel window of the tile this CTA renders (the whole tile unless k_alloc cut the tile up)
+    int wx0 = tx0, wy0 = ty0, ww = TILE_W, wh = TILE_H;
+    if (TILE_SPLITTABLE) {
+        wx0 = tx0 + (int)((item >> 21) & 3u) * REGION;
+        wy0 = ty0 + (int)((item >> 23) & 3u) * REGION_H;
+        ww = (int)(((item >> 25) & 3u) + 1u) * REGION;
+        wh = (int)(((item >> 27) & 3u) + 1u) * REGION_H;
+    }
+    const bool windowed = ww != TILE_W || wh != TILE_H; // then the lists hold triangles that miss the window
+    const int ww_shift = 31 - __clz(ww), n_win = ww * wh; // ww is a power of two
+    const float wx0f = (float)wx0, wy0f = (float)wy0, wx1f = (float)(wx0 + ww - 1), wy1f = (float)(wy0 + wh - 1);
+    const float tx0f = (float)tx0, ty0f = (float)ty0;
 
     // (loads issued together; masked afterwards so that they do not wait for the overflow flag)
     const uint32_t overflow = W.counters[2];
@@ -158,39 +257,16 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ F
     const bool usable = overflow == 0;
     if (!usable) l_count = m_count = s_count = 0;
     const RasterRec *__restrict__ rrec = W.rrec;
-    const float depth_max = U.depth_max;
-
-    // ---- empty tile: nothing to rasterise, write the clear colour and depth (canvas.rs:425-433) ----
-    if (l_count + m_count + s_count == 0 && (S.n_transparent == 0 || !usable)) {
-        const int W_ = (int)U.canvas_w, H_ = (int)U.canvas_h;
-        const uint32_t clear_px = 255u | (186u << 8) | (155u << 16) | (255u << 24); // memory order b g r pad
-        if ((W_ & 3) == 0) {
-            for (int q = tid; q < TILE_PIXELS / 4; q += TILE_THREADS) { // 4 pixels (16 B) per store
-                const int x = tx0 + (q & (TILE_W / 4 - 1)) * 4, y = ty0 + q / (TILE_W / 4);
-                if (x >= W_ || y >= H_) continue;
-                *reinterpret_cast<uint4 *>(color + ((size_t)(H_ - 1 - y) * W_ + x) * 4) =
-                    make_uint4(clear_px, clear_px, clear_px, clear_px);
-                *reinterpret_cast<float4 *>(depth + (size_t)y * W_ + x) = make_float4(depth_max, depth_max, depth_max, depth_max);
-            }
-        } else {
-            for (int p = tid; p < TILE_PIXELS; p += TILE_THREADS) {
-                const int x = tx0 + (p & (TILE_W - 1)), y = ty0 + p / TILE_W;
-                if (x >= W_ || y >= H_) continue;
-                reinterpret_cast<uint32_t *>(color)[(size_t)(H_ - 1 - y) * W_ + x] = clear_px;
-                depth[(size_t)y * W_ + x] = depth_max;
-            }
-        }
-        if (W.tile_cycles && tid == 0) W.tile_cycles[tile] = (uint32_t)(clock64() - t_start);
-        return;
-    }
+    const PrepRec *__restrict__ prep = W.prep;
     fill_u8_table(u8tab, tid, TILE_THREADS); // visible after the barrier that ends phase A
 
-    // ---- phase A: large triangles, every lane tests its own 4x2 block ------------------------------
+    // ---- phase A: large triangles, every lane tests its own 4 x BLK_H block -----------------------
     {
-        // warp -> 16x16 region, lane -> 4x2 block (canvas coordinates: x right, y = depth-buffer row)
+        // warp -> REGION x REGION_H region, lane -> 4 x BLK_H block (canvas coordinates: x right, y = depth-buffer row)
         constexpr int WARPS_X = TILE_W / REGION;
         const int rx0 = tx0 + (warp % WARPS_X) * REGION, ry0 = ty0 + (warp / WARPS_X) * REGION_H;
         const int bx0 = rx0 + (lane & 3) * 4, by0 = ry0 + (lane >> 2) * BLK_H;
+        const bool warp_in = rx0 >= wx0 && rx0 < wx0 + ww && ry0 >= wy0 && ry0 < wy0 + wh; // regions tile the window
         const float fx0 = (float)rx0, fy0 = (float)ry0, fx1 = fx0 + (float)(REGION - 1), fy1 = fy0 + (float)(REGION_H - 1);
         float xf[4], yf[BLK_H];
 #pragma unroll
@@ -205,75 +281,99 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ F
             sl[i] = NO_SLOT;
         }
 #pragma unroll 1
-        for (uint32_t base = 0; base < l_count; base += CHUNK) {
-            const uint32_t n = min((uint32_t)CHUNK, l_count - base);
-            __syncthreads();
-            if ((uint32_t)tid < n) {
-                const uint32_t slot = W.list_refs[l_begin + base + tid];
-                stage_triangle(staged + tid, rrec + slot, slot);
+        for (uint32_t seg = 0; seg < l_count; seg += CAND_CAP) {
+            const uint32_t seg_n = min((uint32_t)CAND_CAP, l_count - seg);
+            const uint32_t *refs = W.list_refs + l_begin + seg;
+            uint32_t n_refs = seg_n;
+            if (windowed) {
+                n_refs = filter_refs(refs, seg_n, prep, cand, &s_cand_count, wx0f, wx1f, wy0f, wy1f, tid);
+                refs = cand;
             }
-            __syncthreads();
 #pragma unroll 1
-            for (uint32_t k = 0; k < n; k++) {
-                const StagedTri &s = staged[k];
-                if (s.x1 < fx0 || s.x0 > fx1 || s.y1 < fy0 || s.y0 > fy1) continue; // warp-uniform
-                const float lo_x = fmaxf(s.x0, xf[0]), hi_x = fminf(s.x1, xf[3]);
-                const float lo_y = fmaxf(s.y0, yf[0]), hi_y = fminf(s.y1, yf[BLK_H - 1]);
-                if (lo_x > hi_x || lo_y > hi_y) continue;
-                const uint32_t flags = s.flags, slot = s.slot;
-                if (!(flags & TRI_SLOW)) {
-                    // block-level reject at the best corner of the clipped block (exact, see rect_may_cover)
-                    bool any = true;
+            for (uint32_t base = 0; base < n_refs; base += CHUNK) {
+                const uint32_t n = min((uint32_t)CHUNK, n_refs - base);
+                __syncthreads();
+                stage_copy(staged, prep, refs + base, n, tid);
+                __syncthreads();
+#pragma unroll 1
+                for (uint32_t k = 0; k < (warp_in ? n : 0u); k++) {
+                    const float *s = staged[k];
+                    const float sx0 = s[S_X0], sx1 = s[S_X1], sy0 = s[S_Y0], sy1 = s[S_Y1];
+                    if (sx1 < fx0 || sx0 > fx1 || sy1 < fy0 || sy0 > fy1) continue; // warp-uniform
+                    const float lo_x = fmaxf(sx0, xf[0]), hi_x = fminf(sx1, xf[3]);
+                    const float lo_y = fmaxf(sy0, yf[0]), hi_y = fminf(sy1, yf[BLK_H - 1]);
+                    if (lo_x > hi_x || lo_y > hi_y) continue;
+                    const uint32_t flags = __float_as_uint(s[S_FLAGS]), slot = __float_as_uint(s[S_SLOT]);
+                    if (!(flags & TRI_SLOW)) {
+                        // block-level reject at the best corner of the clipped block (exact, see rect_may_cover)
+                        if (!staged_may_cover(s, flags, lo_x, hi_x, lo_y, hi_y)) continue;
+                        const float thr0 = (flags & 1u) ? -0.5f : 0.0f, thr1 = (flags & 2u) ? -0.5f : 0.0f,
+                                    thr2 = (flags & 4u) ? -0.5f : 0.0f;
+                        const float da = s[S_DA], db = s[S_DB], dc = s[S_DC];
+                        const float rf0 = s[S_RF], rf1 = s[S_RF + 1], rf2 = s[S_RF + 2];
+                        const float g0 = FMUL(da, rf0), g1 = FMUL(db, rf1), g2 = FMUL(dc, rf2);
+                        // edge values of the block's pixels (f > 0 after sign normalisation:
+                        // alpha >= 0 <=> e >= 0, alpha > 0 <=> e > 0), coverage and early depth reject, branch-free
+                        float e0[PX], e1[PX], e2[PX];
+                        uint32_t mask = 0;
+                        float pys[3][BLK_H];
 #pragma unroll
-                    for (int e = 0; e < 3; e++) {
-                        const float cx = s.ecx[e], cy = s.ecy[e];
-                        const float xm = cx >= 0.0f ? hi_x : lo_x, ym = cy >= 0.0f ? hi_y : lo_y;
-                        const float em = FSUB(FADD(FADD(FMUL(cx, xm), FMUL(cy, ym)), s.ek1[e]), s.ek2[e]);
-                        any = any && em > s.thr[e];
-                    }
-                    if (!any) continue;
-                    float pxs[3][4], pys[3][BLK_H];
+                        for (int e = 0; e < 3; e++)
 #pragma unroll
-                    for (int e = 0; e < 3; e++) {
+                            for (int j = 0; j < BLK_H; j++) pys[e][j] = FMUL(s[S_ECY + e], yf[j]);
 #pragma unroll
-                        for (int i = 0; i < 4; i++) pxs[e][i] = FMUL(s.ecx[e], xf[i]);
+                        for (int j = 0; j < BLK_H; j++) {
 #pragma unroll
-                        for (int j = 0; j < BLK_H; j++) pys[e][j] = FMUL(s.ecy[e], yf[j]);
-                    }
+                            for (int i = 0; i < 4; i++) {
+                                const int p = j * 4 + i;
+                                e0[p] = FSUB(FADD(FADD(FMUL(s[S_ECX], xf[i]), pys[0][j]), s[S_EK1]), s[S_EK2]);
+                                e1[p] = FSUB(FADD(FADD(FMUL(s[S_ECX + 1], xf[i]), pys[1][j]), s[S_EK1 + 1]), s[S_EK2 + 1]);
+                                e2[p] = FSUB(FADD(FADD(FMUL(s[S_ECX + 2], xf[i]), pys[2][j]), s[S_EK1 + 2]), s[S_EK2 + 2]);
+                                bool in = xf[i] >= lo_x && xf[i] <= hi_x && yf[j] >= lo_y && yf[j] <= hi_y && e0[p] > thr0 &&
+                                          e1[p] > thr1 && e2[p] > thr2;
+                                // early depth reject (exactly conservative, see TRI_EARLYZ): skip the divisions
+                                if (flags & TRI_EARLYZ)
+                                    in = in && !(fmaf(e2[p], g2, fmaf(e1[p], g1, e0[p] * g0)) * EARLYZ_SCALE > zb[p]);
+                                mask |= (in ? 1u : 0u) << p;
+                            }
+                        }
+                        if (!mask) continue;
+                        if (flags & TRI_FASTDIV) {
+                            const float f0 = s[S_F], f1 = s[S_F + 1], f2 = s[S_F + 2];
 #pragma unroll
-                    for (int j = 0; j < BLK_H; j++) {
+                            for (int p = 0; p < PX; p++) { // all pixels of the block: no branches, the quotients overlap
+                                const float alpha = exact_div(e0[p], f0, rf0), beta = exact_div(e1[p], f1, rf1),
+                                            gama = exact_div(e2[p], f2, rf2);
+                                const float d = FADD(FADD(FMUL(alpha, da), FMUL(beta, db)), FMUL(gama, dc)); // canvas.rs:682
+                                // strict `<` (canvas.rs:923); on equal depth the earlier draw (smaller slot) stays
+                                const bool take = ((mask >> p) & 1u) && (d < zb[p] || (d == zb[p] && slot < sl[p] && sl[p] != NO_SLOT));
+                                zb[p] = take ? d : zb[p];
+                                sl[p] = take ? slot : sl[p];
+                            }
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            if (xf[i] < lo_x || xf[i] > hi_x || yf[j] < lo_y || yf[j] > hi_y) continue;
-                            // f > 0 after sign normalisation: alpha >= 0 <=> e >= 0, alpha > 0 <=> e > 0
-                            const float e0 = FSUB(FADD(FADD(pxs[0][i], pys[0][j]), s.ek1[0]), s.ek2[0]);
-                            const float e1 = FSUB(FADD(FADD(pxs[1][i], pys[1][j]), s.ek1[1]), s.ek2[1]);
-                            const float e2 = FSUB(FADD(FADD(pxs[2][i], pys[2][j]), s.ek1[2]), s.ek2[2]);
-                            if (!(e0 > s.thr[0] && e1 > s.thr[1] && e2 > s.thr[2])) continue;
-                            const int p = j * 4 + i;
-                            // early depth reject (exactly conservative, see TRI_EARLYZ): skip the divisions
-                            if ((flags & TRI_EARLYZ) &&
-                                fmaf(e2, s.g[2], fmaf(e1, s.g[1], e0 * s.g[0])) * EARLYZ_SCALE > zb[p])
-                                continue;
-                            const float alpha = FDIV(e0, s.f[0]), beta = FDIV(e1, s.f[1]), gama = FDIV(e2, s.f[2]);
-                            const float d = FADD(FADD(FMUL(alpha, s.da), FMUL(beta, s.db)), FMUL(gama, s.dc)); // canvas.rs:682
-                            // strict `<` (canvas.rs:923); on equal depth the earlier draw (smaller slot) stays
+                            for (int p = 0; p < PX; p++) {
+                                if (!((mask >> p) & 1u)) continue;
+                                const float alpha = FDIV(e0[p], s[S_F]), beta = FDIV(e1[p], s[S_F + 1]), gama = FDIV(e2[p], s[S_F + 2]);
+                                const float d = FADD(FADD(FMUL(alpha, da), FMUL(beta, db)), FMUL(gama, dc));
+                                if (d < zb[p] || (d == zb[p] && slot < sl[p] && sl[p] != NO_SLOT)) {
+                                    zb[p] = d;
+                                    sl[p] = slot;
+                                }
+                            }
+                        }
+                    } else {
+                        const TriRegs t = tri_from_words(s);
+#pragma unroll
+                        for (int p = 0; p < PX; p++) {
+                            const float x = xf[p & 3], y = yf[p >> 2];
+                            if (x < lo_x || x > hi_x || y < lo_y || y > hi_y) continue;
+                            float d;
+                            if (!cover_pixel(t, flags, x, y, d)) continue;
                             if (d < zb[p] || (d == zb[p] && slot < sl[p] && sl[p] != NO_SLOT)) {
                                 zb[p] = d;
                                 sl[p] = slot;
                             }
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int p = 0; p < PX; p++) {
-                        const float x = xf[p & 3], y = yf[p >> 2];
-                        if (x < lo_x || x > hi_x || y < lo_y || y > hi_y) continue;
-                        float d;
-                        if (!cover_pixel(s.ecx, s.ecy, s.ek1, s.ek2, s.f, flags, s.da, s.db, s.dc, x, y, d)) continue;
-                        if (d < zb[p] || (d == zb[p] && slot < sl[p] && sl[p] != NO_SLOT)) {
-                            zb[p] = d;
-                            sl[p] = slot;
                         }
                     }
                 }
@@ -288,120 +388,194 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ F
     }
     __syncthreads();
 
-    if (W.tile_cycles && tid == 0) W.tile_cycles[U.n_coarse + tile] = (uint32_t)(clock64() - t_start); // end of phase A
+#ifndef DRAW_TAP_B
+    if (W.tile_cycles && tid == 0) atomicMax(&W.tile_cycles[U.n_coarse + tile], (uint32_t)(clock64() - t_start)); // end of phase A
+#endif
     // ---- phase B1: medium triangles -------------------------------------------------------------------
-    // Per chunk of 64 triangles: (1) one thread per triangle stages it and counts the 8x4-pixel blocks of
-    // its bbox inside the tile; (2) coarse raster: one thread per (triangle, block) runs the exact block
-    // test and queues the blocks that can be covered; (3) fine raster: warps take queued blocks, one
-    // pixel per lane, and commit covered fragments with atomicMin on the key.
+    // Per chunk of 64 triangles: (1) the chunk is staged and one thread per triangle counts the 8x4-pixel
+    // blocks of its bbox inside the window; (2) coarse raster: one thread per (triangle, block) runs the
+    // exact block test and queues the blocks that can be covered; (3) fine raster: warps take queued
+    // blocks, one pixel per lane, and commit covered fragments with atomicMin on the key.
     {
         __shared__ uint16_t queue[CHUNK * (TILE_W / 8) * (TILE_H / 4)]; // item = tri | bx << 6 | by << 9
         __shared__ uint32_t blk_prefix[CHUNK + 1];
         __shared__ uint32_t q_count;
-        const float tx0f = (float)tx0, ty0f = (float)ty0, tx1f = (float)(tx0 + TILE_W - 1), ty1f = (float)(ty0 + TILE_H - 1);
+#ifdef DRAW_TAP_B
+        long long tap_stage = 0, tap_coarse = 0, tap_fine = 0;
+#endif
+#if DRAW_TAP_B == 2
+        long long tap_filter = 0;
+#endif
 #pragma unroll 1
-        for (uint32_t base = 0; base < m_count; base += CHUNK) {
-            const uint32_t n = min((uint32_t)CHUNK, m_count - base);
-            __syncthreads();
-            if ((uint32_t)tid < n) {
-                const uint32_t slot = W.list_refs[m_begin + base + tid];
-                stage_triangle(staged + tid, rrec + slot, slot);
-                const StagedTri &t = staged[tid];
-                const float w = FSUB(fminf(t.x1, tx1f), fmaxf(t.x0, tx0f)), h = FSUB(fminf(t.y1, ty1f), fmaxf(t.y0, ty0f));
-                blk_prefix[tid + 1] = ((uint32_t)w / 8u + 1u) * ((uint32_t)h / 4u + 1u); // blocks of 8x4 from the bbox corner
+        for (uint32_t seg = 0; seg < m_count; seg += CAND_CAP) {
+            const uint32_t seg_n = min((uint32_t)CAND_CAP, m_count - seg);
+            const uint32_t *refs = W.list_refs + m_begin + seg;
+            uint32_t n_refs = seg_n;
+            if (windowed) {
+#if DRAW_TAP_B == 2
+                const long long tf0 = clock64();
+#endif
+                n_refs = filter_refs(refs, seg_n, prep, cand, &s_cand_count, wx0f, wx1f, wy0f, wy1f, tid);
+                refs = cand;
+#if DRAW_TAP_B == 2
+                tap_filter += clock64() - tf0;
+#endif
             }
-            if (tid == 0) {
-                blk_prefix[0] = 0;
-                q_count = 0;
-            }
-            __syncthreads();
-            if (warp == 0) { // inclusive scan of the (up to 64) block counts
-                uint32_t a = lane < n ? blk_prefix[lane + 1] : 0u, b = lane + 32 < n ? blk_prefix[lane + 33] : 0u;
+#pragma unroll 1
+            for (uint32_t base = 0; base < n_refs; base += CHUNK) {
+                const uint32_t n = min((uint32_t)CHUNK, n_refs - base);
+                __syncthreads();
+#ifdef DRAW_TAP_B
+                const long long tb0 = clock64();
+#endif
+                stage_copy(staged, prep, refs + base, n, tid);
+                if (tid == 0) {
+                    blk_prefix[0] = 0;
+                    q_count = 0;
+                }
+                __syncthreads();
+                if (warp == 0) { // block counts (8x4 blocks from the corner of the bbox clipped to the window) and their inclusive scan
+                    uint32_t cnt[2];
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t ua = __shfl_up_sync(0xFFFFFFFFu, a, d), ub = __shfl_up_sync(0xFFFFFFFFu, b, d);
-                    if (lane >= d) { a += ua; b += ub; }
-                }
-                b += __shfl_sync(0xFFFFFFFFu, a, 31);
-                if (lane < n) blk_prefix[lane + 1] = a;
-                if (lane + 32 < n) blk_prefix[lane + 33] = b;
-            }
-            __syncthreads();
-            // (2) coarse raster
-            const uint32_t total = blk_prefix[n];
-#pragma unroll 1
-            for (uint32_t pbase = 0; pbase < total; pbase += TILE_THREADS) {
-                const uint32_t p = pbase + tid;
-                bool hit = false;
-                uint32_t item = 0;
-                if (p < total) {
-                    uint32_t lo = 0, hi = n; // largest k with blk_prefix[k] <= p
-                    while (hi - lo > 1) {
-                        const uint32_t mid = (lo + hi) >> 1;
-                        if (blk_prefix[mid] <= p) lo = mid; else hi = mid;
+                    for (int h = 0; h < 2; h++) {
+                        const uint32_t k = (uint32_t)lane + 32u * h;
+                        cnt[h] = 0;
+                        if (k < n) {
+                            const float *t = staged[k];
+                            const float w = FSUB(fminf(t[S_X1], wx1f), fmaxf(t[S_X0], wx0f)), hgt = FSUB(fminf(t[S_Y1], wy1f), fmaxf(t[S_Y0], wy0f));
+                            cnt[h] = (w < 0.0f || hgt < 0.0f) ? 0u : ((uint32_t)w / 8u + 1u) * ((uint32_t)hgt / 4u + 1u);
+                        }
                     }
-                    const StagedTri &t = staged[lo];
-                    const float lx = fmaxf(t.x0, tx0f), hx = fminf(t.x1, tx1f), ly = fmaxf(t.y0, ty0f), hy = fminf(t.y1, ty1f);
-                    const uint32_t nbx = (uint32_t)FSUB(hx, lx) / 8u + 1u, local = p - blk_prefix[lo];
-                    const uint32_t bxi = local % nbx, byi = local / nbx;
-                    const float bx = FADD(lx, (float)(bxi * 8u)), by = FADD(ly, (float)(byi * 4u));
-                    hit = rect_may_cover(t, bx, fminf(FADD(bx, 7.0f), hx), by, fminf(FADD(by, 3.0f), hy));
-                    item = lo | (bxi << 6) | (byi << 9);
+                    uint32_t a = cnt[0], b = cnt[1];
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t ua = __shfl_up_sync(0xFFFFFFFFu, a, d), ub = __shfl_up_sync(0xFFFFFFFFu, b, d);
+                        if (lane >= d) { a += ua; b += ub; }
+                    }
+                    b += __shfl_sync(0xFFFFFFFFu, a, 31);
+                    if ((uint32_t)lane < n) blk_prefix[lane + 1] = a;
+                    if ((uint32_t)lane + 32u < n) blk_prefix[lane + 33] = b;
                 }
-                const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
-                uint32_t wbase = 0;
-                if (lane == 0 && ballot) wbase = atomicAdd(&q_count, (uint32_t)__popc(ballot));
-                wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-                if (hit) queue[wbase + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)item;
-            }
-            __syncthreads();
-            // (3) fine raster
-            const uint32_t nq = q_count;
-            const float dxf = (float)(lane & 7), dyf = (float)(lane >> 3);
+                __syncthreads();
+#ifdef DRAW_TAP_B
+                const long long tb1 = clock64();
+#endif
+                // (2) coarse raster
+                const uint32_t total = blk_prefix[n];
 #pragma unroll 1
-            for (uint32_t j = (uint32_t)warp; j < nq; j += TILE_THREADS / 32) {
-                const uint32_t item = queue[j];
-                const StagedTri &t = staged[item & 63u];
-                const float lx = fmaxf(t.x0, tx0f), hx = fminf(t.x1, tx1f), ly = fmaxf(t.y0, ty0f), hy = fminf(t.y1, ty1f);
-                const float x = FADD(FADD(lx, (float)(((item >> 6) & 7u) * 8u)), dxf);
-                const float y = FADD(FADD(ly, (float)((item >> 9) * 4u)), dyf);
-                if (x > hx || y > hy) continue;
-                unsigned long long *cell = &keys[(int)FSUB(y, ty0f) * TILE_W + (int)FSUB(x, tx0f)];
-                float d;
-                if (!(t.flags & TRI_SLOW)) {
-                    const float e0 = FSUB(FADD(FADD(FMUL(t.ecx[0], x), FMUL(t.ecy[0], y)), t.ek1[0]), t.ek2[0]);
-                    const float e1 = FSUB(FADD(FADD(FMUL(t.ecx[1], x), FMUL(t.ecy[1], y)), t.ek1[1]), t.ek2[1]);
-                    const float e2 = FSUB(FADD(FADD(FMUL(t.ecx[2], x), FMUL(t.ecy[2], y)), t.ek1[2]), t.ek2[2]);
-                    if (!(e0 > t.thr[0] && e1 > t.thr[1] && e2 > t.thr[2])) continue;
-                    // early depth reject in key space (exactly conservative, see TRI_EARLYZ)
-                    if ((t.flags & TRI_EARLYZ) &&
-                        depth_key(fmaf(e2, t.g[2], fmaf(e1, t.g[1], e0 * t.g[0])) * EARLYZ_SCALE) > (uint32_t)(*cell >> 32))
-                        continue;
-                    const float alpha = FDIV(e0, t.f[0]), beta = FDIV(e1, t.f[1]), gama = FDIV(e2, t.f[2]);
-                    d = FADD(FADD(FMUL(alpha, t.da), FMUL(beta, t.db)), FMUL(gama, t.dc)); // canvas.rs:682
-                } else if (!cover_pixel(t.ecx, t.ecy, t.ek1, t.ek2, t.f, t.flags, t.da, t.db, t.dc, x, y, d)) {
-                    continue;
+                for (uint32_t pbase = 0; pbase < total; pbase += TILE_THREADS) {
+                    const uint32_t p = pbase + tid;
+                    bool hit = false;
+                    uint32_t qitem = 0;
+                    if (p < total) {
+                        uint32_t lo = 0, hi = n; // largest k with blk_prefix[k] <= p
+                        while (hi - lo > 1) {
+                            const uint32_t mid = (lo + hi) >> 1;
+                            if (blk_prefix[mid] <= p) lo = mid; else hi = mid;
+                        }
+                        const float *t = staged[lo];
+                        const float lx = fmaxf(t[S_X0], wx0f), hx = fminf(t[S_X1], wx1f), ly = fmaxf(t[S_Y0], wy0f), hy = fminf(t[S_Y1], wy1f);
+                        const uint32_t nbx = (uint32_t)FSUB(hx, lx) / 8u + 1u, local = p - blk_prefix[lo];
+                        const uint32_t bxi = local % nbx, byi = local / nbx;
+                        const float bx = FADD(lx, (float)(bxi * 8u)), by = FADD(ly, (float)(byi * 4u));
+                        hit = staged_may_cover(t, __float_as_uint(t[S_FLAGS]), bx, fminf(FADD(bx, 7.0f), hx), by, fminf(FADD(by, 3.0f), hy));
+                        qitem = lo | (bxi << 6) | (byi << 9);
+                    }
+                    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
+                    uint32_t wbase = 0;
+                    if (lane == 0 && ballot) wbase = atomicAdd(&q_count, (uint32_t)__popc(ballot));
+                    wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+                    if (hit) queue[wbase + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)qitem;
                 }
-                if (!(d < depth_max)) continue;
-                const unsigned long long key = make_key(d, t.slot);
-                if (key < *cell) atomicMin(cell, key);
+                __syncthreads();
+#ifdef DRAW_TAP_B
+                const long long tb2 = clock64();
+#endif
+                // (3) fine raster
+                const uint32_t nq = q_count;
+                const float dxf = (float)(lane & 7), dyf = (float)(lane >> 3);
+#pragma unroll 1
+                for (uint32_t j = (uint32_t)warp; j < nq; j += TILE_THREADS / 32) {
+                    const uint32_t qitem = queue[j];
+                    const float *t = staged[qitem & 63u];
+                    const float lx = fmaxf(t[S_X0], wx0f), hx = fminf(t[S_X1], wx1f), ly = fmaxf(t[S_Y0], wy0f), hy = fminf(t[S_Y1], wy1f);
+                    const float x = FADD(FADD(lx, (float)(((qitem >> 6) & 7u) * 8u)), dxf);
+                    const float y = FADD(FADD(ly, (float)((qitem >> 9) * 4u)), dyf);
+                    if (x > hx || y > hy) continue;
+                    unsigned long long *cell = &keys[(int)FSUB(y, ty0f) * TILE_W + (int)FSUB(x, tx0f)];
+                    const uint32_t flags = __float_as_uint(t[S_FLAGS]);
+                    float d;
+                    if (!(flags & TRI_SLOW)) {
+                        const float e0 = FSUB(FADD(FADD(FMUL(t[S_ECX], x), FMUL(t[S_ECY], y)), t[S_EK1]), t[S_EK2]);
+                        const float e1 = FSUB(FADD(FADD(FMUL(t[S_ECX + 1], x), FMUL(t[S_ECY + 1], y)), t[S_EK1 + 1]), t[S_EK2 + 1]);
+                        const float e2 = FSUB(FADD(FADD(FMUL(t[S_ECX + 2], x), FMUL(t[S_ECY + 2], y)), t[S_EK1 + 2]), t[S_EK2 + 2]);
+                        if (!(e0 > ((flags & 1u) ? -0.5f : 0.0f) && e1 > ((flags & 2u) ? -0.5f : 0.0f) && e2 > ((flags & 4u) ? -0.5f : 0.0f)))
+                            continue;
+                        const float da = t[S_DA], db = t[S_DB], dc = t[S_DC];
+                        const float rf0 = t[S_RF], rf1 = t[S_RF + 1], rf2 = t[S_RF + 2];
+                        // early depth reject in key space (exactly conservative, see TRI_EARLYZ)
+                        if ((flags & TRI_EARLYZ) &&
+                            depth_key(fmaf(e2, FMUL(dc, rf2), fmaf(e1, FMUL(db, rf1), e0 * FMUL(da, rf0))) * EARLYZ_SCALE) > (uint32_t)(*cell >> 32))
+                            continue;
+                        float alpha, beta, gama;
+                        if (flags & TRI_FASTDIV) {
+                            alpha = exact_div(e0, t[S_F], rf0); beta = exact_div(e1, t[S_F + 1], rf1); gama = exact_div(e2, t[S_F + 2], rf2);
+                        } else {
+                            alpha = FDIV(e0, t[S_F]); beta = FDIV(e1, t[S_F + 1]); gama = FDIV(e2, t[S_F + 2]);
+                        }
+                        d = FADD(FADD(FMUL(alpha, da), FMUL(beta, db)), FMUL(gama, dc)); // canvas.rs:682
+                    } else {
+                        const TriRegs tr = tri_from_words(t);
+                        if (!cover_pixel(tr, flags, x, y, d)) continue;
+                    }
+                    if (!(d < depth_max)) continue;
+                    const unsigned long long key = make_key(d, __float_as_uint(t[S_SLOT]));
+                    if (key < *cell) atomicMin(cell, key);
+                }
+#ifdef DRAW_TAP_B
+                __syncthreads();
+                tap_stage += tb1 - tb0; tap_coarse += tb2 - tb1; tap_fine += clock64() - tb2;
+#endif
             }
         }
+#if DRAW_TAP_B == 1
+        if (W.tile_cycles && tid == 0) { // debug build: phase taps replaced by B1's stage / stage+coarse totals
+            atomicMax(&W.tile_cycles[U.n_coarse + tile], (uint32_t)tap_stage);
+            atomicMax(&W.tile_cycles[2 * U.n_coarse + tile], (uint32_t)(tap_stage + tap_coarse));
+            atomicMax(&W.tile_cycles[tile], (uint32_t)(tap_stage + tap_coarse + tap_fine));
+        }
+#endif
+#if DRAW_TAP_B == 2
+        if (W.tile_cycles && tid == 0) atomicMax(&W.tile_cycles[U.n_coarse + tile], (uint32_t)tap_filter); // medium filter
+#endif
     }
+#if DRAW_TAP_B == 2
+    const long long tb2_0 = clock64();
+#endif
     // ---- phase B2: small triangles, one per lane, atomicMin on the key --------------------------
     // (item j of a round goes to lane j / warps of warp j % warps, so a short list spreads over all warps)
     for (uint32_t i = (uint32_t)(lane * (TILE_THREADS / 32) + warp); i < s_count; i += TILE_THREADS) {
         const uint32_t slot = W.list_refs[s_begin + i];
-        const RasterRec r = load_raster(rrec + slot);
-        const TriEdges t = prepare_edges(r);
-        const int lx = max((int)(r.bbx & 0xFFFF), tx0), hx = min((int)(r.bbx >> 16), tx0 + TILE_W - 1);
-        const int ly = max((int)(r.bby & 0xFFFF), ty0), hy = min((int)(r.bby >> 16), ty0 + TILE_H - 1);
+        const uint4 *pq = reinterpret_cast<const uint4 *>(prep + slot);
+        const uint4 bb = __ldg(pq + 5); // x0 x1 y0 y1
+        const int lx = max((int)__uint_as_float(bb.x), wx0), hx = min((int)__uint_as_float(bb.y), wx0 + ww - 1);
+        const int ly = max((int)__uint_as_float(bb.z), wy0), hy = min((int)__uint_as_float(bb.w), wy0 + wh - 1);
+        if (lx > hx || ly > hy) continue; // misses the window
+        float w[PREP_WORDS];
+#pragma unroll
+        for (int q = 0; q < 7; q++) {
+            if (q == 5) continue;
+            const uint4 v = __ldg(pq + q);
+            w[4 * q] = __uint_as_float(v.x); w[4 * q + 1] = __uint_as_float(v.y); w[4 * q + 2] = __uint_as_float(v.z); w[4 * q + 3] = __uint_as_float(v.w);
+        }
+        w[S_X0] = w[S_X1] = w[S_Y0] = w[S_Y1] = 0.0f;
+        const TriRegs t = tri_from_words(w);
         float y = (float)ly;
         for (int yi = ly; yi <= hy; yi++, y = FADD(y, 1.0f)) {
             float x = (float)lx;
             for (int xi = lx; xi <= hx; xi++, x = FADD(x, 1.0f)) {
                 float d;
-                if (!cover_pixel(t.ecx, t.ecy, t.ek1, t.ek2, t.f, t.flags, r.da, r.db, r.dc, x, y, d)) continue;
+                if (!cover_pixel(t, t.flags, x, y, d)) continue;
                 if (!(d < depth_max)) continue; // also rejects NaN; equality with the clear depth fails `<`
                 const unsigned long long key = make_key(d, slot);
                 unsigned long long *cell = &keys[(yi - ty0) * TILE_W + (xi - tx0)];
@@ -411,11 +585,17 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ F
     }
     __syncthreads();
 
-    if (W.tile_cycles && tid == 0) W.tile_cycles[2 * U.n_coarse + tile] = (uint32_t)(clock64() - t_start); // end of phase B
+#ifndef DRAW_TAP_B
+    if (W.tile_cycles && tid == 0) atomicMax(&W.tile_cycles[2 * U.n_coarse + tile], (uint32_t)(clock64() - t_start)); // end of phase B
+#endif
+#if DRAW_TAP_B == 2
+    if (W.tile_cycles && tid == 0) atomicMax(&W.tile_cycles[2 * U.n_coarse + tile], (uint32_t)(clock64() - tb2_0) + W.tile_cycles[U.n_coarse + tile]); // + B2
+#endif
     // ---- phase C: deferred shading, fused clear ----------------------------------------------------
 #pragma unroll 1
-    for (int it = 0; it < TILE_PIXELS / TILE_THREADS; it++) {
-        const int p = it * TILE_THREADS + tid;
+    for (int q = tid; q < n_win; q += TILE_THREADS) { // the window's pixels
+        const int x = wx0 + (q & (ww - 1)), y = wy0 + (q >> ww_shift);
+        const int p = (y - ty0) * TILE_W + (x - tx0);
         const uint32_t slot = (uint32_t)keys[p];
         uint32_t c = 155u | (186u << 8) | (255u << 16) | (255u << 24); // azul_bb, pad 255 (canvas.rs:131)
         float d = depth_max;
@@ -423,8 +603,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ F
         if (slot != NO_SLOT) {
             const RasterRec r = load_raster(rrec + slot);
             float op;
-            c = shade_pixel(S.materials, S.texels, u8tab, r, W.srec + slot, (float)(tx0 + (p & (TILE_W - 1))),
-                            (float)(ty0 + p / TILE_W), &d, &op) | (255u << 24);
+            c = shade_pixel(S.materials, S.texels, u8tab, r, W.srec + slot, (float)x, (float)y, &d, &op) | (255u << 24);
             id = r.id;
         }
         colour[p] = c;
@@ -437,27 +616,29 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ F
     for (uint32_t base = 0; base < n_tslots; base += CHUNK) {
         const uint32_t n = min((uint32_t)CHUNK, n_tslots - base);
         __syncthreads();
-        if ((uint32_t)tid < n) stage_triangle(staged + tid, W.t_rrec + base + tid, base + tid);
+        if ((uint32_t)tid < n) stage_triangle(staged[tid], W.t_rrec + base + tid, base + tid);
         __syncthreads();
 #pragma unroll 1
         for (uint32_t k = 0; k < n; k++) {
-            const StagedTri &s = staged[k];
-            if (s.x1 < (float)tx0 || s.x0 > (float)(tx0 + TILE_W - 1) || s.y1 < (float)ty0 || s.y0 > (float)(ty0 + TILE_H - 1))
-                continue;
+            const float *s = staged[k];
+            if (s[S_X1] < wx0f || s[S_X0] > wx1f || s[S_Y1] < wy0f || s[S_Y0] > wy1f) continue;
+            const TriRegs t = tri_from_words(s);
+            const uint32_t tslot = __float_as_uint(s[S_SLOT]), tid_draw = __float_as_uint(s[S_ID]);
 #pragma unroll 1
-            for (int it = 0; it < TILE_PIXELS / TILE_THREADS; it++) {
-                const int p = it * TILE_THREADS + tid;
-                const float x = (float)(tx0 + (p & (TILE_W - 1))), y = (float)(ty0 + p / TILE_W);
-                if (x < s.x0 || x > s.x1 || y < s.y0 || y > s.y1) continue;
+            for (int q = tid; q < n_win; q += TILE_THREADS) {
+                const int xi = wx0 + (q & (ww - 1)), yi = wy0 + (q >> ww_shift);
+                const int p = (yi - ty0) * TILE_W + (xi - tx0);
+                const float x = (float)xi, y = (float)yi;
+                if (x < s[S_X0] || x > s[S_X1] || y < s[S_Y0] || y > s[S_Y1]) continue;
                 float d;
-                if (!cover_pixel(s.ecx, s.ecy, s.ek1, s.ek2, s.f, s.flags | TRI_SLOW, s.da, s.db, s.dc, x, y, d)) continue;
+                if (!cover_pixel(t, t.flags | TRI_SLOW, x, y, d)) continue;
                 const unsigned long long key = keys[p];
                 const uint32_t wid = (uint32_t)key;
-                if (!(wid == NO_SLOT || s.id > wid)) continue;            // drawn before the opaque winner: overwritten
+                if (!(wid == NO_SLOT || tid_draw > wid)) continue;           // drawn before the opaque winner: overwritten
                 if (!(d < __uint_as_float((uint32_t)(key >> 32)))) continue; // canvas.rs:923, depth write is off
-                const RasterRec r = load_raster(W.t_rrec + s.slot);
+                const RasterRec r = load_raster(W.t_rrec + tslot);
                 float d2, op;
-                const uint32_t rgb = shade_pixel(S.materials, S.texels, u8tab, r, W.t_srec + s.slot, x, y, &d2, &op);
+                const uint32_t rgb = shade_pixel(S.materials, S.texels, u8tab, r, W.t_srec + tslot, x, y, &d2, &op);
                 // canvas.rs:916-921: opacity < 1 blends with the stored colour, else replaces it
                 colour[p] = op < 1.0f ? blend_rgb(colour[p], rgb, op) : (rgb | (255u << 24));
             }
@@ -465,21 +646,22 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ F
     }
 
     // ---- phase E: single write-back -------------------------------------------------------------
-    const int W_ = (int)U.canvas_w, H_ = (int)U.canvas_h;
-#pragma unroll
-    for (int it = 0; it < TILE_PIXELS / TILE_THREADS; it++) {
-        const int p = it * TILE_THREADS + tid;
-        const int x = tx0 + (p & (TILE_W - 1)), y = ty0 + p / TILE_W;
+#pragma unroll 1
+    for (int q = tid; q < n_win; q += TILE_THREADS) {
+        const int x = wx0 + (q & (ww - 1)), y = wy0 + (q >> ww_shift);
+        const int p = (y - ty0) * TILE_W + (x - tx0);
         if (x >= W_ || y >= H_) continue;
         const uint32_t c = colour[p]; // r g b pad -> memory order b g r pad
         reinterpret_cast<uint32_t *>(color)[(size_t)(H_ - 1 - y) * W_ + x] =
             ((c >> 16) & 255u) | (c & 0x0000FF00u) | ((c & 255u) << 16) | (c & 0xFF000000u);
         depth[(size_t)y * W_ + x] = __uint_as_float((uint32_t)(keys[p] >> 32));
     }
+#if !defined(DRAW_TAP_B) || DRAW_TAP_B == 2
     if (W.tile_cycles) {
         __syncthreads();
-        if (tid == 0) W.tile_cycles[tile] = (uint32_t)(clock64() - t_start);
+        if (tid == 0) atomicMax(&W.tile_cycles[tile], (uint32_t)(clock64() - t_start));
     }
+#endif
 }
 
 // Canvas::clear (canvas.rs:425-433) as a standalone operation (draw_canvas_clear).
@@ -499,10 +681,11 @@ __global__ void __launch_bounds__(256) k_fill_u32(uint32_t *__restrict__ dst, si
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+uint32_t tile_grid_items(const FrameUniforms &U); // k_binning.cu
 void launch_tile(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, uint8_t *color, float *depth,
                  cudaStream_t stream) {
-    const uint32_t stripe_tiles = (U.tile_y_end - U.tile_y_begin) * U.tiles_x;
-    if (stripe_tiles) launch_pdl(k_tile, stripe_tiles, TILE_THREADS, stream, U, S, W, color, depth);
+    const uint32_t items = tile_grid_items(U); // one CTA per work-list slot; unused slots exit at once
+    if (items) launch_pdl(k_tile, items, TILE_THREADS, stream, U, S, W, color, depth);
 }
 
 cudaError_t launch_clear(uint8_t *color, float *depth, size_t n_pixels, float depth_max, cudaStream_t stream,

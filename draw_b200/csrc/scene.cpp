@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -22,6 +23,7 @@
 #include "host_math.hpp"
 
 namespace drawb200 {
+int g_pdl_enabled = 1;
 // k_geometry.cu / k_binning.cu / k_tile.cu
 void launch_vertex(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
 void launch_setup(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
@@ -140,23 +142,27 @@ struct draw_scene {
     };
     std::vector<TransparentRange> transparent_ranges;
 
-    // Per-frame work buffers, double-buffered: the vertex / setup / binning kernels of frame k+1 run on
-    // the scene's side stream while k_tile of frame k still runs on its canvas' stream.
+    // Per-frame work buffers, N_WORK_SETS deep, each with its own side stream: the vertex / setup /
+    // binning kernels of the next frames (a chain of six small, latency-bound launches) run on side
+    // streams while k_tile of frame k still runs on its canvas' stream.
     struct WorkSet {
         DevBuf<float> vert[9];
-        DevBuf<uint32_t> flags, list_count, list_offset, refs, counters, tile_cycles, tile_cost, tile_order;
+        DevBuf<uint32_t> flags, list_count, list_offset, refs, counters, tile_cycles, tile_cost, tile_order, empty_tiles;
         DevBuf<unsigned long long> scan_desc;
         DevBuf<uint2> clip_queue;
         DevBuf<RasterRec> rrec, trrec;
+        DevBuf<PrepRec> prep;
         DevBuf<ShadeRec> srec, tsrec;
         FrameDev work{};
+        cudaStream_t stream = nullptr;   // side stream of this set
         cudaEvent_t geo_done = nullptr;  // side stream: binning of the frame using this set has finished
         cudaEvent_t tile_done = nullptr; // canvas stream: k_tile of the frame using this set has finished
         bool tile_pending = false;
     };
-    WorkSet sets[2];
+    static constexpr int MAX_WORK_SETS = 8;
+    WorkSet sets[MAX_WORK_SETS];
+    int n_sets = 4;
     int next_set = 0, last_set = 0;
-    cudaStream_t side_stream = nullptr;
     bool debug_tile_cycles = false;
     size_t rec_cap = 0, refs_cap = 0;
     // optional per-kernel timing (draw_scene_set_kernel_timing): 0..6 around the six side-stream kernels,
@@ -193,6 +199,11 @@ struct draw_canvas {
 };
 
 namespace {
+
+int env_int(const char *name, int fallback) {
+    const char *v = std::getenv(name);
+    return v && *v ? std::atoi(v) : fallback;
+}
 
 int ensure_device(int device) {
     int cur = -1;
@@ -303,6 +314,7 @@ int ensure_work_buffers(draw_scene *s, draw_scene::WorkSet &ws, size_t n_lists) 
     if (s->refs_cap == 0) s->refs_cap = std::max<size_t>((size_t)1 << 22, 4 * (size_t)d.n_triangles);
     TRY(ws.rrec.reserve(s->rec_cap));
     TRY(ws.srec.reserve(s->rec_cap));
+    TRY(ws.prep.reserve(s->rec_cap));
     TRY(ws.trrec.reserve(4 * (size_t)d.n_transparent));
     TRY(ws.tsrec.reserve(4 * (size_t)d.n_transparent));
     TRY(ws.list_count.reserve(n_lists));
@@ -310,7 +322,8 @@ int ensure_work_buffers(draw_scene *s, draw_scene::WorkSet &ws, size_t n_lists) 
     TRY(ws.refs.reserve(s->refs_cap));
     TRY(ws.counters.reserve(8));
     TRY(ws.tile_cost.reserve(n_lists));
-    TRY(ws.tile_order.reserve(n_lists));
+    TRY(ws.tile_order.reserve(n_lists + TILE_EXTRA_ITEMS));
+    TRY(ws.empty_tiles.reserve(n_lists / LISTS_PER_TILE + EMPTY_GROUP));
     TRY(ws.scan_desc.reserve((size_t)d.n_triangles / 256 + 2));
     TRY(ws.clip_queue.reserve(d.n_triangles));
     FrameDev &w = ws.work;
@@ -318,12 +331,13 @@ int ensure_work_buffers(draw_scene *s, draw_scene::WorkSet &ws, size_t n_lists) 
     w.v_hx = ws.vert[3].ptr; w.v_hy = ws.vert[4].ptr; w.v_hz = ws.vert[5].ptr;
     w.v_depth = ws.vert[6].ptr; w.v_sx = ws.vert[7].ptr; w.v_sy = ws.vert[8].ptr;
     w.v_flags = ws.flags.ptr;
-    w.rrec = ws.rrec.ptr; w.srec = ws.srec.ptr;
+    w.rrec = ws.rrec.ptr; w.srec = ws.srec.ptr; w.prep = ws.prep.ptr;
     w.t_rrec = ws.trrec.ptr; w.t_srec = ws.tsrec.ptr;
     w.list_count = ws.list_count.ptr; w.list_offset = ws.list_offset.ptr; w.list_refs = ws.refs.ptr;
     w.counters = ws.counters.ptr;
     w.tile_cost = ws.tile_cost.ptr;
     w.tile_order = ws.tile_order.ptr;
+    w.empty_tiles = ws.empty_tiles.ptr;
     w.scan_desc = ws.scan_desc.ptr;
     w.clip_queue = ws.clip_queue.ptr;
     w.rec_cap = (uint32_t)s->rec_cap;
@@ -389,11 +403,20 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     const uint32_t tiles_x = (uint32_t)((c->width + TILE_W - 1) / TILE_W), tiles_y = (uint32_t)((c->height + TILE_H - 1) / TILE_H);
     const uint32_t n_coarse = tiles_x * tiles_y;
     const uint32_t n_lists = LISTS_PER_TILE * n_coarse;
+    if (tiles_x >= MAX_TILES_X || tiles_y >= MAX_TILES_Y)
+        return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas %zux%zu is too large for the tile work list", c->width, c->height);
     draw_scene::WorkSet &ws = s->sets[s->next_set];
+    const draw_scene::WorkSet &prev_ws = s->sets[s->last_set];
     s->last_set = s->next_set;
-    s->next_set ^= 1;
+    s->next_set = (s->next_set + 1) % s->n_sets;
     TRY(ensure_work_buffers(s, ws, n_lists));
-    if (!s->side_stream) CU(cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking));
+    if (!ws.stream) {
+        // highest priority: the chain's few CTAs must get SM slots while the previous frame's k_tile
+        // (thousands of CTAs on the canvas stream) is still being dispatched
+        int prio_low = 0, prio_high = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+        CU(cudaStreamCreateWithPriority(&ws.stream, cudaStreamNonBlocking, env_int("DRAW_B200_PRIO", 1) ? prio_high : prio_low));
+    }
 
     FrameUniforms U{};
     const m4 m = transformation_matrix(s->camera, s->width, s->height); // :904
@@ -415,14 +438,31 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     U.tiles_y = tiles_y;
     U.n_coarse = n_coarse;
     U.n_lists = n_lists;
+    U.has_transparent = s->dev.n_transparent != 0;
+    U.split_min_cost = (uint32_t)std::max(1, env_int("DRAW_B200_SPLIT_MIN_COST", TILE_SPLIT_MIN_COST));
+    U.split_div = (uint32_t)std::min(std::max(1, env_int("DRAW_B200_SPLIT_DIV", TILE_SPLIT_DIV)), (int)TILE_EXTRA_ITEMS);
+    U.split_max = (uint32_t)std::min(std::max(1, env_int("DRAW_B200_SPLIT_MAX", TILE_MAX_SPLIT)), (int)TILE_MAX_SPLIT);
     const size_t y0 = c->stripe_y1 ? c->stripe_y0 : 0, y1 = c->stripe_y1 ? c->stripe_y1 : c->height;
     U.tile_y_begin = (uint32_t)(y0 / TILE_H);
     U.tile_y_end = (uint32_t)((y1 + TILE_H - 1) / TILE_H);
+    // early trigger only for a lone frame: with other frames in flight the idle dependents would hold SM slots
+    bool others_in_flight = false;
+    for (int i = 0; i < s->n_sets; i++)
+        if (&s->sets[i] != &ws && s->sets[i].tile_pending && cudaEventQuery(s->sets[i].tile_done) == cudaErrorNotReady) others_in_flight = true;
+    cudaGetLastError(); // cudaErrorNotReady is not sticky, but keep the error state clean
+    const int pdl_mode = env_int("DRAW_B200_PDL", 3); // 0 off, 1 always early, 2 never early, 3 early for a lone frame
+    g_pdl_enabled = pdl_mode != 0;
+    U.pdl_early = pdl_mode == 1 || (pdl_mode == 3 && !others_in_flight);
 
     // Side stream: geometry + binning.  It only waits for the tile kernel that last read this work set.
-    cudaStream_t side = s->side_stream;
+    cudaStream_t side = ws.stream;
     if (ws.tile_pending) CU(cudaStreamWaitEvent(side, ws.tile_done, 0));
-    if (s->dev.n_transparent) TRY(sort_transparent(s, side));
+    if (s->dev.n_transparent) {
+        // the painter sort rewrites the shared index streams: order it after the previous frame's geometry
+        if (&prev_ws != &ws && prev_ws.geo_done && prev_ws.tile_pending) CU(cudaStreamWaitEvent(side, prev_ws.geo_done, 0));
+        TRY(sort_transparent(s, side));
+    }
+    if (ws.work.tile_cycles) CU(cudaMemsetAsync(ws.work.tile_cycles, 0, n_lists * sizeof(uint32_t), side)); // debug taps are atomicMax'd
 
     cudaEvent_t *ev = nullptr;
     if (s->kernel_timing) {
@@ -555,6 +595,7 @@ int draw_scene_create(size_t width, size_t height, draw_scene **out) {
     s->device = dev;
     s->width = width;
     s->height = height;
+    s->n_sets = std::min(std::max(env_int("DRAW_B200_SETS", 4), 1), (int)draw_scene::MAX_WORK_SETS);
     // Scene::new, scene/mod.rs:760-786
     const f3 pos{0.0f, 0.0f, 150.0f};
     const f3 dir = scale(pos, -1.0f);
@@ -585,7 +626,8 @@ void draw_scene_destroy(draw_scene *scene) {
         }
         for (int i = 0; i < N_FRAME_KERNELS + 2; i++)
             if (scene->kev[i]) cudaEventDestroy(scene->kev[i]);
-        if (scene->side_stream) cudaStreamDestroy(scene->side_stream);
+        for (draw_scene::WorkSet &ws : scene->sets)
+            if (ws.stream) cudaStreamDestroy(ws.stream);
     }
     delete scene;
 }
