@@ -245,14 +245,14 @@ class Scene:
         N.check(N.lib().draw_scene_read_vertex_visual(self._h, canvas._h, first, count, out.ctypes.data))
         return out
 
-    KERNELS = ("k_vertex", "k_setup", "k_clip", "k_bin_count", "k_alloc", "k_bin_fill", "k_tile")
+    KERNELS = ("k_vertex", "k_setup", "k_clip", "k_bin_count", "k_alloc", "k_bin_fill", "k_raster", "k_clear_empty", "k_tile")
 
     def set_kernel_timing(self, enabled):
         N.check(N.lib().draw_scene_set_kernel_timing(self._h, 1 if enabled else 0))
 
     def last_kernel_times(self, canvas):
         """Device time (ms) of each kernel of the last frame, keyed by kernel name."""
-        ms = (C.c_float * 7)()
+        ms = (C.c_float * 9)()
         N.check(N.lib().draw_scene_last_kernel_times(self._h, canvas._h, ms))
         return dict(zip(self.KERNELS, (float(x) for x in ms)))
 

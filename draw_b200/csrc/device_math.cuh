@@ -211,6 +211,66 @@ __device__ __forceinline__ void store_prep(PrepRec *dst, const PrepRec &p) {
     for (int i = 0; i < 7; i++) d[i] = src[i]; // the last quad is padding
 }
 
+// One triangle in registers.
+struct TriRegs {
+    float ecx[3], ecy[3], ek1[3], ek2[3], f[3], rf[3];
+    float da, db, dc;
+    uint32_t flags;
+};
+__device__ __forceinline__ TriRegs tri_from_prep(const PrepRec &p) {
+    TriRegs t;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        t.ecx[i] = p.ecx[i]; t.ecy[i] = p.ecy[i]; t.ek1[i] = p.ek1[i]; t.ek2[i] = p.ek2[i]; t.f[i] = p.f[i]; t.rf[i] = p.rf[i];
+    }
+    t.da = p.da; t.db = p.db; t.dc = p.dc;
+    t.flags = p.flags;
+    return t;
+}
+
+// Coverage + depth of one pixel (canvas.rs:673-682).  Tame triangles: sign tests on the
+// sign-normalised edge values, divisions only for covered pixels.  Others: the reference's literal
+// divide-then-compare.  The quotients e/f are the same either way.
+__device__ __forceinline__ bool cover_pixel(const TriRegs &t, uint32_t flags, float x, float y, float &depth) {
+    float e[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) e[i] = FSUB(FADD(FADD(FMUL(t.ecx[i], x), FMUL(t.ecy[i], y)), t.ek1[i]), t.ek2[i]);
+    float bary[3];
+    if (!(flags & TRI_SLOW)) {
+        const bool in = (e[0] > 0.0f || (e[0] == 0.0f && (flags & 1u))) && (e[1] > 0.0f || (e[1] == 0.0f && (flags & 2u))) &&
+                        (e[2] > 0.0f || (e[2] == 0.0f && (flags & 4u)));
+        if (!in) return false;
+        if (flags & TRI_FASTDIV) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) bary[i] = exact_div(e[i], t.f[i], t.rf[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 3; i++) bary[i] = FDIV(e[i], t.f[i]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; i++) bary[i] = FDIV(e[i], t.f[i]);
+        if (!(bary[0] >= 0.0f && bary[1] >= 0.0f && bary[2] >= 0.0f)) return false;
+        if (!((bary[0] > 0.0f || (flags & 1u)) && (bary[1] > 0.0f || (flags & 2u)) && (bary[2] > 0.0f || (flags & 4u))))
+            return false;
+    }
+    depth = FADD(FADD(FMUL(bary[0], t.da), FMUL(bary[1], t.db)), FMUL(bary[2], t.dc)); // canvas.rs:682
+    return true;
+}
+
+// Order-preserving map float -> uint32 (-0 is folded onto +0: the reference's `<` treats them as
+// equal, so the earlier draw must win between them), and its inverse.
+__device__ __forceinline__ uint32_t depth_key(float d) {
+    const uint32_t b = __float_as_uint(FADD(d, 0.0f));
+    return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float depth_from_key(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+}
+__device__ __forceinline__ unsigned long long make_key(float d, uint32_t slot) {
+    return ((unsigned long long)depth_key(d) << 32) | slot;
+}
+
 // Can any pixel of the rectangle [lx,hx] x [ly,hy] be covered?  Exact, not heuristic: each edge
 // value fl(fl(fl(cx*x + cy*y) + k1) - k2) is a monotone function of x and of y because every
 // rounding step is monotone, so its maximum over the rectangle sits at the corner selected by

@@ -27,7 +27,8 @@ constexpr int TILE_W = DRAW_TILE_W, TILE_H = DRAW_TILE_H, REGION = 16;
 #endif
 constexpr int SMALL_AREA = DRAW_SMALL_AREA, MEDIUM_AREA = DRAW_MEDIUM_AREA;
 constexpr int LISTS_PER_TILE = 3;
-constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
+constexpr uint32_t NO_SLOT = 0xFFFFFFFFu, NO_PAGE = 0xFFFFFFFFu;
+constexpr unsigned long long KEY_EMPTY = ~0ull;
 #ifndef DRAW_TILE_THREADS
 #define DRAW_TILE_THREADS 512
 #endif
@@ -41,9 +42,8 @@ constexpr int REGION_H = 8 * BLK_H;
 // units of warp regions (a 4x4 grid of REGION x REGION_H rectangles): the whole tile, or one of the
 // 2 / 4 / 8 / 16 windows a dense tile is cut into.
 //   bits 0-9 tile x | 10-20 tile y | 21-22 window x0 | 23-24 window y0 | 25-26 window w-1 | 27-28 window h-1
-// Tiles with nothing binned to them are not items of their own: they are listed in FrameDev::empty_tiles
-// (as x | y << 10) and an item with ITEM_EMPTY set names a group of EMPTY_GROUP of them, one per warp
-// of the CTA (bits 0-28 = group index).
+// Tiles with nothing binned to them are not items: they are listed in FrameDev::empty_tiles (as
+// x | y << 10, count in counters[13]) and written by k_clear_empty.
 constexpr int REGIONS_X = TILE_W / REGION, REGIONS_Y = TILE_H / REGION_H;
 constexpr bool TILE_SPLITTABLE = REGIONS_X == 4 && (REGIONS_Y == 4 || REGIONS_Y == 2);
 #ifndef DRAW_TILE_MAX_SPLIT
@@ -59,8 +59,8 @@ constexpr int TILE_EXTRA_ITEMS = 1024;                        // work-list slots
 #define DRAW_TILE_SPLIT_DIV 296
 #endif
 constexpr int TILE_SPLIT_DIV = DRAW_TILE_SPLIT_DIV;           // a window should cost about total / this (<= TILE_EXTRA_ITEMS)
-constexpr uint32_t ITEM_NONE = 0xFFFFFFFFu, ITEM_EMPTY = 1u << 29;
-constexpr int EMPTY_GROUP = TILE_THREADS / 32;
+constexpr uint32_t ITEM_NONE = 0xFFFFFFFFu;
+constexpr int N_COUNTERS = 64, ITEM_CURSOR = 32; // FrameDev::counters; k_tile's item cursor sits in the second 128-byte line
 constexpr uint32_t MAX_TILES_X = 1u << 10, MAX_TILES_Y = 1u << 11;
 #if defined(__CUDACC__)
 __host__ __device__
@@ -165,11 +165,17 @@ struct FrameDev {
     ShadeRec *t_srec;
     uint32_t *list_count;       // per list (large, medium, small per tile): count, then fill cursor [n_lists]
     uint32_t *list_offset;      // first entry of each list in list_refs [n_lists + 1]
-    uint32_t *list_refs;        // record slots grouped by list [refs_cap]
-    uint32_t *counters;         // [0] records  [1] refs  [2] overflow bits  [3] k_setup CTA ticket  [4] k_alloc CTAs done  [5] clip queue length  [6] total tile cost  [8]
+    uint32_t *list_refs;        // large lists: record slots [refs_cap]
+    uint2 *m_refs, *s_refs;     // medium / small lists: (record slot, tile x | y << 10) [refs_cap each]
+    uint32_t *tile_page;        // key page of each tile, or NO_PAGE [n_coarse]
+    unsigned long long *key_pages; // page p = TILE_W * TILE_H keys (depth key << 32 | slot), all ones = empty; k_raster
+                                   // fills them with atomicMin, k_tile consumes and resets them [page_cap pages]
+    uint32_t page_cap;
+    uint32_t *counters;         // [0] records  [1] refs  [2] overflow bits  [3] k_setup CTA ticket  [4] k_alloc CTAs done  [5] clip queue length
+                                // [6] total tile cost  [8..10] large / medium / small references  [11] key pages handed out  [13] empty tiles  [32] k_tile item cursor  [N_COUNTERS]
     uint32_t *tile_cost;        // estimated k_tile work per tile [n_coarse]
     uint32_t *tile_order;       // k_tile work items (make_item), heaviest first, padded with ITEM_NONE [n_coarse + TILE_EXTRA_ITEMS]
-    uint32_t *empty_tiles;      // tiles with empty lists as x | y << 10, padded with NO_SLOT to a multiple of EMPTY_GROUP [n_coarse + EMPTY_GROUP]
+    uint32_t *empty_tiles;      // tiles with empty lists as x | y << 10 [n_coarse]
     unsigned long long *scan_desc; // k_setup chained-scan descriptors [ceil(n_triangles / 256)]
     uint2 *clip_queue;          // (triangle, first reserved slot | NO_SLOT) of triangles to clip [n_triangles]
     uint32_t rec_cap, refs_cap;
@@ -178,6 +184,6 @@ struct FrameDev {
 
 enum : uint32_t { OVERFLOW_RECORDS = 1u, OVERFLOW_REFS = 2u };
 
-constexpr int N_FRAME_KERNELS = 7; // k_vertex k_setup k_clip k_bin<count> k_alloc k_bin<fill> k_tile
+constexpr int N_FRAME_KERNELS = 9; // k_vertex k_setup k_clip k_bin<count> k_alloc k_bin<fill> k_raster k_clear_empty k_tile
 
 } // namespace drawb200

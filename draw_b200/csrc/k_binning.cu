@@ -20,15 +20,22 @@
 
 namespace drawb200 {
 
+// Each class has its own reference array (a tile's list is a contiguous range of it, and the ranges of
+// all tiles tile the array without gaps, which is what lets k_raster walk the medium and small
+// references of the whole frame as one flat list).  Medium and small references carry their tile.
 template <bool FILL>
-__device__ __forceinline__ void bin_hit(const FrameDev &W, uint32_t list, uint32_t slot) {
+__device__ __forceinline__ void bin_hit(const FrameDev &W, uint32_t cls, uint32_t list, uint32_t slot, uint32_t tile_xy) {
     const uint32_t pos = atomicAdd(&W.list_count[list], 1u);
-    if (FILL) W.list_refs[W.list_offset[list] + pos] = slot;
+    if (FILL) {
+        const uint32_t at = W.list_offset[list] + pos;
+        if (cls == 0u) W.list_refs[at] = slot;
+        else (cls == 1u ? W.m_refs : W.s_refs)[at] = make_uint2(slot, tile_xy);
+    }
 }
 // Estimated k_tile work of one reference, in quarter block-iterations (one iteration = a warp testing an
 // 8x4 block of a medium triangle, ~130 instructions): a large triangle costs every warp of the CTA a
 // pass, a medium one its 8x4 blocks, a small one a lane.  Summed per tile by k_bin<count> for k_alloc.
-constexpr uint32_t COST_LARGE = 80u, COST_MEDIUM_BLOCK = 4u, COST_SMALL = 1u;
+constexpr uint32_t COST_LARGE = 80u, COST_MEDIUM_BLOCK = 4u, COST_SMALL = 1u, COST_TILE_BASE = 16u;
 
 // Reference one tile from a record if the triangle can cover a pixel of it; the list class follows
 // the area of the bbox clipped to the tile.
@@ -41,10 +48,15 @@ __device__ __forceinline__ void bin_tile(const FrameUniforms &U, const FrameDev 
     const int area = (hx - lx + 1) * (hy - ly + 1);
     const uint32_t cls = area <= SMALL_AREA ? 2u : (area <= MEDIUM_AREA ? 1u : 0u);
     const uint32_t tile = (uint32_t)ty * U.tiles_x + (uint32_t)tx;
-    bin_hit<FILL>(W, cls * U.n_coarse + tile, slot);
-    if (!FILL) {
-        const uint32_t blocks = (uint32_t)((hx - lx) / 8 + 1) * (uint32_t)((hy - ly) / 4 + 1);
-        atomicAdd(&W.tile_cost[tile], cls == 2u ? COST_SMALL : (cls == 1u ? COST_MEDIUM_BLOCK * blocks : COST_LARGE));
+    const uint32_t blocks = (uint32_t)((hx - lx) / 8 + 1) * (uint32_t)((hy - ly) / 4 + 1);
+    // A medium reference with many 8x4 blocks is entered 2-4 times, each entry naming a share of the blocks
+    // (ref_part bits), so that k_raster's warp-per-reference jobs stay short; k_tile skips the extra entries.
+    const uint32_t parts = cls == 1u ? min(4u, (blocks + 7u) / 8u) : 1u;
+    for (uint32_t part = 0; part < parts; part++)
+        bin_hit<FILL>(W, cls, cls * U.n_coarse + tile, slot, (uint32_t)tx | (uint32_t)ty << 10 | part << 21 | (parts - 1u) << 23);
+    if (!FILL) { // [tile]: cost of the large references, [n_coarse + tile]: of the medium and small ones
+        if (cls == 0u) atomicAdd(&W.tile_cost[tile], COST_LARGE);
+        else atomicAdd(&W.tile_cost[U.n_coarse + tile], cls == 2u ? COST_SMALL : COST_MEDIUM_BLOCK * blocks);
     }
 }
 
@@ -193,8 +205,8 @@ __device__ __forceinline__ uint32_t tile_splits(uint32_t cost, uint32_t target, 
 }
 
 __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const __grid_constant__ FrameUniforms U, const FrameDev W) {
-    __shared__ uint32_t warp_sum[ALLOC_THREADS / 32], warp_cost[ALLOC_THREADS / 32];
-    __shared__ uint32_t block_base, is_last;
+    __shared__ uint32_t warp_sum[3][ALLOC_THREADS / 32], warp_cost[ALLOC_THREADS / 32];
+    __shared__ uint32_t block_base3[3], block_base, is_last;
     __shared__ uint32_t bucket_start[COST_BUCKETS];
     pdl_prologue(U.pdl_early != 0);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -205,41 +217,56 @@ __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const __grid_constant__
     const uint32_t c = c0 + c1 + c2;
     const uint32_t ty = valid ? tile / U.tiles_x : 0u;
     const bool in_stripe = valid && ty >= U.tile_y_begin && ty < U.tile_y_end;
-    const uint32_t cost = in_stripe ? W.tile_cost[tile] : 0u; // summed by k_bin<count> (COST_* above)
+    // A tile with medium or small references gets a key page if one is left: k_raster then rasterises those
+    // references into the page for the whole frame at once and k_tile only merges the page (device_types.h).
+    uint32_t page = NO_PAGE;
+    if (in_stripe && c1 + c2 > 0 && W.page_cap) {
+        page = atomicAdd(&W.counters[11], 1u);
+        if (page >= W.page_cap) page = NO_PAGE;
+    }
+    // estimated k_tile work, summed per class by k_bin<count> (COST_* above)
+    uint32_t cost = 0;
+    if (in_stripe && c > 0) cost = COST_TILE_BASE + W.tile_cost[tile] + (page == NO_PAGE ? W.tile_cost[nc + tile] : 0u);
 
-    uint32_t incl = c, cost_sum = cost;
+    // exclusive prefixes of the three counts over the CTA, one range reservation per class
+    uint32_t inc0 = c0, inc1 = c1, inc2 = c2, cost_sum = cost;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= (uint32_t)d) incl += up;
+        const uint32_t u0 = __shfl_up_sync(0xFFFFFFFFu, inc0, d), u1 = __shfl_up_sync(0xFFFFFFFFu, inc1, d),
+                       u2 = __shfl_up_sync(0xFFFFFFFFu, inc2, d);
+        if (lane >= (uint32_t)d) { inc0 += u0; inc1 += u1; inc2 += u2; }
         cost_sum += __shfl_xor_sync(0xFFFFFFFFu, cost_sum, d);
     }
-    if (lane == 31) warp_sum[warp] = incl;
+    if (lane == 31) { warp_sum[0][warp] = inc0; warp_sum[1][warp] = inc1; warp_sum[2][warp] = inc2; }
     if (lane == 0) warp_cost[warp] = cost_sum;
     __syncthreads();
-    if (tid == 0) {
-        uint32_t total = 0, total_cost = 0;
+    if (tid < 3) {
+        uint32_t total = 0;
         for (int w = 0; w < ALLOC_THREADS / 32; w++) {
-            const uint32_t t = warp_sum[w];
-            warp_sum[w] = total;
+            const uint32_t t = warp_sum[tid][w];
+            warp_sum[tid][w] = total;
             total += t;
-            total_cost += warp_cost[w];
         }
-        const uint32_t base = total ? atomicAdd(&W.counters[1], total) : 0u;
+        const uint32_t base = total ? atomicAdd(&W.counters[8 + tid], total) : 0u;
+        if (total) atomicAdd(&W.counters[1], total); // all classes: frame statistics, buffer growth
         if (total && base + total > W.refs_cap) atomicOr(&W.counters[2], OVERFLOW_REFS);
+        block_base3[tid] = base;
+    }
+    if (tid == 32) {
+        uint32_t total_cost = 0;
+        for (int w = 0; w < ALLOC_THREADS / 32; w++) total_cost += warp_cost[w];
         if (total_cost) atomicAdd(&W.counters[6], total_cost);
-        block_base = base;
     }
     __syncthreads();
     if (valid) {
-        const uint32_t off = block_base + warp_sum[warp] + incl - c;
-        W.list_offset[tile] = off;
-        W.list_offset[nc + tile] = off + c0;
-        W.list_offset[2 * nc + tile] = off + c0 + c1;
+        W.list_offset[tile] = block_base3[0] + warp_sum[0][warp] + inc0 - c0;
+        W.list_offset[nc + tile] = block_base3[1] + warp_sum[1][warp] + inc1 - c1;
+        W.list_offset[2 * nc + tile] = block_base3[2] + warp_sum[2][warp] + inc2 - c2;
         W.list_count[tile] = 0; // become the fill cursors
         W.list_count[nc + tile] = 0;
         W.list_count[2 * nc + tile] = 0;
         W.tile_cost[tile] = in_stripe ? cost : COST_NOT_IN_STRIPE;
+        W.tile_page[tile] = page;
     }
     // ---- the last CTA builds the work list -------------------------------------------------------
     __threadfence();
@@ -254,7 +281,7 @@ __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const __grid_constant__
     const uint32_t total_cost = __ldcg(&W.counters[6]);
     const uint32_t target = max(U.split_min_cost, total_cost / U.split_div + 1u); // split_div <= TILE_EXTRA_ITEMS
     const uint32_t max_split = U.split_max;
-    const bool group_empties = U.has_transparent == 0; // else every tile runs the full path (cost 0, last bucket)
+    const bool list_empties = U.has_transparent == 0; // else every tile runs the full path (cost 0, last bucket)
     constexpr int BATCH = 8; // independent loads in flight per thread
     for (uint32_t t0 = tid; t0 < nc; t0 += ALLOC_THREADS * BATCH) {
         uint32_t cost_k[BATCH];
@@ -266,7 +293,7 @@ __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const __grid_constant__
 #pragma unroll
         for (int k = 0; k < BATCH; k++)
             if (cost_k[k] != COST_NOT_IN_STRIPE) {
-                if (cost_k[k] == 0 && group_empties) { // listed on its own: one warp of a group CTA clears it
+                if (cost_k[k] == 0 && list_empties) { // listed on its own: k_clear_empty writes it
                     const uint32_t t = t0 + k * ALLOC_THREADS;
                     W.empty_tiles[atomicAdd(&n_empty, 1u)] = (t % U.tiles_x) | (t / U.tiles_x) << 10;
                     continue;
@@ -286,12 +313,10 @@ __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const __grid_constant__
         block_base = run; // number of tile / window items
     }
     __syncthreads();
-    const uint32_t n_dense = block_base, n_groups = (n_empty + EMPTY_GROUP - 1) / EMPTY_GROUP;
+    const uint32_t n_dense = block_base;
     const uint32_t grid_items = (U.tile_y_end - U.tile_y_begin) * U.tiles_x + (TILE_SPLITTABLE ? TILE_EXTRA_ITEMS : 0);
-    // after the tile items: one item per group of empty tiles, then nothing
-    for (uint32_t i = tid; i < n_groups; i += ALLOC_THREADS) W.tile_order[n_dense + i] = ITEM_EMPTY | i;
-    for (uint32_t i = n_dense + n_groups + tid; i < grid_items; i += ALLOC_THREADS) W.tile_order[i] = ITEM_NONE;
-    for (uint32_t i = n_empty + tid; i < n_groups * EMPTY_GROUP; i += ALLOC_THREADS) W.empty_tiles[i] = NO_SLOT;
+    for (uint32_t i = n_dense + tid; i < grid_items; i += ALLOC_THREADS) W.tile_order[i] = ITEM_NONE;
+    if (tid == 0) W.counters[13] = n_empty; // k_clear_empty's work
     for (uint32_t t0 = tid; t0 < nc; t0 += ALLOC_THREADS * BATCH) {
         uint32_t cost_k[BATCH];
 #pragma unroll
@@ -301,7 +326,7 @@ __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const __grid_constant__
         }
 #pragma unroll
         for (int k = 0; k < BATCH; k++)
-            if (cost_k[k] != COST_NOT_IN_STRIPE && !(cost_k[k] == 0 && group_empties)) {
+            if (cost_k[k] != COST_NOT_IN_STRIPE && !(cost_k[k] == 0 && list_empties)) {
                 const uint32_t t = t0 + k * ALLOC_THREADS, s = tile_splits(cost_k[k], target, max_split);
                 const uint32_t tx = t % U.tiles_x, tyy = t / U.tiles_x;
                 const uint32_t at = atomicAdd(&bucket_start[cost_bucket(cost_k[k] / s)], s);

@@ -22,8 +22,8 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FrameUni
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     // per-frame reset of the binning state (the binning kernels run after this one on the same stream)
     for (uint32_t t = i; t < U.n_lists; t += gridDim.x * blockDim.x) W.list_count[t] = 0;
-    for (uint32_t t = i; t < U.n_coarse; t += gridDim.x * blockDim.x) W.tile_cost[t] = 0;
-    if (i < 8) W.counters[i] = 0;
+    for (uint32_t t = i; t < 2 * U.n_coarse; t += gridDim.x * blockDim.x) W.tile_cost[t] = 0;
+    if (i < N_COUNTERS) W.counters[i] = 0;
     const uint32_t n_desc = (S.n_triangles + 255) / 256;
     for (uint32_t t = i; t < n_desc; t += gridDim.x * blockDim.x) W.scan_desc[t] = 0ull;
     if (i >= S.n_vertices) return;

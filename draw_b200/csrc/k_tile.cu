@@ -50,11 +50,11 @@ static_assert(PREP_WORDS == 28 && (STAGE_STRIDE & 1) == 1 && offsetof(PrepRec, x
 // Copies n prepared records into shared memory: one 16-byte load per thread (8 threads per record, the
 // eighth idle), so a chunk of 64 is a single load per thread of a 512-thread CTA.
 __device__ __forceinline__ void stage_copy(float (*staged)[STAGE_STRIDE], const PrepRec *__restrict__ prep,
-                                           const uint32_t *refs, uint32_t n, int tid) {
+                                           const uint32_t *refs, uint32_t ref_stride, uint32_t n, int tid) {
     for (uint32_t i = (uint32_t)tid; i < n * 8u; i += TILE_THREADS) {
         const uint32_t k = i >> 3, q = i & 7u;
         if (q == 7u) continue;
-        const uint32_t slot = refs[k];
+        const uint32_t slot = refs[k * ref_stride];
         const uint4 v = __ldg(reinterpret_cast<const uint4 *>(prep + slot) + q);
         float *d = staged[k] + 4 * q;
         d[0] = __uint_as_float(v.x); d[1] = __uint_as_float(v.y); d[2] = __uint_as_float(v.z);
@@ -78,7 +78,7 @@ __device__ __forceinline__ void stage_triangle(float *dst, const RasterRec *src,
 
 // Window filter: keeps the references whose bbox meets the window (only their bbox quad is read).
 // Returns the number kept; cand[] is valid after the call (ends with a barrier).
-__device__ __forceinline__ uint32_t filter_refs(const uint32_t *__restrict__ list, uint32_t count,
+__device__ __forceinline__ uint32_t filter_refs(const uint32_t *__restrict__ list, uint32_t list_stride, uint32_t count,
                                                 const PrepRec *__restrict__ prep, uint32_t *cand, uint32_t *s_count,
                                                 float wx0f, float wx1f, float wy0f, float wy1f, int tid) {
     __syncthreads(); // cand / s_count may still be in use by the previous segment
@@ -90,10 +90,12 @@ __device__ __forceinline__ uint32_t filter_refs(const uint32_t *__restrict__ lis
         bool keep = false;
         uint32_t slot = 0;
         if (i < count) {
-            slot = list[i];
+            slot = list[i * list_stride];
+            // medium lists: entries 1..3 of a reference split for k_raster name the same triangle again
+            const bool extra_part = list_stride == 2u && ((list[i * 2u + 1u] >> 21) & 3u) != 0u;
             const uint4 bb = __ldg(reinterpret_cast<const uint4 *>(prep + slot) + 5); // x0 x1 y0 y1
-            keep = !(__uint_as_float(bb.y) < wx0f || __uint_as_float(bb.x) > wx1f || __uint_as_float(bb.w) < wy0f ||
-                     __uint_as_float(bb.z) > wy1f);
+            keep = !extra_part && !(__uint_as_float(bb.y) < wx0f || __uint_as_float(bb.x) > wx1f ||
+                                    __uint_as_float(bb.w) < wy0f || __uint_as_float(bb.z) > wy1f);
         }
         const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, keep);
         uint32_t wbase = 0;
@@ -105,12 +107,6 @@ __device__ __forceinline__ uint32_t filter_refs(const uint32_t *__restrict__ lis
     return *s_count;
 }
 
-// One triangle in registers (phase B2, phase D).
-struct TriRegs {
-    float ecx[3], ecy[3], ek1[3], ek2[3], f[3], rf[3];
-    float da, db, dc;
-    uint32_t flags;
-};
 __device__ __forceinline__ TriRegs tri_from_words(const float *w) {
     TriRegs t;
 #pragma unroll
@@ -121,36 +117,6 @@ __device__ __forceinline__ TriRegs tri_from_words(const float *w) {
     t.da = w[S_DA]; t.db = w[S_DB]; t.dc = w[S_DC];
     t.flags = __float_as_uint(w[S_FLAGS]);
     return t;
-}
-
-// Coverage + depth of one pixel (canvas.rs:673-682).  Tame triangles: sign tests on the
-// sign-normalised edge values, divisions only for covered pixels.  Others: the reference's literal
-// divide-then-compare.  The quotients e/f are the same either way.
-__device__ __forceinline__ bool cover_pixel(const TriRegs &t, uint32_t flags, float x, float y, float &depth) {
-    float e[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) e[i] = FSUB(FADD(FADD(FMUL(t.ecx[i], x), FMUL(t.ecy[i], y)), t.ek1[i]), t.ek2[i]);
-    float bary[3];
-    if (!(flags & TRI_SLOW)) {
-        const bool in = (e[0] > 0.0f || (e[0] == 0.0f && (flags & 1u))) && (e[1] > 0.0f || (e[1] == 0.0f && (flags & 2u))) &&
-                        (e[2] > 0.0f || (e[2] == 0.0f && (flags & 4u)));
-        if (!in) return false;
-        if (flags & TRI_FASTDIV) {
-#pragma unroll
-            for (int i = 0; i < 3; i++) bary[i] = exact_div(e[i], t.f[i], t.rf[i]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 3; i++) bary[i] = FDIV(e[i], t.f[i]);
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 3; i++) bary[i] = FDIV(e[i], t.f[i]);
-        if (!(bary[0] >= 0.0f && bary[1] >= 0.0f && bary[2] >= 0.0f)) return false;
-        if (!((bary[0] > 0.0f || (flags & 1u)) && (bary[1] > 0.0f || (flags & 2u)) && (bary[2] > 0.0f || (flags & 4u))))
-            return false;
-    }
-    depth = FADD(FADD(FMUL(bary[0], t.da), FMUL(bary[1], t.db)), FMUL(bary[2], t.dc)); // canvas.rs:682
-    return true;
 }
 
 // Exact block reject on a staged triangle (see rect_may_cover in device_math.cuh).
@@ -167,69 +133,19 @@ __device__ __forceinline__ bool staged_may_cover(const float *s, uint32_t flags,
     return any;
 }
 
-// Order-preserving map float -> uint32 (-0 is folded onto +0: the reference's `<` treats them as
-// equal, so the earlier draw must win between them).
-__device__ __forceinline__ uint32_t depth_key(float d) {
-    const uint32_t b = __float_as_uint(FADD(d, 0.0f));
-    return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
-}
-__device__ __forceinline__ unsigned long long make_key(float d, uint32_t slot) {
-    return ((unsigned long long)depth_key(d) << 32) | slot;
-}
-
-__global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(const __grid_constant__ FrameUniforms U, const SceneDev S,
-                                                       const FrameDev W, uint8_t *__restrict__ color,
-                                                       float *__restrict__ depth) {
+// One work item (k_alloc, device_types.h): a tile or one pixel window of a dense tile.
+__device__ __forceinline__ void tile_item(const uint32_t item, const FrameUniforms &U, const SceneDev &S, const FrameDev &W,
+                                          uint8_t *__restrict__ color, float *__restrict__ depth, const float *u8tab,
+                                          const bool usable) {
     __shared__ unsigned long long keys[TILE_PIXELS]; // (depth key, slot), later (depth bits, draw id)
     __shared__ uint32_t colour[TILE_PIXELS];         // r | g << 8 | b << 16 | pad << 24
     __shared__ float staged[CHUNK][STAGE_STRIDE];
     __shared__ uint32_t cand[CAND_CAP];
-    __shared__ float u8tab[256]; // (u8 as f32) / 255.0
     __shared__ uint32_t s_cand_count;
-    pdl_prologue();
-
-    // work item (k_alloc, device_types.h): a tile, one pixel window of a dense tile, or a group of empty
-    // tiles; heaviest first
-    const uint32_t item = W.tile_order[blockIdx.x];
-    if (item == ITEM_NONE) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W_ = (int)U.canvas_w, H_ = (int)U.canvas_h;
     const float depth_max = U.depth_max;
 
-    // ---- empty tiles: nothing to rasterise, write the clear colour and depth (canvas.rs:425-433) ----
-    // One tile per warp, two 256-byte rows (colour) per store instruction, pointers stepped by a row pair.
-    if (item & ITEM_EMPTY) {
-        const uint32_t et = W.empty_tiles[(item & (ITEM_EMPTY - 1u)) * EMPTY_GROUP + (uint32_t)warp];
-        if (et == NO_SLOT) return;
-        const int ex0 = (int)(et & (MAX_TILES_X - 1)) * TILE_W, ey0 = (int)(et >> 10) * TILE_H;
-        const uint32_t clear_px = 255u | (186u << 8) | (155u << 16) | (255u << 24); // memory order b g r pad
-        if ((W_ & 3) == 0) {
-            constexpr int QPR = TILE_W / 4, RPI = 32 / QPR; // 16-byte quads per tile row, rows per warp store
-            const int x = ex0 + (lane % QPR) * 4, r0 = lane / QPR;
-            const int rows = min(TILE_H, H_ - ey0);
-            if (x < W_) {
-                uint4 *cp = reinterpret_cast<uint4 *>(color + ((size_t)(H_ - 1 - ey0 - r0) * W_ + x) * 4);
-                float4 *dp = reinterpret_cast<float4 *>(depth + (size_t)(ey0 + r0) * W_ + x);
-                const ptrdiff_t step = (ptrdiff_t)RPI * (W_ / 4); // in 16-byte units: colour rows go up, depth rows down
-                const uint4 cv = make_uint4(clear_px, clear_px, clear_px, clear_px);
-                const float4 dv = make_float4(depth_max, depth_max, depth_max, depth_max);
-#pragma unroll 4
-                for (int r = r0; r < rows; r += RPI, cp -= step, dp += step) {
-                    *cp = cv;
-                    *dp = dv;
-                }
-            }
-        } else {
-            for (int p = lane; p < TILE_PIXELS; p += 32) {
-                const int x = ex0 + (p & (TILE_W - 1)), y = ey0 + p / TILE_W;
-                if (x >= W_ || y >= H_) continue;
-                reinterpret_cast<uint32_t *>(color)[(size_t)(H_ - 1 - y) * W_ + x] = clear_px;
-                depth[(size_t)y * W_ + x] = depth_max;
-            }
-        }
-        if (W.tile_cycles && lane == 0) atomicMax(&W.tile_cycles[(et >> 10) * U.tiles_x + (et & (MAX_TILES_X - 1))], 1u);
-        return;
-    }
     const uint32_t tile_x = item & (MAX_TILES_X - 1), tile_y = (item >> 10) & (MAX_TILES_Y - 1);
     const uint32_t tile = tile_y * U.tiles_x + tile_x;
     const long long t_start = W.tile_cycles ? clock64() : 0;
@@ -248,17 +164,16 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(cons
     const float wx0f = (float)wx0, wy0f = (float)wy0, wx1f = (float)(wx0 + ww - 1), wy1f = (float)(wy0 + wh - 1);
     const float tx0f = (float)tx0, ty0f = (float)ty0;
 
-    // (loads issued together; masked afterwards so that they do not wait for the overflow flag)
-    const uint32_t overflow = W.counters[2];
     const uint32_t l_begin = W.list_offset[tile], m_begin = W.list_offset[U.n_coarse + tile],
                    s_begin = W.list_offset[2 * U.n_coarse + tile];
     uint32_t l_count = W.list_count[tile], m_count = W.list_count[U.n_coarse + tile],
              s_count = W.list_count[2 * U.n_coarse + tile]; // the fill cursors end at the counts
-    const bool usable = overflow == 0;
+    const uint32_t page = W.tile_page[tile];
     if (!usable) l_count = m_count = s_count = 0;
+    // the tile has a key page: k_raster has already rasterised its medium and small lists into it
+    if (page != NO_PAGE) m_count = s_count = 0;
     const RasterRec *__restrict__ rrec = W.rrec;
     const PrepRec *__restrict__ prep = W.prep;
-    fill_u8_table(u8tab, tid, TILE_THREADS); // visible after the barrier that ends phase A
 
     // ---- phase A: large triangles, every lane tests its own 4 x BLK_H block -----------------------
     {
@@ -280,21 +195,75 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(cons
             zb[i] = depth_max;
             sl[i] = NO_SLOT;
         }
+        // The tile's key page (k_raster's result): its loads are issued here, together with the stores that
+        // leave it empty for the next frame, and consumed after the first chunk of large triangles has been
+        // staged, so that the two L2 round trips overlap.  A lane's 4 pixels of a row are 32 contiguous bytes.
+        const bool have_page = page != NO_PAGE && usable && warp_in;
+        ulonglong2 pk01[BLK_H], pk23[BLK_H];
+        if (have_page) {
+            unsigned long long *pk = W.key_pages + (size_t)page * TILE_PIXELS;
+#pragma unroll
+            for (int j = 0; j < BLK_H; j++) {
+                ulonglong2 *src = reinterpret_cast<ulonglong2 *>(pk + (by0 - ty0 + j) * TILE_W + (bx0 - tx0));
+#if DRAW_PAGE_LD == 1
+                pk01[j] = *src;
+                pk23[j] = *(src + 1);
+#elif DRAW_PAGE_LD == 2
+                pk01[j] = *reinterpret_cast<volatile ulonglong2 *>(src);
+                pk23[j] = *reinterpret_cast<volatile ulonglong2 *>(src + 1);
+#else
+                pk01[j] = __ldcg(src);
+                pk23[j] = __ldcg(src + 1);
+#endif
+
+            }
+        }
+        bool page_pending = have_page;
+        auto merge_page = [&]() { // the page's fragments become the starting depth / winner of the lane's pixels
+#pragma unroll
+            for (int j = 0; j < BLK_H; j++) {
+                const unsigned long long kk[4] = {pk01[j].x, pk01[j].y, pk23[j].x, pk23[j].y};
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (kk[i] != KEY_EMPTY) {
+                        zb[j * 4 + i] = depth_from_key((uint32_t)(kk[i] >> 32));
+                        sl[j * 4 + i] = (uint32_t)kk[i];
+                    }
+            }
+            page_pending = false;
+            // Leave the page empty for the next frame: after every lane of the warp has its keys (the loads
+            // above are consumed), the warp's region — REGION_H rows of 128 bytes — is overwritten with whole
+            // 128-byte lines, 8 lanes per row.
+            __syncwarp();
+            unsigned long long *pk = W.key_pages + (size_t)page * TILE_PIXELS;
+            constexpr int ROW_QUADS = REGION * 8 / 16; // 16-byte stores per region row
+#pragma unroll
+            for (int r = lane / ROW_QUADS; r < REGION_H; r += 32 / ROW_QUADS)
+                __stcg(reinterpret_cast<ulonglong2 *>(pk + (ry0 - ty0 + r) * TILE_W + (rx0 - tx0)) + lane % ROW_QUADS,
+                       make_ulonglong2(KEY_EMPTY, KEY_EMPTY));
+        };
 #pragma unroll 1
         for (uint32_t seg = 0; seg < l_count; seg += CAND_CAP) {
             const uint32_t seg_n = min((uint32_t)CAND_CAP, l_count - seg);
             const uint32_t *refs = W.list_refs + l_begin + seg;
             uint32_t n_refs = seg_n;
             if (windowed) {
-                n_refs = filter_refs(refs, seg_n, prep, cand, &s_cand_count, wx0f, wx1f, wy0f, wy1f, tid);
+                n_refs = filter_refs(refs, 1u, seg_n, prep, cand, &s_cand_count, wx0f, wx1f, wy0f, wy1f, tid);
                 refs = cand;
             }
 #pragma unroll 1
             for (uint32_t base = 0; base < n_refs; base += CHUNK) {
                 const uint32_t n = min((uint32_t)CHUNK, n_refs - base);
                 __syncthreads();
-                stage_copy(staged, prep, refs + base, n, tid);
+                stage_copy(staged, prep, refs + base, 1u, n, tid);
                 __syncthreads();
+#if DRAW_TAP_B == 3
+                if (W.tile_cycles && tid == 0) atomicMax(&W.tile_cycles[U.n_coarse + tile], (uint32_t)(clock64() - t_start)); // staged
+#endif
+                if (page_pending) merge_page();
+#if DRAW_TAP_B == 3
+                if (W.tile_cycles && tid == 0) atomicMax(&W.tile_cycles[2 * U.n_coarse + tile], (uint32_t)(clock64() - t_start)); // page merged
+#endif
 #pragma unroll 1
                 for (uint32_t k = 0; k < (warp_in ? n : 0u); k++) {
                     const float *s = staged[k];
@@ -379,6 +348,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(cons
                 }
             }
         }
+        if (page_pending) merge_page();
         // ---- merge: publish the block as keys --------------------------------------------------------
 #pragma unroll
         for (int p = 0; p < PX; p++) {
@@ -390,6 +360,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(cons
 
 #ifndef DRAW_TAP_B
     if (W.tile_cycles && tid == 0) atomicMax(&W.tile_cycles[U.n_coarse + tile], (uint32_t)(clock64() - t_start)); // end of phase A
+#endif
+#if DRAW_TAP_B == 3
+    if (W.tile_cycles && tid == 0) atomicMax(&W.tile_cycles[tile], (uint32_t)(clock64() - t_start)); // end of phase A
+    if (W.tile_cycles) return;
 #endif
     // ---- phase B1: medium triangles -------------------------------------------------------------------
     // Per chunk of 64 triangles: (1) the chunk is staged and one thread per triangle counts the 8x4-pixel
@@ -409,14 +383,15 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(cons
 #pragma unroll 1
         for (uint32_t seg = 0; seg < m_count; seg += CAND_CAP) {
             const uint32_t seg_n = min((uint32_t)CAND_CAP, m_count - seg);
-            const uint32_t *refs = W.list_refs + m_begin + seg;
-            uint32_t n_refs = seg_n;
-            if (windowed) {
+            const uint32_t *refs = reinterpret_cast<const uint32_t *>(W.m_refs + m_begin + seg); // (slot, tile) pairs
+            uint32_t n_refs = seg_n, ref_stride = 2u;
+            { // always filtered: besides the window test this drops the extra entries of split references
 #if DRAW_TAP_B == 2
                 const long long tf0 = clock64();
 #endif
-                n_refs = filter_refs(refs, seg_n, prep, cand, &s_cand_count, wx0f, wx1f, wy0f, wy1f, tid);
+                n_refs = filter_refs(refs, 2u, seg_n, prep, cand, &s_cand_count, wx0f, wx1f, wy0f, wy1f, tid);
                 refs = cand;
+                ref_stride = 1u;
 #if DRAW_TAP_B == 2
                 tap_filter += clock64() - tf0;
 #endif
@@ -428,7 +403,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(cons
 #ifdef DRAW_TAP_B
                 const long long tb0 = clock64();
 #endif
-                stage_copy(staged, prep, refs + base, n, tid);
+                stage_copy(staged, prep, refs + base * ref_stride, ref_stride, n, tid);
                 if (tid == 0) {
                     blk_prefix[0] = 0;
                     q_count = 0;
@@ -555,7 +530,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(cons
     // ---- phase B2: small triangles, one per lane, atomicMin on the key --------------------------
     // (item j of a round goes to lane j / warps of warp j % warps, so a short list spreads over all warps)
     for (uint32_t i = (uint32_t)(lane * (TILE_THREADS / 32) + warp); i < s_count; i += TILE_THREADS) {
-        const uint32_t slot = W.list_refs[s_begin + i];
+        const uint32_t slot = W.s_refs[s_begin + i].x;
         const uint4 *pq = reinterpret_cast<const uint4 *>(prep + slot);
         const uint4 bb = __ldg(pq + 5); // x0 x1 y0 y1
         const int lx = max((int)__uint_as_float(bb.x), wx0), hx = min((int)__uint_as_float(bb.y), wx0 + ww - 1);
@@ -592,6 +567,18 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(cons
     if (W.tile_cycles && tid == 0) atomicMax(&W.tile_cycles[2 * U.n_coarse + tile], (uint32_t)(clock64() - tb2_0) + W.tile_cycles[U.n_coarse + tile]); // + B2
 #endif
     // ---- phase C: deferred shading, fused clear ----------------------------------------------------
+    // The records of all the lane's winners are requested first (prefetch into L1: no registers held), so
+    // that the pixel loop below pays the L2 round trip once and not once per pixel.
+#pragma unroll 1
+    for (int q = tid; q < n_win; q += TILE_THREADS) {
+        const int x = wx0 + (q & (ww - 1)), y = wy0 + (q >> ww_shift);
+        const uint32_t slot = (uint32_t)keys[(y - ty0) * TILE_W + (x - tx0)];
+        if (slot == NO_SLOT) continue;
+        const char *sp = reinterpret_cast<const char *>(W.srec + slot);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(rrec + slot));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(sp));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + sizeof(ShadeRec) - 16));
+    }
 #pragma unroll 1
     for (int q = tid; q < n_win; q += TILE_THREADS) { // the window's pixels
         const int x = wx0 + (q & (ww - 1)), y = wy0 + (q >> ww_shift);
@@ -652,9 +639,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(cons
         const int p = (y - ty0) * TILE_W + (x - tx0);
         if (x >= W_ || y >= H_) continue;
         const uint32_t c = colour[p]; // r g b pad -> memory order b g r pad
-        reinterpret_cast<uint32_t *>(color)[(size_t)(H_ - 1 - y) * W_ + x] =
-            ((c >> 16) & 255u) | (c & 0x0000FF00u) | ((c & 255u) << 16) | (c & 0xFF000000u);
-        depth[(size_t)y * W_ + x] = __uint_as_float((uint32_t)(keys[p] >> 32));
+        __stcs(reinterpret_cast<uint32_t *>(color) + (size_t)(H_ - 1 - y) * W_ + x,
+               ((c >> 16) & 255u) | (c & 0x0000FF00u) | ((c & 255u) << 16) | (c & 0xFF000000u));
+        __stcs(depth + (size_t)y * W_ + x, __uint_as_float((uint32_t)(keys[p] >> 32)));
     }
 #if !defined(DRAW_TAP_B) || DRAW_TAP_B == 2
     if (W.tile_cycles) {
@@ -662,6 +649,92 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(cons
         if (tid == 0) atomicMax(&W.tile_cycles[tile], (uint32_t)(clock64() - t_start));
     }
 #endif
+}
+
+// ------------------------------------------------------------------------------------------
+// k_clear_empty : the tiles nothing was binned to get the clear colour and depth (canvas.rs:425-433).
+// They are most of a frame's bytes and none of its arithmetic, so they have their own launch: it
+// starts as soon as k_alloc has listed them, on the canvas' stream, and streams to HBM while the
+// latency-bound rest of the frame (k_bin<fill>, k_raster, the dense tiles of k_tile — and the previous
+// frame's) leaves the memory system idle.  One tile per warp, two 256-byte rows (colour) per store
+// instruction, pointers stepped by a row pair.
+// ------------------------------------------------------------------------------------------
+constexpr int CLEAR_THREADS = 256;
+__global__ void __launch_bounds__(CLEAR_THREADS) k_clear_empty(const __grid_constant__ FrameUniforms U, const FrameDev W,
+                                                               uint8_t *__restrict__ color, float *__restrict__ depth) {
+    pdl_prologue(false);
+    const uint32_t n_empty = W.counters[13];
+    const int lane = threadIdx.x & 31;
+    const int W_ = (int)U.canvas_w, H_ = (int)U.canvas_h;
+    const float depth_max = U.depth_max;
+    const uint32_t n_warps = gridDim.x * (CLEAR_THREADS / 32);
+    for (uint32_t e = blockIdx.x * (CLEAR_THREADS / 32) + (threadIdx.x >> 5); e < n_empty; e += n_warps) {
+        const uint32_t et = W.empty_tiles[e];
+        const int ex0 = (int)(et & (MAX_TILES_X - 1)) * TILE_W, ey0 = (int)(et >> 10) * TILE_H;
+        const uint32_t clear_px = 255u | (186u << 8) | (155u << 16) | (255u << 24); // memory order b g r pad
+        if ((W_ & 3) == 0) {
+            constexpr int QPR = TILE_W / 4, RPI = 32 / QPR; // 16-byte quads per tile row, rows per warp store
+            const int x = ex0 + (lane % QPR) * 4, r0 = lane / QPR;
+            const int rows = min(TILE_H, H_ - ey0);
+            if (x < W_) {
+                uint4 *cp = reinterpret_cast<uint4 *>(color + ((size_t)(H_ - 1 - ey0 - r0) * W_ + x) * 4);
+                float4 *dp = reinterpret_cast<float4 *>(depth + (size_t)(ey0 + r0) * W_ + x);
+                const ptrdiff_t step = (ptrdiff_t)RPI * (W_ / 4); // in 16-byte units: colour rows go up, depth rows down
+                const uint4 cv = make_uint4(clear_px, clear_px, clear_px, clear_px);
+                const float4 dv = make_float4(depth_max, depth_max, depth_max, depth_max);
+#pragma unroll 4
+                for (int r = r0; r < rows; r += RPI, cp -= step, dp += step) {
+                    __stcs(cp, cv); // streaming stores: the frame is written once and not read back, keep L2 for the records
+                    __stcs(dp, dv);
+                }
+            }
+        } else {
+            for (int p = lane; p < TILE_PIXELS; p += 32) {
+                const int x = ex0 + (p & (TILE_W - 1)), y = ey0 + p / TILE_W;
+                if (x >= W_ || y >= H_) continue;
+                __stcs(reinterpret_cast<uint32_t *>(color) + (size_t)(H_ - 1 - y) * W_ + x, clear_px);
+                __stcs(depth + (size_t)y * W_ + x, depth_max);
+            }
+        }
+        if (W.tile_cycles && lane == 0) atomicMax(&W.tile_cycles[(et >> 10) * U.tiles_x + (et & (MAX_TILES_X - 1))], 1u);
+    }
+}
+
+// Persistent CTAs (two per SM): each takes the next item of the work list — heaviest first — until the
+// list is exhausted, so that no CTA is launched just to find out that there is nothing to do, and the
+// per-CTA set-up is paid once.  Thread 0 keeps one list index and one item in flight ahead of the
+// item being processed (the cursor's atomicAdd and the list load are L2 round trips).
+__global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(const __grid_constant__ FrameUniforms U, const SceneDev S,
+                                                                            const FrameDev W, uint8_t *__restrict__ color,
+                                                                            float *__restrict__ depth, const uint32_t n_slots) {
+    __shared__ uint32_t s_item;
+    __shared__ float u8tab[256]; // (u8 as f32) / 255.0, filled once per CTA (visible after the loop's first barrier)
+    fill_u8_table(u8tab, threadIdx.x, TILE_THREADS);
+    pdl_prologue();
+    // The first item of a CTA is its own index; the cursor (in a cache line of its own: a load that shares
+    // a line with a contended atomic queues behind it) hands out the rest.
+    const bool usable = W.counters[2] == 0; // a work buffer overflowed: lists are unusable, the host re-renders
+    uint32_t *cursor = W.counters + ITEM_CURSOR;
+    uint32_t item = ITEM_NONE, ahead = 0; // thread 0 only
+    if (threadIdx.x == 0) {
+        ahead = gridDim.x + atomicAdd(cursor, 1u);
+        item = blockIdx.x < n_slots ? __ldcg(&W.tile_order[blockIdx.x]) : ITEM_NONE;
+    }
+    while (true) {
+        uint32_t next_item = ITEM_NONE, next_ahead = 0;
+        if (threadIdx.x == 0) {
+            s_item = item;
+            next_item = ahead < n_slots ? __ldcg(&W.tile_order[ahead]) : ITEM_NONE; // consumed after the item below
+            next_ahead = gridDim.x + atomicAdd(cursor, 1u);
+        }
+        __syncthreads();
+        const uint32_t cur = s_item;
+        if (cur == ITEM_NONE) break; // items are contiguous; the slots after them hold ITEM_NONE
+        tile_item(cur, U, S, W, color, depth, u8tab, usable);
+        __syncthreads(); // shared memory (and s_item) are reused by the next item
+        item = next_item;
+        ahead = next_ahead;
+    }
 }
 
 // Canvas::clear (canvas.rs:425-433) as a standalone operation (draw_canvas_clear).
@@ -684,8 +757,13 @@ __global__ void __launch_bounds__(256) k_fill_u32(uint32_t *__restrict__ dst, si
 uint32_t tile_grid_items(const FrameUniforms &U); // k_binning.cu
 void launch_tile(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, uint8_t *color, float *depth,
                  cudaStream_t stream) {
-    const uint32_t items = tile_grid_items(U); // one CTA per work-list slot; unused slots exit at once
-    if (items) launch_pdl(k_tile, items, TILE_THREADS, stream, U, S, W, color, depth);
+    const uint32_t slots = tile_grid_items(U); // work-list slots (k_alloc fills the unused ones with ITEM_NONE)
+    if (slots) launch_pdl(k_tile, min(slots, 148u * (1024u / TILE_THREADS)), TILE_THREADS, stream, U, S, W, color, depth, slots);
+}
+
+unsigned g_clear_ctas = 148u * 4u; // scene.cpp: DRAW_B200_CLEAR_CTAS
+void launch_clear_empty(const FrameUniforms &U, const FrameDev &W, uint8_t *color, float *depth, cudaStream_t stream) {
+    if (tile_grid_items(U)) launch_pdl(k_clear_empty, g_clear_ctas, CLEAR_THREADS, stream, U, W, color, depth);
 }
 
 cudaError_t launch_clear(uint8_t *color, float *depth, size_t n_pixels, float depth_max, cudaStream_t stream,

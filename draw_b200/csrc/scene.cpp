@@ -24,6 +24,7 @@
 
 namespace drawb200 {
 int g_pdl_enabled = 1;
+extern unsigned g_clear_ctas;
 // k_geometry.cu / k_binning.cu / k_tile.cu
 void launch_vertex(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
 void launch_setup(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
@@ -31,8 +32,11 @@ void launch_clip(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, c
 void launch_bin_count(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream);
 void launch_alloc(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream);
 void launch_bin_fill(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream);
+void launch_raster(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream);
+cudaError_t launch_fill_u64(unsigned long long *dst, size_t n, unsigned long long value, cudaStream_t stream);
 void launch_tile(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, uint8_t *color, float *depth,
                  cudaStream_t stream);
+void launch_clear_empty(const FrameUniforms &U, const FrameDev &W, uint8_t *color, float *depth, cudaStream_t stream);
 cudaError_t launch_clear(uint8_t *color, float *depth, size_t n_pixels, float depth_max, cudaStream_t stream,
                          uint64_t *launches);
 cudaError_t launch_fill_u32(uint32_t *dst, size_t n, uint32_t value, cudaStream_t stream, uint64_t *launches);
@@ -152,9 +156,14 @@ struct draw_scene {
         DevBuf<uint2> clip_queue;
         DevBuf<RasterRec> rrec, trrec;
         DevBuf<PrepRec> prep;
+        DevBuf<uint2> m_refs, s_refs;
+        DevBuf<uint32_t> tile_page;
+        DevBuf<unsigned long long> key_pages;
+        size_t pages_clean = 0; // pages [0, pages_clean) of key_pages.ptr are known to be empty
         DevBuf<ShadeRec> srec, tsrec;
         FrameDev work{};
         cudaStream_t stream = nullptr;   // side stream of this set
+        cudaEvent_t alloc_done = nullptr; // side stream: k_alloc has listed the frame's empty tiles and work items
         cudaEvent_t geo_done = nullptr;  // side stream: binning of the frame using this set has finished
         cudaEvent_t tile_done = nullptr; // canvas stream: k_tile of the frame using this set has finished
         bool tile_pending = false;
@@ -168,7 +177,7 @@ struct draw_scene {
     // optional per-kernel timing (draw_scene_set_kernel_timing): 0..6 around the six side-stream kernels,
     // 7 / 8 around k_tile on the canvas stream
     bool kernel_timing = false;
-    cudaEvent_t kev[N_FRAME_KERNELS + 2] = {};
+    cudaEvent_t kev[N_FRAME_KERNELS + 3] = {};
     bool kev_recorded = false;
 };
 
@@ -187,6 +196,8 @@ struct draw_canvas {
     size_t h_color_cap = 0;
     bool host_dirty = true;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t aux_stream = nullptr;                  // k_clear_empty runs here, beside k_tile
+    cudaEvent_t ev_begin = nullptr, ev_clear = nullptr; // fork / join of the auxiliary stream
     size_t stripe_y0 = 0, stripe_y1 = 0; // rows; y1 == 0 means whole canvas
     uint32_t *h_status = nullptr;        // pinned: counters of the last frame
     bool frame_pending = false;
@@ -320,10 +331,27 @@ int ensure_work_buffers(draw_scene *s, draw_scene::WorkSet &ws, size_t n_lists) 
     TRY(ws.list_count.reserve(n_lists));
     TRY(ws.list_offset.reserve(n_lists + 1));
     TRY(ws.refs.reserve(s->refs_cap));
-    TRY(ws.counters.reserve(8));
+    TRY(ws.m_refs.reserve(s->refs_cap));
+    TRY(ws.s_refs.reserve(s->refs_cap));
+    TRY(ws.tile_page.reserve(n_lists / LISTS_PER_TILE));
+    {
+        // key pages for k_raster: one per tile at most (DRAW_B200_PAGES caps the pool; 0 disables k_raster)
+        const size_t want = std::min<size_t>(n_lists / LISTS_PER_TILE, (size_t)std::max(0, env_int("DRAW_B200_PAGES", 16384)));
+        const unsigned long long *before = ws.key_pages.ptr;
+        TRY(ws.key_pages.reserve(want * TILE_W * TILE_H));
+        if (ws.key_pages.ptr != before) ws.pages_clean = 0;
+        if (want > ws.pages_clean) {
+            cudaStream_t st = ws.stream ? ws.stream : 0;
+            CU(launch_fill_u64(ws.key_pages.ptr + ws.pages_clean * TILE_W * TILE_H, (want - ws.pages_clean) * TILE_W * TILE_H, KEY_EMPTY, st));
+            if (!ws.stream) CU(cudaStreamSynchronize(0));
+            ws.pages_clean = want;
+        }
+        ws.work.page_cap = (uint32_t)want;
+    }
+    TRY(ws.counters.reserve(N_COUNTERS));
     TRY(ws.tile_cost.reserve(n_lists));
     TRY(ws.tile_order.reserve(n_lists + TILE_EXTRA_ITEMS));
-    TRY(ws.empty_tiles.reserve(n_lists / LISTS_PER_TILE + EMPTY_GROUP));
+    TRY(ws.empty_tiles.reserve(n_lists / LISTS_PER_TILE));
     TRY(ws.scan_desc.reserve((size_t)d.n_triangles / 256 + 2));
     TRY(ws.clip_queue.reserve(d.n_triangles));
     FrameDev &w = ws.work;
@@ -334,6 +362,8 @@ int ensure_work_buffers(draw_scene *s, draw_scene::WorkSet &ws, size_t n_lists) 
     w.rrec = ws.rrec.ptr; w.srec = ws.srec.ptr; w.prep = ws.prep.ptr;
     w.t_rrec = ws.trrec.ptr; w.t_srec = ws.tsrec.ptr;
     w.list_count = ws.list_count.ptr; w.list_offset = ws.list_offset.ptr; w.list_refs = ws.refs.ptr;
+    w.m_refs = ws.m_refs.ptr; w.s_refs = ws.s_refs.ptr;
+    w.tile_page = ws.tile_page.ptr; w.key_pages = ws.key_pages.ptr;
     w.counters = ws.counters.ptr;
     w.tile_cost = ws.tile_cost.ptr;
     w.tile_order = ws.tile_order.ptr;
@@ -347,6 +377,7 @@ int ensure_work_buffers(draw_scene *s, draw_scene::WorkSet &ws, size_t n_lists) 
         TRY(ws.tile_cycles.reserve(n_lists));
         w.tile_cycles = ws.tile_cycles.ptr;
     }
+    if (!ws.alloc_done) CU(cudaEventCreateWithFlags(&ws.alloc_done, cudaEventDisableTiming));
     if (!ws.geo_done) CU(cudaEventCreateWithFlags(&ws.geo_done, cudaEventDisableTiming));
     if (!ws.tile_done) CU(cudaEventCreateWithFlags(&ws.tile_done, cudaEventDisableTiming));
     return DRAW_OK;
@@ -409,7 +440,6 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     const draw_scene::WorkSet &prev_ws = s->sets[s->last_set];
     s->last_set = s->next_set;
     s->next_set = (s->next_set + 1) % s->n_sets;
-    TRY(ensure_work_buffers(s, ws, n_lists));
     if (!ws.stream) {
         // highest priority: the chain's few CTAs must get SM slots while the previous frame's k_tile
         // (thousands of CTAs on the canvas stream) is still being dispatched
@@ -417,6 +447,7 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
         CU(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
         CU(cudaStreamCreateWithPriority(&ws.stream, cudaStreamNonBlocking, env_int("DRAW_B200_PRIO", 1) ? prio_high : prio_low));
     }
+    TRY(ensure_work_buffers(s, ws, n_lists));
 
     FrameUniforms U{};
     const m4 m = transformation_matrix(s->camera, s->width, s->height); // :904
@@ -452,6 +483,7 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     cudaGetLastError(); // cudaErrorNotReady is not sticky, but keep the error state clean
     const int pdl_mode = env_int("DRAW_B200_PDL", 3); // 0 off, 1 always early, 2 never early, 3 early for a lone frame
     g_pdl_enabled = pdl_mode != 0;
+    g_clear_ctas = (unsigned)std::max(1, env_int("DRAW_B200_CLEAR_CTAS", 148 * 4));
     U.pdl_early = pdl_mode == 1 || (pdl_mode == 3 && !others_in_flight);
 
     // Side stream: geometry + binning.  It only waits for the tile kernel that last read this work set.
@@ -466,7 +498,7 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
 
     cudaEvent_t *ev = nullptr;
     if (s->kernel_timing) {
-        for (int i = 0; i < N_FRAME_KERNELS + 2; i++)
+        for (int i = 0; i < N_FRAME_KERNELS + 3; i++)
             if (!s->kev[i]) CU(cudaEventCreate(&s->kev[i]));
         ev = s->kev;
         s->kev_recorded = true;
@@ -481,19 +513,36 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     launch_bin_count(U, ws.work, side);
     if (ev) cudaEventRecord(ev[4], side);
     launch_alloc(U, ws.work, side);
+    CU(cudaEventRecord(ws.alloc_done, side));
     if (ev) cudaEventRecord(ev[5], side);
     launch_bin_fill(U, ws.work, side);
     if (ev) cudaEventRecord(ev[6], side);
+    launch_raster(U, ws.work, side);
+    if (ev) cudaEventRecord(ev[7], side);
     CU(cudaEventRecord(ws.geo_done, side));
     // Canvas stream: the tile kernel (the only stage that touches the canvas), then the frame's counters.
+    // The empty tiles are cleared on the canvas' auxiliary stream as soon as k_alloc has listed them: the
+    // stores stream to HBM under the rest of the geometry chain and under k_tile's dense tiles (disjoint
+    // pixels), and the canvas stream joins them before anything after k_tile can look at the frame.
     cudaStream_t st = c->stream;
+    if (!c->aux_stream) CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    if (!c->ev_begin) CU(cudaEventCreateWithFlags(&c->ev_begin, cudaEventDisableTiming));
+    if (!c->ev_clear) CU(cudaEventCreateWithFlags(&c->ev_clear, cudaEventDisableTiming));
+    CU(cudaEventRecord(c->ev_begin, st)); // whatever still reads or writes the canvas on its stream comes first
+    CU(cudaStreamWaitEvent(c->aux_stream, c->ev_begin, 0));
+    CU(cudaStreamWaitEvent(c->aux_stream, ws.alloc_done, 0));
+    if (ev) cudaEventRecord(ev[N_FRAME_KERNELS - 1], c->aux_stream);
+    launch_clear_empty(U, ws.work, c->color(), c->depth(), c->aux_stream);
+    if (ev) cudaEventRecord(ev[N_FRAME_KERNELS], c->aux_stream);
+    CU(cudaEventRecord(c->ev_clear, c->aux_stream));
     CU(cudaStreamWaitEvent(st, ws.geo_done, 0));
-    if (ev) cudaEventRecord(ev[7], st);
+    if (ev) cudaEventRecord(ev[N_FRAME_KERNELS + 1], st);
     launch_tile(U, s->dev, ws.work, c->color(), c->depth(), st);
-    if (ev) cudaEventRecord(ev[8], st);
+    if (ev) cudaEventRecord(ev[N_FRAME_KERNELS + 2], st);
+    CU(cudaStreamWaitEvent(st, c->ev_clear, 0));
     CU(cudaEventRecord(ws.tile_done, st));
     ws.tile_pending = true;
-    s->launches += 4 + (s->dev.n_triangles ? 2 : 0) + (U.tile_y_end > U.tile_y_begin ? 1 : 0);
+    s->launches += 5 + (s->dev.n_triangles ? 2 : 0) + (U.tile_y_end > U.tile_y_begin ? 2 : 0);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_status, ws.work.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     c->frame_pending = true;
@@ -621,10 +670,11 @@ void draw_scene_destroy(draw_scene *scene) {
         if (cur != scene->device) cudaSetDevice(scene->device);
         cudaDeviceSynchronize();
         for (draw_scene::WorkSet &ws : scene->sets) {
+            if (ws.alloc_done) cudaEventDestroy(ws.alloc_done);
             if (ws.geo_done) cudaEventDestroy(ws.geo_done);
             if (ws.tile_done) cudaEventDestroy(ws.tile_done);
         }
-        for (int i = 0; i < N_FRAME_KERNELS + 2; i++)
+        for (int i = 0; i < N_FRAME_KERNELS + 3; i++)
             if (scene->kev[i]) cudaEventDestroy(scene->kev[i]);
         for (draw_scene::WorkSet &ws : scene->sets)
             if (ws.stream) cudaStreamDestroy(ws.stream);
@@ -837,13 +887,14 @@ int draw_scene_set_kernel_timing(draw_scene *scene, int enabled) {
     return DRAW_OK;
 }
 
-int draw_scene_last_kernel_times(draw_scene *scene, draw_canvas *canvas, float ms[7]) {
+int draw_scene_last_kernel_times(draw_scene *scene, draw_canvas *canvas, float ms[9]) {
     GUARD_BEGIN
     if (!scene || !canvas || !ms) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!scene->kev_recorded) return fail(DRAW_ERR_INVALID_ARGUMENT, "kernel timing was not enabled for the last frame");
     TRY(finish_frame(canvas));
-    for (int i = 0; i < N_FRAME_KERNELS - 1; i++) CU(cudaEventElapsedTime(&ms[i], scene->kev[i], scene->kev[i + 1]));
-    CU(cudaEventElapsedTime(&ms[N_FRAME_KERNELS - 1], scene->kev[7], scene->kev[8])); // k_tile, on the canvas stream
+    for (int i = 0; i < N_FRAME_KERNELS - 2; i++) CU(cudaEventElapsedTime(&ms[i], scene->kev[i], scene->kev[i + 1])); // side stream
+    CU(cudaEventElapsedTime(&ms[N_FRAME_KERNELS - 2], scene->kev[N_FRAME_KERNELS - 1], scene->kev[N_FRAME_KERNELS])); // k_clear_empty
+    CU(cudaEventElapsedTime(&ms[N_FRAME_KERNELS - 1], scene->kev[N_FRAME_KERNELS + 1], scene->kev[N_FRAME_KERNELS + 2])); // k_tile
     return DRAW_OK;
     GUARD_END
 }
@@ -916,6 +967,12 @@ void draw_canvas_destroy(draw_canvas *canvas) {
     if (cudaGetDevice(&cur) == cudaSuccess) {
         if (cur != canvas->device) cudaSetDevice(canvas->device);
         if (canvas->stream) cudaStreamSynchronize(canvas->stream);
+        if (canvas->aux_stream) {
+            cudaStreamSynchronize(canvas->aux_stream);
+            cudaStreamDestroy(canvas->aux_stream);
+        }
+        if (canvas->ev_begin) cudaEventDestroy(canvas->ev_begin);
+        if (canvas->ev_clear) cudaEventDestroy(canvas->ev_clear);
         if (canvas->own_stream) cudaStreamDestroy(canvas->own_stream);
         if (canvas->h_color) cudaFreeHost(canvas->h_color);
         if (canvas->h_status) cudaFreeHost(canvas->h_status);

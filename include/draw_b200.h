@@ -143,9 +143,9 @@ int draw_scene_launch_count(const draw_scene *scene, uint64_t *out);
 
 /* Measurement tap: when enabled, every frame records CUDA events between its kernels on the
  * canvas' stream; last_kernel_times waits for the frame and returns the device time in ms of
- * k_vertex, k_setup, k_clip, k_bin<count>, k_alloc, k_bin<fill>, k_tile (DESIGN.md describes them). */
+ * k_vertex, k_setup, k_clip, k_bin<count>, k_alloc, k_bin<fill>, k_raster, k_clear_empty, k_tile (DESIGN.md describes them). */
 int draw_scene_set_kernel_timing(draw_scene *scene, int enabled);
-int draw_scene_last_kernel_times(draw_scene *scene, draw_canvas *canvas, float ms[7]);
+int draw_scene_last_kernel_times(draw_scene *scene, draw_canvas *canvas, float ms[9]);
 
 /* Debug tap: sizes of the last frame's tile lists (coarse tiles first, then fine tiles, see
  * DESIGN.md).  out == NULL only returns the number of coarse tiles. */

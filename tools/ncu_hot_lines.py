@@ -14,7 +14,7 @@ rep = sys.argv[1]
 lib = sys.argv[2] if len(sys.argv) > 2 else "draw_b200/libdraw_b200.so"
 kern = sys.argv[3] if len(sys.argv) > 3 else "k_tile"
 
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kern], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 h = rows[1]
 ci = {n: i for i, n in enumerate(h)}
