@@ -71,7 +71,9 @@ inline uint32_t make_item(uint32_t tx, uint32_t ty, uint32_t splits, uint32_t i)
     return tx | ty << 10 | rx0 << 21 | ry0 << 23 | (rw - 1u) << 25 | (rh - 1u) << 27;
 }
 
-// Per-frame constants, passed to every kernel by value (__grid_constant__): no upload, no sync.
+// Per-frame constants.  They live in device memory (one small upload per frame) and every kernel takes a
+// pointer to them, so that a frame's launches are identical from frame to frame and can be replayed as a
+// CUDA graph (scene.cpp).
 struct FrameUniforms {
     float m[16];        // matrix_transf, row-major (scene/mod.rs:817-899)
     float planes[6][4]; // near, far, right, left, top, bottom as (nx,ny,nz,k) (scene/mod.rs:481-593)
@@ -85,6 +87,8 @@ struct FrameUniforms {
     uint32_t n_coarse;                 // tiles_x * tiles_y
     uint32_t n_lists;                  // LISTS_PER_TILE * n_coarse: large, medium, small lists
     uint32_t split_min_cost, split_div, split_max; // k_alloc's tile splitting policy (defaults: TILE_SPLIT_*)
+    uint8_t *color;                    // the canvas: BGRA8, row 0 = top (canvas.rs:955-956)
+    float *depth;                      // depth buffer, row 0 = y 0 (canvas.rs:413-423)
     uint32_t has_transparent;          // transparent triangles are not binned: no tile may take the empty-tile path
     uint32_t pdl_early;                // geometry / binning kernels trigger their dependents at once (device_math.cuh)
 };

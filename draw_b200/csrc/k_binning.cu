@@ -109,7 +109,8 @@ __device__ __forceinline__ TileRange tile_range(const FrameUniforms &U, uint32_t
 }
 
 template <bool FILL>
-__global__ void __launch_bounds__(BIN_THREADS) k_bin(const __grid_constant__ FrameUniforms U, const FrameDev W) {
+__global__ void __launch_bounds__(BIN_THREADS) k_bin(const FrameUniforms *__restrict__ Up, const FrameDev W) {
+    const FrameUniforms &U = *Up; // per-frame uniforms, device-resident (one upload per frame; the launches never change)
     pdl_prologue(U.pdl_early != 0);
     if (FILL && W.counters[2] != 0) return; // a buffer overflowed: the host re-renders with larger buffers
     uint32_t n = W.counters[0];
@@ -204,7 +205,8 @@ __device__ __forceinline__ uint32_t tile_splits(uint32_t cost, uint32_t target, 
     return min(max_split, 1u << (31 - __clz(q)));
 }
 
-__global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const __grid_constant__ FrameUniforms U, const FrameDev W) {
+__global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const FrameUniforms *__restrict__ Up, const FrameDev W) {
+    const FrameUniforms &U = *Up; // per-frame uniforms, device-resident (one upload per frame; the launches never change)
     __shared__ uint32_t warp_sum[3][ALLOC_THREADS / 32], warp_cost[ALLOC_THREADS / 32];
     __shared__ uint32_t block_base3[3], block_base, is_last;
     __shared__ uint32_t bucket_start[COST_BUCKETS];
@@ -339,18 +341,18 @@ __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const __grid_constant__
 // launchers
 // ------------------------------------------------------------------------------------------
 static int bin_blocks(const FrameDev &) { return 148 * 4; }
-void launch_bin_count(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream) {
-    launch_pdl(k_bin<false>, bin_blocks(W), BIN_THREADS, stream, U, W);
+void launch_bin_count(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream) {
+    launch_pdl(k_bin<false>, bin_blocks(W), BIN_THREADS, stream, dU, W);
 }
 uint32_t tile_grid_items(const FrameUniforms &U) { // k_tile's grid: one CTA per work-list slot
     const uint32_t stripe_tiles = (U.tile_y_end - U.tile_y_begin) * U.tiles_x;
     return stripe_tiles ? stripe_tiles + (TILE_SPLITTABLE ? TILE_EXTRA_ITEMS : 0) : 0;
 }
-void launch_alloc(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream) {
-    launch_pdl(k_alloc, (U.n_coarse + ALLOC_THREADS - 1) / ALLOC_THREADS, ALLOC_THREADS, stream, U, W);
+void launch_alloc(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream) {
+    launch_pdl(k_alloc, (U.n_coarse + ALLOC_THREADS - 1) / ALLOC_THREADS, ALLOC_THREADS, stream, dU, W);
 }
-void launch_bin_fill(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream) {
-    launch_pdl(k_bin<true>, bin_blocks(W), BIN_THREADS, stream, U, W);
+void launch_bin_fill(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream) {
+    launch_pdl(k_bin<true>, bin_blocks(W), BIN_THREADS, stream, dU, W);
 }
 
 } // namespace drawb200

@@ -16,8 +16,9 @@ namespace drawb200 {
 // ------------------------------------------------------------------------------------------
 // k_vertex
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ FrameUniforms U, const SceneDev S,
+__global__ void __launch_bounds__(256) k_vertex(const FrameUniforms *__restrict__ Up, const SceneDev S,
                                                 const FrameDev W) {
+    const FrameUniforms &U = *Up; // per-frame uniforms, device-resident (one upload per frame; the launches never change)
     pdl_prologue(U.pdl_early != 0);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     // per-frame reset of the binning state (the binning kernels run after this one on the same stream)
@@ -295,8 +296,9 @@ constexpr int SETUP_THREADS = 256;
 // what lets k_tile break depth ties by comparing slots.  Inside a CTA: ballot/popc-style prefix sums
 // over the per-thread output counts (0..4).  Across CTAs: single-pass chained scan with decoupled
 // look-back; CTAs take a ticket so that the chain follows launch order and cannot deadlock.
-__global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__ FrameUniforms U, const SceneDev S,
+__global__ void __launch_bounds__(SETUP_THREADS) k_setup(const FrameUniforms *__restrict__ Up, const SceneDev S,
                                                          const FrameDev W) {
+    const FrameUniforms &U = *Up; // per-frame uniforms, device-resident (one upload per frame; the launches never change)
     __shared__ uint32_t warp_tot[SETUP_THREADS / 32];
     __shared__ uint32_t s_ticket, s_base;
     pdl_prologue(U.pdl_early != 0);
@@ -480,8 +482,9 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 // ------------------------------------------------------------------------------------------
 constexpr int CLIP_THREADS = 128;
 
-__global__ void __launch_bounds__(CLIP_THREADS) k_clip(const __grid_constant__ FrameUniforms U, const SceneDev S,
+__global__ void __launch_bounds__(CLIP_THREADS) k_clip(const FrameUniforms *__restrict__ Up, const SceneDev S,
                                                        const FrameDev W) {
+    const FrameUniforms &U = *Up; // per-frame uniforms, device-resident (one upload per frame; the launches never change)
     pdl_prologue(U.pdl_early != 0);
     const uint32_t n = W.counters[5];
     for (uint32_t q = blockIdx.x * CLIP_THREADS + threadIdx.x; q < n; q += gridDim.x * CLIP_THREADS) {
@@ -505,21 +508,21 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip(const __grid_constant__ F
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-void launch_clip(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, cudaStream_t stream) {
+void launch_clip(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream) {
     if (!S.n_triangles) return;
-    launch_pdl(k_clip, 148u * 2u, CLIP_THREADS, stream, U, S, W);
+    launch_pdl(k_clip, 148u * 2u, CLIP_THREADS, stream, dU, S, W);
 }
 
-void launch_vertex(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, cudaStream_t stream) {
+void launch_vertex(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream) {
     const uint32_t by_vertex = (S.n_vertices + 255) / 256, by_list = (U.n_lists + 255) / 256;
     uint32_t blocks = by_vertex > 1 ? by_vertex : 1;
     if (blocks < by_list && blocks < 148 * 4) blocks = by_list < 148 * 4 ? by_list : 148 * 4;
-    launch_pdl(k_vertex, blocks, 256, stream, U, S, W);
+    launch_pdl(k_vertex, blocks, 256, stream, dU, S, W);
 }
 
-void launch_setup(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, cudaStream_t stream) {
+void launch_setup(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream) {
     if (!S.n_triangles) return;
-    launch_pdl(k_setup, (S.n_triangles + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, stream, U, S, W);
+    launch_pdl(k_setup, (S.n_triangles + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, stream, dU, S, W);
 }
 
 } // namespace drawb200

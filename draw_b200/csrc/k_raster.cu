@@ -34,7 +34,8 @@ __device__ __forceinline__ void commit_fragment(unsigned long long *cell, unsign
 #endif
 }
 
-__global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster(const __grid_constant__ FrameUniforms U, const FrameDev W) {
+__global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster(const FrameUniforms *__restrict__ Up, const FrameDev W) {
+    const FrameUniforms &U = *Up; // per-frame uniforms, device-resident (one upload per frame; the launches never change)
     pdl_prologue(U.pdl_early != 0);
     if (W.counters[2] != 0 || W.page_cap == 0) return; // a buffer overflowed: the host re-renders; or no pages at all
     const uint32_t n_medium = min(W.counters[9], W.refs_cap), n_small = min(W.counters[10], W.refs_cap);
@@ -128,8 +129,8 @@ __global__ void __launch_bounds__(256) k_fill_u64(unsigned long long *__restrict
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = value;
 }
 
-void launch_raster(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream) {
-    launch_pdl(k_raster, 148u * 8u, RASTER_THREADS, stream, U, W);
+void launch_raster(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream) {
+    launch_pdl(k_raster, 148u * 8u, RASTER_THREADS, stream, dU, W);
 }
 cudaError_t launch_fill_u64(unsigned long long *dst, size_t n, unsigned long long value, cudaStream_t stream) {
     k_fill_u64<<<148 * 4, 256, 0, stream>>>(dst, n, value);

@@ -660,8 +660,10 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
 // instruction, pointers stepped by a row pair.
 // ------------------------------------------------------------------------------------------
 constexpr int CLEAR_THREADS = 256;
-__global__ void __launch_bounds__(CLEAR_THREADS) k_clear_empty(const __grid_constant__ FrameUniforms U, const FrameDev W,
-                                                               uint8_t *__restrict__ color, float *__restrict__ depth) {
+__global__ void __launch_bounds__(CLEAR_THREADS) k_clear_empty(const FrameUniforms *__restrict__ Up, const FrameDev W) {
+    const FrameUniforms &U = *Up; // per-frame uniforms, device-resident (one upload per frame; the launches never change)
+    uint8_t *__restrict__ color = U.color;
+    float *__restrict__ depth = U.depth;
     pdl_prologue(false);
     const uint32_t n_empty = W.counters[13];
     const int lane = threadIdx.x & 31;
@@ -704,9 +706,11 @@ __global__ void __launch_bounds__(CLEAR_THREADS) k_clear_empty(const __grid_cons
 // list is exhausted, so that no CTA is launched just to find out that there is nothing to do, and the
 // per-CTA set-up is paid once.  Thread 0 keeps one list index and one item in flight ahead of the
 // item being processed (the cursor's atomicAdd and the list load are L2 round trips).
-__global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(const __grid_constant__ FrameUniforms U, const SceneDev S,
-                                                                            const FrameDev W, uint8_t *__restrict__ color,
-                                                                            float *__restrict__ depth, const uint32_t n_slots) {
+__global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(const FrameUniforms *__restrict__ Up, const SceneDev S,
+                                                                            const FrameDev W, const uint32_t n_slots) {
+    const FrameUniforms &U = *Up; // per-frame uniforms, device-resident (one upload per frame; the launches never change)
+    uint8_t *__restrict__ color = U.color;
+    float *__restrict__ depth = U.depth;
     __shared__ uint32_t s_item;
     __shared__ float u8tab[256]; // (u8 as f32) / 255.0, filled once per CTA (visible after the loop's first barrier)
     fill_u8_table(u8tab, threadIdx.x, TILE_THREADS);
@@ -754,16 +758,17 @@ __global__ void __launch_bounds__(256) k_fill_u32(uint32_t *__restrict__ dst, si
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+extern unsigned g_tile_ctas;
 uint32_t tile_grid_items(const FrameUniforms &U); // k_binning.cu
-void launch_tile(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, uint8_t *color, float *depth,
-                 cudaStream_t stream) {
+void launch_tile(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream) {
     const uint32_t slots = tile_grid_items(U); // work-list slots (k_alloc fills the unused ones with ITEM_NONE)
-    if (slots) launch_pdl(k_tile, min(slots, 148u * (1024u / TILE_THREADS)), TILE_THREADS, stream, U, S, W, color, depth, slots);
+    if (slots) launch_pdl(k_tile, min(slots, g_tile_ctas), TILE_THREADS, stream, dU, S, W, slots);
 }
 
 unsigned g_clear_ctas = 148u * 4u; // scene.cpp: DRAW_B200_CLEAR_CTAS
-void launch_clear_empty(const FrameUniforms &U, const FrameDev &W, uint8_t *color, float *depth, cudaStream_t stream) {
-    if (tile_grid_items(U)) launch_pdl(k_clear_empty, g_clear_ctas, CLEAR_THREADS, stream, U, W, color, depth);
+unsigned g_tile_ctas = 148u * (1024u / TILE_THREADS); // scene.cpp: DRAW_B200_TILE_CTAS (persistent CTAs of k_tile)
+void launch_clear_empty(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream) {
+    if (tile_grid_items(U)) launch_pdl(k_clear_empty, g_clear_ctas, CLEAR_THREADS, stream, dU, W);
 }
 
 cudaError_t launch_clear(uint8_t *color, float *depth, size_t n_pixels, float depth_max, cudaStream_t stream,

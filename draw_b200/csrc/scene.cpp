@@ -24,19 +24,18 @@
 
 namespace drawb200 {
 int g_pdl_enabled = 1;
-extern unsigned g_clear_ctas;
+extern unsigned g_clear_ctas, g_tile_ctas;
 // k_geometry.cu / k_binning.cu / k_tile.cu
-void launch_vertex(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
-void launch_setup(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
-void launch_clip(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
-void launch_bin_count(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream);
-void launch_alloc(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream);
-void launch_bin_fill(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream);
-void launch_raster(const FrameUniforms &U, const FrameDev &W, cudaStream_t stream);
+void launch_vertex(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
+void launch_setup(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
+void launch_clip(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
+void launch_bin_count(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream);
+void launch_alloc(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream);
+void launch_bin_fill(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream);
+void launch_raster(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream);
 cudaError_t launch_fill_u64(unsigned long long *dst, size_t n, unsigned long long value, cudaStream_t stream);
-void launch_tile(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, uint8_t *color, float *depth,
-                 cudaStream_t stream);
-void launch_clear_empty(const FrameUniforms &U, const FrameDev &W, uint8_t *color, float *depth, cudaStream_t stream);
+void launch_tile(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
+void launch_clear_empty(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream);
 cudaError_t launch_clear(uint8_t *color, float *depth, size_t n_pixels, float depth_max, cudaStream_t stream,
                          uint64_t *launches);
 cudaError_t launch_fill_u32(uint32_t *dst, size_t n, uint32_t value, cudaStream_t stream, uint64_t *launches);
@@ -125,6 +124,13 @@ std::set<draw_scene *> g_live_scenes;
 // ------------------------------------------------------------------------------------------
 // handles
 // ------------------------------------------------------------------------------------------
+// What a captured frame graph depends on besides the uniforms (which it reads from device memory).
+struct GraphKey {
+    SceneDev scene;
+    FrameDev work;
+    uint32_t n_coarse, n_lists, tiles_x, tile_y_begin, tile_y_end, clear_ctas;
+};
+
 struct draw_scene {
     int device = 0;
     size_t width = 0, height = 0;
@@ -162,11 +168,18 @@ struct draw_scene {
         size_t pages_clean = 0; // pages [0, pages_clean) of key_pages.ptr are known to be empty
         DevBuf<ShadeRec> srec, tsrec;
         FrameDev work{};
-        cudaStream_t stream = nullptr;   // side stream of this set
+        cudaStream_t stream = nullptr;   // the frame using this set runs here ...
+        cudaStream_t aux_stream = nullptr; // ... and its k_clear_empty here, beside k_bin<fill> / k_raster / k_tile
+        DevBuf<FrameUniforms> d_uniforms;
+        FrameUniforms *h_uniforms = nullptr; // pinned staging of d_uniforms
+        cudaGraphExec_t graph_exec = nullptr;
+        GraphKey graph_key{};
         cudaEvent_t alloc_done = nullptr; // side stream: k_alloc has listed the frame's empty tiles and work items
         cudaEvent_t geo_done = nullptr;  // side stream: binning of the frame using this set has finished
-        cudaEvent_t tile_done = nullptr; // canvas stream: k_tile of the frame using this set has finished
-        bool tile_pending = false;
+        cudaEvent_t canvas_ready = nullptr; // canvas stream: the canvas of the frame using this set may be written
+        cudaEvent_t clear_done = nullptr; // aux stream: k_clear_empty has finished
+        cudaEvent_t frame_done = nullptr; // the whole frame using this set has finished
+        bool frame_pending = false;
     };
     static constexpr int MAX_WORK_SETS = 8;
     WorkSet sets[MAX_WORK_SETS];
@@ -196,8 +209,6 @@ struct draw_canvas {
     size_t h_color_cap = 0;
     bool host_dirty = true;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaStream_t aux_stream = nullptr;                  // k_clear_empty runs here, beside k_tile
-    cudaEvent_t ev_begin = nullptr, ev_clear = nullptr; // fork / join of the auxiliary stream
     size_t stripe_y0 = 0, stripe_y1 = 0; // rows; y1 == 0 means whole canvas
     uint32_t *h_status = nullptr;        // pinned: counters of the last frame
     bool frame_pending = false;
@@ -215,6 +226,21 @@ int env_int(const char *name, int fallback) {
     const char *v = std::getenv(name);
     return v && *v ? std::atoi(v) : fallback;
 }
+
+// Tuning knobs, read from the environment once (defaults are what bench.py measures).
+struct Config {
+    int graphs = env_int("DRAW_B200_GRAPH", 1);   // replay each frame as a CUDA graph
+    int prio = env_int("DRAW_B200_PRIO", 0);      // work-set streams at the highest priority
+    int pdl = env_int("DRAW_B200_PDL", 3);        // programmatic dependent launch: 0 off, 1 early trigger, 2 late, 3 early for a lone frame
+    int sets = std::min(std::max(env_int("DRAW_B200_SETS", 4), 1), 8); // frames in flight per scene
+    int pages = std::max(0, env_int("DRAW_B200_PAGES", 16384));        // key pages per work set (0: k_raster off)
+    int clear_ctas = std::max(1, env_int("DRAW_B200_CLEAR_CTAS", 148 * 4));
+    int tile_ctas = std::max(1, env_int("DRAW_B200_TILE_CTAS", 148 * (1024 / TILE_THREADS)));
+    int split_min_cost = std::max(1, env_int("DRAW_B200_SPLIT_MIN_COST", TILE_SPLIT_MIN_COST));
+    int split_div = std::min(std::max(1, env_int("DRAW_B200_SPLIT_DIV", TILE_SPLIT_DIV)), (int)TILE_EXTRA_ITEMS);
+    int split_max = std::min(std::max(1, env_int("DRAW_B200_SPLIT_MAX", TILE_MAX_SPLIT)), (int)TILE_MAX_SPLIT);
+};
+const Config g_cfg;
 
 int ensure_device(int device) {
     int cur = -1;
@@ -336,7 +362,7 @@ int ensure_work_buffers(draw_scene *s, draw_scene::WorkSet &ws, size_t n_lists) 
     TRY(ws.tile_page.reserve(n_lists / LISTS_PER_TILE));
     {
         // key pages for k_raster: one per tile at most (DRAW_B200_PAGES caps the pool; 0 disables k_raster)
-        const size_t want = std::min<size_t>(n_lists / LISTS_PER_TILE, (size_t)std::max(0, env_int("DRAW_B200_PAGES", 16384)));
+        const size_t want = std::min<size_t>(n_lists / LISTS_PER_TILE, (size_t)g_cfg.pages);
         const unsigned long long *before = ws.key_pages.ptr;
         TRY(ws.key_pages.reserve(want * TILE_W * TILE_H));
         if (ws.key_pages.ptr != before) ws.pages_clean = 0;
@@ -379,7 +405,9 @@ int ensure_work_buffers(draw_scene *s, draw_scene::WorkSet &ws, size_t n_lists) 
     }
     if (!ws.alloc_done) CU(cudaEventCreateWithFlags(&ws.alloc_done, cudaEventDisableTiming));
     if (!ws.geo_done) CU(cudaEventCreateWithFlags(&ws.geo_done, cudaEventDisableTiming));
-    if (!ws.tile_done) CU(cudaEventCreateWithFlags(&ws.tile_done, cudaEventDisableTiming));
+    if (!ws.canvas_ready) CU(cudaEventCreateWithFlags(&ws.canvas_ready, cudaEventDisableTiming));
+    if (!ws.clear_done) CU(cudaEventCreateWithFlags(&ws.clear_done, cudaEventDisableTiming));
+    if (!ws.frame_done) CU(cudaEventCreateWithFlags(&ws.frame_done, cudaEventDisableTiming));
     return DRAW_OK;
 }
 
@@ -428,6 +456,46 @@ int sort_transparent(draw_scene *s, cudaStream_t stream) {
     return DRAW_OK;
 }
 
+// The launches of one frame on the work set's streams (directly, or under stream capture).
+int launch_frame(draw_scene *s, draw_scene::WorkSet &ws, const FrameUniforms &U, cudaStream_t side, cudaEvent_t *ev,
+                 bool capturing) {
+    const FrameUniforms *dU = ws.d_uniforms.ptr;
+    // ws.canvas_ready is recorded on the canvas' stream outside the graph: an external event of the capture
+    const unsigned ext = capturing ? cudaEventWaitExternal : 0u;
+    CU(cudaMemcpyAsync(ws.d_uniforms.ptr, ws.h_uniforms, sizeof(FrameUniforms), cudaMemcpyHostToDevice, side));
+    if (ev) cudaEventRecord(ev[0], side);
+    launch_vertex(U, dU, s->dev, ws.work, side);
+    if (ev) cudaEventRecord(ev[1], side);
+    launch_setup(U, dU, s->dev, ws.work, side);
+    if (ev) cudaEventRecord(ev[2], side);
+    launch_clip(U, dU, s->dev, ws.work, side);
+    if (ev) cudaEventRecord(ev[3], side);
+    launch_bin_count(U, dU, ws.work, side);
+    if (ev) cudaEventRecord(ev[4], side);
+    launch_alloc(U, dU, ws.work, side);
+    CU(cudaEventRecord(ws.alloc_done, side));
+    if (ev) cudaEventRecord(ev[5], side);
+    // the empty tiles are cleared as soon as k_alloc has listed them: the stores stream to HBM under the
+    // rest of the chain and under k_tile's dense tiles (disjoint pixels)
+    CU(cudaStreamWaitEvent(ws.aux_stream, ws.alloc_done, 0));
+    CU(cudaStreamWaitEvent(ws.aux_stream, ws.canvas_ready, ext));
+    if (ev) cudaEventRecord(ev[N_FRAME_KERNELS - 1], ws.aux_stream);
+    launch_clear_empty(U, dU, ws.work, ws.aux_stream);
+    if (ev) cudaEventRecord(ev[N_FRAME_KERNELS], ws.aux_stream);
+    CU(cudaEventRecord(ws.clear_done, ws.aux_stream));
+    launch_bin_fill(U, dU, ws.work, side);
+    if (ev) cudaEventRecord(ev[6], side);
+    launch_raster(U, dU, ws.work, side);
+    if (ev) cudaEventRecord(ev[7], side);
+    CU(cudaEventRecord(ws.geo_done, side));
+    CU(cudaStreamWaitEvent(side, ws.canvas_ready, ext));
+    if (ev) cudaEventRecord(ev[N_FRAME_KERNELS + 1], side);
+    launch_tile(U, dU, s->dev, ws.work, side);
+    if (ev) cudaEventRecord(ev[N_FRAME_KERNELS + 2], side);
+    CU(cudaStreamWaitEvent(side, ws.clear_done, 0));
+    return DRAW_OK;
+}
+
 int enqueue_frame(draw_scene *s, draw_canvas *c) {
     TRY(ensure_device(s->device));
     if (s->geometry_dirty) TRY(upload_geometry(s));
@@ -445,7 +513,10 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
         // (thousands of CTAs on the canvas stream) is still being dispatched
         int prio_low = 0, prio_high = 0;
         CU(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
-        CU(cudaStreamCreateWithPriority(&ws.stream, cudaStreamNonBlocking, env_int("DRAW_B200_PRIO", 1) ? prio_high : prio_low));
+        CU(cudaStreamCreateWithPriority(&ws.stream, cudaStreamNonBlocking, g_cfg.prio ? prio_high : prio_low));
+        CU(cudaStreamCreateWithFlags(&ws.aux_stream, cudaStreamNonBlocking));
+        CU(cudaMallocHost(&ws.h_uniforms, sizeof(FrameUniforms)));
+        TRY(ws.d_uniforms.reserve(1));
     }
     TRY(ensure_work_buffers(s, ws, n_lists));
 
@@ -470,28 +541,42 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     U.n_coarse = n_coarse;
     U.n_lists = n_lists;
     U.has_transparent = s->dev.n_transparent != 0;
-    U.split_min_cost = (uint32_t)std::max(1, env_int("DRAW_B200_SPLIT_MIN_COST", TILE_SPLIT_MIN_COST));
-    U.split_div = (uint32_t)std::min(std::max(1, env_int("DRAW_B200_SPLIT_DIV", TILE_SPLIT_DIV)), (int)TILE_EXTRA_ITEMS);
-    U.split_max = (uint32_t)std::min(std::max(1, env_int("DRAW_B200_SPLIT_MAX", TILE_MAX_SPLIT)), (int)TILE_MAX_SPLIT);
+    U.split_min_cost = (uint32_t)g_cfg.split_min_cost;
+    U.split_div = (uint32_t)g_cfg.split_div;
+    U.split_max = (uint32_t)g_cfg.split_max;
     const size_t y0 = c->stripe_y1 ? c->stripe_y0 : 0, y1 = c->stripe_y1 ? c->stripe_y1 : c->height;
     U.tile_y_begin = (uint32_t)(y0 / TILE_H);
     U.tile_y_end = (uint32_t)((y1 + TILE_H - 1) / TILE_H);
     // early trigger only for a lone frame: with other frames in flight the idle dependents would hold SM slots
     bool others_in_flight = false;
     for (int i = 0; i < s->n_sets; i++)
-        if (&s->sets[i] != &ws && s->sets[i].tile_pending && cudaEventQuery(s->sets[i].tile_done) == cudaErrorNotReady) others_in_flight = true;
+        if (&s->sets[i] != &ws && s->sets[i].frame_pending && cudaEventQuery(s->sets[i].frame_done) == cudaErrorNotReady) others_in_flight = true;
     cudaGetLastError(); // cudaErrorNotReady is not sticky, but keep the error state clean
-    const int pdl_mode = env_int("DRAW_B200_PDL", 3); // 0 off, 1 always early, 2 never early, 3 early for a lone frame
+    const int pdl_mode = g_cfg.pdl; // 0 off, 1 always early, 2 never early, 3 early for a lone frame
     g_pdl_enabled = pdl_mode != 0;
-    g_clear_ctas = (unsigned)std::max(1, env_int("DRAW_B200_CLEAR_CTAS", 148 * 4));
+    g_clear_ctas = (unsigned)g_cfg.clear_ctas;
+    g_tile_ctas = (unsigned)g_cfg.tile_ctas;
     U.pdl_early = pdl_mode == 1 || (pdl_mode == 3 && !others_in_flight);
 
-    // Side stream: geometry + binning.  It only waits for the tile kernel that last read this work set.
-    cudaStream_t side = ws.stream;
-    if (ws.tile_pending) CU(cudaStreamWaitEvent(side, ws.tile_done, 0));
+    U.color = c->color();
+    U.depth = c->depth();
+
+    // ---- enqueue ----------------------------------------------------------------------------------
+    // Everything of the frame runs on the work set's own streams: the geometry chain and k_tile on
+    // ws.stream, k_clear_empty beside them on ws.aux_stream (forked after k_alloc, joined after k_tile).
+    // The canvas' stream only brackets the frame: the set's stream first waits for whatever the canvas
+    // stream still does with the canvas, and the canvas stream then waits for the frame.  Frames that
+    // use different work sets are therefore independent and overlap; a set's next frame follows its
+    // previous one in stream order.
+    cudaStream_t side = ws.stream, st = c->stream;
+    if (ws.frame_pending) CU(cudaEventSynchronize(ws.frame_done)); // the pinned uniforms of the set are about to be rewritten
+    *ws.h_uniforms = U;
+    // what the canvas stream still does with the canvas comes before the two kernels that write it
+    // (k_clear_empty, k_tile wait for this event; the geometry chain does not touch the canvas and does not wait)
+    CU(cudaEventRecord(ws.canvas_ready, st));
     if (s->dev.n_transparent) {
         // the painter sort rewrites the shared index streams: order it after the previous frame's geometry
-        if (&prev_ws != &ws && prev_ws.geo_done && prev_ws.tile_pending) CU(cudaStreamWaitEvent(side, prev_ws.geo_done, 0));
+        if (&prev_ws != &ws && prev_ws.frame_pending) CU(cudaStreamWaitEvent(side, prev_ws.geo_done, 0));
         TRY(sort_transparent(s, side));
     }
     if (ws.work.tile_cycles) CU(cudaMemsetAsync(ws.work.tile_cycles, 0, n_lists * sizeof(uint32_t), side)); // debug taps are atomicMax'd
@@ -503,45 +588,44 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
         ev = s->kev;
         s->kev_recorded = true;
     }
-    if (ev) cudaEventRecord(ev[0], side);
-    launch_vertex(U, s->dev, ws.work, side);
-    if (ev) cudaEventRecord(ev[1], side);
-    launch_setup(U, s->dev, ws.work, side);
-    if (ev) cudaEventRecord(ev[2], side);
-    launch_clip(U, s->dev, ws.work, side);
-    if (ev) cudaEventRecord(ev[3], side);
-    launch_bin_count(U, ws.work, side);
-    if (ev) cudaEventRecord(ev[4], side);
-    launch_alloc(U, ws.work, side);
-    CU(cudaEventRecord(ws.alloc_done, side));
-    if (ev) cudaEventRecord(ev[5], side);
-    launch_bin_fill(U, ws.work, side);
-    if (ev) cudaEventRecord(ev[6], side);
-    launch_raster(U, ws.work, side);
-    if (ev) cudaEventRecord(ev[7], side);
-    CU(cudaEventRecord(ws.geo_done, side));
-    // Canvas stream: the tile kernel (the only stage that touches the canvas), then the frame's counters.
-    // The empty tiles are cleared on the canvas' auxiliary stream as soon as k_alloc has listed them: the
-    // stores stream to HBM under the rest of the geometry chain and under k_tile's dense tiles (disjoint
-    // pixels), and the canvas stream joins them before anything after k_tile can look at the frame.
-    cudaStream_t st = c->stream;
-    if (!c->aux_stream) CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
-    if (!c->ev_begin) CU(cudaEventCreateWithFlags(&c->ev_begin, cudaEventDisableTiming));
-    if (!c->ev_clear) CU(cudaEventCreateWithFlags(&c->ev_clear, cudaEventDisableTiming));
-    CU(cudaEventRecord(c->ev_begin, st)); // whatever still reads or writes the canvas on its stream comes first
-    CU(cudaStreamWaitEvent(c->aux_stream, c->ev_begin, 0));
-    CU(cudaStreamWaitEvent(c->aux_stream, ws.alloc_done, 0));
-    if (ev) cudaEventRecord(ev[N_FRAME_KERNELS - 1], c->aux_stream);
-    launch_clear_empty(U, ws.work, c->color(), c->depth(), c->aux_stream);
-    if (ev) cudaEventRecord(ev[N_FRAME_KERNELS], c->aux_stream);
-    CU(cudaEventRecord(c->ev_clear, c->aux_stream));
-    CU(cudaStreamWaitEvent(st, ws.geo_done, 0));
-    if (ev) cudaEventRecord(ev[N_FRAME_KERNELS + 1], st);
-    launch_tile(U, s->dev, ws.work, c->color(), c->depth(), st);
-    if (ev) cudaEventRecord(ev[N_FRAME_KERNELS + 2], st);
-    CU(cudaStreamWaitEvent(st, c->ev_clear, 0));
-    CU(cudaEventRecord(ws.tile_done, st));
-    ws.tile_pending = true;
+    // A frame's launches do not change from frame to frame (the uniforms are read from device memory), so
+    // they are captured once per work set as a CUDA graph and replayed: one launch call instead of nine
+    // kernels, six events and a copy.  Measurement taps, the debug taps and scenes whose painter sort
+    // uploads indices between frames use the direct path.
+    const bool use_graph = g_cfg.graphs && !ev && !ws.work.tile_cycles && s->dev.n_transparent == 0;
+    if (use_graph) {
+        GraphKey key{};
+        key.scene = s->dev;
+        key.work = ws.work;
+        key.n_coarse = U.n_coarse; key.n_lists = U.n_lists; key.tiles_x = U.tiles_x;
+        key.tile_y_begin = U.tile_y_begin; key.tile_y_end = U.tile_y_end; key.clear_ctas = g_clear_ctas + 65536u * g_tile_ctas;
+        if (!ws.graph_exec || std::memcmp(&key, &ws.graph_key, sizeof key) != 0) {
+            if (ws.graph_exec) CU(cudaGraphExecDestroy(ws.graph_exec));
+            ws.graph_exec = nullptr;
+            const int pdl_saved = g_pdl_enabled;
+            g_pdl_enabled = 0; // plain kernel nodes: the graph already removes the launch gaps
+            CU(cudaStreamBeginCapture(side, cudaStreamCaptureModeThreadLocal));
+            const int rc = launch_frame(s, ws, U, side, nullptr, true);
+            cudaGraph_t graph = nullptr;
+            const cudaError_t e = cudaStreamEndCapture(side, &graph);
+            g_pdl_enabled = pdl_saved;
+            if (rc != DRAW_OK) {
+                if (graph) cudaGraphDestroy(graph);
+                return rc;
+            }
+            CU(e);
+            const cudaError_t ei = cudaGraphInstantiate(&ws.graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            CU(ei);
+            ws.graph_key = key;
+        }
+        CU(cudaGraphLaunch(ws.graph_exec, side));
+    } else {
+        TRY(launch_frame(s, ws, U, side, ev, false));
+    }
+    CU(cudaEventRecord(ws.frame_done, side));
+    ws.frame_pending = true;
+    CU(cudaStreamWaitEvent(st, ws.frame_done, 0));
     s->launches += 5 + (s->dev.n_triangles ? 2 : 0) + (U.tile_y_end > U.tile_y_begin ? 2 : 0);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_status, ws.work.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -644,7 +728,7 @@ int draw_scene_create(size_t width, size_t height, draw_scene **out) {
     s->device = dev;
     s->width = width;
     s->height = height;
-    s->n_sets = std::min(std::max(env_int("DRAW_B200_SETS", 4), 1), (int)draw_scene::MAX_WORK_SETS);
+    s->n_sets = g_cfg.sets;
     // Scene::new, scene/mod.rs:760-786
     const f3 pos{0.0f, 0.0f, 150.0f};
     const f3 dir = scale(pos, -1.0f);
@@ -672,12 +756,18 @@ void draw_scene_destroy(draw_scene *scene) {
         for (draw_scene::WorkSet &ws : scene->sets) {
             if (ws.alloc_done) cudaEventDestroy(ws.alloc_done);
             if (ws.geo_done) cudaEventDestroy(ws.geo_done);
-            if (ws.tile_done) cudaEventDestroy(ws.tile_done);
         }
         for (int i = 0; i < N_FRAME_KERNELS + 3; i++)
             if (scene->kev[i]) cudaEventDestroy(scene->kev[i]);
-        for (draw_scene::WorkSet &ws : scene->sets)
+        for (draw_scene::WorkSet &ws : scene->sets) {
+            if (ws.graph_exec) cudaGraphExecDestroy(ws.graph_exec);
             if (ws.stream) cudaStreamDestroy(ws.stream);
+            if (ws.aux_stream) cudaStreamDestroy(ws.aux_stream);
+            if (ws.h_uniforms) cudaFreeHost(ws.h_uniforms);
+            if (ws.canvas_ready) cudaEventDestroy(ws.canvas_ready);
+            if (ws.clear_done) cudaEventDestroy(ws.clear_done);
+            if (ws.frame_done) cudaEventDestroy(ws.frame_done);
+        }
     }
     delete scene;
 }
@@ -967,12 +1057,6 @@ void draw_canvas_destroy(draw_canvas *canvas) {
     if (cudaGetDevice(&cur) == cudaSuccess) {
         if (cur != canvas->device) cudaSetDevice(canvas->device);
         if (canvas->stream) cudaStreamSynchronize(canvas->stream);
-        if (canvas->aux_stream) {
-            cudaStreamSynchronize(canvas->aux_stream);
-            cudaStreamDestroy(canvas->aux_stream);
-        }
-        if (canvas->ev_begin) cudaEventDestroy(canvas->ev_begin);
-        if (canvas->ev_clear) cudaEventDestroy(canvas->ev_clear);
         if (canvas->own_stream) cudaStreamDestroy(canvas->own_stream);
         if (canvas->h_color) cudaFreeHost(canvas->h_color);
         if (canvas->h_status) cudaFreeHost(canvas->h_status);

@@ -1,1 +1,2 @@
-for n in 592 296 148 74 37; do echo "clear_ctas=$n"; DRAW_B200_CLEAR_CTAS=$n DRAW_B200_LIB=/root/repo/draw_b200/libdraw_b200_tap3.so python tools/list_stats.py c3 2>&1 | cut -c1-300 | head -1; DRAW_B200_CLEAR_CTAS=$n tools/ab_quick.sh c3 -- "" | grep fps; done
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for n in 296 222 148; do for sets in 4 6; do echo "tile_ctas=$n sets=$sets"; DRAW_B200_TILE_CTAS=$n DRAW_B200_SETS=$sets tools/ab_quick.sh c3 c2 c4 -- "" | grep fps | cut -c1-70; done; done
