@@ -328,6 +328,7 @@ def run_ours(args, cfg):
     per_step = []
     for k in range(min(args.steps, 30)):
         flush.fill_(float(k))
+        torch.cuda.synchronize()  # the frame's geometry runs on the scene's own streams: start it on an idle GPU
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
         frame(k, ring[0])
@@ -337,30 +338,32 @@ def run_ours(args, cfg):
     del flush
 
     # ---- e2e: public API, host in / host out ----------------------------------------------------
-    # Two canvases on their own streams, double-buffered: frame k renders while frame k-1 is copied
-    # to pinned host memory.  Every frame is read back in full; nothing is skipped.
+    # Three canvases on their own streams with the host mirror enabled: every render is followed by the
+    # copy of its frame to pinned host memory, frame k renders while frames k-1 / k-2 are on the PCIe
+    # link.  Every frame is read back in full and looked at on the host; nothing is skipped.
+    N_E2E = 3
     pair = []
-    for _ in range(2):
+    for _ in range(N_E2E):
         c = draw_b200.Canvas(W, H)
         c.init_depth(DEPTH_MAX)
         c.apply_offset(0, 0)
+        c.enable_host_mirror(True)
         pair.append(c)
-    for k in range(4):
-        frame(k, pair[k % 2])
-        pair[k % 2].as_bytes_slice(copy=False)
+    for k in range(2 * N_E2E):
+        frame(k, pair[k % N_E2E])
+        pair[k % N_E2E].as_bytes_slice(copy=False)
     barrier()
     t0 = time.perf_counter()
-    checksum, prev = 0, None
-    for k in range(args.steps):
-        cur = pair[k % 2]
-        if cams is None:  # the per-step host input: the camera (scene.camera = Camera::new(...))
-            scene.camera = draw_b200.Camera.new([0.0, 0.0, 150.0], [0.0, 0.0, -150.0])
-        frame(k, cur)
-        if prev is not None:
-            host = prev.as_bytes_slice(copy=False)
+    checksum = 0
+    for k in range(args.steps + N_E2E - 1):
+        if k >= N_E2E - 1:  # the oldest frame in flight: wait for it and look at it on the host
+            host = pair[(k - (N_E2E - 1)) % N_E2E].as_bytes_slice(copy=False)
             checksum ^= int(host[H // 2, W // 2, 0])
-        prev = cur
-    host = prev.as_bytes_slice(copy=False)
+        if k < args.steps:
+            if cams is None:  # the per-step host input: the camera (scene.camera = Camera::new(...))
+                scene.camera = draw_b200.Camera.new([0.0, 0.0, 150.0], [0.0, 0.0, -150.0])
+            frame(k, pair[k % N_E2E])
+    host = pair[(args.steps - 1) % N_E2E].as_bytes_slice(copy=False)
     checksum ^= int(host[H // 2, W // 2, 0])
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -378,8 +381,16 @@ def run_ours(args, cfg):
 
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
+        # Two kernels write the frame: k_clear_empty the tiles nothing was binned to, k_tile (the longest
+        # kernel of the frame: `roofline`) the others.  Algorithmic bytes of a launch = 8 B per pixel of the
+        # tiles it writes (colour + depth, once) + for k_tile the bound textures (read at most once).
+        st = ring[0].last_frame_stats()
+        tile_px = draw_b200.tile_size() * 64
+        clear_bytes = min(8 * W * H, 8 * tile_px * st["empty_tiles"])  # border tiles counted whole: slight over-count
+        tile_bytes = 8 * W * H - clear_bytes + cfg["tex_bytes"]
         t_tile = kmean["k_tile"] * 1e-3
-        achieved = cfg["algo_bytes_tile_kernel"] / t_tile / 1e9
+        achieved = tile_bytes / t_tile / 1e9
+        clear_gbs = clear_bytes / (kmean["k_clear_empty"] * 1e-3) / 1e9
         frame_gbs = cfg["algo_bytes_frame"] / (ms_total * 1e-3 / args.steps) / 1e9
         line = {
             "metric": "frames/s at 3840x2160 (Phong+texture)", "value": fps, "unit": "frames/s",
@@ -392,18 +403,26 @@ def run_ours(args, cfg):
                        "l2": f"ring of {n_ring} canvases x {8 * W * H / 1e6:.0f} MB (colour+depth) = "
                              f"{n_ring * 8 * W * H / 1e6:.0f} MB > 126 MB L2, rotated every step",
                        "ms_per_step_l2_flushed": float(np.median(per_step)),
-                       "l2_flushed_protocol": "256 MB fill between steps, CUDA events per step, median"},
+                       "l2_flushed_protocol": "one frame at a time: 256 MB fill, device idle, CUDA events around the frame, median"},
             "clocks": clocks,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 220,
                     "d2h_bytes_per_step": 4 * W * H + 12,
-                    "note": "per step: camera set on host, Scene::render, Canvas::as_bytes_slice into pinned host memory, double-buffered over two canvases (frame k renders while frame k-1 is copied); "
+                    "note": "per step: camera set on host, Scene::render, Canvas::as_bytes_slice of the frame in pinned host memory; three canvases in flight with the host mirror enabled (the copy of a frame follows its render on the canvas stream, frame k renders while frames k-1 / k-2 cross PCIe); "
                             "host memory; geometry is uploaded once by add_obj like the reference's Scene owns "
                             "its objects"},
             "gpu_launches": launches,
             "kernel_ms": kmean,
             "roofline": {"bound": "hbm", "kernel": "k_tile", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic("k_tile", args.config), "peak_source": peak_src,
-                         "algo_bytes_per_launch": cfg["algo_bytes_tile_kernel"],
+                         "algo_bytes_per_launch": tile_bytes,
+                         "note": "k_tile is the longest kernel of the frame; it writes the non-empty tiles (8 B/pixel) and "
+                                 "reads the bound textures. k_clear_empty (under `clear`) writes the empty tiles and is the "
+                                 "frame's HBM-heavy kernel; a write-only stream reaches about half of the copy peak on "
+                                 "this part (a 66 MB device fill measures 3.1 TB/s). `frame_*` = SURVEY.md 8(d) "
+                                 "ALGO_BYTES(frame) / time per frame of the timed region",
+                         "clear": {"kernel": "k_clear_empty", "achieved": clear_gbs, "frac": clear_gbs / peak,
+                                   "algo_bytes_per_launch": clear_bytes, "empty_tiles": st["empty_tiles"],
+                                   "traffic": ncu_traffic("k_clear_empty", args.config)},
                          "frame_algo_bytes": cfg["algo_bytes_frame"], "frame_achieved": frame_gbs,
                          "frame_frac": frame_gbs / peak},
         }

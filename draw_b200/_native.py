@@ -43,11 +43,12 @@ class ObjectDesc(C.Structure):
 
 class FrameStats(C.Structure):
     _fields_ = [("input_triangles", C.c_uint32), ("setup_records", C.c_uint32), ("tile_refs", C.c_uint32),
-                ("transparent_slots", C.c_uint32), ("overflow", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+                ("transparent_slots", C.c_uint32), ("overflow", C.c_uint32), ("empty_tiles", C.c_uint32),
+                ("key_pages", C.c_uint32), ("reserved", C.c_uint32 * 1)]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n in ("input_triangles", "setup_records", "tile_refs",
-                                                   "transparent_slots", "overflow")}
+                                                   "transparent_slots", "overflow", "empty_tiles", "key_pages")}
 
 
 IMAGE_LOADER = C.CFUNCTYPE(C.c_int, C.c_char_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32),
@@ -87,6 +88,7 @@ SIGNATURES = {
     "draw_canvas_disable_depth_update": (C.c_int, [C.c_void_p]),
     "draw_canvas_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "draw_canvas_map_host": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "draw_canvas_enable_host_mirror": (C.c_int, [C.c_void_p, C.c_int]),
     "draw_canvas_read_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "draw_canvas_sync": (C.c_int, [C.c_void_p]),
     "draw_canvas_last_frame_stats": (C.c_int, [C.c_void_p, C.POINTER(FrameStats)]),

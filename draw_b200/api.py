@@ -116,6 +116,11 @@ class Canvas:
         a = np.frombuffer(buf, dtype=np.uint8).reshape(self.height, self.width, 4)
         return a.copy() if copy else a
 
+    def enable_host_mirror(self, enabled=True):
+        """Every render also copies the frame to the pinned host mirror (the reference's frame lives in
+        host memory); as_bytes_slice then only waits."""
+        N.check(N.lib().draw_canvas_enable_host_mirror(self._h, 1 if enabled else 0))
+
     def depth(self):
         """float32 [H, W]; row = canvas y, not flipped (get_pixel_depth, canvas.rs:413)."""
         out = np.empty((self.height, self.width), np.float32)
@@ -245,14 +250,14 @@ class Scene:
         N.check(N.lib().draw_scene_read_vertex_visual(self._h, canvas._h, first, count, out.ctypes.data))
         return out
 
-    KERNELS = ("k_vertex", "k_setup", "k_clip", "k_bin_count", "k_alloc", "k_bin_fill", "k_raster", "k_clear_empty", "k_tile")
+    KERNELS = ("k_vertex", "k_setup", "k_clip", "k_bin_count", "k_alloc", "k_bin_fill", "k_raster", "k_clear_empty", "k_tile", "k_shade")
 
     def set_kernel_timing(self, enabled):
         N.check(N.lib().draw_scene_set_kernel_timing(self._h, 1 if enabled else 0))
 
     def last_kernel_times(self, canvas):
         """Device time (ms) of each kernel of the last frame, keyed by kernel name."""
-        ms = (C.c_float * 9)()
+        ms = (C.c_float * 10)()
         N.check(N.lib().draw_scene_last_kernel_times(self._h, canvas._h, ms))
         return dict(zip(self.KERNELS, (float(x) for x in ms)))
 

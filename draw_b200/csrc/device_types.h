@@ -41,7 +41,7 @@ constexpr int REGION_H = 8 * BLK_H;
 // k_tile work items, built by k_alloc (heaviest first).  An item is a tile plus a pixel window of it in
 // units of warp regions (a 4x4 grid of REGION x REGION_H rectangles): the whole tile, or one of the
 // 2 / 4 / 8 / 16 windows a dense tile is cut into.
-//   bits 0-9 tile x | 10-20 tile y | 21-22 window x0 | 23-24 window y0 | 25-26 window w-1 | 27-28 window h-1
+//   bits 0-9 tile x | 10-20 tile y | 21-22 window x0 | 23-24 window y0 | 25-26 window w-1 | 27-28 window h-1 | 29 ITEM_DEFER
 // Tiles with nothing binned to them are not items: they are listed in FrameDev::empty_tiles (as
 // x | y << 10, count in counters[13]) and written by k_clear_empty.
 constexpr int REGIONS_X = TILE_W / REGION, REGIONS_Y = TILE_H / REGION_H;
@@ -60,6 +60,7 @@ constexpr int TILE_EXTRA_ITEMS = 1024;                        // work-list slots
 #endif
 constexpr int TILE_SPLIT_DIV = DRAW_TILE_SPLIT_DIV;           // a window should cost about total / this (<= TILE_EXTRA_ITEMS)
 constexpr uint32_t ITEM_NONE = 0xFFFFFFFFu;
+constexpr uint32_t ITEM_DEFER = 1u << 29; // k_tile only adds the large triangles to the tile's key page; k_shade shades it
 constexpr int N_COUNTERS = 64, ITEM_CURSOR = 32; // FrameDev::counters; k_tile's item cursor sits in the second 128-byte line
 constexpr uint32_t MAX_TILES_X = 1u << 10, MAX_TILES_Y = 1u << 11;
 #if defined(__CUDACC__)
@@ -87,6 +88,7 @@ struct FrameUniforms {
     uint32_t n_coarse;                 // tiles_x * tiles_y
     uint32_t n_lists;                  // LISTS_PER_TILE * n_coarse: large, medium, small lists
     uint32_t split_min_cost, split_div, split_max; // k_alloc's tile splitting policy (defaults: TILE_SPLIT_*)
+    uint32_t defer_max;                // tiles with a key page and fewer large references than this are shaded by k_shade
     uint8_t *color;                    // the canvas: BGRA8, row 0 = top (canvas.rs:955-956)
     float *depth;                      // depth buffer, row 0 = y 0 (canvas.rs:413-423)
     uint32_t has_transparent;          // transparent triangles are not binned: no tile may take the empty-tile path
@@ -115,7 +117,7 @@ struct SceneDev {
     const uint32_t *tri_tslot;       // transparent triangles: ordinal among them; else unused (may be null)
     const MaterialDev *materials;
     const uint8_t *texels;
-    uint32_t n_vertices, n_triangles, n_transparent;
+    uint32_t n_vertices, n_triangles, n_transparent, n_materials;
 };
 
 // What the tile kernel needs to rasterise one screen triangle (48 B).
@@ -176,9 +178,10 @@ struct FrameDev {
                                    // fills them with atomicMin, k_tile consumes and resets them [page_cap pages]
     uint32_t page_cap;
     uint32_t *counters;         // [0] records  [1] refs  [2] overflow bits  [3] k_setup CTA ticket  [4] k_alloc CTAs done  [5] clip queue length
-                                // [6] total tile cost  [8..10] large / medium / small references  [11] key pages handed out  [13] empty tiles  [32] k_tile item cursor  [N_COUNTERS]
+                                // [6] total tile cost  [8..10] large / medium / small references  [11] key pages handed out  [13] empty tiles  [14] tiles for k_shade  [32] k_tile item cursor  [N_COUNTERS]
     uint32_t *tile_cost;        // estimated k_tile work per tile [n_coarse]
     uint32_t *tile_order;       // k_tile work items (make_item), heaviest first, padded with ITEM_NONE [n_coarse + TILE_EXTRA_ITEMS]
+    uint32_t *shade_tiles;      // tiles k_shade resolves from their key page, as x | y << 10 (count in counters[14]) [n_coarse]
     uint32_t *empty_tiles;      // tiles with empty lists as x | y << 10 [n_coarse]
     unsigned long long *scan_desc; // k_setup chained-scan descriptors [ceil(n_triangles / 256)]
     uint2 *clip_queue;          // (triangle, first reserved slot | NO_SLOT) of triangles to clip [n_triangles]
@@ -188,6 +191,6 @@ struct FrameDev {
 
 enum : uint32_t { OVERFLOW_RECORDS = 1u, OVERFLOW_REFS = 2u };
 
-constexpr int N_FRAME_KERNELS = 9; // k_vertex k_setup k_clip k_bin<count> k_alloc k_bin<fill> k_raster k_clear_empty k_tile
+constexpr int N_FRAME_KERNELS = 10; // k_vertex k_setup k_clip k_bin<count> k_alloc k_bin<fill> k_raster k_clear_empty k_tile k_shade
 
 } // namespace drawb200

@@ -192,6 +192,9 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const FrameUniforms *__rest
 // ------------------------------------------------------------------------------------------
 constexpr int ALLOC_THREADS = 256;
 constexpr uint32_t COST_NOT_IN_STRIPE = 0xFFFFFFFFu;
+// tile_cost after k_alloc's first part: cost in the low 28 bits, what k_tile does with the tile above them
+constexpr uint32_t TILE_KIND_SHIFT = 28, TILE_KIND_SHIFTED = 1u << TILE_KIND_SHIFT;
+constexpr uint32_t TILE_KIND_FULL = 0, TILE_KIND_DEFER = 1, TILE_KIND_RASTER_ONLY = 2, TILE_KIND_EMPTY = 3;
 constexpr int COST_BUCKETS = 34;
 
 __device__ __forceinline__ int cost_bucket(uint32_t cost) { // 0 = heaviest ... COST_BUCKETS-1 = empty tile
@@ -226,9 +229,19 @@ __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const FrameUniforms *__
         page = atomicAdd(&W.counters[11], 1u);
         if (page >= W.page_cap) page = NO_PAGE;
     }
-    // estimated k_tile work, summed per class by k_bin<count> (COST_* above)
-    uint32_t cost = 0;
-    if (in_stripe && c > 0) cost = COST_TILE_BASE + W.tile_cost[tile] + (page == NO_PAGE ? W.tile_cost[nc + tile] : 0u);
+    // What k_tile has to do for the tile (TILE_KIND_*), and its estimated cost, summed per class by
+    // k_bin<count> (COST_* above).  A tile with a key page and few large triangles is resolved by k_shade,
+    // one thread per pixel: k_tile then only adds its large triangles to the page (nothing at all if there
+    // are none), which keeps the serial per-tile work — and the longest item — short.
+    uint32_t cost = 0, kind = TILE_KIND_EMPTY;
+    if (in_stripe && c > 0) {
+        const bool defer = page != NO_PAGE && U.has_transparent == 0 && c0 < U.defer_max;
+        kind = defer ? (c0 == 0 ? TILE_KIND_RASTER_ONLY : TILE_KIND_DEFER) : TILE_KIND_FULL;
+        if (kind != TILE_KIND_RASTER_ONLY)
+            cost = COST_TILE_BASE + W.tile_cost[tile] + (page == NO_PAGE ? W.tile_cost[nc + tile] : 0u);
+        if (cost >= TILE_KIND_SHIFTED) cost = TILE_KIND_SHIFTED - 1u;
+        if (defer) W.shade_tiles[atomicAdd(&W.counters[14], 1u)] = (tile % U.tiles_x) | ty << 10;
+    }
 
     // exclusive prefixes of the three counts over the CTA, one range reservation per class
     uint32_t inc0 = c0, inc1 = c1, inc2 = c2, cost_sum = cost;
@@ -267,7 +280,7 @@ __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const FrameUniforms *__
         W.list_count[tile] = 0; // become the fill cursors
         W.list_count[nc + tile] = 0;
         W.list_count[2 * nc + tile] = 0;
-        W.tile_cost[tile] = in_stripe ? cost : COST_NOT_IN_STRIPE;
+        W.tile_cost[tile] = in_stripe ? (cost | kind << TILE_KIND_SHIFT) : COST_NOT_IN_STRIPE;
         W.tile_page[tile] = page;
     }
     // ---- the last CTA builds the work list -------------------------------------------------------
@@ -295,13 +308,15 @@ __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const FrameUniforms *__
 #pragma unroll
         for (int k = 0; k < BATCH; k++)
             if (cost_k[k] != COST_NOT_IN_STRIPE) {
-                if (cost_k[k] == 0 && list_empties) { // listed on its own: k_clear_empty writes it
+                const uint32_t kind = cost_k[k] >> TILE_KIND_SHIFT, cost = cost_k[k] & (TILE_KIND_SHIFTED - 1u);
+                if (kind == TILE_KIND_EMPTY && list_empties) { // listed on its own: k_clear_empty writes it
                     const uint32_t t = t0 + k * ALLOC_THREADS;
                     W.empty_tiles[atomicAdd(&n_empty, 1u)] = (t % U.tiles_x) | (t / U.tiles_x) << 10;
                     continue;
                 }
-                const uint32_t s = tile_splits(cost_k[k], target, max_split);
-                atomicAdd(&bucket_start[cost_bucket(cost_k[k] / s)], s);
+                if (kind == TILE_KIND_RASTER_ONLY) continue; // k_raster + k_shade do it all
+                const uint32_t s = tile_splits(cost, target, max_split);
+                atomicAdd(&bucket_start[cost_bucket(cost / s)], s);
             }
     }
     __syncthreads();
@@ -328,11 +343,14 @@ __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const FrameUniforms *__
         }
 #pragma unroll
         for (int k = 0; k < BATCH; k++)
-            if (cost_k[k] != COST_NOT_IN_STRIPE && !(cost_k[k] == 0 && list_empties)) {
-                const uint32_t t = t0 + k * ALLOC_THREADS, s = tile_splits(cost_k[k], target, max_split);
+            if (cost_k[k] != COST_NOT_IN_STRIPE) {
+                const uint32_t kind = cost_k[k] >> TILE_KIND_SHIFT, cost = cost_k[k] & (TILE_KIND_SHIFTED - 1u);
+                if ((kind == TILE_KIND_EMPTY && list_empties) || kind == TILE_KIND_RASTER_ONLY) continue;
+                const uint32_t t = t0 + k * ALLOC_THREADS, s = tile_splits(cost, target, max_split);
                 const uint32_t tx = t % U.tiles_x, tyy = t / U.tiles_x;
-                const uint32_t at = atomicAdd(&bucket_start[cost_bucket(cost_k[k] / s)], s);
-                for (uint32_t i = 0; i < s; i++) W.tile_order[at + i] = make_item(tx, tyy, s, i);
+                const uint32_t at = atomicAdd(&bucket_start[cost_bucket(cost / s)], s);
+                for (uint32_t i = 0; i < s; i++)
+                    W.tile_order[at + i] = make_item(tx, tyy, s, i) | (kind == TILE_KIND_DEFER ? ITEM_DEFER : 0u);
             }
     }
 }

@@ -137,7 +137,7 @@ __device__ __forceinline__ bool staged_may_cover(const float *s, uint32_t flags,
 __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUniforms &U, const SceneDev &S, const FrameDev &W,
                                           uint8_t *__restrict__ color, float *__restrict__ depth, const float *u8tab,
                                           const bool usable) {
-    __shared__ unsigned long long keys[TILE_PIXELS]; // (depth key, slot), later (depth bits, draw id)
+    __shared__ __align__(16) unsigned long long keys[TILE_PIXELS]; // (depth key, slot), later (depth bits, draw id)
     __shared__ uint32_t colour[TILE_PIXELS];         // r | g << 8 | b << 16 | pad << 24
     __shared__ float staged[CHUNK][STAGE_STRIDE];
     __shared__ uint32_t cand[CAND_CAP];
@@ -148,6 +148,7 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
 
     const uint32_t tile_x = item & (MAX_TILES_X - 1), tile_y = (item >> 10) & (MAX_TILES_Y - 1);
     const uint32_t tile = tile_y * U.tiles_x + tile_x;
+    const bool defer = (item & ITEM_DEFER) != 0; // only add the large triangles to the key page; k_shade does the rest
     const long long t_start = W.tile_cycles ? clock64() : 0;
     const int tx0 = (int)tile_x * TILE_W, ty0 = (int)tile_y * TILE_H;
 
@@ -231,6 +232,7 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
                     }
             }
             page_pending = false;
+            if (defer) return; // the page is rewritten below with the merged keys and emptied by k_shade
             // Leave the page empty for the next frame: after every lane of the warp has its keys (the loads
             // above are consumed), the warp's region — REGION_H rows of 128 bytes — is overwritten with whole
             // 128-byte lines, 8 lanes per row.
@@ -358,6 +360,18 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
     }
     __syncthreads();
 
+    if (defer) {
+        // the window's keys go back to the page, whole rows at a time (16 bytes per lane, consecutive lanes)
+        unsigned long long *pk = W.key_pages + (size_t)page * TILE_PIXELS;
+        const int row_pairs = ww / 2; // 16-byte key pairs per window row
+        for (int q = tid; q < row_pairs * wh; q += TILE_THREADS) {
+            const int lx = (wx0 - tx0) + 2 * (q % row_pairs), ly = (wy0 - ty0) + q / row_pairs;
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&keys[ly * TILE_W + lx]);
+            __stcg(reinterpret_cast<ulonglong2 *>(pk + ly * TILE_W + lx), v);
+        }
+        if (W.tile_cycles && tid == 0) atomicMax(&W.tile_cycles[tile], (uint32_t)(clock64() - t_start));
+        return;
+    }
 #ifndef DRAW_TAP_B
     if (W.tile_cycles && tid == 0) atomicMax(&W.tile_cycles[U.n_coarse + tile], (uint32_t)(clock64() - t_start)); // end of phase A
 #endif
@@ -575,7 +589,7 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
         const uint32_t slot = (uint32_t)keys[(y - ty0) * TILE_W + (x - tx0)];
         if (slot == NO_SLOT) continue;
         const char *sp = reinterpret_cast<const char *>(W.srec + slot);
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(rrec + slot));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(prep + slot));
         asm volatile("prefetch.global.L1 [%0];" ::"l"(sp));
         asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + sizeof(ShadeRec) - 16));
     }
@@ -588,10 +602,9 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
         float d = depth_max;
         uint32_t id = NO_SLOT;
         if (slot != NO_SLOT) {
-            const RasterRec r = load_raster(rrec + slot);
             float op;
-            c = shade_pixel(S.materials, S.texels, u8tab, r, W.srec + slot, (float)x, (float)y, &d, &op) | (255u << 24);
-            id = r.id;
+            c = shade_pixel_prep(S.materials, S.texels, u8tab, prep + slot, W.srec + slot, (float)x, (float)y, &d, &op, &id) |
+                (255u << 24);
         }
         colour[p] = c;
         keys[p] = ((unsigned long long)__float_as_uint(d) << 32) | id; // own pixel: no sync needed

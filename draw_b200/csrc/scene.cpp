@@ -36,6 +36,7 @@ void launch_raster(const FrameUniforms &U, const FrameUniforms *dU, const FrameD
 cudaError_t launch_fill_u64(unsigned long long *dst, size_t n, unsigned long long value, cudaStream_t stream);
 void launch_tile(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
 void launch_clear_empty(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream);
+void launch_shade(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
 cudaError_t launch_clear(uint8_t *color, float *depth, size_t n_pixels, float depth_max, cudaStream_t stream,
                          uint64_t *launches);
 cudaError_t launch_fill_u32(uint32_t *dst, size_t n, uint32_t value, cudaStream_t stream, uint64_t *launches);
@@ -157,7 +158,7 @@ struct draw_scene {
     // streams while k_tile of frame k still runs on its canvas' stream.
     struct WorkSet {
         DevBuf<float> vert[9];
-        DevBuf<uint32_t> flags, list_count, list_offset, refs, counters, tile_cycles, tile_cost, tile_order, empty_tiles;
+        DevBuf<uint32_t> flags, list_count, list_offset, refs, counters, tile_cycles, tile_cost, tile_order, empty_tiles, shade_tiles;
         DevBuf<unsigned long long> scan_desc;
         DevBuf<uint2> clip_queue;
         DevBuf<RasterRec> rrec, trrec;
@@ -190,7 +191,7 @@ struct draw_scene {
     // optional per-kernel timing (draw_scene_set_kernel_timing): 0..6 around the six side-stream kernels,
     // 7 / 8 around k_tile on the canvas stream
     bool kernel_timing = false;
-    cudaEvent_t kev[N_FRAME_KERNELS + 3] = {};
+    cudaEvent_t kev[N_FRAME_KERNELS + 4] = {};
     bool kev_recorded = false;
 };
 
@@ -208,6 +209,7 @@ struct draw_canvas {
     uint8_t *h_color = nullptr; // pinned mirror
     size_t h_color_cap = 0;
     bool host_dirty = true;
+    bool host_mirror = false;   // every render also refreshes the pinned mirror (draw_canvas_enable_host_mirror)
     cudaStream_t own_stream = nullptr, stream = nullptr;
     size_t stripe_y0 = 0, stripe_y1 = 0; // rows; y1 == 0 means whole canvas
     uint32_t *h_status = nullptr;        // pinned: counters of the last frame
@@ -238,6 +240,7 @@ struct Config {
     int tile_ctas = std::max(1, env_int("DRAW_B200_TILE_CTAS", 148 * (1024 / TILE_THREADS)));
     int split_min_cost = std::max(1, env_int("DRAW_B200_SPLIT_MIN_COST", TILE_SPLIT_MIN_COST));
     int split_div = std::min(std::max(1, env_int("DRAW_B200_SPLIT_DIV", TILE_SPLIT_DIV)), (int)TILE_EXTRA_ITEMS);
+    int defer_max = std::max(0, env_int("DRAW_B200_DEFER_MAX", 0));  // k_shade takes tiles with fewer large references (0: off)
     int split_max = std::min(std::max(1, env_int("DRAW_B200_SPLIT_MAX", TILE_MAX_SPLIT)), (int)TILE_MAX_SPLIT);
 };
 const Config g_cfg;
@@ -339,6 +342,7 @@ int upload_geometry(draw_scene *s) {
     d.n_vertices = (uint32_t)pos[0].size();
     d.n_triangles = (uint32_t)mat.size();
     d.n_transparent = n_transparent;
+    d.n_materials = (uint32_t)materials.size();
     s->geometry_dirty = false;
     return DRAW_OK;
 }
@@ -378,6 +382,7 @@ int ensure_work_buffers(draw_scene *s, draw_scene::WorkSet &ws, size_t n_lists) 
     TRY(ws.tile_cost.reserve(n_lists));
     TRY(ws.tile_order.reserve(n_lists + TILE_EXTRA_ITEMS));
     TRY(ws.empty_tiles.reserve(n_lists / LISTS_PER_TILE));
+    TRY(ws.shade_tiles.reserve(n_lists / LISTS_PER_TILE));
     TRY(ws.scan_desc.reserve((size_t)d.n_triangles / 256 + 2));
     TRY(ws.clip_queue.reserve(d.n_triangles));
     FrameDev &w = ws.work;
@@ -394,6 +399,7 @@ int ensure_work_buffers(draw_scene *s, draw_scene::WorkSet &ws, size_t n_lists) 
     w.tile_cost = ws.tile_cost.ptr;
     w.tile_order = ws.tile_order.ptr;
     w.empty_tiles = ws.empty_tiles.ptr;
+    w.shade_tiles = ws.shade_tiles.ptr;
     w.scan_desc = ws.scan_desc.ptr;
     w.clip_queue = ws.clip_queue.ptr;
     w.rec_cap = (uint32_t)s->rec_cap;
@@ -492,7 +498,20 @@ int launch_frame(draw_scene *s, draw_scene::WorkSet &ws, const FrameUniforms &U,
     if (ev) cudaEventRecord(ev[N_FRAME_KERNELS + 1], side);
     launch_tile(U, dU, s->dev, ws.work, side);
     if (ev) cudaEventRecord(ev[N_FRAME_KERNELS + 2], side);
+    launch_shade(U, dU, s->dev, ws.work, side);
+    if (ev) cudaEventRecord(ev[N_FRAME_KERNELS + 3], side);
     CU(cudaStreamWaitEvent(side, ws.clear_done, 0));
+    return DRAW_OK;
+}
+
+int ensure_host_mirror(draw_canvas *c, size_t bytes) {
+    if (c->h_color_cap >= bytes) return DRAW_OK;
+    if (c->h_color) cudaFreeHost(c->h_color);
+    c->h_color = nullptr;
+    c->h_color_cap = 0;
+    CU(cudaMallocHost(&c->h_color, bytes));
+    c->h_color_cap = bytes;
+    c->host_dirty = true;
     return DRAW_OK;
 }
 
@@ -544,6 +563,7 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     U.split_min_cost = (uint32_t)g_cfg.split_min_cost;
     U.split_div = (uint32_t)g_cfg.split_div;
     U.split_max = (uint32_t)g_cfg.split_max;
+    U.defer_max = (uint32_t)g_cfg.defer_max;
     const size_t y0 = c->stripe_y1 ? c->stripe_y0 : 0, y1 = c->stripe_y1 ? c->stripe_y1 : c->height;
     U.tile_y_begin = (uint32_t)(y0 / TILE_H);
     U.tile_y_end = (uint32_t)((y1 + TILE_H - 1) / TILE_H);
@@ -583,7 +603,7 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
 
     cudaEvent_t *ev = nullptr;
     if (s->kernel_timing) {
-        for (int i = 0; i < N_FRAME_KERNELS + 3; i++)
+        for (int i = 0; i < N_FRAME_KERNELS + 4; i++)
             if (!s->kev[i]) CU(cudaEventCreate(&s->kev[i]));
         ev = s->kev;
         s->kev_recorded = true;
@@ -626,12 +646,19 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     CU(cudaEventRecord(ws.frame_done, side));
     ws.frame_pending = true;
     CU(cudaStreamWaitEvent(st, ws.frame_done, 0));
-    s->launches += 5 + (s->dev.n_triangles ? 2 : 0) + (U.tile_y_end > U.tile_y_begin ? 2 : 0);
+    s->launches += 5 + (s->dev.n_triangles ? 2 : 0) + (U.tile_y_end > U.tile_y_begin ? (U.defer_max ? 3 : 2) : 0);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(c->h_status, ws.work.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_status, ws.work.counters, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     c->frame_pending = true;
     c->host_dirty = true;
     c->last_scene = s;
+    if (c->host_mirror && !c->ext_color) {
+        // the frame follows its render to the host without waiting for the host to ask (map_host then only waits)
+        const size_t bytes = c->width * c->height * 4;
+        TRY(ensure_host_mirror(c, bytes));
+        CU(cudaMemcpyAsync(c->h_color, c->color(), bytes, cudaMemcpyDeviceToHost, st));
+        c->host_dirty = false;
+    }
     return DRAW_OK;
 }
 
@@ -652,6 +679,8 @@ int finish_frame(draw_canvas *c) {
         const uint32_t n_rec = c->h_status[0], n_refs = c->h_status[1], overflow = c->h_status[2];
         c->stats.setup_records = n_rec;
         c->stats.tile_refs = n_refs;
+        c->stats.empty_tiles = c->h_status[13];
+        c->stats.key_pages = c->h_status[11];
         if (alive) {
             c->stats.input_triangles = s->dev.n_triangles;
             c->stats.transparent_slots = s->dev.n_transparent * 4;
@@ -757,7 +786,7 @@ void draw_scene_destroy(draw_scene *scene) {
             if (ws.alloc_done) cudaEventDestroy(ws.alloc_done);
             if (ws.geo_done) cudaEventDestroy(ws.geo_done);
         }
-        for (int i = 0; i < N_FRAME_KERNELS + 3; i++)
+        for (int i = 0; i < N_FRAME_KERNELS + 4; i++)
             if (scene->kev[i]) cudaEventDestroy(scene->kev[i]);
         for (draw_scene::WorkSet &ws : scene->sets) {
             if (ws.graph_exec) cudaGraphExecDestroy(ws.graph_exec);
@@ -977,14 +1006,15 @@ int draw_scene_set_kernel_timing(draw_scene *scene, int enabled) {
     return DRAW_OK;
 }
 
-int draw_scene_last_kernel_times(draw_scene *scene, draw_canvas *canvas, float ms[9]) {
+int draw_scene_last_kernel_times(draw_scene *scene, draw_canvas *canvas, float ms[10]) {
     GUARD_BEGIN
     if (!scene || !canvas || !ms) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!scene->kev_recorded) return fail(DRAW_ERR_INVALID_ARGUMENT, "kernel timing was not enabled for the last frame");
     TRY(finish_frame(canvas));
-    for (int i = 0; i < N_FRAME_KERNELS - 2; i++) CU(cudaEventElapsedTime(&ms[i], scene->kev[i], scene->kev[i + 1])); // side stream
-    CU(cudaEventElapsedTime(&ms[N_FRAME_KERNELS - 2], scene->kev[N_FRAME_KERNELS - 1], scene->kev[N_FRAME_KERNELS])); // k_clear_empty
-    CU(cudaEventElapsedTime(&ms[N_FRAME_KERNELS - 1], scene->kev[N_FRAME_KERNELS + 1], scene->kev[N_FRAME_KERNELS + 2])); // k_tile
+    for (int i = 0; i < 7; i++) CU(cudaEventElapsedTime(&ms[i], scene->kev[i], scene->kev[i + 1])); // k_vertex .. k_raster
+    CU(cudaEventElapsedTime(&ms[7], scene->kev[N_FRAME_KERNELS - 1], scene->kev[N_FRAME_KERNELS]));     // k_clear_empty (aux stream)
+    CU(cudaEventElapsedTime(&ms[8], scene->kev[N_FRAME_KERNELS + 1], scene->kev[N_FRAME_KERNELS + 2])); // k_tile
+    CU(cudaEventElapsedTime(&ms[9], scene->kev[N_FRAME_KERNELS + 2], scene->kev[N_FRAME_KERNELS + 3])); // k_shade
     return DRAW_OK;
     GUARD_END
 }
@@ -1039,9 +1069,9 @@ int draw_canvas_create(size_t width, size_t height, draw_canvas **out) {
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess)
         return cleanup(fail(DRAW_ERR_CUDA, "cudaStreamCreate failed"));
     c->stream = c->own_stream;
-    if (cudaMallocHost(&c->h_status, 4 * sizeof(uint32_t)) != cudaSuccess)
+    if (cudaMallocHost(&c->h_status, 16 * sizeof(uint32_t)) != cudaSuccess)
         return cleanup(fail(DRAW_ERR_OUT_OF_MEMORY, "cudaMallocHost failed"));
-    std::memset(c->h_status, 0, 4 * sizeof(uint32_t));
+    std::memset(c->h_status, 0, 16 * sizeof(uint32_t));
     int rc = c->d_color.reserve(width * height * 4);
     if (rc) return cleanup(rc);
     rc = fill_color_black(c, 0, width * height); // vec![Pixel::black(); len], canvas.rs:368
@@ -1147,14 +1177,7 @@ int draw_canvas_map_host(draw_canvas *canvas, const uint8_t **out_bytes, size_t 
     if (!canvas || !out_bytes) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
     TRY(finish_frame(canvas));
     const size_t bytes = canvas->width * canvas->height * 4;
-    if (canvas->h_color_cap < bytes) {
-        if (canvas->h_color) cudaFreeHost(canvas->h_color);
-        canvas->h_color = nullptr;
-        canvas->h_color_cap = 0;
-        CU(cudaMallocHost(&canvas->h_color, bytes));
-        canvas->h_color_cap = bytes;
-        canvas->host_dirty = true;
-    }
+    TRY(ensure_host_mirror(canvas, bytes));
     if (canvas->host_dirty) {
         CU(cudaMemcpyAsync(canvas->h_color, canvas->color(), bytes, cudaMemcpyDeviceToHost, canvas->stream));
         CU(cudaStreamSynchronize(canvas->stream));
@@ -1162,6 +1185,16 @@ int draw_canvas_map_host(draw_canvas *canvas, const uint8_t **out_bytes, size_t 
     }
     *out_bytes = canvas->h_color;
     if (out_len) *out_len = bytes;
+    return DRAW_OK;
+    GUARD_END
+}
+
+int draw_canvas_enable_host_mirror(draw_canvas *canvas, int enabled) {
+    GUARD_BEGIN
+    if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    TRY(ensure_device(canvas->device));
+    canvas->host_mirror = enabled != 0;
+    if (canvas->host_mirror) TRY(ensure_host_mirror(canvas, canvas->width * canvas->height * 4));
     return DRAW_OK;
     GUARD_END
 }

@@ -17,27 +17,24 @@ __device__ __forceinline__ void fill_u8_table(float *tab, int tid, int n_threads
 // into the map (SURVEY.md §8c deviation 6; never triggers for uv in [0,1]).
 __device__ __forceinline__ uint32_t fetch_texel(const uint8_t *__restrict__ texels, uint32_t off, uint32_t w, uint32_t h,
                                                 float u, float v) {
-    unsigned long long ui = sat_usize(floorf(FMUL(u, FSUB((float)w, 1.0f))));
-    unsigned long long vr = sat_usize(floorf(FMUL(v, FSUB((float)h, 1.0f))));
+    // Rust's `as usize` saturates and maps NaN to 0; so does cvt.rzi.u32, and whatever exceeds 2^32 - 1
+    // is clamped to the last texel below either way
+    uint32_t ui = __float2uint_rz(floorf(FMUL(u, FSUB((float)w, 1.0f))));
+    uint32_t vr = __float2uint_rz(floorf(FMUL(v, FSUB((float)h, 1.0f))));
     if (ui > w - 1) ui = w - 1;
     if (vr > h - 1) vr = h - 1;
-    const uint32_t *p = reinterpret_cast<const uint32_t *>(texels + off) + ((size_t)(h - 1 - (uint32_t)vr) * w + (uint32_t)ui);
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(texels + off) + ((size_t)(h - 1 - vr) * w + ui);
     return __ldg(p);
 }
 
-// canvas.rs:673-743 for one covered pixel: literal barycentrics, interpolation, texel fetches and
-// Phong.  Returns r | g << 8 | b << 16; *depth_out gets the interpolated depth.
-__device__ __forceinline__ uint32_t shade_pixel(const MaterialDev *__restrict__ materials,
-                                                const uint8_t *__restrict__ texels, const float *u8tab,
-                                                const RasterRec &r, const ShadeRec *__restrict__ sp, float x, float y,
-                                                float *depth_out, float *opacity_out) {
-    const Edge e_bc = make_edge(r.bx, r.by, r.cx, r.cy), e_ca = make_edge(r.cx, r.cy, r.ax, r.ay),
-               e_ab = make_edge(r.ax, r.ay, r.bx, r.by);
-    const float alpha = FDIV(edge_eval(e_bc, x, y), edge_eval(e_bc, r.ax, r.ay));
-    const float beta = FDIV(edge_eval(e_ca, x, y), edge_eval(e_ca, r.bx, r.by));
-    const float gama = FDIV(edge_eval(e_ab, x, y), edge_eval(e_ab, r.cx, r.cy));
-    *depth_out = FADD(FADD(FMUL(alpha, r.da), FMUL(beta, r.db)), FMUL(gama, r.dc));
-
+// canvas.rs:685-743 for one covered pixel whose barycentrics are known: interpolation, texel fetches
+// and Phong.  Returns r | g << 8 | b << 16.
+// MATERIALS_CACHED: `materials` is a copy of the table in shared memory (plain loads) instead of the
+// global table (read-only path).
+template <bool MATERIALS_CACHED = false>
+__device__ __forceinline__ uint32_t shade_bary(const MaterialDev *materials, const uint8_t *__restrict__ texels,
+                                               const float *u8tab, const ShadeRec *__restrict__ sp, float alpha, float beta,
+                                               float gama, float *opacity_out) {
     // ShadeRec as 9 x uint4: n[3][3] l[3][3] h[3][3] uv[3][2] material pad pad
     const uint4 *q = reinterpret_cast<const uint4 *>(sp);
     float w[36];
@@ -58,7 +55,8 @@ __device__ __forceinline__ uint32_t shade_pixel(const MaterialDev *__restrict__ 
 #undef INTERP
     // MaterialDev as 4 x uint4: ka3 kd1 | kd2 ks3 | alpha ka_off ka_w ka_h | kd_off kd_w kd_h pad
     const uint4 *mq = reinterpret_cast<const uint4 *>(materials + __float_as_uint(w[33]));
-    const uint4 m0 = __ldg(mq), m1 = __ldg(mq + 1), m2 = __ldg(mq + 2), m3 = __ldg(mq + 3);
+    const uint4 m0 = MATERIALS_CACHED ? mq[0] : __ldg(mq), m1 = MATERIALS_CACHED ? mq[1] : __ldg(mq + 1),
+                m2 = MATERIALS_CACHED ? mq[2] : __ldg(mq + 2), m3 = MATERIALS_CACHED ? mq[3] : __ldg(mq + 3);
     const v3 ka{__uint_as_float(m0.x), __uint_as_float(m0.y), __uint_as_float(m0.z)};
     const v3 kd{__uint_as_float(m0.w), __uint_as_float(m1.x), __uint_as_float(m1.y)};
     const v3 ks{__uint_as_float(m1.z), __uint_as_float(m1.w), __uint_as_float(m2.x)};
@@ -81,6 +79,49 @@ __device__ __forceinline__ uint32_t shade_pixel(const MaterialDev *__restrict__ 
     const float cb = FADD(FMUL(c_r.z, FADD(c_a.z, FMUL(ks.z, s))), FMUL(ks.z, spec));
     // Pixel::from_normalized_vec3, canvas.rs:89-92
     return sat_u8(FMUL(cr, 255.0f)) | (sat_u8(FMUL(cg, 255.0f)) << 8) | (sat_u8(FMUL(cb, 255.0f)) << 16);
+}
+
+// canvas.rs:673-682 from the raster record: literal barycentrics (edge functions rebuilt from the snapped
+// vertices) and the interpolated depth; then shade_bary.  Used where no prepared record exists (transparent
+// triangles).
+template <bool MATERIALS_CACHED = false>
+__device__ __forceinline__ uint32_t shade_pixel(const MaterialDev *materials, const uint8_t *__restrict__ texels,
+                                                const float *u8tab, const RasterRec &r, const ShadeRec *__restrict__ sp,
+                                                float x, float y, float *depth_out, float *opacity_out) {
+    const Edge e_bc = make_edge(r.bx, r.by, r.cx, r.cy), e_ca = make_edge(r.cx, r.cy, r.ax, r.ay),
+               e_ab = make_edge(r.ax, r.ay, r.bx, r.by);
+    const float alpha = FDIV(edge_eval(e_bc, x, y), edge_eval(e_bc, r.ax, r.ay));
+    const float beta = FDIV(edge_eval(e_ca, x, y), edge_eval(e_ca, r.bx, r.by));
+    const float gama = FDIV(edge_eval(e_ab, x, y), edge_eval(e_ab, r.cx, r.cy));
+    *depth_out = FADD(FADD(FMUL(alpha, r.da), FMUL(beta, r.db)), FMUL(gama, r.dc));
+    return shade_bary<MATERIALS_CACHED>(materials, texels, u8tab, sp, alpha, beta, gama, opacity_out);
+}
+
+// The same from the prepared record (opaque triangles): its edge functions are the raster record's, sign-
+// normalised together with f (the quotients are bit-identical, device_math.cuh), and under TRI_FASTDIV the
+// division is exact_div.  ~55 instructions fewer per pixel than rebuilding the edges.  *id_out = draw id.
+template <bool MATERIALS_CACHED = false>
+__device__ __forceinline__ uint32_t shade_pixel_prep(const MaterialDev *materials, const uint8_t *__restrict__ texels,
+                                                     const float *u8tab, const PrepRec *__restrict__ pp,
+                                                     const ShadeRec *__restrict__ sp, float x, float y, float *depth_out,
+                                                     float *opacity_out, uint32_t *id_out) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(pp);
+    const uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4), q6 = __ldg(q + 6);
+    const float ecx[3] = {__uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z)};
+    const float ecy[3] = {__uint_as_float(q0.w), __uint_as_float(q1.x), __uint_as_float(q1.y)};
+    const float ek1[3] = {__uint_as_float(q1.z), __uint_as_float(q1.w), __uint_as_float(q2.x)};
+    const float ek2[3] = {__uint_as_float(q2.y), __uint_as_float(q2.z), __uint_as_float(q2.w)};
+    const float f[3] = {__uint_as_float(q3.x), __uint_as_float(q3.y), __uint_as_float(q3.z)};
+    const float rf[3] = {__uint_as_float(q3.w), __uint_as_float(q4.x), __uint_as_float(q4.y)};
+    float bary[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float e = FSUB(FADD(FADD(FMUL(ecx[i], x), FMUL(ecy[i], y)), ek1[i]), ek2[i]);
+        bary[i] = (q6.y & TRI_FASTDIV) ? exact_div(e, f[i], rf[i]) : FDIV(e, f[i]);
+    }
+    *depth_out = FADD(FADD(FMUL(bary[0], __uint_as_float(q4.z)), FMUL(bary[1], __uint_as_float(q4.w))), FMUL(bary[2], __uint_as_float(q6.x)));
+    *id_out = q6.z;
+    return shade_bary<MATERIALS_CACHED>(materials, texels, u8tab, sp, bary[0], bary[1], bary[2], opacity_out);
 }
 
 // Pixel * f32 + Pixel * f32 (canvas.rs:136-169, :916-921): per channel truncate, u8 wrapping add, pad 0.

@@ -97,7 +97,9 @@ typedef struct draw_frame_stats {
     uint32_t tile_refs;         /* (tile, triangle) pairs produced by binning */
     uint32_t transparent_slots; /* slots scanned by the ordered transparent pass */
     uint32_t overflow;          /* non-zero: a device buffer was too small, frame was re-rendered */
-    uint32_t reserved[3];
+    uint32_t empty_tiles;       /* tiles of the stripe nothing was binned to (written by k_clear_empty) */
+    uint32_t key_pages;         /* tiles whose medium / small triangles k_raster rasterised into a key page */
+    uint32_t reserved[1];
 } draw_frame_stats;
 
 /* ---- library ------------------------------------------------------------------------ */
@@ -143,9 +145,9 @@ int draw_scene_launch_count(const draw_scene *scene, uint64_t *out);
 
 /* Measurement tap: when enabled, every frame records CUDA events between its kernels on the
  * canvas' stream; last_kernel_times waits for the frame and returns the device time in ms of
- * k_vertex, k_setup, k_clip, k_bin<count>, k_alloc, k_bin<fill>, k_raster, k_clear_empty, k_tile (DESIGN.md describes them). */
+ * k_vertex, k_setup, k_clip, k_bin<count>, k_alloc, k_bin<fill>, k_raster, k_clear_empty, k_tile, k_shade (DESIGN.md describes them). */
 int draw_scene_set_kernel_timing(draw_scene *scene, int enabled);
-int draw_scene_last_kernel_times(draw_scene *scene, draw_canvas *canvas, float ms[9]);
+int draw_scene_last_kernel_times(draw_scene *scene, draw_canvas *canvas, float ms[10]);
 
 /* Debug tap: sizes of the last frame's tile lists (coarse tiles first, then fine tiles, see
  * DESIGN.md).  out == NULL only returns the number of coarse tiles. */
@@ -170,6 +172,11 @@ int draw_canvas_size(const draw_canvas *canvas, size_t *width, size_t *height);
  * pinned host mirror if it changed, and returns that mirror: width*height*4 bytes, B,G,R,pad
  * per pixel, row 0 = top.  Valid until the next render / resize / destroy on this canvas. */
 int draw_canvas_map_host(draw_canvas *canvas, const uint8_t **out_bytes, size_t *out_len);
+/* The reference's frame always lives in host memory (Canvas::frame, canvas.rs:353).  With the host
+ * mirror enabled every draw_scene_render also enqueues the device-to-host copy of the frame behind
+ * its kernels, so the PCIe transfer of frame k overlaps the rendering of frame k+1 on another canvas
+ * and draw_canvas_map_host only waits.  Off by default (the copy costs 4*W*H bytes of PCIe per frame). */
+int draw_canvas_enable_host_mirror(draw_canvas *canvas, int enabled);
 /* depth_frame (get_pixel_depth :413): width*height floats, row index = canvas y (not flipped). */
 int draw_canvas_read_depth(draw_canvas *canvas, float *dst, size_t n_floats);
 /* Wait for everything enqueued on the canvas' stream. */
