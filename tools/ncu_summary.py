@@ -28,7 +28,14 @@ def launches(path):
 def kernel(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    h, units, vals = rows[0], rows[1], rows[2]
+    h, units = rows[0], rows[1]
+    for vals in rows[2:]:
+        if len(vals) == len(h):
+            kernel_row(h, units, vals)
+            print()
+
+
+def kernel_row(h, units, vals):
     want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
             "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__cycles_active.avg", "sm__cycles_elapsed.max",
