@@ -312,6 +312,15 @@ def run_ours(args, cfg):
     frames_total = args.steps * world
     fps = frames_total / (ms_total * 1e-3)
 
+    if args.quick:  # A/B runs: the timed region only
+        if rank == 0:
+            print(json.dumps({"quick": True, "config": args.config, "value": fps, "us_per_step": 1e3 * ms_total / args.steps,
+                              "gpu_launches": launches, "clocks": clocks}), flush=True)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
     # ---- per-kernel times (separate pass, same workload, events around each kernel) -----------
     scene.set_kernel_timing(True)
     ktimes = {k: [] for k in scene.KERNELS}
@@ -444,6 +453,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true", help="A/B runs: time the K steps and print a short line (no e2e, no per-kernel pass)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfg = load_workload(args.config)

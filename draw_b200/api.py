@@ -78,7 +78,7 @@ class Canvas:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and N is not None:  # module globals are torn down at interpreter exit
             N.lib().draw_canvas_destroy(h)
 
     def init_depth(self, depth=DEPTH_MAX_DEFAULT):
@@ -173,7 +173,7 @@ class Scene:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and N is not None:
             N.lib().draw_scene_destroy(h)
 
     @property

@@ -93,6 +93,8 @@ struct FrameUniforms {
     float *depth;                      // depth buffer, row 0 = y 0 (canvas.rs:413-423)
     uint32_t has_transparent;          // transparent triangles are not binned: no tile may take the empty-tile path
     uint32_t pdl_early;                // geometry / binning kernels trigger their dependents at once (device_math.cuh)
+    uint32_t bin_records_per_warp;     // k_bin: with at most this many records per warp of its grid a warp takes a record, else a thread
+    uint32_t clear_in_tile;            // k_tile's CTAs write the empty tiles between their items; no k_clear_empty launch
 };
 
 // Texture (scene/mod.rs:206-216) with both TextureMaps flattened into the texel pool.  Maps are
@@ -178,7 +180,7 @@ struct FrameDev {
                                    // fills them with atomicMin, k_tile consumes and resets them [page_cap pages]
     uint32_t page_cap;
     uint32_t *counters;         // [0] records  [1] refs  [2] overflow bits  [3] k_setup CTA ticket  [4] k_alloc CTAs done  [5] clip queue length
-                                // [6] total tile cost  [8..10] large / medium / small references  [11] key pages handed out  [13] empty tiles  [14] tiles for k_shade  [32] k_tile item cursor  [N_COUNTERS]
+                                // [6] total tile cost  [8..10] large / medium / small references  [11] key pages handed out  [13] empty tiles  [14] tiles for k_shade  [15] k_tile items  [32] k_tile item cursor  [N_COUNTERS]
     uint32_t *tile_cost;        // estimated k_tile work per tile [n_coarse]
     uint32_t *tile_order;       // k_tile work items (make_item), heaviest first, padded with ITEM_NONE [n_coarse + TILE_EXTRA_ITEMS]
     uint32_t *shade_tiles;      // tiles k_shade resolves from their key page, as x | y << 10 (count in counters[14]) [n_coarse]

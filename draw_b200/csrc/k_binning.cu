@@ -90,7 +90,7 @@ __device__ __forceinline__ BinTri bin_prepare(const FrameDev &W, const RasterRec
 
 constexpr int BIN_THREADS = 256;
 constexpr int WIDE_TILES = 8;        // thread-per-record mode: records covering more tiles are binned by the whole warp
-constexpr int RECORDS_PER_WARP = 8;  // up to this many records per warp of the grid: one warp per record
+// (FrameUniforms::bin_records_per_warp: up to this many records per warp of the grid, one warp per record)
 
 // Tile range of a record's bbox, clipped to this launch's stripe.
 struct TileRange {
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const FrameUniforms *__rest
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n_warps = gridDim.x * (BIN_THREADS / 32);
 
-    if (n <= n_warps * RECORDS_PER_WARP) {
+    if (n <= n_warps * U.bin_records_per_warp) {
         // Few records (they may each cover many tiles): one warp per record, lanes stride over its
         // tiles so that the atomics of one record are in flight together.
         for (uint32_t slot = blockIdx.x * (BIN_THREADS / 32) + (threadIdx.x >> 5); slot < n; slot += n_warps) {
@@ -333,7 +333,10 @@ __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const FrameUniforms *__
     const uint32_t n_dense = block_base;
     const uint32_t grid_items = (U.tile_y_end - U.tile_y_begin) * U.tiles_x + (TILE_SPLITTABLE ? TILE_EXTRA_ITEMS : 0);
     for (uint32_t i = n_dense + tid; i < grid_items; i += ALLOC_THREADS) W.tile_order[i] = ITEM_NONE;
-    if (tid == 0) W.counters[13] = n_empty; // k_clear_empty's work
+    if (tid == 0) {
+        W.counters[13] = n_empty; // k_clear_empty's work (or k_tile's, FrameUniforms::clear_in_tile)
+        W.counters[15] = n_dense; // k_tile's items
+    }
     for (uint32_t t0 = tid; t0 < nc; t0 += ALLOC_THREADS * BATCH) {
         uint32_t cost_k[BATCH];
 #pragma unroll
@@ -358,7 +361,8 @@ __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const FrameUniforms *__
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-static int bin_blocks(const FrameDev &) { return 148 * 4; }
+unsigned g_bin_ctas = 148u * 4u; // scene.cpp: DRAW_B200_BIN_CTAS
+static int bin_blocks(const FrameDev &) { return (int)g_bin_ctas; }
 void launch_bin_count(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream) {
     launch_pdl(k_bin<false>, bin_blocks(W), BIN_THREADS, stream, dU, W);
 }

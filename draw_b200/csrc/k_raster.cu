@@ -22,6 +22,10 @@
 namespace drawb200 {
 
 constexpr int RASTER_THREADS = 256;
+#ifndef DRAW_RASTER_MINB
+#define DRAW_RASTER_MINB 4
+#endif
+constexpr int RASTER_MIN_CTAS = DRAW_RASTER_MINB;
 
 __device__ __forceinline__ void commit_fragment(unsigned long long *cell, unsigned long long key) {
 #ifndef DRAW_RASTER_PRECHECK
@@ -34,7 +38,7 @@ __device__ __forceinline__ void commit_fragment(unsigned long long *cell, unsign
 #endif
 }
 
-__global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster(const FrameUniforms *__restrict__ Up, const FrameDev W) {
+__global__ void __launch_bounds__(RASTER_THREADS, RASTER_MIN_CTAS) k_raster(const FrameUniforms *__restrict__ Up, const FrameDev W) {
     const FrameUniforms &U = *Up; // per-frame uniforms, device-resident (one upload per frame; the launches never change)
     pdl_prologue(U.pdl_early != 0);
     if (W.counters[2] != 0 || W.page_cap == 0) return; // a buffer overflowed: the host re-renders; or no pages at all
@@ -44,13 +48,11 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster(const FrameUniform
     const float depth_max = U.depth_max;
 
     // ---- medium references: one per warp ---------------------------------------------------------
-#pragma unroll 1
-    for (uint32_t i = gwarp; i < n_medium; i += n_warps) {
-        const uint2 ref = __ldg(W.m_refs + i); // same address in every lane: one broadcast load
+    auto medium_ref = [&](const uint2 ref) {
         const uint32_t tile_x = ref.y & (MAX_TILES_X - 1), tile_y = (ref.y >> 10) & (MAX_TILES_Y - 1);
         const uint32_t part = (ref.y >> 21) & 3u, parts = ((ref.y >> 23) & 3u) + 1u; // this entry's share of the blocks
         const uint32_t page = W.tile_page[tile_y * U.tiles_x + tile_x];
-        if (page == NO_PAGE) continue; // k_tile rasterises this tile's lists itself
+        if (page == NO_PAGE) return; // k_tile rasterises this tile's lists itself
         const uint4 *q = reinterpret_cast<const uint4 *>(W.prep + ref.x);
         const uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4), q5 = __ldg(q + 5),
                     q6 = __ldg(q + 6);
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster(const FrameUniform
         const int tx0 = (int)tile_x * TILE_W, ty0 = (int)tile_y * TILE_H;
         const int lx = max((int)__uint_as_float(q5.x), tx0), hx = min((int)__uint_as_float(q5.y), tx0 + TILE_W - 1);
         const int ly = max((int)__uint_as_float(q5.z), ty0), hy = min((int)__uint_as_float(q5.w), ty0 + TILE_H - 1);
-        if (lx > hx || ly > hy) continue;
+        if (lx > hx || ly > hy) return;
         const uint32_t nbx = (uint32_t)(hx - lx) / 8u + 1u, nby = (uint32_t)(hy - ly) / 4u + 1u, n_blocks = nbx * nby; // <= 64
         unsigned long long *page_keys = W.key_pages + (size_t)page * (TILE_W * TILE_H);
 #pragma unroll 1
@@ -92,7 +94,28 @@ __global__ void __launch_bounds__(RASTER_THREADS, 4) k_raster(const FrameUniform
                 commit_fragment(page_keys + (py - ty0) * TILE_W + (px - tx0), make_key(d, ref.x));
             }
         }
+    };
+#ifndef DRAW_RASTER_PIPE
+#pragma unroll 1
+    for (uint32_t i = gwarp; i < n_medium; i += n_warps) medium_ref(__ldg(W.m_refs + i)); // same address in every lane: one broadcast load
+#else
+    // software pipeline: the next reference is loaded before this one is processed and its record and page
+    // entry are requested (L1 prefetch) before the loop comes back to them
+    if (gwarp < n_medium) {
+        uint2 ref = __ldg(W.m_refs + gwarp);
+#pragma unroll 1
+        for (uint32_t i = gwarp; i < n_medium; i += n_warps) {
+            const uint32_t i_next = i + n_warps;
+            const uint2 ref_next = i_next < n_medium ? __ldg(W.m_refs + i_next) : ref;
+            if (i_next < n_medium && lane == 0) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(W.prep + ref_next.x));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(W.tile_page + ((ref_next.y >> 10) & (MAX_TILES_Y - 1)) * U.tiles_x + (ref_next.y & (MAX_TILES_X - 1))));
+            }
+            medium_ref(ref);
+            ref = ref_next;
+        }
     }
+#endif
 
     // ---- small references: one per lane ----------------------------------------------------------
     const uint32_t n_threads = gridDim.x * RASTER_THREADS;
@@ -129,8 +152,9 @@ __global__ void __launch_bounds__(256) k_fill_u64(unsigned long long *__restrict
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = value;
 }
 
+unsigned g_raster_ctas = 148u * 8u; // scene.cpp: DRAW_B200_RASTER_CTAS
 void launch_raster(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream) {
-    launch_pdl(k_raster, 148u * 8u, RASTER_THREADS, stream, dU, W);
+    launch_pdl(k_raster, g_raster_ctas, RASTER_THREADS, stream, dU, W);
 }
 cudaError_t launch_fill_u64(unsigned long long *dst, size_t n, unsigned long long value, cudaStream_t stream) {
     k_fill_u64<<<148 * 4, 256, 0, stream>>>(dst, n, value);

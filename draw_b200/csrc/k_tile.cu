@@ -664,6 +664,34 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
 #endif
 }
 
+// One empty tile written by the whole CTA (clear-in-tile mode, FrameUniforms::clear_in_tile): 16 bytes of
+// colour and 16 of depth per thread, fire-and-forget streaming stores that drain while the CTA works on
+// its raster item.
+__device__ __forceinline__ void clear_tile_cta(const uint32_t et, const int W_, const int H_, const float depth_max,
+                                               uint8_t *__restrict__ color, float *__restrict__ depth, const int tid) {
+    const int ex0 = (int)(et & (MAX_TILES_X - 1)) * TILE_W, ey0 = (int)(et >> 10) * TILE_H;
+    const uint32_t clear_px = 255u | (186u << 8) | (155u << 16) | (255u << 24); // memory order b g r pad
+    if ((W_ & 3) == 0) {
+        constexpr int QPR = TILE_W / 4; // 16-byte quads per tile row
+#pragma unroll
+        for (int q = tid; q < QPR * TILE_H; q += TILE_THREADS) {
+            const int x = ex0 + (q % QPR) * 4, y = ey0 + q / QPR;
+            if (x < W_ && y < H_) {
+                __stcs(reinterpret_cast<uint4 *>(color + ((size_t)(H_ - 1 - y) * W_ + x) * 4),
+                       make_uint4(clear_px, clear_px, clear_px, clear_px));
+                __stcs(reinterpret_cast<float4 *>(depth + (size_t)y * W_ + x), make_float4(depth_max, depth_max, depth_max, depth_max));
+            }
+        }
+    } else {
+        for (int p = tid; p < TILE_PIXELS; p += TILE_THREADS) {
+            const int x = ex0 + (p & (TILE_W - 1)), y = ey0 + p / TILE_W;
+            if (x >= W_ || y >= H_) continue;
+            __stcs(reinterpret_cast<uint32_t *>(color) + (size_t)(H_ - 1 - y) * W_ + x, clear_px);
+            __stcs(depth + (size_t)y * W_ + x, depth_max);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // k_clear_empty : the tiles nothing was binned to get the clear colour and depth (canvas.rs:425-433).
 // They are most of a frame's bytes and none of its arithmetic, so they have their own launch: it
@@ -724,15 +752,22 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(cons
     const FrameUniforms &U = *Up; // per-frame uniforms, device-resident (one upload per frame; the launches never change)
     uint8_t *__restrict__ color = U.color;
     float *__restrict__ depth = U.depth;
-    __shared__ uint32_t s_item;
+    __shared__ uint32_t s_item, s_index;
     __shared__ float u8tab[256]; // (u8 as f32) / 255.0, filled once per CTA (visible after the loop's first barrier)
     fill_u8_table(u8tab, threadIdx.x, TILE_THREADS);
     pdl_prologue();
     // The first item of a CTA is its own index; the cursor (in a cache line of its own: a load that shares
     // a line with a contended atomic queues behind it) hands out the rest.
     const bool usable = W.counters[2] == 0; // a work buffer overflowed: lists are unusable, the host re-renders
+    // Clear-in-tile mode: the empty tiles (k_alloc's list) are dealt out evenly over the raster items and
+    // written by the item's CTA before it starts on the item; there is no k_clear_empty launch.  The
+    // stores need no answer, so they drain to HBM under the latency-bound raster work instead of
+    // holding every SM for a launch of their own.
+    const uint32_t n_empty = U.clear_in_tile ? W.counters[13] : 0u, n_items = W.counters[15];
+    const uint32_t per_item = n_items ? (n_empty + n_items - 1u) / n_items : 0u;
+    const int W_ = (int)U.canvas_w, H_ = (int)U.canvas_h;
     uint32_t *cursor = W.counters + ITEM_CURSOR;
-    uint32_t item = ITEM_NONE, ahead = 0; // thread 0 only
+    uint32_t item = ITEM_NONE, index = blockIdx.x, ahead = 0; // thread 0 only
     if (threadIdx.x == 0) {
         ahead = gridDim.x + atomicAdd(cursor, 1u);
         item = blockIdx.x < n_slots ? __ldcg(&W.tile_order[blockIdx.x]) : ITEM_NONE;
@@ -741,17 +776,31 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(cons
         uint32_t next_item = ITEM_NONE, next_ahead = 0;
         if (threadIdx.x == 0) {
             s_item = item;
+            s_index = index;
             next_item = ahead < n_slots ? __ldcg(&W.tile_order[ahead]) : ITEM_NONE; // consumed after the item below
             next_ahead = gridDim.x + atomicAdd(cursor, 1u);
         }
         __syncthreads();
-        const uint32_t cur = s_item;
+        const uint32_t cur = s_item, cur_index = s_index;
         if (cur == ITEM_NONE) break; // items are contiguous; the slots after them hold ITEM_NONE
+        // mode 1: before the item; 2: after it; 3: before in even CTAs, after in odd ones (the two CTAs of an SM
+        // are then rarely both storing)
+        const bool clear_first = U.clear_in_tile == 1u || (U.clear_in_tile == 3u && (blockIdx.x & 1u) == 0u);
+        if (clear_first)
+            for (uint32_t e = cur_index * per_item, e_end = min(n_empty, e + per_item); e < e_end; e++)
+                clear_tile_cta(__ldg(&W.empty_tiles[e]), W_, H_, U.depth_max, color, depth, threadIdx.x);
         tile_item(cur, U, S, W, color, depth, u8tab, usable);
+        if (!clear_first)
+            for (uint32_t e = cur_index * per_item, e_end = min(n_empty, e + per_item); e < e_end; e++)
+                clear_tile_cta(__ldg(&W.empty_tiles[e]), W_, H_, U.depth_max, color, depth, threadIdx.x);
         __syncthreads(); // shared memory (and s_item) are reused by the next item
         item = next_item;
+        index = ahead;
         ahead = next_ahead;
     }
+    if (n_items == 0u) // nothing to rasterise in this stripe: the CTAs share the empty tiles
+        for (uint32_t e = blockIdx.x; e < n_empty; e += gridDim.x)
+            clear_tile_cta(__ldg(&W.empty_tiles[e]), W_, H_, U.depth_max, color, depth, threadIdx.x);
 }
 
 // Canvas::clear (canvas.rs:425-433) as a standalone operation (draw_canvas_clear).

@@ -24,6 +24,9 @@
 
 namespace drawb200 {
 int g_pdl_enabled = 1;
+extern unsigned g_clip_ctas; // k_geometry.cu
+extern unsigned g_bin_ctas;  // k_binning.cu
+extern unsigned g_raster_ctas; // k_raster.cu
 extern unsigned g_clear_ctas, g_tile_ctas;
 // k_geometry.cu / k_binning.cu / k_tile.cu
 void launch_vertex(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
@@ -37,6 +40,8 @@ cudaError_t launch_fill_u64(unsigned long long *dst, size_t n, unsigned long lon
 void launch_tile(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
 void launch_clear_empty(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream);
 void launch_shade(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
+void launch_sort_transparent(const FrameUniforms *dU, const SceneDev &S, const void *ranges, uint32_t n_ranges, uint32_t *keys0,
+                             uint32_t *keys1, uint32_t *perm0, uint32_t *perm1, uint32_t *scratch, cudaStream_t stream); // k_sort.cu
 cudaError_t launch_clear(uint8_t *color, float *depth, size_t n_pixels, float depth_max, cudaStream_t stream,
                          uint64_t *launches);
 cudaError_t launch_fill_u32(uint32_t *dst, size_t n, uint32_t value, cudaStream_t stream, uint64_t *launches);
@@ -152,6 +157,9 @@ struct draw_scene {
         size_t object, mesh, first_tri; // first_tri = position in the global draw order
     };
     std::vector<TransparentRange> transparent_ranges;
+    // device painter sort (k_sort.cu): one (first, n, scratch base) per transparent mesh, key / permutation ping-pong, scratch
+    DevBuf<uint4> d_sort_ranges;
+    DevBuf<uint32_t> d_sort_keys[2], d_sort_perm[2], d_sort_tmp;
 
     // Per-frame work buffers, N_WORK_SETS deep, each with its own side stream: the vertex / setup /
     // binning kernels of the next frames (a chain of six small, latency-bound launches) run on side
@@ -242,6 +250,12 @@ struct Config {
     int split_div = std::min(std::max(1, env_int("DRAW_B200_SPLIT_DIV", TILE_SPLIT_DIV)), (int)TILE_EXTRA_ITEMS);
     int defer_max = std::max(0, env_int("DRAW_B200_DEFER_MAX", 0));  // k_shade takes tiles with fewer large references (0: off)
     int split_max = std::min(std::max(1, env_int("DRAW_B200_SPLIT_MAX", TILE_MAX_SPLIT)), (int)TILE_MAX_SPLIT);
+    int bin_rpw = std::max(0, env_int("DRAW_B200_BIN_RPW", 8));   // k_bin: warp-per-record up to this many records per warp of the grid
+    int clip_ctas = std::max(1, env_int("DRAW_B200_CLIP_CTAS", 148 * 2));
+    int bin_ctas = std::max(1, env_int("DRAW_B200_BIN_CTAS", 148 * 4));
+    int raster_ctas = std::max(1, env_int("DRAW_B200_RASTER_CTAS", 148 * 8));
+    int skip = env_int("DRAW_B200_SKIP", 0); // timing experiments only: bit i set = kernel i of the frame is not launched (frames are then wrong)
+    int clear_in_tile = env_int("DRAW_B200_CLEAR_IN_TILE", 0); // empty tiles written by k_tile's CTAs instead of k_clear_empty
 };
 const Config g_cfg;
 
@@ -272,7 +286,9 @@ int pick_device(int *out) {
 
 // Rebuilds the device geometry from the host objects: SoA, all objects concatenated, triangles
 // in the reference's draw order (per object: opaque meshes, then transparent meshes).
+int fetch_transparent_order(draw_scene *s);
 int upload_geometry(draw_scene *s) {
+    TRY(fetch_transparent_order(s));
     std::vector<float> pos[3], nrm[3], uv[2];
     std::vector<uint32_t> idx[9], mat, tslot;
     std::vector<MaterialDev> materials;
@@ -343,6 +359,22 @@ int upload_geometry(draw_scene *s) {
     d.n_triangles = (uint32_t)mat.size();
     d.n_transparent = n_transparent;
     d.n_materials = (uint32_t)materials.size();
+    if (n_transparent) {
+        std::vector<uint4> ranges;
+        uint32_t base = 0;
+        for (const draw_scene::TransparentRange &tr : s->transparent_ranges) {
+            const uint32_t n = (uint32_t)(s->objects[tr.object].transparent[tr.mesh].tris.size() / 9);
+            ranges.push_back(make_uint4((uint32_t)tr.first_tri, n, base, 0u));
+            base += n;
+        }
+        TRY(s->d_sort_ranges.upload(ranges));
+        for (int i = 0; i < 2; i++) {
+            TRY(s->d_sort_keys[i].reserve(base));
+            TRY(s->d_sort_perm[i].reserve(base));
+        }
+        TRY(s->d_sort_tmp.reserve(base));
+        CU(cudaDeviceSynchronize());
+    }
     s->geometry_dirty = false;
     return DRAW_OK;
 }
@@ -420,31 +452,17 @@ int ensure_work_buffers(draw_scene *s, draw_scene::WorkSet &ws, size_t n_lists) 
 // Painter sort of every transparent mesh (scene/mod.rs:1100-1115): stable, far to near by
 // f32::total_cmp of the centroid distance, persistent across frames; re-uploads the index
 // streams of meshes whose order changed.
-int sort_transparent(draw_scene *s, cudaStream_t stream) {
-    const f3 cam = s->camera.position;
+// The device keeps the transparent meshes' triangle lists in the order the painter sort left them
+// (k_sort.cu; the reference's lists persist the same way, scene/mod.rs:1100-1115).  Before the geometry
+// is rebuilt from the host objects (an object was added) that order is read back into them.
+int fetch_transparent_order(draw_scene *s) {
+    if (s->transparent_ranges.empty() || !s->d_idx[0].ptr) return DRAW_OK;
+    CU(cudaDeviceSynchronize());
     for (const draw_scene::TransparentRange &tr : s->transparent_ranges) {
         HostObject &o = s->objects[tr.object];
         HostMesh &m = o.transparent[tr.mesh];
         const size_t n = m.tris.size() / 9;
-        std::vector<int32_t> key(n);
-        for (size_t t = 0; t < n; t++) {
-            const uint32_t *p = &m.tris[9 * t];
-            auto vert = [&](uint32_t v) { return f3{o.pos[3 * v], o.pos[3 * v + 1], o.pos[3 * v + 2]}; };
-            const f3 center = divide(add(add(vert(p[0]), vert(p[1])), vert(p[2])), 3.0f); // :1108
-            key[t] = total_order_key(length(sub(center, cam)));                           // Vec3::dist
-        }
-        std::vector<uint32_t> order(n);
-        for (size_t t = 0; t < n; t++) order[t] = (uint32_t)t;
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] > key[b]; });
-        bool changed = false;
-        for (size_t t = 0; t < n; t++)
-            if (order[t] != t) { changed = true; break; }
-        if (!changed) continue;
-        std::vector<uint32_t> sorted(m.tris.size());
-        for (size_t t = 0; t < n; t++) std::memcpy(&sorted[9 * t], &m.tris[9 * order[t]], 9 * sizeof(uint32_t));
-        m.tris.swap(sorted);
-        // global index bases of this object
-        uint32_t vbase = 0, nbase = 0, tbase = 0;
+        uint32_t vbase = 0, nbase = 0, tbase = 0; // global index bases of this object
         for (size_t oi = 0; oi < tr.object; oi++) {
             vbase += (uint32_t)(s->objects[oi].pos.size() / 3);
             nbase += (uint32_t)(s->objects[oi].nrm.size() / 3);
@@ -453,10 +471,8 @@ int sort_transparent(draw_scene *s, cudaStream_t stream) {
         std::vector<uint32_t> stream_host(n);
         for (int c = 0; c < 9; c++) {
             const uint32_t base = c < 3 ? vbase : (c < 6 ? tbase : nbase);
-            for (size_t t = 0; t < n; t++) stream_host[t] = m.tris[9 * t + c] + base;
-            // pageable source: the call returns once the data is staged, so the vector may be reused
-            CU(cudaMemcpyAsync(s->d_idx[c].ptr + tr.first_tri, stream_host.data(), n * sizeof(uint32_t),
-                               cudaMemcpyHostToDevice, stream));
+            CU(cudaMemcpy(stream_host.data(), s->d_idx[c].ptr + tr.first_tri, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            for (size_t t = 0; t < n; t++) m.tris[9 * t + c] = stream_host[t] - base;
         }
     }
     return DRAW_OK;
@@ -469,38 +485,49 @@ int launch_frame(draw_scene *s, draw_scene::WorkSet &ws, const FrameUniforms &U,
     // ws.canvas_ready is recorded on the canvas' stream outside the graph: an external event of the capture
     const unsigned ext = capturing ? cudaEventWaitExternal : 0u;
     CU(cudaMemcpyAsync(ws.d_uniforms.ptr, ws.h_uniforms, sizeof(FrameUniforms), cudaMemcpyHostToDevice, side));
+    // painter sort of the transparent meshes, in place in the shared index streams (enqueue_frame has ordered
+    // this stream after the previous frame's geometry, which reads them)
+    if (s->dev.n_transparent)
+        launch_sort_transparent(dU, s->dev, s->d_sort_ranges.ptr, (uint32_t)s->transparent_ranges.size(), s->d_sort_keys[0].ptr,
+                                s->d_sort_keys[1].ptr, s->d_sort_perm[0].ptr, s->d_sort_perm[1].ptr, s->d_sort_tmp.ptr, side);
     if (ev) cudaEventRecord(ev[0], side);
-    launch_vertex(U, dU, s->dev, ws.work, side);
+    if (!(g_cfg.skip & 1)) launch_vertex(U, dU, s->dev, ws.work, side);
     if (ev) cudaEventRecord(ev[1], side);
-    launch_setup(U, dU, s->dev, ws.work, side);
+    if (!(g_cfg.skip & 2)) launch_setup(U, dU, s->dev, ws.work, side);
     if (ev) cudaEventRecord(ev[2], side);
-    launch_clip(U, dU, s->dev, ws.work, side);
+    if (!(g_cfg.skip & 4)) launch_clip(U, dU, s->dev, ws.work, side);
     if (ev) cudaEventRecord(ev[3], side);
-    launch_bin_count(U, dU, ws.work, side);
+    if (!(g_cfg.skip & 8)) launch_bin_count(U, dU, ws.work, side);
     if (ev) cudaEventRecord(ev[4], side);
-    launch_alloc(U, dU, ws.work, side);
+    if (!(g_cfg.skip & 16)) launch_alloc(U, dU, ws.work, side);
     CU(cudaEventRecord(ws.alloc_done, side));
     if (ev) cudaEventRecord(ev[5], side);
     // the empty tiles are cleared as soon as k_alloc has listed them: the stores stream to HBM under the
     // rest of the chain and under k_tile's dense tiles (disjoint pixels)
-    CU(cudaStreamWaitEvent(ws.aux_stream, ws.alloc_done, 0));
-    CU(cudaStreamWaitEvent(ws.aux_stream, ws.canvas_ready, ext));
-    if (ev) cudaEventRecord(ev[N_FRAME_KERNELS - 1], ws.aux_stream);
-    launch_clear_empty(U, dU, ws.work, ws.aux_stream);
-    if (ev) cudaEventRecord(ev[N_FRAME_KERNELS], ws.aux_stream);
-    CU(cudaEventRecord(ws.clear_done, ws.aux_stream));
-    launch_bin_fill(U, dU, ws.work, side);
+    // (clear-in-tile mode: k_tile's CTAs write them between their raster items and there is no such launch)
+    if (!U.clear_in_tile) {
+        CU(cudaStreamWaitEvent(ws.aux_stream, ws.alloc_done, 0));
+        CU(cudaStreamWaitEvent(ws.aux_stream, ws.canvas_ready, ext));
+        if (ev) cudaEventRecord(ev[N_FRAME_KERNELS - 1], ws.aux_stream);
+        if (!(g_cfg.skip & 128)) launch_clear_empty(U, dU, ws.work, ws.aux_stream);
+        if (ev) cudaEventRecord(ev[N_FRAME_KERNELS], ws.aux_stream);
+        CU(cudaEventRecord(ws.clear_done, ws.aux_stream));
+    } else if (ev) {
+        cudaEventRecord(ev[N_FRAME_KERNELS - 1], side);
+        cudaEventRecord(ev[N_FRAME_KERNELS], side);
+    }
+    if (!(g_cfg.skip & 32)) launch_bin_fill(U, dU, ws.work, side);
     if (ev) cudaEventRecord(ev[6], side);
-    launch_raster(U, dU, ws.work, side);
+    if (!(g_cfg.skip & 64)) launch_raster(U, dU, ws.work, side);
     if (ev) cudaEventRecord(ev[7], side);
     CU(cudaEventRecord(ws.geo_done, side));
     CU(cudaStreamWaitEvent(side, ws.canvas_ready, ext));
     if (ev) cudaEventRecord(ev[N_FRAME_KERNELS + 1], side);
-    launch_tile(U, dU, s->dev, ws.work, side);
+    if (!(g_cfg.skip & 256)) launch_tile(U, dU, s->dev, ws.work, side);
     if (ev) cudaEventRecord(ev[N_FRAME_KERNELS + 2], side);
-    launch_shade(U, dU, s->dev, ws.work, side);
+    if (!(g_cfg.skip & 512)) launch_shade(U, dU, s->dev, ws.work, side);
     if (ev) cudaEventRecord(ev[N_FRAME_KERNELS + 3], side);
-    CU(cudaStreamWaitEvent(side, ws.clear_done, 0));
+    if (!U.clear_in_tile) CU(cudaStreamWaitEvent(side, ws.clear_done, 0));
     return DRAW_OK;
 }
 
@@ -564,6 +591,11 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     U.split_div = (uint32_t)g_cfg.split_div;
     U.split_max = (uint32_t)g_cfg.split_max;
     U.defer_max = (uint32_t)g_cfg.defer_max;
+    U.clear_in_tile = (uint32_t)g_cfg.clear_in_tile;
+    U.bin_records_per_warp = (uint32_t)g_cfg.bin_rpw;
+    g_clip_ctas = (unsigned)g_cfg.clip_ctas;
+    g_bin_ctas = (unsigned)g_cfg.bin_ctas;
+    g_raster_ctas = (unsigned)g_cfg.raster_ctas;
     const size_t y0 = c->stripe_y1 ? c->stripe_y0 : 0, y1 = c->stripe_y1 ? c->stripe_y1 : c->height;
     U.tile_y_begin = (uint32_t)(y0 / TILE_H);
     U.tile_y_end = (uint32_t)((y1 + TILE_H - 1) / TILE_H);
@@ -597,7 +629,6 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     if (s->dev.n_transparent) {
         // the painter sort rewrites the shared index streams: order it after the previous frame's geometry
         if (&prev_ws != &ws && prev_ws.frame_pending) CU(cudaStreamWaitEvent(side, prev_ws.geo_done, 0));
-        TRY(sort_transparent(s, side));
     }
     if (ws.work.tile_cycles) CU(cudaMemsetAsync(ws.work.tile_cycles, 0, n_lists * sizeof(uint32_t), side)); // debug taps are atomicMax'd
 
@@ -618,7 +649,7 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
         key.scene = s->dev;
         key.work = ws.work;
         key.n_coarse = U.n_coarse; key.n_lists = U.n_lists; key.tiles_x = U.tiles_x;
-        key.tile_y_begin = U.tile_y_begin; key.tile_y_end = U.tile_y_end; key.clear_ctas = g_clear_ctas + 65536u * g_tile_ctas;
+        key.tile_y_begin = U.tile_y_begin; key.tile_y_end = U.tile_y_end; key.clear_ctas = g_clear_ctas + 65536u * g_tile_ctas + 7u * g_clip_ctas + 1000003u * g_bin_ctas + 15485863u * g_raster_ctas;
         if (!ws.graph_exec || std::memcmp(&key, &ws.graph_key, sizeof key) != 0) {
             if (ws.graph_exec) CU(cudaGraphExecDestroy(ws.graph_exec));
             ws.graph_exec = nullptr;
@@ -646,7 +677,7 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     CU(cudaEventRecord(ws.frame_done, side));
     ws.frame_pending = true;
     CU(cudaStreamWaitEvent(st, ws.frame_done, 0));
-    s->launches += 5 + (s->dev.n_triangles ? 2 : 0) + (U.tile_y_end > U.tile_y_begin ? (U.defer_max ? 3 : 2) : 0);
+    s->launches += 5 + (s->dev.n_triangles ? 2 : 0) + (s->dev.n_transparent ? 1 : 0) + (U.tile_y_end > U.tile_y_begin ? (U.defer_max ? 3 : 2) - (U.clear_in_tile ? 1 : 0) : 0);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_status, ws.work.counters, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     c->frame_pending = true;

@@ -258,3 +258,57 @@ def test_small_buffers_grow_and_rerender():
     assert st["setup_records"] > 0 and st["tile_refs"] > 0
     want = render_oracle(objs, 3840, 2160, cam=path[60])
     assert_frames_equal(got, want, "C4 frame 60")
+
+
+def _glass_torus(n_theta=48, n_phi=40):
+    """A torus cut into two transparent meshes (3 840 triangles: several 1024-element chunks of the
+    device radix sort, and plenty of equal centroid distances from the symmetry, i.e. ties that only a
+    stable sort keeps in list order)."""
+    from draw_b200 import synthetic
+    from draw_b200.model import IndexedMesh, Object, Texture
+    t = synthetic.torus(n_theta, n_phi)
+    tris = t.meshes[0].triangles
+    half = tris.shape[0] // 2 + 17
+    meshes = [IndexedMesh("a", tris[:half].copy(), 1), IndexedMesh("b", tris[half:].copy(), 2)]
+    tex = [Texture(), Texture(name="ga", alpha=0.6, kd=np.array([0.1, 0.8, 0.3], F)),
+           Texture(name="gb", alpha=0.35, kd=np.array([0.9, 0.2, 0.1], F))]
+    return Object("glass_torus", t.vertices, t.normals_vertices, t.texture_vertices, meshes, tex)
+
+
+def test_painter_sort_on_device_large_meshes_moving_camera():
+    """scene/mod.rs:1100-1115: per-frame, in-place, stable sort of every transparent mesh (k_sort.cu)."""
+    back = _tri_object([[-120, -90, -40], [120, -90, -40], [0, 110, -40]], kd=(1.0, 1.0, 0.0))
+    cams = [[0, 0, 150, 0, 0, -150], [0, 0, 150, 0, 0, -150], [130, 30, 80, -1, -0.2, -0.6], [-90, -60, 110, 0.7, 0.5, -1],
+            [10, 140, 60, 0, -1, -0.4], [0, 0, 150, 0, 0, -150]]
+    cams = [np.array(c, F) for c in cams]
+    got, want = _both([back, _glass_torus()], 320, 240, cam=cams)
+    assert (want[0][..., 3] == 0).any(), "transparent pass not exercised"
+    assert_frames_equal(got, want, "device painter sort")
+
+
+def test_painter_order_survives_adding_an_object():
+    """The sorted order of a transparent mesh persists in the reference's list; a geometry re-upload
+    (add_obj between frames) must not reset it."""
+    import draw_b200
+    from oracle import pyoracle
+    W, H = 256, 192
+    s, c = draw_b200.Scene(W, H), draw_b200.Canvas(W, H)
+    o, oc = pyoracle.Scene(W, H), pyoracle.Canvas(W, H)
+    c.init_depth(DEPTH_MAX)
+    oc.init_depth(DEPTH_MAX)
+    glass = _glass_torus(24, 20)
+    s.add_obj(glass)
+    o.add_obj(glass)
+    for cam in ([120, 40, 90, -1, -0.3, -0.8], [-100, -20, 120, 0.8, 0.1, -1]):
+        cam = np.array(cam, F)
+        s.camera = draw_b200.Camera.new(cam[:3], cam[3:])
+        o.set_camera(cam[:3], cam[3:])
+        s.render(c)
+        o.render(oc)
+    extra = _tri_object([[-80, -60, 0], [80, -60, 0], [0, 80, 0]], kd=(0.2, 0.2, 1.0))
+    s.add_obj(extra)
+    o.add_obj(extra)
+    for _ in range(2):
+        s.render(c)
+        o.render(oc)
+    assert_frames_equal((c.as_bytes_slice(), c.depth()), (oc.as_bytes(), oc.depth()), "order after add_obj")
