@@ -247,7 +247,10 @@ def run_ours(args, cfg):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     else:
         dist = None
-    # a real (non-default) stream: the library enqueues on it and torch's events are recorded on it
+    # a real (non-default) stream for the timing events.  Every canvas of the ring renders on its own stream
+    # (frames on different canvases are independent and overlap, as they would for an application that
+    # keeps several frames in flight); before the closing event is recorded the timing stream is made to
+    # wait, on the device, for every canvas (Canvas.stream_wait), so ev0 -> ev1 spans all K frames.
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
@@ -263,7 +266,8 @@ def run_ours(args, cfg):
         c = draw_b200.Canvas(W, H)
         c.init_depth(DEPTH_MAX)
         c.apply_offset(0, 0)
-        c.set_stream(stream.cuda_stream)
+        if os.environ.get("DRAW_BENCH_SHARED_STREAM"):  # A/B: all canvases enqueue on the timing stream
+            c.set_stream(stream.cuda_stream)
         ring.append(c)
     cams = cfg["cameras"]
 
@@ -296,6 +300,8 @@ def run_ours(args, cfg):
     ev0.record(stream)
     for k in range(args.steps):
         frame(k, ring[k % n_ring])
+    for c in ring:
+        c.stream_wait(stream.cuda_stream)
     ev1.record(stream)
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -341,6 +347,7 @@ def run_ours(args, cfg):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
         frame(k, ring[0])
+        ring[0].stream_wait(stream.cuda_stream)
         b.record(stream)
         torch.cuda.synchronize()
         per_step.append(a.elapsed_time(b))

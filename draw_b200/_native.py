@@ -78,6 +78,7 @@ SIGNATURES = {
     "draw_scene_last_kernel_times": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),
     "draw_scene_debug_list_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "draw_scene_debug_tile_cycles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "draw_scene_debug_trace": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "draw_canvas_create": (C.c_int, [C.c_size_t, C.c_size_t, C.POINTER(C.c_void_p)]),
     "draw_canvas_destroy": (None, [C.c_void_p]),
     "draw_canvas_init_depth": (C.c_int, [C.c_void_p, C.c_float]),
@@ -95,6 +96,7 @@ SIGNATURES = {
     "draw_canvas_device_ptrs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "draw_canvas_bind_external": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "draw_canvas_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "draw_canvas_stream_wait": (C.c_int, [C.c_void_p, C.c_void_p]),
     "draw_canvas_set_stripe": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t]),
     "draw_tile_size": (C.c_int, []),
     "draw_canvas_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),

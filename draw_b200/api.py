@@ -150,6 +150,10 @@ class Canvas:
     def set_stream(self, cuda_stream):
         N.check(N.lib().draw_canvas_set_stream(self._h, cuda_stream))
 
+    def stream_wait(self, cuda_stream):
+        """Make `cuda_stream` wait (on the device) for everything enqueued so far for this canvas."""
+        N.check(N.lib().draw_canvas_stream_wait(self._h, cuda_stream))
+
     def set_stripe(self, y0, y1):
         N.check(N.lib().draw_canvas_set_stripe(self._h, y0, y1))
 
@@ -269,6 +273,14 @@ class Scene:
         out = np.empty(n, np.uint32)
         N.check(N.lib().draw_scene_debug_list_counts(self._h, canvas._h, out.ctypes.data, n, C.byref(nc)))
         return out[:nc.value], out[nc.value:2 * nc.value], out[2 * nc.value:]
+
+    def debug_trace(self, enable=True, cap=1 << 18):
+        """Returns the CTA records gathered so far as uint32 [n, 4] (kernel | SM << 8 | work set << 24,
+        CTA, start ns, end ns), then switches recording on or off and empties the buffer."""
+        out = np.zeros((cap, 4), np.uint32)
+        n = C.c_size_t(0)
+        N.check(N.lib().draw_scene_debug_trace(self._h, 1 if enable else 0, out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value].copy()
 
     def debug_tile_cycles(self, canvas=None, enable=True):
         """Toggle per-tile cycle recording; with a canvas, return the last frame's cycles per coarse tile."""

@@ -28,6 +28,36 @@ __device__ __forceinline__ void pdl_prologue(bool early = true) {
     cudaGridDependencySynchronize();
 #endif
 }
+// Debug timeline (draw_scene_debug_trace): thread 0 of every CTA of the frame kernels records
+// (kernel id | SM << 8 | work set << 24, CTA index, start, end) with the nanosecond global timer, so that
+// the overlap of the frames in flight can be looked at without a system profiler.  Off (null pointer)
+// it costs one uniform branch per CTA.
+struct CtaTrace {
+    uint4 *trace;
+    uint32_t *count;
+    uint32_t cap, word, t0;
+    static __device__ __forceinline__ uint32_t now() {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        return (uint32_t)t;
+    }
+    __device__ __forceinline__ CtaTrace(const FrameDev &W, uint32_t kernel_id) : trace(W.trace), count(W.trace_count), cap(W.trace_cap), word(0), t0(0) {
+        if (trace && threadIdx.x == 0) {
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            word = kernel_id | smid << 8 | W.trace_tag << 24;
+            t0 = now();
+        }
+    }
+    __device__ __forceinline__ ~CtaTrace() {
+        if (trace && threadIdx.x == 0) {
+            const uint32_t t1 = now(), at = atomicAdd(count, 1u);
+            if (at < cap) trace[at] = make_uint4(word, blockIdx.x, t0, t1);
+        }
+    }
+};
+
+extern int g_kernel_priority_set, g_kernel_priority; // scene.cpp
 extern int g_pdl_enabled; // scene.cpp (DRAW_B200_PDL=0 launches without the attribute)
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t stream, Args... args) {
@@ -35,11 +65,18 @@ inline void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, 
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(block);
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int n_attr = 0;
+    if (g_pdl_enabled) {
+        attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n_attr++].val.programmaticStreamSerializationAllowed = 1;
+    }
+    if (g_kernel_priority_set) { // scene.cpp: the geometry chain above the tile kernels (DRAW_B200_KPRIO)
+        attr[n_attr].id = cudaLaunchAttributePriority;
+        attr[n_attr++].val.priority = g_kernel_priority;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = g_pdl_enabled ? 1 : 0;
+    cfg.numAttrs = n_attr;
     cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 

@@ -93,6 +93,7 @@ struct FrameUniforms {
     float *depth;                      // depth buffer, row 0 = y 0 (canvas.rs:413-423)
     uint32_t has_transparent;          // transparent triangles are not binned: no tile may take the empty-tile path
     uint32_t pdl_early;                // geometry / binning kernels trigger their dependents at once (device_math.cuh)
+    uint32_t cost_shade;               // k_alloc's cost of shading one fully covered tile (same units as COST_* in k_binning.cu)
     uint32_t bin_records_per_warp;     // k_bin: with at most this many records per warp of its grid a warp takes a record, else a thread
     uint32_t clear_in_tile;            // k_tile's CTAs write the empty tiles between their items; no k_clear_empty launch
 };
@@ -189,6 +190,9 @@ struct FrameDev {
     uint2 *clip_queue;          // (triangle, first reserved slot | NO_SLOT) of triangles to clip [n_triangles]
     uint32_t rec_cap, refs_cap;
     uint32_t *tile_cycles;      // debug: SM cycles spent by each coarse tile's CTA (null = off) [n_coarse]
+    uint4 *trace;               // debug: one record per CTA of every frame kernel (device_math.cuh: CtaTrace), null = off
+    uint32_t *trace_count;      // records written (may exceed trace_cap: the excess is dropped)
+    uint32_t trace_cap, trace_tag; // tag = work set of the frame
 };
 
 enum : uint32_t { OVERFLOW_RECORDS = 1u, OVERFLOW_REFS = 2u };

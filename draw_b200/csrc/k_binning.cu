@@ -111,6 +111,7 @@ __device__ __forceinline__ TileRange tile_range(const FrameUniforms &U, uint32_t
 template <bool FILL>
 __global__ void __launch_bounds__(BIN_THREADS) k_bin(const FrameUniforms *__restrict__ Up, const FrameDev W) {
     const FrameUniforms &U = *Up; // per-frame uniforms, device-resident (one upload per frame; the launches never change)
+    const CtaTrace trace_(W, (FILL ? 5u : 3u));
     pdl_prologue(U.pdl_early != 0);
     if (FILL && W.counters[2] != 0) return; // a buffer overflowed: the host re-renders with larger buffers
     uint32_t n = W.counters[0];
@@ -213,6 +214,7 @@ __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const FrameUniforms *__
     __shared__ uint32_t warp_sum[3][ALLOC_THREADS / 32], warp_cost[ALLOC_THREADS / 32];
     __shared__ uint32_t block_base3[3], block_base, is_last;
     __shared__ uint32_t bucket_start[COST_BUCKETS];
+    const CtaTrace trace_(W, 4u);
     pdl_prologue(U.pdl_early != 0);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.x * ALLOC_THREADS + tid, nc = U.n_coarse;
@@ -237,8 +239,14 @@ __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const FrameUniforms *__
     if (in_stripe && c > 0) {
         const bool defer = page != NO_PAGE && U.has_transparent == 0 && c0 < U.defer_max;
         kind = defer ? (c0 == 0 ? TILE_KIND_RASTER_ONLY : TILE_KIND_DEFER) : TILE_KIND_FULL;
-        if (kind != TILE_KIND_RASTER_ONLY)
-            cost = COST_TILE_BASE + W.tile_cost[tile] + (page == NO_PAGE ? W.tile_cost[nc + tile] : 0u);
+        if (kind != TILE_KIND_RASTER_ONLY) {
+            // shading: cost_shade units for a tile's worth of covered pixels; a tile with large triangles is taken
+            // as covered, the others by the bbox area of their medium / small references (COST_MEDIUM_BLOCK per 32 px)
+            const uint32_t cm = W.tile_cost[nc + tile];
+            const uint32_t full = (uint32_t)(TILE_W * TILE_H / 32) * COST_MEDIUM_BLOCK;
+            const uint32_t shade = c0 ? U.cost_shade : (uint32_t)((unsigned long long)min(cm, full) * U.cost_shade / full);
+            cost = COST_TILE_BASE + W.tile_cost[tile] + (page == NO_PAGE ? cm : 0u) + shade;
+        }
         if (cost >= TILE_KIND_SHIFTED) cost = TILE_KIND_SHIFTED - 1u;
         if (defer) W.shade_tiles[atomicAdd(&W.counters[14], 1u)] = (tile % U.tiles_x) | ty << 10;
     }

@@ -19,6 +19,7 @@ namespace drawb200 {
 __global__ void __launch_bounds__(256) k_vertex(const FrameUniforms *__restrict__ Up, const SceneDev S,
                                                 const FrameDev W) {
     const FrameUniforms &U = *Up; // per-frame uniforms, device-resident (one upload per frame; the launches never change)
+    const CtaTrace trace_(W, 0u);
     pdl_prologue(U.pdl_early != 0);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     // per-frame reset of the binning state (the binning kernels run after this one on the same stream)
@@ -301,6 +302,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const FrameUniforms *__
     const FrameUniforms &U = *Up; // per-frame uniforms, device-resident (one upload per frame; the launches never change)
     __shared__ uint32_t warp_tot[SETUP_THREADS / 32];
     __shared__ uint32_t s_ticket, s_base;
+    const CtaTrace trace_(W, 1u);
     pdl_prologue(U.pdl_early != 0);
 
     if (threadIdx.x == 0) s_ticket = atomicAdd(&W.counters[3], 1u);
@@ -485,6 +487,7 @@ constexpr int CLIP_THREADS = 128;
 __global__ void __launch_bounds__(CLIP_THREADS) k_clip(const FrameUniforms *__restrict__ Up, const SceneDev S,
                                                        const FrameDev W) {
     const FrameUniforms &U = *Up; // per-frame uniforms, device-resident (one upload per frame; the launches never change)
+    const CtaTrace trace_(W, 2u);
     pdl_prologue(U.pdl_early != 0);
     const uint32_t n = W.counters[5];
     for (uint32_t q = blockIdx.x * CLIP_THREADS + threadIdx.x; q < n; q += gridDim.x * CLIP_THREADS) {

@@ -38,8 +38,14 @@ __device__ __forceinline__ void commit_fragment(unsigned long long *cell, unsign
 #endif
 }
 
-__global__ void __launch_bounds__(RASTER_THREADS, RASTER_MIN_CTAS) k_raster(const FrameUniforms *__restrict__ Up, const FrameDev W) {
+#ifdef DRAW_RASTER_MAXNREG
+__global__ void __maxnreg__(DRAW_RASTER_MAXNREG) k_raster(
+#else
+__global__ void __launch_bounds__(RASTER_THREADS, RASTER_MIN_CTAS) k_raster(
+#endif
+    const FrameUniforms *__restrict__ Up, const FrameDev W) {
     const FrameUniforms &U = *Up; // per-frame uniforms, device-resident (one upload per frame; the launches never change)
+    const CtaTrace trace_(W, 6u);
     pdl_prologue(U.pdl_early != 0);
     if (W.counters[2] != 0 || W.page_cap == 0) return; // a buffer overflowed: the host re-renders; or no pages at all
     const uint32_t n_medium = min(W.counters[9], W.refs_cap), n_small = min(W.counters[10], W.refs_cap);

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, 4) k_shade(const FrameUniforms 
     if (cached)
         for (uint32_t i = threadIdx.x; i < S.n_materials * (sizeof(MaterialDev) / 16); i += SHADE_THREADS)
             reinterpret_cast<uint4 *>(mat_cache)[i] = __ldg(reinterpret_cast<const uint4 *>(S.materials) + i);
+    const CtaTrace trace_(W, 9u);
     pdl_prologue(false);
     __syncthreads();
     if (W.counters[2] != 0) return; // overflow: k_raster and k_tile left the pages untouched, the host re-renders

@@ -701,10 +701,14 @@ __device__ __forceinline__ void clear_tile_cta(const uint32_t et, const int W_, 
 // instruction, pointers stepped by a row pair.
 // ------------------------------------------------------------------------------------------
 constexpr int CLEAR_THREADS = 256;
-__global__ void __launch_bounds__(CLEAR_THREADS) k_clear_empty(const FrameUniforms *__restrict__ Up, const FrameDev W) {
+#ifndef DRAW_CLEAR_MINB
+#define DRAW_CLEAR_MINB 1
+#endif
+__global__ void __launch_bounds__(CLEAR_THREADS, DRAW_CLEAR_MINB) k_clear_empty(const FrameUniforms *__restrict__ Up, const FrameDev W) {
     const FrameUniforms &U = *Up; // per-frame uniforms, device-resident (one upload per frame; the launches never change)
     uint8_t *__restrict__ color = U.color;
     float *__restrict__ depth = U.depth;
+    const CtaTrace trace_(W, 7u);
     pdl_prologue(false);
     const uint32_t n_empty = W.counters[13];
     const int lane = threadIdx.x & 31;
@@ -747,7 +751,12 @@ __global__ void __launch_bounds__(CLEAR_THREADS) k_clear_empty(const FrameUnifor
 // list is exhausted, so that no CTA is launched just to find out that there is nothing to do, and the
 // per-CTA set-up is paid once.  Thread 0 keeps one list index and one item in flight ahead of the
 // item being processed (the cursor's atomicAdd and the list load are L2 round trips).
-__global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(const FrameUniforms *__restrict__ Up, const SceneDev S,
+#ifdef DRAW_TILE_MAXNREG // leave registers free for a co-resident k_clear_empty CTA (experiments)
+__global__ void __maxnreg__(DRAW_TILE_MAXNREG) k_tile(
+#else
+__global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(
+#endif
+    const FrameUniforms *__restrict__ Up, const SceneDev S,
                                                                             const FrameDev W, const uint32_t n_slots) {
     const FrameUniforms &U = *Up; // per-frame uniforms, device-resident (one upload per frame; the launches never change)
     uint8_t *__restrict__ color = U.color;
@@ -755,6 +764,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(cons
     __shared__ uint32_t s_item, s_index;
     __shared__ float u8tab[256]; // (u8 as f32) / 255.0, filled once per CTA (visible after the loop's first barrier)
     fill_u8_table(u8tab, threadIdx.x, TILE_THREADS);
+    const CtaTrace trace_(W, 8u);
     pdl_prologue();
     // The first item of a CTA is its own index; the cursor (in a cache line of its own: a load that shares
     // a line with a contended atomic queues behind it) hands out the rest.

@@ -24,6 +24,7 @@
 
 namespace drawb200 {
 int g_pdl_enabled = 1;
+int g_kernel_priority_set = 0, g_kernel_priority = 0;
 extern unsigned g_clip_ctas; // k_geometry.cu
 extern unsigned g_bin_ctas;  // k_binning.cu
 extern unsigned g_raster_ctas; // k_raster.cu
@@ -188,13 +189,18 @@ struct draw_scene {
         cudaEvent_t canvas_ready = nullptr; // canvas stream: the canvas of the frame using this set may be written
         cudaEvent_t clear_done = nullptr; // aux stream: k_clear_empty has finished
         cudaEvent_t frame_done = nullptr; // the whole frame using this set has finished
+        cudaEvent_t status_done = nullptr; // aux stream: the frame's counters have been copied to the host
         bool frame_pending = false;
+        bool status_pending = false;
     };
     static constexpr int MAX_WORK_SETS = 8;
     WorkSet sets[MAX_WORK_SETS];
     int n_sets = 4;
     int next_set = 0, last_set = 0;
     bool debug_tile_cycles = false;
+    DevBuf<uint4> d_trace;        // debug timeline (draw_scene_debug_trace), shared by the work sets
+    DevBuf<uint32_t> d_trace_count;
+    bool debug_trace = false;
     size_t rec_cap = 0, refs_cap = 0;
     // optional per-kernel timing (draw_scene_set_kernel_timing): 0..6 around the six side-stream kernels,
     // 7 / 8 around k_tile on the canvas stream
@@ -221,6 +227,8 @@ struct draw_canvas {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     size_t stripe_y0 = 0, stripe_y1 = 0; // rows; y1 == 0 means whole canvas
     uint32_t *h_status = nullptr;        // pinned: counters of the last frame
+    cudaEvent_t status_done = nullptr;   // the copy of the last frame's counters into h_status has landed
+    cudaEvent_t join_event = nullptr;    // draw_canvas_stream_wait
     bool frame_pending = false;
     draw_scene *last_scene = nullptr;
     draw_frame_stats stats{};
@@ -254,6 +262,8 @@ struct Config {
     int clip_ctas = std::max(1, env_int("DRAW_B200_CLIP_CTAS", 148 * 2));
     int bin_ctas = std::max(1, env_int("DRAW_B200_BIN_CTAS", 148 * 4));
     int raster_ctas = std::max(1, env_int("DRAW_B200_RASTER_CTAS", 148 * 8));
+    int cost_shade = std::max(0, env_int("DRAW_B200_COST_SHADE", 0)); // k_alloc: cost of shading a covered tile (0: not counted)
+    int kprio = env_int("DRAW_B200_KPRIO", 0); // 1: geometry / binning / k_raster launches get a higher priority than k_tile and k_clear_empty; 2: the reverse
     int skip = env_int("DRAW_B200_SKIP", 0); // timing experiments only: bit i set = kernel i of the frame is not launched (frames are then wrong)
     int clear_in_tile = env_int("DRAW_B200_CLEAR_IN_TILE", 0); // empty tiles written by k_tile's CTAs instead of k_clear_empty
 };
@@ -441,11 +451,21 @@ int ensure_work_buffers(draw_scene *s, draw_scene::WorkSet &ws, size_t n_lists) 
         TRY(ws.tile_cycles.reserve(n_lists));
         w.tile_cycles = ws.tile_cycles.ptr;
     }
+    w.trace = nullptr;
+    w.trace_count = nullptr;
+    w.trace_cap = 0;
+    w.trace_tag = (uint32_t)(&ws - s->sets);
+    if (s->debug_trace) {
+        w.trace = s->d_trace.ptr;
+        w.trace_count = s->d_trace_count.ptr;
+        w.trace_cap = (uint32_t)s->d_trace.cap;
+    }
     if (!ws.alloc_done) CU(cudaEventCreateWithFlags(&ws.alloc_done, cudaEventDisableTiming));
     if (!ws.geo_done) CU(cudaEventCreateWithFlags(&ws.geo_done, cudaEventDisableTiming));
     if (!ws.canvas_ready) CU(cudaEventCreateWithFlags(&ws.canvas_ready, cudaEventDisableTiming));
     if (!ws.clear_done) CU(cudaEventCreateWithFlags(&ws.clear_done, cudaEventDisableTiming));
     if (!ws.frame_done) CU(cudaEventCreateWithFlags(&ws.frame_done, cudaEventDisableTiming));
+    if (!ws.status_done) CU(cudaEventCreateWithFlags(&ws.status_done, cudaEventDisableTiming));
     return DRAW_OK;
 }
 
@@ -490,6 +510,11 @@ int launch_frame(draw_scene *s, draw_scene::WorkSet &ws, const FrameUniforms &U,
     if (s->dev.n_transparent)
         launch_sort_transparent(dU, s->dev, s->d_sort_ranges.ptr, (uint32_t)s->transparent_ranges.size(), s->d_sort_keys[0].ptr,
                                 s->d_sort_keys[1].ptr, s->d_sort_perm[0].ptr, s->d_sort_perm[1].ptr, s->d_sort_tmp.ptr, side);
+    int prio_least = 0, prio_greatest = 0;
+    if (g_cfg.kprio) cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    const int prio_chain = g_cfg.kprio == 1 ? prio_greatest : prio_least, prio_tile = g_cfg.kprio == 1 ? prio_least : prio_greatest;
+    g_kernel_priority_set = g_cfg.kprio != 0;
+    g_kernel_priority = prio_chain;
     if (ev) cudaEventRecord(ev[0], side);
     if (!(g_cfg.skip & 1)) launch_vertex(U, dU, s->dev, ws.work, side);
     if (ev) cudaEventRecord(ev[1], side);
@@ -509,6 +534,7 @@ int launch_frame(draw_scene *s, draw_scene::WorkSet &ws, const FrameUniforms &U,
         CU(cudaStreamWaitEvent(ws.aux_stream, ws.alloc_done, 0));
         CU(cudaStreamWaitEvent(ws.aux_stream, ws.canvas_ready, ext));
         if (ev) cudaEventRecord(ev[N_FRAME_KERNELS - 1], ws.aux_stream);
+        g_kernel_priority = prio_tile;
         if (!(g_cfg.skip & 128)) launch_clear_empty(U, dU, ws.work, ws.aux_stream);
         if (ev) cudaEventRecord(ev[N_FRAME_KERNELS], ws.aux_stream);
         CU(cudaEventRecord(ws.clear_done, ws.aux_stream));
@@ -516,6 +542,7 @@ int launch_frame(draw_scene *s, draw_scene::WorkSet &ws, const FrameUniforms &U,
         cudaEventRecord(ev[N_FRAME_KERNELS - 1], side);
         cudaEventRecord(ev[N_FRAME_KERNELS], side);
     }
+    g_kernel_priority = prio_chain;
     if (!(g_cfg.skip & 32)) launch_bin_fill(U, dU, ws.work, side);
     if (ev) cudaEventRecord(ev[6], side);
     if (!(g_cfg.skip & 64)) launch_raster(U, dU, ws.work, side);
@@ -523,10 +550,12 @@ int launch_frame(draw_scene *s, draw_scene::WorkSet &ws, const FrameUniforms &U,
     CU(cudaEventRecord(ws.geo_done, side));
     CU(cudaStreamWaitEvent(side, ws.canvas_ready, ext));
     if (ev) cudaEventRecord(ev[N_FRAME_KERNELS + 1], side);
+    g_kernel_priority = prio_tile;
     if (!(g_cfg.skip & 256)) launch_tile(U, dU, s->dev, ws.work, side);
     if (ev) cudaEventRecord(ev[N_FRAME_KERNELS + 2], side);
     if (!(g_cfg.skip & 512)) launch_shade(U, dU, s->dev, ws.work, side);
     if (ev) cudaEventRecord(ev[N_FRAME_KERNELS + 3], side);
+    g_kernel_priority_set = 0;
     if (!U.clear_in_tile) CU(cudaStreamWaitEvent(side, ws.clear_done, 0));
     return DRAW_OK;
 }
@@ -593,6 +622,7 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     U.defer_max = (uint32_t)g_cfg.defer_max;
     U.clear_in_tile = (uint32_t)g_cfg.clear_in_tile;
     U.bin_records_per_warp = (uint32_t)g_cfg.bin_rpw;
+    U.cost_shade = (uint32_t)g_cfg.cost_shade;
     g_clip_ctas = (unsigned)g_cfg.clip_ctas;
     g_bin_ctas = (unsigned)g_cfg.bin_ctas;
     g_raster_ctas = (unsigned)g_cfg.raster_ctas;
@@ -623,6 +653,7 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     cudaStream_t side = ws.stream, st = c->stream;
     if (ws.frame_pending) CU(cudaEventSynchronize(ws.frame_done)); // the pinned uniforms of the set are about to be rewritten
     *ws.h_uniforms = U;
+    if (ws.status_pending) CU(cudaStreamWaitEvent(side, ws.status_done, 0)); // k_vertex resets the counters that copy reads
     // what the canvas stream still does with the canvas comes before the two kernels that write it
     // (k_clear_empty, k_tile wait for this event; the geometry chain does not touch the canvas and does not wait)
     CU(cudaEventRecord(ws.canvas_ready, st));
@@ -679,7 +710,14 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     CU(cudaStreamWaitEvent(st, ws.frame_done, 0));
     s->launches += 5 + (s->dev.n_triangles ? 2 : 0) + (s->dev.n_transparent ? 1 : 0) + (U.tile_y_end > U.tile_y_begin ? (U.defer_max ? 3 : 2) - (U.clear_in_tile ? 1 : 0) : 0);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(c->h_status, ws.work.counters, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    // The frame's counters go to the host on the set's auxiliary stream, not on the canvas' stream: when
+    // several canvases share a stream the next frame's canvas_ready would otherwise sit behind this copy.
+    CU(cudaStreamWaitEvent(ws.aux_stream, ws.frame_done, 0));
+    CU(cudaMemcpyAsync(c->h_status, ws.work.counters, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ws.aux_stream));
+    if (!c->status_done) CU(cudaEventCreateWithFlags(&c->status_done, cudaEventDisableTiming));
+    CU(cudaEventRecord(c->status_done, ws.aux_stream));
+    CU(cudaEventRecord(ws.status_done, ws.aux_stream));
+    ws.status_pending = true;
     c->frame_pending = true;
     c->host_dirty = true;
     c->last_scene = s;
@@ -698,6 +736,7 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
 int finish_frame(draw_canvas *c) {
     TRY(ensure_device(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    if (c->status_done) CU(cudaEventSynchronize(c->status_done));
     int guard = 0;
     while (c->frame_pending) {
         c->frame_pending = false;
@@ -727,6 +766,7 @@ int finish_frame(draw_canvas *c) {
         CU(cudaDeviceSynchronize()); // both work sets are about to be reallocated
         TRY(enqueue_frame(s, c));
         CU(cudaStreamSynchronize(c->stream));
+        CU(cudaEventSynchronize(c->status_done));
     }
     return DRAW_OK;
 }
@@ -827,6 +867,7 @@ void draw_scene_destroy(draw_scene *scene) {
             if (ws.canvas_ready) cudaEventDestroy(ws.canvas_ready);
             if (ws.clear_done) cudaEventDestroy(ws.clear_done);
             if (ws.frame_done) cudaEventDestroy(ws.frame_done);
+            if (ws.status_done) cudaEventDestroy(ws.status_done);
         }
     }
     delete scene;
@@ -1065,6 +1106,31 @@ int draw_scene_debug_tile_cycles(draw_scene *scene, draw_canvas *canvas, int ena
     GUARD_END
 }
 
+int draw_scene_debug_trace(draw_scene *scene, int enable, uint32_t *out, size_t cap_records, size_t *n_records) {
+    GUARD_BEGIN
+    if (!scene) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    TRY(ensure_device(scene->device));
+    CU(cudaDeviceSynchronize());
+    if (out && n_records) {
+        *n_records = 0;
+        if (scene->d_trace_count.ptr) {
+            uint32_t n = 0;
+            CU(cudaMemcpy(&n, scene->d_trace_count.ptr, sizeof n, cudaMemcpyDeviceToHost));
+            const size_t m = std::min<size_t>({(size_t)n, scene->d_trace.cap, cap_records});
+            if (m) CU(cudaMemcpy(out, scene->d_trace.ptr, m * sizeof(uint4), cudaMemcpyDeviceToHost));
+            *n_records = m;
+        }
+    }
+    scene->debug_trace = enable != 0;
+    if (enable) {
+        TRY(scene->d_trace.reserve(1u << 18));
+        TRY(scene->d_trace_count.reserve(1));
+        CU(cudaMemset(scene->d_trace_count.ptr, 0, sizeof(uint32_t)));
+    }
+    return DRAW_OK;
+    GUARD_END
+}
+
 int draw_scene_debug_list_counts(draw_scene *scene, draw_canvas *canvas, uint32_t *out, size_t n, size_t *n_coarse) {
     GUARD_BEGIN
     if (!scene || !canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
@@ -1118,6 +1184,11 @@ void draw_canvas_destroy(draw_canvas *canvas) {
     if (cudaGetDevice(&cur) == cudaSuccess) {
         if (cur != canvas->device) cudaSetDevice(canvas->device);
         if (canvas->stream) cudaStreamSynchronize(canvas->stream);
+        if (canvas->status_done) {
+            cudaEventSynchronize(canvas->status_done); // the copy into h_status
+            cudaEventDestroy(canvas->status_done);
+        }
+        if (canvas->join_event) cudaEventDestroy(canvas->join_event);
         if (canvas->own_stream) cudaStreamDestroy(canvas->own_stream);
         if (canvas->h_color) cudaFreeHost(canvas->h_color);
         if (canvas->h_status) cudaFreeHost(canvas->h_status);
@@ -1313,6 +1384,19 @@ int draw_canvas_set_stream(draw_canvas *canvas, void *cuda_stream) {
     if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas is NULL");
     TRY(finish_frame(canvas));
     canvas->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : canvas->own_stream;
+    return DRAW_OK;
+    GUARD_END
+}
+
+int draw_canvas_stream_wait(draw_canvas *canvas, void *cuda_stream) {
+    GUARD_BEGIN
+    if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas is NULL");
+    TRY(ensure_device(canvas->device));
+    cudaStream_t waiter = static_cast<cudaStream_t>(cuda_stream);
+    if (waiter == canvas->stream) return DRAW_OK; // already ordered
+    if (!canvas->join_event) CU(cudaEventCreateWithFlags(&canvas->join_event, cudaEventDisableTiming));
+    CU(cudaEventRecord(canvas->join_event, canvas->stream));
+    CU(cudaStreamWaitEvent(waiter, canvas->join_event, 0));
     return DRAW_OK;
     GUARD_END
 }

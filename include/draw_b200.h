@@ -156,6 +156,11 @@ int draw_scene_debug_list_counts(draw_scene *scene, draw_canvas *canvas, uint32_
 /* Debug tap: enable != 0 makes later frames record the SM cycles each coarse tile's CTA spent in
  * k_tile; out (n = number of coarse tiles) receives the last frame's values, or NULL to only toggle. */
 int draw_scene_debug_tile_cycles(draw_scene *scene, draw_canvas *canvas, int enable, uint32_t *out, size_t n);
+/* Debug timeline: while enabled, thread 0 of every CTA of the frame kernels appends one record of four
+ * uint32 (kernel id | SM << 8 | work set << 24, CTA index, start ns, end ns; low 32 bits of the GPU's global
+ * timer).  A call first copies up to cap_records records gathered so far into out (if not NULL), then
+ * enables or disables recording and empties the buffer.  Waits for the device. */
+int draw_scene_debug_trace(draw_scene *scene, int enable, uint32_t *out, size_t cap_records, size_t *n_records);
 
 /* ---- Canvas (canvas.rs) -------------------------------------------------------------- */
 /* Canvas::new(width, height) :366 — colour BGRA8 (Pixel, :51-59), black; no depth yet. */
@@ -192,6 +197,10 @@ int draw_canvas_device_ptrs(draw_canvas *canvas, void **out_color, void **out_de
 int draw_canvas_bind_external(draw_canvas *canvas, void *color_dev, void *depth_dev);
 /* Enqueue on an existing CUDA stream (a cudaStream_t passed as void*); NULL = own stream. */
 int draw_canvas_set_stream(draw_canvas *canvas, void *cuda_stream);
+/* Device-side join: makes cuda_stream (a cudaStream_t passed as void*) wait for everything enqueued so far
+ * for this canvas (its last render included) without blocking the host.  Lets canvases render on their own
+ * streams — frames on different canvases then overlap — while a caller's stream consumes or times them. */
+int draw_canvas_stream_wait(draw_canvas *canvas, void *cuda_stream);
 /* Sort-first partition: render only canvas rows y in [y0, y1) (canvas y = depth-buffer row;
  * colour row = height-1-y).  Rows outside are left untouched.  (0, height) = whole frame.
  * y0 and y1 must be multiples of the tile height (draw_tile_size, 32) or equal to height. */
