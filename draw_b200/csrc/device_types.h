@@ -30,7 +30,7 @@ constexpr int LISTS_PER_TILE = 3;
 constexpr uint32_t NO_SLOT = 0xFFFFFFFFu, NO_PAGE = 0xFFFFFFFFu;
 constexpr unsigned long long KEY_EMPTY = ~0ull;
 #ifndef DRAW_TILE_THREADS
-#define DRAW_TILE_THREADS 512
+#define DRAW_TILE_THREADS 256
 #endif
 constexpr int TILE_THREADS = DRAW_TILE_THREADS;
 // k_tile phase A geometry: a warp owns a REGION x REGION_H rectangle (4 lanes across, 8 down), a lane

@@ -306,26 +306,32 @@ __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const FrameUniforms *__
     const uint32_t max_split = U.split_max;
     const bool list_empties = U.has_transparent == 0; // else every tile runs the full path (cost 0, last bucket)
     constexpr int BATCH = 8; // independent loads in flight per thread
-    for (uint32_t t0 = tid; t0 < nc; t0 += ALLOC_THREADS * BATCH) {
+    for (uint32_t base = 0; base < nc; base += ALLOC_THREADS * BATCH) { // warp-uniform trip count: ballots below
         uint32_t cost_k[BATCH];
 #pragma unroll
         for (int k = 0; k < BATCH; k++) {
-            const uint32_t t = t0 + k * ALLOC_THREADS;
+            const uint32_t t = base + tid + k * ALLOC_THREADS;
             cost_k[k] = t < nc ? __ldcg(&W.tile_cost[t]) : COST_NOT_IN_STRIPE;
         }
 #pragma unroll
-        for (int k = 0; k < BATCH; k++)
-            if (cost_k[k] != COST_NOT_IN_STRIPE) {
-                const uint32_t kind = cost_k[k] >> TILE_KIND_SHIFT, cost = cost_k[k] & (TILE_KIND_SHIFTED - 1u);
-                if (kind == TILE_KIND_EMPTY && list_empties) { // listed on its own: k_clear_empty writes it
-                    const uint32_t t = t0 + k * ALLOC_THREADS;
-                    W.empty_tiles[atomicAdd(&n_empty, 1u)] = (t % U.tiles_x) | (t / U.tiles_x) << 10;
-                    continue;
-                }
-                if (kind == TILE_KIND_RASTER_ONLY) continue; // k_raster + k_shade do it all
-                const uint32_t s = tile_splits(cost, target, max_split);
-                atomicAdd(&bucket_start[cost_bucket(cost / s)], s);
+        for (int k = 0; k < BATCH; k++) {
+            const uint32_t t = base + tid + k * ALLOC_THREADS;
+            const bool in = cost_k[k] != COST_NOT_IN_STRIPE;
+            const uint32_t kind = cost_k[k] >> TILE_KIND_SHIFT, cost = cost_k[k] & (TILE_KIND_SHIFTED - 1u);
+            // empty tiles are listed on their own (k_clear_empty writes them): most of the frame's tiles, so one
+            // shared-memory atomic per warp, not per tile
+            const bool empty = in && kind == TILE_KIND_EMPTY && list_empties;
+            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, empty);
+            if (ballot) {
+                uint32_t wbase = 0;
+                if (lane == 0) wbase = atomicAdd(&n_empty, (uint32_t)__popc(ballot));
+                wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+                if (empty) W.empty_tiles[wbase + __popc(ballot & ((1u << lane) - 1u))] = (t % U.tiles_x) | (t / U.tiles_x) << 10;
             }
+            if (!in || empty || kind == TILE_KIND_RASTER_ONLY) continue; // raster-only: k_raster + k_shade do it all
+            const uint32_t s = tile_splits(cost, target, max_split);
+            atomicAdd(&bucket_start[cost_bucket(cost / s)], s);
+        }
     }
     __syncthreads();
     if (tid == 0) {

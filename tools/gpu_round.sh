@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call: parity tests, bench lines, launch list, ncu full captures.  Outputs under gpurun_out/.
 mkdir -p gpurun_out
-T=${TAG:-r01b}
+T=${TAG:-r01c}
 ( timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 ) > gpurun_out/${T}_pytest.log
 timeout 300 python bench.py > gpurun_out/${T}_bench_c3.json 2> gpurun_out/${T}_bench_c3.err
 for c in c2 c4 c5; do timeout 300 python bench.py --config $c --no-cpu > gpurun_out/${T}_bench_$c.json 2> gpurun_out/${T}_bench_$c.err; done
