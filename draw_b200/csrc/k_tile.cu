@@ -1,11 +1,11 @@
 // k_tile.cu — per-tile raster / depth / shade kernel (mororo18/draw canvas.rs:577-750, 906-960).
 //
-// One CTA (512 threads) per 64x32-pixel tile.  The tile's depth, winning record and colour stay on
+// One CTA (TILE_THREADS = 256 threads) per 64x32-pixel tile or pixel window of one (persistent CTAs, k_alloc's work list).  The tile's depth, winning record and colour stay on
 // chip (registers, then shared memory) for the whole kernel; colour and depth go to HBM exactly
 // once at the end, with the clear fused in.  No tensor cores: nothing here is a contraction.
 //
 //   phase A  "large" list: triangles are staged through shared memory 64 at a time; every lane owns
-//            a 4x1 pixel block (warp = 16x8 region) and tests it against each triangle, after a
+//            a 4 x BLK_H pixel block (warp = REGION x REGION_H region) and tests it against each triangle, after a
 //            warp-level bbox reject and an exact block-level edge reject.  Depth/winner in registers.
 //   merge    each lane publishes its 8 pixels as 64-bit keys (depth, slot) in shared memory.
 //   phase B  "medium" list (bbox in the tile <= 1024 px): a coarse pass tests every 8x4 block of every
@@ -48,7 +48,7 @@ static_assert(PREP_WORDS == 28 && (STAGE_STRIDE & 1) == 1 && offsetof(PrepRec, x
               offsetof(PrepRec, flags) == 4 * S_FLAGS && offsetof(PrepRec, slot) == 4 * S_SLOT, "PrepRec layout");
 
 // Copies n prepared records into shared memory: one 16-byte load per thread (8 threads per record, the
-// eighth idle), so a chunk of 64 is a single load per thread of a 512-thread CTA.
+// eighth idle), so a chunk of 64 is two loads per thread of a 256-thread CTA.
 __device__ __forceinline__ void stage_copy(float (*staged)[STAGE_STRIDE], const PrepRec *__restrict__ prep,
                                            const uint32_t *refs, uint32_t ref_stride, uint32_t n, int tid) {
     for (uint32_t i = (uint32_t)tid; i < n * 8u; i += TILE_THREADS) {
