@@ -403,10 +403,11 @@ def run_ours(args, cfg):
         st = ring[0].last_frame_stats()
         tile_px = draw_b200.tile_size() * 64
         clear_bytes = min(8 * W * H, 8 * tile_px * st["empty_tiles"])  # border tiles counted whole: slight over-count
-        tile_bytes = 8 * W * H - clear_bytes + cfg["tex_bytes"]
+        fused_clear = bool(st.get("clear_in_tile"))  # k_tile's CTAs write the empty tiles too: it owns the whole frame
+        tile_bytes = 8 * W * H - (0 if fused_clear else clear_bytes) + cfg["tex_bytes"]
         t_tile = kmean["k_tile"] * 1e-3
         achieved = tile_bytes / t_tile / 1e9
-        clear_gbs = clear_bytes / (kmean["k_clear_empty"] * 1e-3) / 1e9
+        clear_gbs = None if fused_clear else clear_bytes / (kmean["k_clear_empty"] * 1e-3) / 1e9
         frame_gbs = cfg["algo_bytes_frame"] / (ms_total * 1e-3 / args.steps) / 1e9
         line = {
             "metric": "frames/s at 3840x2160 (Phong+texture)", "value": fps, "unit": "frames/s",
@@ -431,14 +432,18 @@ def run_ours(args, cfg):
             "roofline": {"bound": "hbm", "kernel": "k_tile", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic("k_tile", args.config), "peak_source": peak_src,
                          "algo_bytes_per_launch": tile_bytes,
-                         "note": "k_tile is the longest kernel of the frame; it writes the non-empty tiles (8 B/pixel) and "
-                                 "reads the bound textures. k_clear_empty (under `clear`) writes the empty tiles and is the "
-                                 "frame's HBM-heavy kernel; a write-only stream reaches about half of the copy peak on "
-                                 "this part (a 66 MB device fill measures 3.1 TB/s). `frame_*` = SURVEY.md 8(d) "
-                                 "ALGO_BYTES(frame) / time per frame of the timed region",
-                         "clear": {"kernel": "k_clear_empty", "achieved": clear_gbs, "frac": clear_gbs / peak,
-                                   "algo_bytes_per_launch": clear_bytes, "empty_tiles": st["empty_tiles"],
-                                   "traffic": ncu_traffic("k_clear_empty", args.config)},
+                         "note": ("k_tile writes the whole frame once — 8 B/pixel: the rasterised tiles from shared memory, the "
+                                  "empty tiles as streaming stores between its raster items — and reads the bound textures; "
+                                  if fused_clear else
+                                  "k_tile writes the non-empty tiles (8 B/pixel) and reads the bound textures; k_clear_empty "
+                                  "(under `clear`) writes the empty tiles; ") +
+                                 "its duration is event-timed with the frame's kernels run one after the other. `frame_*` = "
+                                 "SURVEY.md 8(d) ALGO_BYTES(frame) / time per frame of the timed region (frames overlapped)",
+                         "clear": None if fused_clear else {
+                             "kernel": "k_clear_empty", "achieved": clear_gbs, "frac": clear_gbs / peak,
+                             "algo_bytes_per_launch": clear_bytes, "empty_tiles": st["empty_tiles"],
+                             "traffic": ncu_traffic("k_clear_empty", args.config)},
+                         "empty_tiles": st["empty_tiles"],
                          "frame_algo_bytes": cfg["algo_bytes_frame"], "frame_achieved": frame_gbs,
                          "frame_frac": frame_gbs / peak},
         }

@@ -44,11 +44,11 @@ class ObjectDesc(C.Structure):
 class FrameStats(C.Structure):
     _fields_ = [("input_triangles", C.c_uint32), ("setup_records", C.c_uint32), ("tile_refs", C.c_uint32),
                 ("transparent_slots", C.c_uint32), ("overflow", C.c_uint32), ("empty_tiles", C.c_uint32),
-                ("key_pages", C.c_uint32), ("reserved", C.c_uint32 * 1)]
+                ("key_pages", C.c_uint32), ("clear_in_tile", C.c_uint32)]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n in ("input_triangles", "setup_records", "tile_refs",
-                                                   "transparent_slots", "overflow", "empty_tiles", "key_pages")}
+                                                   "transparent_slots", "overflow", "empty_tiles", "key_pages", "clear_in_tile")}
 
 
 IMAGE_LOADER = C.CFUNCTYPE(C.c_int, C.c_char_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32),

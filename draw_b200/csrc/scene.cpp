@@ -253,19 +253,21 @@ struct Config {
     int sets = std::min(std::max(env_int("DRAW_B200_SETS", 6), 1), 8); // frames in flight per scene
     int pages = std::max(0, env_int("DRAW_B200_PAGES", 16384));        // key pages per work set (0: k_raster off)
     int clear_ctas = std::max(1, env_int("DRAW_B200_CLEAR_CTAS", 148 * 4));
-    int tile_ctas = std::max(1, env_int("DRAW_B200_TILE_CTAS", 148 * (1024 / TILE_THREADS)));
+    int tile_ctas = std::max(1, env_int("DRAW_B200_TILE_CTAS", 148 * 3)); // persistent CTAs of k_tile: three per SM leave room for the other frames' kernels
     int split_min_cost = std::max(1, env_int("DRAW_B200_SPLIT_MIN_COST", TILE_SPLIT_MIN_COST));
     int split_div = std::min(std::max(1, env_int("DRAW_B200_SPLIT_DIV", TILE_SPLIT_DIV)), (int)TILE_EXTRA_ITEMS);
     int defer_max = std::max(0, env_int("DRAW_B200_DEFER_MAX", 0));  // k_shade takes tiles with fewer large references (0: off)
     int split_max = std::min(std::max(1, env_int("DRAW_B200_SPLIT_MAX", TILE_MAX_SPLIT)), (int)TILE_MAX_SPLIT);
     int bin_rpw = std::max(0, env_int("DRAW_B200_BIN_RPW", 8));   // k_bin: warp-per-record up to this many records per warp of the grid
-    int clip_ctas = std::max(1, env_int("DRAW_B200_CLIP_CTAS", 148 * 2));
-    int bin_ctas = std::max(1, env_int("DRAW_B200_BIN_CTAS", 148 * 4));
-    int raster_ctas = std::max(1, env_int("DRAW_B200_RASTER_CTAS", 148 * 8));
+    // grids of the geometry / binning kernels; 0 = by scene size (enqueue_frame): with several frames in flight a
+    // kernel costs the pipeline its CTAs' residency, so small scenes get small grids
+    int clip_ctas = std::max(0, env_int("DRAW_B200_CLIP_CTAS", 0));
+    int bin_ctas = std::max(0, env_int("DRAW_B200_BIN_CTAS", 0));
+    int raster_ctas = std::max(0, env_int("DRAW_B200_RASTER_CTAS", 0));
     int cost_shade = std::max(0, env_int("DRAW_B200_COST_SHADE", 0)); // k_alloc: cost of shading a covered tile (0: not counted)
     int kprio = env_int("DRAW_B200_KPRIO", 0); // 1: geometry / binning / k_raster launches get a higher priority than k_tile and k_clear_empty; 2: the reverse
     int skip = env_int("DRAW_B200_SKIP", 0); // timing experiments only: bit i set = kernel i of the frame is not launched (frames are then wrong)
-    int clear_in_tile = env_int("DRAW_B200_CLEAR_IN_TILE", 0); // empty tiles written by k_tile's CTAs instead of k_clear_empty
+    int clear_in_tile = env_int("DRAW_B200_CLEAR_IN_TILE", 2); // who writes the empty tiles: 0 k_clear_empty on its own stream; k_tile's CTAs 1 before / 2 after each raster item, 3 alternating
 };
 const Config g_cfg;
 
@@ -623,9 +625,10 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     U.clear_in_tile = (uint32_t)g_cfg.clear_in_tile;
     U.bin_records_per_warp = (uint32_t)g_cfg.bin_rpw;
     U.cost_shade = (uint32_t)g_cfg.cost_shade;
-    g_clip_ctas = (unsigned)g_cfg.clip_ctas;
-    g_bin_ctas = (unsigned)g_cfg.bin_ctas;
-    g_raster_ctas = (unsigned)g_cfg.raster_ctas;
+    const bool small_scene = s->dev.n_triangles <= 200000u;
+    g_clip_ctas = g_cfg.clip_ctas ? (unsigned)g_cfg.clip_ctas : (small_scene ? 74u : 296u);
+    g_bin_ctas = g_cfg.bin_ctas ? (unsigned)g_cfg.bin_ctas : (small_scene ? 296u : 592u);
+    g_raster_ctas = g_cfg.raster_ctas ? (unsigned)g_cfg.raster_ctas : (small_scene ? 592u : 1184u);
     const size_t y0 = c->stripe_y1 ? c->stripe_y0 : 0, y1 = c->stripe_y1 ? c->stripe_y1 : c->height;
     U.tile_y_begin = (uint32_t)(y0 / TILE_H);
     U.tile_y_end = (uint32_t)((y1 + TILE_H - 1) / TILE_H);
@@ -751,6 +754,7 @@ int finish_frame(draw_canvas *c) {
         c->stats.tile_refs = n_refs;
         c->stats.empty_tiles = c->h_status[13];
         c->stats.key_pages = c->h_status[11];
+        c->stats.clear_in_tile = (uint32_t)g_cfg.clear_in_tile;
         if (alive) {
             c->stats.input_triangles = s->dev.n_triangles;
             c->stats.transparent_slots = s->dev.n_transparent * 4;

@@ -97,9 +97,9 @@ typedef struct draw_frame_stats {
     uint32_t tile_refs;         /* (tile, triangle) pairs produced by binning */
     uint32_t transparent_slots; /* slots scanned by the ordered transparent pass */
     uint32_t overflow;          /* non-zero: a device buffer was too small, frame was re-rendered */
-    uint32_t empty_tiles;       /* tiles of the stripe nothing was binned to (written by k_clear_empty) */
+    uint32_t empty_tiles;       /* tiles of the stripe nothing was binned to (they only get the clear colour and depth) */
     uint32_t key_pages;         /* tiles whose medium / small triangles k_raster rasterised into a key page */
-    uint32_t reserved[1];
+    uint32_t clear_in_tile;     /* non-zero: k_tile's CTAs wrote the empty tiles between their items; 0: k_clear_empty did */
 } draw_frame_stats;
 
 /* ---- library ------------------------------------------------------------------------ */

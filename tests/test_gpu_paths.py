@@ -8,6 +8,9 @@ variant runs a subset of the parity tests in a fresh interpreter:
   DRAW_B200_DEFER_MAX=16   k_shade resolves the key pages of tiles with few large triangles
   DRAW_B200_GRAPH=0        direct kernel launches instead of graph replay (PDL between the kernels)
   DRAW_B200_SPLIT_MAX=1    no tile windows
+  DRAW_B200_CLEAR_IN_TILE=0  the empty tiles are written by k_clear_empty on its own stream (default: by k_tile's
+                             CTAs after each raster item, mode 2; 1 = before the item, 3 = alternating)
+  DRAW_B200_BIN_RPW=0      k_bin always in thread-per-record mode (default: warp per record for small scenes)
 """
 import os
 import subprocess
@@ -23,8 +26,11 @@ SUBSET = "c2 or c3 or c1_textured or clipping or odd or ties or degenerate or st
 
 
 @pytest.mark.parametrize("env", [{"DRAW_B200_PAGES": "0"}, {"DRAW_B200_DEFER_MAX": "16"}, {"DRAW_B200_GRAPH": "0"},
-                                 {"DRAW_B200_SPLIT_MAX": "1", "DRAW_B200_DEFER_MAX": "1"}],
-                         ids=["no_pages", "k_shade", "no_graph", "no_windows_raster_only_deferred"])
+                                 {"DRAW_B200_SPLIT_MAX": "1", "DRAW_B200_DEFER_MAX": "1"},
+                                 {"DRAW_B200_CLEAR_IN_TILE": "0", "DRAW_B200_BIN_RPW": "0"},
+                                 {"DRAW_B200_CLEAR_IN_TILE": "3", "DRAW_B200_TILE_CTAS": "37", "DRAW_B200_SETS": "2"}],
+                         ids=["no_pages", "k_shade", "no_graph", "no_windows_raster_only_deferred", "k_clear_empty_thread_bin",
+                              "clear_alternating_few_ctas"])
 def test_alternative_paths_are_bit_exact(env):
     e = dict(os.environ)
     e.update(env)
