@@ -82,6 +82,22 @@ def load_workload(name):
     return cfg
 
 
+def fill_roofline(config, frame_seconds, sm_mhz):
+    """SURVEY.md §8(d), secondary bound (binds the overdraw-heavy C4): ALGO_FLOP(frame) = 23 F_cov + 101 P_vis against
+    the non-FMA FP32 peak, SMs x 128 lanes x clock.  F_cov / P_vis are counted by the CPU oracle offline
+    (tools/make_fill_counts.py -> tests/golden/fill_counts.json); nothing is counted inside the timed region."""
+    try:
+        fc = json.load(open(os.path.join(GOLDEN, "fill_counts.json")))[config]
+    except Exception:
+        return None
+    flop = 23.0 * fc["f_cov_mean"] + 101.0 * fc["p_vis_mean"]
+    peak = 148 * 128 * (sm_mhz or 1965.0) * 1e6 / 1e12
+    achieved = flop / frame_seconds / 1e12
+    return {"bound": "fp32 without FMA (parity forbids contraction)", "algo_flop_per_frame": flop, "f_cov": fc["f_cov_mean"],
+            "p_vis": fc["p_vis_mean"], "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": "148 SMs x 128 lanes x SM clock under load"}
+
+
 def ncu_traffic(kernel, config):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
@@ -445,7 +461,8 @@ def run_ours(args, cfg):
                              "traffic": ncu_traffic("k_clear_empty", args.config)},
                          "empty_tiles": st["empty_tiles"],
                          "frame_algo_bytes": cfg["algo_bytes_frame"], "frame_achieved": frame_gbs,
-                         "frame_frac": frame_gbs / peak},
+                         "frame_frac": frame_gbs / peak,
+                         "fill": fill_roofline(args.config, ms_total * 1e-3 / args.steps, (clocks or {}).get("sm_mhz"))},
         }
         if sort_first is not None:
             line["sort_first"] = sort_first
