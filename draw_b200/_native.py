@@ -103,6 +103,10 @@ SIGNATURES = {
     "draw_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "draw_ipc_close": (C.c_int, [C.c_void_p]),
     "draw_object_load_obj": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "draw_image_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "draw_image_free": (None, [C.c_void_p]),
+    "draw_image_loader_builtin": (C.c_int, [C.c_char_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32),
+                                            C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "draw_object_free": (None, [C.c_void_p]),
     "draw_object_desc_of": (C.c_int, [C.c_void_p, C.POINTER(ObjectDesc)]),
 }

@@ -318,6 +318,18 @@ def tile_size():
     return N.lib().draw_tile_size()
 
 
+def load_image(path):
+    """TextureMap::load_from_file (scene/mod.rs:174-202) through the library's own decoder (PNG only):
+    uint8 [height, width, components], components 3 or 4, row 0 = top."""
+    px, w, h, c = C.c_void_p(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+    N.check(N.lib().draw_image_load(str(path).encode(), C.byref(px), C.byref(w), C.byref(h), C.byref(c)))
+    try:
+        n = w.value * h.value * c.value
+        return np.ctypeslib.as_array(C.cast(px, C.POINTER(C.c_uint8)), shape=(n,)).copy().reshape(h.value, w.value, c.value)
+    finally:
+        N.lib().draw_image_free(px)
+
+
 def load_obj(path, decode_images=True):
     """Object::load_from_file (scene/object.rs:106) through the library's C++ loader
     (draw_object_load_obj).  Texture files named by the MTL are decoded with PIL when
@@ -328,6 +340,9 @@ def load_obj(path, decode_images=True):
     libc.malloc.argtypes = [C.c_size_t]
 
     def _decode(cpath, _user, out_pixels, out_w, out_h, out_comp):
+        # PNG: the library's own decoder; anything else (the airplane's JPEG): PIL stands in for stb_image
+        if N.lib().draw_image_loader_builtin(cpath, None, out_pixels, out_w, out_h, out_comp) == 0:
+            return 0
         try:
             from PIL import Image
             im = Image.open(cpath.decode())

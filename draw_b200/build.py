@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdraw_b200.so")
-SOURCES = ["k_geometry.cu", "k_binning.cu", "k_raster.cu", "k_tile.cu", "k_shade.cu", "k_sort.cu", "scene.cpp", "obj_loader.cpp"]
+SOURCES = ["k_geometry.cu", "k_binning.cu", "k_raster.cu", "k_tile.cu", "k_shade.cu", "k_sort.cu", "scene.cpp", "obj_loader.cpp", "image_decode.cpp"]
 HEADERS = ["device_types.h", "device_math.cuh", "shading.cuh", "host_math.hpp", os.path.join("..", "..", "include", "draw_b200.h")]
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
@@ -58,7 +58,7 @@ def build(force=False, verbose=False, defines=(), out=None):
             raise RuntimeError(f"nvcc failed on {src}")
         objs.append(obj)
     cmd = [nvcc_path(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
-           "-o", lib, *objs]
+           "-o", lib, *objs, "-lz"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:
         sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)

@@ -223,6 +223,15 @@ int draw_ipc_close(void *dev_ptr);
 typedef int (*draw_image_loader)(const char *path, void *user, uint8_t **out_pixels, uint32_t *out_w,
                                  uint32_t *out_h, uint32_t *out_components);
 int draw_object_load_obj(const char *path, draw_image_loader loader, void *user, draw_object **out);
+/* TextureMap::load_from_file (scene/mod.rs:174-202) for the lossless format among the reference's assets: decodes
+ * a PNG file (RGB, RGBA or palette; 8/16 bits; non-interlaced) to width*height*components bytes, components 3 or 4,
+ * row 0 = top — the bytes stb_image returns for the same file.  Other formats (JPEG is lossy and decoder-dependent)
+ * fail with DRAW_ERR_INVALID_ARGUMENT.  The buffer is malloc()ed; release it with draw_image_free. */
+int draw_image_load(const char *path, uint8_t **out_pixels, uint32_t *out_w, uint32_t *out_h, uint32_t *out_components);
+void draw_image_free(uint8_t *pixels);
+/* draw_image_load as a draw_image_loader callback (user is ignored), for draw_object_load_obj. */
+int draw_image_loader_builtin(const char *path, void *user, uint8_t **out_pixels, uint32_t *out_w, uint32_t *out_h,
+                              uint32_t *out_components);
 void draw_object_free(draw_object *obj);
 /* Borrow the loaded object as a desc (valid until draw_object_free). */
 int draw_object_desc_of(const draw_object *obj, draw_object_desc *out);
