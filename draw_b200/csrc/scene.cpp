@@ -195,7 +195,7 @@ struct draw_scene {
     };
     static constexpr int MAX_WORK_SETS = 8;
     WorkSet sets[MAX_WORK_SETS];
-    int n_sets = 6;
+    int n_sets = 8;
     int next_set = 0, last_set = 0;
     bool debug_tile_cycles = false;
     DevBuf<uint4> d_trace;        // debug timeline (draw_scene_debug_trace), shared by the work sets
@@ -250,7 +250,7 @@ struct Config {
     int graphs = env_int("DRAW_B200_GRAPH", 1);   // replay each frame as a CUDA graph
     int prio = env_int("DRAW_B200_PRIO", 0);      // work-set streams at the highest priority
     int pdl = env_int("DRAW_B200_PDL", 3);        // programmatic dependent launch: 0 off, 1 early trigger, 2 late, 3 early for a lone frame
-    int sets = std::min(std::max(env_int("DRAW_B200_SETS", 6), 1), 8); // frames in flight per scene
+    int sets = std::min(std::max(env_int("DRAW_B200_SETS", 8), 1), 8); // frames in flight per scene
     int pages = std::max(0, env_int("DRAW_B200_PAGES", 16384));        // key pages per work set (0: k_raster off)
     int clear_ctas = std::max(1, env_int("DRAW_B200_CLEAR_CTAS", 148 * 4));
     int tile_ctas = std::max(1, env_int("DRAW_B200_TILE_CTAS", 148 * 3)); // persistent CTAs of k_tile: three per SM leave room for the other frames' kernels
