@@ -89,6 +89,7 @@ struct FrameUniforms {
     uint32_t n_lists;                  // LISTS_PER_TILE * n_coarse: large, medium, small lists
     uint32_t split_min_cost, split_div, split_max; // k_alloc's tile splitting policy (defaults: TILE_SPLIT_*)
     uint32_t defer_max;                // tiles with a key page and fewer large references than this are shaded by k_shade
+    uint32_t *status_host;             // pinned host memory of the canvas (device-mapped): k_tile copies counters[0..15] there
     uint8_t *color;                    // the canvas: BGRA8, row 0 = top (canvas.rs:955-956)
     float *depth;                      // depth buffer, row 0 = y 0 (canvas.rs:413-423)
     uint32_t has_transparent;          // transparent triangles are not binned: no tile may take the empty-tile path

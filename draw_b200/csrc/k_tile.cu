@@ -769,6 +769,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(
     // The first item of a CTA is its own index; the cursor (in a cache line of its own: a load that shares
     // a line with a contended atomic queues behind it) hands out the rest.
     const bool usable = W.counters[2] == 0; // a work buffer overflowed: lists are unusable, the host re-renders
+    // The frame's counters (record / reference totals, overflow flags, statistics: final since k_alloc) go to the
+    // canvas' pinned host memory as sixteen posted stores — no copy-engine transfer that would queue behind the
+    // frames' 33-132 MB read-backs, no extra launch.  Visible to the host once the kernel has completed.
+    if (blockIdx.x == 0 && threadIdx.x < 16 && U.status_host) {
+        U.status_host[threadIdx.x] = __ldcg(&W.counters[threadIdx.x]);
+        __threadfence_system();
+    }
     // Clear-in-tile mode: the empty tiles (k_alloc's list) are dealt out evenly over the raster items and
     // written by the item's CTA before it starts on the item; there is no k_clear_empty launch.  The
     // stores need no answer, so they drain to HBM under the latency-bound raster work instead of

@@ -189,9 +189,7 @@ struct draw_scene {
         cudaEvent_t canvas_ready = nullptr; // canvas stream: the canvas of the frame using this set may be written
         cudaEvent_t clear_done = nullptr; // aux stream: k_clear_empty has finished
         cudaEvent_t frame_done = nullptr; // the whole frame using this set has finished
-        cudaEvent_t status_done = nullptr; // aux stream: the frame's counters have been copied to the host
         bool frame_pending = false;
-        bool status_pending = false;
     };
     static constexpr int MAX_WORK_SETS = 8;
     WorkSet sets[MAX_WORK_SETS];
@@ -227,7 +225,6 @@ struct draw_canvas {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     size_t stripe_y0 = 0, stripe_y1 = 0; // rows; y1 == 0 means whole canvas
     uint32_t *h_status = nullptr;        // pinned: counters of the last frame
-    cudaEvent_t status_done = nullptr;   // the copy of the last frame's counters into h_status has landed
     cudaEvent_t join_event = nullptr;    // draw_canvas_stream_wait
     bool frame_pending = false;
     draw_scene *last_scene = nullptr;
@@ -467,7 +464,6 @@ int ensure_work_buffers(draw_scene *s, draw_scene::WorkSet &ws, size_t n_lists) 
     if (!ws.canvas_ready) CU(cudaEventCreateWithFlags(&ws.canvas_ready, cudaEventDisableTiming));
     if (!ws.clear_done) CU(cudaEventCreateWithFlags(&ws.clear_done, cudaEventDisableTiming));
     if (!ws.frame_done) CU(cudaEventCreateWithFlags(&ws.frame_done, cudaEventDisableTiming));
-    if (!ws.status_done) CU(cudaEventCreateWithFlags(&ws.status_done, cudaEventDisableTiming));
     return DRAW_OK;
 }
 
@@ -643,6 +639,7 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     g_tile_ctas = (unsigned)g_cfg.tile_ctas;
     U.pdl_early = pdl_mode == 1 || (pdl_mode == 3 && !others_in_flight);
 
+    U.status_host = c->h_status; // pinned, mapped: the pointer is valid on the device (unified addressing)
     U.color = c->color();
     U.depth = c->depth();
 
@@ -656,7 +653,6 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     cudaStream_t side = ws.stream, st = c->stream;
     if (ws.frame_pending) CU(cudaEventSynchronize(ws.frame_done)); // the pinned uniforms of the set are about to be rewritten
     *ws.h_uniforms = U;
-    if (ws.status_pending) CU(cudaStreamWaitEvent(side, ws.status_done, 0)); // k_vertex resets the counters that copy reads
     // what the canvas stream still does with the canvas comes before the two kernels that write it
     // (k_clear_empty, k_tile wait for this event; the geometry chain does not touch the canvas and does not wait)
     CU(cudaEventRecord(ws.canvas_ready, st));
@@ -713,14 +709,6 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     CU(cudaStreamWaitEvent(st, ws.frame_done, 0));
     s->launches += 5 + (s->dev.n_triangles ? 2 : 0) + (s->dev.n_transparent ? 1 : 0) + (U.tile_y_end > U.tile_y_begin ? (U.defer_max ? 3 : 2) - (U.clear_in_tile ? 1 : 0) : 0);
     CU(cudaGetLastError());
-    // The frame's counters go to the host on the set's auxiliary stream, not on the canvas' stream: when
-    // several canvases share a stream the next frame's canvas_ready would otherwise sit behind this copy.
-    CU(cudaStreamWaitEvent(ws.aux_stream, ws.frame_done, 0));
-    CU(cudaMemcpyAsync(c->h_status, ws.work.counters, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ws.aux_stream));
-    if (!c->status_done) CU(cudaEventCreateWithFlags(&c->status_done, cudaEventDisableTiming));
-    CU(cudaEventRecord(c->status_done, ws.aux_stream));
-    CU(cudaEventRecord(ws.status_done, ws.aux_stream));
-    ws.status_pending = true;
     c->frame_pending = true;
     c->host_dirty = true;
     c->last_scene = s;
@@ -739,7 +727,6 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
 int finish_frame(draw_canvas *c) {
     TRY(ensure_device(c->device));
     CU(cudaStreamSynchronize(c->stream));
-    if (c->status_done) CU(cudaEventSynchronize(c->status_done));
     int guard = 0;
     while (c->frame_pending) {
         c->frame_pending = false;
@@ -770,7 +757,6 @@ int finish_frame(draw_canvas *c) {
         CU(cudaDeviceSynchronize()); // both work sets are about to be reallocated
         TRY(enqueue_frame(s, c));
         CU(cudaStreamSynchronize(c->stream));
-        CU(cudaEventSynchronize(c->status_done));
     }
     return DRAW_OK;
 }
@@ -871,7 +857,6 @@ void draw_scene_destroy(draw_scene *scene) {
             if (ws.canvas_ready) cudaEventDestroy(ws.canvas_ready);
             if (ws.clear_done) cudaEventDestroy(ws.clear_done);
             if (ws.frame_done) cudaEventDestroy(ws.frame_done);
-            if (ws.status_done) cudaEventDestroy(ws.status_done);
         }
     }
     delete scene;
@@ -1188,10 +1173,6 @@ void draw_canvas_destroy(draw_canvas *canvas) {
     if (cudaGetDevice(&cur) == cudaSuccess) {
         if (cur != canvas->device) cudaSetDevice(canvas->device);
         if (canvas->stream) cudaStreamSynchronize(canvas->stream);
-        if (canvas->status_done) {
-            cudaEventSynchronize(canvas->status_done); // the copy into h_status
-            cudaEventDestroy(canvas->status_done);
-        }
         if (canvas->join_event) cudaEventDestroy(canvas->join_event);
         if (canvas->own_stream) cudaStreamDestroy(canvas->own_stream);
         if (canvas->h_color) cudaFreeHost(canvas->h_color);
