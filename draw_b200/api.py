@@ -150,6 +150,10 @@ class Canvas:
     def set_stream(self, cuda_stream):
         N.check(N.lib().draw_canvas_set_stream(self._h, cuda_stream))
 
+    def export_png(self, path):
+        """Application::export_frame_as(Png) (app/mod.rs:316-360): the current frame as an RGBA PNG file."""
+        N.check(N.lib().draw_canvas_export_png(self._h, str(path).encode()))
+
     def stream_wait(self, cuda_stream):
         """Make `cuda_stream` wait (on the device) for everything enqueued so far for this canvas."""
         N.check(N.lib().draw_canvas_stream_wait(self._h, cuda_stream))
@@ -328,6 +332,12 @@ def load_image(path):
         return np.ctypeslib.as_array(C.cast(px, C.POINTER(C.c_uint8)), shape=(n,)).copy().reshape(h.value, w.value, c.value)
     finally:
         N.lib().draw_image_free(px)
+
+
+def write_png(path, pixels):
+    """stbi_write_png (app/mod.rs:362-378): uint8 [height, width, 3 or 4] -> PNG file."""
+    a = np.ascontiguousarray(pixels, dtype=np.uint8)
+    N.check(N.lib().draw_image_write_png(str(path).encode(), a.ctypes.data, a.shape[1], a.shape[0], a.shape[2]))
 
 
 def load_obj(path, decode_images=True):

@@ -194,6 +194,49 @@ int draw_image_load(const char *path, uint8_t **out_pixels, uint32_t *out_w, uin
 
 void draw_image_free(uint8_t *pixels) { std::free(pixels); }
 
+// stbi_write_png's job in the reference (app/mod.rs:362-378): width*height*components bytes -> a PNG file.
+// Lossless, so any conforming encoder yields a file that decodes to the same pixels; this one uses zlib's
+// deflate and the Up filter on every row but the first (cheap, and effective on rendered frames whose
+// background is constant).  components: 3 (RGB) or 4 (RGBA), 8 bits per sample.
+int draw_image_write_png(const char *path, const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t components) {
+    try {
+        if (!path || !pixels || !width || !height || (components != 3 && components != 4))
+            return loader_fail(DRAW_ERR_INVALID_ARGUMENT, "draw_image_write_png: bad argument (components must be 3 or 4)");
+        const size_t stride = (size_t)width * components;
+        std::vector<uint8_t> raw((stride + 1) * (size_t)height);
+        for (uint32_t y = 0; y < height; y++) {
+            uint8_t *row = &raw[(stride + 1) * (size_t)y];
+            const uint8_t *src = pixels + stride * y, *up = y ? src - stride : nullptr;
+            row[0] = up ? 2 : 0;
+            for (size_t i = 0; i < stride; i++) row[1 + i] = up ? (uint8_t)(src[i] - up[i]) : src[i];
+        }
+        uLongf zlen = compressBound((uLong)raw.size());
+        std::vector<uint8_t> z(zlen);
+        if (compress2(z.data(), &zlen, raw.data(), (uLong)raw.size(), 6) != Z_OK) return loader_fail(DRAW_ERR_INTERNAL, "PNG: deflate failed");
+        FILE *f = std::fopen(path, "wb");
+        if (!f) return loader_fail(DRAW_ERR_INVALID_ARGUMENT, (std::string("cannot write ") + path).c_str());
+        auto put_chunk = [&](const char *type, const uint8_t *data, size_t len) {
+            uint8_t hdr[8] = {(uint8_t)(len >> 24), (uint8_t)(len >> 16), (uint8_t)(len >> 8), (uint8_t)len,
+                              (uint8_t)type[0], (uint8_t)type[1], (uint8_t)type[2], (uint8_t)type[3]};
+            uLong crc = crc32(0L, hdr + 4, 4);
+            if (len) crc = crc32(crc, data, (uInt)len);
+            const uint8_t tail[4] = {(uint8_t)(crc >> 24), (uint8_t)(crc >> 16), (uint8_t)(crc >> 8), (uint8_t)crc};
+            return std::fwrite(hdr, 1, 8, f) == 8 && (!len || std::fwrite(data, 1, len, f) == len) && std::fwrite(tail, 1, 4, f) == 4;
+        };
+        static const uint8_t SIG[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+        const uint8_t ihdr[13] = {(uint8_t)(width >> 24), (uint8_t)(width >> 16), (uint8_t)(width >> 8), (uint8_t)width,
+                                  (uint8_t)(height >> 24), (uint8_t)(height >> 16), (uint8_t)(height >> 8), (uint8_t)height,
+                                  8, (uint8_t)(components == 3 ? 2 : 6), 0, 0, 0};
+        bool ok = std::fwrite(SIG, 1, 8, f) == 8 && put_chunk("IHDR", ihdr, 13) && put_chunk("IDAT", z.data(), zlen) && put_chunk("IEND", nullptr, 0);
+        ok = (std::fclose(f) == 0) && ok;
+        return ok ? DRAW_OK : loader_fail(DRAW_ERR_INTERNAL, "PNG: short write");
+    } catch (const std::bad_alloc &) {
+        return loader_fail(DRAW_ERR_OUT_OF_MEMORY, "host allocation failed");
+    } catch (...) {
+        return loader_fail(DRAW_ERR_INTERNAL, "internal error");
+    }
+}
+
 int draw_image_loader_builtin(const char *path, void *, uint8_t **out_pixels, uint32_t *out_w, uint32_t *out_h,
                               uint32_t *out_components) {
     return draw_image_load(path, out_pixels, out_w, out_h, out_components) == DRAW_OK ? 0 : 1;

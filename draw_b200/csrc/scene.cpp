@@ -1373,6 +1373,21 @@ int draw_canvas_set_stream(draw_canvas *canvas, void *cuda_stream) {
     GUARD_END
 }
 
+int draw_canvas_export_png(draw_canvas *canvas, const char *path) {
+    GUARD_BEGIN
+    if (!canvas || !path) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    const uint8_t *bgra = nullptr;
+    size_t len = 0;
+    TRY(draw_canvas_map_host(canvas, &bgra, &len));
+    // app/mod.rs:347-352: "reverse the RGB order" — swap bytes 0 and 2 of every pixel, keep the pad byte as alpha
+    std::vector<uint8_t> rgba(len);
+    for (size_t i = 0; i + 3 < len; i += 4) {
+        rgba[i] = bgra[i + 2]; rgba[i + 1] = bgra[i + 1]; rgba[i + 2] = bgra[i]; rgba[i + 3] = bgra[i + 3];
+    }
+    return draw_image_write_png(path, rgba.data(), (uint32_t)canvas->width, (uint32_t)canvas->height, 4);
+    GUARD_END
+}
+
 int draw_canvas_stream_wait(draw_canvas *canvas, void *cuda_stream) {
     GUARD_BEGIN
     if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas is NULL");

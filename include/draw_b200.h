@@ -195,6 +195,9 @@ int draw_canvas_device_ptrs(draw_canvas *canvas, void **out_color, void **out_de
  * framebuffer opened through CUDA IPC).  NULL restores the canvas' own buffer.  The colour
  * buffer must hold width*height*4 bytes; depth width*height floats. */
 int draw_canvas_bind_external(draw_canvas *canvas, void *color_dev, void *depth_dev);
+/* Application::export_frame_as(Png) (app/mod.rs:316-360) without the file dialog: waits for the frame, swaps B and R
+ * (the frame is BGRA, the file RGBA with the pad byte as alpha) and writes it with draw_image_write_png. */
+int draw_canvas_export_png(draw_canvas *canvas, const char *path);
 /* Enqueue on an existing CUDA stream (a cudaStream_t passed as void*); NULL = own stream. */
 int draw_canvas_set_stream(draw_canvas *canvas, void *cuda_stream);
 /* Device-side join: makes cuda_stream (a cudaStream_t passed as void*) wait for everything enqueued so far
@@ -229,6 +232,9 @@ int draw_object_load_obj(const char *path, draw_image_loader loader, void *user,
  * fail with DRAW_ERR_INVALID_ARGUMENT.  The buffer is malloc()ed; release it with draw_image_free. */
 int draw_image_load(const char *path, uint8_t **out_pixels, uint32_t *out_w, uint32_t *out_h, uint32_t *out_components);
 void draw_image_free(uint8_t *pixels);
+/* stbi_write_png in Application::write_img (app/mod.rs:362-378): writes width*height*components bytes (components 3
+ * or 4, row 0 = top) as a PNG file.  Lossless: the file decodes to exactly the bytes given. */
+int draw_image_write_png(const char *path, const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t components);
 /* draw_image_load as a draw_image_loader callback (user is ignored), for draw_object_load_obj. */
 int draw_image_loader_builtin(const char *path, void *user, uint8_t **out_pixels, uint32_t *out_w, uint32_t *out_h,
                               uint32_t *out_components);

@@ -58,3 +58,19 @@ def test_host_mirror_follows_every_render():
         s.render(a)
         s.render(b)
         assert np.array_equal(a.as_bytes_slice(), b.as_bytes_slice())
+
+
+def test_export_png_is_the_frame_with_b_and_r_swapped(tmp_path):
+    """draw_canvas_export_png = Application::export_frame_as(Png) (app/mod.rs:316-360): RGBA file of the BGRA frame."""
+    import numpy as np
+    import draw_b200
+    from conftest import load_scene
+    s, c = draw_b200.Scene(400, 300), draw_b200.Canvas(400, 300)
+    c.init_depth(100000.0)
+    for o in load_scene("c1_lemur_airplane"):
+        s.add_obj(o)
+    s.render(c)
+    p = str(tmp_path / "frame.png")
+    c.export_png(p)
+    frame = c.as_bytes_slice()
+    assert np.array_equal(draw_b200.load_image(p), frame[..., [2, 1, 0, 3]])

@@ -97,3 +97,16 @@ def test_reference_texture_if_present():
     want = np.asarray(PIL.open(p))
     got = _lib_decode(p)
     assert got.shape == want.shape and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("c", [3, 4])
+def test_png_writer_round_trips(tmp_path, c):
+    """draw_image_write_png (stbi_write_png's job, app/mod.rs:362-378): the file decodes — with PIL and with the
+    library's own decoder — to exactly the bytes written."""
+    import draw_b200.api as api
+    a = _noise(45, 67, c, seed=9 + c)
+    a[10:30, 5:60] = a[10, 5]  # a constant region, like a rendered frame's background
+    p = str(tmp_path / f"out{c}.png")
+    api.write_png(p, a)
+    assert np.array_equal(np.asarray(PIL.open(p)), a)
+    assert np.array_equal(api.load_image(p), a)
