@@ -85,7 +85,7 @@ def load_workload(name):
 def fill_roofline(config, frame_seconds, sm_mhz):
     """SURVEY.md §8(d), secondary bound (binds the overdraw-heavy C4): ALGO_FLOP(frame) = 23 F_cov + 101 P_vis against
     the non-FMA FP32 peak, SMs x 128 lanes x clock.  F_cov / P_vis are counted by the CPU oracle offline
-    (tools/make_fill_counts.py -> tests/golden/fill_counts.json); nothing is counted inside the timed region."""
+    (tests/golden/make_fill_counts.py -> tests/golden/fill_counts.json); nothing is counted inside the timed region."""
     try:
         fc = json.load(open(os.path.join(GOLDEN, "fill_counts.json")))[config]
     except Exception:

@@ -2,11 +2,11 @@
 """Counts, with the CPU oracle, what SURVEY.md §8(d)'s fill roofline needs per config:
 F_cov = fragments that pass the inside test (overdraw included), P_vis = pixels whose final colour comes from
 a triangle.  Writes tests/golden/fill_counts.json (means per frame; C4 over its 120-frame camera path).
-    python tools/make_fill_counts.py [c2 c3 c4 c5]
+    python tests/golden/make_fill_counts.py [c2 c3 c4 c5]
 Test / measurement infrastructure: bench.py only reads the JSON."""
 import json, os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import bench
 from oracle import pyoracle

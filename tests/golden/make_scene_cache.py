@@ -3,7 +3,7 @@
 
 Runs HERE (needs /root/reference/models and PIL); the GPU box only reads the generated files.
 Loader = oracle/obj_loader.py, the numpy restatement of object.rs:106-454.  Re-run after any
-loader change:  python tools/make_scene_cache.py [--ref /root/reference]
+loader change:  python tests/golden/make_scene_cache.py [--ref /root/reference]
 """
 import argparse
 import os
@@ -11,7 +11,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from draw_b200 import scene_cache, synthetic  # noqa: E402
