@@ -122,24 +122,8 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(const FrameUniforms *__rest
     if (n <= n_warps * U.bin_records_per_warp) {
         // Few records (they may each cover many tiles): one warp per record, lanes stride over its
         // tiles so that the atomics of one record are in flight together.
-        // (software-pipelined: the next record of the warp is requested before this one is worked on — a warp's
-        // records are a serial chain of L2 round trips otherwise, and the CTA's residency is what the kernel
-        // costs the frames in flight)
-        const uint32_t first = blockIdx.x * (BIN_THREADS / 32) + (threadIdx.x >> 5);
-        RasterRec r_next;
-        if (first < n) r_next = load_raster(W.rrec + first); // same address in every lane: one broadcast load
-        for (uint32_t slot = first; slot < n; slot += n_warps) {
-#ifndef DRAW_BIN_NOPIPE
-            const RasterRec r = r_next;
-#else
-            const RasterRec r = load_raster(W.rrec + slot);
-#endif
-#ifndef DRAW_BIN_NOPIPE
-            if (slot + n_warps < n) r_next = load_raster(W.rrec + slot + n_warps);
-#else
-            __syncwarp();
-            if (slot + n_warps < n) r_next = r; // A/B build: loaded at the top of the next iteration instead
-#endif
+        for (uint32_t slot = blockIdx.x * (BIN_THREADS / 32) + (threadIdx.x >> 5); slot < n; slot += n_warps) {
+            const RasterRec r = load_raster(W.rrec + slot); // same address in every lane: one broadcast load
             const TileRange tr = tile_range(U, r.bbx, r.bby);
             const int total = tr.count();
             if (r.id == NO_SLOT) continue; // reserved by k_setup, not used by k_clip
