@@ -124,6 +124,20 @@ grid-size and residency changes listed above acted on, and the model next round'
 
 ```
 {ko}```
+
+## 5. Tried this round, measured, not kept (A/B on the timed region, `tools/gpu_ab.sh`; so that they are not tried again blind)
+
+| change | result |
+|---|---|
+| launch priorities: geometry chain above `k_tile` (and the reverse), `DRAW_B200_KPRIO` | ±0.5 % on C2-C4 |
+| `k_tile` / `k_raster` capped at 56 or 48 registers so that a `k_clear_empty` CTA can co-reside | 0 to −5 % (spills; the clear was already hidden) |
+| finer tile windows with a shading term in `k_alloc`'s cost model (`DRAW_B200_COST_SHADE`, `SPLIT_DIV` 592-1024, up to 16 windows) | −1 to −3 % on C3 (per-item prologue latency outweighs the better balance) |
+| `k_bin` always thread-per-record (`DRAW_B200_BIN_RPW=0`) | C3 +6 %, C4 −12 %: kept as a knob, default unchanged |
+| software-pipelined record fetches in `k_bin` (warp mode) and reference fetches in `k_raster` (`-DDRAW_RASTER_PIPE`) | ±1 % |
+| `k_raster` at 5 or 6 CTAs per SM (48 / 40 registers) | −1 % (spills) |
+| 256-descriptor look-back window in `k_setup`'s chained scan (C5, 39 063 CTAs) | C5 −6 %: the look-back is not what `barrier` waits for; more polling traffic |
+| larger grids for C5's `k_bin` / `k_raster` / `k_tile` | ±0.5 % |
+| empty tiles written before each raster item instead of after it (`DRAW_B200_CLEAR_IN_TILE=1`) | C3 −4 % against mode 2 (all CTAs store at once at the start of the launch) |
 """
 open("profiles/README.md", "w").write(out)
 print("profiles/README.md written")
