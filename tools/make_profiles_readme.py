@@ -137,6 +137,7 @@ grid-size and residency changes listed above acted on, and the model next round'
 | `k_raster` at 5 or 6 CTAs per SM (48 / 40 registers) | −1 % (spills) |
 | 256-descriptor look-back window in `k_setup`'s chained scan (C5, 39 063 CTAs) | C5 −6 %: the look-back is not what `barrier` waits for; more polling traffic |
 | larger grids for C5's `k_bin` / `k_raster` / `k_tile` | ±0.5 % |
+| empty-tile list entries fetched eight at a time before the stores in `k_tile` | C3 −2 %, C4 +1 % (more spills) |
 | empty tiles written before each raster item instead of after it (`DRAW_B200_CLEAR_IN_TILE=1`) | C3 −4 % against mode 2 (all CTAs store at once at the start of the launch) |
 """
 open("profiles/README.md", "w").write(out)
