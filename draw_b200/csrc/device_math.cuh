@@ -57,8 +57,10 @@ struct CtaTrace {
     }
 };
 
-extern int g_kernel_priority_set, g_kernel_priority; // scene.cpp
-extern int g_pdl_enabled; // scene.cpp (DRAW_B200_PDL=0 launches without the attribute)
+// per-call launch configuration, set by enqueue_frame (scene.cpp) on the calling thread: handles may be used from
+// different threads
+extern thread_local int g_kernel_priority_set, g_kernel_priority;
+extern thread_local int g_pdl_enabled; // scene.cpp (DRAW_B200_PDL=0 launches without the attribute)
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t stream, Args... args) {
     cudaLaunchConfig_t cfg = {};

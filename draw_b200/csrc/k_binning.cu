@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(ALLOC_THREADS) k_alloc(const FrameUniforms *__
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-unsigned g_bin_ctas = 148u * 4u; // scene.cpp: DRAW_B200_BIN_CTAS
+thread_local unsigned g_bin_ctas = 148u * 4u; // scene.cpp: DRAW_B200_BIN_CTAS
 static int bin_blocks(const FrameDev &) { return (int)g_bin_ctas; }
 void launch_bin_count(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream) {
     launch_pdl(k_bin<false>, bin_blocks(W), BIN_THREADS, stream, dU, W);

@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(CLIP_THREADS) k_clip(const FrameUniforms *__re
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-unsigned g_clip_ctas = 148u * 2u; // scene.cpp: DRAW_B200_CLIP_CTAS
+thread_local unsigned g_clip_ctas = 148u * 2u; // scene.cpp: DRAW_B200_CLIP_CTAS
 void launch_clip(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream) {
     if (!S.n_triangles) return;
     launch_pdl(k_clip, g_clip_ctas, CLIP_THREADS, stream, dU, S, W);

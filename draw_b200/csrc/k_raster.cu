@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) k_fill_u64(unsigned long long *__restrict
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = value;
 }
 
-unsigned g_raster_ctas = 148u * 8u; // scene.cpp: DRAW_B200_RASTER_CTAS
+thread_local unsigned g_raster_ctas = 148u * 8u; // scene.cpp: DRAW_B200_RASTER_CTAS
 void launch_raster(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream) {
     launch_pdl(k_raster, g_raster_ctas, RASTER_THREADS, stream, dU, W);
 }

@@ -837,15 +837,15 @@ __global__ void __launch_bounds__(256) k_fill_u32(uint32_t *__restrict__ dst, si
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-extern unsigned g_tile_ctas;
+extern thread_local unsigned g_tile_ctas;
 uint32_t tile_grid_items(const FrameUniforms &U); // k_binning.cu
 void launch_tile(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream) {
     const uint32_t slots = tile_grid_items(U); // work-list slots (k_alloc fills the unused ones with ITEM_NONE)
     if (slots) launch_pdl(k_tile, min(slots, g_tile_ctas), TILE_THREADS, stream, dU, S, W, slots);
 }
 
-unsigned g_clear_ctas = 148u * 4u; // scene.cpp: DRAW_B200_CLEAR_CTAS
-unsigned g_tile_ctas = 148u * (1024u / TILE_THREADS); // scene.cpp: DRAW_B200_TILE_CTAS (persistent CTAs of k_tile)
+thread_local unsigned g_clear_ctas = 148u * 4u; // scene.cpp: DRAW_B200_CLEAR_CTAS
+thread_local unsigned g_tile_ctas = 148u * (1024u / TILE_THREADS); // scene.cpp: DRAW_B200_TILE_CTAS (persistent CTAs of k_tile)
 void launch_clear_empty(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream) {
     if (tile_grid_items(U)) launch_pdl(k_clear_empty, g_clear_ctas, CLEAR_THREADS, stream, dU, W);
 }

@@ -23,12 +23,12 @@
 #include "host_math.hpp"
 
 namespace drawb200 {
-int g_pdl_enabled = 1;
-int g_kernel_priority_set = 0, g_kernel_priority = 0;
-extern unsigned g_clip_ctas; // k_geometry.cu
-extern unsigned g_bin_ctas;  // k_binning.cu
-extern unsigned g_raster_ctas; // k_raster.cu
-extern unsigned g_clear_ctas, g_tile_ctas;
+thread_local int g_pdl_enabled = 1;
+thread_local int g_kernel_priority_set = 0, g_kernel_priority = 0;
+extern thread_local unsigned g_clip_ctas; // k_geometry.cu
+extern thread_local unsigned g_bin_ctas;  // k_binning.cu
+extern thread_local unsigned g_raster_ctas; // k_raster.cu
+extern thread_local unsigned g_clear_ctas, g_tile_ctas;
 // k_geometry.cu / k_binning.cu / k_tile.cu
 void launch_vertex(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
 void launch_setup(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
