@@ -106,12 +106,20 @@ class SortFirst:
         if mode == "p2p":
             import torch
             handle = torch.zeros(64, dtype=torch.uint8, device=device)
+            export_error = None
             if self.rank == 0:
                 buf = (C.c_uint8 * 64)()
-                N.check(N.lib().draw_canvas_ipc_export(self.canvas._h, buf))
-                handle.copy_(torch.tensor(list(buf), dtype=torch.uint8))
+                try:
+                    N.check(N.lib().draw_canvas_ipc_export(self.canvas._h, buf))
+                    handle.copy_(torch.tensor(list(buf), dtype=torch.uint8))
+                except Exception as e:  # every rank must still reach the broadcast: an all-zero handle says "no"
+                    export_error = e
             dist.broadcast(handle, 0)
+            if export_error is not None:
+                raise export_error
             if self.rank != 0:
+                if not bool(handle.any().item()):
+                    raise RuntimeError("rank 0 could not export its framebuffer through CUDA IPC")
                 raw = (C.c_uint8 * 64)(*handle.cpu().tolist())
                 peer = C.c_void_p()
                 N.check(N.lib().draw_ipc_open(raw, C.byref(peer)))
@@ -148,10 +156,19 @@ def bench_sort_first(scene, cfg, dist, steps=50, warmup=5):
     W, H = cfg["W"], cfg["H"]
     out = {"workload": cfg["label"], "stripes": stripe_bounds(H, dist.get_world_size())}
     for mode in ("nccl", "p2p"):
+        sf, err = None, ""
         try:
             sf = SortFirst(scene, W, H, dist, device, mode=mode)
         except Exception as e:  # e.g. peer access not available
-            out[mode] = {"error": str(e)[:200]}
+            err = str(e)[:200]
+        # the ranks decide together: a mode is timed only if every rank could set it up (a rank that skipped on
+        # its own would leave the others waiting in the gather / barrier)
+        ok = torch.tensor([1 if sf is not None else 0], device=device, dtype=torch.int32)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            if sf is not None:
+                sf.close()
+            out[mode] = {"error": err or "another rank could not set this mode up"}
             continue
         for _ in range(max(warmup, 3)):
             sf.render()
