@@ -104,3 +104,36 @@ def test_checker_torus_texture_fetch():
                   synthetic.checker_texture(64, 8), synthetic.checker_texture(64, 8, seed=7))
     a, b, _, _ = _render_both([synthetic.torus(16, 12, texture=tex)], 96, 72)
     _assert_same(a, b)
+
+
+def test_painter_sort_ties_moving_camera():
+    """Two transparent meshes cut from a symmetric torus (many equal centroid distances: only a stable sort keeps
+    their list order), a camera that moves between frames so the persistent in-place order matters
+    (scene/mod.rs:1100-1115).  The C++ oracle sorts with std::stable_sort, the numpy one with Python's sort:
+    two independent stable sorts that must agree with each other — and the GPU's radix sort with both
+    (tests/test_gpu_parity.py::test_painter_sort_on_device_large_meshes_moving_camera)."""
+    from draw_b200.model import IndexedMesh, Object
+    t = synthetic.torus(10, 8)
+    tris = t.meshes[0].triangles
+    half = tris.shape[0] // 2 + 3
+    glass = Object("glass", t.vertices, t.normals_vertices, t.texture_vertices,
+                   [IndexedMesh("a", tris[:half].copy(), 1), IndexedMesh("b", tris[half:].copy(), 2)],
+                   [Texture(), Texture(name="ga", alpha=0.6, kd=np.array([0.1, 0.8, 0.3], F)),
+                    Texture(name="gb", alpha=0.35, kd=np.array([0.9, 0.2, 0.1], F))])
+    W, H = 64, 48
+    s1, c1 = pyoracle.Scene(W, H), pyoracle.Canvas(W, H)
+    s2, c2 = np_oracle.Scene(W, H), np_oracle.Canvas(W, H)
+    for c in (c1, c2):
+        c.init_depth(100000.0)
+    s1.add_obj(glass)
+    s2.add_obj(glass)
+    for cam in ([0, 0, 150, 0, 0, -150], [130, 30, 80, -1, -0.2, -0.6], [-90, -60, 110, 0.7, 0.5, -1], [0, 0, 150, 0, 0, -150]):
+        cam = np.array(cam, F)
+        s1.set_camera(cam[:3], cam[3:])
+        s2.set_camera(cam[:3], cam[3:])
+        s1.render(c1)
+        s2.render(c2)
+        # (transparent triangles do not write depth, so only the colour carries the result)
+        assert np.array_equal(c1.as_bytes(), c2.frame), "colour bytes differ"
+        assert np.array_equal(c1.depth().view(np.uint32), c2.depth_frame.view(np.uint32)), "depth bits differ"
+        assert (c1.as_bytes()[..., 3] == 0).any(), "transparent pass not exercised"
