@@ -4,27 +4,34 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c3|c2|c4|c5]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      (N > 1)
 
-One "step" is one frame: Scene::render of the whole scene into a 4K canvas (BASELINE.json
-configs[2], "C3": soldier1 + skeleton + lemur, 20 697 triangles, Phong + texture).  Rank 0 prints
-ONE JSON line.  Keys beyond the base contract:
+Workload at N = 1: BASELINE.json configs[2], "C3" (soldier1 + skeleton + lemur, 20 697 triangles, 4K, Phong +
+texture).  One "step" is one pass of the hot path over one BATCH of frames: `config.frames_per_step` calls of
+Scene::render, each with the next camera of a committed camera path (so that K = 20 steps span > 100 ms and
+dozens of clock samples; a single 4K frame of this scene is ~40 us of GPU time).  The metric stays frames/s.
+Rank 0 prints ONE JSON line.  Keys beyond the base contract:
 
-  value / ms_per_step   frames already resident in HBM, K frames back to back on one stream,
-                        CUDA events around the K steps, max over ranks.  Frames rotate over a ring
-                        of canvases larger than L2 so no step finds its framebuffer in L2.
-  e2e                   the same metric through the public API with host buffers: every step sets
-                        the camera (host), renders, and reads the BGRA frame back into pinned host
-                        memory (Canvas::as_bytes_slice), host clock around the K steps.
-  roofline              k_tile (the dominant kernel): algorithmic bytes per launch / its mean
-                        device time from CUDA events recorded around it on the launching stream,
-                        against MEASURED_PEAKS.json's HBM copy bandwidth.
-  cpu_baseline          the CPU oracle (C++ restatement of the reference renderer, 1 thread) on a
-                        bounded number of frames of the same workload, rank 0, N = 1 only.
-  sort_first            (N > 1) one frame partitioned into tile-row stripes across the ranks and
-                        gathered on rank 0 over NCCL; reported beside the frame-parallel `value`.
+  value / ms_per_step   scene resident in HBM, K steps back to back, CUDA events on the timing stream (joined on
+                        the device to every canvas' stream), max over ranks.  Frames rotate over a ring of
+                        canvases larger than L2 so no frame finds its framebuffer in L2.
+  lone_frame            latency of ONE frame on an idle GPU with L2 flushed (256 MB fill) before it.
+  e2e                   the same metric through the public API with host buffers: every frame sets the camera
+                        (host), renders, and is read back into pinned host memory (Canvas::as_bytes_slice); host
+                        clock.  `value` keeps three canvases in flight, `serial_value` is the reference's own loop
+                        (src/app/mod.rs:196-202: render, read, repeat — one canvas); `d2h_ceiling_gbs` is a plain
+                        cudaMemcpyAsync of the same bytes, all ranks at once.
+  roofline              k_tile (the dominant kernel): algorithmic bytes per launch / its mean device time from
+                        CUDA events recorded around it on the launching stream, against MEASURED_PEAKS.json.
+  cpu_baseline          the CPU oracle (C++ restatement of the reference renderer, 1 thread) on a bounded number
+                        of frames of the same workload, rank 0, N = 1 only.
+  sort_first            (N > 1) ONE frame partitioned across the ranks (transform replicated, each rank rasterises
+                        its tile rows, stripes land in rank 0's framebuffer over NVLink) on BASELINE.json
+                        configs[3] (C4) and, at N = 8, configs[4] (C5); every composed frame is compared with the
+                        single-GPU frame (`bit_exact`).
 
---impl reference times the reference's CPU implementation of the path.  The reference is a Rust
-program; no Rust toolchain exists in this image, so the arm runs the C++ oracle port
-(oracle/oracle.cpp), single-threaded like the reference (it has no threads anywhere in src/).
+--impl reference times the reference's CPU implementation of the path.  The reference is a Rust program; no
+Rust toolchain exists in this image, so the arm runs the C++ oracle port (oracle/oracle.cpp), single-threaded
+like the reference (it has no threads anywhere in src/); each of its steps is a bounded sample of the step
+above (`cpu_baseline.sample`).  Both arms print the same `config`.
 """
 import argparse
 import json
@@ -41,23 +48,29 @@ sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 DEPTH_MAX = 100000.0
 
+# frames_per_step: a step is ~5 ms of GPU work
 CONFIGS = {
-    "c2": dict(scene="c2_donut", W=1920, H=1080, label="C2 donut 1920x1080 Phong only"),
-    "c3": dict(scene="c3_trio", W=3840, H=2160, label="C3 soldier1+skeleton+lemur 3840x2160 Phong+texture"),
-    "c4": dict(scene="c4_dungeon", W=3840, H=2160, label="C4 dungeon_set 120-frame fly-through 3840x2160", path=True),
-    "c5": dict(scene=None, W=7680, H=4320, label="C5 synthetic 10M-triangle torus 7680x4320 Phong+checker texture"),
+    "c2": dict(scene="c2_donut", W=1920, H=1080, label="C2 donut 1920x1080 Phong only", path="orbit_camera_path.npy",
+               frames_per_step=256),
+    "c3": dict(scene="c3_trio", W=3840, H=2160, label="C3 soldier1+skeleton+lemur 3840x2160 Phong+texture",
+               path="orbit_camera_path.npy", frames_per_step=128),
+    "c4": dict(scene="c4_dungeon", W=3840, H=2160, label="C4 dungeon_set 120-frame fly-through 3840x2160",
+               path="c4_camera_path.npy", frames_per_step=16),
+    "c5": dict(scene=None, W=7680, H=4320, label="C5 synthetic 10M-triangle torus 7680x4320 Phong+checker texture",
+               path=None, frames_per_step=4),
 }
 
 
 def load_workload(name):
     from draw_b200 import scene_cache, synthetic
     cfg = dict(CONFIGS[name])
+    cfg["name"] = name
     if name == "c5":
         n_theta, n_phi = int(os.environ.get("DRAW_C5_NTHETA", 2500)), int(os.environ.get("DRAW_C5_NPHI", 2000))
         cfg["objects"] = [synthetic.torus(n_theta, n_phi, texture=synthetic.checker_material())]
     else:
         cfg["objects"] = scene_cache.load(os.path.join(GOLDEN, "scenes", cfg["scene"] + ".npz"))
-    cfg["cameras"] = (np.load(os.path.join(GOLDEN, "c4_camera_path.npy")) if cfg.get("path") else None)
+    cfg["cameras"] = np.load(os.path.join(GOLDEN, cfg["path"])) if cfg.get("path") else None
     objs = cfg["objects"]
     cfg["triangles"] = int(sum(o.triangle_count() for o in objs))
     n_pos = sum(o.vertices.shape[0] for o in objs)
@@ -80,6 +93,24 @@ def load_workload(name):
     cfg["algo_bytes_frame"] = 8 * cfg["W"] * cfg["H"] + 36 * cfg["triangles"] + 12 * (n_pos + n_nrm + n_uv) + tex_bytes
     cfg["algo_bytes_tile_kernel"] = 8 * cfg["W"] * cfg["H"] + tex_bytes
     return cfg
+
+
+def ring_size(cfg):
+    return max(2, int(np.ceil(160e6 / (8 * cfg["W"] * cfg["H"]))) + 1)
+
+
+def workload_config(cfg, world):
+    """The `config` object of the JSON line — the same in both arms (--impl ours / reference)."""
+    W, H = cfg["W"], cfg["H"]
+    n_ring = ring_size(cfg)
+    cams = cfg["cameras"]
+    return {"workload": cfg["label"], "triangles": cfg["triangles"], "width": W, "height": H,
+            "frames_per_step": cfg["frames_per_step"],
+            "camera": (f"{len(cams)}-camera path tests/golden/{cfg['path']}, next camera every frame" if cams is not None
+                       else "default camera (scene/mod.rs:763-765)"),
+            "parallelism": "single GPU" if world == 1 else f"frame-parallel x{world} (no collective)",
+            "l2": f"ring of {n_ring} canvases x {8 * W * H / 1e6:.0f} MB (colour+depth) = "
+                  f"{n_ring * 8 * W * H / 1e6:.0f} MB > 126 MB L2, rotated every frame"}
 
 
 def fill_roofline(config, frame_seconds, sm_mhz):
@@ -119,8 +150,7 @@ def measured_peak_hbm():
 
 class ClockSampler:
     """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md).  NVML is polled
-    from a thread every ~2 ms (the timed region can be a few tens of ms, too short for nvidia-smi's
-    loop mode); falls back to one nvidia-smi query if pynvml is unavailable."""
+    from a thread every ~2 ms; falls back to one nvidia-smi query if pynvml is unavailable."""
     REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
                "hw_power_brake_slowdown": 0x80}
 
@@ -206,7 +236,7 @@ def cpu_baseline(cfg, budget_s=12.0, max_frames=400):
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": "frames/s", "cores": 1, "kind": "port",
             "mtri_per_s": cfg["triangles"] * n / dt / 1e6,
-            "sample": f"{n} frames of the {cfg['label']} workload in {dt:.1f} s, C++ oracle port "
+            "sample": f"the first {n} frames of the {cfg['label']} workload's camera path in {dt:.1f} s, C++ oracle port "
                       f"(oracle/oracle.cpp, -O3, -ffp-contract=off), 1 thread of {os.cpu_count()} host cores; "
                       "the reference renderer is single-threaded"}
 
@@ -216,28 +246,37 @@ def run_reference(args, cfg):
     if rank != 0:
         return
     s, c = oracle_scene(cfg)
-    # bounded sample: at most ~60 s of CPU work overall
+    # A step of this arm is a bounded sample of the GPU arm's step (frames_per_step frames): as many of its frames
+    # as fit in ~2 s of CPU time, at least one; the whole run stays within a few minutes.
     oracle_frame(s, c, cfg, 0)
     t0 = time.perf_counter()
     oracle_frame(s, c, cfg, 0)
-    per = time.perf_counter() - t0
-    steps = max(1, min(args.steps, int(45.0 / max(per, 1e-6))))
-    warm = max(0, min(args.warmup, int(10.0 / max(per, 1e-6))))
-    for k in range(warm):
-        oracle_frame(s, c, cfg, k)
+    per = max(time.perf_counter() - t0, 1e-6)
+    steps = max(1, args.steps)
+    budget = 120.0 / (steps + args.warmup)  # seconds per step
+    fps_step = int(max(1, min(cfg["frames_per_step"], budget / per)))
+    k = 0
+    for _ in range(args.warmup):
+        for _ in range(fps_step):
+            oracle_frame(s, c, cfg, k)
+            k += 1
+    k = 0
     t0 = time.perf_counter()
-    for k in range(steps):
-        oracle_frame(s, c, cfg, k)
+    for _ in range(steps):
+        for _ in range(fps_step):
+            oracle_frame(s, c, cfg, k)
+            k += 1
     dt = time.perf_counter() - t0
-    fps = steps / dt
+    fps = steps * fps_step / dt
     line = {
         "impl": "reference", "metric": "frames/s at 3840x2160 (Phong+texture)", "value": fps, "unit": "frames/s",
-        "mtri_per_s": cfg["triangles"] * fps / 1e6, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "mtri_per_s": cfg["triangles"] * fps / 1e6, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "reference model assets (committed scene cache), default camera",
-        "config": {"workload": cfg["label"], "triangles": cfg["triangles"], "width": cfg["W"], "height": cfg["H"]},
+        "dtype": "f32", "data": "reference model assets (committed scene cache), committed camera path; no published baseline",
+        "config": workload_config(cfg, max(1, args.gpus)),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port",
-                         "sample": f"{steps} frames ({args.steps} requested) of {cfg['label']}; C++ oracle port of the "
+                         "sample": f"each step = the next {fps_step} of the step's {cfg['frames_per_step']} frames of {cfg['label']} "
+                                   f"({steps} steps, {steps * fps_step} frames, {dt:.1f} s); C++ oracle port of the "
                                    f"single-threaded Rust reference (no Rust toolchain in this image), 1 of "
                                    f"{os.cpu_count()} host cores"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -249,6 +288,13 @@ def run_reference(args, cfg):
 # ------------------------------------------------------------------------------------------------
 # GPU side
 # ------------------------------------------------------------------------------------------------
+def new_canvas(draw_b200, W, H):
+    c = draw_b200.Canvas(W, H)
+    c.init_depth(DEPTH_MAX)
+    c.apply_offset(0, 0)
+    return c
+
+
 def run_ours(args, cfg):
     import torch
     import draw_b200
@@ -266,31 +312,30 @@ def run_ours(args, cfg):
     # a real (non-default) stream for the timing events.  Every canvas of the ring renders on its own stream
     # (frames on different canvases are independent and overlap, as they would for an application that
     # keeps several frames in flight); before the closing event is recorded the timing stream is made to
-    # wait, on the device, for every canvas (Canvas.stream_wait), so ev0 -> ev1 spans all K frames.
+    # wait, on the device, for every canvas (Canvas.stream_wait), so ev0 -> ev1 spans all the frames.
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     W, H = cfg["W"], cfg["H"]
+    FPS = cfg["frames_per_step"]
 
     scene = draw_b200.Scene(W, H)
     for o in cfg["objects"]:
         scene.add_obj(o)
     # ring of canvases: working set of framebuffers larger than the 126 MB L2
-    n_ring = max(2, int(np.ceil(160e6 / (8 * W * H))) + 1)
+    n_ring = ring_size(cfg)
     ring = []
     for _ in range(n_ring):
-        c = draw_b200.Canvas(W, H)
-        c.init_depth(DEPTH_MAX)
-        c.apply_offset(0, 0)
+        c = new_canvas(draw_b200, W, H)
         if os.environ.get("DRAW_BENCH_SHARED_STREAM"):  # A/B: all canvases enqueue on the timing stream
             c.set_stream(stream.cuda_stream)
         ring.append(c)
     cams = cfg["cameras"]
+    cam_values = [draw_b200.Camera.new(cam[:3], cam[3:]) for cam in cams] if cams is not None else None
 
     def frame(k, canvas):
-        if cams is not None:
-            cam = cams[k % len(cams)]
-            scene.camera = draw_b200.Camera.new(cam[:3], cam[3:])
+        if cam_values is not None:
+            scene.camera = cam_values[k % len(cam_values)]  # scene.camera = Camera::new(pos_k, dir_k, ratio)
         scene.render(canvas)
 
     def barrier():
@@ -298,15 +343,20 @@ def run_ours(args, cfg):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # settle work-buffer capacities over the whole camera path before anything is timed
+    # every frame-in-flight slot of the scene is set up before anything is timed (streams, work buffers, key pages,
+    # frame graphs), then work-buffer capacities are settled over the whole camera path, then every (slot, canvas)
+    # pairing is run once
+    scene.prepare(ring[0])
     for k in range(len(cams) if cams is not None else 1):
         frame(k, ring[0])
         ring[0].sync()
-    for k in range(args.warmup):
+    for k in range(8 * n_ring):
+        frame(k, ring[k % n_ring])
+    for k in range(args.warmup * FPS):
         frame(k, ring[k % n_ring])
     barrier()
 
-    # ---- timed region: K frames back to back ------------------------------------------------
+    # ---- timed region: K steps of FPS frames, back to back ---------------------------------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -314,7 +364,7 @@ def run_ours(args, cfg):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
-    for k in range(args.steps):
+    for k in range(args.steps * FPS):
         frame(k, ring[k % n_ring])
     for c in ring:
         c.stream_wait(stream.cuda_stream)
@@ -331,12 +381,13 @@ def run_ours(args, cfg):
         t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-    frames_total = args.steps * world
+    frames_rank = args.steps * FPS
+    frames_total = frames_rank * world
     fps = frames_total / (ms_total * 1e-3)
 
     if args.quick:  # A/B runs: the timed region only
         if rank == 0:
-            print(json.dumps({"quick": True, "config": args.config, "value": fps, "us_per_step": 1e3 * ms_total / args.steps,
+            print(json.dumps({"quick": True, "config": args.config, "value": fps, "us_per_frame": 1e3 * ms_total / frames_rank,
                               "gpu_launches": launches, "clocks": clocks}), flush=True)
         if dist is not None:
             dist.barrier()
@@ -346,19 +397,19 @@ def run_ours(args, cfg):
     # ---- per-kernel times (separate pass, same workload, events around each kernel) -----------
     scene.set_kernel_timing(True)
     ktimes = {k: [] for k in scene.KERNELS}
-    n_prof = min(args.steps, 50)
+    n_prof = min(frames_rank, 64)
     for k in range(n_prof):
         frame(k, ring[k % n_ring])
         for name, ms in scene.last_kernel_times(ring[k % n_ring]).items():
             ktimes[name].append(ms)
     scene.set_kernel_timing(False)
     kmean = {k: float(np.mean(v)) for k, v in ktimes.items()}
-    not_launched = [k for k, v in kmean.items() if v < 0.004 and k in ("k_clear_empty", "k_shade")]  # an empty event pair
+    not_launched = [k for k, v in kmean.items() if v < 0.004 and k in scene.OPTIONAL_KERNELS]  # an empty event pair
 
-    # ---- L2-flushed per-step timing (second protocol, reported beside the ring number) ---------
+    # ---- lone frame: L2 flushed, idle device -----------------------------------------------------
     flush = torch.empty(int(256e6) // 4, dtype=torch.float32, device="cuda")
-    per_step = []
-    for k in range(min(args.steps, 30)):
+    per_frame = []
+    for k in range(min(frames_rank, 32)):
         flush.fill_(float(k))
         torch.cuda.synchronize()  # the frame's geometry runs on the scene's own streams: start it on an idle GPU
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -367,56 +418,94 @@ def run_ours(args, cfg):
         ring[0].stream_wait(stream.cuda_stream)
         b.record(stream)
         torch.cuda.synchronize()
-        per_step.append(a.elapsed_time(b))
+        per_frame.append(a.elapsed_time(b))
     del flush
 
     # ---- e2e: public API, host in / host out ----------------------------------------------------
-    # Three canvases on their own streams with the host mirror enabled: every render is followed by the
+    # (1) three canvases on their own streams with the host mirror enabled: every render is followed by the
     # copy of its frame to pinned host memory, frame k renders while frames k-1 / k-2 are on the PCIe
     # link.  Every frame is read back in full and looked at on the host; nothing is skipped.
     N_E2E = 3
     pair = []
     for _ in range(N_E2E):
-        c = draw_b200.Canvas(W, H)
-        c.init_depth(DEPTH_MAX)
-        c.apply_offset(0, 0)
+        c = new_canvas(draw_b200, W, H)
         c.enable_host_mirror(True)
         pair.append(c)
     for k in range(2 * N_E2E):
         frame(k, pair[k % N_E2E])
         pair[k % N_E2E].as_bytes_slice(copy=False)
+    n_e2e = frames_rank
     barrier()
     t0 = time.perf_counter()
     checksum = 0
-    for k in range(args.steps + N_E2E - 1):
+    for k in range(n_e2e + N_E2E - 1):
         if k >= N_E2E - 1:  # the oldest frame in flight: wait for it and look at it on the host
             host = pair[(k - (N_E2E - 1)) % N_E2E].as_bytes_slice(copy=False)
             checksum ^= int(host[H // 2, W // 2, 0])
-        if k < args.steps:
-            if cams is None:  # the per-step host input: the camera (scene.camera = Camera::new(...))
+        if k < n_e2e:
+            if cams is None:  # the per-frame host input: the camera (scene.camera = Camera::new(...))
                 scene.camera = draw_b200.Camera.new([0.0, 0.0, 150.0], [0.0, 0.0, -150.0])
             frame(k, pair[k % N_E2E])
-    host = pair[(args.steps - 1) % N_E2E].as_bytes_slice(copy=False)
+    host = pair[(n_e2e - 1) % N_E2E].as_bytes_slice(copy=False)
     checksum ^= int(host[H // 2, W // 2, 0])
     barrier()
     e2e_s = time.perf_counter() - t0
-    del pair
+    # (2) the reference's own loop (src/app/mod.rs:196-202): one canvas, render, read the frame, repeat
+    serial = pair[0]
+    n_serial = min(n_e2e, 256)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(n_serial):
+        if cams is None:
+            scene.camera = draw_b200.Camera.new([0.0, 0.0, 150.0], [0.0, 0.0, -150.0])
+        frame(k, serial)
+        host = serial.as_bytes_slice(copy=False)
+        checksum ^= int(host[H // 2, W // 2, 0])
+    barrier()
+    serial_s = time.perf_counter() - t0
+    del pair, serial
+    # (3) what the link gives: the same number of bytes per frame as a plain device-to-pinned-host copy, every rank at once
+    dev_buf = torch.empty(4 * W * H, dtype=torch.uint8, device="cuda")
+    host_buf = torch.empty(4 * W * H, dtype=torch.uint8, pin_memory=True)
+    for _ in range(3):
+        host_buf.copy_(dev_buf, non_blocking=True)
+    n_copy = 64
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_copy):
+        host_buf.copy_(dev_buf, non_blocking=True)
+    barrier()
+    copy_s = time.perf_counter() - t0
+    del dev_buf, host_buf
     if dist is not None:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        t = torch.tensor([e2e_s, serial_s, copy_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_fps = frames_total / e2e_s
+        e2e_s, serial_s, copy_s = (float(x) for x in t.tolist())
+    e2e_fps = n_e2e * world / e2e_s
+    serial_fps = n_serial * world / serial_s
+    d2h_ceiling = n_copy * world * 4 * W * H / copy_s / 1e9
 
     sort_first = None
-    if dist is not None:
+    if dist is not None and not os.environ.get("DRAW_BENCH_NO_SORT_FIRST"):
         from draw_b200 import multi
-        sort_first = multi.bench_sort_first(scene, cfg, dist, steps=min(args.steps, 100), warmup=args.warmup)
+        sort_first = {}
+        names = ["c4"] + (["c5"] if world >= 8 or os.environ.get("DRAW_BENCH_SORT_FIRST_C5") else [])
+        for name in names:
+            sf_cfg = cfg if name == args.config else load_workload(name)
+            if name == args.config:
+                sf_scene = scene
+            else:
+                sf_scene = draw_b200.Scene(sf_cfg["W"], sf_cfg["H"])
+                for o in sf_cfg["objects"]:
+                    sf_scene.add_obj(o)
+            sort_first[name] = multi.bench_sort_first(sf_scene, sf_cfg, dist, frames=int(os.environ.get("DRAW_BENCH_SF_FRAMES", 120)))
+            if sf_scene is not scene:
+                del sf_scene
 
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
-        # Two kernels write the frame: k_clear_empty the tiles nothing was binned to, k_tile (the longest
-        # kernel of the frame: `roofline`) the others.  Algorithmic bytes of a launch = 8 B per pixel of the
-        # tiles it writes (colour + depth, once) + for k_tile the bound textures (read at most once).
+        # k_tile (the longest kernel of the frame: `roofline`) writes the frame.  Algorithmic bytes of a launch =
+        # 8 B per pixel (colour + depth, once) + the bound textures (read at most once).
         st = ring[0].last_frame_stats()
         tile_px = draw_b200.tile_size() * 64
         clear_bytes = min(8 * W * H, 8 * tile_px * st["empty_tiles"])  # border tiles counted whole: slight over-count
@@ -425,25 +514,32 @@ def run_ours(args, cfg):
         t_tile = kmean["k_tile"] * 1e-3
         achieved = tile_bytes / t_tile / 1e9
         clear_gbs = None if fused_clear else clear_bytes / (kmean["k_clear_empty"] * 1e-3) / 1e9
-        frame_gbs = cfg["algo_bytes_frame"] / (ms_total * 1e-3 / args.steps) / 1e9
+        s_per_frame = ms_total * 1e-3 / frames_rank
+        frame_gbs = cfg["algo_bytes_frame"] / s_per_frame / 1e9
+        lone_ms = float(np.median(per_frame))
         line = {
             "metric": "frames/s at 3840x2160 (Phong+texture)", "value": fps, "unit": "frames/s",
             "mtri_per_s": cfg["triangles"] * fps / 1e6,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "us_per_frame": 1e6 * s_per_frame,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "reference model assets (committed scene cache), default camera; no published baseline",
-            "config": {"workload": cfg["label"], "triangles": cfg["triangles"], "width": W, "height": H,
-                       "parallelism": "single GPU" if world == 1 else f"frame-parallel x{world} (no collective)",
-                       "l2": f"ring of {n_ring} canvases x {8 * W * H / 1e6:.0f} MB (colour+depth) = "
-                             f"{n_ring * 8 * W * H / 1e6:.0f} MB > 126 MB L2, rotated every step",
-                       "ms_per_step_l2_flushed": float(np.median(per_step)),
-                       "l2_flushed_protocol": "one frame at a time: 256 MB fill, device idle, CUDA events around the frame, median"},
+            "data": "reference model assets (committed scene cache), committed camera path; no published baseline",
+            "config": workload_config(cfg, world),
+            "lone_frame": {"ms": lone_ms, "frames_per_s": 1e3 / lone_ms,
+                           "frame_frac": cfg["algo_bytes_frame"] / (lone_ms * 1e-3) / 1e9 / peak,
+                           "protocol": "one frame at a time: 256 MB fill (L2 flushed), device idle, CUDA events around the frame, median of 32"},
             "clocks": clocks,
-            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 220,
-                    "d2h_bytes_per_step": 4 * W * H + 12,
-                    "note": "per step: camera set on host, Scene::render, Canvas::as_bytes_slice of the frame in pinned host memory; three canvases in flight with the host mirror enabled (the copy of a frame follows its render on the canvas stream, frame k renders while frames k-1 / k-2 cross PCIe); "
-                            "host memory; geometry is uploaded once by add_obj like the reference's Scene owns "
-                            "its objects"},
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 220 * FPS,
+                    "d2h_bytes_per_step": (4 * W * H + 64) * FPS,
+                    "serial_value": serial_fps, "d2h_ceiling_gbs": d2h_ceiling,
+                    "d2h_achieved_gbs": e2e_fps * 4 * W * H / 1e9,
+                    "note": "per frame: camera set on host, Scene::render, Canvas::as_bytes_slice of the frame in pinned host memory, "
+                            "one byte of it read on the host.  value: three canvases in flight with the host mirror enabled (the copy "
+                            "of a frame follows its render on the canvas stream, frame k renders while frames k-1 / k-2 cross PCIe); "
+                            "serial_value: the reference's loop (src/app/mod.rs:196-202), one canvas, render -> read -> next; "
+                            "d2h_ceiling_gbs: plain cudaMemcpyAsync of 4*W*H bytes to pinned host memory, all ranks at once "
+                            "(what the PCIe / host-memory path gives).  Geometry is uploaded once by add_obj like the reference's "
+                            "Scene owns its objects"},
             "gpu_launches": launches,
             "kernel_ms": {k: v for k, v in kmean.items() if k not in not_launched},
             "kernel_ms_note": "CUDA events around each kernel, kernels of a frame run one after the other (no overlap "
@@ -465,7 +561,7 @@ def run_ours(args, cfg):
                          "empty_tiles": st["empty_tiles"],
                          "frame_algo_bytes": cfg["algo_bytes_frame"], "frame_achieved": frame_gbs,
                          "frame_frac": frame_gbs / peak,
-                         "fill": fill_roofline(args.config, ms_total * 1e-3 / args.steps, (clocks or {}).get("sm_mhz"))},
+                         "fill": fill_roofline(args.config, s_per_frame, (clocks or {}).get("sm_mhz"))},
         }
         if sort_first is not None:
             line["sort_first"] = sort_first
@@ -480,8 +576,8 @@ def run_ours(args, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)  # C3: an 80 ms timed region (dozens of clock samples)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=40)  # C3: 40 x 128 frames, a ~200 ms timed region
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

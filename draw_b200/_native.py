@@ -70,6 +70,7 @@ SIGNATURES = {
     "draw_scene_move_camera_direction": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "draw_scene_set_light": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "draw_scene_render": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "draw_scene_prepare": (C.c_int, [C.c_void_p, C.c_void_p]),
     "draw_scene_get_uniforms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "draw_scene_read_vertex_visual": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
     "draw_scene_counts": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),

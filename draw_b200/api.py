@@ -38,7 +38,8 @@ class Camera:
 
     @staticmethod
     def new(pos, direction):
-        return ("camera", np.asarray(pos, np.float32).copy(), np.asarray(direction, np.float32).copy())
+        """Camera::new(pos, dir, ratio) as a value for `scene.camera = ...` (marshalled once, here)."""
+        return ("camera", _vec3(pos), _vec3(direction))
 
     def _h(self):
         return self._scene._h
@@ -192,7 +193,7 @@ class Scene:
     def camera(self, value):
         if not (isinstance(value, tuple) and value and value[0] == "camera"):
             raise TypeError("assign Camera.new(pos, direction)")
-        N.check(N.lib().draw_scene_set_camera(self._h, _vec3(value[1]), _vec3(value[2])))
+        N.check(N.lib().draw_scene_set_camera(self._h, value[1], value[2]))
 
     def set_light(self, pos):
         N.check(N.lib().draw_scene_set_light(self._h, _vec3(pos)))
@@ -247,6 +248,10 @@ class Scene:
     def render(self, canvas: Canvas):
         N.check(N.lib().draw_scene_render(self._h, canvas._h))
 
+    def prepare(self, canvas: Canvas):
+        """Set up every frame-in-flight slot for this canvas' geometry now and wait (draw_scene_prepare)."""
+        N.check(N.lib().draw_scene_prepare(self._h, canvas._h))
+
     # ---- parity / measurement taps
     def uniforms(self):
         m, p = (C.c_float * 16)(), (C.c_float * 24)()
@@ -259,6 +264,8 @@ class Scene:
         return out
 
     KERNELS = ("k_vertex", "k_setup", "k_clip", "k_bin_count", "k_alloc", "k_bin_fill", "k_raster", "k_clear_empty", "k_tile", "k_shade")
+
+    OPTIONAL_KERNELS = ("k_clear_empty", "k_shade")
 
     def set_kernel_timing(self, enabled):
         N.check(N.lib().draw_scene_set_kernel_timing(self._h, 1 if enabled else 0))

@@ -200,6 +200,7 @@ struct draw_scene {
     DevBuf<uint32_t> d_trace_count;
     bool debug_trace = false;
     size_t rec_cap = 0, refs_cap = 0;
+    bool needs_prepare = true; // the next render sets up every work set (streams, buffers, key pages, frame graph), not only its own
     // optional per-kernel timing (draw_scene_set_kernel_timing): 0..6 around the six side-stream kernels,
     // 7 / 8 around k_tile on the canvas stream
     bool kernel_timing = false;
@@ -228,11 +229,20 @@ struct draw_canvas {
     cudaEvent_t join_event = nullptr;    // draw_canvas_stream_wait
     bool frame_pending = false;
     draw_scene *last_scene = nullptr;
+    // what the pending frame was rendered with: an overflowed frame is rendered again from exactly these
+    // inputs, whatever the scene's camera / light and the canvas' offset / stripe have become since
+    struct FrameInputs {
+        CameraState camera;
+        f3 light;
+        int off_x = 0, off_y = 0;
+        size_t stripe_y0 = 0, stripe_y1 = 0;
+        float depth_max = 0.0f;
+    } pending_inputs;
     draw_frame_stats stats{};
     uint64_t launches = 0;
 
-    uint8_t *color() { return ext_color ? ext_color : d_color.ptr; }
-    float *depth() { return ext_depth ? ext_depth : d_depth.ptr; }
+    uint8_t *color() const { return ext_color ? ext_color : d_color.ptr; }
+    float *depth() const { return ext_depth ? ext_depth : d_depth.ptr; }
 };
 
 namespace {
@@ -545,7 +555,8 @@ int launch_frame(draw_scene *s, draw_scene::WorkSet &ws, const FrameUniforms &U,
     if (ev) cudaEventRecord(ev[6], side);
     if (!(g_cfg.skip & 64)) launch_raster(U, dU, ws.work, side);
     if (ev) cudaEventRecord(ev[7], side);
-    CU(cudaEventRecord(ws.geo_done, side));
+    // a real event in both paths (an event-record node under capture): the next frame's painter sort waits for it
+    CU(cudaEventRecordWithFlags(ws.geo_done, side, capturing ? cudaEventRecordExternal : 0u));
     CU(cudaStreamWaitEvent(side, ws.canvas_ready, ext));
     if (ev) cudaEventRecord(ev[N_FRAME_KERNELS + 1], side);
     g_kernel_priority = prio_tile;
@@ -569,31 +580,19 @@ int ensure_host_mirror(draw_canvas *c, size_t bytes) {
     return DRAW_OK;
 }
 
-int enqueue_frame(draw_scene *s, draw_canvas *c) {
-    TRY(ensure_device(s->device));
-    if (s->geometry_dirty) TRY(upload_geometry(s));
-    const uint32_t tiles_x = (uint32_t)((c->width + TILE_W - 1) / TILE_W), tiles_y = (uint32_t)((c->height + TILE_H - 1) / TILE_H);
-    const uint32_t n_coarse = tiles_x * tiles_y;
-    const uint32_t n_lists = LISTS_PER_TILE * n_coarse;
-    if (tiles_x >= MAX_TILES_X || tiles_y >= MAX_TILES_Y)
-        return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas %zux%zu is too large for the tile work list", c->width, c->height);
-    draw_scene::WorkSet &ws = s->sets[s->next_set];
-    const draw_scene::WorkSet &prev_ws = s->sets[s->last_set];
-    s->last_set = s->next_set;
-    s->next_set = (s->next_set + 1) % s->n_sets;
-    if (!ws.stream) {
-        // highest priority: the chain's few CTAs must get SM slots while the previous frame's k_tile
-        // (thousands of CTAs on the canvas stream) is still being dispatched
-        int prio_low = 0, prio_high = 0;
-        CU(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
-        CU(cudaStreamCreateWithPriority(&ws.stream, cudaStreamNonBlocking, g_cfg.prio ? prio_high : prio_low));
-        CU(cudaStreamCreateWithFlags(&ws.aux_stream, cudaStreamNonBlocking));
-        CU(cudaMallocHost(&ws.h_uniforms, sizeof(FrameUniforms)));
-        TRY(ws.d_uniforms.reserve(1));
-    }
-    TRY(ensure_work_buffers(s, ws, n_lists));
+// Grids of the frame's kernels, by scene size (a kernel costs the pipeline its CTAs' residency).
+void set_launch_grids(const draw_scene *s) {
+    const bool small_scene = s->dev.n_triangles <= 200000u;
+    g_clip_ctas = g_cfg.clip_ctas ? (unsigned)g_cfg.clip_ctas : (small_scene ? 74u : 296u);
+    g_bin_ctas = g_cfg.bin_ctas ? (unsigned)g_cfg.bin_ctas : (small_scene ? 296u : 592u);
+    g_raster_ctas = g_cfg.raster_ctas ? (unsigned)g_cfg.raster_ctas : (small_scene ? 592u : 1184u);
+    g_clear_ctas = (unsigned)g_cfg.clear_ctas;
+    g_tile_ctas = (unsigned)g_cfg.tile_ctas;
+}
 
-    FrameUniforms U{};
+// Frame constants that depend on the scene, the canvas and the tuning knobs (everything but the work set).
+void fill_uniforms(draw_scene *s, const draw_canvas *c, FrameUniforms &U) {
+    const uint32_t tiles_x = (uint32_t)((c->width + TILE_W - 1) / TILE_W), tiles_y = (uint32_t)((c->height + TILE_H - 1) / TILE_H);
     const m4 m = transformation_matrix(s->camera, s->width, s->height); // :904
     std::memcpy(U.m, m.v, sizeof U.m);
     plane4 planes[6];
@@ -611,8 +610,8 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     U.canvas_h = (uint32_t)c->height;
     U.tiles_x = tiles_x;
     U.tiles_y = tiles_y;
-    U.n_coarse = n_coarse;
-    U.n_lists = n_lists;
+    U.n_coarse = tiles_x * tiles_y;
+    U.n_lists = LISTS_PER_TILE * U.n_coarse;
     U.has_transparent = s->dev.n_transparent != 0;
     U.split_min_cost = (uint32_t)g_cfg.split_min_cost;
     U.split_div = (uint32_t)g_cfg.split_div;
@@ -621,13 +620,88 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     U.clear_in_tile = (uint32_t)g_cfg.clear_in_tile;
     U.bin_records_per_warp = (uint32_t)g_cfg.bin_rpw;
     U.cost_shade = (uint32_t)g_cfg.cost_shade;
-    const bool small_scene = s->dev.n_triangles <= 200000u;
-    g_clip_ctas = g_cfg.clip_ctas ? (unsigned)g_cfg.clip_ctas : (small_scene ? 74u : 296u);
-    g_bin_ctas = g_cfg.bin_ctas ? (unsigned)g_cfg.bin_ctas : (small_scene ? 296u : 592u);
-    g_raster_ctas = g_cfg.raster_ctas ? (unsigned)g_cfg.raster_ctas : (small_scene ? 592u : 1184u);
     const size_t y0 = c->stripe_y1 ? c->stripe_y0 : 0, y1 = c->stripe_y1 ? c->stripe_y1 : c->height;
     U.tile_y_begin = (uint32_t)(y0 / TILE_H);
     U.tile_y_end = (uint32_t)((y1 + TILE_H - 1) / TILE_H);
+    U.status_host = c->h_status; // pinned, mapped: the pointer is valid on the device (unified addressing)
+    U.color = c->color();
+    U.depth = c->depth();
+}
+
+// Makes one work set ready for frames of this scene / canvas geometry: its streams and pinned uniforms, its
+// buffers (key pages filled), and — unless a measurement or debug tap needs the direct path — the frame's
+// launches captured once as a CUDA graph (they do not change from frame to frame: the uniforms are read
+// from device memory).
+int ensure_set_ready(draw_scene *s, draw_scene::WorkSet &ws, const FrameUniforms &U, bool want_graph) {
+    if (!ws.stream) {
+        int prio_low = 0, prio_high = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+        CU(cudaStreamCreateWithPriority(&ws.stream, cudaStreamNonBlocking, g_cfg.prio ? prio_high : prio_low));
+        CU(cudaStreamCreateWithFlags(&ws.aux_stream, cudaStreamNonBlocking));
+        CU(cudaMallocHost(&ws.h_uniforms, sizeof(FrameUniforms)));
+        TRY(ws.d_uniforms.reserve(1));
+    }
+    TRY(ensure_work_buffers(s, ws, U.n_lists));
+    if (!want_graph) return DRAW_OK;
+    GraphKey key{};
+    key.scene = s->dev;
+    key.work = ws.work;
+    key.n_coarse = U.n_coarse; key.n_lists = U.n_lists; key.tiles_x = U.tiles_x;
+    key.tile_y_begin = U.tile_y_begin; key.tile_y_end = U.tile_y_end;
+    key.clear_ctas = g_clear_ctas + 65536u * g_tile_ctas + 7u * g_clip_ctas + 1000003u * g_bin_ctas + 15485863u * g_raster_ctas;
+    if (ws.graph_exec && std::memcmp(&key, &ws.graph_key, sizeof key) == 0) return DRAW_OK;
+    if (ws.graph_exec) CU(cudaGraphExecDestroy(ws.graph_exec));
+    ws.graph_exec = nullptr;
+    const int pdl_saved = g_pdl_enabled;
+    g_pdl_enabled = 0; // plain kernel nodes: the graph already removes the launch gaps
+    CU(cudaStreamBeginCapture(ws.stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = launch_frame(s, ws, U, ws.stream, nullptr, true);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(ws.stream, &graph);
+    g_pdl_enabled = pdl_saved;
+    if (rc != DRAW_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    CU(e);
+    const cudaError_t ei = cudaGraphInstantiate(&ws.graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    CU(ei);
+    CU(cudaGraphUpload(ws.graph_exec, ws.stream)); // the first replay does not pay the upload
+    ws.graph_key = key;
+    return DRAW_OK;
+}
+
+int enqueue_frame(draw_scene *s, draw_canvas *c) {
+    TRY(ensure_device(s->device));
+    if (s->geometry_dirty) TRY(upload_geometry(s));
+    FrameUniforms U{};
+    fill_uniforms(s, c, U);
+    if (U.tiles_x >= MAX_TILES_X || U.tiles_y >= MAX_TILES_Y)
+        return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas %zux%zu is too large for the tile work list", c->width, c->height);
+    draw_scene::WorkSet &ws = s->sets[s->next_set];
+    const draw_scene::WorkSet &prev_ws = s->sets[s->last_set];
+    s->last_set = s->next_set;
+    s->next_set = (s->next_set + 1) % s->n_sets;
+
+    set_launch_grids(s);
+    // A frame's launches are replayed as a CUDA graph: one launch call instead of nine kernels, six events and
+    // a copy.  Measurement taps and the debug taps use the direct path.
+    const bool timing = s->kernel_timing;
+    const bool use_graph = g_cfg.graphs && !timing && !s->debug_tile_cycles;
+    if (s->needs_prepare) {
+        // First frame of this scene (or of its new geometry / capacities): every work set is set up now — streams,
+        // ~30 buffers, the fill of its key pages, graph capture and instantiation — so that no later frame pays a
+        // few milliseconds of set-up in the middle of a steady stream of frames (draw_scene_prepare does the same).
+        for (int i = 0; i < s->n_sets; i++) {
+            if (s->sets[i].frame_pending) CU(cudaEventSynchronize(s->sets[i].frame_done));
+            TRY(ensure_set_ready(s, s->sets[i], U, use_graph));
+        }
+        s->needs_prepare = false;
+    }
+    if (ws.frame_pending) CU(cudaEventSynchronize(ws.frame_done)); // the pinned uniforms of the set are about to be rewritten
+    TRY(ensure_set_ready(s, ws, U, use_graph));
+
     // early trigger only for a lone frame: with other frames in flight the idle dependents would hold SM slots
     bool others_in_flight = false;
     for (int i = 0; i < s->n_sets; i++)
@@ -635,13 +709,7 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     cudaGetLastError(); // cudaErrorNotReady is not sticky, but keep the error state clean
     const int pdl_mode = g_cfg.pdl; // 0 off, 1 always early, 2 never early, 3 early for a lone frame
     g_pdl_enabled = pdl_mode != 0;
-    g_clear_ctas = (unsigned)g_cfg.clear_ctas;
-    g_tile_ctas = (unsigned)g_cfg.tile_ctas;
     U.pdl_early = pdl_mode == 1 || (pdl_mode == 3 && !others_in_flight);
-
-    U.status_host = c->h_status; // pinned, mapped: the pointer is valid on the device (unified addressing)
-    U.color = c->color();
-    U.depth = c->depth();
 
     // ---- enqueue ----------------------------------------------------------------------------------
     // Everything of the frame runs on the work set's own streams: the geometry chain and k_tile on
@@ -651,59 +719,26 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     // use different work sets are therefore independent and overlap; a set's next frame follows its
     // previous one in stream order.
     cudaStream_t side = ws.stream, st = c->stream;
-    if (ws.frame_pending) CU(cudaEventSynchronize(ws.frame_done)); // the pinned uniforms of the set are about to be rewritten
     *ws.h_uniforms = U;
     // what the canvas stream still does with the canvas comes before the two kernels that write it
     // (k_clear_empty, k_tile wait for this event; the geometry chain does not touch the canvas and does not wait)
     CU(cudaEventRecord(ws.canvas_ready, st));
     if (s->dev.n_transparent) {
         // the painter sort rewrites the shared index streams: order it after the previous frame's geometry
+        // (geo_done is a real event in both paths: launch_frame records it with cudaEventRecordExternal under capture)
         if (&prev_ws != &ws && prev_ws.frame_pending) CU(cudaStreamWaitEvent(side, prev_ws.geo_done, 0));
     }
-    if (ws.work.tile_cycles) CU(cudaMemsetAsync(ws.work.tile_cycles, 0, n_lists * sizeof(uint32_t), side)); // debug taps are atomicMax'd
+    if (ws.work.tile_cycles) CU(cudaMemsetAsync(ws.work.tile_cycles, 0, U.n_lists * sizeof(uint32_t), side)); // debug taps are atomicMax'd
 
     cudaEvent_t *ev = nullptr;
-    if (s->kernel_timing) {
+    if (timing) {
         for (int i = 0; i < N_FRAME_KERNELS + 4; i++)
             if (!s->kev[i]) CU(cudaEventCreate(&s->kev[i]));
         ev = s->kev;
         s->kev_recorded = true;
     }
-    // A frame's launches do not change from frame to frame (the uniforms are read from device memory), so
-    // they are captured once per work set as a CUDA graph and replayed: one launch call instead of nine
-    // kernels, six events and a copy.  Measurement taps, the debug taps and scenes whose painter sort
-    // uploads indices between frames use the direct path.
-    const bool use_graph = g_cfg.graphs && !ev && !ws.work.tile_cycles && s->dev.n_transparent == 0;
-    if (use_graph) {
-        GraphKey key{};
-        key.scene = s->dev;
-        key.work = ws.work;
-        key.n_coarse = U.n_coarse; key.n_lists = U.n_lists; key.tiles_x = U.tiles_x;
-        key.tile_y_begin = U.tile_y_begin; key.tile_y_end = U.tile_y_end; key.clear_ctas = g_clear_ctas + 65536u * g_tile_ctas + 7u * g_clip_ctas + 1000003u * g_bin_ctas + 15485863u * g_raster_ctas;
-        if (!ws.graph_exec || std::memcmp(&key, &ws.graph_key, sizeof key) != 0) {
-            if (ws.graph_exec) CU(cudaGraphExecDestroy(ws.graph_exec));
-            ws.graph_exec = nullptr;
-            const int pdl_saved = g_pdl_enabled;
-            g_pdl_enabled = 0; // plain kernel nodes: the graph already removes the launch gaps
-            CU(cudaStreamBeginCapture(side, cudaStreamCaptureModeThreadLocal));
-            const int rc = launch_frame(s, ws, U, side, nullptr, true);
-            cudaGraph_t graph = nullptr;
-            const cudaError_t e = cudaStreamEndCapture(side, &graph);
-            g_pdl_enabled = pdl_saved;
-            if (rc != DRAW_OK) {
-                if (graph) cudaGraphDestroy(graph);
-                return rc;
-            }
-            CU(e);
-            const cudaError_t ei = cudaGraphInstantiate(&ws.graph_exec, graph, 0);
-            cudaGraphDestroy(graph);
-            CU(ei);
-            ws.graph_key = key;
-        }
-        CU(cudaGraphLaunch(ws.graph_exec, side));
-    } else {
-        TRY(launch_frame(s, ws, U, side, ev, false));
-    }
+    if (use_graph) CU(cudaGraphLaunch(ws.graph_exec, side));
+    else TRY(launch_frame(s, ws, U, side, ev, false));
     CU(cudaEventRecord(ws.frame_done, side));
     ws.frame_pending = true;
     CU(cudaStreamWaitEvent(st, ws.frame_done, 0));
@@ -712,6 +747,11 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     c->frame_pending = true;
     c->host_dirty = true;
     c->last_scene = s;
+    c->pending_inputs.camera = s->camera;
+    c->pending_inputs.light = s->light;
+    c->pending_inputs.off_x = c->off_x; c->pending_inputs.off_y = c->off_y;
+    c->pending_inputs.stripe_y0 = c->stripe_y0; c->pending_inputs.stripe_y1 = c->stripe_y1;
+    c->pending_inputs.depth_max = c->depth_max;
     if (c->host_mirror && !c->ext_color) {
         // the frame follows its render to the host without waiting for the host to ask (map_host then only waits)
         const size_t bytes = c->width * c->height * 4;
@@ -754,8 +794,26 @@ int finish_frame(draw_canvas *c) {
             s->rec_cap = std::max<size_t>((size_t)n_rec + n_rec / 4 + 1024, 4 * (size_t)s->dev.n_triangles + 1024);
         if (overflow & OVERFLOW_REFS) s->refs_cap = (size_t)n_refs + n_refs / 4 + 4096;
         else if (overflow & OVERFLOW_RECORDS) s->refs_cap = std::max(s->refs_cap, 4 * s->rec_cap);
-        CU(cudaDeviceSynchronize()); // both work sets are about to be reallocated
-        TRY(enqueue_frame(s, c));
+        CU(cudaDeviceSynchronize()); // the work sets are about to be reallocated
+        s->needs_prepare = true;
+        // Render the frame again from the inputs it was rendered with (the scene's camera / light and the
+        // canvas' offset / stripe may have moved on since), then put the current state back.
+        const draw_canvas::FrameInputs in = c->pending_inputs;
+        const CameraState cam_now = s->camera;
+        const f3 light_now = s->light;
+        const int off_x_now = c->off_x, off_y_now = c->off_y;
+        const size_t sy0_now = c->stripe_y0, sy1_now = c->stripe_y1;
+        const float dmax_now = c->depth_max;
+        s->camera = in.camera; s->light = in.light;
+        c->off_x = in.off_x; c->off_y = in.off_y;
+        c->stripe_y0 = in.stripe_y0; c->stripe_y1 = in.stripe_y1;
+        c->depth_max = in.depth_max;
+        const int rc = enqueue_frame(s, c);
+        s->camera = cam_now; s->light = light_now;
+        c->off_x = off_x_now; c->off_y = off_y_now;
+        c->stripe_y0 = sy0_now; c->stripe_y1 = sy1_now;
+        c->depth_max = dmax_now;
+        TRY(rc);
         CU(cudaStreamSynchronize(c->stream));
     }
     return DRAW_OK;
@@ -896,20 +954,21 @@ int draw_scene_add_object(draw_scene *scene, const draw_object_desc *desc, uint3
         w = m.width; h = m.height;
         return DRAW_OK;
     };
-    std::vector<std::pair<const uint8_t *, uint32_t>> seen; // identical images (map_Ka == map_Kd is common) share storage
+    struct SeenMap { const uint8_t *pixels; uint32_t w, h, comp, off; };
+    std::vector<SeenMap> seen; // identical images (map_Ka == map_Kd is common) share storage
     for (size_t i = 0; i < desc->n_materials; i++) {
         const draw_material &m = desc->materials[i];
         MaterialDev d{};
         for (int c = 0; c < 3; c++) { d.ka[c] = m.ka[c]; d.kd[c] = m.kd[c]; d.ks[c] = m.ks[c]; }
         d.alpha = m.alpha;
         auto add_dedup = [&](const draw_texture_map &tm, uint32_t &off, uint32_t &w, uint32_t &h) -> int {
-            for (auto &pr : seen)
-                if (tm.pixels && pr.first == tm.pixels) {
-                    off = pr.second; w = tm.width; h = tm.height;
+            for (const SeenMap &sm : seen) // same pointer AND same layout: a sub-image or another component view is a different map
+                if (tm.pixels && sm.pixels == tm.pixels && sm.w == tm.width && sm.h == tm.height && sm.comp == tm.components) {
+                    off = sm.off; w = tm.width; h = tm.height;
                     return DRAW_OK;
                 }
             TRY(add_map(tm, off, w, h));
-            if (tm.pixels) seen.push_back({tm.pixels, off});
+            if (tm.pixels) seen.push_back({tm.pixels, tm.width, tm.height, tm.components, off});
             return DRAW_OK;
         };
         TRY(add_dedup(m.map_ka, d.ka_off, d.ka_w, d.ka_h));
@@ -938,6 +997,7 @@ int draw_scene_add_object(draw_scene *scene, const draw_object_desc *desc, uint3
     scene->objects.push_back(std::move(o));
     scene->geometry_dirty = true;
     scene->rec_cap = scene->refs_cap = 0; // re-derive capacities for the new triangle count
+    scene->needs_prepare = true;
     if (out_id) *out_id = (uint32_t)scene->objects.size() - 1;
     return DRAW_OK;
     GUARD_END
@@ -1010,6 +1070,30 @@ int draw_scene_render(draw_scene *scene, draw_canvas *canvas) {
     }
     canvas->stats.overflow = 0;
     return enqueue_frame(scene, canvas);
+    GUARD_END
+}
+
+int draw_scene_prepare(draw_scene *scene, draw_canvas *canvas) {
+    GUARD_BEGIN
+    if (!scene || !canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "scene or canvas is NULL");
+    if (scene->device != canvas->device)
+        return fail(DRAW_ERR_INVALID_ARGUMENT, "scene (device %d) and canvas (device %d) live on different devices",
+                    scene->device, canvas->device);
+    TRY(ensure_device(scene->device));
+    if (scene->geometry_dirty) TRY(upload_geometry(scene));
+    FrameUniforms U{};
+    fill_uniforms(scene, canvas, U);
+    if (U.tiles_x >= MAX_TILES_X || U.tiles_y >= MAX_TILES_Y)
+        return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas %zux%zu is too large for the tile work list", canvas->width, canvas->height);
+    set_launch_grids(scene);
+    const bool use_graph = g_cfg.graphs && !scene->kernel_timing && !scene->debug_tile_cycles;
+    for (int i = 0; i < scene->n_sets; i++) {
+        if (scene->sets[i].frame_pending) CU(cudaEventSynchronize(scene->sets[i].frame_done));
+        TRY(ensure_set_ready(scene, scene->sets[i], U, use_graph));
+    }
+    scene->needs_prepare = false;
+    CU(cudaDeviceSynchronize()); // key pages are filled, graphs uploaded: the next render only enqueues
+    return DRAW_OK;
     GUARD_END
 }
 

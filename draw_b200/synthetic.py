@@ -145,3 +145,13 @@ def flythrough_camera(n_frames=120):
     pos = np.stack([30.0 * np.sin(2 * np.pi * k / 120.0), np.full_like(k, 10.0), 150.0 - 2.5 * k], 1)
     dr = np.stack([0.3 * np.sin(2 * np.pi * k / 60.0), np.full_like(k, -0.05), np.full_like(k, -1.0)], 1)
     return np.concatenate([pos, dr], 1).astype(F)
+
+
+def orbit_camera(n_frames=64):
+    """C2 / C3 bench camera path: a small orbit about the default camera so that every step renders a different
+    frame of the same scene: pos_k = (15 sin(2 pi k/n), 8 sin(4 pi k/n), 150), dir_k = -pos_k (looking at the
+    origin), evaluated in float64 and rounded once to float32.  Frame 0 is the default camera
+    (scene/mod.rs:763-765).  Returns float32 [n_frames, 6]."""
+    k = np.arange(n_frames, dtype=np.float64)
+    pos = np.stack([15.0 * np.sin(2 * np.pi * k / n_frames), 8.0 * np.sin(4 * np.pi * k / n_frames), np.full_like(k, 150.0)], 1)
+    return np.concatenate([pos, -pos], 1).astype(F)

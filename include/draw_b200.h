@@ -130,6 +130,11 @@ int draw_scene_set_light(draw_scene *scene, const float pos[3]);
 /* Scene::render(&mut Canvas) :901 — THE hot path.  Enqueues the frame on the canvas' stream
  * and returns without waiting; the first host read (map_host / read_depth / sync) waits. */
 int draw_scene_render(draw_scene *scene, draw_canvas *canvas);
+/* Not in the reference (its first frame allocates nothing): sets up everything later frames of this scene on
+ * this canvas' geometry need — every frame-in-flight slot's streams and work buffers, its key pages, the
+ * captured frame graph — and waits for it, so that the first draw_scene_render costs what the others do.
+ * Optional: the first render after draw_scene_add_object does the same set-up without waiting. */
+int draw_scene_prepare(draw_scene *scene, draw_canvas *canvas);
 /* Debug / parity taps: matrix_transf (:817-899, row-major 16 floats) and the six view planes
  * (:481-593) as near, far, right, left, top, bottom, each (nx, ny, nz, k). */
 int draw_scene_get_uniforms(draw_scene *scene, float matrix[16], float planes[24]);

@@ -60,6 +60,7 @@ def main():
         print(f"{name}: {len(objs)} objects, {tris} triangles, {verts} vertices, "
               f"{os.path.getsize(path) / 1e6:.2f} MB")
     np.save(os.path.join(os.path.dirname(args.out), "c4_camera_path.npy"), synthetic.flythrough_camera(120))
+    np.save(os.path.join(os.path.dirname(args.out), "orbit_camera_path.npy"), synthetic.orbit_camera(64))
 
 
 if __name__ == "__main__":
