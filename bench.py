@@ -504,16 +504,12 @@ def run_ours(args, cfg):
 
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
-        # k_tile (the longest kernel of the frame: `roofline`) writes the frame.  Algorithmic bytes of a launch =
-        # 8 B per pixel (colour + depth, once) + the bound textures (read at most once).
+        # k_tile (the longest kernel of the frame: `roofline`) writes the whole frame once.  Algorithmic bytes of a launch =
+        # 8 B per pixel (colour + depth) + the bound textures (read at most once).
         st = ring[0].last_frame_stats()
-        tile_px = draw_b200.tile_size() * 64
-        clear_bytes = min(8 * W * H, 8 * tile_px * st["empty_tiles"])  # border tiles counted whole: slight over-count
-        fused_clear = bool(st.get("clear_in_tile"))  # k_tile's CTAs write the empty tiles too: it owns the whole frame
-        tile_bytes = 8 * W * H - (0 if fused_clear else clear_bytes) + cfg["tex_bytes"]
+        tile_bytes = 8 * W * H + cfg["tex_bytes"]
         t_tile = kmean["k_tile"] * 1e-3
         achieved = tile_bytes / t_tile / 1e9
-        clear_gbs = None if fused_clear else clear_bytes / (kmean["k_clear_empty"] * 1e-3) / 1e9
         s_per_frame = ms_total * 1e-3 / frames_rank
         frame_gbs = cfg["algo_bytes_frame"] / s_per_frame / 1e9
         lone_ms = float(np.median(per_frame))
@@ -547,18 +543,14 @@ def run_ours(args, cfg):
             "roofline": {"bound": "hbm", "kernel": "k_tile", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic("k_tile", args.config), "peak_source": peak_src,
                          "algo_bytes_per_launch": tile_bytes,
-                         "note": ("k_tile writes the whole frame once — 8 B/pixel: the rasterised tiles from shared memory, the "
-                                  "empty tiles as streaming stores between its raster items — and reads the bound textures; "
-                                  if fused_clear else
-                                  "k_tile writes the non-empty tiles (8 B/pixel) and reads the bound textures; k_clear_empty "
-                                  "(under `clear`) writes the empty tiles; ") +
+                         "note": "k_tile writes the whole frame once — 8 B/pixel: the rasterised tiles from shared memory, the "
+                                 "empty tiles as streaming stores between its raster items — and reads the bound textures; "
                                  "its duration is event-timed with the frame's kernels run one after the other. `frame_*` = "
                                  "SURVEY.md 8(d) ALGO_BYTES(frame) / time per frame of the timed region (frames overlapped)",
-                         "clear": None if fused_clear else {
-                             "kernel": "k_clear_empty", "achieved": clear_gbs, "frac": clear_gbs / peak,
-                             "algo_bytes_per_launch": clear_bytes, "empty_tiles": st["empty_tiles"],
-                             "traffic": ncu_traffic("k_clear_empty", args.config)},
-                         "empty_tiles": st["empty_tiles"],
+                         "empty_tiles": st["empty_tiles"], "work_items": st["work_items"],
+                         "refs": {k: st[k] for k in ("large_refs", "medium_refs", "small_refs", "transparent_refs")},
+                         "k_front_phase_us": dict(zip(("vertex", "barrier1", "triangle", "barrier2_and_huge", "tile", "triangle_slowest_cta", "huge"),
+                                                      (x / 1e3 for x in st["front_phase_ns"]))),
                          "frame_algo_bytes": cfg["algo_bytes_frame"], "frame_achieved": frame_gbs,
                          "frame_frac": frame_gbs / peak,
                          "fill": fill_roofline(args.config, s_per_frame, (clocks or {}).get("sm_mhz"))},

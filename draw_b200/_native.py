@@ -42,13 +42,15 @@ class ObjectDesc(C.Structure):
 
 
 class FrameStats(C.Structure):
-    _fields_ = [("input_triangles", C.c_uint32), ("setup_records", C.c_uint32), ("tile_refs", C.c_uint32),
-                ("transparent_slots", C.c_uint32), ("overflow", C.c_uint32), ("empty_tiles", C.c_uint32),
-                ("key_pages", C.c_uint32), ("clear_in_tile", C.c_uint32)]
+    _NAMES = ("input_triangles", "setup_records", "tile_refs", "large_refs", "medium_refs", "small_refs", "transparent_refs",
+              "overflow", "empty_tiles", "work_items")
+    _fields_ = [(n, C.c_uint32) for n in _NAMES] + [("front_phase_ns", C.c_uint32 * 7), ("front_block_ns", C.c_uint32 * 5)]
 
     def as_dict(self):
-        return {n: int(getattr(self, n)) for n in ("input_triangles", "setup_records", "tile_refs",
-                                                   "transparent_slots", "overflow", "empty_tiles", "key_pages", "clear_in_tile")}
+        d = {n: int(getattr(self, n)) for n in self._NAMES}
+        d["front_phase_ns"] = [int(x) for x in self.front_phase_ns]
+        d["front_block_ns"] = [int(x) for x in self.front_block_ns]
+        return d
 
 
 IMAGE_LOADER = C.CFUNCTYPE(C.c_int, C.c_char_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32),
@@ -99,6 +101,12 @@ SIGNATURES = {
     "draw_canvas_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "draw_canvas_stream_wait": (C.c_int, [C.c_void_p, C.c_void_p]),
     "draw_canvas_set_stripe": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t]),
+    "draw_canvas_set_tile_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "draw_device_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "draw_device_free": (C.c_int, [C.c_void_p]),
+    "draw_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "draw_flag_signal": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "draw_flags_wait": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "draw_tile_size": (C.c_int, []),
     "draw_canvas_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "draw_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -129,8 +137,8 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.draw_version() != 100:
-            raise ImportError(f"libdraw_b200.so version {L.draw_version()} does not match this binding (100)")
+        if L.draw_version() != 200:
+            raise ImportError(f"libdraw_b200.so version {L.draw_version()} does not match this binding (200)")
         _lib = L
     return _lib
 

@@ -162,6 +162,10 @@ class Canvas:
     def set_stripe(self, y0, y1):
         N.check(N.lib().draw_canvas_set_stripe(self._h, y0, y1))
 
+    def set_tile_rows(self, phase, step):
+        """Sort-first, interleaved: render only the tile rows ty with ty % step == phase."""
+        N.check(N.lib().draw_canvas_set_tile_rows(self._h, int(phase), int(step)))
+
 
 class ObjectInfo:
     """scene/object.rs:12-16."""
@@ -263,21 +267,20 @@ class Scene:
         N.check(N.lib().draw_scene_read_vertex_visual(self._h, canvas._h, first, count, out.ctypes.data))
         return out
 
-    KERNELS = ("k_vertex", "k_setup", "k_clip", "k_bin_count", "k_alloc", "k_bin_fill", "k_raster", "k_clear_empty", "k_tile", "k_shade")
-
-    OPTIONAL_KERNELS = ("k_clear_empty", "k_shade")
+    KERNELS = ("k_sort_transparent", "k_front", "k_raster", "k_tile")
+    OPTIONAL_KERNELS = ("k_sort_transparent",)
 
     def set_kernel_timing(self, enabled):
         N.check(N.lib().draw_scene_set_kernel_timing(self._h, 1 if enabled else 0))
 
     def last_kernel_times(self, canvas):
         """Device time (ms) of each kernel of the last frame, keyed by kernel name."""
-        ms = (C.c_float * 10)()
+        ms = (C.c_float * 4)()
         N.check(N.lib().draw_scene_last_kernel_times(self._h, canvas._h, ms))
         return dict(zip(self.KERNELS, (float(x) for x in ms)))
 
     def debug_list_counts(self, canvas):
-        """(large, medium, small) list sizes per tile of the last frame, as uint32 arrays."""
+        """Per tile of the last frame: large references, medium / small weight, transparent references (uint32 arrays)."""
         nc = C.c_size_t()
         N.check(N.lib().draw_scene_debug_list_counts(self._h, canvas._h, None, 0, C.byref(nc)))
         n = nc.value * 3
@@ -300,9 +303,9 @@ class Scene:
             return None
         nc = C.c_size_t()
         N.check(N.lib().draw_scene_debug_list_counts(self._h, canvas._h, None, 0, C.byref(nc)))
-        out = np.zeros(nc.value * 3, np.uint32)
-        N.check(N.lib().draw_scene_debug_tile_cycles(self._h, canvas._h, 1 if enable else 0, out.ctypes.data, nc.value * 3))
-        return out.reshape(3, nc.value)  # rows: whole CTA, end of phase A, end of phase B (cycles since CTA start)
+        out = np.zeros(nc.value * 4, np.uint32)
+        N.check(N.lib().draw_scene_debug_tile_cycles(self._h, canvas._h, 1 if enable else 0, out.ctypes.data, nc.value * 4))
+        return out.reshape(4, nc.value)  # rows: whole item, end of phase A, of phase C, of phase D (cycles since the item started)
 
     def counts(self):
         a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()

@@ -13,21 +13,6 @@
 
 namespace drawb200 {
 
-// Programmatic dependent launch: the frame's kernels are launched back to back on one stream with
-// cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel's CTAs may become resident
-// while the previous kernel drains.  Every kernel calls pdl_prologue() first: it lets its own
-// dependents launch early and then waits until the kernels it depends on have completed and their
-// writes are visible (griddepcontrol.wait), which preserves plain stream-order semantics for data.
-// `early` (FrameUniforms::pdl_early): trigger before doing any work, which hides the whole launch
-// latency of the dependent kernel but makes its CTAs resident (and idle) for the duration of this
-// kernel — right for a lone frame, wrong when several frames are in flight and those slots are
-// needed by another frame's kernels; otherwise dependents launch when this kernel's CTAs exit.
-__device__ __forceinline__ void pdl_prologue(bool early = true) {
-#if __CUDA_ARCH__ >= 900
-    if (early) cudaTriggerProgrammaticLaunchCompletion();
-    cudaGridDependencySynchronize();
-#endif
-}
 // Debug timeline (draw_scene_debug_trace): thread 0 of every CTA of the frame kernels records
 // (kernel id | SM << 8 | work set << 24, CTA index, start, end) with the nanosecond global timer, so that
 // the overlap of the frames in flight can be looked at without a system profiler.  Off (null pointer)
@@ -56,31 +41,6 @@ struct CtaTrace {
         }
     }
 };
-
-// per-call launch configuration, set by enqueue_frame (scene.cpp) on the calling thread: handles may be used from
-// different threads
-extern thread_local int g_kernel_priority_set, g_kernel_priority;
-extern thread_local int g_pdl_enabled; // scene.cpp (DRAW_B200_PDL=0 launches without the attribute)
-template <typename... KArgs, typename... Args>
-inline void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t stream, Args... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(block);
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
-    int n_attr = 0;
-    if (g_pdl_enabled) {
-        attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[n_attr++].val.programmaticStreamSerializationAllowed = 1;
-    }
-    if (g_kernel_priority_set) { // scene.cpp: the geometry chain above the tile kernels (DRAW_B200_KPRIO)
-        attr[n_attr].id = cudaLaunchAttributePriority;
-        attr[n_attr++].val.priority = g_kernel_priority;
-    }
-    cfg.attrs = attr;
-    cfg.numAttrs = n_attr;
-    cudaLaunchKernelEx(&cfg, kernel, args...);
-}
 
 #define FADD(a, b) __fadd_rn((a), (b))
 #define FSUB(a, b) __fsub_rn((a), (b))

@@ -5,12 +5,14 @@
 
 namespace drawb200 {
 
-// Screen partition.  A CTA of k_tile owns one tile of TILE_W x TILE_H pixels and keeps its depth /
-// winner / colour on chip.  Each tile has three lists of raster records, classed by the area of
-// (record bbox intersected with the tile):
-//   large   list id = tile                  > MEDIUM_AREA px : every lane tests its own pixels
-//   medium  list id = n_coarse + tile       <= MEDIUM_AREA px: one record per warp, lane per pixel
-//   small   list id = 2 * n_coarse + tile   <= SMALL_AREA px : one record per lane
+// Screen partition.  A CTA of k_tile owns one tile of TILE_W x TILE_H pixels (or a window of one) and keeps
+// its depth / winner / colour on chip.  A (record, tile) reference is classed by the area of the record's
+// bbox inside the tile:
+//   large   > MEDIUM_AREA px : per-tile list (FrameDev::list_refs); k_tile, every lane tests its own pixels
+//   medium  <= MEDIUM_AREA px: frame-wide list m_refs; k_raster, one reference per warp, lane per pixel
+//   small   <= SMALL_AREA px : frame-wide list s_refs; k_raster, one reference per lane
+// Medium and small fragments go to the tile's key page (64-bit atomicMin in L2); k_tile starts from the page.
+// Transparent records have per-tile lists of their own (t_refs), consumed in draw order by k_tile.
 // REGION is the square each warp owns during the large-record phase (8 pixels per lane).
 #ifndef DRAW_TILE_W
 #define DRAW_TILE_W 64
@@ -26,8 +28,7 @@ constexpr int TILE_W = DRAW_TILE_W, TILE_H = DRAW_TILE_H, REGION = 16;
 #define DRAW_SMALL_AREA 8
 #endif
 constexpr int SMALL_AREA = DRAW_SMALL_AREA, MEDIUM_AREA = DRAW_MEDIUM_AREA;
-constexpr int LISTS_PER_TILE = 3;
-constexpr uint32_t NO_SLOT = 0xFFFFFFFFu, NO_PAGE = 0xFFFFFFFFu;
+constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
 constexpr unsigned long long KEY_EMPTY = ~0ull;
 #ifndef DRAW_TILE_THREADS
 #define DRAW_TILE_THREADS 256
@@ -38,12 +39,12 @@ constexpr int TILE_THREADS = DRAW_TILE_THREADS;
 constexpr int BLK_H = TILE_W * TILE_H / TILE_THREADS / 4;
 constexpr int REGION_H = 8 * BLK_H;
 
-// k_tile work items, built by k_alloc (heaviest first).  An item is a tile plus a pixel window of it in
+// k_tile work items, built by k_front (heaviest first).  An item is a tile plus a pixel window of it in
 // units of warp regions (a 4x4 grid of REGION x REGION_H rectangles): the whole tile, or one of the
 // 2 / 4 / 8 / 16 windows a dense tile is cut into.
-//   bits 0-9 tile x | 10-20 tile y | 21-22 window x0 | 23-24 window y0 | 25-26 window w-1 | 27-28 window h-1 | 29 ITEM_DEFER
-// Tiles with nothing binned to them are not items: they are listed in FrameDev::empty_tiles (as
-// x | y << 10, count in counters[13]) and written by k_clear_empty.
+//   bits 0-9 tile x | 10-20 tile y | 21-22 window x0 | 23-24 window y0 | 25-26 window w-1 | 27-28 window h-1
+// Tiles with nothing to draw are not items: they are listed in FrameDev::empty_tiles (as x | y << 10,
+// count in counters[CNT_EMPTY]) and written by k_tile's CTAs between their items.
 constexpr int REGIONS_X = TILE_W / REGION, REGIONS_Y = TILE_H / REGION_H;
 constexpr bool TILE_SPLITTABLE = REGIONS_X == 4 && (REGIONS_Y == 4 || REGIONS_Y == 2);
 #ifndef DRAW_TILE_MAX_SPLIT
@@ -53,15 +54,13 @@ constexpr bool TILE_SPLITTABLE = REGIONS_X == 4 && (REGIONS_Y == 4 || REGIONS_Y 
 #define DRAW_TILE_SPLIT_MIN_COST 256
 #endif
 constexpr int TILE_MAX_SPLIT = DRAW_TILE_MAX_SPLIT < REGIONS_X * REGIONS_Y ? DRAW_TILE_MAX_SPLIT : REGIONS_X * REGIONS_Y; // 1, 2, 4, 8 or 16
-constexpr int TILE_SPLIT_MIN_COST = DRAW_TILE_SPLIT_MIN_COST; // windows are not made cheaper than this (k_alloc cost units)
+constexpr int TILE_SPLIT_MIN_COST = DRAW_TILE_SPLIT_MIN_COST; // windows are not made cheaper than this (k_front cost units)
 constexpr int TILE_EXTRA_ITEMS = 1024;                        // work-list slots beyond one per tile
 #ifndef DRAW_TILE_SPLIT_DIV
 #define DRAW_TILE_SPLIT_DIV 296
 #endif
 constexpr int TILE_SPLIT_DIV = DRAW_TILE_SPLIT_DIV;           // a window should cost about total / this (<= TILE_EXTRA_ITEMS)
 constexpr uint32_t ITEM_NONE = 0xFFFFFFFFu;
-constexpr uint32_t ITEM_DEFER = 1u << 29; // k_tile only adds the large triangles to the tile's key page; k_shade shades it
-constexpr int N_COUNTERS = 64, ITEM_CURSOR = 32; // FrameDev::counters; k_tile's item cursor sits in the second 128-byte line
 constexpr uint32_t MAX_TILES_X = 1u << 10, MAX_TILES_Y = 1u << 11;
 #if defined(__CUDACC__)
 __host__ __device__
@@ -83,21 +82,30 @@ struct FrameUniforms {
     float off_x, off_y; // canvas offset (canvas.rs:382-385)
     float depth_max;    // canvas.rs:403
     uint32_t canvas_w, canvas_h;
-    uint32_t tiles_x, tiles_y;         // whole canvas, in coarse tiles
-    uint32_t tile_y_begin, tile_y_end; // coarse tile rows rendered by this launch (sort-first stripe)
+    uint32_t tiles_x, tiles_y;         // whole canvas, in tiles
+    // Tile rows rendered by this launch (sort-first partition): rows ty in [tile_y_begin, tile_y_end) with
+    // ty % row_step == row_phase.  The whole canvas is (0, tiles_y, 1, 0).
+    uint32_t tile_y_begin, tile_y_end, row_step, row_phase;
     uint32_t n_coarse;                 // tiles_x * tiles_y
-    uint32_t n_lists;                  // LISTS_PER_TILE * n_coarse: large, medium, small lists
-    uint32_t split_min_cost, split_div, split_max; // k_alloc's tile splitting policy (defaults: TILE_SPLIT_*)
-    uint32_t defer_max;                // tiles with a key page and fewer large references than this are shaded by k_shade
-    uint32_t *status_host;             // pinned host memory of the canvas (device-mapped): k_tile copies counters[0..15] there
+    uint32_t split_min_cost, split_div, split_max; // k_front's tile splitting policy (defaults: TILE_SPLIT_*)
+    uint32_t bar_base;                 // value of the work set's grid-barrier counter when k_front starts (host-tracked)
+    uint32_t *status_host;             // pinned host memory of the canvas (device-mapped): k_tile copies counters[0..31] there
     uint8_t *color;                    // the canvas: BGRA8, row 0 = top (canvas.rs:955-956)
     float *depth;                      // depth buffer, row 0 = y 0 (canvas.rs:413-423)
-    uint32_t has_transparent;          // transparent triangles are not binned: no tile may take the empty-tile path
-    uint32_t pdl_early;                // geometry / binning kernels trigger their dependents at once (device_math.cuh)
-    uint32_t cost_shade;               // k_alloc's cost of shading one fully covered tile (same units as COST_* in k_binning.cu)
-    uint32_t bin_records_per_warp;     // k_bin: with at most this many records per warp of its grid a warp takes a record, else a thread
-    uint32_t clear_in_tile;            // k_tile's CTAs write the empty tiles between their items; no k_clear_empty launch
 };
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline bool row_is_mine(const FrameUniforms &U, uint32_t ty) {
+    return ty >= U.tile_y_begin && ty < U.tile_y_end && ty % U.row_step == U.row_phase;
+}
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline uint32_t rows_mine(const FrameUniforms &U) { // number of tile rows this launch renders
+    uint32_t first = U.tile_y_begin + (U.row_phase + U.row_step - U.tile_y_begin % U.row_step) % U.row_step;
+    return first < U.tile_y_end ? (U.tile_y_end - 1 - first) / U.row_step + 1 : 0;
+}
 
 // Texture (scene/mod.rs:206-216) with both TextureMaps flattened into the texel pool.  Maps are
 // stored with 4 bytes per texel (3-component images are padded at upload) so that a texel is one
@@ -111,11 +119,15 @@ struct alignas(16) MaterialDev {
     uint32_t ka_h;
 };
 
-// Scene geometry, SoA, all objects concatenated (indices are global after upload).
+// Scene geometry, all objects concatenated (indices are global after upload).  Positions exist twice: as SoA
+// streams for the per-vertex pass (coalesced 128-bit loads, four vertices per thread) and packed as float4 for
+// the per-triangle gathers (one 16-byte load = one 32-byte sector per corner instead of three).  Normals and
+// uvs are only ever gathered: packed only.
 struct SceneDev {
-    const float *px, *py, *pz;       // positions           [n_vertices]
-    const float *nx, *ny, *nz;       // normals             [n_normals]
-    const float *tu, *tv;            // uv                  [n_uvs]
+    const float *px, *py, *pz;       // positions, SoA                [n_vertices]
+    const float4 *pos4;              // positions, packed (x, y, z, 0) [n_vertices]
+    const float4 *nrm4;              // normals, packed (x, y, z, 0)   [n_normals]
+    const float2 *uv2;               // uv                             [n_uvs]
     const uint32_t *idx[9];          // v0 v1 v2 t0 t1 t2 n0 n1 n2, one stream each [n_triangles]
     const uint32_t *tri_mat;         // material id | (transparent << 31), draw order [n_triangles]
     const uint32_t *tri_tslot;       // transparent triangles: ordinal among them; else unused (may be null)
@@ -163,41 +175,56 @@ struct alignas(16) ShadeRec {
 
 // Per-frame work buffers (owned by the scene, sized for the scene and the canvas).
 struct FrameDev {
-    float *v_lx, *v_ly, *v_lz;  // light     (scene/mod.rs:922)
-    float *v_hx, *v_hy, *v_hz;  // halfway   (:925)
-    float *v_depth;             // :924
-    float *v_sx, *v_sy;         // screen xy after the divide (:1047-1058), before the canvas offset
-    uint32_t *v_flags;          // 2 bits per plane: bit 2p = f>0, bit 2p+1 = f<=0
+    float4 *vA;                 // per vertex: screen x, y after the divide (scene/mod.rs:1047-1058, before the canvas
+                                // offset), depth (:924), plane-side flags as bits (2 per plane: bit 2p = f>0, bit 2p+1 = f<=0)
+    float4 *vLH;                // per vertex, 2 x float4 = one 32-byte sector: light xyz (:922), halfway xyz (:925), 0, 0
     RasterRec *rrec;            // opaque records, slots in draw order [rec_cap]
-    PrepRec *prep;              // the same records prepared for rasterisation (k_bin<count>) [rec_cap]
+    PrepRec *prep;              // the same records prepared for rasterisation [rec_cap]
     ShadeRec *srec;
     RasterRec *t_rrec;          // transparent records, slot = 4*ordinal + k, in draw order [4*n_transparent]
+    PrepRec *t_prep;
     ShadeRec *t_srec;
-    uint32_t *list_count;       // per list (large, medium, small per tile): count, then fill cursor [n_lists]
-    uint32_t *list_offset;      // first entry of each list in list_refs [n_lists + 1]
+    // per tile [n_coarse]
+    uint32_t *l_count, *t_count;   // large / transparent references: count (k_front P1), then fill cursor (k_raster), then count again
+    uint32_t *l_offset, *t_offset; // first entry of the tile's list in list_refs / t_refs
+    uint32_t *ms_weight;           // medium / small references of the tile, weighed by their 8x4 blocks: non-zero = k_raster
+                                   // may have put fragments in the tile's key page
+    // reference lists
+    uint2 *l_pairs, *t_pairs;   // (tile, slot) pairs appended by k_front, scattered into the tiles' lists by k_raster's prologue [refs_cap]
     uint32_t *list_refs;        // large lists: record slots [refs_cap]
-    uint2 *m_refs, *s_refs;     // medium / small lists: (record slot, tile x | y << 10) [refs_cap each]
-    uint32_t *tile_page;        // key page of each tile, or NO_PAGE [n_coarse]
-    unsigned long long *key_pages; // page p = TILE_W * TILE_H keys (depth key << 32 | slot), all ones = empty; k_raster
-                                   // fills them with atomicMin, k_tile consumes and resets them [page_cap pages]
-    uint32_t page_cap;
-    uint32_t *counters;         // [0] records  [1] refs  [2] overflow bits  [3] k_setup CTA ticket  [4] k_alloc CTAs done  [5] clip queue length
-                                // [6] total tile cost  [8..10] large / medium / small references  [11] key pages handed out  [13] empty tiles  [14] tiles for k_shade  [15] k_tile items  [32] k_tile item cursor  [N_COUNTERS]
-    uint32_t *tile_cost;        // estimated k_tile work per tile [n_coarse]
-    uint32_t *tile_order;       // k_tile work items (make_item), heaviest first, padded with ITEM_NONE [n_coarse + TILE_EXTRA_ITEMS]
-    uint32_t *shade_tiles;      // tiles k_shade resolves from their key page, as x | y << 10 (count in counters[14]) [n_coarse]
-    uint32_t *empty_tiles;      // tiles with empty lists as x | y << 10 [n_coarse]
-    unsigned long long *scan_desc; // k_setup chained-scan descriptors [ceil(n_triangles / 256)]
-    uint2 *clip_queue;          // (triangle, first reserved slot | NO_SLOT) of triangles to clip [n_triangles]
+    uint32_t *t_refs;           // transparent lists: ordered slots 4*ordinal + k, unordered inside a tile's list [refs_cap]
+    uint4 *huge_jobs;           // records covering more than k_front's HUGE_TILES tiles: (bbx, bby, slot | transparent << 31, first pair)
+    uint32_t huge_cap;
+    uint2 *m_refs, *s_refs;     // medium / small references of the whole frame: (record slot, tile x | y << 10 | part bits) [refs_cap each]
+    unsigned long long *key_pages; // page of tile t = TILE_W * TILE_H keys (depth key << 32 | slot) at t * TILE_W * TILE_H, all ones =
+                                   // empty; k_raster fills them with atomicMin, k_tile consumes and resets them
+    uint32_t *counters;         // CNT_* below [N_COUNTERS]
+    uint32_t *tile_order;       // k_tile work items (make_item), bucketed by cost: bucket b's items are tile_order[b * bucket_cap ..
+                                // + counters[CNT_BUCKETS + b]), bucket 0 the heaviest [COST_BUCKETS * bucket_cap]
+    uint32_t bucket_cap;        // tiles + TILE_EXTRA_ITEMS: any one bucket can hold every item
+    uint32_t *empty_tiles;      // tiles with nothing to draw as x | y << 10 [n_coarse]
+    unsigned long long *scan_desc; // P1 chained-scan descriptors [ceil(n_triangles / 256)]
     uint32_t rec_cap, refs_cap;
-    uint32_t *tile_cycles;      // debug: SM cycles spent by each coarse tile's CTA (null = off) [n_coarse]
+    uint32_t *tile_cycles;      // debug: SM cycles spent by each tile's CTA (null = off) [n_coarse]
     uint4 *trace;               // debug: one record per CTA of every frame kernel (device_math.cuh: CtaTrace), null = off
     uint32_t *trace_count;      // records written (may exceed trace_cap: the excess is dropped)
     uint32_t trace_cap, trace_tag; // tag = work set of the frame
 };
+// FrameDev::counters.  Words 0..31 are posted to the canvas' pinned status block by k_tile.
+enum : int {
+    CNT_RECORDS = 0, CNT_REFS_NEEDED = 1, CNT_OVERFLOW = 2, CNT_TICKET = 3, CNT_NONEMPTY = 4, CNT_L_PAIRS = 5, CNT_T_PAIRS = 6,
+    CNT_L_CURSOR = 7, CNT_T_CURSOR = 8, CNT_MEDIUM = 9, CNT_SMALL = 10, CNT_EMPTY = 13, CNT_ITEMS = 15,
+    CNT_HUGE = 30,      // 64-bit (8-byte aligned): huge records queued << 32 | their (record, tile) pairs
+    CNT_PHASE_NS = 16,  // 6 words: global-timer stamps of k_front's phases (block 0), low 32 bits; + 8: durations of the first block's sub-phases
+    CNT_BUCKETS = 32,   // COST_BUCKETS words
+    CNT_ITEM_CURSOR = 96, // k_tile's item cursor, in a 128-byte line of its own
+    CNT_BARRIER = 128,    // k_front's grid barrier, in a line of its own; never reset (FrameUniforms::bar_base)
+    N_COUNTERS = 160, N_STATUS_WORDS = 32
+};
+constexpr int COST_BUCKETS = 34;
 
-enum : uint32_t { OVERFLOW_RECORDS = 1u, OVERFLOW_REFS = 2u };
+enum : uint32_t { OVERFLOW_RECORDS = 1u, OVERFLOW_REFS = 2u, OVERFLOW_STALL = 4u, OVERFLOW_HUGE = 8u }; // STALL: a grid barrier of k_front timed out (never in a cooperative launch)
 
-constexpr int N_FRAME_KERNELS = 10; // k_vertex k_setup k_clip k_bin<count> k_alloc k_bin<fill> k_raster k_clear_empty k_tile k_shade
+constexpr int N_FRAME_KERNELS = 4; // k_sort_transparent k_front k_raster k_tile
 
 } // namespace drawb200

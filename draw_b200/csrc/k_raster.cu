@@ -1,12 +1,11 @@
 // k_raster.cu — rasterises the medium and small triangle references of the whole frame into key pages.
 //
-// The reference loops over every triangle's bbox one after the other (canvas.rs:668-680).  k_tile does
-// the same per screen tile, in shared memory — which makes a tile with hundreds of small triangles (a
-// rib cage, a skull) one long serial job on one SM while most of the GPU has nothing to do.  This kernel
-// takes that part of the work out of the tiles: every (triangle, tile) reference of the medium and small
-// classes is an independent work item, spread evenly over all SMs, and the depth test is a 64-bit
-// atomicMin on the key (order-preserving depth bits << 32 | record slot) of the pixel in the tile's
-// *key page* in global memory (L2-resident: 16 KB per tile with such references).  Slots are
+// The reference loops over every triangle's bbox one after the other (canvas.rs:668-680).  Doing the same per
+// screen tile makes a tile with hundreds of small triangles (a rib cage, a skull) one long serial job on one SM
+// while most of the GPU has nothing to do.  This kernel takes that part of the work out of the tiles: every
+// (triangle, tile) reference of the medium and small classes is an independent work item, spread evenly over
+// all SMs, and the depth test is a 64-bit atomicMin on the key (order-preserving depth bits << 32 | record
+// slot) of the pixel in the tile's *key page* in global memory (L2-resident: 16 KB per tile).  Slots are
 // handed out in draw order, so the minimum key is exactly the fragment the reference's sequential
 // strict-`<` depth test keeps (k_tile.cu, header).  k_tile then starts from the page (its depths
 // also serve the large triangles' early depth reject), adds the large triangles, shades, writes
@@ -15,8 +14,6 @@
 //   medium reference : one warp; lanes test up to 32 of the triangle's 8x4-pixel blocks exactly
 //                      (rect_may_cover), then the warp visits the surviving blocks, one pixel per lane
 //   small reference  : one lane (bbox of at most 8 pixels)
-//
-// Tiles that did not get a page (pool exhausted) keep their references for k_tile's own phases B1 / B2.
 #include "device_math.cuh"
 
 namespace drawb200 {
@@ -45,10 +42,24 @@ __global__ void __launch_bounds__(RASTER_THREADS, RASTER_MIN_CTAS) k_raster(
 #endif
     const FrameUniforms *__restrict__ Up, const FrameDev W) {
     const FrameUniforms &U = *Up; // per-frame uniforms, device-resident (one upload per frame; the launches never change)
-    const CtaTrace trace_(W, 6u);
-    pdl_prologue(U.pdl_early != 0);
-    if (W.counters[2] != 0 || W.page_cap == 0) return; // a buffer overflowed: the host re-renders; or no pages at all
-    const uint32_t n_medium = min(W.counters[9], W.refs_cap), n_small = min(W.counters[10], W.refs_cap);
+    const CtaTrace trace_(W, 2u);
+    if (W.counters[CNT_OVERFLOW] != 0) return; // a buffer overflowed: the host re-renders
+    // Prologue: the (tile, slot) pairs of the large and transparent classes go to their tiles' lists (k_front has
+    // given every tile its offset; k_tile, the next kernel, reads the lists).  Fire-and-forget work spread over the
+    // whole grid, under the latency of the raster work below.
+    {
+        const uint32_t n_l = W.counters[CNT_L_PAIRS], n_t = W.counters[CNT_T_PAIRS];
+        const uint32_t gtid = blockIdx.x * RASTER_THREADS + threadIdx.x, gsize = gridDim.x * RASTER_THREADS;
+        for (uint32_t i = gtid; i < n_l; i += gsize) {
+            const uint2 pr = __ldg(W.l_pairs + i);
+            W.list_refs[W.l_offset[pr.x] + atomicAdd(&W.l_count[pr.x], 1u)] = pr.y;
+        }
+        for (uint32_t i = gtid; i < n_t; i += gsize) {
+            const uint2 pr = __ldg(W.t_pairs + i);
+            W.t_refs[W.t_offset[pr.x] + atomicAdd(&W.t_count[pr.x], 1u)] = pr.y;
+        }
+    }
+    const uint32_t n_medium = min(W.counters[CNT_MEDIUM], W.refs_cap), n_small = min(W.counters[CNT_SMALL], W.refs_cap);
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n_warps = gridDim.x * (RASTER_THREADS / 32), gwarp = blockIdx.x * (RASTER_THREADS / 32) + (threadIdx.x >> 5);
     const float depth_max = U.depth_max;
@@ -57,8 +68,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, RASTER_MIN_CTAS) k_raster(
     auto medium_ref = [&](const uint2 ref) {
         const uint32_t tile_x = ref.y & (MAX_TILES_X - 1), tile_y = (ref.y >> 10) & (MAX_TILES_Y - 1);
         const uint32_t part = (ref.y >> 21) & 3u, parts = ((ref.y >> 23) & 3u) + 1u; // this entry's share of the blocks
-        const uint32_t page = W.tile_page[tile_y * U.tiles_x + tile_x];
-        if (page == NO_PAGE) return; // k_tile rasterises this tile's lists itself
+        const uint32_t page = tile_y * U.tiles_x + tile_x;
         const uint4 *q = reinterpret_cast<const uint4 *>(W.prep + ref.x);
         const uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4), q5 = __ldg(q + 5),
                     q6 = __ldg(q + 6);
@@ -115,7 +125,6 @@ __global__ void __launch_bounds__(RASTER_THREADS, RASTER_MIN_CTAS) k_raster(
             const uint2 ref_next = i_next < n_medium ? __ldg(W.m_refs + i_next) : ref;
             if (i_next < n_medium && lane == 0) {
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(W.prep + ref_next.x));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(W.tile_page + ((ref_next.y >> 10) & (MAX_TILES_Y - 1)) * U.tiles_x + (ref_next.y & (MAX_TILES_X - 1))));
             }
             medium_ref(ref);
             ref = ref_next;
@@ -129,8 +138,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, RASTER_MIN_CTAS) k_raster(
     for (uint32_t i = blockIdx.x * RASTER_THREADS + threadIdx.x; i < n_small; i += n_threads) {
         const uint2 ref = __ldg(W.s_refs + i);
         const uint32_t tile_x = ref.y & (MAX_TILES_X - 1), tile_y = (ref.y >> 10) & (MAX_TILES_Y - 1);
-        const uint32_t page = W.tile_page[tile_y * U.tiles_x + tile_x];
-        if (page == NO_PAGE) continue;
+        const uint32_t page = tile_y * U.tiles_x + tile_x;
         const RasterRec r = load_raster(W.rrec + ref.x); // 48 bytes; the edge set-up is cheaper than reading the PrepRec
         PrepRec p;
         make_prep(r, p);
@@ -159,8 +167,8 @@ __global__ void __launch_bounds__(256) k_fill_u64(unsigned long long *__restrict
 }
 
 thread_local unsigned g_raster_ctas = 148u * 8u; // scene.cpp: DRAW_B200_RASTER_CTAS
-void launch_raster(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream) {
-    launch_pdl(k_raster, g_raster_ctas, RASTER_THREADS, stream, dU, W);
+void launch_raster(const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream) {
+    k_raster<<<g_raster_ctas, RASTER_THREADS, 0, stream>>>(dU, W);
 }
 cudaError_t launch_fill_u64(unsigned long long *dst, size_t n, unsigned long long value, cudaStream_t stream) {
     k_fill_u64<<<148 * 4, 256, 0, stream>>>(dst, n, value);

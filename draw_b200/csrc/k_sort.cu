@@ -29,7 +29,8 @@ struct SortRange {
 
 __device__ __forceinline__ uint32_t painter_key(const SceneDev &S, const v3 cam, uint32_t tri) {
     const uint32_t i0 = S.idx[0][tri], i1 = S.idx[1][tri], i2 = S.idx[2][tri];
-    const v3 a{S.px[i0], S.py[i0], S.pz[i0]}, b{S.px[i1], S.py[i1], S.pz[i1]}, c{S.px[i2], S.py[i2], S.pz[i2]};
+    const float4 pa = __ldg(S.pos4 + i0), pb = __ldg(S.pos4 + i1), pc = __ldg(S.pos4 + i2);
+    const v3 a{pa.x, pa.y, pa.z}, b{pb.x, pb.y, pb.z}, c{pc.x, pc.y, pc.z};
     const v3 center = v_div(v_add(v_add(a, b), c), 3.0f); // scene/mod.rs:1108
     const float d = v_norm(v_sub(center, cam));            // Vec3::dist, linalg.rs:177-180
     const uint32_t bits = __float_as_uint(d);

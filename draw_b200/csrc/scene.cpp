@@ -23,29 +23,23 @@
 #include "host_math.hpp"
 
 namespace drawb200 {
-thread_local int g_pdl_enabled = 1;
-thread_local int g_kernel_priority_set = 0, g_kernel_priority = 0;
-extern thread_local unsigned g_clip_ctas; // k_geometry.cu
-extern thread_local unsigned g_bin_ctas;  // k_binning.cu
+extern thread_local unsigned g_front_ctas;  // k_front.cu
 extern thread_local unsigned g_raster_ctas; // k_raster.cu
-extern thread_local unsigned g_clear_ctas, g_tile_ctas;
-// k_geometry.cu / k_binning.cu / k_tile.cu
-void launch_vertex(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
-void launch_setup(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
-void launch_clip(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
-void launch_bin_count(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream);
-void launch_alloc(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream);
-void launch_bin_fill(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream);
-void launch_raster(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream);
+extern thread_local unsigned g_tile_ctas;   // k_tile.cu
+// k_front.cu / k_raster.cu / k_tile.cu / k_sort.cu
+cudaError_t launch_front(const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
+int front_max_ctas_per_sm();
+uint32_t tile_grid_items(const FrameUniforms &U);
+void launch_raster(const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream);
 cudaError_t launch_fill_u64(unsigned long long *dst, size_t n, unsigned long long value, cudaStream_t stream);
 void launch_tile(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
-void launch_clear_empty(const FrameUniforms &U, const FrameUniforms *dU, const FrameDev &W, cudaStream_t stream);
-void launch_shade(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream);
 void launch_sort_transparent(const FrameUniforms *dU, const SceneDev &S, const void *ranges, uint32_t n_ranges, uint32_t *keys0,
                              uint32_t *keys1, uint32_t *perm0, uint32_t *perm1, uint32_t *scratch, cudaStream_t stream); // k_sort.cu
 cudaError_t launch_clear(uint8_t *color, float *depth, size_t n_pixels, float depth_max, cudaStream_t stream,
                          uint64_t *launches);
 cudaError_t launch_fill_u32(uint32_t *dst, size_t n, uint32_t value, cudaStream_t stream, uint64_t *launches);
+cudaError_t launch_flag_signal(uint32_t *flag, uint32_t value, cudaStream_t stream);                               // k_sync.cu
+cudaError_t launch_flags_wait(const uint32_t *flags, uint32_t n, uint32_t value, uint32_t *error_word, cudaStream_t stream);
 } // namespace drawb200
 
 using namespace drawb200;
@@ -135,7 +129,7 @@ std::set<draw_scene *> g_live_scenes;
 struct GraphKey {
     SceneDev scene;
     FrameDev work;
-    uint32_t n_coarse, n_lists, tiles_x, tile_y_begin, tile_y_end, clear_ctas;
+    uint32_t n_coarse, tiles_x, tile_y_begin, tile_y_end, row_step, row_phase, grids;
 };
 
 struct draw_scene {
@@ -148,7 +142,9 @@ struct draw_scene {
     uint64_t launches = 0;
 
     // device geometry
-    DevBuf<float> d_pos[3], d_nrm[3], d_uv[2];
+    DevBuf<float> d_pos[3];
+    DevBuf<float4> d_pos4, d_nrm4;
+    DevBuf<float2> d_uv2;
     DevBuf<uint32_t> d_idx[9], d_mat, d_tslot;
     DevBuf<MaterialDev> d_materials;
     DevBuf<uint8_t> d_texels;
@@ -162,32 +158,31 @@ struct draw_scene {
     DevBuf<uint4> d_sort_ranges;
     DevBuf<uint32_t> d_sort_keys[2], d_sort_perm[2], d_sort_tmp;
 
-    // Per-frame work buffers, N_WORK_SETS deep, each with its own side stream: the vertex / setup /
-    // binning kernels of the next frames (a chain of six small, latency-bound launches) run on side
-    // streams while k_tile of frame k still runs on its canvas' stream.
+    // Per-frame work buffers, n_sets deep, each with its own stream: a frame runs entirely on its work set's
+    // stream (the canvas' stream only brackets it), so frames that use different sets overlap — the front
+    // kernel of the next frames runs beside k_tile of frame k.
     struct WorkSet {
-        DevBuf<float> vert[9];
-        DevBuf<uint32_t> flags, list_count, list_offset, refs, counters, tile_cycles, tile_cost, tile_order, empty_tiles, shade_tiles;
+        DevBuf<float4> vA, vLH;
+        DevBuf<uint32_t> l_count, t_count, l_offset, t_offset, ms_weight, list_refs, t_refs, counters, tile_cycles,
+            tile_order, empty_tiles;
         DevBuf<unsigned long long> scan_desc;
-        DevBuf<uint2> clip_queue;
         DevBuf<RasterRec> rrec, trrec;
-        DevBuf<PrepRec> prep;
-        DevBuf<uint2> m_refs, s_refs;
-        DevBuf<uint32_t> tile_page;
+        DevBuf<PrepRec> prep, tprep;
+        DevBuf<ShadeRec> srec, tsrec;
+        DevBuf<uint2> l_pairs, t_pairs, m_refs, s_refs;
+        DevBuf<uint4> huge_jobs;
         DevBuf<unsigned long long> key_pages;
         size_t pages_clean = 0; // pages [0, pages_clean) of key_pages.ptr are known to be empty
-        DevBuf<ShadeRec> srec, tsrec;
         FrameDev work{};
-        cudaStream_t stream = nullptr;   // the frame using this set runs here ...
-        cudaStream_t aux_stream = nullptr; // ... and its k_clear_empty here, beside k_bin<fill> / k_raster / k_tile
+        cudaStream_t stream = nullptr;   // the frame using this set runs here
         DevBuf<FrameUniforms> d_uniforms;
         FrameUniforms *h_uniforms = nullptr; // pinned staging of d_uniforms
         cudaGraphExec_t graph_exec = nullptr;
         GraphKey graph_key{};
-        cudaEvent_t alloc_done = nullptr; // side stream: k_alloc has listed the frame's empty tiles and work items
-        cudaEvent_t geo_done = nullptr;  // side stream: binning of the frame using this set has finished
+        uint32_t bar_base = 0;           // value of the set's grid-barrier counter before its next k_front (device_types.h)
+        uint32_t front_grid = 0;         // CTAs of the k_front launch (captured in the graph)
+        cudaEvent_t geo_done = nullptr;  // k_front of the frame using this set has finished (it reads the index streams)
         cudaEvent_t canvas_ready = nullptr; // canvas stream: the canvas of the frame using this set may be written
-        cudaEvent_t clear_done = nullptr; // aux stream: k_clear_empty has finished
         cudaEvent_t frame_done = nullptr; // the whole frame using this set has finished
         bool frame_pending = false;
     };
@@ -201,10 +196,11 @@ struct draw_scene {
     bool debug_trace = false;
     size_t rec_cap = 0, refs_cap = 0;
     bool needs_prepare = true; // the next render sets up every work set (streams, buffers, key pages, frame graph), not only its own
-    // optional per-kernel timing (draw_scene_set_kernel_timing): 0..6 around the six side-stream kernels,
-    // 7 / 8 around k_tile on the canvas stream
+    bool graphs_ok = true; // cleared if the frame cannot be captured as a CUDA graph (direct launches then)
+    // optional per-kernel timing (draw_scene_set_kernel_timing): events before k_sort_transparent, k_front, k_raster,
+    // k_tile and after k_tile
     bool kernel_timing = false;
-    cudaEvent_t kev[N_FRAME_KERNELS + 4] = {};
+    cudaEvent_t kev[N_FRAME_KERNELS + 1] = {};
     bool kev_recorded = false;
 };
 
@@ -225,19 +221,28 @@ struct draw_canvas {
     bool host_mirror = false;   // every render also refreshes the pinned mirror (draw_canvas_enable_host_mirror)
     cudaStream_t own_stream = nullptr, stream = nullptr;
     size_t stripe_y0 = 0, stripe_y1 = 0; // rows; y1 == 0 means whole canvas
-    uint32_t *h_status = nullptr;        // pinned: counters of the last frame
+    uint32_t row_step = 1, row_phase = 0; // tile rows ty % row_step == row_phase only (draw_canvas_set_tile_rows)
+    // Pinned, device-mapped status blocks (N_STATUS_WORDS words each): k_tile posts a frame's counters into the block
+    // the frame was given, so several frames may be enqueued on a canvas before the host looks at any of them.
+    static constexpr int STATUS_SLOTS = 8;
+    uint32_t *h_status = nullptr;
+    int next_status_slot = 0;
+    cudaEvent_t slot_event[STATUS_SLOTS] = {}; // recorded on the canvas' stream behind the frame that posts into the slot
     cudaEvent_t join_event = nullptr;    // draw_canvas_stream_wait
-    bool frame_pending = false;
-    draw_scene *last_scene = nullptr;
-    // what the pending frame was rendered with: an overflowed frame is rendered again from exactly these
-    // inputs, whatever the scene's camera / light and the canvas' offset / stripe have become since
+    // What a frame enqueued on this canvas and not yet looked at by the host was rendered with: an overflowed frame
+    // — and every frame enqueued after it — is rendered again from exactly these inputs, in order, whatever the
+    // scene's camera / light and the canvas' offset / partition have become since.
     struct FrameInputs {
+        draw_scene *scene = nullptr;
+        int status_slot = 0;
         CameraState camera;
         f3 light;
         int off_x = 0, off_y = 0;
         size_t stripe_y0 = 0, stripe_y1 = 0;
+        uint32_t row_step = 1, row_phase = 0;
         float depth_max = 0.0f;
-    } pending_inputs;
+    };
+    std::vector<FrameInputs> pending;
     draw_frame_stats stats{};
     uint64_t launches = 0;
 
@@ -256,25 +261,16 @@ int env_int(const char *name, int fallback) {
 struct Config {
     int graphs = env_int("DRAW_B200_GRAPH", 1);   // replay each frame as a CUDA graph
     int prio = env_int("DRAW_B200_PRIO", 0);      // work-set streams at the highest priority
-    int pdl = env_int("DRAW_B200_PDL", 3);        // programmatic dependent launch: 0 off, 1 early trigger, 2 late, 3 early for a lone frame
     int sets = std::min(std::max(env_int("DRAW_B200_SETS", 8), 1), 8); // frames in flight per scene
-    int pages = std::max(0, env_int("DRAW_B200_PAGES", 16384));        // key pages per work set (0: k_raster off)
-    int clear_ctas = std::max(1, env_int("DRAW_B200_CLEAR_CTAS", 148 * 4));
     int tile_ctas = std::max(1, env_int("DRAW_B200_TILE_CTAS", 148 * 3)); // persistent CTAs of k_tile: three per SM leave room for the other frames' kernels
     int split_min_cost = std::max(1, env_int("DRAW_B200_SPLIT_MIN_COST", TILE_SPLIT_MIN_COST));
     int split_div = std::min(std::max(1, env_int("DRAW_B200_SPLIT_DIV", TILE_SPLIT_DIV)), (int)TILE_EXTRA_ITEMS);
-    int defer_max = std::max(0, env_int("DRAW_B200_DEFER_MAX", 0));  // k_shade takes tiles with fewer large references (0: off)
     int split_max = std::min(std::max(1, env_int("DRAW_B200_SPLIT_MAX", TILE_MAX_SPLIT)), (int)TILE_MAX_SPLIT);
-    int bin_rpw = std::max(0, env_int("DRAW_B200_BIN_RPW", 8));   // k_bin: warp-per-record up to this many records per warp of the grid
-    // grids of the geometry / binning kernels; 0 = by scene size (enqueue_frame): with several frames in flight a
-    // kernel costs the pipeline its CTAs' residency, so small scenes get small grids
-    int clip_ctas = std::max(0, env_int("DRAW_B200_CLIP_CTAS", 0));
-    int bin_ctas = std::max(0, env_int("DRAW_B200_BIN_CTAS", 0));
+    // grids; 0 = by scene size (set_launch_grids): with several frames in flight a kernel costs the pipeline its CTAs' residency
+    int front_cps = std::max(0, env_int("DRAW_B200_FRONT_CPS", 0)); // k_front CTAs per SM
     int raster_ctas = std::max(0, env_int("DRAW_B200_RASTER_CTAS", 0));
-    int cost_shade = std::max(0, env_int("DRAW_B200_COST_SHADE", 0)); // k_alloc: cost of shading a covered tile (0: not counted)
-    int kprio = env_int("DRAW_B200_KPRIO", 0); // 1: geometry / binning / k_raster launches get a higher priority than k_tile and k_clear_empty; 2: the reverse
-    int skip = env_int("DRAW_B200_SKIP", 0); // timing experiments only: bit i set = kernel i of the frame is not launched (frames are then wrong)
-    int clear_in_tile = env_int("DRAW_B200_CLEAR_IN_TILE", 2); // who writes the empty tiles: 0 k_clear_empty on its own stream; k_tile's CTAs 1 before / 2 after each raster item, 3 alternating
+    int rec_cap = std::max(0, env_int("DRAW_B200_REC_CAP", 0));   // initial record / reference capacities (tests force overflows)
+    int refs_cap = std::max(0, env_int("DRAW_B200_REFS_CAP", 0));
 };
 const Config g_cfg;
 
@@ -308,7 +304,9 @@ int pick_device(int *out) {
 int fetch_transparent_order(draw_scene *s);
 int upload_geometry(draw_scene *s) {
     TRY(fetch_transparent_order(s));
-    std::vector<float> pos[3], nrm[3], uv[2];
+    std::vector<float> pos[3];
+    std::vector<float4> pos4, nrm4;
+    std::vector<float2> uv2;
     std::vector<uint32_t> idx[9], mat, tslot;
     std::vector<MaterialDev> materials;
     std::vector<uint8_t> texels;
@@ -320,14 +318,14 @@ int upload_geometry(draw_scene *s) {
 
     for (size_t oi = 0; oi < s->objects.size(); oi++) {
         const HostObject &o = s->objects[oi];
-        const uint32_t vbase = (uint32_t)pos[0].size(), nbase = (uint32_t)nrm[0].size(), tbase = (uint32_t)uv[0].size();
+        const uint32_t vbase = (uint32_t)pos4.size(), nbase = (uint32_t)nrm4.size(), tbase = (uint32_t)uv2.size();
         const uint32_t mbase = (uint32_t)materials.size(), xbase = (uint32_t)texels.size();
-        for (size_t i = 0; i < o.pos.size() / 3; i++)
+        for (size_t i = 0; i < o.pos.size() / 3; i++) {
             for (int c = 0; c < 3; c++) pos[c].push_back(o.pos[3 * i + c]);
-        for (size_t i = 0; i < o.nrm.size() / 3; i++)
-            for (int c = 0; c < 3; c++) nrm[c].push_back(o.nrm[3 * i + c]);
-        for (size_t i = 0; i < o.uv.size() / 3; i++)
-            for (int c = 0; c < 2; c++) uv[c].push_back(o.uv[3 * i + c]);
+            pos4.push_back(make_float4(o.pos[3 * i], o.pos[3 * i + 1], o.pos[3 * i + 2], 0.0f));
+        }
+        for (size_t i = 0; i < o.nrm.size() / 3; i++) nrm4.push_back(make_float4(o.nrm[3 * i], o.nrm[3 * i + 1], o.nrm[3 * i + 2], 0.0f));
+        for (size_t i = 0; i < o.uv.size() / 3; i++) uv2.push_back(make_float2(o.uv[3 * i], o.uv[3 * i + 1]));
         for (MaterialDev m : o.materials) {
             m.ka_off += xbase;
             m.kd_off += xbase;
@@ -353,11 +351,15 @@ int upload_geometry(draw_scene *s) {
             push_mesh(o.transparent[mi], true);
         }
     }
-    if (mat.size() >= (1u << 30)) return fail(DRAW_ERR_INVALID_ARGUMENT, "too many triangles (%zu)", mat.size());
+    if (mat.size() >= (1u << 29)) return fail(DRAW_ERR_INVALID_ARGUMENT, "too many triangles (%zu)", mat.size());
 
-    for (int c = 0; c < 3; c++) TRY(s->d_pos[c].upload(pos[c]));
-    for (int c = 0; c < 3; c++) TRY(s->d_nrm[c].upload(nrm[c]));
-    for (int c = 0; c < 2; c++) TRY(s->d_uv[c].upload(uv[c]));
+    for (int c = 0; c < 3; c++) {
+        while (pos[c].size() % 4) pos[c].push_back(0.0f); // k_front reads the streams four vertices at a time
+        TRY(s->d_pos[c].upload(pos[c]));
+    }
+    TRY(s->d_pos4.upload(pos4));
+    TRY(s->d_nrm4.upload(nrm4));
+    TRY(s->d_uv2.upload(uv2));
     for (int c = 0; c < 9; c++) TRY(s->d_idx[c].upload(idx[c]));
     TRY(s->d_mat.upload(mat));
     TRY(s->d_tslot.upload(tslot));
@@ -367,14 +369,13 @@ int upload_geometry(draw_scene *s) {
 
     SceneDev &d = s->dev;
     d.px = s->d_pos[0].ptr; d.py = s->d_pos[1].ptr; d.pz = s->d_pos[2].ptr;
-    d.nx = s->d_nrm[0].ptr; d.ny = s->d_nrm[1].ptr; d.nz = s->d_nrm[2].ptr;
-    d.tu = s->d_uv[0].ptr; d.tv = s->d_uv[1].ptr;
+    d.pos4 = s->d_pos4.ptr; d.nrm4 = s->d_nrm4.ptr; d.uv2 = s->d_uv2.ptr;
     for (int c = 0; c < 9; c++) d.idx[c] = s->d_idx[c].ptr;
     d.tri_mat = s->d_mat.ptr;
     d.tri_tslot = any_transparent ? s->d_tslot.ptr : nullptr;
     d.materials = s->d_materials.ptr;
     d.texels = s->d_texels.ptr;
-    d.n_vertices = (uint32_t)pos[0].size();
+    d.n_vertices = (uint32_t)pos4.size();
     d.n_triangles = (uint32_t)mat.size();
     d.n_transparent = n_transparent;
     d.n_materials = (uint32_t)materials.size();
@@ -398,66 +399,72 @@ int upload_geometry(draw_scene *s) {
     return DRAW_OK;
 }
 
-int ensure_work_buffers(draw_scene *s, draw_scene::WorkSet &ws, size_t n_lists) {
+int ensure_work_buffers(draw_scene *s, draw_scene::WorkSet &ws, size_t n_tiles) {
     const SceneDev &d = s->dev;
-    for (int i = 0; i < 9; i++) TRY(ws.vert[i].reserve(d.n_vertices));
-    TRY(ws.flags.reserve(d.n_vertices));
-    if (s->rec_cap == 0) s->rec_cap = 2 * (size_t)d.n_triangles + 4096;
-    if (s->refs_cap == 0) s->refs_cap = std::max<size_t>((size_t)1 << 22, 4 * (size_t)d.n_triangles);
+    TRY(ws.vA.reserve(d.n_vertices));
+    TRY(ws.vLH.reserve(2 * (size_t)d.n_vertices));
+    if (s->rec_cap == 0) s->rec_cap = g_cfg.rec_cap ? (size_t)g_cfg.rec_cap : 2 * (size_t)d.n_triangles + 4096;
+    if (s->refs_cap == 0) s->refs_cap = g_cfg.refs_cap ? (size_t)g_cfg.refs_cap : std::max<size_t>((size_t)1 << 22, 4 * (size_t)d.n_triangles);
+    const size_t t_refs_cap = d.n_transparent ? s->refs_cap : 1;
     TRY(ws.rrec.reserve(s->rec_cap));
     TRY(ws.srec.reserve(s->rec_cap));
     TRY(ws.prep.reserve(s->rec_cap));
     TRY(ws.trrec.reserve(4 * (size_t)d.n_transparent));
     TRY(ws.tsrec.reserve(4 * (size_t)d.n_transparent));
-    TRY(ws.list_count.reserve(n_lists));
-    TRY(ws.list_offset.reserve(n_lists + 1));
-    TRY(ws.refs.reserve(s->refs_cap));
+    TRY(ws.tprep.reserve(4 * (size_t)d.n_transparent));
+    TRY(ws.l_count.reserve(n_tiles));
+    TRY(ws.t_count.reserve(n_tiles));
+    TRY(ws.l_offset.reserve(n_tiles));
+    TRY(ws.t_offset.reserve(n_tiles));
+    TRY(ws.ms_weight.reserve(n_tiles));
+    TRY(ws.l_pairs.reserve(s->refs_cap));
+    TRY(ws.list_refs.reserve(s->refs_cap));
+    TRY(ws.t_pairs.reserve(t_refs_cap));
+    TRY(ws.t_refs.reserve(t_refs_cap));
+    const size_t huge_cap = std::min<size_t>(s->rec_cap, (size_t)1 << 20);
+    TRY(ws.huge_jobs.reserve(huge_cap));
     TRY(ws.m_refs.reserve(s->refs_cap));
     TRY(ws.s_refs.reserve(s->refs_cap));
-    TRY(ws.tile_page.reserve(n_lists / LISTS_PER_TILE));
     {
-        // key pages for k_raster: one per tile at most (DRAW_B200_PAGES caps the pool; 0 disables k_raster)
-        const size_t want = std::min<size_t>(n_lists / LISTS_PER_TILE, (size_t)g_cfg.pages);
+        // key pages: one per tile, all empty between frames (k_tile leaves the pages it consumed empty)
         const unsigned long long *before = ws.key_pages.ptr;
-        TRY(ws.key_pages.reserve(want * TILE_W * TILE_H));
+        TRY(ws.key_pages.reserve(n_tiles * TILE_W * TILE_H));
         if (ws.key_pages.ptr != before) ws.pages_clean = 0;
-        if (want > ws.pages_clean) {
+        if (n_tiles > ws.pages_clean) {
             cudaStream_t st = ws.stream ? ws.stream : 0;
-            CU(launch_fill_u64(ws.key_pages.ptr + ws.pages_clean * TILE_W * TILE_H, (want - ws.pages_clean) * TILE_W * TILE_H, KEY_EMPTY, st));
+            CU(launch_fill_u64(ws.key_pages.ptr + ws.pages_clean * TILE_W * TILE_H, (n_tiles - ws.pages_clean) * TILE_W * TILE_H, KEY_EMPTY, st));
             if (!ws.stream) CU(cudaStreamSynchronize(0));
-            ws.pages_clean = want;
+            ws.pages_clean = n_tiles;
         }
-        ws.work.page_cap = (uint32_t)want;
     }
-    TRY(ws.counters.reserve(N_COUNTERS));
-    TRY(ws.tile_cost.reserve(n_lists));
-    TRY(ws.tile_order.reserve(n_lists + TILE_EXTRA_ITEMS));
-    TRY(ws.empty_tiles.reserve(n_lists / LISTS_PER_TILE));
-    TRY(ws.shade_tiles.reserve(n_lists / LISTS_PER_TILE));
-    TRY(ws.scan_desc.reserve((size_t)d.n_triangles / 256 + 2));
-    TRY(ws.clip_queue.reserve(d.n_triangles));
+    if (!ws.counters.ptr) {
+        TRY(ws.counters.reserve(N_COUNTERS));
+        CU(cudaMemset(ws.counters.ptr, 0, N_COUNTERS * sizeof(uint32_t))); // the grid-barrier word starts at bar_base = 0
+        ws.bar_base = 0;
+    }
+    TRY(ws.tile_order.reserve((size_t)COST_BUCKETS * (n_tiles + TILE_EXTRA_ITEMS)));
+    TRY(ws.empty_tiles.reserve(n_tiles));
+    TRY(ws.scan_desc.reserve((size_t)d.n_triangles / 128 + 2)); // one descriptor per 128-triangle block (k_front.cu: FRONT_THREADS)
     FrameDev &w = ws.work;
-    w.v_lx = ws.vert[0].ptr; w.v_ly = ws.vert[1].ptr; w.v_lz = ws.vert[2].ptr;
-    w.v_hx = ws.vert[3].ptr; w.v_hy = ws.vert[4].ptr; w.v_hz = ws.vert[5].ptr;
-    w.v_depth = ws.vert[6].ptr; w.v_sx = ws.vert[7].ptr; w.v_sy = ws.vert[8].ptr;
-    w.v_flags = ws.flags.ptr;
+    w.vA = ws.vA.ptr; w.vLH = ws.vLH.ptr;
     w.rrec = ws.rrec.ptr; w.srec = ws.srec.ptr; w.prep = ws.prep.ptr;
-    w.t_rrec = ws.trrec.ptr; w.t_srec = ws.tsrec.ptr;
-    w.list_count = ws.list_count.ptr; w.list_offset = ws.list_offset.ptr; w.list_refs = ws.refs.ptr;
+    w.t_rrec = ws.trrec.ptr; w.t_srec = ws.tsrec.ptr; w.t_prep = ws.tprep.ptr;
+    w.l_count = ws.l_count.ptr; w.t_count = ws.t_count.ptr; w.l_offset = ws.l_offset.ptr; w.t_offset = ws.t_offset.ptr;
+    w.ms_weight = ws.ms_weight.ptr;
+    w.l_pairs = ws.l_pairs.ptr; w.t_pairs = ws.t_pairs.ptr; w.list_refs = ws.list_refs.ptr; w.t_refs = ws.t_refs.ptr;
     w.m_refs = ws.m_refs.ptr; w.s_refs = ws.s_refs.ptr;
-    w.tile_page = ws.tile_page.ptr; w.key_pages = ws.key_pages.ptr;
+    w.huge_jobs = ws.huge_jobs.ptr; w.huge_cap = (uint32_t)huge_cap;
+    w.key_pages = ws.key_pages.ptr;
     w.counters = ws.counters.ptr;
-    w.tile_cost = ws.tile_cost.ptr;
     w.tile_order = ws.tile_order.ptr;
+    w.bucket_cap = (uint32_t)(n_tiles + TILE_EXTRA_ITEMS);
     w.empty_tiles = ws.empty_tiles.ptr;
-    w.shade_tiles = ws.shade_tiles.ptr;
     w.scan_desc = ws.scan_desc.ptr;
-    w.clip_queue = ws.clip_queue.ptr;
     w.rec_cap = (uint32_t)s->rec_cap;
-    w.refs_cap = (uint32_t)s->refs_cap;
+    w.refs_cap = (uint32_t)std::min(s->refs_cap, t_refs_cap == 1 ? s->refs_cap : t_refs_cap);
     w.tile_cycles = nullptr;
     if (s->debug_tile_cycles) {
-        TRY(ws.tile_cycles.reserve(n_lists));
+        TRY(ws.tile_cycles.reserve(4 * n_tiles));
         w.tile_cycles = ws.tile_cycles.ptr;
     }
     w.trace = nullptr;
@@ -469,10 +476,8 @@ int ensure_work_buffers(draw_scene *s, draw_scene::WorkSet &ws, size_t n_lists) 
         w.trace_count = s->d_trace_count.ptr;
         w.trace_cap = (uint32_t)s->d_trace.cap;
     }
-    if (!ws.alloc_done) CU(cudaEventCreateWithFlags(&ws.alloc_done, cudaEventDisableTiming));
     if (!ws.geo_done) CU(cudaEventCreateWithFlags(&ws.geo_done, cudaEventDisableTiming));
     if (!ws.canvas_ready) CU(cudaEventCreateWithFlags(&ws.canvas_ready, cudaEventDisableTiming));
-    if (!ws.clear_done) CU(cudaEventCreateWithFlags(&ws.clear_done, cudaEventDisableTiming));
     if (!ws.frame_done) CU(cudaEventCreateWithFlags(&ws.frame_done, cudaEventDisableTiming));
     return DRAW_OK;
 }
@@ -506,66 +511,32 @@ int fetch_transparent_order(draw_scene *s) {
     return DRAW_OK;
 }
 
-// The launches of one frame on the work set's streams (directly, or under stream capture).
+// The launches of one frame on the work set's stream (directly, or under stream capture): the uniforms, the
+// painter sort if the scene has transparent meshes, k_front, k_raster, k_tile.
 int launch_frame(draw_scene *s, draw_scene::WorkSet &ws, const FrameUniforms &U, cudaStream_t side, cudaEvent_t *ev,
                  bool capturing) {
     const FrameUniforms *dU = ws.d_uniforms.ptr;
     // ws.canvas_ready is recorded on the canvas' stream outside the graph: an external event of the capture
     const unsigned ext = capturing ? cudaEventWaitExternal : 0u;
     CU(cudaMemcpyAsync(ws.d_uniforms.ptr, ws.h_uniforms, sizeof(FrameUniforms), cudaMemcpyHostToDevice, side));
+    if (ev) cudaEventRecord(ev[0], side);
     // painter sort of the transparent meshes, in place in the shared index streams (enqueue_frame has ordered
-    // this stream after the previous frame's geometry, which reads them)
+    // this stream after the previous frame's k_front, which reads them)
     if (s->dev.n_transparent)
         launch_sort_transparent(dU, s->dev, s->d_sort_ranges.ptr, (uint32_t)s->transparent_ranges.size(), s->d_sort_keys[0].ptr,
                                 s->d_sort_keys[1].ptr, s->d_sort_perm[0].ptr, s->d_sort_perm[1].ptr, s->d_sort_tmp.ptr, side);
-    int prio_least = 0, prio_greatest = 0;
-    if (g_cfg.kprio) cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
-    const int prio_chain = g_cfg.kprio == 1 ? prio_greatest : prio_least, prio_tile = g_cfg.kprio == 1 ? prio_least : prio_greatest;
-    g_kernel_priority_set = g_cfg.kprio != 0;
-    g_kernel_priority = prio_chain;
-    if (ev) cudaEventRecord(ev[0], side);
-    if (!(g_cfg.skip & 1)) launch_vertex(U, dU, s->dev, ws.work, side);
     if (ev) cudaEventRecord(ev[1], side);
-    if (!(g_cfg.skip & 2)) launch_setup(U, dU, s->dev, ws.work, side);
-    if (ev) cudaEventRecord(ev[2], side);
-    if (!(g_cfg.skip & 4)) launch_clip(U, dU, s->dev, ws.work, side);
-    if (ev) cudaEventRecord(ev[3], side);
-    if (!(g_cfg.skip & 8)) launch_bin_count(U, dU, ws.work, side);
-    if (ev) cudaEventRecord(ev[4], side);
-    if (!(g_cfg.skip & 16)) launch_alloc(U, dU, ws.work, side);
-    CU(cudaEventRecord(ws.alloc_done, side));
-    if (ev) cudaEventRecord(ev[5], side);
-    // the empty tiles are cleared as soon as k_alloc has listed them: the stores stream to HBM under the
-    // rest of the chain and under k_tile's dense tiles (disjoint pixels)
-    // (clear-in-tile mode: k_tile's CTAs write them between their raster items and there is no such launch)
-    if (!U.clear_in_tile) {
-        CU(cudaStreamWaitEvent(ws.aux_stream, ws.alloc_done, 0));
-        CU(cudaStreamWaitEvent(ws.aux_stream, ws.canvas_ready, ext));
-        if (ev) cudaEventRecord(ev[N_FRAME_KERNELS - 1], ws.aux_stream);
-        g_kernel_priority = prio_tile;
-        if (!(g_cfg.skip & 128)) launch_clear_empty(U, dU, ws.work, ws.aux_stream);
-        if (ev) cudaEventRecord(ev[N_FRAME_KERNELS], ws.aux_stream);
-        CU(cudaEventRecord(ws.clear_done, ws.aux_stream));
-    } else if (ev) {
-        cudaEventRecord(ev[N_FRAME_KERNELS - 1], side);
-        cudaEventRecord(ev[N_FRAME_KERNELS], side);
-    }
-    g_kernel_priority = prio_chain;
-    if (!(g_cfg.skip & 32)) launch_bin_fill(U, dU, ws.work, side);
-    if (ev) cudaEventRecord(ev[6], side);
-    if (!(g_cfg.skip & 64)) launch_raster(U, dU, ws.work, side);
-    if (ev) cudaEventRecord(ev[7], side);
+    ws.front_grid = g_front_ctas;
+    CU(launch_front(dU, s->dev, ws.work, side));
     // a real event in both paths (an event-record node under capture): the next frame's painter sort waits for it
     CU(cudaEventRecordWithFlags(ws.geo_done, side, capturing ? cudaEventRecordExternal : 0u));
+    if (ev) cudaEventRecord(ev[2], side);
+    launch_raster(dU, ws.work, side);
+    if (ev) cudaEventRecord(ev[3], side);
+    // what the canvas' stream still does with the canvas comes before the kernel that writes it
     CU(cudaStreamWaitEvent(side, ws.canvas_ready, ext));
-    if (ev) cudaEventRecord(ev[N_FRAME_KERNELS + 1], side);
-    g_kernel_priority = prio_tile;
-    if (!(g_cfg.skip & 256)) launch_tile(U, dU, s->dev, ws.work, side);
-    if (ev) cudaEventRecord(ev[N_FRAME_KERNELS + 2], side);
-    if (!(g_cfg.skip & 512)) launch_shade(U, dU, s->dev, ws.work, side);
-    if (ev) cudaEventRecord(ev[N_FRAME_KERNELS + 3], side);
-    g_kernel_priority_set = 0;
-    if (!U.clear_in_tile) CU(cudaStreamWaitEvent(side, ws.clear_done, 0));
+    launch_tile(U, dU, s->dev, ws.work, side);
+    if (ev) cudaEventRecord(ev[4], side);
     return DRAW_OK;
 }
 
@@ -580,13 +551,21 @@ int ensure_host_mirror(draw_canvas *c, size_t bytes) {
     return DRAW_OK;
 }
 
-// Grids of the frame's kernels, by scene size (a kernel costs the pipeline its CTAs' residency).
+// Grids of the frame's kernels, by scene size (a kernel costs the pipeline its CTAs' residency).  k_front: two CTAs of
+// 128 threads per SM for small scenes — they then fit beside three k_tile CTAs of another frame — and as many as fit
+// (eight) for large ones, whose phases need the latency hiding.
 void set_launch_grids(const draw_scene *s) {
+    static const int front_cap = front_max_ctas_per_sm();
+    static const int n_sm = [] {
+        int dev = 0, n = 148;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+        return n;
+    }();
     const bool small_scene = s->dev.n_triangles <= 200000u;
-    g_clip_ctas = g_cfg.clip_ctas ? (unsigned)g_cfg.clip_ctas : (small_scene ? 74u : 296u);
-    g_bin_ctas = g_cfg.bin_ctas ? (unsigned)g_cfg.bin_ctas : (small_scene ? 296u : 592u);
+    const int cps = std::min(front_cap, g_cfg.front_cps ? g_cfg.front_cps : (small_scene ? 2 : 8)); // CTAs of 128 threads
+    g_front_ctas = (unsigned)(n_sm * std::max(1, cps));
     g_raster_ctas = g_cfg.raster_ctas ? (unsigned)g_cfg.raster_ctas : (small_scene ? 592u : 1184u);
-    g_clear_ctas = (unsigned)g_cfg.clear_ctas;
     g_tile_ctas = (unsigned)g_cfg.tile_ctas;
 }
 
@@ -611,24 +590,21 @@ void fill_uniforms(draw_scene *s, const draw_canvas *c, FrameUniforms &U) {
     U.tiles_x = tiles_x;
     U.tiles_y = tiles_y;
     U.n_coarse = tiles_x * tiles_y;
-    U.n_lists = LISTS_PER_TILE * U.n_coarse;
-    U.has_transparent = s->dev.n_transparent != 0;
     U.split_min_cost = (uint32_t)g_cfg.split_min_cost;
     U.split_div = (uint32_t)g_cfg.split_div;
     U.split_max = (uint32_t)g_cfg.split_max;
-    U.defer_max = (uint32_t)g_cfg.defer_max;
-    U.clear_in_tile = (uint32_t)g_cfg.clear_in_tile;
-    U.bin_records_per_warp = (uint32_t)g_cfg.bin_rpw;
-    U.cost_shade = (uint32_t)g_cfg.cost_shade;
     const size_t y0 = c->stripe_y1 ? c->stripe_y0 : 0, y1 = c->stripe_y1 ? c->stripe_y1 : c->height;
     U.tile_y_begin = (uint32_t)(y0 / TILE_H);
     U.tile_y_end = (uint32_t)((y1 + TILE_H - 1) / TILE_H);
-    U.status_host = c->h_status; // pinned, mapped: the pointer is valid on the device (unified addressing)
+    U.row_step = c->row_step ? c->row_step : 1u;
+    U.row_phase = c->row_phase % U.row_step;
+    U.bar_base = 0; // set per work set by enqueue_frame
+    U.status_host = c->h_status + (size_t)c->next_status_slot * N_STATUS_WORDS; // pinned, mapped: valid on the device (unified addressing)
     U.color = c->color();
     U.depth = c->depth();
 }
 
-// Makes one work set ready for frames of this scene / canvas geometry: its streams and pinned uniforms, its
+// Makes one work set ready for frames of this scene / canvas geometry: its stream and pinned uniforms, its
 // buffers (key pages filled), and — unless a measurement or debug tap needs the direct path — the frame's
 // launches captured once as a CUDA graph (they do not change from frame to frame: the uniforms are read
 // from device memory).
@@ -637,37 +613,37 @@ int ensure_set_ready(draw_scene *s, draw_scene::WorkSet &ws, const FrameUniforms
         int prio_low = 0, prio_high = 0;
         CU(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
         CU(cudaStreamCreateWithPriority(&ws.stream, cudaStreamNonBlocking, g_cfg.prio ? prio_high : prio_low));
-        CU(cudaStreamCreateWithFlags(&ws.aux_stream, cudaStreamNonBlocking));
         CU(cudaMallocHost(&ws.h_uniforms, sizeof(FrameUniforms)));
         TRY(ws.d_uniforms.reserve(1));
     }
-    TRY(ensure_work_buffers(s, ws, U.n_lists));
-    if (!want_graph) return DRAW_OK;
+    TRY(ensure_work_buffers(s, ws, U.n_coarse));
+    if (!want_graph || !s->graphs_ok) return DRAW_OK;
     GraphKey key{};
     key.scene = s->dev;
     key.work = ws.work;
-    key.n_coarse = U.n_coarse; key.n_lists = U.n_lists; key.tiles_x = U.tiles_x;
-    key.tile_y_begin = U.tile_y_begin; key.tile_y_end = U.tile_y_end;
-    key.clear_ctas = g_clear_ctas + 65536u * g_tile_ctas + 7u * g_clip_ctas + 1000003u * g_bin_ctas + 15485863u * g_raster_ctas;
+    key.n_coarse = U.n_coarse; key.tiles_x = U.tiles_x;
+    key.tile_y_begin = U.tile_y_begin; key.tile_y_end = U.tile_y_end; key.row_step = U.row_step; key.row_phase = U.row_phase;
+    key.grids = g_front_ctas + 4099u * g_tile_ctas + 1000003u * g_raster_ctas;
     if (ws.graph_exec && std::memcmp(&key, &ws.graph_key, sizeof key) == 0) return DRAW_OK;
     if (ws.graph_exec) CU(cudaGraphExecDestroy(ws.graph_exec));
     ws.graph_exec = nullptr;
-    const int pdl_saved = g_pdl_enabled;
-    g_pdl_enabled = 0; // plain kernel nodes: the graph already removes the launch gaps
     CU(cudaStreamBeginCapture(ws.stream, cudaStreamCaptureModeThreadLocal));
     const int rc = launch_frame(s, ws, U, ws.stream, nullptr, true);
     cudaGraph_t graph = nullptr;
-    const cudaError_t e = cudaStreamEndCapture(ws.stream, &graph);
-    g_pdl_enabled = pdl_saved;
-    if (rc != DRAW_OK) {
-        if (graph) cudaGraphDestroy(graph);
-        return rc;
+    cudaError_t e = cudaStreamEndCapture(ws.stream, &graph);
+    if (rc == DRAW_OK && e == cudaSuccess) {
+        e = cudaGraphInstantiate(&ws.graph_exec, graph, 0);
+        if (e == cudaSuccess) e = cudaGraphUpload(ws.graph_exec, ws.stream); // the first replay does not pay the upload
     }
-    CU(e);
-    const cudaError_t ei = cudaGraphInstantiate(&ws.graph_exec, graph, 0);
-    cudaGraphDestroy(graph);
-    CU(ei);
-    CU(cudaGraphUpload(ws.graph_exec, ws.stream)); // the first replay does not pay the upload
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != DRAW_OK || e != cudaSuccess) {
+        // e.g. a driver that cannot capture a cooperative launch: frames are launched directly from now on
+        cudaGetLastError();
+        if (ws.graph_exec) cudaGraphExecDestroy(ws.graph_exec);
+        ws.graph_exec = nullptr;
+        s->graphs_ok = false;
+        return DRAW_OK;
+    }
     ws.graph_key = key;
     return DRAW_OK;
 }
@@ -685,73 +661,72 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     s->next_set = (s->next_set + 1) % s->n_sets;
 
     set_launch_grids(s);
-    // A frame's launches are replayed as a CUDA graph: one launch call instead of nine kernels, six events and
-    // a copy.  Measurement taps and the debug taps use the direct path.
+    // A frame's launches are replayed as a CUDA graph: one launch call instead of a copy, three or four kernels and
+    // two events.  Measurement taps and the debug taps use the direct path.
     const bool timing = s->kernel_timing;
-    const bool use_graph = g_cfg.graphs && !timing && !s->debug_tile_cycles;
+    const bool want_graph = g_cfg.graphs && !timing && !s->debug_tile_cycles;
     if (s->needs_prepare) {
-        // First frame of this scene (or of its new geometry / capacities): every work set is set up now — streams,
+        // First frame of this scene (or of its new geometry / capacities): every work set is set up now — stream,
         // ~30 buffers, the fill of its key pages, graph capture and instantiation — so that no later frame pays a
         // few milliseconds of set-up in the middle of a steady stream of frames (draw_scene_prepare does the same).
         for (int i = 0; i < s->n_sets; i++) {
             if (s->sets[i].frame_pending) CU(cudaEventSynchronize(s->sets[i].frame_done));
-            TRY(ensure_set_ready(s, s->sets[i], U, use_graph));
+            TRY(ensure_set_ready(s, s->sets[i], U, want_graph));
         }
         s->needs_prepare = false;
     }
     if (ws.frame_pending) CU(cudaEventSynchronize(ws.frame_done)); // the pinned uniforms of the set are about to be rewritten
-    TRY(ensure_set_ready(s, ws, U, use_graph));
-
-    // early trigger only for a lone frame: with other frames in flight the idle dependents would hold SM slots
-    bool others_in_flight = false;
-    for (int i = 0; i < s->n_sets; i++)
-        if (&s->sets[i] != &ws && s->sets[i].frame_pending && cudaEventQuery(s->sets[i].frame_done) == cudaErrorNotReady) others_in_flight = true;
-    cudaGetLastError(); // cudaErrorNotReady is not sticky, but keep the error state clean
-    const int pdl_mode = g_cfg.pdl; // 0 off, 1 always early, 2 never early, 3 early for a lone frame
-    g_pdl_enabled = pdl_mode != 0;
-    U.pdl_early = pdl_mode == 1 || (pdl_mode == 3 && !others_in_flight);
+    TRY(ensure_set_ready(s, ws, U, want_graph));
+    const bool use_graph = want_graph && s->graphs_ok && ws.graph_exec;
 
     // ---- enqueue ----------------------------------------------------------------------------------
-    // Everything of the frame runs on the work set's own streams: the geometry chain and k_tile on
-    // ws.stream, k_clear_empty beside them on ws.aux_stream (forked after k_alloc, joined after k_tile).
-    // The canvas' stream only brackets the frame: the set's stream first waits for whatever the canvas
-    // stream still does with the canvas, and the canvas stream then waits for the frame.  Frames that
-    // use different work sets are therefore independent and overlap; a set's next frame follows its
-    // previous one in stream order.
+    // Everything of the frame runs on the work set's own stream.  The canvas' stream only brackets the frame:
+    // k_tile first waits for whatever the canvas stream still does with the canvas, and the canvas stream then
+    // waits for the frame.  Frames that use different work sets are therefore independent and overlap; a set's
+    // next frame follows its previous one in stream order.
     cudaStream_t side = ws.stream, st = c->stream;
+    U.bar_base = ws.bar_base;
     *ws.h_uniforms = U;
-    // what the canvas stream still does with the canvas comes before the two kernels that write it
-    // (k_clear_empty, k_tile wait for this event; the geometry chain does not touch the canvas and does not wait)
+    // (k_tile waits for this event; k_front and k_raster do not touch the canvas and do not wait)
     CU(cudaEventRecord(ws.canvas_ready, st));
     if (s->dev.n_transparent) {
-        // the painter sort rewrites the shared index streams: order it after the previous frame's geometry
+        // the painter sort rewrites the shared index streams: order it after the previous frame's k_front
         // (geo_done is a real event in both paths: launch_frame records it with cudaEventRecordExternal under capture)
         if (&prev_ws != &ws && prev_ws.frame_pending) CU(cudaStreamWaitEvent(side, prev_ws.geo_done, 0));
     }
-    if (ws.work.tile_cycles) CU(cudaMemsetAsync(ws.work.tile_cycles, 0, U.n_lists * sizeof(uint32_t), side)); // debug taps are atomicMax'd
+    if (ws.work.tile_cycles) CU(cudaMemsetAsync(ws.work.tile_cycles, 0, 4 * (size_t)U.n_coarse * sizeof(uint32_t), side)); // debug taps are atomicMax'd
 
     cudaEvent_t *ev = nullptr;
     if (timing) {
-        for (int i = 0; i < N_FRAME_KERNELS + 4; i++)
+        for (int i = 0; i < N_FRAME_KERNELS + 1; i++)
             if (!s->kev[i]) CU(cudaEventCreate(&s->kev[i]));
         ev = s->kev;
         s->kev_recorded = true;
     }
     if (use_graph) CU(cudaGraphLaunch(ws.graph_exec, side));
     else TRY(launch_frame(s, ws, U, side, ev, false));
+    ws.bar_base += 3u * ws.front_grid; // k_front's three grid barriers (k_front.cu; the third is only waited at if the frame has huge records)
     CU(cudaEventRecord(ws.frame_done, side));
     ws.frame_pending = true;
     CU(cudaStreamWaitEvent(st, ws.frame_done, 0));
-    s->launches += 5 + (s->dev.n_triangles ? 2 : 0) + (s->dev.n_transparent ? 1 : 0) + (U.tile_y_end > U.tile_y_begin ? (U.defer_max ? 3 : 2) - (U.clear_in_tile ? 1 : 0) : 0);
+    s->launches += 2 + (s->dev.n_transparent ? 1 : 0) + (tile_grid_items(U) ? 1 : 0);
     CU(cudaGetLastError());
-    c->frame_pending = true;
     c->host_dirty = true;
-    c->last_scene = s;
-    c->pending_inputs.camera = s->camera;
-    c->pending_inputs.light = s->light;
-    c->pending_inputs.off_x = c->off_x; c->pending_inputs.off_y = c->off_y;
-    c->pending_inputs.stripe_y0 = c->stripe_y0; c->pending_inputs.stripe_y1 = c->stripe_y1;
-    c->pending_inputs.depth_max = c->depth_max;
+    {
+        draw_canvas::FrameInputs in;
+        in.scene = s;
+        in.status_slot = c->next_status_slot;
+        in.camera = s->camera;
+        in.light = s->light;
+        in.off_x = c->off_x; in.off_y = c->off_y;
+        in.stripe_y0 = c->stripe_y0; in.stripe_y1 = c->stripe_y1;
+        in.row_step = c->row_step; in.row_phase = c->row_phase;
+        in.depth_max = c->depth_max;
+        if (!c->slot_event[in.status_slot]) CU(cudaEventCreateWithFlags(&c->slot_event[in.status_slot], cudaEventDisableTiming));
+        CU(cudaEventRecord(c->slot_event[in.status_slot], st));
+        c->pending.push_back(in);
+        c->next_status_slot = (c->next_status_slot + 1) % draw_canvas::STATUS_SLOTS;
+    }
     if (c->host_mirror && !c->ext_color) {
         // the frame follows its render to the host without waiting for the host to ask (map_host then only waits)
         const size_t bytes = c->width * c->height * 4;
@@ -762,58 +737,90 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     return DRAW_OK;
 }
 
-// Waits for the canvas' stream; if the last frame overflowed a work buffer, grows it and
-// renders the frame again (so what the host reads is always a complete frame).
+// Statistics of a completed frame, from the status block k_tile posted them to.
+void record_stats(draw_canvas *c, const draw_canvas::FrameInputs &frame) {
+    const uint32_t *st = c->h_status + (size_t)frame.status_slot * N_STATUS_WORDS;
+    c->stats.setup_records = st[CNT_RECORDS];
+    c->stats.large_refs = st[CNT_L_PAIRS];
+    c->stats.medium_refs = st[CNT_MEDIUM];
+    c->stats.small_refs = st[CNT_SMALL];
+    c->stats.transparent_refs = st[CNT_T_PAIRS];
+    c->stats.tile_refs = c->stats.large_refs + c->stats.medium_refs + c->stats.small_refs + c->stats.transparent_refs;
+    c->stats.empty_tiles = st[CNT_EMPTY];
+    c->stats.work_items = st[CNT_ITEMS];
+    for (int i = 0; i < 5; i++) c->stats.front_phase_ns[i] = st[CNT_PHASE_NS + i + 1] - st[CNT_PHASE_NS + i];
+    c->stats.front_phase_ns[5] = st[CNT_PHASE_NS + 6] - st[CNT_PHASE_NS + 2];                              // triangle phase, slowest CTA
+    c->stats.front_phase_ns[6] = st[CNT_PHASE_NS + 7] ? st[CNT_PHASE_NS + 7] - st[CNT_PHASE_NS + 6] : 0u; // huge-record phase (after the barrier)
+    for (int i = 0; i < 5; i++) c->stats.front_block_ns[i] = st[CNT_PHASE_NS + 8 + i];
+    bool alive;
+    {
+        std::lock_guard<std::mutex> lk(g_registry_mutex);
+        alive = g_live_scenes.count(frame.scene) != 0;
+    }
+    if (alive) c->stats.input_triangles = frame.scene->dev.n_triangles;
+}
+
+// Waits for the canvas' stream and settles the frames enqueued on it since the last call: statistics of the last
+// one; if any of them overflowed a work buffer, the buffers are grown and that frame and every later one are
+// rendered again, in order, each from the inputs it was enqueued with (so what the host reads is always complete).
 int finish_frame(draw_canvas *c) {
     TRY(ensure_device(c->device));
     CU(cudaStreamSynchronize(c->stream));
-    int guard = 0;
-    while (c->frame_pending) {
-        c->frame_pending = false;
-        draw_scene *s = c->last_scene;
-        bool alive;
-        {
-            std::lock_guard<std::mutex> lk(g_registry_mutex);
-            alive = g_live_scenes.count(s) != 0;
+    for (int guard = 0; !c->pending.empty(); guard++) {
+        const std::vector<draw_canvas::FrameInputs> frames = c->pending;
+        c->pending.clear();
+        size_t first_bad = frames.size();
+        uint32_t overflow = 0, n_rec = 0, n_refs = 0;
+        for (size_t i = 0; i < frames.size(); i++) {
+            const uint32_t *st = c->h_status + (size_t)frames[i].status_slot * N_STATUS_WORDS;
+            if (st[CNT_OVERFLOW] && first_bad == frames.size()) first_bad = i;
+            if (i >= first_bad) {
+                overflow |= st[CNT_OVERFLOW];
+                n_rec = std::max(n_rec, st[CNT_RECORDS]);
+                n_refs = std::max(n_refs, st[CNT_REFS_NEEDED]);
+            }
         }
-        const uint32_t n_rec = c->h_status[0], n_refs = c->h_status[1], overflow = c->h_status[2];
-        c->stats.setup_records = n_rec;
-        c->stats.tile_refs = n_refs;
-        c->stats.empty_tiles = c->h_status[13];
-        c->stats.key_pages = c->h_status[11];
-        c->stats.clear_in_tile = (uint32_t)g_cfg.clear_in_tile;
-        if (alive) {
-            c->stats.input_triangles = s->dev.n_triangles;
-            c->stats.transparent_slots = s->dev.n_transparent * 4;
-        }
-        if (!overflow) break;
-        c->stats.overflow = overflow;
-        if (!alive) return fail(DRAW_ERR_INTERNAL, "frame overflowed a work buffer and its scene is gone");
-        if (++guard > 4) return fail(DRAW_ERR_INTERNAL, "work buffers keep overflowing");
-        if (overflow & OVERFLOW_RECORDS)
-            s->rec_cap = std::max<size_t>((size_t)n_rec + n_rec / 4 + 1024, 4 * (size_t)s->dev.n_triangles + 1024);
-        if (overflow & OVERFLOW_REFS) s->refs_cap = (size_t)n_refs + n_refs / 4 + 4096;
-        else if (overflow & OVERFLOW_RECORDS) s->refs_cap = std::max(s->refs_cap, 4 * s->rec_cap);
+        record_stats(c, frames.back());
+        if (first_bad == frames.size()) break;
+        c->stats.overflow |= overflow;
+        if (overflow & OVERFLOW_STALL) return fail(DRAW_ERR_INTERNAL, "a grid barrier of k_front timed out (the launch was not co-resident)");
+        if (overflow & OVERFLOW_HUGE) return fail(DRAW_ERR_INTERNAL, "more than 2^20 records each cover hundreds of tiles");
+        if (guard >= 4) return fail(DRAW_ERR_INTERNAL, "work buffers keep overflowing");
         CU(cudaDeviceSynchronize()); // the work sets are about to be reallocated
-        s->needs_prepare = true;
-        // Render the frame again from the inputs it was rendered with (the scene's camera / light and the
-        // canvas' offset / stripe may have moved on since), then put the current state back.
-        const draw_canvas::FrameInputs in = c->pending_inputs;
-        const CameraState cam_now = s->camera;
-        const f3 light_now = s->light;
-        const int off_x_now = c->off_x, off_y_now = c->off_y;
-        const size_t sy0_now = c->stripe_y0, sy1_now = c->stripe_y1;
-        const float dmax_now = c->depth_max;
-        s->camera = in.camera; s->light = in.light;
-        c->off_x = in.off_x; c->off_y = in.off_y;
-        c->stripe_y0 = in.stripe_y0; c->stripe_y1 = in.stripe_y1;
-        c->depth_max = in.depth_max;
-        const int rc = enqueue_frame(s, c);
-        s->camera = cam_now; s->light = light_now;
-        c->off_x = off_x_now; c->off_y = off_y_now;
-        c->stripe_y0 = sy0_now; c->stripe_y1 = sy1_now;
-        c->depth_max = dmax_now;
-        TRY(rc);
+        for (size_t i = first_bad; i < frames.size(); i++) {
+            const draw_canvas::FrameInputs &in = frames[i];
+            draw_scene *fs = in.scene;
+            {
+                std::lock_guard<std::mutex> lk(g_registry_mutex);
+                if (!g_live_scenes.count(fs)) return fail(DRAW_ERR_INTERNAL, "frame overflowed a work buffer and its scene is gone");
+            }
+            if (i == first_bad || fs != frames[i - 1].scene) {
+                if (overflow & OVERFLOW_RECORDS)
+                    fs->rec_cap = std::max(fs->rec_cap, std::max<size_t>((size_t)n_rec + n_rec / 4 + 1024, 4 * (size_t)fs->dev.n_triangles + 1024));
+                if (overflow & OVERFLOW_REFS) fs->refs_cap = std::max(fs->refs_cap, (size_t)n_refs + n_refs / 4 + 4096);
+                else if (overflow & OVERFLOW_RECORDS) fs->refs_cap = std::max(fs->refs_cap, 4 * fs->rec_cap);
+                fs->needs_prepare = true;
+            }
+            // render the frame again from the inputs it was rendered with, then put the current state back
+            const CameraState cam_now = fs->camera;
+            const f3 light_now = fs->light;
+            const int off_x_now = c->off_x, off_y_now = c->off_y;
+            const size_t sy0_now = c->stripe_y0, sy1_now = c->stripe_y1;
+            const uint32_t rstep_now = c->row_step, rphase_now = c->row_phase;
+            const float dmax_now = c->depth_max;
+            fs->camera = in.camera; fs->light = in.light;
+            c->off_x = in.off_x; c->off_y = in.off_y;
+            c->stripe_y0 = in.stripe_y0; c->stripe_y1 = in.stripe_y1;
+            c->row_step = in.row_step; c->row_phase = in.row_phase;
+            c->depth_max = in.depth_max;
+            const int rc = enqueue_frame(fs, c);
+            fs->camera = cam_now; fs->light = light_now;
+            c->off_x = off_x_now; c->off_y = off_y_now;
+            c->stripe_y0 = sy0_now; c->stripe_y1 = sy1_now;
+            c->row_step = rstep_now; c->row_phase = rphase_now;
+            c->depth_max = dmax_now;
+            TRY(rc);
+        }
         CU(cudaStreamSynchronize(c->stream));
     }
     return DRAW_OK;
@@ -901,19 +908,14 @@ void draw_scene_destroy(draw_scene *scene) {
     if (cudaGetDevice(&cur) == cudaSuccess) {
         if (cur != scene->device) cudaSetDevice(scene->device);
         cudaDeviceSynchronize();
-        for (draw_scene::WorkSet &ws : scene->sets) {
-            if (ws.alloc_done) cudaEventDestroy(ws.alloc_done);
-            if (ws.geo_done) cudaEventDestroy(ws.geo_done);
-        }
-        for (int i = 0; i < N_FRAME_KERNELS + 4; i++)
+        for (int i = 0; i < N_FRAME_KERNELS + 1; i++)
             if (scene->kev[i]) cudaEventDestroy(scene->kev[i]);
         for (draw_scene::WorkSet &ws : scene->sets) {
             if (ws.graph_exec) cudaGraphExecDestroy(ws.graph_exec);
             if (ws.stream) cudaStreamDestroy(ws.stream);
-            if (ws.aux_stream) cudaStreamDestroy(ws.aux_stream);
             if (ws.h_uniforms) cudaFreeHost(ws.h_uniforms);
+            if (ws.geo_done) cudaEventDestroy(ws.geo_done);
             if (ws.canvas_ready) cudaEventDestroy(ws.canvas_ready);
-            if (ws.clear_done) cudaEventDestroy(ws.clear_done);
             if (ws.frame_done) cudaEventDestroy(ws.frame_done);
         }
     }
@@ -1063,12 +1065,26 @@ int draw_scene_render(draw_scene *scene, draw_canvas *canvas) {
         return fail(DRAW_ERR_INVALID_ARGUMENT, "scene (device %d) and canvas (device %d) live on different devices",
                     scene->device, canvas->device);
     if (!canvas->has_depth) return fail(DRAW_ERR_INVALID_ARGUMENT, "Depth not initialized"); // canvas.rs:914
-    if (canvas->frame_pending) {
-        // settle the previous frame's status first (grows buffers if it overflowed)
+    if (!canvas->pending.empty()) {
+        // Settle the earlier frames of this canvas that have completed (no wait): a frame that overflowed a work buffer
+        // is re-rendered, with everything enqueued after it, before the new frame goes in.  A canvas has STATUS_SLOTS
+        // status blocks: with that many frames in flight on it, the oldest is waited for.
         TRY(ensure_device(canvas->device));
-        if (cudaStreamQuery(canvas->stream) == cudaSuccess) TRY(finish_frame(canvas));
+        while (!canvas->pending.empty()) {
+            const draw_canvas::FrameInputs &front = canvas->pending.front();
+            if ((int)canvas->pending.size() >= draw_canvas::STATUS_SLOTS - 1) CU(cudaEventSynchronize(canvas->slot_event[front.status_slot]));
+            else if (cudaEventQuery(canvas->slot_event[front.status_slot]) != cudaSuccess) break;
+            if (canvas->h_status[(size_t)front.status_slot * N_STATUS_WORDS + CNT_OVERFLOW]) {
+                TRY(finish_frame(canvas));
+                break;
+            }
+            record_stats(canvas, front);
+            canvas->pending.erase(canvas->pending.begin());
+        }
+        cudaGetLastError(); // cudaErrorNotReady is not sticky, but keep the error state clean
+    } else {
+        canvas->stats.overflow = 0; // of the frames enqueued from here on
     }
-    canvas->stats.overflow = 0;
     return enqueue_frame(scene, canvas);
     GUARD_END
 }
@@ -1086,10 +1102,10 @@ int draw_scene_prepare(draw_scene *scene, draw_canvas *canvas) {
     if (U.tiles_x >= MAX_TILES_X || U.tiles_y >= MAX_TILES_Y)
         return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas %zux%zu is too large for the tile work list", canvas->width, canvas->height);
     set_launch_grids(scene);
-    const bool use_graph = g_cfg.graphs && !scene->kernel_timing && !scene->debug_tile_cycles;
+    const bool want_graph = g_cfg.graphs && !scene->kernel_timing && !scene->debug_tile_cycles;
     for (int i = 0; i < scene->n_sets; i++) {
         if (scene->sets[i].frame_pending) CU(cudaEventSynchronize(scene->sets[i].frame_done));
-        TRY(ensure_set_ready(scene, scene->sets[i], U, use_graph));
+        TRY(ensure_set_ready(scene, scene->sets[i], U, want_graph));
     }
     scene->needs_prepare = false;
     CU(cudaDeviceSynchronize()); // key pages are filled, graphs uploaded: the next render only enqueues
@@ -1114,11 +1130,17 @@ int draw_scene_read_vertex_visual(draw_scene *scene, draw_canvas *canvas, size_t
     if (!scene || !canvas || !out) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
     TRY(finish_frame(canvas));
     if (first + count > scene->dev.n_vertices) return fail(DRAW_ERR_INVALID_ARGUMENT, "vertex range out of bounds");
-    std::vector<float> tmp(count);
-    const int order[7] = {0, 1, 2, 3, 4, 5, 6}; // light xyz, halfway xyz, depth
-    for (int k = 0; k < 7; k++) {
-        CU(cudaMemcpy(tmp.data(), scene->sets[scene->last_set].vert[order[k]].ptr + first, count * sizeof(float), cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < count; i++) out[7 * i + k] = tmp[i];
+    const draw_scene::WorkSet &ws = scene->sets[scene->last_set];
+    std::vector<float4> a(count), lh(2 * count);
+    if (count) {
+        CU(cudaMemcpy(a.data(), ws.vA.ptr + first, count * sizeof(float4), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(lh.data(), ws.vLH.ptr + 2 * first, 2 * count * sizeof(float4), cudaMemcpyDeviceToHost));
+    }
+    for (size_t i = 0; i < count; i++) {
+        float *o = out + 7 * i;
+        o[0] = lh[2 * i].x; o[1] = lh[2 * i].y; o[2] = lh[2 * i].z;         // light
+        o[3] = lh[2 * i].w; o[4] = lh[2 * i + 1].x; o[5] = lh[2 * i + 1].y; // halfway
+        o[6] = a[i].z;                                                       // depth
     }
     return DRAW_OK;
     GUARD_END
@@ -1151,15 +1173,12 @@ int draw_scene_set_kernel_timing(draw_scene *scene, int enabled) {
     return DRAW_OK;
 }
 
-int draw_scene_last_kernel_times(draw_scene *scene, draw_canvas *canvas, float ms[10]) {
+int draw_scene_last_kernel_times(draw_scene *scene, draw_canvas *canvas, float ms[4]) {
     GUARD_BEGIN
     if (!scene || !canvas || !ms) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!scene->kev_recorded) return fail(DRAW_ERR_INVALID_ARGUMENT, "kernel timing was not enabled for the last frame");
     TRY(finish_frame(canvas));
-    for (int i = 0; i < 7; i++) CU(cudaEventElapsedTime(&ms[i], scene->kev[i], scene->kev[i + 1])); // k_vertex .. k_raster
-    CU(cudaEventElapsedTime(&ms[7], scene->kev[N_FRAME_KERNELS - 1], scene->kev[N_FRAME_KERNELS]));     // k_clear_empty (aux stream)
-    CU(cudaEventElapsedTime(&ms[8], scene->kev[N_FRAME_KERNELS + 1], scene->kev[N_FRAME_KERNELS + 2])); // k_tile
-    CU(cudaEventElapsedTime(&ms[9], scene->kev[N_FRAME_KERNELS + 2], scene->kev[N_FRAME_KERNELS + 3])); // k_shade
+    for (int i = 0; i < N_FRAME_KERNELS; i++) CU(cudaEventElapsedTime(&ms[i], scene->kev[i], scene->kev[i + 1])); // k_sort_transparent k_front k_raster k_tile
     return DRAW_OK;
     GUARD_END
 }
@@ -1173,7 +1192,7 @@ int draw_scene_debug_tile_cycles(draw_scene *scene, draw_canvas *canvas, int ena
     TRY(finish_frame(canvas));
     DevBuf<uint32_t> &cyc = scene->sets[scene->last_set].tile_cycles;
     if (!cyc.ptr || n > cyc.cap) return fail(DRAW_ERR_INVALID_ARGUMENT, "no tile cycles recorded");
-    // layout: [tile] whole CTA, [n_tiles + tile] end of phase A, [2 n_tiles + tile] end of phase B
+    // layout: [tile] whole item, [n_tiles + tile] end of phase A, [2 n_tiles + tile] end of phase C, [3 n_tiles + tile] end of phase D
     CU(cudaMemcpy(out, cyc.ptr, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return DRAW_OK;
     GUARD_END
@@ -1209,11 +1228,14 @@ int draw_scene_debug_list_counts(draw_scene *scene, draw_canvas *canvas, uint32_
     if (!scene || !canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
     TRY(finish_frame(canvas));
     const size_t tiles_x = (canvas->width + TILE_W - 1) / TILE_W, tiles_y = (canvas->height + TILE_H - 1) / TILE_H;
-    const size_t coarse = tiles_x * tiles_y, lists = coarse * LISTS_PER_TILE;
+    const size_t coarse = tiles_x * tiles_y;
     if (n_coarse) *n_coarse = coarse;
     if (!out) return DRAW_OK;
-    if (n != lists) return fail(DRAW_ERR_INVALID_ARGUMENT, "n must be %zu", lists);
-    CU(cudaMemcpy(out, scene->sets[scene->last_set].list_count.ptr, lists * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (n != 3 * coarse) return fail(DRAW_ERR_INVALID_ARGUMENT, "n must be %zu", 3 * coarse);
+    const draw_scene::WorkSet &ws = scene->sets[scene->last_set];
+    CU(cudaMemcpy(out, ws.l_count.ptr, coarse * sizeof(uint32_t), cudaMemcpyDeviceToHost));              // large references
+    CU(cudaMemcpy(out + coarse, ws.ms_weight.ptr, coarse * sizeof(uint32_t), cudaMemcpyDeviceToHost));   // medium / small weight
+    CU(cudaMemcpy(out + 2 * coarse, ws.t_count.ptr, coarse * sizeof(uint32_t), cudaMemcpyDeviceToHost)); // transparent references
     return DRAW_OK;
     GUARD_END
 }
@@ -1239,9 +1261,9 @@ int draw_canvas_create(size_t width, size_t height, draw_canvas **out) {
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess)
         return cleanup(fail(DRAW_ERR_CUDA, "cudaStreamCreate failed"));
     c->stream = c->own_stream;
-    if (cudaMallocHost(&c->h_status, 16 * sizeof(uint32_t)) != cudaSuccess)
+    if (cudaMallocHost(&c->h_status, draw_canvas::STATUS_SLOTS * N_STATUS_WORDS * sizeof(uint32_t)) != cudaSuccess)
         return cleanup(fail(DRAW_ERR_OUT_OF_MEMORY, "cudaMallocHost failed"));
-    std::memset(c->h_status, 0, 16 * sizeof(uint32_t));
+    std::memset(c->h_status, 0, draw_canvas::STATUS_SLOTS * N_STATUS_WORDS * sizeof(uint32_t));
     int rc = c->d_color.reserve(width * height * 4);
     if (rc) return cleanup(rc);
     rc = fill_color_black(c, 0, width * height); // vec![Pixel::black(); len], canvas.rs:368
@@ -1258,6 +1280,8 @@ void draw_canvas_destroy(draw_canvas *canvas) {
         if (cur != canvas->device) cudaSetDevice(canvas->device);
         if (canvas->stream) cudaStreamSynchronize(canvas->stream);
         if (canvas->join_event) cudaEventDestroy(canvas->join_event);
+        for (cudaEvent_t e : canvas->slot_event)
+            if (e) cudaEventDestroy(e);
         if (canvas->own_stream) cudaStreamDestroy(canvas->own_stream);
         if (canvas->h_color) cudaFreeHost(canvas->h_color);
         if (canvas->h_status) cudaFreeHost(canvas->h_status);
@@ -1308,6 +1332,8 @@ int draw_canvas_resize(draw_canvas *canvas, size_t width, size_t height) {
     canvas->height = height;
     TRY(fill_color_black(canvas, keep, new_n - keep));
     canvas->stripe_y0 = canvas->stripe_y1 = 0;
+    canvas->row_step = 1;
+    canvas->row_phase = 0;
     canvas->host_dirty = true;
     // self.init_depth(self.depth_max), canvas.rs:392 — allocates the depth buffer even if none existed
     return draw_canvas_init_depth(canvas, canvas->depth_max);
@@ -1448,6 +1474,54 @@ int draw_ipc_close(void *dev_ptr) {
     GUARD_END
 }
 
+int draw_device_alloc(size_t bytes, void **out_dev_ptr) {
+    GUARD_BEGIN
+    if (!out_dev_ptr || bytes == 0) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument or zero size");
+    int dev = 0;
+    TRY(pick_device(&dev));
+    CU(cudaMalloc(out_dev_ptr, bytes));
+    CU(cudaMemset(*out_dev_ptr, 0, bytes));
+    CU(cudaDeviceSynchronize());
+    return DRAW_OK;
+    GUARD_END
+}
+
+int draw_device_free(void *dev_ptr) {
+    GUARD_BEGIN
+    if (dev_ptr) CU(cudaFree(dev_ptr));
+    return DRAW_OK;
+    GUARD_END
+}
+
+int draw_ipc_export(void *dev_ptr, uint8_t handle[64]) {
+    GUARD_BEGIN
+    if (!dev_ptr || !handle) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, dev_ptr));
+    std::memcpy(handle, &h, 64);
+    return DRAW_OK;
+    GUARD_END
+}
+
+int draw_flag_signal(void *flag_dev, uint32_t value, draw_canvas *canvas) {
+    GUARD_BEGIN
+    if (!flag_dev || !canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    TRY(ensure_device(canvas->device));
+    CU(launch_flag_signal(static_cast<uint32_t *>(flag_dev), value, canvas->stream));
+    return DRAW_OK;
+    GUARD_END
+}
+
+int draw_flags_wait(const void *flags_dev, uint32_t n_flags, uint32_t value, void *error_word_dev, draw_canvas *canvas) {
+    GUARD_BEGIN
+    if (!flags_dev || !canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n_flags > 64) return fail(DRAW_ERR_INVALID_ARGUMENT, "at most 64 flags");
+    TRY(ensure_device(canvas->device));
+    CU(launch_flags_wait(static_cast<const uint32_t *>(flags_dev), n_flags, value, static_cast<uint32_t *>(error_word_dev), canvas->stream));
+    return DRAW_OK;
+    GUARD_END
+}
+
 int draw_canvas_set_stream(draw_canvas *canvas, void *cuda_stream) {
     GUARD_BEGIN
     if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas is NULL");
@@ -1495,6 +1569,14 @@ int draw_canvas_set_stripe(draw_canvas *canvas, size_t y0, size_t y1) {
         canvas->stripe_y0 = y0;
         canvas->stripe_y1 = y1;
     }
+    return DRAW_OK;
+}
+
+int draw_canvas_set_tile_rows(draw_canvas *canvas, uint32_t phase, uint32_t step) {
+    if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas is NULL");
+    if (step == 0 || phase >= step) return fail(DRAW_ERR_INVALID_ARGUMENT, "tile rows must satisfy phase < step, step >= 1");
+    canvas->row_step = step;
+    canvas->row_phase = phase;
     return DRAW_OK;
 }
 

@@ -5,23 +5,26 @@ partitions of the render path exist here:
 
   frame-parallel   a sequence of frames is dealt round-robin to the ranks; every rank holds the
                    whole scene and renders whole frames.  No collective on the data path.
-  sort-first       ONE frame is split into horizontal stripes of tile rows; every rank runs the
-                   (cheap) vertex/setup stages for the whole scene and rasterises only its stripe.
-                   Stripes are disjoint, so compositing needs no depth compare.  Two ways to land
-                   the stripes in rank 0's framebuffer:
-                     "nccl"  each rank renders into its own canvas, then send/recv of the stripe
-                             rows to rank 0 (torch.distributed batch_isend_irecv over NCCL/NVLink);
-                     "p2p"   rank 0 exports its colour buffer through CUDA IPC; the other ranks'
-                             tile kernels store their pixels straight into it over NVLink (peer
-                             stores from k_tile), so the gather is fused into the raster kernel and
-                             only a barrier remains.
+  sort-first       ONE frame is split by tile rows (rows of draw_tile_size() = 32 pixels): rank r renders the
+                   rows ty with ty % world == r ("interleaved": the scene usually sits mid-screen, contiguous
+                   stripes would give the middle ranks all of it) or a contiguous stripe of rows.  Every rank runs
+                   the per-vertex / per-triangle stages for the whole scene (k_front: replicated, bit-identical),
+                   bins and rasterises only its rows.  Rows are disjoint, so compositing needs no depth compare.
+                   Two ways to land the rows in rank 0's framebuffer:
+                     "nccl"  each rank renders into its own canvas, then one grouped NCCL send/recv of its row
+                             blocks to rank 0 (torch.distributed batch_isend_irecv), ordered on the canvas' stream:
+                             the canvas renders on torch's current stream, so the gather follows k_tile and the
+                             next frame follows the gather without the host waiting for either;
+                     "p2p"   rank 0 exports its colour buffer through CUDA IPC; the other ranks' tile kernels
+                             store their pixels straight into it over NVLink (peer stores from k_tile), so the
+                             gather is fused into the raster kernel.  Completion is a device-side flag per rank
+                             in a small buffer rank 0 owns (draw_flag_signal / draw_flags_wait): no collective,
+                             no host synchronisation in the loop.
 
 The colour buffer is y-flipped (canvas.rs:955-956): canvas rows [y0, y1) live in frame rows
 [H - y1, H - y0), still one contiguous byte range.
 """
 import ctypes as C
-
-import numpy as np
 
 TILE_H = 32  # draw_tile_size(); kept here so the partition logic is testable without the library
 
@@ -40,6 +43,20 @@ def stripe_bounds(height, world, tile_h=TILE_H):
     return out
 
 
+def interleaved_rows(height, world, rank, tile_h=TILE_H):
+    """Pixel-row blocks [(y0, y1)] of rank `rank` under the interleaved partition: tile rows ty % world == rank."""
+    rows = (height + tile_h - 1) // tile_h
+    return [(ty * tile_h, min((ty + 1) * tile_h, height)) for ty in range(rank, rows, world)]
+
+
+def rank_blocks(height, world, rank, layout, tile_h=TILE_H):
+    """Row blocks [(y0, y1)] a rank renders, for layout "interleaved" or "stripes"."""
+    if layout == "interleaved":
+        return interleaved_rows(height, world, rank, tile_h)
+    y0, y1 = stripe_bounds(height, world, tile_h)[rank]
+    return [(y0, y1)] if y1 > y0 else []
+
+
 def stripe_byte_range(height, width, y0, y1):
     """Byte range of canvas rows [y0, y1) inside the BGRA8 frame (rows are y-flipped)."""
     return (height - y1) * width * 4, (height - y0) * width * 4
@@ -50,26 +67,32 @@ def frames_of_rank(n_frames, world, rank):
     return list(range(rank, n_frames, world))
 
 
-def gather_stripes(dist, frame, bounds, height, width, root=0):
-    """Gather every rank's stripe of `frame` (flat uint8 tensor of H*W*4 bytes, same size on every
-    rank) into the root's `frame`.  Works with any backend (NCCL on GPU tensors, gloo on CPU)."""
+def gather_blocks(dist, frame, blocks_of_rank, height, width, root=0):
+    """Gather every rank's row blocks of `frame` (flat uint8 tensor of H*W*4 bytes, same size on every
+    rank) into the root's `frame`: one grouped send/recv.  `blocks_of_rank(r)` lists rank r's (y0, y1)
+    blocks.  Works with any backend (NCCL on GPU tensors, gloo on CPU); with NCCL the operations are
+    ordered on the current CUDA stream and the host does not wait for the data."""
     rank, world = dist.get_rank(), dist.get_world_size()
     ops = []
     if rank == root:
         for r in range(world):
-            y0, y1 = bounds[r]
-            if r == root or y1 <= y0:
+            if r == root:
                 continue
-            b0, b1 = stripe_byte_range(height, width, y0, y1)
-            ops.append(dist.P2POp(dist.irecv, frame[b0:b1], r))
+            for y0, y1 in blocks_of_rank(r):
+                b0, b1 = stripe_byte_range(height, width, y0, y1)
+                ops.append(dist.P2POp(dist.irecv, frame[b0:b1], r))
     else:
-        y0, y1 = bounds[rank]
-        if y1 > y0:
+        for y0, y1 in blocks_of_rank(rank):
             b0, b1 = stripe_byte_range(height, width, y0, y1)
             ops.append(dist.P2POp(dist.isend, frame[b0:b1], root))
     if ops:
         for req in dist.batch_isend_irecv(ops):
-            req.wait()
+            req.wait()  # NCCL: makes the current stream wait, not the host
+
+
+def gather_stripes(dist, frame, bounds, height, width, root=0):
+    """gather_blocks for contiguous stripes given as [(y0, y1)] per rank."""
+    gather_blocks(dist, frame, lambda r: [bounds[r]] if bounds[r][1] > bounds[r][0] else [], height, width, root)
 
 
 class _DevicePtr:
@@ -85,107 +108,228 @@ def canvas_color_tensor(canvas, device):
     return torch.as_tensor(_DevicePtr(ptr, canvas.width * canvas.height * 4), device=device)
 
 
-class SortFirst:
-    """One frame across all ranks.  `mode` is "nccl" or "p2p" (see module docstring)."""
+def _broadcast_handle(dist, device, make):
+    """Rank 0 produces a 64-byte IPC handle with make(); every rank gets it (or raises together)."""
+    import torch
+    handle = torch.zeros(64, dtype=torch.uint8, device=device)
+    error = None
+    if dist.get_rank() == 0:
+        try:
+            handle.copy_(torch.tensor(list(make()), dtype=torch.uint8))
+        except Exception as e:  # every rank must still reach the broadcast: an all-zero handle says "no"
+            error = e
+    dist.broadcast(handle, 0)
+    if error is not None:
+        raise error
+    if not bool(handle.any().item()):
+        raise RuntimeError("rank 0 could not export its buffer through CUDA IPC")
+    return (C.c_uint8 * 64)(*handle.cpu().tolist())
 
-    def __init__(self, scene, width, height, dist, device, mode="nccl", depth_max=100000.0):
+
+FLAG_CONSUMED = 32  # word of the flag buffer in which rank 0 publishes the last frame it has consumed
+FLAG_ERROR = 63     # set by a wait that timed out
+
+
+class SortFirst:
+    """One frame across all ranks.  mode: "nccl" or "p2p"; layout: "interleaved" or "stripes" (module docstring)."""
+
+    def __init__(self, scene, width, height, dist, device, mode="nccl", layout="interleaved", depth_max=100000.0, stream=None):
+        import torch
         import draw_b200
         from . import _native as N
-        self.scene, self.dist, self.mode = scene, dist, mode
+        self.scene, self.dist, self.mode, self.layout = scene, dist, mode, layout
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.width, self.height = width, height
-        self.bounds = stripe_bounds(height, self.world, draw_b200.tile_size())
+        th = draw_b200.tile_size()
+        self.blocks = lambda r: rank_blocks(height, self.world, r, layout, th)
+        self.mine = self.blocks(self.rank)
         self.canvas = draw_b200.Canvas(width, height)
         self.canvas.init_depth(depth_max)
         self.canvas.apply_offset(0, 0)
-        self.y0, self.y1 = self.bounds[self.rank]
-        if self.y1 > self.y0:
-            self.canvas.set_stripe(self.y0, self.y1)
+        # the canvas renders on a torch stream of its own: the NCCL operations are issued with that stream current
+        # and are therefore ordered against the frame (a NULL stream would mean "the canvas' own stream")
+        self.stream = stream if stream is not None else torch.cuda.Stream(device=device)
+        self.canvas.set_stream(self.stream.cuda_stream)
+        if self.mine:
+            if layout == "interleaved":
+                self.canvas.set_tile_rows(self.rank, self.world)
+            else:
+                self.canvas.set_stripe(*self.mine[0])
         self.frame = canvas_color_tensor(self.canvas, device)
-        self._peer = None
+        self.seq = 0
+        self._peer = self._flags = self._own_flags = None
         if mode == "p2p":
-            import torch
-            handle = torch.zeros(64, dtype=torch.uint8, device=device)
-            export_error = None
+            lib = N.lib()
+            raw = _broadcast_handle(dist, device, lambda: self._export_canvas(lib, N))
             if self.rank == 0:
-                buf = (C.c_uint8 * 64)()
-                try:
-                    N.check(N.lib().draw_canvas_ipc_export(self.canvas._h, buf))
-                    handle.copy_(torch.tensor(list(buf), dtype=torch.uint8))
-                except Exception as e:  # every rank must still reach the broadcast: an all-zero handle says "no"
-                    export_error = e
-            dist.broadcast(handle, 0)
-            if export_error is not None:
-                raise export_error
+                own = C.c_void_p()
+                N.check(lib.draw_device_alloc(256, C.byref(own)))
+                self._own_flags = own
+            flags_raw = _broadcast_handle(dist, device, lambda: self._export_ptr(lib, N, self._own_flags))
             if self.rank != 0:
-                if not bool(handle.any().item()):
-                    raise RuntimeError("rank 0 could not export its framebuffer through CUDA IPC")
-                raw = (C.c_uint8 * 64)(*handle.cpu().tolist())
-                peer = C.c_void_p()
-                N.check(N.lib().draw_ipc_open(raw, C.byref(peer)))
-                self._peer = peer
+                peer, flags = C.c_void_p(), C.c_void_p()
+                N.check(lib.draw_ipc_open(raw, C.byref(peer)))
+                N.check(lib.draw_ipc_open(flags_raw, C.byref(flags)))
+                self._peer, self._flags = peer, flags
                 _, own_depth = self.canvas.device_ptrs()
                 self.canvas.bind_external(peer.value, own_depth)  # colour -> rank 0's framebuffer over NVLink
+            else:
+                self._flags = self._own_flags
+            dist.barrier()
+
+    def _export_canvas(self, lib, N):
+        buf = (C.c_uint8 * 64)()
+        N.check(lib.draw_canvas_ipc_export(self.canvas._h, buf))
+        return buf
+
+    @staticmethod
+    def _export_ptr(lib, N, ptr):
+        buf = (C.c_uint8 * 64)()
+        N.check(lib.draw_ipc_export(ptr, buf))
+        return buf
 
     def close(self):
+        from . import _native as N
+        self.canvas.sync()
+        self.dist.barrier()  # nobody closes a mapping a peer may still be writing through
         if self._peer is not None:
-            from . import _native as N
             self.canvas.bind_external(None, None)
             N.lib().draw_ipc_close(self._peer)
-            self._peer = None
+            N.lib().draw_ipc_close(self._flags)
+            self._peer = self._flags = None
+        self.dist.barrier()
+        if self._own_flags is not None:
+            N.lib().draw_device_free(self._own_flags)
+            self._own_flags = self._flags = None
+
+    def _flag(self, word):
+        return C.c_void_p(self._flags.value + 4 * word)
 
     def render(self):
-        """Render this rank's stripe and land all stripes in rank 0's frame.  Returns after the
-        collective has been enqueued / completed; rank 0 then reads canvas.as_bytes_slice()."""
-        if self.y1 > self.y0:
-            self.scene.render(self.canvas)
+        """Enqueue: render this rank's rows and land all rows in rank 0's frame.  Nothing here waits on
+        the host; rank 0's canvas stream is ordered after the arrival of every rank's rows (read the
+        frame with canvas.as_bytes_slice(), or consume it on that stream)."""
+        from . import _native as N
+        self.seq += 1
         if self.mode == "nccl":
-            self.canvas.sync()  # NCCL runs on torch's stream; the stripe must be complete first
-            gather_stripes(self.dist, self.frame, self.bounds, self.height, self.width)
+            import torch
+            if self.mine:
+                self.scene.render(self.canvas)
+            with torch.cuda.stream(self.stream):
+                gather_blocks(self.dist, self.frame, self.blocks, self.height, self.width)
+            return
+        lib = N.lib()
+        if self.rank != 0:
+            # rank 0 must be done with the previous frame before its framebuffer is overwritten (k_tile waits for
+            # the canvas stream; k_front and k_raster of this frame do not)
+            N.check(lib.draw_flags_wait(self._flag(FLAG_CONSUMED), 1, self.seq - 1, self._flag(FLAG_ERROR), self.canvas._h))
+            if self.mine:
+                self.scene.render(self.canvas)
+            N.check(lib.draw_flag_signal(self._flag(self.rank), self.seq, self.canvas._h))
         else:
-            self.canvas.sync()  # peer stores are complete when the kernel is
-            self.dist.barrier()
+            # whatever rank 0 has enqueued on the canvas' stream so far (its use of the previous frame) comes first:
+            # starting the next frame is what tells the peers that the previous one has been consumed
+            N.check(lib.draw_flag_signal(self._flag(FLAG_CONSUMED), self.seq - 1, self.canvas._h))
+            if self.mine:
+                self.scene.render(self.canvas)
+            if self.world > 1:
+                N.check(lib.draw_flags_wait(self._flag(1), self.world - 1, self.seq, self._flag(FLAG_ERROR), self.canvas._h))
 
 
-def bench_sort_first(scene, cfg, dist, steps=50, warmup=5):
-    """Times sort-first rendering of one frame of `cfg` per step in both gather modes."""
-    import time
-
+def bench_sort_first(scene, cfg, dist, frames=120, warmup=8):
+    """Sort-first rendering of `frames` frames of cfg's camera path, one frame at a time across all ranks, in
+    both gather modes and both layouts.  Device-timed (CUDA events on the canvas' stream, max over ranks); the
+    composed frame of the first cameras is compared on rank 0 with the single-GPU frame (`bit_exact`)."""
     import torch
+    import draw_b200
     device = torch.device("cuda", torch.cuda.current_device())
+    rank, world = dist.get_rank(), dist.get_world_size()
     W, H = cfg["W"], cfg["H"]
-    out = {"workload": cfg["label"], "stripes": stripe_bounds(H, dist.get_world_size())}
-    for mode in ("nccl", "p2p"):
-        sf, err = None, ""
-        try:
-            sf = SortFirst(scene, W, H, dist, device, mode=mode)
-        except Exception as e:  # e.g. peer access not available
-            err = str(e)[:200]
-        # the ranks decide together: a mode is timed only if every rank could set it up (a rank that skipped on
-        # its own would leave the others waiting in the gather / barrier)
-        ok = torch.tensor([1 if sf is not None else 0], device=device, dtype=torch.int32)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) == 0:
-            if sf is not None:
-                sf.close()
-            out[mode] = {"error": err or "another rank could not set this mode up"}
-            continue
-        for _ in range(max(warmup, 3)):
-            sf.render()
-        dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            sf.render()
-        dist.barrier()
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        ms = float(dt.item()) / steps * 1e3
-        out[mode] = {"ms_per_frame": ms, "frames_per_s": 1e3 / ms, "mtri_per_s": cfg["triangles"] / ms / 1e3,
-                     "gather_bytes_into_root": 4 * W * (H - (sf.bounds[0][1] - sf.bounds[0][0]))}
-        sf.close()
-        del sf
-    out["note"] = ("one frame split into tile-row stripes; vertex/setup replicated on every rank; host clock "
-                   "around `steps` frames with barriers, max over ranks; includes the per-frame stream sync")
+    cams = cfg["cameras"]
+    cam_values = [draw_b200.Camera.new(c[:3], c[3:]) for c in cams] if cams is not None else None
+    n_cam = len(cam_values) if cam_values else 1
+
+    def set_cam(k):
+        if cam_values is not None:
+            scene.camera = cam_values[k % n_cam]
+
+    stream = torch.cuda.Stream(device=device)
+    # single-GPU reference on every rank: the time of the same frames rendered whole, one at a time
+    full = draw_b200.Canvas(W, H)
+    full.init_depth(100000.0)
+    full.apply_offset(0, 0)
+    full.set_stream(stream.cuda_stream)
+    for k in range(n_cam):  # settles work-buffer capacities over the path
+        set_cam(k)
+        scene.render(full)
+        full.sync()
+    check = sorted({0, n_cam // 3, (2 * n_cam) // 3}) if rank == 0 else []
+    refs = {}
+    for k in check:
+        set_cam(k)
+        scene.render(full)
+        with torch.cuda.stream(stream):
+            refs[k] = canvas_color_tensor(full, device).clone()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for k in range(frames):
+        set_cam(k)
+        scene.render(full)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    single_ms = e0.elapsed_time(e1) / frames
+    del full
+    out = {"workload": cfg["label"], "frames": frames, "single_gpu_ms_per_frame": single_ms,
+           "gather_bytes_into_root": 4 * W * H * (world - 1) // world}
+    for layout in ("interleaved", "stripes"):
+        for mode in ("p2p", "nccl"):
+            key = f"{mode}_{layout}"
+            sf, err = None, ""
+            try:
+                sf = SortFirst(scene, W, H, dist, device, mode=mode, layout=layout, stream=stream)
+            except Exception as e:  # e.g. peer access not available
+                err = str(e)[:200]
+            # the ranks decide together: a mode is timed only if every rank could set it up (a rank that skipped on
+            # its own would leave the others waiting in the gather)
+            ok = torch.tensor([1 if sf is not None else 0], device=device, dtype=torch.int32)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                if sf is not None:
+                    sf.close()
+                out[key] = {"error": err or "another rank could not set this mode up"}
+                continue
+            # parity first: composed frame == single-GPU frame, bit for bit (every rank renders, rank 0 compares)
+            bit_exact = True
+            for k in sorted({0, n_cam // 3, (2 * n_cam) // 3}):
+                set_cam(k)
+                sf.render()
+                if rank == 0:
+                    with torch.cuda.stream(stream):
+                        bit_exact = bit_exact and bool(torch.equal(sf.frame, refs[k]))
+            for k in range(warmup):
+                set_cam(k)
+                sf.render()
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0.record(stream)
+            for k in range(frames):
+                set_cam(k)
+                sf.render()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            dt = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            ms = float(dt.item()) / frames
+            be = torch.tensor([1 if bit_exact else 0], device=device, dtype=torch.int32)
+            dist.broadcast(be, 0)
+            out[key] = {"ms_per_frame": ms, "frames_per_s": 1e3 / ms, "mtri_per_s": cfg["triangles"] / ms / 1e3,
+                        "speedup_vs_single_gpu": single_ms / ms, "bit_exact": bool(int(be.item()))}
+            sf.close()
+            del sf
+    out["note"] = ("one frame at a time split by tile rows across the ranks; per-vertex / per-triangle stages replicated on "
+                   "every rank; CUDA events on the canvas stream around all frames, max over ranks, no host synchronisation "
+                   "inside the loop; single_gpu_ms_per_frame = the same frames rendered whole on one GPU the same way; "
+                   "bit_exact = composed frame of three cameras of the path == single-GPU frame")
     return out

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DRAW_B200_VERSION 100 /* 0.1.0 */
+#define DRAW_B200_VERSION 200 /* 0.2.0 */
 
 typedef enum draw_status {
     DRAW_OK = 0,
@@ -93,13 +93,15 @@ typedef enum draw_camera_dir {
 /* Counters of the last completed frame (device-side bookkeeping, read back at sync). */
 typedef struct draw_frame_stats {
     uint32_t input_triangles;   /* triangles in the scene's draw list */
-    uint32_t setup_records;     /* triangles that survived cull / reject / clip / zero-area */
-    uint32_t tile_refs;         /* (tile, triangle) pairs produced by binning */
-    uint32_t transparent_slots; /* slots scanned by the ordered transparent pass */
+    uint32_t setup_records;     /* record slots used: triangles that survived cull / reject / clip / zero-area (4 per clipped one) */
+    uint32_t tile_refs;         /* (tile, triangle) pairs produced by binning, all classes */
+    uint32_t large_refs, medium_refs, small_refs, transparent_refs; /* by class */
     uint32_t overflow;          /* non-zero: a device buffer was too small, frame was re-rendered */
-    uint32_t empty_tiles;       /* tiles of the stripe nothing was binned to (they only get the clear colour and depth) */
-    uint32_t key_pages;         /* tiles whose medium / small triangles k_raster rasterised into a key page */
-    uint32_t clear_in_tile;     /* non-zero: k_tile's CTAs wrote the empty tiles between their items; 0: k_clear_empty did */
+    uint32_t empty_tiles;       /* tiles of this render's rows nothing was binned to (they only get the clear colour and depth) */
+    uint32_t work_items;        /* k_tile work items: non-empty tiles, dense ones cut into windows */
+    uint32_t front_phase_ns[7]; /* k_front, CTA 0: vertex phase, barrier, triangle phase, barrier (+ huge-record phase), tile phase;
+                                   then the triangle phase of the slowest CTA and the huge-record phase */
+    uint32_t front_block_ns[5]; /* k_front, first 256-triangle block: set-up, slot scan, record write, binning, clip path */
 } draw_frame_stats;
 
 /* ---- library ------------------------------------------------------------------------ */
@@ -148,18 +150,19 @@ int draw_scene_counts(const draw_scene *scene, size_t *n_objects, size_t *n_tria
 /* Kernels launched by this scene so far (bench.py reports the delta over the timed region). */
 int draw_scene_launch_count(const draw_scene *scene, uint64_t *out);
 
-/* Measurement tap: when enabled, every frame records CUDA events between its kernels on the
- * canvas' stream; last_kernel_times waits for the frame and returns the device time in ms of
- * k_vertex, k_setup, k_clip, k_bin<count>, k_alloc, k_bin<fill>, k_raster, k_clear_empty, k_tile, k_shade (DESIGN.md describes them). */
+/* Measurement tap: when enabled, every frame records CUDA events between its kernels on the frame's
+ * stream; last_kernel_times waits for the frame and returns the device time in ms of
+ * k_sort_transparent, k_front, k_raster, k_tile (DESIGN.md describes them). */
 int draw_scene_set_kernel_timing(draw_scene *scene, int enabled);
-int draw_scene_last_kernel_times(draw_scene *scene, draw_canvas *canvas, float ms[10]);
+int draw_scene_last_kernel_times(draw_scene *scene, draw_canvas *canvas, float ms[4]);
 
-/* Debug tap: sizes of the last frame's tile lists (coarse tiles first, then fine tiles, see
- * DESIGN.md).  out == NULL only returns the number of coarse tiles. */
+/* Debug tap: per tile of the last frame, three arrays of n_coarse words each: large references, medium / small
+ * weight (8x4 blocks of bbox; non-zero = the tile has a key page to merge), transparent references.
+ * out == NULL only returns the number of tiles. */
 int draw_scene_debug_list_counts(draw_scene *scene, draw_canvas *canvas, uint32_t *out, size_t n, size_t *n_coarse);
 
-/* Debug tap: enable != 0 makes later frames record the SM cycles each coarse tile's CTA spent in
- * k_tile; out (n = number of coarse tiles) receives the last frame's values, or NULL to only toggle. */
+/* Debug tap: enable != 0 makes later frames record SM cycles per tile in k_tile; out (n <= 4 * number of tiles)
+ * receives the last frame's values — whole item, end of phase A, end of phase C, end of phase D — or NULL to only toggle. */
 int draw_scene_debug_tile_cycles(draw_scene *scene, draw_canvas *canvas, int enable, uint32_t *out, size_t n);
 /* Debug timeline: while enabled, thread 0 of every CTA of the frame kernels appends one record of four
  * uint32 (kernel id | SM << 8 | work set << 24, CTA index, start ns, end ns; low 32 bits of the GPU's global
@@ -213,6 +216,10 @@ int draw_canvas_stream_wait(draw_canvas *canvas, void *cuda_stream);
  * colour row = height-1-y).  Rows outside are left untouched.  (0, height) = whole frame.
  * y0 and y1 must be multiples of the tile height (draw_tile_size, 32) or equal to height. */
 int draw_canvas_set_stripe(draw_canvas *canvas, size_t y0, size_t y1);
+/* Sort-first partition, interleaved: render only the tile rows ty (rows of draw_tile_size() pixels, counted from
+ * canvas y = 0) with ty % step == phase, inside the stripe.  Interleaving balances the ranks when the scene sits
+ * mid-screen.  (0, 1) = every row.  Reset by draw_canvas_resize. */
+int draw_canvas_set_tile_rows(draw_canvas *canvas, uint32_t phase, uint32_t step);
 int draw_tile_size(void);
 /* Peer access for the fused sort-first gather (one process per GPU): the owner exports its
  * canvas' own colour buffer as a 64-byte CUDA IPC handle; another process on the same node opens
@@ -221,6 +228,17 @@ int draw_tile_size(void);
 int draw_canvas_ipc_export(draw_canvas *canvas, uint8_t handle[64]);
 int draw_ipc_open(const uint8_t handle[64], void **out_dev_ptr);
 int draw_ipc_close(void *dev_ptr);
+/* Device-side completion flags of that gather (no host in the loop, no collective): a small zero-filled device
+ * buffer of 32-bit words owned by one rank (draw_device_alloc) and opened by the others (draw_ipc_export /
+ * draw_ipc_open).  draw_flag_signal enqueues, behind everything enqueued so far for the canvas, a system-scope
+ * release store of `value` into one word (local or a peer's); draw_flags_wait enqueues on the canvas' stream a
+ * wait until each of the n_flags (<= 64) consecutive words has reached `value` (words only grow; wrap-safe).  The
+ * wait gives up after 5 s and sets *error_word_dev (may be NULL) to 1 instead of hanging the device. */
+int draw_device_alloc(size_t bytes, void **out_dev_ptr);
+int draw_device_free(void *dev_ptr);
+int draw_ipc_export(void *dev_ptr, uint8_t handle[64]);
+int draw_flag_signal(void *flag_dev, uint32_t value, draw_canvas *canvas);
+int draw_flags_wait(const void *flags_dev, uint32_t n_flags, uint32_t value, void *error_word_dev, draw_canvas *canvas);
 
 /* ---- Object loader (object.rs:73-454), host only ------------------------------------- */
 /* Object::load_from_file :106.  Texture images referenced by the MTL are decoded by the

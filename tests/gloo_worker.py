@@ -31,6 +31,21 @@ def main():
                 assert int(img[H - 1 - y, 0, 0]) == (y * 7 + r) & 255, (r, y)
                 assert (img[H - 1 - y] == img[H - 1 - y, 0, 0]).all()
 
+    # the same with interleaved tile rows (rank r owns rows ty % world == r): one grouped send/recv of row blocks
+    frame2 = torch.zeros(H * W * 4, dtype=torch.uint8)
+    img2 = frame2.view(H, W, 4)
+    blocks = lambda r: multi.interleaved_rows(H, world, r)
+    for y0, y1 in blocks(rank):
+        for y in range(y0, y1):
+            img2[H - 1 - y] = (y * 5 + rank) & 255
+    multi.gather_blocks(dist, frame2, blocks, H, W, root=0)
+    if rank == 0:
+        for r in range(world):
+            for a, b in blocks(r):
+                for y in range(a, b):
+                    assert int(img2[H - 1 - y, 0, 0]) == (y * 5 + r) & 255, (r, y)
+                    assert (img2[H - 1 - y] == img2[H - 1 - y, 0, 0]).all()
+
     # frame-parallel assignment covers every frame exactly once
     mine = multi.frames_of_rank(10, world, rank)
     gathered = [None] * world

@@ -1,5 +1,7 @@
 """Worker of tests/test_gpu_multi.py: sort-first rendering on WORLD_SIZE GPUs must reproduce the
-single-GPU frame bit for bit, through the NCCL gather and through the fused peer-store path."""
+single-GPU frame bit for bit, through the NCCL gather and through the fused peer-store path, with interleaved
+tile rows and with contiguous stripes.  (The single-GPU frame is the one tests/test_gpu_parity.py compares with
+the oracle, so equality with it is equality with the oracle.)"""
 import os
 import sys
 
@@ -35,18 +37,18 @@ def main():
             full.init_depth(100000.0)
             scene.render(full)
             ref = full.as_bytes_slice()
-        for mode in ("nccl", "p2p"):
-            sf = multi.SortFirst(scene, W, H, dist, device, mode=mode)
-            for _ in range(2):
-                sf.render()
-            if rank == 0:
-                got = sf.canvas.as_bytes_slice()
-                assert np.array_equal(got, ref), f"{scene_name} {mode}: composed frame differs from the single-GPU frame"
-            dist.barrier()
-            sf.close()
-            del sf
+        for layout in ("interleaved", "stripes"):
+            for mode in ("nccl", "p2p"):
+                sf = multi.SortFirst(scene, W, H, dist, device, mode=mode, layout=layout)
+                for _ in range(3):  # consecutive frames into the same framebuffer: the flags / stream ordering hold
+                    sf.render()
+                if rank == 0:
+                    got = sf.canvas.as_bytes_slice()
+                    assert np.array_equal(got, ref), f"{scene_name} {mode} {layout}: composed frame differs from the single-GPU frame"
+                sf.close()
+                del sf
         if rank == 0:
-            print(f"{scene_name} {W}x{H}: sort-first over {dist.get_world_size()} GPUs == single GPU (nccl, p2p)", flush=True)
+            print(f"{scene_name} {W}x{H}: sort-first over {dist.get_world_size()} GPUs == single GPU (nccl, p2p) x (interleaved, stripes)", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

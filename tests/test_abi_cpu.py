@@ -32,10 +32,20 @@ def test_binding_covers_the_header():
     assert set(_native.SIGNATURES) == _declared_symbols()
 
 
+def test_rust_sys_crate_binds_every_declared_symbol():
+    """bindings/draw-b200-sys is shipped as source (no Rust toolchain here): it must at least name every export."""
+    src = open(os.path.join(ROOT, "bindings", "draw-b200-sys", "src", "lib.rs")).read()
+    bound = set(re.findall(r"pub fn (draw_[a-z0-9_]+)\s*\(", src))
+    assert bound == _declared_symbols(), sorted(bound ^ _declared_symbols())
+    for f in ("Cargo.toml", "build.rs"):
+        assert os.path.exists(os.path.join(ROOT, "bindings", "draw-b200-sys", f))
+    assert "DRAW_B200_VERSION: c_int = 200" in src
+
+
 def test_version_and_error_string():
     from draw_b200 import _native
     L = _native.lib()
-    assert L.draw_version() == 100
+    assert L.draw_version() == 200
     assert isinstance(L.draw_last_error(), bytes)
     assert L.draw_tile_size() == 32
 

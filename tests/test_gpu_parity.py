@@ -214,6 +214,35 @@ def test_stripes_compose_to_the_full_frame():
     assert_frames_equal((canvas.as_bytes_slice(), canvas.depth()), full, "stripes")
 
 
+def test_interleaved_tile_rows_compose_to_the_full_frame():
+    """draw_canvas_set_tile_rows: the sort-first partition by tile rows ty % step == phase; the passes of all phases
+    (here on one GPU, one after the other) compose the full frame, also inside a stripe and with a transparent mesh."""
+    import draw_b200
+    for name, (W, H), steps in (("c3_trio", (1280, 720), (2, 3, 8)), ("c1_lemur_airplane", (800, 600), (4,)), ("c4_dungeon", (960, 540), (5,))):
+        objs = load_scene(name)
+        full = render_gpu(objs, W, H)
+        scene, canvas = draw_b200.Scene(W, H), draw_b200.Canvas(W, H)
+        canvas.init_depth(DEPTH_MAX)
+        for o in objs:
+            scene.add_obj(o)
+        for step in steps:
+            canvas.clear()
+            for phase in range(step):
+                canvas.set_tile_rows(phase, step)
+                scene.render(canvas)
+            assert_frames_equal((canvas.as_bytes_slice(), canvas.depth()), full, f"{name} rows % {step}")
+        # interleaved rows inside two stripes
+        canvas.clear()
+        for y0, y1 in ((0, 256), (256, H)):
+            canvas.set_stripe(y0, y1)
+            for phase in range(3):
+                canvas.set_tile_rows(phase, 3)
+                scene.render(canvas)
+        assert_frames_equal((canvas.as_bytes_slice(), canvas.depth()), full, f"{name} rows % 3 in stripes")
+    with pytest.raises(draw_b200.DrawError):
+        canvas.set_tile_rows(3, 3)
+
+
 def test_resize_and_clear_semantics():
     import draw_b200
     from oracle import pyoracle
@@ -255,7 +284,8 @@ def test_small_buffers_grow_and_rerender():
     objs = load_scene("c4_dungeon")
     (got, scene, canvas) = render_gpu(objs, 3840, 2160, cam=path[60], return_handles=True)
     st = canvas.last_frame_stats()
-    assert st["setup_records"] > 0 and st["tile_refs"] > 0
+    assert st["setup_records"] > 0 and st["tile_refs"] > 0 and st["work_items"] > 0
+    assert st["tile_refs"] == st["large_refs"] + st["medium_refs"] + st["small_refs"] + st["transparent_refs"]
     want = render_oracle(objs, 3840, 2160, cam=path[60])
     assert_frames_equal(got, want, "C4 frame 60")
 
@@ -312,3 +342,47 @@ def test_painter_order_survives_adding_an_object():
         s.render(c)
         o.render(oc)
     assert_frames_equal((c.as_bytes_slice(), c.depth()), (oc.as_bytes(), oc.depth()), "order after add_obj")
+
+
+def test_glass_mesh_of_ten_thousand_triangles():
+    """The transparent pass is binned per tile and put in draw order on chip (k_tile phase D): a 10 240-triangle
+    glass torus (40 960 ordered slots: forty 1024-slot ordering windows) over an opaque backdrop, small on screen so
+    that single tiles hold hundreds of references, and again filling the screen."""
+    back = _tri_object([[-120, -90, -40], [120, -90, -40], [0, 110, -40]], kd=(1.0, 1.0, 0.0))
+    glass = _glass_torus(80, 64)
+    assert glass.triangle_count() == 10240
+    cams = [np.array(c, F) for c in ([0, 0, 150, 0, 0, -150], [60, 20, 60, -1, -0.3, -1], [0, 0, 150, 0, 0, -150])]
+    got, want = _both([back, glass], 480, 360, cam=cams)
+    assert (want[0][..., 3] == 0).any(), "transparent pass not exercised"
+    assert_frames_equal(got, want, "10k glass torus")
+    got, want = _both([glass, back], 1920, 1080, cam=cams[1:2])
+    assert_frames_equal(got, want, "10k glass torus, 1080p")
+
+
+def test_opaque_scene_then_a_transparent_object_is_added():
+    """an opaque-only scene renders (graph replay), a transparent object is added, the next frames take
+    the path with the painter sort; the cross-frame ordering event must be usable in both."""
+    import draw_b200
+    from oracle import pyoracle
+    W, H = 320, 240
+    s, c = draw_b200.Scene(W, H), draw_b200.Canvas(W, H)
+    o, oc = pyoracle.Scene(W, H), pyoracle.Canvas(W, H)
+    c.init_depth(DEPTH_MAX)
+    oc.init_depth(DEPTH_MAX)
+    back = _tri_object([[-120, -90, -40], [120, -90, -40], [0, 110, -40]], kd=(1.0, 1.0, 0.0))
+    s.add_obj(back)
+    o.add_obj(back)
+    for _ in range(3):
+        s.render(c)
+        o.render(oc)
+    assert_frames_equal((c.as_bytes_slice(), c.depth()), (oc.as_bytes(), oc.depth()), "opaque only")
+    glass = _glass_torus(24, 20)
+    s.add_obj(glass)
+    o.add_obj(glass)
+    for cam in ([0, 0, 150, 0, 0, -150], [120, 40, 90, -1, -0.3, -0.8], [120, 40, 90, -1, -0.3, -0.8]):
+        cam = np.array(cam, F)
+        s.camera = draw_b200.Camera.new(cam[:3], cam[3:])
+        o.set_camera(cam[:3], cam[3:])
+        s.render(c)
+        o.render(oc)
+    assert_frames_equal((c.as_bytes_slice(), c.depth()), (oc.as_bytes(), oc.depth()), "after adding glass")

@@ -1,16 +1,14 @@
 """The alternative code paths of the library, each bit-exact against the oracle.
 
-The defaults (CUDA-graph replay, k_raster key pages, in-tile shading) are what every other GPU test
-runs.  The knobs that select the other paths are read once when the library is loaded, so each
-variant runs a subset of the parity tests in a fresh interpreter:
+The defaults (CUDA-graph replay of the frame, k_front with one CTA per SM for small scenes, tile windows) are
+what every other GPU test runs.  The knobs that select the other paths are read once when the library is loaded,
+so each variant runs a subset of the parity tests in a fresh interpreter:
 
-  DRAW_B200_PAGES=0        no key pages: k_tile rasterises the medium / small lists itself (phases B1, B2)
-  DRAW_B200_DEFER_MAX=16   k_shade resolves the key pages of tiles with few large triangles
-  DRAW_B200_GRAPH=0        direct kernel launches instead of graph replay (PDL between the kernels)
+  DRAW_B200_GRAPH=0        direct kernel launches instead of graph replay
   DRAW_B200_SPLIT_MAX=1    no tile windows
-  DRAW_B200_CLEAR_IN_TILE=0  the empty tiles are written by k_clear_empty on its own stream (default: by k_tile's
-                             CTAs after each raster item, mode 2; 1 = before the item, 3 = alternating)
-  DRAW_B200_BIN_RPW=0      k_bin always in thread-per-record mode (default: warp per record for small scenes)
+  DRAW_B200_FRONT_CPS=4    k_front with four CTAs per SM (what large scenes get) on the small test scenes
+  DRAW_B200_TILE_CTAS / DRAW_B200_RASTER_CTAS / DRAW_B200_SETS   small grids, two frames in flight
+  DRAW_B200_REC_CAP / DRAW_B200_REFS_CAP   tiny initial work buffers: every first frame overflows and is re-rendered
 """
 import os
 import subprocess
@@ -22,15 +20,13 @@ from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
 
-SUBSET = "c2 or c3 or c1_textured or clipping or odd or ties or degenerate or stripes or checker or small_buffers"
+SUBSET = "c2 or c3 or c1_textured or clipping or odd or ties or degenerate or stripes or checker or small_buffers or glass"
 
 
-@pytest.mark.parametrize("env", [{"DRAW_B200_PAGES": "0"}, {"DRAW_B200_DEFER_MAX": "16"}, {"DRAW_B200_GRAPH": "0"},
-                                 {"DRAW_B200_SPLIT_MAX": "1", "DRAW_B200_DEFER_MAX": "1"},
-                                 {"DRAW_B200_CLEAR_IN_TILE": "0", "DRAW_B200_BIN_RPW": "0"},
-                                 {"DRAW_B200_CLEAR_IN_TILE": "3", "DRAW_B200_TILE_CTAS": "37", "DRAW_B200_SETS": "2"}],
-                         ids=["no_pages", "k_shade", "no_graph", "no_windows_raster_only_deferred", "k_clear_empty_thread_bin",
-                              "clear_alternating_few_ctas"])
+@pytest.mark.parametrize("env", [{"DRAW_B200_GRAPH": "0"}, {"DRAW_B200_SPLIT_MAX": "1"}, {"DRAW_B200_FRONT_CPS": "4"},
+                                 {"DRAW_B200_TILE_CTAS": "37", "DRAW_B200_RASTER_CTAS": "19", "DRAW_B200_SETS": "2"},
+                                 {"DRAW_B200_REC_CAP": "1500", "DRAW_B200_REFS_CAP": "3000"}],
+                         ids=["no_graph", "no_windows", "front_4_per_sm", "few_ctas_two_sets", "tiny_buffers"])
 def test_alternative_paths_are_bit_exact(env):
     e = dict(os.environ)
     e.update(env)
@@ -38,6 +34,16 @@ def test_alternative_paths_are_bit_exact(env):
                         "-k", SUBSET], env=e, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "failed" not in r.stdout
+
+
+def test_forced_overflow_rerenders_from_the_frame_s_own_inputs():
+    """Tiny work buffers: the overflow flags are raised (asserted), the frame is re-rendered with grown buffers from
+    the camera / stripe it was rendered with — also when those have changed before the frame is read."""
+    e = dict(os.environ)
+    e.update({"DRAW_B200_REC_CAP": "600", "DRAW_B200_REFS_CAP": "900"})
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "overflow_worker.py")], env=e, capture_output=True, text=True,
+                       timeout=600, cwd=ROOT)
+    assert r.returncode == 0 and "overflow worker ok" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
 def test_host_mirror_follows_every_render():

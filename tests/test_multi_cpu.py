@@ -30,6 +30,18 @@ def test_stripe_byte_range_is_flipped_and_contiguous():
     assert all(x[0] == y[1] for x, y in zip(ranges, ranges[1:]))
 
 
+def test_interleaved_rows_partition_the_canvas():
+    for H in (2160, 4320, 600, 33, 32, 1):
+        for world in (1, 2, 4, 8):
+            rows = sorted(sum((multi.interleaved_rows(H, world, r) for r in range(world)), []))
+            assert rows[0][0] == 0 and rows[-1][1] == H and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+            counts = [len(multi.interleaved_rows(H, world, r)) for r in range(world)]
+            assert max(counts) - min(counts) <= 1
+            for r in range(world):
+                assert all((y0 // 32) % world == r for y0, _ in multi.interleaved_rows(H, world, r))
+            assert multi.rank_blocks(H, world, 0, "stripes") == ([multi.stripe_bounds(H, world)[0]] if multi.stripe_bounds(H, world)[0][1] else [])
+
+
 def test_frames_of_rank():
     assert multi.frames_of_rank(7, 4, 1) == [1, 5]
     assert sum((multi.frames_of_rank(120, 8, r) for r in range(8)), []).__len__() == 120

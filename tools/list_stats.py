@@ -12,23 +12,27 @@ for name in sys.argv[1:] or ["c3"]:
     c.init_depth(100000.0)
     for o in cfg["objects"]:
         s.add_obj(o)
-    frames = [None] if cfg["cameras"] is None else [cfg["cameras"][k] for k in (0, 30, 60, 90)]
+    frames = [None] if cfg["cameras"] is None else [cfg["cameras"][k % len(cfg["cameras"])] for k in (0, 30, 60, 90)]
     for cam in frames:
         if cam is not None:
             s.camera = draw_b200.Camera.new(cam[:3], cam[3:])
         s.debug_tile_cycles(enable=True)
         s.render(c)
         s.render(c)
-        cyc3 = s.debug_tile_cycles(c)
-        cyc = cyc3[0]
-        coarse, medium, fine = s.debug_list_counts(c)
+        cyc4 = s.debug_tile_cycles(c)  # rows: whole item, end of phase A, of phase C, of phase D
+        cyc = cyc4[0]
+        large, ms, transparent = s.debug_list_counts(c)
         order = np.argsort(cyc)[::-1][:8]
-        print("  slowest tiles (cycles, large n, medium n, small n):", [(int(cyc[t]), int(coarse[t]), int(medium[t]), int(fine[t]), "A/B/rest", int(cyc3[1][t]), int(cyc3[2][t]) - int(cyc3[1][t]), int(cyc[t]) - int(cyc3[2][t])) for t in order])
-        print("  cycles p50/p90/p99/max", [int(np.percentile(cyc, p)) for p in (50, 90, 99, 100)], "sum", int(cyc.sum()),
-              "empty-tile median", int(np.median(cyc[(coarse == 0)])))
+        print("  slowest tiles (cycles | large refs, medium/small weight, transparent refs | cycles in A, C, D, E):")
+        for t in order:
+            print("   ", int(cyc[t]), "|", int(large[t]), int(ms[t]), int(transparent[t]), "|", int(cyc4[1][t]), int(cyc4[2][t]) - int(cyc4[1][t]),
+                  int(cyc4[3][t]) - int(cyc4[2][t]), int(cyc[t]) - int(cyc4[3][t]))
+        busy = cyc > 0
+        print("  item cycles p50/p90/p99/max", [int(np.percentile(cyc[busy], p)) for p in (50, 90, 99, 100)], "sum", int(cyc.sum()), "items", int(busy.sum()))
+        for nm, row0, row1 in (("A", None, 1), ("C", 1, 2), ("D", 2, 3), ("E", 3, 0)):
+            d = cyc4[row1].astype(np.int64) - (cyc4[row0].astype(np.int64) if row0 is not None else 0)
+            print(f"    phase {nm}: p50/p90/max", [int(np.percentile(d[busy], p)) for p in (50, 90, 100)], "share of item cycles", round(float(d[busy].sum()) / max(1, int(cyc.sum())), 3))
         st = c.last_frame_stats()
-        q = lambda a: [int(np.percentile(a, p)) for p in (50, 90, 99, 100)]
-        print(name, "records", st["setup_records"], "refs", st["tile_refs"],
-              "| medium lists: nonempty", int((medium > 0).sum()), "sum", int(medium.sum()), "max", int(medium.max()),
-              "| coarse lists: nonempty", int((coarse > 0).sum()), "of", coarse.size, "sum", int(coarse.sum()), "p50/90/99/max", q(coarse[coarse > 0]) if (coarse > 0).any() else None,
-              "| fine lists: nonempty", int((fine > 0).sum()), "of", fine.size, "sum", int(fine.sum()), "p50/90/99/max", q(fine[fine > 0]) if (fine > 0).any() else None)
+        print(name, {k: st[k] for k in ("setup_records", "large_refs", "medium_refs", "small_refs", "transparent_refs", "empty_tiles", "work_items")},
+              "k_front phases us", [round(x / 1e3, 1) for x in st["front_phase_ns"]],
+              "first block (set-up, scan, records, binning, clip) us", [round(x / 1e3, 1) for x in st["front_block_ns"]])

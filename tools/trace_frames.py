@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench, draw_b200
 
-NAMES = ["vertex", "setup", "clip", "bin_count", "alloc", "bin_fill", "raster", "clear", "tile", "shade"]
+NAMES = ["-", "front", "raster", "tile"]  # CtaTrace kernel ids (k_front.cu, k_raster.cu, k_tile.cu)
 name = sys.argv[1] if len(sys.argv) > 1 else "c3"
 n_frames = int(sys.argv[2]) if len(sys.argv) > 2 else 24
 mode = sys.argv[3] if len(sys.argv) > 3 else "shared"
@@ -46,7 +46,7 @@ span = t1.max()
 print(f"{name} {mode}: {len(rec)} CTA records, {n_frames} frames in {span / 1e3:.1f} us = {span / 1e3 / n_frames:.2f} us/frame")
 # launches: group by (kernel, tag), split in time where gaps between consecutive CTA starts exceed the frame cadence / 2
 launches = []
-for k in range(10):
+for k in range(len(NAMES)):
     for g in range(8):
         m = (kid == k) & (tag == g)
         if not m.any():
@@ -64,7 +64,7 @@ for a, b, k, g, n, nsm, busy in launches:
     if lo <= a <= hi:
         print(f"{(a - lo) / 1e3:8.1f} {(b - lo) / 1e3:7.1f} {(b - a) / 1e3:7.1f} {NAMES[k]:10s} {g:4d} {n:5d} {nsm:4d} {busy / 1e3:10.1f}")
 print("\nper kernel, per frame: mean launch duration us | CTA-time us | CTA-time / 148 SMs us")
-for k in range(10):
+for k in range(len(NAMES)):
     ls = [l for l in launches if l[2] == k]
     if ls:
         print(f"  {NAMES[k]:10s} {np.mean([(l[1] - l[0]) for l in ls]) / 1e3:8.1f} {np.mean([l[6] for l in ls]) / 1e3:10.1f} {np.mean([l[6] for l in ls]) / 1e3 / 148:8.2f}")
