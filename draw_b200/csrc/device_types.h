@@ -89,6 +89,7 @@ struct FrameUniforms {
     uint32_t n_coarse;                 // tiles_x * tiles_y
     uint32_t split_min_cost, split_div, split_max; // k_front's tile splitting policy (defaults: TILE_SPLIT_*)
     uint32_t bar_base;                 // value of the work set's grid-barrier counter when k_front starts (host-tracked)
+    uint32_t clear_first;              // k_tile: a CTA writes its share of the empty tiles before its raster item (else after it)
     uint32_t *status_host;             // pinned host memory of the canvas (device-mapped): k_tile copies counters[0..31] there
     uint8_t *color;                    // the canvas: BGRA8, row 0 = top (canvas.rs:955-956)
     float *depth;                      // depth buffer, row 0 = y 0 (canvas.rs:413-423)

@@ -24,7 +24,7 @@
 //                     bucket segment + rank of k_tile's work list, the empty tiles to the list for the clear.
 // (The pairs are scattered into the tiles' lists by the next kernel's prologue: k_raster, which does not need them.)
 //
-// The grid is 148 x c CTAs of 128 threads at <= 64 registers, c = 2 for small scenes — they fit on an SM beside
+// The grid is 148 x c CTAs of 128 threads at <= 64 registers, c = 1 for small scenes — it fits on an SM beside
 // three CTAs of another frame's k_tile, so frames in flight still overlap — and launched cooperatively
 // (all CTAs co-resident: the barriers cannot deadlock).  Arithmetic contract: device_math.cuh.
 #include "device_math.cuh"

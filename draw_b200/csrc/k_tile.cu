@@ -118,13 +118,14 @@ __device__ __forceinline__ bool staged_may_cover(const float *s, uint32_t flags,
 }
 
 constexpr int TWIN = CAND_CAP; // phase D: slot values per ordering window
+constexpr int MAT_CACHE = 128; // materials kept in shared memory by k_tile (8 KB)
 // debug taps (FrameDev::tile_cycles, 4 x n_coarse words): SM cycles since the item started at the end of each phase
 enum : int { TAP_TOTAL = 0, TAP_A = 1, TAP_C = 2, TAP_D = 3 };
 
 // One work item (k_front, device_types.h): a tile or one pixel window of a dense tile.
 __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUniforms &U, const SceneDev &S, const FrameDev &W,
                                           uint8_t *__restrict__ color, float *__restrict__ depth, const float *u8tab,
-                                          const bool usable) {
+                                          const MaterialDev *mats, const bool usable) {
     __shared__ __align__(16) unsigned long long keys[TILE_PIXELS]; // (depth key, slot), later (depth bits, draw id)
     __shared__ __align__(16) uint32_t colour[TILE_PIXELS];         // r | g << 8 | b << 16 | pad << 24
     __shared__ float staged[CHUNK][STAGE_STRIDE];
@@ -247,6 +248,25 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
                         const float da = s[S_DA], db = s[S_DB], dc = s[S_DC];
                         const float rf0 = s[S_RF], rf1 = s[S_RF + 1], rf2 = s[S_RF + 2];
                         const float g0 = FMUL(da, rf0), g1 = FMUL(db, rf1), g2 = FMUL(dc, rf2);
+                        if (flags & TRI_EARLYZ) {
+                            // Early depth reject for the whole block.  Every edge value is monotone in x and in y (each
+                            // rounding is), so its minimum over the block sits at a corner; the approximate depth
+                            // fma(e2, g2, fma(e1, g1, e0 * g0)) is monotone in each e (g >= 0 under TRI_EARLYZ), so L below
+                            // bounds it from below for every pixel of the block.  If L * EARLYZ_SCALE exceeds the block's
+                            // largest stored depth, the per-pixel test below rejects every pixel: same result, 8 x 3 edge
+                            // evaluations not done (overdrawn scenes: most triangles of a tile are hidden).
+                            float em[3];
+#pragma unroll
+                            for (int e = 0; e < 3; e++) {
+                                const float cx = s[S_ECX + e], cy = s[S_ECY + e];
+                                const float xm = cx >= 0.0f ? lo_x : hi_x, ym = cy >= 0.0f ? lo_y : hi_y;
+                                em[e] = FSUB(FADD(FADD(FMUL(cx, xm), FMUL(cy, ym)), s[S_EK1 + e]), s[S_EK2 + e]);
+                            }
+                            float zmax = zb[0];
+#pragma unroll
+                            for (int p = 1; p < PX; p++) zmax = fmaxf(zmax, zb[p]);
+                            if (fmaf(em[2], g2, fmaf(em[1], g1, em[0] * g0)) * EARLYZ_SCALE > zmax) continue;
+                        }
                         // edge values of the block's pixels (f > 0 after sign normalisation:
                         // alpha >= 0 <=> e >= 0, alpha > 0 <=> e > 0), coverage and early depth reject, branch-free
                         float e0[PX], e1[PX], e2[PX];
@@ -328,6 +348,8 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
     // ---- phase C: deferred shading, fused clear ----------------------------------------------------
     // The records of all the lane's winners are requested first (prefetch into L1: no registers held), so
     // that the pixel loop below pays the L2 round trip once and not once per pixel.
+    // (Measured alternatives that did not pay: two pixels per lane as independent streams; per-warp staging of the
+    // distinct winners' records in shared memory — the phase is bound by instruction issue, ~250 per 32 pixels.)
 #pragma unroll 1
     for (int q = tid; q < n_win; q += TILE_THREADS) {
         const int x = wx0 + (q & (ww - 1)), y = wy0 + (q >> ww_shift);
@@ -348,8 +370,7 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
         uint32_t id = NO_SLOT;
         if (slot != NO_SLOT) {
             float op;
-            c = shade_pixel_prep(S.materials, S.texels, u8tab, prep + slot, W.srec + slot, (float)x, (float)y, &d, &op, &id) |
-                (255u << 24);
+            c = shade_pixel_prep<true>(mats, S.texels, u8tab, prep + slot, W.srec + slot, (float)x, (float)y, &d, &op, &id) | (255u << 24);
         }
         colour[p] = c;
         keys[p] = ((unsigned long long)__float_as_uint(d) << 32) | id; // own pixel: no sync needed
@@ -445,7 +466,7 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
                         if (!(d < __uint_as_float((uint32_t)(key >> 32)))) continue; // canvas.rs:923, depth write is off
                         const RasterRec r = load_raster(W.t_rrec + tslot);
                         float d2, op;
-                        const uint32_t rgb = shade_pixel(S.materials, S.texels, u8tab, r, W.t_srec + tslot, x, y, &d2, &op);
+                        const uint32_t rgb = shade_pixel<true>(mats, S.texels, u8tab, r, W.t_srec + tslot, x, y, &d2, &op);
                         // canvas.rs:916-921: opacity < 1 blends with the stored colour, else replaces it
                         colour[p] = op < 1.0f ? blend_rgb(colour[p], rgb, op) : (rgb | (255u << 24));
                     }
@@ -533,6 +554,15 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(cons
     __shared__ uint32_t s_item, s_index, s_bucket_end[COST_BUCKETS];
     __shared__ float u8tab[256]; // (u8 as f32) / 255.0, filled once per CTA (visible after the loop's first barrier)
     fill_u8_table(u8tab, threadIdx.x, TILE_THREADS);
+    // the material table on chip when it fits (64 B each): one dependent global load less per shaded pixel
+    __shared__ __align__(16) MaterialDev s_mats[MAT_CACHE];
+    const bool mats_cached = S.n_materials <= (uint32_t)MAT_CACHE;
+    if (mats_cached) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(S.materials);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_mats);
+        for (uint32_t i = threadIdx.x; i < S.n_materials * 4u; i += TILE_THREADS) dst[i] = __ldg(src + i);
+    }
+    const MaterialDev *mats = mats_cached ? s_mats : S.materials;
     const CtaTrace trace_(W, 3u);
     const bool usable = W.counters[CNT_OVERFLOW] == 0; // a work buffer overflowed: lists are unusable, the host re-renders
     // The work list is bucketed by cost (heaviest bucket first): bucket b's items are tile_order[b * bucket_cap ..
@@ -560,6 +590,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(cons
     const uint32_t n_empty = W.counters[CNT_EMPTY];
     const uint32_t per_item = n_items ? (n_empty + n_items - 1u) / n_items : 0u;
     const int W_ = (int)U.canvas_w, H_ = (int)U.canvas_h;
+    // The empty tiles are dealt out evenly over the raster items: item k's CTA writes tiles [k * per_item, (k+1) * per_item)
+    // — before the item (FrameUniforms::clear_first: the stores drain to HBM under the item's latency-bound work) or after it.
+    auto clear_share = [&](uint32_t k) {
+        for (uint32_t e = k * per_item, e_end = min(n_empty, e + per_item); e < e_end; e++)
+            clear_tile_cta(__ldg(&W.empty_tiles[e]), W_, H_, U.depth_max, color, depth, threadIdx.x);
+    };
     auto fetch_item = [&](uint32_t i) -> uint32_t { // thread 0 only
         if (i >= n_items) return ITEM_NONE;
         int b = 0;
@@ -585,9 +621,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(cons
         __syncthreads();
         const uint32_t cur = s_item, cur_index = s_index;
         if (cur == ITEM_NONE) break;
-        tile_item(cur, U, S, W, color, depth, u8tab, usable);
-        for (uint32_t e = cur_index * per_item, e_end = min(n_empty, e + per_item); e < e_end; e++)
-            clear_tile_cta(__ldg(&W.empty_tiles[e]), W_, H_, U.depth_max, color, depth, threadIdx.x);
+        if (U.clear_first) clear_share(cur_index);
+        tile_item(cur, U, S, W, color, depth, u8tab, mats, usable);
+        if (!U.clear_first) clear_share(cur_index);
         __syncthreads(); // shared memory (and s_item) are reused by the next item
         item = next_item;
         index = ahead;
@@ -619,7 +655,8 @@ uint32_t tile_grid_items(const FrameUniforms &U); // k_front.cu
 thread_local unsigned g_tile_ctas = 148u * 3u;    // scene.cpp: DRAW_B200_TILE_CTAS (persistent CTAs of k_tile)
 void launch_tile(const FrameUniforms &U, const FrameUniforms *dU, const SceneDev &S, const FrameDev &W, cudaStream_t stream) {
     const uint32_t slots = tile_grid_items(U); // upper bound of the work items
-    if (slots) k_tile<<<min(slots, g_tile_ctas), TILE_THREADS, 0, stream>>>(dU, S, W);
+    if (!slots) return;
+    k_tile<<<min(slots, g_tile_ctas), TILE_THREADS, 0, stream>>>(dU, S, W);
 }
 
 cudaError_t launch_clear(uint8_t *color, float *depth, size_t n_pixels, float depth_max, cudaStream_t stream,

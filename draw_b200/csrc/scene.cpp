@@ -269,6 +269,7 @@ struct Config {
     // grids; 0 = by scene size (set_launch_grids): with several frames in flight a kernel costs the pipeline its CTAs' residency
     int front_cps = std::max(0, env_int("DRAW_B200_FRONT_CPS", 0)); // k_front CTAs per SM
     int raster_ctas = std::max(0, env_int("DRAW_B200_RASTER_CTAS", 0));
+    int clear_first = env_int("DRAW_B200_CLEAR_FIRST", 0); // k_tile: empty-tile stores before (1) or after (0) a CTA's raster item
     int rec_cap = std::max(0, env_int("DRAW_B200_REC_CAP", 0));   // initial record / reference capacities (tests force overflows)
     int refs_cap = std::max(0, env_int("DRAW_B200_REFS_CAP", 0));
 };
@@ -551,9 +552,10 @@ int ensure_host_mirror(draw_canvas *c, size_t bytes) {
     return DRAW_OK;
 }
 
-// Grids of the frame's kernels, by scene size (a kernel costs the pipeline its CTAs' residency).  k_front: two CTAs of
-// 128 threads per SM for small scenes — they then fit beside three k_tile CTAs of another frame — and as many as fit
-// (eight) for large ones, whose phases need the latency hiding.
+// Grids of the frame's kernels, by scene size (a kernel costs the pipeline its CTAs' residency).  k_front: one CTA of
+// 128 threads per SM for small scenes — it fits beside three k_tile CTAs of another frame, and with several frames in
+// flight that is worth more than the few microseconds a second CTA per SM saves a lone frame (measured: C3 26.3 k
+// frames/s against 23.3 k) — and as many as fit (eight) for large ones, whose phases need the latency hiding.
 void set_launch_grids(const draw_scene *s) {
     static const int front_cap = front_max_ctas_per_sm();
     static const int n_sm = [] {
@@ -563,7 +565,7 @@ void set_launch_grids(const draw_scene *s) {
         return n;
     }();
     const bool small_scene = s->dev.n_triangles <= 200000u;
-    const int cps = std::min(front_cap, g_cfg.front_cps ? g_cfg.front_cps : (small_scene ? 2 : 8)); // CTAs of 128 threads
+    const int cps = std::min(front_cap, g_cfg.front_cps ? g_cfg.front_cps : (small_scene ? 1 : 8)); // CTAs of 128 threads
     g_front_ctas = (unsigned)(n_sm * std::max(1, cps));
     g_raster_ctas = g_cfg.raster_ctas ? (unsigned)g_cfg.raster_ctas : (small_scene ? 592u : 1184u);
     g_tile_ctas = (unsigned)g_cfg.tile_ctas;
@@ -599,6 +601,7 @@ void fill_uniforms(draw_scene *s, const draw_canvas *c, FrameUniforms &U) {
     U.row_step = c->row_step ? c->row_step : 1u;
     U.row_phase = c->row_phase % U.row_step;
     U.bar_base = 0; // set per work set by enqueue_frame
+    U.clear_first = (uint32_t)g_cfg.clear_first;
     U.status_host = c->h_status + (size_t)c->next_status_slot * N_STATUS_WORDS; // pinned, mapped: valid on the device (unified addressing)
     U.color = c->color();
     U.depth = c->depth();

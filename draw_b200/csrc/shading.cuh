@@ -31,16 +31,17 @@ __device__ __forceinline__ uint32_t fetch_texel(const uint8_t *__restrict__ texe
 // and Phong.  Returns r | g << 8 | b << 16.
 // MATERIALS_CACHED: `materials` is a copy of the table in shared memory (plain loads) instead of the
 // global table (read-only path).
-template <bool MATERIALS_CACHED = false>
+// RECORDS_ON_CHIP: the records are copies in shared memory (plain loads) instead of global memory (read-only path).
+template <bool MATERIALS_CACHED = false, bool RECORDS_ON_CHIP = false>
 __device__ __forceinline__ uint32_t shade_bary(const MaterialDev *materials, const uint8_t *__restrict__ texels,
-                                               const float *u8tab, const ShadeRec *__restrict__ sp, float alpha, float beta,
+                                               const float *u8tab, const ShadeRec *sp, float alpha, float beta,
                                                float gama, float *opacity_out) {
     // ShadeRec as 9 x uint4: n[3][3] l[3][3] h[3][3] uv[3][2] material pad pad
     const uint4 *q = reinterpret_cast<const uint4 *>(sp);
     float w[36];
 #pragma unroll
     for (int i = 0; i < 9; i++) {
-        const uint4 t = __ldg(q + i);
+        const uint4 t = RECORDS_ON_CHIP ? q[i] : __ldg(q + i);
         w[4 * i] = __uint_as_float(t.x); w[4 * i + 1] = __uint_as_float(t.y);
         w[4 * i + 2] = __uint_as_float(t.z); w[4 * i + 3] = __uint_as_float(t.w);
     }
@@ -100,13 +101,17 @@ __device__ __forceinline__ uint32_t shade_pixel(const MaterialDev *materials, co
 // The same from the prepared record (opaque triangles): its edge functions are the raster record's, sign-
 // normalised together with f (the quotients are bit-identical, device_math.cuh), and under TRI_FASTDIV the
 // division is exact_div.  ~55 instructions fewer per pixel than rebuilding the edges.  *id_out = draw id.
-template <bool MATERIALS_CACHED = false>
+template <bool MATERIALS_CACHED = false, bool RECORDS_ON_CHIP = false>
 __device__ __forceinline__ uint32_t shade_pixel_prep(const MaterialDev *materials, const uint8_t *__restrict__ texels,
-                                                     const float *u8tab, const PrepRec *__restrict__ pp,
-                                                     const ShadeRec *__restrict__ sp, float x, float y, float *depth_out,
-                                                     float *opacity_out, uint32_t *id_out) {
+                                                     const float *u8tab, const PrepRec *pp, const ShadeRec *sp, float x, float y,
+                                                     float *depth_out, float *opacity_out, uint32_t *id_out) {
     const uint4 *q = reinterpret_cast<const uint4 *>(pp);
-    const uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4), q6 = __ldg(q + 6);
+    uint4 q0, q1, q2, q3, q4, q6;
+    if (RECORDS_ON_CHIP) {
+        q0 = q[0]; q1 = q[1]; q2 = q[2]; q3 = q[3]; q4 = q[4]; q6 = q[6];
+    } else {
+        q0 = __ldg(q); q1 = __ldg(q + 1); q2 = __ldg(q + 2); q3 = __ldg(q + 3); q4 = __ldg(q + 4); q6 = __ldg(q + 6);
+    }
     const float ecx[3] = {__uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z)};
     const float ecy[3] = {__uint_as_float(q0.w), __uint_as_float(q1.x), __uint_as_float(q1.y)};
     const float ek1[3] = {__uint_as_float(q1.z), __uint_as_float(q1.w), __uint_as_float(q2.x)};
@@ -121,7 +126,7 @@ __device__ __forceinline__ uint32_t shade_pixel_prep(const MaterialDev *material
     }
     *depth_out = FADD(FADD(FMUL(bary[0], __uint_as_float(q4.z)), FMUL(bary[1], __uint_as_float(q4.w))), FMUL(bary[2], __uint_as_float(q6.x)));
     *id_out = q6.z;
-    return shade_bary<MATERIALS_CACHED>(materials, texels, u8tab, sp, bary[0], bary[1], bary[2], opacity_out);
+    return shade_bary<MATERIALS_CACHED, RECORDS_ON_CHIP>(materials, texels, u8tab, sp, bary[0], bary[1], bary[2], opacity_out);
 }
 
 // Pixel * f32 + Pixel * f32 (canvas.rs:136-169, :916-921): per channel truncate, u8 wrapping add, pad 0.
