@@ -385,9 +385,20 @@ def run_ours(args, cfg):
     frames_total = frames_rank * world
     fps = frames_total / (ms_total * 1e-3)
 
-    if args.quick:  # A/B runs: the timed region only
+    if args.quick:  # A/B runs: the timed region and the lone-frame latency only
+        lone = []
+        for k in range(24):
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            frame(k * 5, ring[k % n_ring])
+            ring[k % n_ring].stream_wait(stream.cuda_stream)
+            b.record(stream)
+            torch.cuda.synchronize()
+            lone.append(a.elapsed_time(b))
         if rank == 0:
             print(json.dumps({"quick": True, "config": args.config, "value": fps, "us_per_frame": 1e3 * ms_total / frames_rank,
+                              "lone_frame_us_median": 1e3 * float(np.median(lone)), "lone_frame_us_max": 1e3 * float(np.max(lone)),
                               "gpu_launches": launches, "clocks": clocks}), flush=True)
         if dist is not None:
             dist.barrier()

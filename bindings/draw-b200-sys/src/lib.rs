@@ -174,6 +174,7 @@ extern "C" {
     pub fn draw_canvas_stream_wait(canvas: *mut draw_canvas, cuda_stream: *mut c_void) -> c_int;
     pub fn draw_canvas_set_stripe(canvas: *mut draw_canvas, y0: usize, y1: usize) -> c_int;
     pub fn draw_canvas_set_tile_rows(canvas: *mut draw_canvas, phase: u32, step: u32) -> c_int;
+    pub fn draw_canvas_set_empty_tile_color(canvas: *mut draw_canvas, enabled: c_int) -> c_int;
     pub fn draw_tile_size() -> c_int;
     pub fn draw_canvas_ipc_export(canvas: *mut draw_canvas, handle: *mut u8) -> c_int;
     pub fn draw_ipc_open(handle: *const u8, out_dev_ptr: *mut *mut c_void) -> c_int;

@@ -102,6 +102,7 @@ SIGNATURES = {
     "draw_canvas_stream_wait": (C.c_int, [C.c_void_p, C.c_void_p]),
     "draw_canvas_set_stripe": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t]),
     "draw_canvas_set_tile_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "draw_canvas_set_empty_tile_color": (C.c_int, [C.c_void_p, C.c_int]),
     "draw_device_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "draw_device_free": (C.c_int, [C.c_void_p]),
     "draw_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -162,6 +162,10 @@ class Canvas:
     def set_stripe(self, y0, y1):
         N.check(N.lib().draw_canvas_set_stripe(self._h, y0, y1))
 
+    def set_empty_tile_color(self, enabled=True):
+        """False: renders leave the colour of tiles without geometry untouched (the buffer was cleared by its owner)."""
+        N.check(N.lib().draw_canvas_set_empty_tile_color(self._h, 1 if enabled else 0))
+
     def set_tile_rows(self, phase, step):
         """Sort-first, interleaved: render only the tile rows ty with ty % step == phase."""
         N.check(N.lib().draw_canvas_set_tile_rows(self._h, int(phase), int(step)))

@@ -89,6 +89,7 @@ struct FrameUniforms {
     uint32_t n_coarse;                 // tiles_x * tiles_y
     uint32_t split_min_cost, split_div, split_max; // k_front's tile splitting policy (defaults: TILE_SPLIT_*)
     uint32_t bar_base;                 // value of the work set's grid-barrier counter when k_front starts (host-tracked)
+    uint32_t empty_tile_color;         // 0: tiles nothing is binned to keep their colour bytes (the caller has cleared the buffer: draw_canvas_set_empty_tile_color)
     uint32_t clear_first;              // k_tile: a CTA writes its share of the empty tiles before its raster item (else after it)
     uint32_t *status_host;             // pinned host memory of the canvas (device-mapped): k_tile copies counters[0..31] there
     uint8_t *color;                    // the canvas: BGRA8, row 0 = top (canvas.rs:955-956)
@@ -194,7 +195,7 @@ struct FrameDev {
     uint2 *l_pairs, *t_pairs;   // (tile, slot) pairs appended by k_front, scattered into the tiles' lists by k_raster's prologue [refs_cap]
     uint32_t *list_refs;        // large lists: record slots [refs_cap]
     uint32_t *t_refs;           // transparent lists: ordered slots 4*ordinal + k, unordered inside a tile's list [refs_cap]
-    uint4 *huge_jobs;           // records covering more than k_front's HUGE_TILES tiles: (bbx, bby, slot | transparent << 31, first pair)
+    uint4 *huge_jobs;           // records covering more than k_front's HUGE_TILES tiles: (bbx, bby, slot | transparent << 31, first tile row in the frame-wide row space)
     uint32_t huge_cap;
     uint2 *m_refs, *s_refs;     // medium / small references of the whole frame: (record slot, tile x | y << 10 | part bits) [refs_cap each]
     unsigned long long *key_pages; // page of tile t = TILE_W * TILE_H keys (depth key << 32 | slot) at t * TILE_W * TILE_H, all ones =
@@ -215,7 +216,7 @@ struct FrameDev {
 enum : int {
     CNT_RECORDS = 0, CNT_REFS_NEEDED = 1, CNT_OVERFLOW = 2, CNT_TICKET = 3, CNT_NONEMPTY = 4, CNT_L_PAIRS = 5, CNT_T_PAIRS = 6,
     CNT_L_CURSOR = 7, CNT_T_CURSOR = 8, CNT_MEDIUM = 9, CNT_SMALL = 10, CNT_EMPTY = 13, CNT_ITEMS = 15,
-    CNT_HUGE = 30,      // 64-bit (8-byte aligned): huge records queued << 32 | their (record, tile) pairs
+    CNT_HUGE = 30,      // 64-bit (8-byte aligned): huge records queued << 32 | their tile rows
     CNT_PHASE_NS = 16,  // 6 words: global-timer stamps of k_front's phases (block 0), low 32 bits; + 8: durations of the first block's sub-phases
     CNT_BUCKETS = 32,   // COST_BUCKETS words
     CNT_ITEM_CURSOR = 96, // k_tile's item cursor, in a 128-byte line of its own

@@ -649,54 +649,92 @@ __device__ __forceinline__ void bin_block(const FrameUniforms &U, const FrameDev
     bin_pass<true>(U, W, sh, 0u, n_pairs, pos, first, true);
 }
 
-// The frame's huge records (FrameDev::huge_jobs, appended by the triangle phase with the running sum of their tile
-// counts): their (record, tile) pairs form one flat space that is cut into equal shares, one per CTA.  A CTA walks
-// the records its share touches one after the other — every thread holds the record's edge functions in registers
-// and strides over the record's pairs inside the share — twice: count, one reservation per class, write.
-__device__ __forceinline__ void phase_huge(const FrameUniforms &U, const FrameDev &W, FrontShared &sh, uint32_t n_jobs, uint32_t n_pairs) {
-    const uint32_t tid = threadIdx.x;
-    const uint32_t per = (n_pairs + gridDim.x - 1) / gridDim.x;
-    const uint32_t p0 = min(n_pairs, blockIdx.x * per), p1 = min(n_pairs, p0 + per);
-    if (p0 >= p1) return; // block-uniform
-    // first record of the share: the largest j with pair base <= p0 (bases grow with j: one 64-bit counter handed out both)
-    if (tid == 0) sh.ticket = 0u;
-    __syncthreads();
-    {
-        uint32_t best = 0;
-        for (uint32_t j = tid; j < n_jobs; j += FRONT_THREADS)
-            if (__ldcg(&W.huge_jobs[j].w) <= p0) best = j;
-        atomicMax(&sh.ticket, best);
+// Does edge e of the triangle admit any pixel of tile (tx, row band [ly, hy])?  The same arithmetic as rect_may_cover
+// for the tile's rectangle clipped to the record's bbox.
+__device__ __forceinline__ bool edge_admits_tile(const BinTri &t, int e, int tx, int x0, int x1, float lyf, float hyf) {
+    const int lx = max(x0, tx * TILE_W), hx = min(x1, tx * TILE_W + TILE_W - 1);
+    const float xm = t.ecx[e] >= 0.0f ? (float)hx : (float)lx, ym = t.ecy[e] >= 0.0f ? hyf : lyf;
+    const float em = FSUB(FADD(FADD(FMUL(t.ecx[e], xm), FMUL(t.ecy[e], ym)), t.ek1[e]), t.ek2[e]);
+    return em > 0.0f || (em == 0.0f && (t.flags & (1u << e)));
+}
+
+// The tiles of one tile row that a record can cover: an interval [a, b] of tile columns (empty: a > b).  Exactly the
+// tiles rect_may_cover admits: per edge, the best-corner value is monotone in the tile column (the corner's x grows
+// with the column and every rounding step is monotone), so the admitted columns of an edge are a half-line whose end
+// a binary search finds with the very evaluation rect_may_cover would make; the three half-lines intersect in an
+// interval.  A triangle that fills the screen costs 3 x log2(columns) evaluations per row instead of one per tile.
+__device__ __forceinline__ void row_interval(const BinTri &t, const TileRange &tr, int ty, int &a, int &b) {
+    a = tr.tx0;
+    b = tr.tx0 + tr.cols - 1;
+    if (t.flags & TRI_SLOW) return; // rect_may_cover admits everything
+    const float lyf = (float)max(tr.y0, ty * TILE_H), hyf = (float)min(tr.y1, ty * TILE_H + TILE_H - 1);
+    // the whole row band first: most rows of a big bbox hold nothing of the triangle (one evaluation instead of three searches)
+    if (!rect_may_cover(t, (float)tr.x0, (float)tr.x1, lyf, hyf)) {
+        b = a - 1;
+        return;
     }
-    __syncthreads();
-    const uint32_t j_first = sh.ticket;
+#pragma unroll
+    for (int e = 0; e < 3; e++) { // unrolled: the edge arrays stay in registers
+        if (a > b) break;
+        if (t.ecx[e] >= 0.0f) { // admitted columns: [first admitted, b]
+            int lo = a, hi = b + 1;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (edge_admits_tile(t, e, mid, tr.x0, tr.x1, lyf, hyf)) hi = mid; else lo = mid + 1;
+            }
+            a = lo;
+        } else { // admitted columns: [a, last admitted]
+            int lo = a - 1, hi = b;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (edge_admits_tile(t, e, mid, tr.x0, tr.x1, lyf, hyf)) lo = mid; else hi = mid - 1;
+            }
+            b = lo;
+        }
+    }
+}
+
+// Class of a (record, tile) pair known to be admitted (classify_pair without the test).
+__device__ __forceinline__ PairClass class_of_admitted(const FrameUniforms &U, int x0, int x1, int y0, int y1, int tx, int ty, bool transparent) {
+    PairClass c;
+    c.tile = (uint32_t)ty * U.tiles_x + (uint32_t)tx;
+    const int lx = max(x0, tx * TILE_W), hx = min(x1, tx * TILE_W + TILE_W - 1);
+    const int ly = max(y0, ty * TILE_H), hy = min(y1, ty * TILE_H + TILE_H - 1);
+    const int area = (hx - lx + 1) * (hy - ly + 1);
+    c.cls = transparent ? 3u : (area <= SMALL_AREA ? 2u : (area <= MEDIUM_AREA ? 1u : 0u));
+    c.blocks = (uint32_t)((hx - lx) / 8 + 1) * (uint32_t)((hy - ly) / 4 + 1);
+    c.entries = c.cls == 1u ? min(4u, (c.blocks + 7u) / 8u) : 1u;
+    return c;
+}
+
+// The frame's huge records (FrameDev::huge_jobs, appended by the triangle phase).  The unit of work is a (record, tile
+// ROW): the records are dealt out to the warps of the whole grid, a warp holds its record's edge functions in
+// registers, a lane takes a row, finds the interval of admitted columns (row_interval) and walks only those — work
+// in proportion to the references made, not to the tiles of the bbox (a near-plane-clipped triangle whose bbox is
+// the whole screen typically covers a few per cent of it).  Twice: count, one reservation per CTA and class, write.
+__device__ __forceinline__ void phase_huge(const FrameUniforms &U, const FrameDev &W, FrontShared &sh, uint32_t n_jobs) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t gwarp = blockIdx.x * (FRONT_THREADS / 32) + (threadIdx.x >> 5), n_warps = gridDim.x * (FRONT_THREADS / 32);
     ListPos pos{0u, 0u, 0u, 0u};
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
 #pragma unroll 1
-        for (uint32_t j = j_first; j < n_jobs; j++) { // block-uniform
-            const uint4 q = __ldcg(&W.huge_jobs[j]); // the same address in every thread: one broadcast load
-            if (q.w >= p1) break;
+        for (uint32_t j = gwarp; j < n_jobs; j += n_warps) { // warp-uniform
+            const uint4 q = __ldcg(&W.huge_jobs[j]); // the same address in every lane: one broadcast load
             const bool transparent = (q.z >> 31) != 0;
             const uint32_t slot = q.z & 0x7FFFFFFFu;
             const TileRange tr = tile_range(U, q.x, q.y);
             const BinTri t = bin_tri_load((transparent ? W.t_prep : W.prep) + slot);
-            const uint32_t lo = max(p0, q.w) - q.w, hi = min(p1 - q.w, (uint32_t)tr.count());
-            // two pairs per step: the two evaluations are independent chains (the phase is bound by instruction latency)
 #pragma unroll 1
-            for (uint32_t i = lo + tid; i < hi; i += 2 * FRONT_THREADS) {
-                const uint32_t i2 = i + FRONT_THREADS;
-                const bool two = i2 < hi;
-                const int tx = tr.tx0 + (int)i % tr.cols, ty = tr.ty_first + ((int)i / tr.cols) * tr.row_step;
-                const int tx2 = tr.tx0 + (int)(two ? i2 : i) % tr.cols, ty2 = tr.ty_first + ((int)(two ? i2 : i) / tr.cols) * tr.row_step;
-                const PairClass c = classify_pair(U, t, tr.x0, tr.x1, tr.y0, tr.y1, tx, ty, transparent);
-                PairClass c2 = classify_pair(U, t, tr.x0, tr.x1, tr.y0, tr.y1, tx2, ty2, transparent);
-                if (!two) c2.cls = 4u;
-                if (pass == 0) {
-                    pos.count(c);
-                    pos.count(c2);
-                } else {
-                    emit_pair(W, c, slot, tx, ty, pos);
-                    emit_pair(W, c2, slot, tx2, ty2, pos);
+            for (int i = (int)lane; i < tr.n_rows; i += 32) {
+                const int ty = tr.ty_first + i * tr.row_step;
+                int a, b;
+                row_interval(t, tr, ty, a, b);
+#pragma unroll 1
+                for (int tx = a; tx <= b; tx++) {
+                    const PairClass c = class_of_admitted(U, tr.x0, tr.x1, tr.y0, tr.y1, tx, ty, transparent);
+                    if (pass == 0) pos.count(c);
+                    else emit_pair(W, c, slot, tx, ty, pos);
                 }
             }
         }
@@ -895,9 +933,10 @@ __device__ __forceinline__ void phase_setup(const FrameUniforms &U, const SceneD
                 const uint32_t slot_t = (slot + (uint32_t)k) | (transparent ? 0x80000000u : 0u);
                 const uint32_t nt = (uint32_t)tile_range(U, bbx[k], bby[k]).count();
                 if (nt > HUGE_TILES) {
-                    // diverted: position in the queue and first pair of the record from ONE 64-bit counter (jobs << 32 | pairs),
-                    // so that pair bases grow with the queue position
-                    const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long *>(W.counters + CNT_HUGE), (1ull << 32) | nt);
+                    // diverted: position in the queue and first tile row of the record from ONE 64-bit counter (jobs << 32 | rows),
+                    // so that row bases grow with the queue position
+                    const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long *>(W.counters + CNT_HUGE),
+                                                             (1ull << 32) | (uint32_t)tile_range(U, bbx[k], bby[k]).n_rows);
                     const uint32_t pos = (uint32_t)(old >> 32);
                     if (pos < W.huge_cap) W.huge_jobs[pos] = make_uint4(bbx[k], bby[k], slot_t, (uint32_t)old);
                     else atomicOr(&W.counters[CNT_OVERFLOW], OVERFLOW_HUGE);
@@ -1038,9 +1077,9 @@ __global__ void __launch_bounds__(FRONT_THREADS, 8) k_front(const FrameUniforms 
         // huge records, if the frame has any: their pairs are binned by the whole grid, then a third barrier.  Without them
         // the CTAs only arrive at that barrier (the counter's value stays what the host expects) and go on.
         const unsigned long long hq = __ldcg(reinterpret_cast<const unsigned long long *>(W.counters + CNT_HUGE));
-        const uint32_t n_huge = min((uint32_t)(hq >> 32), W.huge_cap), n_huge_pairs = (uint32_t)hq;
+        const uint32_t n_huge = min((uint32_t)(hq >> 32), W.huge_cap);
         if (n_huge) { // the same value in every CTA: final since the barrier above
-            phase_huge(U, W, sh, n_huge, n_huge_pairs);
+            phase_huge(U, W, sh, n_huge);
             if (threadIdx.x == 0) atomicMax(W.counters + CNT_PHASE_NS + 7, (uint32_t)global_timer_ns());
             grid_barrier(W.counters, U.bar_base + 3u * gridDim.x);
         } else {

@@ -180,7 +180,9 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
         // The tile's key page (k_raster's result): its loads are issued here, together with the stores that
         // leave it empty for the next frame, and consumed after the first chunk of large triangles has been
         // staged, so that the two L2 round trips overlap.  A lane's 4 pixels of a row are 32 contiguous bytes.
-        const bool have_page = paged && warp_in;
+        // (Issued for every tile, before it is known whether the page holds anything — an untouched page reads as empty
+        // keys: the round trip overlaps the one of the tile's list header above instead of following it.)
+        const bool have_page = warp_in;
         ulonglong2 pk01[BLK_H], pk23[BLK_H];
         if (have_page) {
             unsigned long long *pk = W.key_pages + (size_t)tile * TILE_PIXELS;
@@ -191,7 +193,7 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
                 pk23[j] = __ldcg(src + 1);
             }
         }
-        bool page_pending = have_page;
+        bool page_pending = have_page && paged;
         auto merge_page = [&]() { // the page's fragments become the starting depth / winner of the lane's pixels
 #pragma unroll
             for (int j = 0; j < BLK_H; j++) {
@@ -516,7 +518,7 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
 // One empty tile written by the whole CTA: 16 bytes of colour and 16 of depth per thread, fire-and-forget
 // streaming stores that drain while the CTA works on its raster item (canvas.rs:425-433).
 __device__ __forceinline__ void clear_tile_cta(const uint32_t et, const int W_, const int H_, const float depth_max,
-                                               uint8_t *__restrict__ color, float *__restrict__ depth, const int tid) {
+                                               uint8_t *__restrict__ color, float *__restrict__ depth, const int tid, const bool write_color) {
     const int ex0 = (int)(et & (MAX_TILES_X - 1)) * TILE_W, ey0 = (int)(et >> 10) * TILE_H;
     const uint32_t clear_px = 255u | (186u << 8) | (155u << 16) | (255u << 24); // memory order b g r pad
     if ((W_ & 3) == 0) {
@@ -525,8 +527,9 @@ __device__ __forceinline__ void clear_tile_cta(const uint32_t et, const int W_, 
         for (int q = tid; q < QPR * TILE_H; q += TILE_THREADS) {
             const int x = ex0 + (q % QPR) * 4, y = ey0 + q / QPR;
             if (x < W_ && y < H_) {
-                __stcs(reinterpret_cast<uint4 *>(color + ((size_t)(H_ - 1 - y) * W_ + x) * 4),
-                       make_uint4(clear_px, clear_px, clear_px, clear_px));
+                if (write_color)
+                    __stcs(reinterpret_cast<uint4 *>(color + ((size_t)(H_ - 1 - y) * W_ + x) * 4),
+                           make_uint4(clear_px, clear_px, clear_px, clear_px));
                 __stcs(reinterpret_cast<float4 *>(depth + (size_t)y * W_ + x), make_float4(depth_max, depth_max, depth_max, depth_max));
             }
         }
@@ -534,7 +537,7 @@ __device__ __forceinline__ void clear_tile_cta(const uint32_t et, const int W_, 
         for (int p = tid; p < TILE_PIXELS; p += TILE_THREADS) {
             const int x = ex0 + (p & (TILE_W - 1)), y = ey0 + p / TILE_W;
             if (x >= W_ || y >= H_) continue;
-            __stcs(reinterpret_cast<uint32_t *>(color) + (size_t)(H_ - 1 - y) * W_ + x, clear_px);
+            if (write_color) __stcs(reinterpret_cast<uint32_t *>(color) + (size_t)(H_ - 1 - y) * W_ + x, clear_px);
             __stcs(depth + (size_t)y * W_ + x, depth_max);
         }
     }
@@ -594,7 +597,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(cons
     // — before the item (FrameUniforms::clear_first: the stores drain to HBM under the item's latency-bound work) or after it.
     auto clear_share = [&](uint32_t k) {
         for (uint32_t e = k * per_item, e_end = min(n_empty, e + per_item); e < e_end; e++)
-            clear_tile_cta(__ldg(&W.empty_tiles[e]), W_, H_, U.depth_max, color, depth, threadIdx.x);
+            clear_tile_cta(__ldg(&W.empty_tiles[e]), W_, H_, U.depth_max, color, depth, threadIdx.x, U.empty_tile_color != 0u);
     };
     auto fetch_item = [&](uint32_t i) -> uint32_t { // thread 0 only
         if (i >= n_items) return ITEM_NONE;
@@ -631,7 +634,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(cons
     }
     if (n_items == 0u) // nothing to rasterise in this launch's rows: the CTAs share the empty tiles
         for (uint32_t e = blockIdx.x; e < n_empty; e += gridDim.x)
-            clear_tile_cta(__ldg(&W.empty_tiles[e]), W_, H_, U.depth_max, color, depth, threadIdx.x);
+            clear_tile_cta(__ldg(&W.empty_tiles[e]), W_, H_, U.depth_max, color, depth, threadIdx.x, U.empty_tile_color != 0u);
 }
 
 // Canvas::clear (canvas.rs:425-433) as a standalone operation (draw_canvas_clear).

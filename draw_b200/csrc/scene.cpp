@@ -222,6 +222,7 @@ struct draw_canvas {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     size_t stripe_y0 = 0, stripe_y1 = 0; // rows; y1 == 0 means whole canvas
     uint32_t row_step = 1, row_phase = 0; // tile rows ty % row_step == row_phase only (draw_canvas_set_tile_rows)
+    bool empty_tile_color = true;         // draw_canvas_set_empty_tile_color
     // Pinned, device-mapped status blocks (N_STATUS_WORDS words each): k_tile posts a frame's counters into the block
     // the frame was given, so several frames may be enqueued on a canvas before the host looks at any of them.
     static constexpr int STATUS_SLOTS = 8;
@@ -602,6 +603,7 @@ void fill_uniforms(draw_scene *s, const draw_canvas *c, FrameUniforms &U) {
     U.row_phase = c->row_phase % U.row_step;
     U.bar_base = 0; // set per work set by enqueue_frame
     U.clear_first = (uint32_t)g_cfg.clear_first;
+    U.empty_tile_color = c->empty_tile_color ? 1u : 0u;
     U.status_host = c->h_status + (size_t)c->next_status_slot * N_STATUS_WORDS; // pinned, mapped: valid on the device (unified addressing)
     U.color = c->color();
     U.depth = c->depth();
@@ -1572,6 +1574,12 @@ int draw_canvas_set_stripe(draw_canvas *canvas, size_t y0, size_t y1) {
         canvas->stripe_y0 = y0;
         canvas->stripe_y1 = y1;
     }
+    return DRAW_OK;
+}
+
+int draw_canvas_set_empty_tile_color(draw_canvas *canvas, int enabled) {
+    if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas is NULL");
+    canvas->empty_tile_color = enabled != 0;
     return DRAW_OK;
 }
 

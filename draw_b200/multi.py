@@ -11,10 +11,11 @@ partitions of the render path exist here:
                    the per-vertex / per-triangle stages for the whole scene (k_front: replicated, bit-identical),
                    bins and rasterises only its rows.  Rows are disjoint, so compositing needs no depth compare.
                    Two ways to land the rows in rank 0's framebuffer:
-                     "nccl"  each rank renders into its own canvas, then one grouped NCCL send/recv of its row
-                             blocks to rank 0 (torch.distributed batch_isend_irecv), ordered on the canvas' stream:
-                             the canvas renders on torch's current stream, so the gather follows k_tile and the
-                             next frame follows the gather without the host waiting for either;
+                     "nccl"  each rank renders into its own canvas, then ONE NCCL collective lands the rows on rank 0
+                             (stripes: grouped send/recv of the contiguous stripes; interleaved rows: pack, gather,
+                             unpack — RowGather), ordered on the canvas' stream: the canvas renders on a torch
+                             stream, so the gather follows k_tile and the next frame follows the gather without the
+                             host waiting for either;
                      "p2p"   rank 0 exports its colour buffer through CUDA IPC; the other ranks' tile kernels
                              store their pixels straight into it over NVLink (peer stores from k_tile), so the
                              gather is fused into the raster kernel.  Completion is a device-side flag per rank
@@ -95,6 +96,40 @@ def gather_stripes(dist, frame, bounds, height, width, root=0):
     gather_blocks(dist, frame, lambda r: [bounds[r]] if bounds[r][1] > bounds[r][0] else [], height, width, root)
 
 
+class RowGather:
+    """Gather of many row blocks per rank (the interleaved partition: a rank owns every world-th tile row) as ONE
+    collective: every rank packs its rows into a contiguous buffer (one index_select), a single gather lands the
+    buffers on the root (NCCL: grouped send / recv over NVLink), and the root scatters the rows of each rank into its
+    frame (one index_copy_ per rank).  A send / recv per row block instead would cost the host tens of
+    microseconds per block.  Works with any backend (NCCL on GPU tensors, gloo on CPU); stream-ordered with NCCL."""
+
+    def __init__(self, dist, height, width, blocks_of_rank, device, root=0):
+        import torch
+        self.dist, self.root = dist, root
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.height, self.width = height, width
+        self.rows = []
+        for r in range(self.world):  # frame rows of rank r (the colour buffer is y-flipped), in block order
+            idx = [fr for (y0, y1) in blocks_of_rank(r) for fr in range(height - y1, height - y0)]
+            self.rows.append(torch.tensor(idx, dtype=torch.long, device=device))
+        self.max_rows = max(1, max(int(t.numel()) for t in self.rows))
+        self.send = torch.zeros((self.max_rows, width), dtype=torch.int32, device=device)
+        self.recv = torch.zeros((self.world, self.max_rows, width), dtype=torch.int32, device=device) if self.rank == root else None
+
+    def gather(self, frame):
+        """frame: flat uint8 tensor of H*W*4 bytes (same size on every rank); the root's frame receives every rank's rows."""
+        import torch
+        px = frame.view(torch.int32).view(self.height, self.width)  # one BGRA pixel = one 32-bit element
+        mine = self.rows[self.rank]
+        if self.rank != self.root and mine.numel():
+            torch.index_select(px, 0, mine, out=self.send[:mine.numel()])
+        self.dist.gather(self.send, [self.recv[r] for r in range(self.world)] if self.rank == self.root else None, dst=self.root)
+        if self.rank == self.root:
+            for r in range(self.world):
+                if r != self.root and self.rows[r].numel():
+                    px.index_copy_(0, self.rows[r], self.recv[r, :self.rows[r].numel()])
+
+
 class _DevicePtr:
     """Expose a raw device pointer to torch through __cuda_array_interface__."""
 
@@ -156,6 +191,7 @@ class SortFirst:
             else:
                 self.canvas.set_stripe(*self.mine[0])
         self.frame = canvas_color_tensor(self.canvas, device)
+        self._row_gather = RowGather(dist, height, width, self.blocks, device) if mode == "nccl" and layout == "interleaved" else None
         self.seq = 0
         self._peer = self._flags = self._own_flags = None
         if mode == "p2p":
@@ -175,6 +211,9 @@ class SortFirst:
                 self.canvas.bind_external(peer.value, own_depth)  # colour -> rank 0's framebuffer over NVLink
             else:
                 self._flags = self._own_flags
+            # rank 0 fills its framebuffer with the clear colour before every frame (a local 4 W H-byte fill); nobody then
+            # stores the pixels of tiles without geometry — most of a frame — over NVLink or at all
+            self.canvas.set_empty_tile_color(False)
             dist.barrier()
 
     def _export_canvas(self, lib, N):
@@ -216,7 +255,10 @@ class SortFirst:
             if self.mine:
                 self.scene.render(self.canvas)
             with torch.cuda.stream(self.stream):
-                gather_blocks(self.dist, self.frame, self.blocks, self.height, self.width)
+                if self._row_gather is not None:
+                    self._row_gather.gather(self.frame)  # pack, one collective, unpack
+                else:
+                    gather_blocks(self.dist, self.frame, self.blocks, self.height, self.width)  # one contiguous stripe per rank
             return
         lib = N.lib()
         if self.rank != 0:
@@ -229,6 +271,7 @@ class SortFirst:
         else:
             # whatever rank 0 has enqueued on the canvas' stream so far (its use of the previous frame) comes first:
             # starting the next frame is what tells the peers that the previous one has been consumed
+            self.canvas.clear()  # colour (and depth) of the whole canvas: the tiles nobody draws in keep it
             N.check(lib.draw_flag_signal(self._flag(FLAG_CONSUMED), self.seq - 1, self.canvas._h))
             if self.mine:
                 self.scene.render(self.canvas)
@@ -280,8 +323,19 @@ def bench_sort_first(scene, cfg, dist, frames=120, warmup=8):
     e1.record(stream)
     torch.cuda.synchronize()
     single_ms = e0.elapsed_time(e1) / frames
+    # ... and one frame at a time (the device idle before each): the latency of a lone frame on one GPU
+    lone = []
+    for k in range(min(frames, 60)):
+        set_cam(k)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        scene.render(full)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        lone.append(e0.elapsed_time(e1))
+    lone_ms = sum(lone) / len(lone)
     del full
-    out = {"workload": cfg["label"], "frames": frames, "single_gpu_ms_per_frame": single_ms,
+    out = {"workload": cfg["label"], "frames": frames, "single_gpu_ms_per_frame": single_ms, "single_gpu_lone_frame_ms": lone_ms,
            "gather_bytes_into_root": 4 * W * H * (world - 1) // world}
     for layout in ("interleaved", "stripes"):
         for mode in ("p2p", "nccl"):
@@ -325,11 +379,14 @@ def bench_sort_first(scene, cfg, dist, frames=120, warmup=8):
             be = torch.tensor([1 if bit_exact else 0], device=device, dtype=torch.int32)
             dist.broadcast(be, 0)
             out[key] = {"ms_per_frame": ms, "frames_per_s": 1e3 / ms, "mtri_per_s": cfg["triangles"] / ms / 1e3,
-                        "speedup_vs_single_gpu": single_ms / ms, "bit_exact": bool(int(be.item()))}
+                        "speedup_vs_single_gpu": single_ms / ms, "speedup_vs_lone_frame": lone_ms / ms,
+                        "bit_exact": bool(int(be.item()))}
             sf.close()
             del sf
     out["note"] = ("one frame at a time split by tile rows across the ranks; per-vertex / per-triangle stages replicated on "
                    "every rank; CUDA events on the canvas stream around all frames, max over ranks, no host synchronisation "
-                   "inside the loop; single_gpu_ms_per_frame = the same frames rendered whole on one GPU the same way; "
+                   "inside the loop; single_gpu_ms_per_frame = the same frames rendered whole on one GPU the same way (frames back to "
+                   "back: the front kernel of frame k+1 overlaps the tile kernel of frame k); single_gpu_lone_frame_ms = one frame "
+                   "at a time on an idle GPU (mean over the first frames of the path); "
                    "bit_exact = composed frame of three cameras of the path == single-GPU frame")
     return out

@@ -220,6 +220,11 @@ int draw_canvas_set_stripe(draw_canvas *canvas, size_t y0, size_t y1);
  * canvas y = 0) with ty % step == phase, inside the stripe.  Interleaving balances the ranks when the scene sits
  * mid-screen.  (0, 1) = every row.  Reset by draw_canvas_resize. */
 int draw_canvas_set_tile_rows(draw_canvas *canvas, uint32_t phase, uint32_t step);
+/* Fused sort-first gather: with enabled == 0 a render leaves the COLOUR of the tiles nothing is drawn in untouched
+ * (their depth is still reset) — the owner of the framebuffer has filled it with the clear colour (draw_canvas_clear)
+ * before the peers' kernels store into it, so only pixels of tiles that hold geometry cross NVLink.  Default: enabled
+ * (Canvas::clear semantics, canvas.rs:425-433: every pixel of the rendered rows is written). */
+int draw_canvas_set_empty_tile_color(draw_canvas *canvas, int enabled);
 int draw_tile_size(void);
 /* Peer access for the fused sort-first gather (one process per GPU): the owner exports its
  * canvas' own colour buffer as a 64-byte CUDA IPC handle; another process on the same node opens

@@ -46,6 +46,22 @@ def main():
                     assert int(img2[H - 1 - y, 0, 0]) == (y * 5 + r) & 255, (r, y)
                     assert (img2[H - 1 - y] == img2[H - 1 - y, 0, 0]).all()
 
+    # the packed form of the same gather (one collective: what the NCCL path of the interleaved layout uses)
+    frame3 = torch.zeros(H * W * 4, dtype=torch.uint8)
+    img3 = frame3.view(H, W, 4)
+    for y0, y1 in blocks(rank):
+        for y in range(y0, y1):
+            img3[H - 1 - y] = (y * 3 + rank) & 255
+    rg = multi.RowGather(dist, H, W, blocks, torch.device("cpu"))
+    rg.gather(frame3)
+    rg.gather(frame3)  # reusable
+    if rank == 0:
+        for r in range(world):
+            for a, b in blocks(r):
+                for y in range(a, b):
+                    assert int(img3[H - 1 - y, 0, 0]) == (y * 3 + r) & 255, (r, y)
+                    assert (img3[H - 1 - y] == img3[H - 1 - y, 0, 0]).all()
+
     # frame-parallel assignment covers every frame exactly once
     mine = multi.frames_of_rank(10, world, rank)
     gathered = [None] * world

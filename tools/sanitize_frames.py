@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Renders a few small frames through libdraw_b200.so and compares them with the oracle; run it under
+compute-sanitizer (tools/sanitize.sh).  Scenes: C1 (textured + transparent, 800x600), C3 at 1280x720 (thousands of small
+triangles: key pages, k_raster atomics), C4 frame 60 at 960x544 (near-plane clipping, records covering hundreds of
+tiles: k_front's huge-record phase, tile windows), each rendered twice on two canvases (frames in flight)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import draw_b200  # noqa: E402
+from conftest import GOLDEN, load_scene  # noqa: E402
+from parity_util import assert_frames_equal, render_oracle  # noqa: E402
+
+path = np.load(GOLDEN + "/c4_camera_path.npy")
+for name, (W, H), cam in (("c1_lemur_airplane", (800, 600), None), ("c3_trio", (1280, 720), None), ("c4_dungeon", (960, 544), path[60])):
+    objs = load_scene(name)
+    s = draw_b200.Scene(W, H)
+    for o in objs:
+        s.add_obj(o)
+    if cam is not None:
+        s.camera = draw_b200.Camera.new(cam[:3], cam[3:])
+    cs = []
+    for _ in range(2):
+        c = draw_b200.Canvas(W, H)
+        c.init_depth(100000.0)
+        cs.append(c)
+    for k in range(4):
+        s.render(cs[k % 2])
+    want = render_oracle(objs, W, H, cam=cam, frames=2)
+    for c in cs:
+        assert_frames_equal((c.as_bytes_slice(), c.depth()), want, name)
+    print(name, W, H, "ok", c.last_frame_stats()["setup_records"], "records", flush=True)
+print("sanitize frames ok")
