@@ -25,7 +25,7 @@ constexpr int TILE_W = DRAW_TILE_W, TILE_H = DRAW_TILE_H, REGION = 16;
 #define DRAW_MEDIUM_AREA 1024
 #endif
 #ifndef DRAW_SMALL_AREA
-#define DRAW_SMALL_AREA 8
+#define DRAW_SMALL_AREA 16
 #endif
 constexpr int SMALL_AREA = DRAW_SMALL_AREA, MEDIUM_AREA = DRAW_MEDIUM_AREA;
 constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;

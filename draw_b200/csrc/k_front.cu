@@ -232,9 +232,14 @@ __device__ __forceinline__ TileRange tile_range(const FrameUniforms &U, uint32_t
     t.cols = t.x1 / TILE_W - t.tx0 + 1;
     const int step = (int)U.row_step;
     const int lo = max(t.y0 / TILE_H, (int)U.tile_y_begin), hi = min(t.y1 / TILE_H, (int)U.tile_y_end - 1);
+    t.row_step = step;
+    if (step == 1) { // every row (no software division on the common path)
+        t.ty_first = lo;
+        t.n_rows = lo <= hi ? hi - lo + 1 : 0;
+        return t;
+    }
     const int first = lo + ((int)U.row_phase + step - lo % step) % step; // first row >= lo of this launch
     t.ty_first = first;
-    t.row_step = step;
     t.n_rows = first <= hi ? (hi - first) / step + 1 : 0;
     return t;
 }
@@ -925,6 +930,34 @@ __device__ __forceinline__ void phase_setup(const FrameUniforms &U, const SceneD
 
         // ---- binning: the block's records become jobs in shared memory, their (record, tile) pairs are
         // spread over the CTA's threads ----------------------------------------------------------------
+        // Fast path — every record of the block is an unclipped triangle inside ONE tile (micro-triangle scenes; most
+        // blocks of any scene with small triangles): a thread bins its own record from registers; no job table, no
+        // pair search.  One count, one reservation per CTA and class, one write.
+        const TileRange own = tile_range(U, bbx[0], bby[0]);
+        const bool simple = kept == 0u || (kept == 1u && single && own.count() == 1);
+        if (__syncthreads_and(simple)) {
+            PairClass c;
+            c.cls = 4u;
+            c.blocks = c.entries = c.tile = 0u;
+            if (kept) {
+                BinTri t;
+                const float *w = sh.tri[threadIdx.x];
+#pragma unroll
+                for (int k = 0; k < 3; k++) { t.ecx[k] = w[k]; t.ecy[k] = w[3 + k]; t.ek1[k] = w[6 + k]; t.ek2[k] = w[9 + k]; }
+                t.flags = __float_as_uint(w[12]);
+                c = classify_pair(U, t, own.x0, own.x1, own.y0, own.y1, own.tx0, own.ty_first, transparent);
+            }
+            ListPos pos{0u, 0u, 0u, 0u};
+            pos.count(c);
+            reserve_lists(W, sh, pos);
+            emit_pair(W, c, slot, own.tx0, own.ty_first, pos);
+            if (stamp) {
+                sub[4] = sub[5] = (uint32_t)global_timer_ns();
+#pragma unroll
+                for (int i = 0; i < 5; i++) W.counters[CNT_PHASE_NS + 8 + i] = sub[i + 1] - sub[i];
+            }
+            continue;
+        }
         uint32_t n_jobs;
         uint32_t jb = block_exclusive((uint32_t)__popc(kept), sh, &n_jobs);
 #pragma unroll

@@ -13,7 +13,7 @@
 //
 //   medium reference : one warp; lanes test up to 32 of the triangle's 8x4-pixel blocks exactly
 //                      (rect_may_cover), then the warp visits the surviving blocks, one pixel per lane
-//   small reference  : one lane (bbox of at most 8 pixels)
+//   small reference  : one lane (bbox of at most 16 pixels)
 #include "device_math.cuh"
 
 namespace drawb200 {
