@@ -712,38 +712,126 @@ __device__ __forceinline__ PairClass class_of_admitted(const FrameUniforms &U, i
     return c;
 }
 
-// The frame's huge records (FrameDev::huge_jobs, appended by the triangle phase).  The unit of work is a (record, tile
-// ROW): the records are dealt out to the warps of the whole grid, a warp holds its record's edge functions in
-// registers, a lane takes a row, finds the interval of admitted columns (row_interval) and walks only those — work
-// in proportion to the references made, not to the tiles of the bbox (a near-plane-clipped triangle whose bbox is
-// the whole screen typically covers a few per cent of it).  Twice: count, one reservation per CTA and class, write.
-__device__ __forceinline__ void phase_huge(const FrameUniforms &U, const FrameDev &W, FrontShared &sh, uint32_t n_jobs) {
-    const uint32_t lane = threadIdx.x & 31u;
+// Writes the list entries of one admitted pair at position `at` of its class' list (emit_pair with the position given).
+__device__ __forceinline__ void emit_at(const FrameDev &W, const PairClass &c, uint32_t slot, int tx, int ty, uint32_t at) {
+    ListPos pos{at, at, at, at};
+    emit_pair(W, c, slot, tx, ty, pos);
+}
+
+// The frame's huge records (FrameDev::huge_jobs, appended by the triangle phase).  The records are dealt out to the
+// warps of the whole grid; a warp holds its record's edge functions in registers.  Per chunk of up to 128 tile rows:
+// a lane takes a row (four row groups) and finds the interval of admitted columns (row_interval) — work in
+// proportion to the references made, not to the tiles of the bbox (a near-plane-clipped triangle whose bbox is the
+// whole screen typically covers a few per cent of it); the admitted (row, column) pairs of a group then form one
+// flat space that the 32 lanes stride over (a row that spans the screen is not one lane's job), once to count the
+// list entries per class, then — after ONE round of atomics per chunk — to write them at ballot / prefix positions.
+__device__ __forceinline__ void phase_huge(const FrameUniforms &U, const FrameDev &W, uint32_t n_jobs) {
+    const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
     const uint32_t gwarp = blockIdx.x * (FRONT_THREADS / 32) + (threadIdx.x >> 5), n_warps = gridDim.x * (FRONT_THREADS / 32);
-    ListPos pos{0u, 0u, 0u, 0u};
+    constexpr int GROUPS = 4;
+    if (gwarp >= n_jobs) return;
+    uint4 q = __ldcg(&W.huge_jobs[gwarp]); // the same address in every lane: one broadcast load
 #pragma unroll 1
-    for (int pass = 0; pass < 2; pass++) {
+    for (uint32_t j = gwarp; j < n_jobs; j += n_warps) { // warp-uniform
+        const bool transparent = (q.z >> 31) != 0;
+        const uint32_t slot = q.z & 0x7FFFFFFFu;
+        const TileRange tr = tile_range(U, q.x, q.y);
+        const BinTri t = bin_tri_load((transparent ? W.t_prep : W.prep) + slot);
+        if (j + n_warps < n_jobs) { // the next record's header, and its edge functions on their way to L2 / L1
+            q = __ldcg(&W.huge_jobs[j + n_warps]);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(((q.z >> 31) ? W.t_prep : W.prep) + (q.z & 0x7FFFFFFFu)));
+        }
 #pragma unroll 1
-        for (uint32_t j = gwarp; j < n_jobs; j += n_warps) { // warp-uniform
-            const uint4 q = __ldcg(&W.huge_jobs[j]); // the same address in every lane: one broadcast load
-            const bool transparent = (q.z >> 31) != 0;
-            const uint32_t slot = q.z & 0x7FFFFFFFu;
-            const TileRange tr = tile_range(U, q.x, q.y);
-            const BinTri t = bin_tri_load((transparent ? W.t_prep : W.prep) + slot);
+        for (int chunk = 0; chunk < tr.n_rows; chunk += 32 * GROUPS) {
+            int a[GROUPS];
+            uint32_t len[GROUPS], excl[GROUPS], tot[GROUPS];
+#pragma unroll
+            for (int g = 0; g < GROUPS; g++) {
+                const int i = chunk + g * 32 + (int)lane;
+                a[g] = 0;
+                len[g] = 0u;
+                if (i < tr.n_rows) {
+                    int b;
+                    row_interval(t, tr, tr.ty_first + i * tr.row_step, a[g], b);
+                    len[g] = b >= a[g] ? (uint32_t)(b - a[g] + 1) : 0u;
+                }
+                uint32_t incl = len[g];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t up = __shfl_up_sync(FULL, incl, d);
+                    if (lane >= (uint32_t)d) incl += up;
+                }
+                excl[g] = incl - len[g];
+                tot[g] = __shfl_sync(FULL, incl, 31);
+            }
+            // the h-th admitted pair of group g: row = the last lane whose exclusive prefix is <= h
+            auto locate = [&](int g, uint32_t h, int &tx, int &ty) {
+                int lo = 0, hi = 32;
+#pragma unroll
+                for (int step = 0; step < 5; step++) {
+                    const int mid = (lo + hi) >> 1;
+                    if (__shfl_sync(FULL, excl[g], mid) <= h) lo = mid; else hi = mid;
+                }
+                tx = __shfl_sync(FULL, a[g], lo) + (int)(h - __shfl_sync(FULL, excl[g], lo));
+                ty = tr.ty_first + (chunk + g * 32 + lo) * tr.row_step;
+            };
+            // count
+            ListPos cnt{0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int g = 0; g < GROUPS; g++) {
 #pragma unroll 1
-            for (int i = (int)lane; i < tr.n_rows; i += 32) {
-                const int ty = tr.ty_first + i * tr.row_step;
-                int a, b;
-                row_interval(t, tr, ty, a, b);
+                for (uint32_t h0 = 0; h0 < tot[g]; h0 += 32) { // warp-uniform
+                    const uint32_t h = h0 + lane;
+                    int tx, ty;
+                    locate(g, min(h, tot[g] - 1u), tx, ty);
+                    if (h < tot[g]) cnt.count(class_of_admitted(U, tr.x0, tr.x1, tr.y0, tr.y1, tx, ty, transparent));
+                }
+            }
+            uint32_t sum[4] = {cnt.l, cnt.m, cnt.s, cnt.t};
+#pragma unroll
+            for (int k = 0; k < 4; k++) sum[k] = __reduce_add_sync(FULL, sum[k]);
+            if ((sum[0] | sum[1] | sum[2] | sum[3]) == 0u) continue; // warp-uniform
+            uint32_t base = 0;
+            if (lane < 4) {
+                const uint32_t mine = lane == 0 ? sum[0] : (lane == 1 ? sum[1] : (lane == 2 ? sum[2] : sum[3]));
+                const int ctr = lane == 0 ? CNT_L_PAIRS : (lane == 1 ? CNT_MEDIUM : (lane == 2 ? CNT_SMALL : CNT_T_PAIRS));
+                if (mine) base = atomicAdd(W.counters + ctr, mine);
+            }
+            uint32_t run_l = __shfl_sync(FULL, base, 0), run_m = __shfl_sync(FULL, base, 1), run_s = __shfl_sync(FULL, base, 2),
+                     run_t = __shfl_sync(FULL, base, 3);
+            // write
+#pragma unroll
+            for (int g = 0; g < GROUPS; g++) {
 #pragma unroll 1
-                for (int tx = a; tx <= b; tx++) {
-                    const PairClass c = class_of_admitted(U, tr.x0, tr.x1, tr.y0, tr.y1, tx, ty, transparent);
-                    if (pass == 0) pos.count(c);
-                    else emit_pair(W, c, slot, tx, ty, pos);
+                for (uint32_t h0 = 0; h0 < tot[g]; h0 += 32) { // warp-uniform
+                    const uint32_t h = h0 + lane;
+                    const bool valid = h < tot[g];
+                    int tx, ty;
+                    locate(g, min(h, tot[g] - 1u), tx, ty);
+                    PairClass c = class_of_admitted(U, tr.x0, tr.x1, tr.y0, tr.y1, tx, ty, transparent);
+                    if (!valid) c.cls = 4u;
+                    const uint32_t ml = __ballot_sync(FULL, c.cls == 0u), ms = __ballot_sync(FULL, c.cls == 2u),
+                                   mt = __ballot_sync(FULL, c.cls == 3u);
+                    uint32_t e_incl = c.cls == 1u ? c.entries : 0u; // medium: 1-4 entries each
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t up = __shfl_up_sync(FULL, e_incl, d);
+                        if (lane >= (uint32_t)d) e_incl += up;
+                    }
+                    const uint32_t m_tot = __shfl_sync(FULL, e_incl, 31);
+                    uint32_t at = 0;
+                    if (c.cls == 0u) at = run_l + (uint32_t)__popc(ml & lt_mask);
+                    else if (c.cls == 1u) at = run_m + e_incl - c.entries;
+                    else if (c.cls == 2u) at = run_s + (uint32_t)__popc(ms & lt_mask);
+                    else if (c.cls == 3u) at = run_t + (uint32_t)__popc(mt & lt_mask);
+                    if (c.cls < 4u) emit_at(W, c, slot, tx, ty, at);
+                    run_l += (uint32_t)__popc(ml);
+                    run_m += m_tot;
+                    run_s += (uint32_t)__popc(ms);
+                    run_t += (uint32_t)__popc(mt);
                 }
             }
         }
-        if (pass == 0) reserve_lists(W, sh, pos);
     }
 }
 
@@ -1112,7 +1200,7 @@ __global__ void __launch_bounds__(FRONT_THREADS, 8) k_front(const FrameUniforms 
         const unsigned long long hq = __ldcg(reinterpret_cast<const unsigned long long *>(W.counters + CNT_HUGE));
         const uint32_t n_huge = min((uint32_t)(hq >> 32), W.huge_cap);
         if (n_huge) { // the same value in every CTA: final since the barrier above
-            phase_huge(U, W, sh, n_huge);
+            phase_huge(U, W, n_huge);
             if (threadIdx.x == 0) atomicMax(W.counters + CNT_PHASE_NS + 7, (uint32_t)global_timer_ns());
             grid_barrier(W.counters, U.bar_base + 3u * gridDim.x);
         } else {

@@ -336,6 +336,90 @@ class Canvas:
                     self.draw_pixel(x, y, rgb, tex["alpha"], depth)
 
 
+    def draw_triangle_2d(self, va, vb, vc, tex, clipping_rect=None):  # canvas.rs:435-575 (the GUI's path)
+        """va, vb, vc: (x, y, u, v, (r, g, b), alpha); tex: uint8 [h, w, 4]; clipping_rect: (x0, y0, x1, y1) or None."""
+        def mul_px(p, f):  # Mul<f32> for Pixel, canvas.rs:154-169: per channel (c as f32 * f) as u8, in r, g, b order
+            return tuple(sat_u8(F(F(c) * f)) for c in p)
+
+        def add_px(p, q):  # Add for Pixel, canvas.rs:136-152: u8 add (wraps in a release build)
+            return tuple((a + b) & 255 for a, b in zip(p, q))
+
+        with np.errstate(invalid="ignore", over="ignore", divide="ignore"):
+            ctr = lambda v: (F(np.floor(F(F(v[0]) + F(0.5)))), F(np.floor(F(F(v[1]) + F(0.5)))))  # pos_map_center :896-904
+            (ax, ay), (bx, by), (cx, cy) = ctr(va), ctr(vb), ctr(vc)
+
+            def edge(px, py, qx, qy):  # :461-480: (p.y - q.y) * x + (q.x - p.x) * y + p.x * q.y - q.x * p.y
+                c0, c1, k1, k2 = F(py - qy), F(qx - px), F(px * qy), F(qx * py)
+                return lambda x, y: F(F(F(F(c0 * x) + F(c1 * y)) + k1) - k2)
+
+            f_ab, f_bc, f_ca = edge(ax, ay, bx, by), edge(bx, by, cx, cy), edge(cx, cy, ax, ay)
+
+            def min3(*v):  # :482-491
+                r = F(np.inf)
+                for e in v:
+                    if e < r:
+                        r = e
+                return r
+
+            def max3(*v):  # :493-502
+                r = F(-np.inf)
+                for e in v:
+                    if e > r:
+                        r = e
+                return r
+
+            def from_coords(a0, b0, a1, b1):  # canvas.rs:315-330
+                return (min(a0, a1), min(b0, b1), max(a0, a1), max(b0, b1))
+
+            def clip(a, b):  # canvas.rs:332-350
+                xm, ym = max(a[0], b[0]), max(a[1], b[1])
+                xM, yM = min(a[2], b[2]), min(a[3], b[3])
+                if xm > xM:
+                    xm = xM = 0
+                if ym > yM:
+                    ym = yM = 0
+                return from_coords(xm, ym, xM, yM)
+
+            screen = from_coords(0, 0, self.width - 1, self.height - 1)
+            drawable = clip(from_coords(sat_usize(min3(ax, bx, cx)), sat_usize(min3(ay, by, cy)),
+                                        sat_usize(max3(ax, bx, cx)), sat_usize(max3(ay, by, cy))), screen)  # :504-514
+            x0, y0, x1, y1 = clip(from_coords(*clipping_rect) if clipping_rect is not None else screen, drawable)  # :516-517
+            f_alpha, f_beta, f_gama = f_bc(ax, ay), f_ca(bx, by), f_ab(cx, cy)
+            m1 = F(-1.0)
+            o_alpha, o_beta, o_gama = f_bc(m1, m1), f_ca(m1, m1), f_ab(m1, m1)
+            th, tw, _ = tex.shape
+            for y in range(y0, y1 + 1):
+                yf = F(y)
+                for x in range(x0, x1 + 1):
+                    xf = F(x)
+                    alpha, beta, gama = F(f_bc(xf, yf) / f_alpha), F(f_ca(xf, yf) / f_beta), F(f_ab(xf, yf) / f_gama)
+                    if not (alpha >= 0 and beta >= 0 and gama >= 0):
+                        continue
+                    if not ((alpha > 0 or F(f_alpha * o_alpha) > 0) and (beta > 0 or F(f_beta * o_beta) > 0)
+                            and (gama > 0 or F(f_gama * o_gama) > 0)):
+                        continue
+                    col = add_px(add_px(mul_px(va[4], alpha), mul_px(vb[4], beta)), mul_px(vc[4], gama))  # :546
+                    c_alpha = F(F(F(alpha * F(va[5])) + F(beta * F(vb[5]))) + F(gama * F(vc[5])))          # :548-550
+                    u = F(F(F(F(va[2]) * alpha) + F(F(vb[2]) * beta)) + F(F(vc[2]) * gama))                  # :552
+                    v = F(F(F(F(va[3]) * alpha) + F(F(vb[3]) * beta)) + F(F(vc[3]) * gama))
+                    ui = min(sat_usize(F(np.floor(F(u * F(tw))))), tw - 1)  # get_rgba_slice, scene/mod.rs:137-152 (+ clamp)
+                    vi = th - 1 - min(sat_usize(F(np.floor(F(v * F(th))))), th - 1)
+                    px = tex[vi, ui]
+                    t_alpha = F(F(px[3]) / F(255.0))                                                       # :555
+                    col = add_px(mul_px(col, t_alpha), mul_px((int(px[0]), int(px[1]), int(px[2])), F(ONE - t_alpha)))  # :562-563
+                    opacity = F(c_alpha * t_alpha)                                                       # :566
+                    row = self.height - y - 1                                                            # draw_pixel_coord_with_depth(.., 0.0) :568
+                    if opacity < 1:
+                        bg = self.frame[row, x]
+                        new = add_px(mul_px((int(bg[2]), int(bg[1]), int(bg[0])), F(ONE - opacity)), mul_px(col, opacity))
+                    else:
+                        new = col
+                    if F(0.0) < self.depth_frame[y, x]:
+                        self.frame[row, x] = (new[2], new[1], new[0], 0)  # every Pixel here came out of Add: padd = 0
+                        if self.depth_update:
+                            self.depth_frame[y, x] = F(0.0)
+
+
 def texel(tmap, u, v):  # scene/mod.rs:154-168 (+ the never-triggering clamp, deviation 6)
     h, w, _ = tmap.shape
     ui = min(sat_usize(F(np.floor(F(u * F(F(w) - ONE))))), w - 1)

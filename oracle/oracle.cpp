@@ -936,6 +936,68 @@ const uint32_t *orc_canvas_winner(orc_canvas *c, size_t *len) {
     if (len) *len = c->winner.size();
     return c->winner.data();
 }
+/* canvas.rs:435-575 */
+void orc_canvas_draw_triangle(orc_canvas *cv, const orc_vertex2d v[3], const uint8_t *rgba, uint32_t tw, uint32_t th,
+                              const uint64_t clip[4]) {
+    orc_canvas &self = *cv;
+    const Vec2 a_center = pos_map_center({v[0].x, v[0].y}); /* :449-451: no canvas offset on this path */
+    const Vec2 b_center = pos_map_center({v[1].x, v[1].y});
+    const Vec2 c_center = pos_map_center({v[2].x, v[2].y});
+    const Vec2 a_uv{v[0].u, v[0].v}, b_uv{v[1].u, v[1].v}, c_uv{v[2].u, v[2].v};
+    const Pixel color_a = pixel_new(v[0].r, v[0].g, v[0].b); /* Color::Custom(col).as_pixel() :41 */
+    const Pixel color_b = pixel_new(v[1].r, v[1].g, v[1].b);
+    const Pixel color_c = pixel_new(v[2].r, v[2].g, v[2].b);
+    /* :461-480 */
+    auto f_ab = [&](float x, float y) {
+        return (a_center.y - b_center.y) * x + (b_center.x - a_center.x) * y + (a_center.x * b_center.y) - (b_center.x * a_center.y);
+    };
+    auto f_bc = [&](float x, float y) {
+        return (b_center.y - c_center.y) * x + (c_center.x - b_center.x) * y + (b_center.x * c_center.y) - (c_center.x * b_center.y);
+    };
+    auto f_ca = [&](float x, float y) {
+        return (c_center.y - a_center.y) * x + (a_center.x - c_center.x) * y + (c_center.x * a_center.y) - (a_center.x * c_center.y);
+    };
+    /* :504-521 */
+    uint64_t x_min = sat_usize(min3(a_center.x, b_center.x, c_center.x)), y_min = sat_usize(min3(a_center.y, b_center.y, c_center.y));
+    uint64_t x_max = sat_usize(max3(a_center.x, b_center.x, c_center.x)), y_max = sat_usize(max3(a_center.y, b_center.y, c_center.y));
+    Rect drawable = rect_from_coords(x_min, y_min, x_max, y_max);
+    const Rect screen = rect_from_coords(0, 0, self.width - 1, self.height - 1);
+    drawable = rect_clip(drawable, screen);
+    const Rect valid = rect_clip(clip ? rect_from_coords(clip[0], clip[1], clip[2], clip[3]) : screen, drawable);
+    x_min = valid.x; y_min = valid.y; x_max = valid.x_max(); y_max = valid.y_max();
+    /* :523-529 */
+    const float f_alpha = f_bc(a_center.x, a_center.y), f_beta = f_ca(b_center.x, b_center.y), f_gama = f_ab(c_center.x, c_center.y);
+    const float f_alpha_outside = f_bc(-1.0f, -1.0f), f_beta_outside = f_ca(-1.0f, -1.0f), f_gama_outside = f_ab(-1.0f, -1.0f);
+    const float f_width = (float)tw, f_height = (float)th;
+    for (uint64_t y = y_min; y <= y_max; y++) { /* :531-573 */
+        const float y_f32 = (float)y;
+        for (uint64_t x = x_min; x <= x_max; x++) {
+            const float x_f32 = (float)x;
+            const float alpha = f_bc(x_f32, y_f32) / f_alpha, beta = f_ca(x_f32, y_f32) / f_beta, gama = f_ab(x_f32, y_f32) / f_gama;
+            if (!(alpha >= 0.0f && beta >= 0.0f && gama >= 0.0f)) continue;
+            if (!((alpha > 0.0f || f_alpha * f_alpha_outside > 0.0f) && (beta > 0.0f || f_beta * f_beta_outside > 0.0f) &&
+                  (gama > 0.0f || f_gama * f_gama_outside > 0.0f)))
+                continue;
+            Pixel color_pixel = pixel_add(pixel_add(pixel_mul(color_a, alpha), pixel_mul(color_b, beta)), pixel_mul(color_c, gama)); /* :546 */
+            const float color_alpha = (alpha * v[0].alpha) + (beta * v[1].alpha) + (gama * v[2].alpha);                            /* :548-550 */
+            const Vec2 color_uv = (a_uv * alpha) + (b_uv * beta) + (c_uv * gama);                                                      /* :552 */
+            /* get_rgba_slice, scene/mod.rs:137-152: u_idx = floor(u * w), v_idx = h - 1 - floor(v * h); indices clamped into
+             * the map for memory safety (SURVEY.md 8c deviation 6; the reference would index out of bounds) */
+            uint64_t u_idx = sat_usize(std::floor(color_uv.x * f_width)), v_raw = sat_usize(std::floor(color_uv.y * f_height));
+            if (u_idx > tw - 1u) u_idx = tw - 1u;
+            if (v_raw > th - 1u) v_raw = th - 1u;
+            const uint8_t *px = rgba + ((th - 1u - v_raw) * (uint64_t)tw + u_idx) * 4u;
+            const float texture_alpha = (float)px[3] / 255.0f;                                                           /* :555 */
+            const Pixel color_texture = pixel_new(px[0], px[1], px[2]);
+            color_pixel = pixel_add(pixel_mul(color_pixel, texture_alpha), pixel_mul(color_texture, 1.0f - texture_alpha)); /* :562-563 */
+            const float final_alpha = color_alpha * texture_alpha;                                                      /* :566 */
+            self.cur_id = NO_WINNER - 1u;
+            self.draw_pixel_coord_with_depth((size_t)x, (size_t)y, color_pixel, final_alpha, 0.0f);                      /* :568 */
+        }
+    }
+}
+void orc_canvas_set_depth_update(orc_canvas *c, int enabled) { c->depth_update_enabled = enabled != 0; }
+
 void orc_scene_render(orc_scene *s, orc_canvas *c, int count_stats) {
     if (count_stats)
         s->render<true>(*c);

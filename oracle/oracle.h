@@ -88,6 +88,19 @@ const float *orc_canvas_depth(orc_canvas *, size_t *len);
  * last wrote the pixel's colour, 0xFFFFFFFF = none.  Bookkeeping only. */
 const uint32_t *orc_canvas_winner(orc_canvas *, size_t *len);
 
+/* VertexSimpleAttributes (canvas.rs:185-191): screen_coord, texture_coord, color (Color::Custom rgb), alpha. */
+typedef struct orc_vertex2d {
+    float x, y, u, v;
+    uint8_t r, g, b, pad;
+    float alpha;
+} orc_vertex2d;
+/* Canvas::draw_triangle (canvas.rs:435-575), the GUI's 2-D path: texture = an RGBA map (Texture::map_kd read with
+ * get_rgba_slice, scene/mod.rs:137-152); clip = Rectangle::from_coords(x0, y0, x1, y1) or NULL for None. */
+void orc_canvas_draw_triangle(orc_canvas *, const orc_vertex2d v[3], const uint8_t *rgba, uint32_t w, uint32_t h,
+                              const uint64_t clip[4]);
+/* Canvas::enable_depth_update / disable_depth_update (canvas.rs:395-401) */
+void orc_canvas_set_depth_update(orc_canvas *, int enabled);
+
 /* Scene::render (scene/mod.rs:901).  count_stats != 0 also fills the counters. */
 void orc_scene_render(orc_scene *, orc_canvas *, int count_stats);
 void orc_scene_stats(orc_scene *, orc_stats *out);

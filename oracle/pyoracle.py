@@ -87,6 +87,8 @@ def lib():
         L.orc_canvas_depth.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_canvas_winner.restype = C.c_void_p
         L.orc_canvas_winner.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_canvas_draw_triangle.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.orc_canvas_set_depth_update.argtypes = [C.c_void_p, C.c_int]
         L.orc_scene_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_scene_stats.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
@@ -102,8 +104,13 @@ def _vec3(v):
     return (C.c_float * 3)(*[float(np.float32(x)) for x in v])
 
 
+# VertexSimpleAttributes (canvas.rs:185-191) as a 24-byte record: the layout of draw_vertex2d / orc_vertex2d
+VERTEX2D = np.dtype([("x", "<f4"), ("y", "<f4"), ("u", "<f4"), ("v", "<f4"), ("r", "u1"), ("g", "u1"), ("b", "u1"), ("pad", "u1"),
+                     ("alpha", "<f4")])
+
+
 class Canvas:
-    """canvas.rs:353-433 — new / init_depth / apply_offset / resize / clear."""
+    """canvas.rs:353-433 — new / init_depth / apply_offset / resize / clear; draw_triangle (:435-575)."""
 
     def __init__(self, width, height):
         self._h = lib().orc_canvas_new(width, height)
@@ -126,6 +133,22 @@ class Canvas:
 
     def clear(self):
         lib().orc_canvas_clear(self._h)
+
+    def enable_depth_update(self):
+        lib().orc_canvas_set_depth_update(self._h, 1)
+
+    def disable_depth_update(self):
+        lib().orc_canvas_set_depth_update(self._h, 0)
+
+    def draw_triangles(self, vertices, texture, clipping_rect=None):
+        """Canvas::draw_triangle (canvas.rs:435-575) for each consecutive triple of `vertices` (VERTEX2D records:
+        x, y, u, v, r, g, b, pad, alpha), in order.  texture: uint8 [h, w, 4]; clipping_rect: (x0, y0, x1, y1) or None."""
+        v = np.ascontiguousarray(vertices, dtype=VERTEX2D)
+        tex = np.ascontiguousarray(texture, np.uint8)
+        assert tex.ndim == 3 and tex.shape[2] == 4 and v.size % 3 == 0
+        clip = (C.c_uint64 * 4)(*[int(c) for c in clipping_rect]) if clipping_rect is not None else None
+        for t in range(v.size // 3):
+            lib().orc_canvas_draw_triangle(self._h, v[3 * t:3 * t + 3].ctypes.data, tex.ctypes.data, tex.shape[1], tex.shape[0], clip)
 
     def _view(self, fn, ctype, dtype):
         n = C.c_size_t(0)
