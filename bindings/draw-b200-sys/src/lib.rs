@@ -41,6 +41,34 @@ pub struct draw_object {
     _private: [u8; 0],
 }
 
+/// Texture as Canvas::draw_triangle reads it (map_kd, RGBA8, device resident), opaque.
+#[repr(C)]
+pub struct draw_texture {
+    _private: [u8; 0],
+}
+/// VertexSimpleAttributes (canvas.rs:185-191).
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct draw_vertex2d {
+    pub x: f32,
+    pub y: f32,
+    pub u: f32,
+    pub v: f32,
+    pub r: u8,
+    pub g: u8,
+    pub b: u8,
+    pub pad: u8,
+    pub alpha: f32,
+}
+/// The arguments of Rectangle::from_coords (canvas.rs:315-330).
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct draw_rect {
+    pub x0: u64,
+    pub y0: u64,
+    pub x1: u64,
+    pub y1: u64,
+}
 /// TextureMap (scene/mod.rs:102-110); `pixels == NULL` is TextureMap::default() (1x1x3 white).
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -165,6 +193,12 @@ extern "C" {
     pub fn draw_canvas_read_depth(canvas: *mut draw_canvas, dst: *mut c_float, n_floats: usize) -> c_int; // get_pixel_depth :413
     pub fn draw_canvas_sync(canvas: *mut draw_canvas) -> c_int;
     pub fn draw_canvas_last_frame_stats(canvas: *mut draw_canvas, out: *mut draw_frame_stats) -> c_int;
+
+    // ---- Canvas::draw_triangle (canvas.rs:435-575)
+    pub fn draw_texture_create(map_kd: *const draw_texture_map, out: *mut *mut draw_texture) -> c_int;
+    pub fn draw_texture_destroy(texture: *mut draw_texture);
+    pub fn draw_canvas_draw_triangles(canvas: *mut draw_canvas, vertices: *const draw_vertex2d, n_triangles: usize,
+                                      texture: *const draw_texture, clipping_rect: *const draw_rect) -> c_int;
 
     // ---- device-side plumbing (multi-GPU drivers)
     pub fn draw_canvas_device_ptrs(canvas: *mut draw_canvas, out_color: *mut *mut c_void, out_depth: *mut *mut c_void) -> c_int;

@@ -292,6 +292,44 @@ impl Drop for Scene {
     }
 }
 
+/// VertexSimpleAttributes (canvas.rs:185-191); `color` is the payload of Color::Custom.
+#[derive(Clone, Copy, Debug)]
+pub struct VertexSimpleAttributes {
+    pub screen_coord: [f32; 2],
+    pub texture_coord: [f32; 2],
+    pub color: [u8; 3],
+    pub alpha: f32,
+}
+/// Rectangle::from_coords' arguments (canvas.rs:315-330).
+#[derive(Clone, Copy, Debug)]
+pub struct Rectangle {
+    pub x0: usize,
+    pub y0: usize,
+    pub x1: usize,
+    pub y1: usize,
+}
+impl Rectangle {
+    pub fn from_coords(x0: usize, y0: usize, x1: usize, y1: usize) -> Self {
+        Self { x0, y0, x1, y1 }
+    }
+}
+/// The texture Canvas::draw_triangle samples (Texture::map_kd through get_rgba_slice, scene/mod.rs:137-152), on the device.
+pub struct DeviceTexture {
+    h: *mut sys::draw_texture,
+}
+impl DeviceTexture {
+    pub fn new(texture: &Texture) -> Self {
+        let mut h = std::ptr::null_mut();
+        check(unsafe { sys::draw_texture_create(&texture.map_kd.as_sys(), &mut h) });
+        Self { h }
+    }
+}
+impl Drop for DeviceTexture {
+    fn drop(&mut self) {
+        unsafe { sys::draw_texture_destroy(self.h) }
+    }
+}
+
 pub struct Canvas {
     h: *mut sys::draw_canvas,
     pub width: usize,
@@ -329,6 +367,26 @@ impl Canvas {
         let mut out = vec![0f32; self.width * self.height];
         check(unsafe { sys::draw_canvas_read_depth(self.h, out.as_mut_ptr(), out.len()) });
         out
+    }
+    /// Canvas::draw_triangle (canvas.rs:435-575).  The reference takes `Option<&Texture>` and asserts it is Some.
+    pub fn draw_triangle(&mut self, a_vertex: VertexSimpleAttributes, b_vertex: VertexSimpleAttributes, c_vertex: VertexSimpleAttributes,
+                         texture: Option<&DeviceTexture>, clipping_rect: Option<Rectangle>) {
+        self.draw_triangles(&[a_vertex, b_vertex, c_vertex], texture.expect("draw_triangle needs a texture"), clipping_rect)
+    }
+    /// One draw command of Gui::render (src/app/gui.rs:382-485): `vertices.len() / 3` draw_triangle calls in order
+    /// with one texture and one clipping rectangle, in two kernel launches.
+    pub fn draw_triangles(&mut self, vertices: &[VertexSimpleAttributes], texture: &DeviceTexture, clipping_rect: Option<Rectangle>) {
+        assert!(vertices.len() % 3 == 0);
+        let v: Vec<sys::draw_vertex2d> = vertices
+            .iter()
+            .map(|a| sys::draw_vertex2d {
+                x: a.screen_coord[0], y: a.screen_coord[1], u: a.texture_coord[0], v: a.texture_coord[1],
+                r: a.color[0], g: a.color[1], b: a.color[2], pad: 0, alpha: a.alpha,
+            })
+            .collect();
+        let rect = clipping_rect.map(|r| sys::draw_rect { x0: r.x0 as u64, y0: r.y0 as u64, x1: r.x1 as u64, y1: r.y1 as u64 });
+        let rect_ptr = rect.as_ref().map_or(std::ptr::null(), |r| r as *const sys::draw_rect);
+        check(unsafe { sys::draw_canvas_draw_triangles(self.h, v.as_ptr(), v.len() / 3, texture.h, rect_ptr) })
     }
     /// Application::export_frame_as(Png) (app/mod.rs:316-360)
     pub fn export_png(&self, path: &str) {

@@ -41,6 +41,10 @@ class ObjectDesc(C.Structure):
                 ("materials", C.c_void_p), ("n_materials", C.c_size_t)]
 
 
+class Rect(C.Structure):  # draw_rect
+    _fields_ = [("x0", C.c_uint64), ("y0", C.c_uint64), ("x1", C.c_uint64), ("y1", C.c_uint64)]
+
+
 class FrameStats(C.Structure):
     _NAMES = ("input_triangles", "setup_records", "tile_refs", "large_refs", "medium_refs", "small_refs", "transparent_refs",
               "overflow", "empty_tiles", "work_items")
@@ -103,6 +107,9 @@ SIGNATURES = {
     "draw_canvas_set_stripe": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t]),
     "draw_canvas_set_tile_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "draw_canvas_set_empty_tile_color": (C.c_int, [C.c_void_p, C.c_int]),
+    "draw_texture_create": (C.c_int, [C.POINTER(TextureMap), C.POINTER(C.c_void_p)]),
+    "draw_texture_destroy": (None, [C.c_void_p]),
+    "draw_canvas_draw_triangles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(Rect)]),
     "draw_device_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "draw_device_free": (C.c_int, [C.c_void_p]),
     "draw_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),

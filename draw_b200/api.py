@@ -68,6 +68,31 @@ class Camera:
     def move_backward(self, dist): self._move(5, dist)
 
 
+# VertexSimpleAttributes (canvas.rs:185-191) as draw_vertex2d lays it out
+VERTEX2D = np.dtype([("x", "<f4"), ("y", "<f4"), ("u", "<f4"), ("v", "<f4"), ("r", "u1"), ("g", "u1"), ("b", "u1"), ("pad", "u1"),
+                     ("alpha", "<f4")])
+
+
+class DeviceTexture:
+    """The `texture: Option<&Texture>` argument of Canvas::draw_triangle (canvas.rs:435): map_kd as an RGBA8 array
+    [height, width, 4], row 0 = top, copied to the device once (draw_texture_create)."""
+
+    def __init__(self, map_kd):
+        a = np.ascontiguousarray(map_kd, np.uint8)
+        if a.ndim != 3 or a.shape[2] != 4:
+            raise ValueError("get_rgba_slice needs a four-component map: uint8 [height, width, 4]")
+        tm = N.TextureMap(a.ctypes.data, a.shape[1], a.shape[0], 4)
+        h = C.c_void_p()
+        N.check(N.lib().draw_texture_create(C.byref(tm), C.byref(h)))
+        self._h = h
+        self.width, self.height = int(a.shape[1]), int(a.shape[0])
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and N is not None:
+            N.lib().draw_texture_destroy(h)
+
+
 class Canvas:
     """canvas.rs:353-983."""
 
@@ -100,6 +125,24 @@ class Canvas:
 
     def disable_depth_update(self):
         N.check(N.lib().draw_canvas_disable_depth_update(self._h))
+
+    def draw_triangles(self, vertices, texture, clipping_rect=None):
+        """Canvas::draw_triangle (canvas.rs:435-575) for every three entries of `vertices` (a VERTEX2D array) in order,
+        with one texture (a DeviceTexture, or an RGBA8 array uploaded for this call) and one clipping rectangle
+        (x0, y0, x1, y1 as given to Rectangle::from_coords, or None) — one draw command of src/app/gui.rs:382-485."""
+        v = np.ascontiguousarray(vertices, VERTEX2D)
+        if v.ndim != 1 or v.size % 3:
+            raise ValueError("vertices holds three VERTEX2D entries per triangle")
+        tex = texture if isinstance(texture, DeviceTexture) else DeviceTexture(texture)
+        rect = None if clipping_rect is None else C.byref(N.Rect(*[int(c) for c in clipping_rect]))
+        N.check(N.lib().draw_canvas_draw_triangles(self._h, v.ctypes.data, v.size // 3, tex._h, rect))
+
+    def draw_triangle(self, a_vertex, b_vertex, c_vertex, texture, clipping_rect=None):
+        """One Canvas::draw_triangle call; each vertex is (x, y, u, v, (r, g, b), alpha)."""
+        v = np.zeros(3, VERTEX2D)
+        for k, (x, y, tu, tv, rgb, alpha) in enumerate((a_vertex, b_vertex, c_vertex)):
+            v[k] = (x, y, tu, tv, rgb[0], rgb[1], rgb[2], 0, alpha)
+        self.draw_triangles(v, texture, clipping_rect)
 
     @staticmethod
     def pixel_bytes():

@@ -1,5 +1,6 @@
 // device_types.h — plain structs shared by the host library (scene.cpp) and the kernels.
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 #include <vector_types.h>
 
@@ -228,5 +229,25 @@ constexpr int COST_BUCKETS = 34;
 enum : uint32_t { OVERFLOW_RECORDS = 1u, OVERFLOW_REFS = 2u, OVERFLOW_STALL = 4u, OVERFLOW_HUGE = 8u }; // STALL: a grid barrier of k_front timed out (never in a cooperative launch)
 
 constexpr int N_FRAME_KERNELS = 4; // k_sort_transparent k_front k_raster k_tile
+
+// Canvas::draw_triangle batches (k_overlay.cu): one draw command's triangles, texture and clipping rectangle.
+constexpr int OVERLAY_BIN = 64;             // pixels per bin edge
+constexpr size_t OVERLAY_REC_BYTES = 80;    // per triangle, written by k_overlay_setup
+constexpr uint32_t OVERLAY_MAX_BATCH = 32768; // triangles per launch pair (sizes the bin masks)
+struct OverlayParams {
+    const void *verts; // 3 draw_vertex2d per triangle
+    void *recs;        // n x OVERLAY_REC_BYTES
+    uint32_t *masks;   // [bins_x * bins_y][words]: bit i of a bin = triangle i's rectangle touches it
+    uint32_t *bin_any; // [bins_x * bins_y]
+    uint32_t n, words, bins_x, bins_y;
+    uint32_t width, height;
+    unsigned long long clip[4]; // x0, y0, x1, y1 as given to Rectangle::from_coords
+    uint32_t has_clip;
+    const void *texels; // RGBA8, row 0 = top
+    uint32_t tex_w, tex_h;
+    uint32_t *color;
+    float *depth;
+    uint32_t depth_update;
+};
 
 } // namespace drawb200

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <set>
@@ -38,6 +39,7 @@ void launch_sort_transparent(const FrameUniforms *dU, const SceneDev &S, const v
 cudaError_t launch_clear(uint8_t *color, float *depth, size_t n_pixels, float depth_max, cudaStream_t stream,
                          uint64_t *launches);
 cudaError_t launch_fill_u32(uint32_t *dst, size_t n, uint32_t value, cudaStream_t stream, uint64_t *launches);
+cudaError_t launch_overlay(const OverlayParams &P, cudaStream_t stream, uint64_t *launches);                        // k_overlay.cu
 cudaError_t launch_flag_signal(uint32_t *flag, uint32_t value, cudaStream_t stream);                               // k_sync.cu
 cudaError_t launch_flags_wait(const uint32_t *flags, uint32_t n, uint32_t value, uint32_t *error_word, cudaStream_t stream);
 } // namespace drawb200
@@ -244,11 +246,21 @@ struct draw_canvas {
         float depth_max = 0.0f;
     };
     std::vector<FrameInputs> pending;
+    // draw_canvas_draw_triangles scratch: the batch's vertices, its records, the bin masks and the per-bin flags
+    DevBuf<uint8_t> ov_verts, ov_recs;
+    DevBuf<uint32_t> ov_masks, ov_any;
     draw_frame_stats stats{};
     uint64_t launches = 0;
 
     uint8_t *color() const { return ext_color ? ext_color : d_color.ptr; }
     float *depth() const { return ext_depth ? ext_depth : d_depth.ptr; }
+};
+
+// Texture (scene/mod.rs:206-216) as Canvas::draw_triangle uses it: map_kd, RGBA8, resident on the device
+struct draw_texture {
+    int device = 0;
+    uint32_t width = 0, height = 0;
+    DevBuf<uint8_t> texels;
 };
 
 namespace {
@@ -1365,6 +1377,84 @@ int draw_canvas_disable_depth_update(draw_canvas *canvas) {
     if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas is NULL");
     canvas->depth_update = false;
     return DRAW_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Canvas::draw_triangle (canvas.rs:435-575)
+// ------------------------------------------------------------------------------------------
+int draw_texture_create(const draw_texture_map *map_kd, draw_texture **out) {
+    GUARD_BEGIN
+    if (!map_kd || !out) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    // get_rgba_slice (scene/mod.rs:137-152) requires four components
+    if (!map_kd->pixels || map_kd->components != 4 || map_kd->width == 0 || map_kd->height == 0)
+        return fail(DRAW_ERR_INVALID_ARGUMENT, "draw_texture_create needs an RGBA map (components == 4) with pixels");
+    if (g_device >= 0) TRY(ensure_device(g_device));
+    std::unique_ptr<draw_texture> t(new draw_texture);
+    CU(cudaGetDevice(&t->device));
+    t->width = map_kd->width;
+    t->height = map_kd->height;
+    const size_t bytes = (size_t)t->width * t->height * 4;
+    TRY(t->texels.reserve(bytes));
+    CU(cudaMemcpy(t->texels.ptr, map_kd->pixels, bytes, cudaMemcpyHostToDevice));
+    *out = t.release();
+    return DRAW_OK;
+    GUARD_END
+}
+
+void draw_texture_destroy(draw_texture *texture) {
+    if (!texture) return;
+    cudaSetDevice(texture->device);
+    delete texture;
+}
+
+int draw_canvas_draw_triangles(draw_canvas *canvas, const draw_vertex2d *vertices, size_t n_triangles, const draw_texture *texture,
+                               const draw_rect *clipping_rect) {
+    GUARD_BEGIN
+    if (!canvas || !texture || (!vertices && n_triangles)) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!canvas->has_depth) return fail(DRAW_ERR_INVALID_ARGUMENT, "Depth not initialized"); // get_pixel_depth indexes an empty Vec
+    if (texture->device != canvas->device) return fail(DRAW_ERR_INVALID_ARGUMENT, "texture and canvas live on different devices");
+    TRY(ensure_device(canvas->device));
+    // A frame still in flight may have to be rendered again (overflow); the triangles go on top of the settled frame.
+    TRY(finish_frame(canvas));
+    OverlayParams P{};
+    P.width = (uint32_t)canvas->width;
+    P.height = (uint32_t)canvas->height;
+    P.bins_x = (P.width + OVERLAY_BIN - 1) / OVERLAY_BIN;
+    P.bins_y = (P.height + OVERLAY_BIN - 1) / OVERLAY_BIN;
+    if (clipping_rect) {
+        P.has_clip = 1;
+        P.clip[0] = clipping_rect->x0;
+        P.clip[1] = clipping_rect->y0;
+        P.clip[2] = clipping_rect->x1;
+        P.clip[3] = clipping_rect->y1;
+    }
+    P.texels = texture->texels.ptr;
+    P.tex_w = texture->width;
+    P.tex_h = texture->height;
+    P.color = reinterpret_cast<uint32_t *>(canvas->color());
+    P.depth = canvas->depth();
+    P.depth_update = canvas->depth_update ? 1u : 0u;
+    const size_t n_bins = (size_t)P.bins_x * P.bins_y;
+    for (size_t first = 0; first < n_triangles; first += OVERLAY_MAX_BATCH) { // batches keep submission order on the stream
+        const uint32_t n = (uint32_t)std::min<size_t>(OVERLAY_MAX_BATCH, n_triangles - first);
+        P.n = n;
+        P.words = (n + 31) / 32;
+        TRY(canvas->ov_verts.reserve((size_t)n * 3 * sizeof(draw_vertex2d)));
+        TRY(canvas->ov_recs.reserve((size_t)n * OVERLAY_REC_BYTES));
+        TRY(canvas->ov_masks.reserve(n_bins * P.words));
+        TRY(canvas->ov_any.reserve(n_bins));
+        // pageable source: the copy has left the caller's buffer when this returns
+        CU(cudaMemcpyAsync(canvas->ov_verts.ptr, vertices + first * 3, (size_t)n * 3 * sizeof(draw_vertex2d), cudaMemcpyHostToDevice,
+                           canvas->stream));
+        P.verts = canvas->ov_verts.ptr;
+        P.recs = canvas->ov_recs.ptr;
+        P.masks = canvas->ov_masks.ptr;
+        P.bin_any = canvas->ov_any.ptr;
+        CU(launch_overlay(P, canvas->stream, &canvas->launches));
+    }
+    if (n_triangles) canvas->host_dirty = true;
+    return DRAW_OK;
+    GUARD_END
 }
 
 int draw_canvas_size(const draw_canvas *canvas, size_t *width, size_t *height) {

@@ -155,3 +155,68 @@ def orbit_camera(n_frames=64):
     k = np.arange(n_frames, dtype=np.float64)
     pos = np.stack([15.0 * np.sin(2 * np.pi * k / n_frames), 8.0 * np.sin(4 * np.pi * k / n_frames), np.full_like(k, 150.0)], 1)
     return np.concatenate([pos, -pos], 1).astype(F)
+
+
+# VertexSimpleAttributes (canvas.rs:185-191) in draw_vertex2d's layout (draw_b200.api.VERTEX2D, oracle.pyoracle.VERTEX2D)
+_VERTEX2D = np.dtype([("x", "<f4"), ("y", "<f4"), ("u", "<f4"), ("v", "<f4"), ("r", "u1"), ("g", "u1"), ("b", "u1"), ("pad", "u1"),
+                      ("alpha", "<f4")])
+
+
+def font_atlas(width=256, height=64, seed=0xA71A5):
+    """A stand-in for the GUI's font atlas (src/app/gui.rs: imgui's RGBA32 font texture): white RGB with an alpha
+    channel of glyph-like blobs, plus a fully opaque white block at the top left (what ImGui's solid fills sample)."""
+    rng = np.random.default_rng(seed)
+    a = np.zeros((height, width, 4), np.uint8)
+    a[..., :3] = 255
+    yy, xx = np.mgrid[0:height, 0:width]
+    alpha = (np.sin(xx * 0.9) * np.cos(yy * 0.7) * 0.5 + 0.5) * 255.0
+    alpha[rng.random((height, width)) < 0.35] = 0.0
+    a[..., 3] = alpha.astype(np.uint8)
+    a[:8, :8, 3] = 255
+    a[8:12, :8, :3] = rng.integers(0, 256, (4, 8, 3))  # a few coloured texels: the texture's RGB takes part in the blend
+    return a
+
+
+def gui_command_list(width, height, n_commands=6, quads_per_command=40, seed=1):
+    """Draw commands shaped like src/app/gui.rs:382-485 feeds Canvas::draw_triangle: per command a clipping rectangle
+    (x0, y0, x1, y1) or None and a VERTEX2D array of window-like quads (two triangles each: solid fills sampling the
+    opaque white texel, glyph quads sampling the atlas) with some free triangles, degenerate and off-screen ones."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for c in range(n_commands):
+        n = quads_per_command
+        v = np.zeros(n * 6, _VERTEX2D)
+        for q in range(n):
+            kind = rng.random()
+            x0, y0 = rng.uniform(-20, width), rng.uniform(-20, height)
+            w, h = (rng.uniform(4, max(5.0, width / 3)), rng.uniform(4, max(5.0, height / 3))) if kind < 0.3 else (rng.uniform(3, 24), rng.uniform(5, 24))
+            x1, y1 = x0 + w, y0 + h
+            if kind < 0.3:
+                u0, v0, u1, v1 = 0.01, 0.99, 0.02, 0.98   # the opaque white block (row 0 = top = v near 1)
+            else:
+                u0, v0 = rng.uniform(0, 0.9), rng.uniform(0, 0.9)
+                u1, v1 = u0 + rng.uniform(0.01, 0.09), v0 + rng.uniform(0.01, 0.09)
+            col = rng.integers(0, 256, 3)
+            alpha = 1.0 if rng.random() < 0.4 else rng.integers(0, 256) / 255.0
+            quad = [(x0, y0, u0, v0), (x1, y0, u1, v0), (x1, y1, u1, v1), (x0, y0, u0, v0), (x1, y1, u1, v1), (x0, y1, u0, v1)]
+            if kind > 0.9:  # free triangles with per-vertex colours and half-pixel coordinates
+                quad = [(rng.uniform(-30, width + 30), rng.uniform(-30, height + 30), rng.uniform(0, 0.99), rng.uniform(0, 0.99)) for _ in range(6)]
+            for k, (x, y, tu, tv) in enumerate(quad):
+                vc = rng.integers(0, 256, 3) if kind > 0.9 else col
+                va = rng.integers(0, 256) / 255.0 if kind > 0.95 else alpha
+                v[q * 6 + k] = (x, y, tu, tv, vc[0], vc[1], vc[2], 0, va)
+        if c == 1:  # degenerate, far off-screen and non-finite vertices
+            v[0:3]["x"] = v[0]["x"]
+            v[0:3]["y"] = v[0]["y"]
+            v[3:6]["x"] += 1.0e9
+            v[6]["x"] = np.nan
+            v[9]["y"] = np.inf
+            v[12:15]["x"] = -5000.0
+        clip = None
+        if c % 3 == 1:
+            cx0, cy0 = int(rng.integers(0, width // 2)), int(rng.integers(0, height // 2))
+            clip = (cx0, cy0, int(rng.integers(cx0, width + 40)), int(rng.integers(cy0, height + 40)))
+        elif c % 3 == 2:  # from_coords normalises swapped corners (gui.rs inverts y, so y0 > y1 is the usual case)
+            clip = (int(rng.integers(width // 2, width)), int(rng.integers(height // 2, height)), int(rng.integers(0, width // 2)), int(rng.integers(0, height // 2)))
+        out.append((clip, v))
+    return out

@@ -196,6 +196,32 @@ int draw_canvas_read_depth(draw_canvas *canvas, float *dst, size_t n_floats);
 int draw_canvas_sync(draw_canvas *canvas);
 int draw_canvas_last_frame_stats(draw_canvas *canvas, draw_frame_stats *out);
 
+/* ---- Canvas::draw_triangle (canvas.rs:435-575), the 2-D path of the GUI -------------- */
+/* VertexSimpleAttributes (canvas.rs:185-191): screen_coord (pixels, y up like the canvas), texture_coord, color
+ * (Color::Custom([r, g, b])) and alpha. */
+typedef struct draw_vertex2d {
+    float x, y, u, v;
+    uint8_t r, g, b, pad;
+    float alpha;
+} draw_vertex2d;
+/* The arguments of Rectangle::from_coords(x0, y0, x1, y1) (canvas.rs:315-330), in canvas pixels. */
+typedef struct draw_rect {
+    uint64_t x0, y0, x1, y1;
+} draw_rect;
+/* The `texture: Option<&Texture>` argument reduced to what the path reads, texture.map_kd through get_rgba_slice
+ * (scene/mod.rs:137-152): an RGBA8 map (components must be 4), copied to the device once. */
+typedef struct draw_texture draw_texture;
+int draw_texture_create(const draw_texture_map *map_kd, draw_texture **out);
+void draw_texture_destroy(draw_texture *texture);
+/* n_triangles calls of Canvas::draw_triangle(a, b, c, Some(texture), clipping_rect) in order (vertices holds 3 per
+ * triangle; clipping_rect may be NULL = None) — one draw command of src/app/gui.rs:382-485.  Pixels are written over
+ * the canvas' frame with depth 0.0 under the canvas' depth-update switch, blended in submission order; the partition
+ * set by draw_canvas_set_stripe / set_tile_rows does not apply.  Waits for a frame still being rendered, then enqueues
+ * on the canvas' stream and returns; the vertices have been copied when it returns.  Needs a depth buffer
+ * (draw_canvas_init_depth), as the reference's depth test does. */
+int draw_canvas_draw_triangles(draw_canvas *canvas, const draw_vertex2d *vertices, size_t n_triangles, const draw_texture *texture,
+                               const draw_rect *clipping_rect);
+
 /* ---- device-side plumbing (not in the reference; used by the multi-GPU drivers) ------ */
 /* Device pointers of the colour (BGRA8, y-flipped rows) and depth (f32) buffers. */
 int draw_canvas_device_ptrs(draw_canvas *canvas, void **out_color, void **out_depth);

@@ -132,6 +132,36 @@ struct Object {
 
 class Scene;
 
+// VertexSimpleAttributes (canvas.rs:185-191); color is the payload of Color::Custom.
+struct VertexSimpleAttributes {
+    float screen_coord[2];
+    float texture_coord[2];
+    uint8_t color[3];
+    float alpha;
+};
+// The arguments of Rectangle::from_coords (canvas.rs:315-330).
+struct Rectangle {
+    size_t x0, y0, x1, y1;
+    static Rectangle from_coords(size_t x0, size_t y0, size_t x1, size_t y1) { return {x0, y0, x1, y1}; }
+};
+// The texture Canvas::draw_triangle samples: Texture::map_kd (RGBA8) through get_rgba_slice (scene/mod.rs:137-152),
+// copied to the device once.
+class DeviceTexture {
+  public:
+    explicit DeviceTexture(const Texture &texture) {
+        const TextureMap &m = texture.map_kd;
+        const draw_texture_map map{m.img.empty() ? nullptr : m.img.data(), (uint32_t)m.width, (uint32_t)m.height, (uint32_t)m.components};
+        check(draw_texture_create(&map, &h_));
+    }
+    ~DeviceTexture() { draw_texture_destroy(h_); }
+    DeviceTexture(const DeviceTexture &) = delete;
+    DeviceTexture &operator=(const DeviceTexture &) = delete;
+    const draw_texture *handle() const { return h_; }
+
+  private:
+    draw_texture *h_ = nullptr;
+};
+
 // Canvas (canvas.rs:353-983).
 class Canvas {
   public:
@@ -166,6 +196,24 @@ class Canvas {
         return d;
     }
     float get_pixel_depth(size_t x, size_t y) { return depth_frame().at(y * width() + x); }   // :413
+    // Canvas::draw_triangle (canvas.rs:435-575); clipping_rect == nullptr is None
+    void draw_triangle(const VertexSimpleAttributes &a, const VertexSimpleAttributes &b, const VertexSimpleAttributes &c,
+                       const DeviceTexture &texture, const Rectangle *clipping_rect = nullptr) {
+        const VertexSimpleAttributes v[3] = {a, b, c};
+        draw_triangles(v, 1, texture, clipping_rect);
+    }
+    // one draw command of Gui::render (src/app/gui.rs:382-485): n_triangles draw_triangle calls in order
+    void draw_triangles(const VertexSimpleAttributes *vertices, size_t n_triangles, const DeviceTexture &texture,
+                        const Rectangle *clipping_rect = nullptr) {
+        std::vector<draw_vertex2d> v(3 * n_triangles);
+        for (size_t i = 0; i < v.size(); i++) {
+            const VertexSimpleAttributes &a = vertices[i];
+            v[i] = {a.screen_coord[0], a.screen_coord[1], a.texture_coord[0], a.texture_coord[1], a.color[0], a.color[1], a.color[2], 0, a.alpha};
+        }
+        draw_rect r{};
+        if (clipping_rect) r = {clipping_rect->x0, clipping_rect->y0, clipping_rect->x1, clipping_rect->y1};
+        check(draw_canvas_draw_triangles(h_, v.data(), n_triangles, texture.handle(), clipping_rect ? &r : nullptr));
+    }
     void export_png(const std::string &path) { check(draw_canvas_export_png(h_, path.c_str())); } // app/mod.rs:316
     void sync() { check(draw_canvas_sync(h_)); }
     draw_canvas *handle() const { return h_; }

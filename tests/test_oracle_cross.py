@@ -175,3 +175,19 @@ def test_draw_triangle_2d_gui_path_cross():
         assert np.array_equal(c.as_bytes(), pc.frame), f"case {case}"
         assert np.array_equal(c.depth().view(np.uint32), pc.depth_frame.view(np.uint32))
         assert (c.as_bytes()[..., 3] == 0).any(), "nothing was drawn"
+
+
+def test_draw_triangle_2d_golden_gui_frame():
+    """The committed GUI frame (tests/golden/make_overlay_golden.py, drawn by the numpy restatement) out of the C++ oracle."""
+    import os
+    from conftest import GOLDEN
+    from draw_b200 import synthetic
+    from oracle import pyoracle
+    want = np.load(os.path.join(GOLDEN, "overlay_gui_96x64.npz"))["frame"]
+    atlas = synthetic.font_atlas(64, 32)
+    c = pyoracle.Canvas(96, 64)
+    c.init_depth(10.0)
+    c.clear()
+    for clip, v in synthetic.gui_command_list(96, 64, n_commands=4, quads_per_command=8, seed=2):
+        c.draw_triangles(v, atlas, clip)
+    assert np.array_equal(c.as_bytes(), want)
