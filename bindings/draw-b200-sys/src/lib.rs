@@ -204,6 +204,7 @@ extern "C" {
     pub fn draw_canvas_device_ptrs(canvas: *mut draw_canvas, out_color: *mut *mut c_void, out_depth: *mut *mut c_void) -> c_int;
     pub fn draw_canvas_bind_external(canvas: *mut draw_canvas, color_dev: *mut c_void, depth_dev: *mut c_void) -> c_int;
     pub fn draw_canvas_export_png(canvas: *mut draw_canvas, path: *const c_char) -> c_int; // export_frame_as(Png), app/mod.rs:316-360
+    pub fn draw_canvas_export_jpeg(canvas: *mut draw_canvas, path: *const c_char) -> c_int; // export_frame_as(Jpeg)
     pub fn draw_canvas_set_stream(canvas: *mut draw_canvas, cuda_stream: *mut c_void) -> c_int;
     pub fn draw_canvas_stream_wait(canvas: *mut draw_canvas, cuda_stream: *mut c_void) -> c_int;
     pub fn draw_canvas_set_stripe(canvas: *mut draw_canvas, y0: usize, y1: usize) -> c_int;
@@ -224,6 +225,7 @@ extern "C" {
     pub fn draw_image_load(path: *const c_char, out_pixels: *mut *mut u8, out_w: *mut u32, out_h: *mut u32, out_components: *mut u32) -> c_int;
     pub fn draw_image_free(pixels: *mut u8);
     pub fn draw_image_write_png(path: *const c_char, pixels: *const u8, width: u32, height: u32, components: u32) -> c_int;
+    pub fn draw_image_write_jpg(path: *const c_char, pixels: *const u8, width: u32, height: u32, components: u32, quality: c_int) -> c_int;
     pub fn draw_image_loader_builtin(path: *const c_char, user: *mut c_void, out_pixels: *mut *mut u8, out_w: *mut u32, out_h: *mut u32, out_components: *mut u32) -> c_int;
     pub fn draw_object_free(obj: *mut draw_object);
     pub fn draw_object_desc_of(obj: *const draw_object, out: *mut draw_object_desc) -> c_int;

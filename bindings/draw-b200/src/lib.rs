@@ -394,6 +394,13 @@ impl Canvas {
         check(unsafe { sys::draw_canvas_export_png(self.h, c.as_ptr()) })
     }
 }
+impl Canvas {
+    /// Application::export_frame_as(Jpeg) (app/mod.rs:316-378)
+    pub fn export_jpeg(&self, path: &str) {
+        let c = CString::new(path).unwrap();
+        check(unsafe { sys::draw_canvas_export_jpeg(self.h, c.as_ptr()) })
+    }
+}
 impl Drop for Canvas {
     fn drop(&mut self) {
         unsafe { sys::draw_canvas_destroy(self.h) }

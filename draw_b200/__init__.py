@@ -12,7 +12,7 @@ __all__ = ["Scene", "Canvas", "Camera", "Object", "IndexedMesh", "Texture", "Dra
 def __getattr__(name):
     # api needs the native library; keep `import draw_b200.model` usable for tools that only
     # handle data, but anything that renders goes through the library or fails loudly.
-    if name in ("Scene", "Canvas", "Camera", "ObjectInfo", "device_count", "set_device", "tile_size", "load_obj", "load_image", "write_png", "DeviceTexture", "VERTEX2D"):
+    if name in ("Scene", "Canvas", "Camera", "ObjectInfo", "device_count", "set_device", "tile_size", "load_obj", "load_image", "write_png", "write_jpg", "DeviceTexture", "VERTEX2D"):
         from . import api
         return getattr(api, name)
     if name == "DrawError":

@@ -124,6 +124,8 @@ SIGNATURES = {
     "draw_image_free": (None, [C.c_void_p]),
     "draw_image_write_png": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "draw_canvas_export_png": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "draw_canvas_export_jpeg": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "draw_image_write_jpg": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
     "draw_image_loader_builtin": (C.c_int, [C.c_char_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32),
                                             C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "draw_object_free": (None, [C.c_void_p]),

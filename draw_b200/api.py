@@ -198,6 +198,10 @@ class Canvas:
         """Application::export_frame_as(Png) (app/mod.rs:316-360): the current frame as an RGBA PNG file."""
         N.check(N.lib().draw_canvas_export_png(self._h, str(path).encode()))
 
+    def export_jpeg(self, path):
+        """Application::export_frame_as(Jpeg) (app/mod.rs:316-378): the current frame as a quality-100 baseline JPEG file."""
+        N.check(N.lib().draw_canvas_export_jpeg(self._h, str(path).encode()))
+
     def stream_wait(self, cuda_stream):
         """Make `cuda_stream` wait (on the device) for everything enqueued so far for this canvas."""
         N.check(N.lib().draw_canvas_stream_wait(self._h, cuda_stream))
@@ -380,7 +384,7 @@ def tile_size():
 
 
 def load_image(path):
-    """TextureMap::load_from_file (scene/mod.rs:174-202) through the library's own decoder (PNG only):
+    """TextureMap::load_from_file (scene/mod.rs:174-202) through the library's own decoders (PNG; JPEG with stb_image's arithmetic):
     uint8 [height, width, components], components 3 or 4, row 0 = top."""
     px, w, h, c = C.c_void_p(), C.c_uint32(), C.c_uint32(), C.c_uint32()
     N.check(N.lib().draw_image_load(str(path).encode(), C.byref(px), C.byref(w), C.byref(h), C.byref(c)))
@@ -397,17 +401,25 @@ def write_png(path, pixels):
     N.check(N.lib().draw_image_write_png(str(path).encode(), a.ctypes.data, a.shape[1], a.shape[0], a.shape[2]))
 
 
+def write_jpg(path, pixels, quality=100):
+    """stbi_write_jpg (app/mod.rs:362-378): uint8 [height, width, 3 or 4] -> baseline JPEG file; quality as
+    stb_image_write reads it (0 = 90, clamped to 1..100; only qualities above 90 are written)."""
+    a = np.ascontiguousarray(pixels, dtype=np.uint8)
+    N.check(N.lib().draw_image_write_jpg(str(path).encode(), a.ctypes.data, a.shape[1], a.shape[0], a.shape[2], int(quality)))
+
+
 def load_obj(path, decode_images=True):
     """Object::load_from_file (scene/object.rs:106) through the library's C++ loader
-    (draw_object_load_obj).  Texture files named by the MTL are decoded with PIL when
-    decode_images is true (the reference uses stb_image), else maps stay at the 1x1 default."""
+    (draw_object_load_obj).  Texture files named by the MTL are decoded by the library (PNG, JPEG) when
+    decode_images is true — PIL only stands in for the formats the library does not decode — else maps stay at
+    the 1x1 default."""
     from .model import IndexedMesh, Texture
     libc = C.CDLL(None)
     libc.malloc.restype = C.c_void_p
     libc.malloc.argtypes = [C.c_size_t]
 
     def _decode(cpath, _user, out_pixels, out_w, out_h, out_comp):
-        # PNG: the library's own decoder; anything else (the airplane's JPEG): PIL stands in for stb_image
+        # PNG / JPEG: the library's own decoders; anything else: PIL stands in for stb_image
         if N.lib().draw_image_loader_builtin(cpath, None, out_pixels, out_w, out_h, out_comp) == 0:
             return 0
         try:

@@ -5,8 +5,7 @@
 // width * height * components, row 0 = top of the image.  This file is the library's own decoder for the
 // lossless format among the reference's assets, PNG (models/lemur/lemurT.png): any correct PNG decoder
 // produces the same bytes as stb_image, so parity does not depend on whose it is.  JPEG is lossy and
-// decoders differ in their IDCT / upsampling arithmetic, so JPEG files are left to the
-// caller's draw_image_loader callback (or to a scene cache prepared with the decoder of record).
+// decoders differ in their IDCT / upsampling arithmetic: jpeg_decode.cpp restates stb_image's.
 //
 // PNG (ISO/IEC 15948): signature, IHDR, [PLTE], [tRNS], IDAT..., IEND; the concatenated IDAT payload is a
 // zlib stream (inflated with zlib) of filtered scanlines; filters None / Sub / Up / Average / Paeth.
@@ -27,6 +26,7 @@
 
 namespace drawb200 {
 int loader_fail(int code, const char *msg); // scene.cpp: sets draw_last_error
+int decode_jpeg(const std::vector<uint8_t> &file, uint8_t **out_pixels, uint32_t *out_w, uint32_t *out_h, uint32_t *out_comp); // jpeg_decode.cpp
 }
 
 namespace {
@@ -183,8 +183,9 @@ int draw_image_load(const char *path, uint8_t **out_pixels, uint32_t *out_w, uin
         std::vector<uint8_t> file;
         if (!read_file(path, file)) return loader_fail(DRAW_ERR_INVALID_ARGUMENT, (std::string("cannot read ") + path).c_str());
         if (file.size() >= 8 && file[0] == 0x89 && file[1] == 'P') return decode_png(file, out_pixels, out_w, out_h, out_components);
+        if (file.size() >= 4 && file[0] == 0xff && file[1] == 0xd8) return drawb200::decode_jpeg(file, out_pixels, out_w, out_h, out_components);
         return loader_fail(DRAW_ERR_INVALID_ARGUMENT,
-                           (std::string(path) + ": only PNG is decoded by the library; pass a draw_image_loader for other formats").c_str());
+                           (std::string(path) + ": only PNG and JPEG are decoded by the library; pass a draw_image_loader for other formats").c_str());
     } catch (const std::bad_alloc &) {
         return loader_fail(DRAW_ERR_OUT_OF_MEMORY, "host allocation failed");
     } catch (...) {

@@ -1641,6 +1641,22 @@ int draw_canvas_export_png(draw_canvas *canvas, const char *path) {
     GUARD_END
 }
 
+int draw_canvas_export_jpeg(draw_canvas *canvas, const char *path) {
+    GUARD_BEGIN
+    if (!canvas || !path) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    const uint8_t *bgra = nullptr;
+    size_t len = 0;
+    TRY(draw_canvas_map_host(canvas, &bgra, &len));
+    std::vector<uint8_t> rgba(len); // app/mod.rs:347-352, as in draw_canvas_export_png
+    for (size_t i = 0; i + 3 < len; i += 4) {
+        rgba[i] = bgra[i + 2]; rgba[i + 1] = bgra[i + 1]; rgba[i + 2] = bgra[i]; rgba[i + 3] = bgra[i + 3];
+    }
+    // write_img hands stbi_write_jpg `width * PIXEL_BYTES` where it takes the quality (app/mod.rs:371-377)
+    const size_t quality = canvas->width * 4;
+    return draw_image_write_jpg(path, rgba.data(), (uint32_t)canvas->width, (uint32_t)canvas->height, 4, (int)std::min<size_t>(quality, 1 << 20));
+    GUARD_END
+}
+
 int draw_canvas_stream_wait(draw_canvas *canvas, void *cuda_stream) {
     GUARD_BEGIN
     if (!canvas) return fail(DRAW_ERR_INVALID_ARGUMENT, "canvas is NULL");

@@ -232,6 +232,9 @@ int draw_canvas_bind_external(draw_canvas *canvas, void *color_dev, void *depth_
 /* Application::export_frame_as(Png) (app/mod.rs:316-360) without the file dialog: waits for the frame, swaps B and R
  * (the frame is BGRA, the file RGBA with the pad byte as alpha) and writes it with draw_image_write_png. */
 int draw_canvas_export_png(draw_canvas *canvas, const char *path);
+/* Application::export_frame_as(Jpeg): the same swap, then draw_image_write_jpg with the quality the reference ends up
+ * passing — width * 4, which stbi_write_jpg clamps to 100 (app/mod.rs:362-378). */
+int draw_canvas_export_jpeg(draw_canvas *canvas, const char *path);
 /* Enqueue on an existing CUDA stream (a cudaStream_t passed as void*); NULL = own stream. */
 int draw_canvas_set_stream(draw_canvas *canvas, void *cuda_stream);
 /* Device-side join: makes cuda_stream (a cudaStream_t passed as void*) wait for everything enqueued so far
@@ -280,15 +283,21 @@ int draw_flags_wait(const void *flags_dev, uint32_t n_flags, uint32_t value, voi
 typedef int (*draw_image_loader)(const char *path, void *user, uint8_t **out_pixels, uint32_t *out_w,
                                  uint32_t *out_h, uint32_t *out_components);
 int draw_object_load_obj(const char *path, draw_image_loader loader, void *user, draw_object **out);
-/* TextureMap::load_from_file (scene/mod.rs:174-202) for the lossless format among the reference's assets: decodes
- * a PNG file (RGB, RGBA or palette; 8/16 bits; non-interlaced) to width*height*components bytes, components 3 or 4,
- * row 0 = top — the bytes stb_image returns for the same file.  Other formats (JPEG is lossy and decoder-dependent)
- * fail with DRAW_ERR_INVALID_ARGUMENT.  The buffer is malloc()ed; release it with draw_image_free. */
+/* TextureMap::load_from_file (scene/mod.rs:174-202) for the two formats among the reference's assets: decodes a PNG
+ * file (RGB, RGBA or palette; 8/16 bits; non-interlaced) or a JPEG file (three components, baseline or progressive
+ * Huffman; stb_image's IDCT / upsampling / colour arithmetic, draw_b200/csrc/jpeg_decode.cpp) to
+ * width*height*components bytes, components 3 or 4, row 0 = top.  Other formats fail with
+ * DRAW_ERR_INVALID_ARGUMENT.  The buffer is malloc()ed; release it with draw_image_free. */
 int draw_image_load(const char *path, uint8_t **out_pixels, uint32_t *out_w, uint32_t *out_h, uint32_t *out_components);
 void draw_image_free(uint8_t *pixels);
 /* stbi_write_png in Application::write_img (app/mod.rs:362-378): writes width*height*components bytes (components 3
  * or 4, row 0 = top) as a PNG file.  Lossless: the file decodes to exactly the bytes given. */
 int draw_image_write_png(const char *path, const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t components);
+/* stbi_write_jpg in Application::write_img: width*height*components bytes (components 3 or 4; a fourth byte is
+ * ignored) as a baseline JFIF file.  quality as stbi_write_jpg reads it: 0 means 90, values are clamped to 1..100;
+ * only qualities above 90 (no chroma subsampling — all the reference's export reaches) are written, others fail with
+ * DRAW_ERR_INVALID_ARGUMENT.  Lossy: see draw_b200/csrc/jpeg_encode.cpp for what is and is not pinned. */
+int draw_image_write_jpg(const char *path, const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t components, int quality);
 /* draw_image_load as a draw_image_loader callback (user is ignored), for draw_object_load_obj. */
 int draw_image_loader_builtin(const char *path, void *user, uint8_t **out_pixels, uint32_t *out_w, uint32_t *out_h,
                               uint32_t *out_components);

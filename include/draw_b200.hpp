@@ -214,6 +214,7 @@ class Canvas {
         if (clipping_rect) r = {clipping_rect->x0, clipping_rect->y0, clipping_rect->x1, clipping_rect->y1};
         check(draw_canvas_draw_triangles(h_, v.data(), n_triangles, texture.handle(), clipping_rect ? &r : nullptr));
     }
+    void export_jpeg(const std::string &path) { check(draw_canvas_export_jpeg(h_, path.c_str())); } // app/mod.rs:316, Jpeg
     void export_png(const std::string &path) { check(draw_canvas_export_png(h_, path.c_str())); } // app/mod.rs:316
     void sync() { check(draw_canvas_sync(h_)); }
     draw_canvas *handle() const { return h_; }

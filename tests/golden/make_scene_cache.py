@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Generate the committed scene fixtures under tests/golden/scenes/ from the reference's assets.
 
-Runs HERE (needs /root/reference/models and PIL); the GPU box only reads the generated files.
+Runs HERE (needs /root/reference/models, PIL for the PNGs' cross-check and the built library for the JPEG); the GPU box only reads the generated files.
 Loader = oracle/obj_loader.py, the numpy restatement of object.rs:106-454.  Re-run after any
 loader change:  python tests/golden/make_scene_cache.py [--ref /root/reference]
 """
@@ -29,6 +29,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden", "scenes"))
+    ap.add_argument("--only", default=None, help="write just this scene (e.g. c1_lemur_airplane)")
     args = ap.parse_args()
     models = os.path.join(args.ref, "models")
     os.makedirs(args.out, exist_ok=True)
@@ -41,7 +42,9 @@ def main():
     soldier = load("soldier1/soldier1.obj")
     skeleton = load("skeleton/fgc_skeleton.obj")
     dungeon = [to_model(o) for o in obj_loader.load_from_directory(os.path.join(models, "dungeon_set"))]
-    jpg = obj_loader.load_image(os.path.join(models, "airplane", "11804_Airplane_diff.jpg"))
+    # the one JPEG among the assets: decoded by the library (draw_b200/csrc/jpeg_decode.cpp, stb_image's arithmetic)
+    import draw_b200
+    jpg = draw_b200.load_image(os.path.join(models, "airplane", "11804_Airplane_diff.jpg"))
     airplane = synthetic.airplane_standin(jpg)
 
     scenes = {
@@ -53,14 +56,17 @@ def main():
         "c4_dungeon": dungeon,
     }
     for name, objs in scenes.items():
+        if args.only and name != args.only:
+            continue
         path = os.path.join(args.out, name + ".npz")
         scene_cache.save(path, objs)
         tris = sum(o.triangle_count() for o in objs)
         verts = sum(o.vertices.shape[0] for o in objs)
         print(f"{name}: {len(objs)} objects, {tris} triangles, {verts} vertices, "
               f"{os.path.getsize(path) / 1e6:.2f} MB")
-    np.save(os.path.join(os.path.dirname(args.out), "c4_camera_path.npy"), synthetic.flythrough_camera(120))
-    np.save(os.path.join(os.path.dirname(args.out), "orbit_camera_path.npy"), synthetic.orbit_camera(64))
+    if not args.only:
+        np.save(os.path.join(os.path.dirname(args.out), "c4_camera_path.npy"), synthetic.flythrough_camera(120))
+        np.save(os.path.join(os.path.dirname(args.out), "orbit_camera_path.npy"), synthetic.orbit_camera(64))
 
 
 if __name__ == "__main__":

@@ -80,3 +80,24 @@ def test_export_png_is_the_frame_with_b_and_r_swapped(tmp_path):
     c.export_png(p)
     frame = c.as_bytes_slice()
     assert np.array_equal(draw_b200.load_image(p), frame[..., [2, 1, 0, 3]])
+
+
+def test_export_jpeg_decodes_to_the_frame(tmp_path):
+    """draw_canvas_export_jpeg = Application::export_frame_as(Jpeg) (app/mod.rs:316-378): the quality the reference ends
+    up with is 100 (it passes width * 4, clamped), so the file decodes — with the library's own decoder — to within the
+    rounding of a quantiser-1 DCT round trip of the frame's R, G, B."""
+    import numpy as np
+    import draw_b200
+    from conftest import load_scene
+    s, c = draw_b200.Scene(401, 299), draw_b200.Canvas(401, 299)
+    c.init_depth(100000.0)
+    for o in load_scene("c1_lemur_airplane"):
+        s.add_obj(o)
+    s.render(c)
+    p = str(tmp_path / "frame.jpg")
+    c.export_jpeg(p)
+    frame = c.as_bytes_slice()
+    got = draw_b200.load_image(p)
+    assert got.shape == (299, 401, 3)
+    d = np.abs(got.astype(int) - frame[..., [2, 1, 0]].astype(int))
+    assert d.max() <= 4 and d.mean() < 0.6

@@ -74,10 +74,10 @@ def test_rejects_what_the_reference_rejects(tmp_path):
     PIL.fromarray(_noise(8, 8, 1, 1)[..., 0], "L").save(g)
     with pytest.raises(N.DrawError):
         _lib_decode(g)                      # 1 component: `unreachable!()` in the reference (scene/mod.rs:187)
-    j = str(tmp_path / "x.jpg")
-    PIL.fromarray(_noise(8, 8, 3, 2), "RGB").save(j)
+    b = str(tmp_path / "x.bmp")
+    PIL.fromarray(_noise(8, 8, 3, 2), "RGB").save(b)
     with pytest.raises(N.DrawError):
-        _lib_decode(j)                      # JPEG is left to the caller's loader
+        _lib_decode(b)                      # formats other than PNG and JPEG are left to the caller's loader
     with pytest.raises(N.DrawError):
         _lib_decode(str(tmp_path / "missing.png"))
     bad = tmp_path / "trunc.png"
