@@ -42,6 +42,15 @@ struct CtaTrace {
     }
 };
 
+// Storage index of the opaque record with this slot number (device_types.h: SLOT_STRIDE).  record_index reads the
+// table through the read-only path (kernels after k_front); record_index_cg is for k_front itself, which writes it.
+__device__ __forceinline__ uint32_t record_index(const FrameDev &W, uint32_t slot) {
+    return __ldg(W.block_loc + (slot >> SLOT_SHIFT)) + (slot & (SLOT_STRIDE - 1u));
+}
+__device__ __forceinline__ uint32_t record_index_cg(const FrameDev &W, uint32_t slot) {
+    return __ldcg(W.block_loc + (slot >> SLOT_SHIFT)) + (slot & (SLOT_STRIDE - 1u));
+}
+
 #define FADD(a, b) __fadd_rn((a), (b))
 #define FSUB(a, b) __fsub_rn((a), (b))
 #define FMUL(a, b) __fmul_rn((a), (b))

@@ -30,6 +30,9 @@ constexpr int TILE_W = DRAW_TILE_W, TILE_H = DRAW_TILE_H, REGION = 16;
 #endif
 constexpr int SMALL_AREA = DRAW_SMALL_AREA, MEDIUM_AREA = DRAW_MEDIUM_AREA;
 constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
+// Opaque records: slot number = block * SLOT_STRIDE + number inside k_front's 128-triangle block (at most 4 records per
+// triangle); storage index = FrameDev::block_loc[block] + number inside the block (record_index, device_math.cuh).
+constexpr uint32_t SLOT_SHIFT = 9, SLOT_STRIDE = 1u << SLOT_SHIFT;
 constexpr unsigned long long KEY_EMPTY = ~0ull;
 #ifndef DRAW_TILE_THREADS
 #define DRAW_TILE_THREADS 256
@@ -206,7 +209,7 @@ struct FrameDev {
                                 // + counters[CNT_BUCKETS + b]), bucket 0 the heaviest [COST_BUCKETS * bucket_cap]
     uint32_t bucket_cap;        // tiles + TILE_EXTRA_ITEMS: any one bucket can hold every item
     uint32_t *empty_tiles;      // tiles with nothing to draw as x | y << 10 [n_coarse]
-    unsigned long long *scan_desc; // P1 chained-scan descriptors [ceil(n_triangles / 256)]
+    uint32_t *block_loc;        // where the records of k_front's 128-triangle block b start in rrec / prep / srec [ceil(n_triangles / 128)]
     uint32_t rec_cap, refs_cap;
     uint32_t *tile_cycles;      // debug: SM cycles spent by each tile's CTA (null = off) [n_coarse]
     uint4 *trace;               // debug: one record per CTA of every frame kernel (device_math.cuh: CtaTrace), null = off

@@ -11,8 +11,8 @@
 //   ---- barrier ----
 //   P1  per triangle  coalesced index loads, packed gathers, back-face cull (:1016-1027), lateral reject + near/far
 //                     clip (:43-90, :662-746), snap + bbox + zero-area cull (canvas.rs:585-666), draw-order-
-//                     preserving slot allocation (warp prefix sums + single-pass chained scan with decoupled look-
-//                     back over 128-triangle blocks taken by ticket), record + prepared record + shading record
+//                     preserving slot numbers (block index * SLOT_STRIDE + prefix sum inside the block) with dense
+//                     storage reserved by one atomic per block, record + prepared record + shading record
 //                     write, and BINNING of the block's records by the CTA that made them, the (record, tile) pairs of
 //                     the block spread evenly over its threads: exact can-it-cover test per tile (rect_may_cover),
 //                     class by the bbox area inside the tile; medium / small references are appended to the frame-
@@ -110,8 +110,6 @@ __device__ __forceinline__ void phase_vertex(const FrameUniforms &U, const Scene
         W.ms_weight[t] = 0;
     }
     if (gtid < (uint32_t)CNT_BARRIER) W.counters[gtid] = 0; // everything but the barrier word
-    const uint32_t n_desc = (S.n_triangles + FRONT_THREADS - 1) / FRONT_THREADS;
-    for (uint32_t t = gtid; t < n_desc; t += gsize) W.scan_desc[t] = 0ull;
 
     const uint32_t n = S.n_vertices, n4 = n & ~3u;
     if (n <= gsize) {
@@ -344,7 +342,7 @@ __device__ __forceinline__ void gather_clip_vert(const SceneDev &S, const FrameD
 // index (opaque: the four slots k_front reserved in draw order; transparent: the ordered slots 4*ordinal + k).
 // Returns the bit mask of the emission indices that survive set-up; their bboxes are returned in bbx / bby.
 __device__ __noinline__ uint32_t clip_triangle(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, uint32_t tri,
-                                               const uint32_t vi[3], uint32_t material, bool transparent, uint32_t slot_base,
+                                               const uint32_t vi[3], uint32_t material, bool transparent, uint32_t loc_base,
                                                uint32_t bbx[4], uint32_t bby[4]) {
     ClipTri in;
 #pragma unroll
@@ -368,7 +366,7 @@ __device__ __noinline__ uint32_t clip_triangle(const FrameUniforms &U, const Sce
             dep[c] = out[k].v[c].a[0];
         }
         if (!setup_raster(U, sx, sy, dep, tri * 4u + (uint32_t)k, r)) continue;
-        const uint32_t slot = slot_base + (uint32_t)k;
+        const uint32_t slot = loc_base + (uint32_t)k;   // where the record is stored (its slot number is the caller's slot + k)
         if (!transparent && slot >= W.rec_cap) continue; // overflow (flagged by the caller): the host re-renders
         ShadeRec s;
         shade_from_clip(out[k], material, s);
@@ -486,10 +484,6 @@ __device__ __forceinline__ void emit_pair(const FrameDev &W, const PairClass &c,
 // ------------------------------------------------------------------------------------------
 // P1 : per triangle
 // ------------------------------------------------------------------------------------------
-// Descriptor of the chained scan over 128-triangle blocks: status in the top 2 bits, count in the rest.
-#define DESC_AGGREGATE (1ull << 62)
-#define DESC_PREFIX (2ull << 62)
-#define DESC_VALUE ((1ull << 62) - 1)
 
 // A record to bin: bbox, slot (bit 31: transparent), and where its edge functions are: in sh.tri[tri_idx] (the
 // record of an unclipped triangle, staged by the thread that made it) or, for the outputs of the clip path
@@ -503,6 +497,7 @@ struct BinJob {
 // whose (record, tile) pairs are split evenly over the whole grid in a phase of its own.
 constexpr uint32_t HUGE_TILES = 32;
 constexpr int MAX_JOBS = 4 * FRONT_THREADS;
+static_assert(SLOT_STRIDE == 4u * FRONT_THREADS, "a block of FRONT_THREADS triangles numbers at most SLOT_STRIDE records");
 constexpr uint32_t NO_TRI = 0xFFFFFFFFu, DIVERTED = 0xFFFFFFFEu; // BinJob::tri_idx: edges in global memory / job moved to the huge queue
 constexpr int TRI_WORDS = 13; // BinTri as words: odd stride, conflict-free for neighbouring jobs
 struct FrontShared {
@@ -586,7 +581,8 @@ __device__ __forceinline__ PairEval eval_pair(const FrameUniforms &U, const Fram
         for (int k = 0; k < 3; k++) { t.ecx[k] = w[k]; t.ecy[k] = w[3 + k]; t.ek1[k] = w[6 + k]; t.ek2[k] = w[9 + k]; }
         t.flags = __float_as_uint(w[12]);
     } else {
-        t = bin_tri_load((transparent ? W.t_prep : W.prep) + e.slot); // written by this CTA before the barrier
+        // written by this CTA before the barrier; an opaque record of this block is stored at sh.base + its number in the block
+        t = bin_tri_load(transparent ? W.t_prep + e.slot : W.prep + (sh.base + (e.slot & (SLOT_STRIDE - 1u))));
     }
     e.c = classify_pair(U, t, tr.x0, tr.x1, tr.y0, tr.y1, e.tx, e.ty, transparent);
     return e;
@@ -736,11 +732,8 @@ __device__ __forceinline__ void phase_huge(const FrameUniforms &U, const FrameDe
         const bool transparent = (q.z >> 31) != 0;
         const uint32_t slot = q.z & 0x7FFFFFFFu;
         const TileRange tr = tile_range(U, q.x, q.y);
-        const BinTri t = bin_tri_load((transparent ? W.t_prep : W.prep) + slot);
-        if (j + n_warps < n_jobs) { // the next record's header, and its edge functions on their way to L2 / L1
-            q = __ldcg(&W.huge_jobs[j + n_warps]);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(((q.z >> 31) ? W.t_prep : W.prep) + (q.z & 0x7FFFFFFFu)));
-        }
+        const BinTri t = bin_tri_load(transparent ? W.t_prep + slot : W.prep + record_index_cg(W, slot));
+        if (j + n_warps < n_jobs) q = __ldcg(&W.huge_jobs[j + n_warps]); // the next record's header
 #pragma unroll 1
         for (int chunk = 0; chunk < tr.n_rows; chunk += 32 * GROUPS) {
             int a[GROUPS];
@@ -835,16 +828,15 @@ __device__ __forceinline__ void phase_huge(const FrameUniforms &U, const FrameDe
     }
 }
 
-// Record slots are handed out in draw order (stable compaction): slot order == draw order, which is
-// what lets k_tile break depth ties by comparing slots.  Inside a block: prefix sums over the per-thread
-// output counts (0, 1, or 4 for a triangle to clip).  Across blocks: single-pass chained scan with decoupled
-// look-back; blocks are taken by ticket so that the chain follows the order in which blocks start, and every
-// block that has a ticket belongs to a resident CTA (cooperative launch): the look-back cannot deadlock.
+// Record slots are numbered in draw order: slot order == draw order, which is what lets k_tile break depth ties by
+// comparing slots.  Inside a block: prefix sums over the per-thread output counts (0, 1, or 4 for a triangle to
+// clip).  Across blocks: block b's numbers start at b * SLOT_STRIDE — no block waits for another (a chained scan
+// with decoupled look-back, the first design, cost C5 a quarter of the phase in waiting) — and the records are
+// stored densely wherever the block's atomicAdd put them (FrameDev::block_loc).
 __device__ __forceinline__ void phase_setup(const FrameUniforms &U, const SceneDev &S, const FrameDev &W, FrontShared &sh) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n_blocks = (S.n_triangles + FRONT_THREADS - 1) / FRONT_THREADS;
     // A CTA's first block is its own index (no round trip); the ticket counter hands out the blocks beyond the grid.
-    // Every block below a given one is therefore held by a resident CTA or already done: the look-back cannot deadlock.
     bool first_block = true;
     while (true) {
         uint32_t bid = blockIdx.x;
@@ -929,7 +921,12 @@ __device__ __forceinline__ void phase_setup(const FrameUniforms &U, const SceneD
         }
         if (lane == 31) sh.warp_tot[warp] = incl;
         __syncthreads();
-        // ---- chained scan across blocks (warp 0) ------------------------------------------------------
+        // ---- the block's records: slot numbers and storage ------------------------------------------------
+        // Slot numbers order the frame's records by draw order (ties in depth go to the smaller slot): block b owns
+        // the numbers [b * SLOT_STRIDE, (b + 1) * SLOT_STRIDE) and hands them out by prefix sum, so no block waits for
+        // another one.  Storage is dense: one atomicAdd per block reserves its records' places, FrameDev::block_loc[b]
+        // remembers where they start, and a record is found at block_loc[slot / SLOT_STRIDE] + slot % SLOT_STRIDE
+        // (record_index, device_math.cuh).
         if (warp == 0) {
             uint32_t wt = lane < FRONT_THREADS / 32 ? sh.warp_tot[lane] : 0u;
             uint32_t wi = wt;
@@ -940,42 +937,18 @@ __device__ __forceinline__ void phase_setup(const FrameUniforms &U, const SceneD
             }
             const uint32_t total = __shfl_sync(FULL, wi, 31);
             if (lane < FRONT_THREADS / 32) sh.warp_tot[lane] = wi - wt; // exclusive offset of each warp
-            volatile unsigned long long *desc = reinterpret_cast<volatile unsigned long long *>(W.scan_desc);
-            uint32_t base = 0;
-            if (bid == 0) {
-                if (lane == 0) desc[0] = DESC_PREFIX | total;
-            } else {
-                if (lane == 0) desc[bid] = DESC_AGGREGATE | total;
-                // look back 32 predecessors at a time until one of them has its inclusive prefix
-                int look = (int)bid - 1;
-                while (true) {
-                    const int j = look - (int)lane;
-                    unsigned long long d = j >= 0 ? desc[j] : DESC_PREFIX;
-                    // wait until every descriptor in the window up to the first PREFIX is published
-                    const uint32_t is_prefix = __ballot_sync(FULL, (d >> 62) == 2);
-                    const uint32_t not_ready = __ballot_sync(FULL, (d >> 62) == 0);
-                    const int first_prefix = is_prefix ? __ffs(is_prefix) - 1 : 32;
-                    const uint32_t window = first_prefix >= 31 ? FULL : ((2u << first_prefix) - 1u);
-                    if (not_ready & window) continue; // spin
-                    uint32_t v = (lane <= (uint32_t)first_prefix && j >= 0) ? (uint32_t)(d & DESC_VALUE) : 0u;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-                    base += v;
-                    if (first_prefix < 32) break;
-                    look -= 32;
-                }
-                if (lane == 0) desc[bid] = DESC_PREFIX | (unsigned long long)(base + total);
-            }
             if (lane == 0) {
+                const uint32_t base = total ? atomicAdd(&W.counters[CNT_RECORDS], total) : 0u; // the counter ends at the frame's record count
                 sh.base = base;
-                if (bid == n_blocks - 1) W.counters[CNT_RECORDS] = base + total; // total record count of the frame
+                W.block_loc[bid] = base;
             }
         }
         __syncthreads();
 
         if (stamp) sub[2] = (uint32_t)global_timer_ns();
-        const uint32_t slot0 = sh.base + sh.warp_tot[warp] + incl - n_out;
-        if (n_out && slot0 + n_out > W.rec_cap) {
+        const uint32_t local0 = sh.warp_tot[warp] + incl - n_out;          // < SLOT_STRIDE: at most four records per thread
+        const uint32_t slot0 = bid * SLOT_STRIDE + local0, loc0 = sh.base + local0;
+        if (n_out && loc0 + n_out > W.rec_cap) {
             atomicOr(&W.counters[CNT_OVERFLOW], OVERFLOW_RECORDS); // the host re-renders the frame with larger buffers
             alive = false;
             clipped = false;
@@ -983,12 +956,12 @@ __device__ __forceinline__ void phase_setup(const FrameUniforms &U, const SceneD
 
         // ---- unclipped survivors: raster, prepared and shading record ---------------------------------
         const bool single = alive && !clipped;
-        const uint32_t slot = transparent ? tslot * 4u : slot0;
+        const uint32_t slot = transparent ? tslot * 4u : slot0, loc = transparent ? tslot * 4u : loc0; // transparent records sit at their slot
         if (single) {
             PrepRec p;
             make_prep(r, p);
-            store_raster((transparent ? W.t_rrec : W.rrec) + slot, r);
-            store_prep((transparent ? W.t_prep : W.prep) + slot, p);
+            store_raster((transparent ? W.t_rrec : W.rrec) + loc, r);
+            store_prep((transparent ? W.t_prep : W.prep) + loc, p);
             { // the edge functions stay on chip for the binning below
                 float *w = sh.tri[threadIdx.x];
 #pragma unroll
@@ -1009,11 +982,11 @@ __device__ __forceinline__ void phase_setup(const FrameUniforms &U, const SceneD
             }
             s.material = material;
             s.pad[0] = s.pad[1] = 0;
-            store_shade((transparent ? W.t_srec : W.srec) + slot, s);
+            store_shade((transparent ? W.t_srec : W.srec) + loc, s);
         }
         // ---- triangles that straddle the near or far plane (rare, register-hungry: out of line) -------
         uint32_t kept = single ? 1u : 0u, bbx[4] = {r.bbx, 0, 0, 0}, bby[4] = {r.bby, 0, 0, 0};
-        if (clipped) kept = clip_triangle(U, S, W, tri, vi, material, transparent, slot, bbx, bby);
+        if (clipped) kept = clip_triangle(U, S, W, tri, vi, material, transparent, loc, bbx, bby);
         if (stamp) sub[3] = (uint32_t)global_timer_ns();
 
         // ---- binning: the block's records become jobs in shared memory, their (record, tile) pairs are

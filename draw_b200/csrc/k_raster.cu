@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, RASTER_MIN_CTAS) k_raster(
         const uint32_t tile_x = ref.y & (MAX_TILES_X - 1), tile_y = (ref.y >> 10) & (MAX_TILES_Y - 1);
         const uint32_t part = (ref.y >> 21) & 3u, parts = ((ref.y >> 23) & 3u) + 1u; // this entry's share of the blocks
         const uint32_t page = tile_y * U.tiles_x + tile_x;
-        const uint4 *q = reinterpret_cast<const uint4 *>(W.prep + ref.x);
+        const uint4 *q = reinterpret_cast<const uint4 *>(W.prep + record_index(W, ref.x));
         const uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4), q5 = __ldg(q + 5),
                     q6 = __ldg(q + 6);
         TriRegs t;
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, RASTER_MIN_CTAS) k_raster(
             const uint32_t i_next = i + n_warps;
             const uint2 ref_next = i_next < n_medium ? __ldg(W.m_refs + i_next) : ref;
             if (i_next < n_medium && lane == 0) {
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(W.prep + ref_next.x));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(W.prep + record_index(W, ref_next.x)));
             }
             medium_ref(ref);
             ref = ref_next;
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, RASTER_MIN_CTAS) k_raster(
         const uint2 ref = __ldg(W.s_refs + i);
         const uint32_t tile_x = ref.y & (MAX_TILES_X - 1), tile_y = (ref.y >> 10) & (MAX_TILES_Y - 1);
         const uint32_t page = tile_y * U.tiles_x + tile_x;
-        const RasterRec r = load_raster(W.rrec + ref.x); // 48 bytes; the edge set-up is cheaper than reading the PrepRec
+        const RasterRec r = load_raster(W.rrec + record_index(W, ref.x)); // 48 bytes; the edge set-up is cheaper than reading the PrepRec
         PrepRec p;
         make_prep(r, p);
         const TriRegs t = tri_from_prep(p);

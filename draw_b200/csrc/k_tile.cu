@@ -50,13 +50,16 @@ static_assert(PREP_WORDS == 28 && (STAGE_STRIDE & 1) == 1 && offsetof(PrepRec, x
 
 // Copies n prepared records into shared memory: one 16-byte load per thread (8 threads per record, the
 // eighth idle), so a chunk of 64 is two loads per thread of a 256-thread CTA.
-__device__ __forceinline__ void stage_copy(float (*staged)[STAGE_STRIDE], const PrepRec *__restrict__ prep,
+// block_loc: the opaque records' slot -> storage table (record_index, device_math.cuh); nullptr for the transparent
+// records, which are stored at their slot.  The staged copy keeps the slot number (the order of the draws).
+__device__ __forceinline__ void stage_copy(float (*staged)[STAGE_STRIDE], const PrepRec *__restrict__ prep, const uint32_t *__restrict__ block_loc,
                                            const uint32_t *refs, uint32_t ref_stride, uint32_t n, int tid) {
     for (uint32_t i = (uint32_t)tid; i < n * 8u; i += TILE_THREADS) {
         const uint32_t k = i >> 3, q = i & 7u;
         if (q == 7u) continue;
         const uint32_t slot = refs[k * ref_stride];
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(prep + slot) + q);
+        const uint32_t at = block_loc ? __ldg(block_loc + (slot >> SLOT_SHIFT)) + (slot & (SLOT_STRIDE - 1u)) : slot;
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(prep + at) + q);
         float *d = staged[k] + 4 * q;
         d[0] = __uint_as_float(v.x); d[1] = __uint_as_float(v.y); d[2] = __uint_as_float(v.z);
         d[3] = q == 6u ? __uint_as_float(slot) : __uint_as_float(v.w);
@@ -65,7 +68,7 @@ __device__ __forceinline__ void stage_copy(float (*staged)[STAGE_STRIDE], const 
 // Window filter: keeps the references whose bbox meets the window (only their bbox quad is read).
 // Returns the number kept; cand[] is valid after the call (ends with a barrier).
 __device__ __forceinline__ uint32_t filter_refs(const uint32_t *__restrict__ list, uint32_t list_stride, uint32_t count,
-                                                const PrepRec *__restrict__ prep, uint32_t *cand, uint32_t *s_count,
+                                                const PrepRec *__restrict__ prep, const uint32_t *__restrict__ block_loc, uint32_t *cand, uint32_t *s_count,
                                                 float wx0f, float wx1f, float wy0f, float wy1f, int tid) {
     __syncthreads(); // cand / s_count may still be in use by the previous segment
     if (tid == 0) *s_count = 0;
@@ -77,7 +80,7 @@ __device__ __forceinline__ uint32_t filter_refs(const uint32_t *__restrict__ lis
         uint32_t slot = 0;
         if (i < count) {
             slot = list[i * list_stride];
-            const uint4 bb = __ldg(reinterpret_cast<const uint4 *>(prep + slot) + 5); // x0 x1 y0 y1
+            const uint4 bb = __ldg(reinterpret_cast<const uint4 *>(prep + (__ldg(block_loc + (slot >> SLOT_SHIFT)) + (slot & (SLOT_STRIDE - 1u)))) + 5); // x0 x1 y0 y1
             keep = !(__uint_as_float(bb.y) < wx0f || __uint_as_float(bb.x) > wx1f ||
                      __uint_as_float(bb.w) < wy0f || __uint_as_float(bb.z) > wy1f);
         }
@@ -223,14 +226,14 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
             const uint32_t *refs = W.list_refs + l_begin + seg;
             uint32_t n_refs = seg_n;
             if (windowed) {
-                n_refs = filter_refs(refs, 1u, seg_n, prep, cand, &s_cand_count, wx0f, wx1f, wy0f, wy1f, tid);
+                n_refs = filter_refs(refs, 1u, seg_n, prep, W.block_loc, cand, &s_cand_count, wx0f, wx1f, wy0f, wy1f, tid);
                 refs = cand;
             }
 #pragma unroll 1
             for (uint32_t base = 0; base < n_refs; base += CHUNK) {
                 const uint32_t n = min((uint32_t)CHUNK, n_refs - base);
                 __syncthreads();
-                stage_copy(staged, prep, refs + base, 1u, n, tid);
+                stage_copy(staged, prep, W.block_loc, refs + base, 1u, n, tid);
                 __syncthreads();
                 if (page_pending) merge_page();
 #pragma unroll 1
@@ -355,10 +358,15 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
 #pragma unroll 1
     for (int q = tid; q < n_win; q += TILE_THREADS) {
         const int x = wx0 + (q & (ww - 1)), y = wy0 + (q >> ww_shift);
-        const uint32_t slot = (uint32_t)keys[(y - ty0) * TILE_W + (x - tx0)];
+        const int p = (y - ty0) * TILE_W + (x - tx0);
+        const uint32_t slot = (uint32_t)keys[p];
         if (slot == NO_SLOT) continue;
-        const char *sp = reinterpret_cast<const char *>(W.srec + slot);
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(prep + slot));
+        // the winner is decided: from here on the pixel carries where its record is stored instead of the slot number
+        // (own pixel in both loops: no barrier)
+        const uint32_t at = record_index(W, slot);
+        reinterpret_cast<uint32_t *>(keys + p)[0] = at;
+        const char *sp = reinterpret_cast<const char *>(W.srec + at);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(prep + at));
         asm volatile("prefetch.global.L1 [%0];" ::"l"(sp));
         asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + sizeof(ShadeRec) - 16));
     }
@@ -366,13 +374,13 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
     for (int q = tid; q < n_win; q += TILE_THREADS) { // the window's pixels
         const int x = wx0 + (q & (ww - 1)), y = wy0 + (q >> ww_shift);
         const int p = (y - ty0) * TILE_W + (x - tx0);
-        const uint32_t slot = (uint32_t)keys[p];
+        const uint32_t at = (uint32_t)keys[p]; // NO_SLOT, or the storage index written above
         uint32_t c = 155u | (186u << 8) | (255u << 16) | (255u << 24); // azul_bb, pad 255 (canvas.rs:131)
         float d = depth_max;
         uint32_t id = NO_SLOT;
-        if (slot != NO_SLOT) {
+        if (at != NO_SLOT) {
             float op;
-            c = shade_pixel_prep<true>(mats, S.texels, u8tab, prep + slot, W.srec + slot, (float)x, (float)y, &d, &op, &id) | (255u << 24);
+            c = shade_pixel_prep<true>(mats, S.texels, u8tab, prep + at, W.srec + at, (float)x, (float)y, &d, &op, &id) | (255u << 24);
         }
         colour[p] = c;
         keys[p] = ((unsigned long long)__float_as_uint(d) << 32) | id; // own pixel: no sync needed
@@ -446,7 +454,7 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
             for (uint32_t base = 0; base < n_ord; base += CHUNK) {
                 const uint32_t n = min((uint32_t)CHUNK, n_ord - base);
                 __syncthreads(); // cand is complete / staged of the previous chunk is no longer read
-                stage_copy(staged, W.t_prep, cand + base, 1u, n, tid);
+                stage_copy(staged, W.t_prep, nullptr, cand + base, 1u, n, tid);
                 __syncthreads();
 #pragma unroll 1
                 for (uint32_t k = 0; k < n; k++) {

@@ -167,7 +167,7 @@ struct draw_scene {
         DevBuf<float4> vA, vLH;
         DevBuf<uint32_t> l_count, t_count, l_offset, t_offset, ms_weight, list_refs, t_refs, counters, tile_cycles,
             tile_order, empty_tiles;
-        DevBuf<unsigned long long> scan_desc;
+        DevBuf<uint32_t> block_loc;
         DevBuf<RasterRec> rrec, trrec;
         DevBuf<PrepRec> prep, tprep;
         DevBuf<ShadeRec> srec, tsrec;
@@ -458,7 +458,7 @@ int ensure_work_buffers(draw_scene *s, draw_scene::WorkSet &ws, size_t n_tiles) 
     }
     TRY(ws.tile_order.reserve((size_t)COST_BUCKETS * (n_tiles + TILE_EXTRA_ITEMS)));
     TRY(ws.empty_tiles.reserve(n_tiles));
-    TRY(ws.scan_desc.reserve((size_t)d.n_triangles / 128 + 2)); // one descriptor per 128-triangle block (k_front.cu: FRONT_THREADS)
+    TRY(ws.block_loc.reserve((size_t)d.n_triangles / 128 + 2)); // one entry per 128-triangle block (k_front.cu: FRONT_THREADS)
     FrameDev &w = ws.work;
     w.vA = ws.vA.ptr; w.vLH = ws.vLH.ptr;
     w.rrec = ws.rrec.ptr; w.srec = ws.srec.ptr; w.prep = ws.prep.ptr;
@@ -473,7 +473,7 @@ int ensure_work_buffers(draw_scene *s, draw_scene::WorkSet &ws, size_t n_tiles) 
     w.tile_order = ws.tile_order.ptr;
     w.bucket_cap = (uint32_t)(n_tiles + TILE_EXTRA_ITEMS);
     w.empty_tiles = ws.empty_tiles.ptr;
-    w.scan_desc = ws.scan_desc.ptr;
+    w.block_loc = ws.block_loc.ptr;
     w.rec_cap = (uint32_t)s->rec_cap;
     w.refs_cap = (uint32_t)std::min(s->refs_cap, t_refs_cap == 1 ? s->refs_cap : t_refs_cap);
     w.tile_cycles = nullptr;
