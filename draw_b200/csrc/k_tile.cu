@@ -94,6 +94,47 @@ __device__ __forceinline__ uint32_t filter_refs(const uint32_t *__restrict__ lis
     return *s_count;
 }
 
+// Front-to-back order for a segment of a tile's large references (n <= CAND_CAP): the depth resolve does not depend on
+// the order the triangles are tested in (ties go to the smaller slot), but the early depth rejects do — with the
+// nearest triangles first, most of the others are turned away per block instead of per pixel.  Key = the smallest
+// vertex depth of the record (a lower bound of its depths) over the slot; bitonic sort in `scratch` (the tile's key
+// array, not in use before the end of phase A); the slots come back in cand[].  Ends with a barrier.
+constexpr uint32_t SORT_MIN_REFS = 16;
+__device__ __forceinline__ void sort_refs_front_to_back(const uint32_t *refs, uint32_t n, const PrepRec *__restrict__ prep,
+                                                        const uint32_t *__restrict__ block_loc, unsigned long long *scratch, uint32_t *cand,
+                                                        int tid) {
+    uint32_t n2 = 32;
+    while (n2 < n) n2 <<= 1;
+    for (uint32_t i = (uint32_t)tid; i < n2; i += TILE_THREADS) {
+        unsigned long long key = ~0ull;
+        if (i < n) {
+            const uint32_t slot = refs[i];
+            const uint4 *q = reinterpret_cast<const uint4 *>(prep + (__ldg(block_loc + (slot >> SLOT_SHIFT)) + (slot & (SLOT_STRIDE - 1u))));
+            const uint4 q4 = __ldg(q + 4), q6 = __ldg(q + 6); // .. da db | dc ..
+            const float zmin = fminf(fminf(__uint_as_float(q4.z), __uint_as_float(q4.w)), __uint_as_float(q6.x));
+            key = ((unsigned long long)depth_key(zmin) << 32) | slot;
+        }
+        scratch[i] = key;
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= n2; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = (uint32_t)tid; i < n2; i += TILE_THREADS) {
+                const uint32_t o = i ^ j;
+                if (o > i) {
+                    const unsigned long long a = scratch[i], b = scratch[o];
+                    if ((a > b) == ((i & k) == 0u)) {
+                        scratch[i] = b;
+                        scratch[o] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    for (uint32_t i = (uint32_t)tid; i < n; i += TILE_THREADS) cand[i] = (uint32_t)scratch[i];
+    __syncthreads();
+}
+
 __device__ __forceinline__ TriRegs tri_from_words(const float *w) {
     TriRegs t;
 #pragma unroll
@@ -180,6 +221,12 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
             zb[i] = depth_max;
             sl[i] = NO_SLOT;
         }
+        float lane_zmax = depth_max; // the largest of zb[]: kept up to date where zb[] changes, read by every block-level depth reject
+        auto refresh_zmax = [&]() {
+            lane_zmax = zb[0];
+#pragma unroll
+            for (int p = 1; p < PX; p++) lane_zmax = fmaxf(lane_zmax, zb[p]);
+        };
         // The tile's key page (k_raster's result): its loads are issued here, together with the stores that
         // leave it empty for the next frame, and consumed after the first chunk of large triangles has been
         // staged, so that the two L2 round trips overlap.  A lane's 4 pixels of a row are 32 contiguous bytes.
@@ -209,6 +256,7 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
                     }
             }
             page_pending = false;
+            refresh_zmax();
             // Leave the page empty for the next frame: after every lane of the warp has its keys (the loads
             // above are consumed), the warp's region — REGION_H rows of 128 bytes — is overwritten with whole
             // 128-byte lines, 8 lanes per row.
@@ -227,6 +275,10 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
             uint32_t n_refs = seg_n;
             if (windowed) {
                 n_refs = filter_refs(refs, 1u, seg_n, prep, W.block_loc, cand, &s_cand_count, wx0f, wx1f, wy0f, wy1f, tid);
+                refs = cand;
+            }
+            if (n_refs >= SORT_MIN_REFS && U.sort_large) {
+                sort_refs_front_to_back(refs, n_refs, prep, W.block_loc, keys, cand, tid);
                 refs = cand;
             }
 #pragma unroll 1
@@ -267,10 +319,7 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
                                 const float xm = cx >= 0.0f ? lo_x : hi_x, ym = cy >= 0.0f ? lo_y : hi_y;
                                 em[e] = FSUB(FADD(FADD(FMUL(cx, xm), FMUL(cy, ym)), s[S_EK1 + e]), s[S_EK2 + e]);
                             }
-                            float zmax = zb[0];
-#pragma unroll
-                            for (int p = 1; p < PX; p++) zmax = fmaxf(zmax, zb[p]);
-                            if (fmaf(em[2], g2, fmaf(em[1], g1, em[0] * g0)) * EARLYZ_SCALE > zmax) continue;
+                            if (fmaf(em[2], g2, fmaf(em[1], g1, em[0] * g0)) * EARLYZ_SCALE > lane_zmax) continue;
                         }
                         // edge values of the block's pixels (f > 0 after sign normalisation:
                         // alpha >= 0 <=> e >= 0, alpha > 0 <=> e > 0), coverage and early depth reject, branch-free
@@ -310,6 +359,7 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
                                 zb[p] = take ? d : zb[p];
                                 sl[p] = take ? slot : sl[p];
                             }
+                            refresh_zmax();
                         } else {
 #pragma unroll
                             for (int p = 0; p < PX; p++) {
@@ -321,6 +371,7 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
                                     sl[p] = slot;
                                 }
                             }
+                            refresh_zmax();
                         }
                     } else {
                         const TriRegs t = tri_from_words(s);
@@ -335,6 +386,7 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
                                 sl[p] = slot;
                             }
                         }
+                        refresh_zmax();
                     }
                 }
             }

@@ -282,6 +282,7 @@ struct Config {
     // grids; 0 = by scene size (set_launch_grids): with several frames in flight a kernel costs the pipeline its CTAs' residency
     int front_cps = std::max(0, env_int("DRAW_B200_FRONT_CPS", 0)); // k_front CTAs per SM
     int raster_ctas = std::max(0, env_int("DRAW_B200_RASTER_CTAS", 0));
+    int sort_large = env_int("DRAW_B200_SORT_LARGE", 1);   // k_tile: a tile's large references front to back (the early depth rejects bite sooner)
     int clear_first = env_int("DRAW_B200_CLEAR_FIRST", 0); // k_tile: empty-tile stores before (1) or after (0) a CTA's raster item
     int rec_cap = std::max(0, env_int("DRAW_B200_REC_CAP", 0));   // initial record / reference capacities (tests force overflows)
     int refs_cap = std::max(0, env_int("DRAW_B200_REFS_CAP", 0));
@@ -615,6 +616,7 @@ void fill_uniforms(draw_scene *s, const draw_canvas *c, FrameUniforms &U) {
     U.row_phase = c->row_phase % U.row_step;
     U.bar_base = 0; // set per work set by enqueue_frame
     U.clear_first = (uint32_t)g_cfg.clear_first;
+    U.sort_large = (uint32_t)g_cfg.sort_large;
     U.empty_tile_color = c->empty_tile_color ? 1u : 0u;
     U.status_host = c->h_status + (size_t)c->next_status_slot * N_STATUS_WORDS; // pinned, mapped: valid on the device (unified addressing)
     U.color = c->color();
