@@ -298,8 +298,6 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
                     if (lo_x > hi_x || lo_y > hi_y) continue;
                     const uint32_t flags = __float_as_uint(s[S_FLAGS]), slot = __float_as_uint(s[S_SLOT]);
                     if (!(flags & TRI_SLOW)) {
-                        // block-level reject at the best corner of the clipped block (exact, see rect_may_cover)
-                        if (!staged_may_cover(s, flags, lo_x, hi_x, lo_y, hi_y)) continue;
                         const float thr0 = (flags & 1u) ? -0.5f : 0.0f, thr1 = (flags & 2u) ? -0.5f : 0.0f,
                                     thr2 = (flags & 4u) ? -0.5f : 0.0f;
                         const float da = s[S_DA], db = s[S_DB], dc = s[S_DC];
@@ -321,6 +319,9 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
                             }
                             if (fmaf(em[2], g2, fmaf(em[1], g1, em[0] * g0)) * EARLYZ_SCALE > lane_zmax) continue;
                         }
+                        // block-level reject at the best corner of the clipped block (exact, see rect_may_cover); after the depth
+                        // reject: in an overdrawn tile most triangles are hidden, which is the cheaper thing to find out
+                        if (!staged_may_cover(s, flags, lo_x, hi_x, lo_y, hi_y)) continue;
                         // edge values of the block's pixels (f > 0 after sign normalisation:
                         // alpha >= 0 <=> e >= 0, alpha > 0 <=> e > 0), coverage and early depth reject, branch-free
                         float e0[PX], e1[PX], e2[PX];
