@@ -72,9 +72,9 @@ if d3:
       f"tile {ph['tile']:.1f}.  Round 1's seven launches for the same work: 108 us.")
 w("")
 
-w("## 2. Multi-GPU (torchrun, one rank per GPU; `r02_bench_c3_n8.json`, `r02_bench_c3_n4_*.json`, `r02_bench_c3_n2_*.json`)\n")
+w("## 2. Multi-GPU (torchrun, one rank per GPU; `r02_bench_c3_n2.json`, `_n4.json`, `_n8.json`: the driver's launch line, `tools/gpu_multi.sh`)\n")
 rows = []
-for n, f in ((2, "r02_bench_c3_n2.json"), (2, "r02_bench_c3_n2_first.json"), (4, "r02_bench_c3_n4.json"), (4, "r02_bench_c3_n4_before_row_search.json"), (8, "r02_bench_c3_n8.json")):
+for n, f in ((2, "r02_bench_c3_n2.json"), (4, "r02_bench_c3_n4.json"), (8, "r02_bench_c3_n8.json")):
     d = line(f)
     if d and not any(r[0] == n for r in rows):
         rows.append((n, d, f))
@@ -86,9 +86,9 @@ if rows:
     for n, d, f in rows:
         w(f"| {n} | {d['value']:.0f} | {d['value'] / base:.2f} | {d['e2e']['value']:.0f} | {d['e2e']['d2h_achieved_gbs']:.0f} / {d['e2e']['d2h_ceiling_gbs']:.0f} | `{f}` |")
     w("")
-    w("e2e does not scale past ~2 GPUs because the box's host side does not: the plain-copy ceiling (all ranks copying 33 MB frames to pinned "
-      "memory at once, no renderer involved) is ~57 GB/s for one GPU and ~90-110 GB/s for 2, 4 or 8 (one NUMA node, 32 vCPUs: "
-      "`nvidia-smi topo`), and the renderer's read-backs sit at that ceiling at every N.\n")
+    w("e2e does not scale with N because the box's host side does not: the plain-copy ceiling (all ranks copying 33 MB frames to pinned "
+      "memory at once, no renderer involved) is ~57 GB/s for one GPU and 70-140 GB/s for 2, 4 or 8 depending on the box the call landed on "
+      "(one NUMA node, 32 vCPUs: `nvidia-smi topo`), and the renderer's read-backs sit at that ceiling at every N.\n")
     w("Sort-first, ONE frame across the ranks (`sort_first` in the same lines; CUDA events around all frames, no host synchronisation in the "
       "loop; every entry `bit_exact: true` = composed frame equals the single-GPU frame):\n")
     w("| N | config | 1 GPU, frames back to back ms | 1 GPU, lone frame ms | p2p interleaved ms (x back-to-back / x lone) | NCCL interleaved | p2p stripes | NCCL stripes |")
@@ -106,10 +106,12 @@ if rows:
             out[-1] += f"{cell('p2p_interleaved')} | {cell('nccl_interleaved')} | {cell('p2p_stripes')} | {cell('nccl_stripes')} |"
     w("")
     w("What bounds sort-first: the front of the frame is replicated.  On C4 a rank's GPU work per frame is ~100 us of `k_front` + `k_raster` "
-      "(vertex phase, triangle set-up and near-plane clipping of all 13 k triangles; only binning shrinks with N) plus 1/N of ~240 us of `k_tile`; "
-      "the front of frame k+1 overlaps the tile kernel of frame k, so the time per frame tends to max(front, tile / N + flag hand-shake).  "
-      "On C5 (10 M triangles, 8K) the replicated triangle phase is 1.3 of a frame's 2.2 ms: SURVEY.md 8(d)'s HBM-roofline ceiling for 8 GPUs is "
-      "1.41 x; the NCCL variants reach 1.6 x because the binning / raster share of the frame is not at that roofline on one GPU either.\n")
+      "(vertex phase, triangle set-up and near-plane clipping of all 13 k triangles; only binning shrinks with N) plus 1/N of ~250 us of `k_tile`; "
+      "the front of frame k+1 overlaps the tile kernel of frame k, so the time per frame tends to max(front, tile / N + flag hand-shake) — and the "
+      "single-GPU pipeline it is compared with got faster this round (0.28 -> 0.21 ms per frame), which is why the ratios at N = 2 fell while "
+      "every absolute time improved.  On C5 (10 M triangles, 8K) the replicated triangle phase is 0.9 of a frame's 1.65 ms: SURVEY.md 8(d)'s "
+      "HBM-roofline ceiling for 8 GPUs is 1.41 x; the NCCL variants reach 1.7 x (0.97 ms per 8K frame of 10 M triangles) because the binning / "
+      "raster share of the frame is not at that roofline on one GPU either.\n")
 
 w("## 3. Launch list of bench steps (`r02_c3_launches.csv`, `ncu --metrics gpu__time_duration.sum --clock-control none`)\n")
 p = os.path.join(P, "r02_c3_launches.csv")
@@ -150,24 +152,32 @@ for f, kernels in (("r02_ncu_full_c3_kernels.md", ("k_front", "k_raster", "k_til
           f"{ncu(f, k_, 'sm__warps_active.avg.pct_of_peak_sustained_active')[0]:.1f} | {ncu(f, k_, 'smsp__inst_executed.sum')[0] / 1e6:.2f} M |")
 w("")
 w("""Reading them:
-- **k_tile, C3** (the `roofline` kernel): 70.5 MB of algorithmic bytes per launch (8 B x 3840 x 2160 + the lemur texture) in ~42 us =
-  ~1.7 TB/s = 0.26 of the measured HBM peak; DRAM traffic 35.7 MB < algorithmic bytes because half of the write-once frame is still in the
-  126 MB L2 when the kernel ends (no wasted re-reads).  Issue-active 35 %, top stalls `long_scoreboard` and `barrier`.  Its duration is one
-  CTA's critical path — prologue, ONE item (~340 items for 444 persistent CTAs; an item is ~17 us: key-page merge 4 us, shading 7 us at ~250
-  instructions per 32 pixels, write-back 1 us), its share of the 3 740 empty-tile clears, the drain of the stores.  Measured and rejected
-  this round: clears before the item (-8 %), two pixels per lane as independent streams (+0 %), per-warp staging of the winners' records in
-  shared memory (-30 %), 4 CTAs per SM, speculative page loads (+0 %).  `r02_tile_phase_cycles_and_front_phases.txt` has the per-phase cycle
-  distribution of the items.
-- **k_tile, C4**: issue-bound (71 % issue-active), 273 M warp instructions for ~65 M covered fragments; the block-level early depth reject
-  added this round removes 24 edge evaluations per hidden triangle and lane (C4 frame time 266 -> ~200 us/frame with the front-end changes;
-  frame fill fraction 18 % -> 24 %).
-- **k_front, C3**: 1.7 M warp instructions, 3.7 % issue-active: a chain of latencies by design (one 128-thread CTA per SM so that it runs
-  beside another frame's `k_tile`); 55 % of the stall samples are CTAs waiting at the two grid barriers for the slowest block of the triangle
-  phase.  With two CTAs per SM a lone frame is 4 us faster and the throughput 12 % lower (A/B in `DESIGN.md` section 4 comment, `scene.cpp`).
-- **k_front, C5**: 1.42 ms, 420 M warp instructions (42 per triangle), 26 % issue-active, DRAM 0.77 GB read + 1.57 GB written (304 B per
-  surviving record) = 20 % of peak: latency- and barrier-bound (`long_scoreboard` 12, `barrier` 12 per issue); the next step is in DESIGN.md
-  section 8.  **k_raster, C5**: issue-bound (62 %); raising the lane-per-reference threshold from 8 to 16 px moved a third of its warp-per-
-  reference jobs to lanes (C5 +12 % frames/s).
+- **k_tile, C3** (the `roofline` kernel): 70.5 MB of algorithmic bytes per launch (8 B x 3840 x 2160 + the lemur texture) in ~43 us =
+  ~1.65 TB/s = 0.25 of the measured HBM peak; DRAM traffic 35.7 MB < algorithmic bytes because half of the write-once frame is still in the
+  126 MB L2 when the kernel ends (no wasted re-reads).  It is NOT memory-bound and cannot be made so at this scene size: 11.9 M warp
+  instructions, of which ~3.8 M are the shading of 481 k visible pixels (~250 instructions per pixel: exact-order Phong, two texel fetches,
+  barycentrics by exact division) and ~2 M the 550 large references; an SM hosts ~2.4 of the ~345 raster items, and an item's phases are
+  issue-bound at that occupancy (`r02_tile_phase_cycles_and_front_phases.txt`: item p50 31 k cycles, max 57 k; phase C 15 k cycles for
+  16 k warp instructions per CTA with three CTAs per SM).  The kernel's duration is the heaviest item's critical path (~29 us) + launch,
+  prologue and drain.  Measured and rejected: clears before the item (-8 %), empty tiles handed out dynamically behind the items (-4 %),
+  two pixels per lane as independent streams (+0 %), per-warp staging of the winners' records in shared memory (-30 %), 4 CTAs per SM,
+  speculative page loads (+0 %), the early-depth weights precomputed in the record (+0 %).
+- **k_tile, C4**: issue-bound (66 % issue-active), 243 M warp instructions (273 M before this round's last three changes) for ~65 M
+  covered fragments.  This round: block-level early depth reject (24 edge evaluations per hidden triangle and lane not done), a tile's
+  large references tested nearest first (bitonic sort by smallest vertex depth, in the tile's key array), the lane's largest stored depth
+  cached, the depth reject ahead of the coverage reject.  C4 frame time 266 (round 1) -> 215 -> 202 us/frame, frame fill fraction
+  18 % -> 24 % -> 26 %.  A warp-level depth reject over the 16x16 region was measured and made it slower (-9 %: the bound over a region is
+  too weak to fire).
+- **k_front, C3**: 1.5 M warp instructions, 4 % issue-active: a chain of latencies by design (one 128-thread CTA per SM so that it runs
+  beside another frame's `k_tile`); half of the stall samples are CTAs waiting at the grid barriers for the slowest block of the triangle
+  phase.  With two CTAs per SM a lone frame is 4 us faster and the throughput 12 % lower.
+- **k_front, C5**: 1.42 -> 1.06 ms.  The first design numbered record slots with a single-pass chained scan (decoupled look-back) over the
+  128-triangle blocks: 28 % of the kernel's stall samples were blocks waiting for their 32 predecessors to publish.  Slots are now
+  block * 512 + prefix inside the block (no cross-block dependency), the records are stored densely where one atomicAdd per block puts
+  them, and consumers translate through a block table (`record_index`).  What is left: 355 M warp instructions, 29 % issue-active, DRAM
+  0.77 GB read + 1.6 GB written (304 B per surviving record) = 2.2 TB/s; top stalls are the index / vertex gathers (`long_scoreboard`)
+  and the per-block barriers of the binning.  Keeping a ticket and the next block's index lines in flight ahead was measured: C5 +2 %,
+  C3 -1 %, not kept.  **k_raster, C5**: issue-bound (66 %), 0.29 ms.
 """)
 w("## 5. compute-sanitizer (`tools/sanitize.sh`; `r02_sanitizer_*.log`)\n")
 for tool in ("memcheck", "racecheck", "synccheck"):
