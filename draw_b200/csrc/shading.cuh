@@ -52,8 +52,6 @@ __device__ __forceinline__ uint32_t shade_bary(const MaterialDev *materials, con
     const v3 N{INTERP(0, 0, 3), INTERP(0, 1, 3), INTERP(0, 2, 3)};
     const v3 L{INTERP(9, 0, 3), INTERP(9, 1, 3), INTERP(9, 2, 3)};
     const v3 H{INTERP(18, 0, 3), INTERP(18, 1, 3), INTERP(18, 2, 3)};
-    const float u = INTERP(27, 0, 2), v = INTERP(27, 1, 2);
-#undef INTERP
     // MaterialDev as 4 x uint4: ka3 kd1 | kd2 ks3 | alpha ka_off ka_w ka_h | kd_off kd_w kd_h pad
     const uint4 *mq = reinterpret_cast<const uint4 *>(materials + __float_as_uint(w[33]));
     const uint4 m0 = MATERIALS_CACHED ? mq[0] : __ldg(mq), m1 = MATERIALS_CACHED ? mq[1] : __ldg(mq + 1),
@@ -63,8 +61,19 @@ __device__ __forceinline__ uint32_t shade_bary(const MaterialDev *materials, con
     const v3 ks{__uint_as_float(m1.z), __uint_as_float(m1.w), __uint_as_float(m2.x)};
     *opacity_out = __uint_as_float(m2.y);
 
-    const uint32_t dt = fetch_texel(texels, m3.x, m3.y, m3.z, u, v); // map_kd   canvas.rs:689-691
-    const uint32_t at = fetch_texel(texels, m2.z, m2.w, m3.w, u, v); // map_ka   canvas.rs:693-695
+    // A 1x1 map (TextureMap::default(), scene/mod.rs:128-135: every material without an image) has one texel, whatever
+    // u and v are: floor(u * (1 - 1)) is 0, or NaN -> 0 under `as usize`.  When both maps are 1x1 the texture
+    // coordinate is not interpolated at all (it feeds nothing else, canvas.rs:685-695).
+    uint32_t dt, at;
+    if ((m3.y | m3.z | m2.w | m3.w) == 1u) { // widths and heights are >= 1
+        dt = __ldg(reinterpret_cast<const uint32_t *>(texels + m3.x));
+        at = __ldg(reinterpret_cast<const uint32_t *>(texels + m2.z));
+    } else {
+        const float u = INTERP(27, 0, 2), v = INTERP(27, 1, 2);
+        dt = fetch_texel(texels, m3.x, m3.y, m3.z, u, v); // map_kd   canvas.rs:689-691
+        at = fetch_texel(texels, m2.z, m2.w, m3.w, u, v); // map_ka   canvas.rs:693-695
+    }
+#undef INTERP
     const v3 dcol{u8tab[dt & 255u], u8tab[(dt >> 8) & 255u], u8tab[(dt >> 16) & 255u]};
     const v3 acol{u8tab[at & 255u], u8tab[(at >> 8) & 255u], u8tab[(at >> 16) & 255u]};
 
