@@ -583,16 +583,24 @@ __device__ __forceinline__ void clear_tile_cta(const uint32_t et, const int W_, 
     const int ex0 = (int)(et & (MAX_TILES_X - 1)) * TILE_W, ey0 = (int)(et >> 10) * TILE_H;
     const uint32_t clear_px = 255u | (186u << 8) | (155u << 16) | (255u << 24); // memory order b g r pad
     if ((W_ & 3) == 0) {
-        constexpr int QPR = TILE_W / 4; // 16-byte quads per tile row
+        // A thread keeps its column of 16-byte quads and steps down the tile: the addresses are computed once per tile
+        // (the clears of a 4K frame with a small scene are most of the frame's stores: ~4 000 tiles, 24 instructions per
+        // store pair when every quad derived its own address).
+        constexpr int QPR = TILE_W / 4, ROWS_PER_STEP = TILE_THREADS / QPR, STEPS = TILE_H / ROWS_PER_STEP; // 16 quads per row, 16 rows per step
+        static_assert(TILE_THREADS % QPR == 0 && TILE_H % ROWS_PER_STEP == 0, "clear_tile_cta geometry");
+        const int x = ex0 + (tid % QPR) * 4, y0 = ey0 + tid / QPR;
+        if (x < W_) {
+            uint4 *c = reinterpret_cast<uint4 *>(color + ((size_t)(H_ - 1 - y0) * W_ + x) * 4);
+            float4 *d = reinterpret_cast<float4 *>(depth + (size_t)y0 * W_ + x);
+            const ptrdiff_t step = (ptrdiff_t)ROWS_PER_STEP * (W_ >> 2); // in 16-byte units; colour rows run upwards (y-flipped)
+            const uint4 cq = make_uint4(clear_px, clear_px, clear_px, clear_px);
+            const float4 dq = make_float4(depth_max, depth_max, depth_max, depth_max);
 #pragma unroll
-        for (int q = tid; q < QPR * TILE_H; q += TILE_THREADS) {
-            const int x = ex0 + (q % QPR) * 4, y = ey0 + q / QPR;
-            if (x < W_ && y < H_) {
-                if (write_color)
-                    __stcs(reinterpret_cast<uint4 *>(color + ((size_t)(H_ - 1 - y) * W_ + x) * 4),
-                           make_uint4(clear_px, clear_px, clear_px, clear_px));
-                __stcs(reinterpret_cast<float4 *>(depth + (size_t)y * W_ + x), make_float4(depth_max, depth_max, depth_max, depth_max));
-            }
+            for (int k = 0; k < STEPS; k++)
+                if (y0 + k * ROWS_PER_STEP < H_) {
+                    if (write_color) __stcs(c - k * step, cq);
+                    __stcs(d + k * step, dq);
+                }
         }
     } else {
         for (int p = tid; p < TILE_PIXELS; p += TILE_THREADS) {
