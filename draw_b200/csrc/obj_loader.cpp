@@ -107,6 +107,7 @@ extern "C" {
 int draw_object_load_obj(const char *path_c, draw_image_loader loader, void *user, draw_object **out) {
     if (out) *out = nullptr;
     if (!path_c || !out) return drawb200::loader_fail(DRAW_ERR_INVALID_ARGUMENT, "draw_object_load_obj: NULL argument");
+    draw_object *o = nullptr; // owned here until handed to the caller: the handlers below release it
     try {
         const std::string path(path_c), dir = dir_of(path);
         std::ifstream in(path);
@@ -196,11 +197,12 @@ int draw_object_load_obj(const char *path_c, draw_image_loader loader, void *use
         if (have_group) obj_groups.push_back(group);
         objects.push_back({obj_name, obj_groups});
 
-        draw_object *o = new draw_object();
+        o = new draw_object();
         o->name = base_of(path); // object.rs:444
         const size_t n_pos = position.size() / 3;
         if (n_pos == 0) {
             delete o;
+            o = nullptr;
             return drawb200::loader_fail(DRAW_ERR_IO, "OBJ file has no vertices");
         }
         // normals normalised (object.rs:146-150): three divisions by the norm
@@ -242,6 +244,7 @@ int draw_object_load_obj(const char *path_c, draw_image_loader loader, void *use
             std::ifstream mf(join(dir, lib));
             if (!mf) {
                 delete o;
+                o = nullptr;
                 return drawb200::loader_fail(DRAW_ERR_IO, ("Unable to open file " + lib).c_str()); // object.rs:136-137
             }
             int cur = -1;
@@ -279,6 +282,7 @@ int draw_object_load_obj(const char *path_c, draw_image_loader loader, void *use
                     if (face.size() < 3) continue;
                     if (face.size() > 4) {
                         delete o;
+                        o = nullptr;
                         return drawb200::loader_fail(DRAW_ERR_IO, "faces with more than 4 vertices are not supported (object.rs:361-363)");
                     }
                     bool f_mt = false, f_mn = false;
@@ -287,6 +291,7 @@ int draw_object_load_obj(const char *path_c, draw_image_loader loader, void *use
                         f_mn |= c.vn < 0;
                         if (c.v < 0 || (size_t)c.v >= n_pos) {
                             delete o;
+                            o = nullptr;
                             return drawb200::loader_fail(DRAW_ERR_IO, "face references a vertex that does not exist");
                         }
                     }
@@ -358,8 +363,11 @@ int draw_object_load_obj(const char *path_c, draw_image_loader loader, void *use
         *out = o;
         return DRAW_OK;
     } catch (const std::exception &e) {
+        delete o; // and the images decoded so far
         return drawb200::loader_fail(DRAW_ERR_IO, e.what());
     } catch (...) {
+        delete o;
+        o = nullptr;
         return drawb200::loader_fail(DRAW_ERR_INTERNAL, "draw_object_load_obj: internal error");
     }
 }
