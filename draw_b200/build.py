@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdraw_b200.so")
-SOURCES = ["k_front.cu", "k_raster.cu", "k_tile.cu", "k_sort.cu", "k_sync.cu", "k_overlay.cu", "scene.cpp", "obj_loader.cpp", "image_decode.cpp", "jpeg_decode.cpp", "jpeg_encode.cpp"]
+SOURCES = ["k_front.cu", "k_raster.cu", "k_tile.cu", "k_sort.cu", "k_sync.cu", "k_overlay.cu", "k_mirror.cu", "scene.cpp", "obj_loader.cpp", "image_decode.cpp", "jpeg_decode.cpp", "jpeg_encode.cpp"]
 HEADERS = ["device_types.h", "device_math.cuh", "shading.cuh", "host_math.hpp", os.path.join("..", "..", "include", "draw_b200.h")]
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",

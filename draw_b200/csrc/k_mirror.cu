@@ -1,0 +1,78 @@
+// k_mirror.cu — the frame's way back to the host (Canvas::as_bytes_slice, mororo18/draw canvas.rs:966-982: the
+// reference's frame lives in host memory).
+//
+// A full read-back is 4*W*H bytes over PCIe per frame — 33 MB at 4K, which caps the renderer at ~1 700 frames/s
+// whatever the GPU does.  Most of a frame is usually the clear colour, and it was the clear colour in the frame
+// the host mirror already holds: those tiles need not cross the bus again.  k_tile records per tile whether it
+// rasterised something into it (1) or only wrote the clear colour (0) (FrameUniforms::tile_state); the canvas
+// remembers the same for the frame its pinned host mirror holds (mirror_state).  k_mirror copies the tiles that are
+// 1 in either — drawn now, or drawn then and cleared since — from the device frame to the mirror through its
+// device-mapped address (posted PCIe writes, whole 256-byte rows), and brings mirror_state up to date.  The mirror
+// ends up byte-identical to the device frame.  The number of tiles copied is posted to the frame's status block.
+#include "device_math.cuh"
+
+namespace drawb200 {
+
+constexpr int MIRROR_THREADS = 256;
+
+__global__ void __launch_bounds__(MIRROR_THREADS) k_mirror(const uint8_t *__restrict__ color, uint8_t *__restrict__ host_color,
+                                                           const uint8_t *__restrict__ tile_state, uint8_t *__restrict__ mirror_state,
+                                                           int W_, int H_, int tiles_x, int n_tiles, uint32_t *__restrict__ counters,
+                                                           uint32_t *__restrict__ status_word) {
+    constexpr int QPR = TILE_W / 4, ROWS_PER_STEP = MIRROR_THREADS / QPR, STEPS = TILE_H / ROWS_PER_STEP;
+    static_assert(MIRROR_THREADS % QPR == 0 && TILE_H % ROWS_PER_STEP == 0, "k_mirror geometry");
+    const int tid = threadIdx.x;
+    uint32_t copied = 0; // CTA-uniform
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t now = tile_state[tile], was = mirror_state[tile];
+        if (!(now | was)) continue; // clear colour on both sides
+        ++copied;
+        const int x = (tile % tiles_x) * TILE_W + (tid % QPR) * 4, y0 = (tile / tiles_x) * TILE_H + tid / QPR;
+        if ((W_ & 3) == 0) {
+            if (x < W_) {
+                const size_t at = ((size_t)(H_ - 1 - y0) * W_ + x) * 4; // colour rows are y-flipped; both buffers alike
+                const ptrdiff_t step = (ptrdiff_t)ROWS_PER_STEP * W_ * 4;
+                uint4 q[STEPS];
+#pragma unroll
+                for (int k = 0; k < STEPS; k++)
+                    if (y0 + k * ROWS_PER_STEP < H_) q[k] = __ldcs(reinterpret_cast<const uint4 *>(color + at - k * step));
+#pragma unroll
+                for (int k = 0; k < STEPS; k++)
+                    if (y0 + k * ROWS_PER_STEP < H_) *reinterpret_cast<uint4 *>(host_color + at - k * step) = q[k];
+            }
+        } else {
+            for (int p = tid; p < TILE_W * TILE_H; p += MIRROR_THREADS) {
+                const int px = (tile % tiles_x) * TILE_W + (p & (TILE_W - 1)), py = (tile / tiles_x) * TILE_H + p / TILE_W;
+                if (px >= W_ || py >= H_) continue;
+                const size_t at = (size_t)(H_ - 1 - py) * W_ + px;
+                reinterpret_cast<uint32_t *>(host_color)[at] = reinterpret_cast<const uint32_t *>(color)[at];
+            }
+        }
+        if (tid == 0) mirror_state[tile] = (uint8_t)now;
+    }
+    // the last CTA to finish posts the frame's total and re-arms the counters
+    if (tid == 0) {
+        if (copied) atomicAdd(&counters[0], copied);
+        __threadfence();
+        if (atomicAdd(&counters[1], 1u) == gridDim.x - 1u) {
+            __threadfence();
+            const uint32_t total = atomicExch(&counters[0], 0u);
+            counters[1] = 0u;
+            if (status_word) {
+                *status_word = total;
+                __threadfence_system();
+            }
+        }
+    }
+}
+
+cudaError_t launch_mirror(const uint8_t *color, uint8_t *host_color, const uint8_t *tile_state, uint8_t *mirror_state, int W_, int H_,
+                          uint32_t *counters, uint32_t *status_word, cudaStream_t stream, uint64_t *launches) {
+    const int tiles_x = (W_ + TILE_W - 1) / TILE_W, tiles_y = (H_ + TILE_H - 1) / TILE_H, n_tiles = tiles_x * tiles_y;
+    const int grid = n_tiles < 148 * 8 ? n_tiles : 148 * 8;
+    k_mirror<<<grid, MIRROR_THREADS, 0, stream>>>(color, host_color, tile_state, mirror_state, W_, H_, tiles_x, n_tiles, counters, status_word);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+} // namespace drawb200

@@ -574,6 +574,7 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
         __syncthreads();
         if (tid == 0) atomicMax(&W.tile_cycles[TAP_TOTAL * U.n_coarse + tile], (uint32_t)(clock64() - t_start));
     }
+    if (tid == 0 && U.tile_state) U.tile_state[tile] = 1; // rasterised content (every window of a split tile says so)
 }
 
 // One empty tile written by the whole CTA: 16 bytes of colour and 16 of depth per thread, fire-and-forget
@@ -664,9 +665,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(cons
     const int W_ = (int)U.canvas_w, H_ = (int)U.canvas_h;
     // The empty tiles are dealt out evenly over the raster items: item k's CTA writes tiles [k * per_item, (k+1) * per_item)
     // — before the item (FrameUniforms::clear_first: the stores drain to HBM under the item's latency-bound work) or after it.
+    auto clear_one = [&](uint32_t e) {
+        const uint32_t et = __ldg(&W.empty_tiles[e]); // x | y << 10
+        clear_tile_cta(et, W_, H_, U.depth_max, color, depth, threadIdx.x, U.empty_tile_color != 0u);
+        if (threadIdx.x == 0 && U.tile_state) U.tile_state[(et >> 10) * U.tiles_x + (et & (MAX_TILES_X - 1))] = 0; // clear colour only
+    };
     auto clear_share = [&](uint32_t k) {
-        for (uint32_t e = k * per_item, e_end = min(n_empty, e + per_item); e < e_end; e++)
-            clear_tile_cta(__ldg(&W.empty_tiles[e]), W_, H_, U.depth_max, color, depth, threadIdx.x, U.empty_tile_color != 0u);
+        for (uint32_t e = k * per_item, e_end = min(n_empty, e + per_item); e < e_end; e++) clear_one(e);
     };
     auto fetch_item = [&](uint32_t i) -> uint32_t { // thread 0 only
         if (i >= n_items) return ITEM_NONE;
@@ -702,8 +707,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1024 / TILE_THREADS) k_tile(cons
         ahead = next_ahead;
     }
     if (n_items == 0u) // nothing to rasterise in this launch's rows: the CTAs share the empty tiles
-        for (uint32_t e = blockIdx.x; e < n_empty; e += gridDim.x)
-            clear_tile_cta(__ldg(&W.empty_tiles[e]), W_, H_, U.depth_max, color, depth, threadIdx.x, U.empty_tile_color != 0u);
+        for (uint32_t e = blockIdx.x; e < n_empty; e += gridDim.x) clear_one(e);
 }
 
 // Canvas::clear (canvas.rs:425-433) as a standalone operation (draw_canvas_clear).

@@ -40,6 +40,8 @@ cudaError_t launch_clear(uint8_t *color, float *depth, size_t n_pixels, float de
                          uint64_t *launches);
 cudaError_t launch_fill_u32(uint32_t *dst, size_t n, uint32_t value, cudaStream_t stream, uint64_t *launches);
 cudaError_t launch_overlay(const OverlayParams &P, cudaStream_t stream, uint64_t *launches);                        // k_overlay.cu
+cudaError_t launch_mirror(const uint8_t *color, uint8_t *host_color, const uint8_t *tile_state, uint8_t *mirror_state, int W_, int H_,
+                          uint32_t *counters, uint32_t *status_word, cudaStream_t stream, uint64_t *launches);      // k_mirror.cu
 cudaError_t launch_flag_signal(uint32_t *flag, uint32_t value, cudaStream_t stream);                               // k_sync.cu
 cudaError_t launch_flags_wait(const uint32_t *flags, uint32_t n, uint32_t value, uint32_t *error_word, cudaStream_t stream);
 } // namespace drawb200
@@ -221,6 +223,14 @@ struct draw_canvas {
     size_t h_color_cap = 0;
     bool host_dirty = true;
     bool host_mirror = false;   // every render also refreshes the pinned mirror (draw_canvas_enable_host_mirror)
+    // Incremental read-back (k_mirror.cu).  tile_state: per tile, 1 = the last render rasterised into it, 0 = it only wrote
+    // the clear colour (written by k_tile); mirror_state: the same for the frame the host mirror holds.
+    uint8_t *h_color_dev = nullptr;     // the mirror's device-side address
+    DevBuf<uint8_t> tile_state, mirror_state;
+    DevBuf<uint32_t> mirror_counters;
+    size_t state_tiles = 0;
+    bool frame_clean = false;           // the colour buffer is exactly what a whole-canvas render left: tile_state describes it
+    bool mirror_valid = false;          // mirror_state describes the mirror
     cudaStream_t own_stream = nullptr, stream = nullptr;
     size_t stripe_y0 = 0, stripe_y1 = 0; // rows; y1 == 0 means whole canvas
     uint32_t row_step = 1, row_phase = 0; // tile rows ty % row_step == row_phase only (draw_canvas_set_tile_rows)
@@ -238,6 +248,7 @@ struct draw_canvas {
     struct FrameInputs {
         draw_scene *scene = nullptr;
         int status_slot = 0;
+        int mirror_path = 0; // how the frame went to the host mirror: 0 not at all, 1 whole-frame copy, 2 changed tiles (k_mirror)
         CameraState camera;
         f3 light;
         int off_x = 0, off_y = 0;
@@ -282,6 +293,7 @@ struct Config {
     // grids; 0 = by scene size (set_launch_grids): with several frames in flight a kernel costs the pipeline its CTAs' residency
     int front_cps = std::max(0, env_int("DRAW_B200_FRONT_CPS", 0)); // k_front CTAs per SM
     int raster_ctas = std::max(0, env_int("DRAW_B200_RASTER_CTAS", 0));
+    int mirror_tiles = env_int("DRAW_B200_MIRROR_TILES", 1); // host mirror: copy only the tiles that changed when most of the frame is clear colour (k_mirror.cu)
     int sort_large = env_int("DRAW_B200_SORT_LARGE", 1);   // k_tile: a tile's large references front to back (the early depth rejects bite sooner)
     int clear_first = env_int("DRAW_B200_CLEAR_FIRST", 0); // k_tile: empty-tile stores before (1) or after (0) a CTA's raster item
     int rec_cap = std::max(0, env_int("DRAW_B200_REC_CAP", 0));   // initial record / reference capacities (tests force overflows)
@@ -563,6 +575,58 @@ int ensure_host_mirror(draw_canvas *c, size_t bytes) {
     CU(cudaMallocHost(&c->h_color, bytes));
     c->h_color_cap = bytes;
     c->host_dirty = true;
+    c->mirror_valid = false;
+    void *dev = nullptr;
+    CU(cudaHostGetDevicePointer(&dev, c->h_color, 0));
+    c->h_color_dev = static_cast<uint8_t *>(dev);
+    return DRAW_OK;
+}
+
+// Per-tile state of the canvas' frame and of its host mirror (k_mirror.cu), sized for the current canvas.
+int ensure_tile_state(draw_canvas *c) {
+    const size_t n = ((c->width + TILE_W - 1) / TILE_W) * ((c->height + TILE_H - 1) / TILE_H);
+    if (c->state_tiles == n && c->tile_state.ptr) return DRAW_OK;
+    TRY(c->tile_state.reserve(n));
+    TRY(c->mirror_state.reserve(n));
+    TRY(c->mirror_counters.reserve(2));
+    CU(cudaMemsetAsync(c->tile_state.ptr, 1, n, c->stream));
+    CU(cudaMemsetAsync(c->mirror_state.ptr, 1, n, c->stream));
+    CU(cudaMemsetAsync(c->mirror_counters.ptr, 0, 2 * sizeof(uint32_t), c->stream));
+    c->state_tiles = n;
+    c->frame_clean = false;
+    c->mirror_valid = false;
+    return DRAW_OK;
+}
+
+// The canvas' colour buffer was written by something other than a whole-canvas render.
+void touch_frame(draw_canvas *c) {
+    c->host_dirty = true;
+    c->frame_clean = false;
+}
+
+// Brings the pinned host mirror up to date with the device frame, on stream st.  When the frame is what a whole-canvas
+// render left, the mirror's state is known and most of the last frame was clear colour, only the tiles that differ cross
+// the bus (k_mirror, *path = 2, tile count posted to status_word); otherwise the whole frame is copied (*path = 1).
+int refresh_mirror(draw_canvas *c, cudaStream_t st, uint32_t *status_word, int *path) {
+    const size_t bytes = c->width * c->height * 4;
+    TRY(ensure_host_mirror(c, bytes));
+    TRY(ensure_tile_state(c));
+    const bool sparse = c->stats.empty_tiles * 2u > c->state_tiles; // the last frame looked at on this canvas
+    if (g_cfg.mirror_tiles && c->frame_clean && c->mirror_valid && sparse) {
+        CU(launch_mirror(c->color(), c->h_color_dev, c->tile_state.ptr, c->mirror_state.ptr, (int)c->width, (int)c->height,
+                         c->mirror_counters.ptr, status_word, st, &c->launches));
+        if (path) *path = 2;
+    } else {
+        CU(cudaMemcpyAsync(c->h_color, c->color(), bytes, cudaMemcpyDeviceToHost, st));
+        if (c->frame_clean) { // the mirror now holds this frame: its state is the frame's
+            CU(cudaMemcpyAsync(c->mirror_state.ptr, c->tile_state.ptr, c->state_tiles, cudaMemcpyDeviceToDevice, st));
+            c->mirror_valid = true;
+        } else {
+            c->mirror_valid = false;
+        }
+        if (path) *path = 1;
+    }
+    c->host_dirty = false;
     return DRAW_OK;
 }
 
@@ -619,6 +683,7 @@ void fill_uniforms(draw_scene *s, const draw_canvas *c, FrameUniforms &U) {
     U.sort_large = (uint32_t)g_cfg.sort_large;
     U.empty_tile_color = c->empty_tile_color ? 1u : 0u;
     U.status_host = c->h_status + (size_t)c->next_status_slot * N_STATUS_WORDS; // pinned, mapped: valid on the device (unified addressing)
+    U.tile_state = c->tile_state.ptr; // enqueue_frame has sized it
     U.color = c->color();
     U.depth = c->depth();
 }
@@ -670,6 +735,7 @@ int ensure_set_ready(draw_scene *s, draw_scene::WorkSet &ws, const FrameUniforms
 int enqueue_frame(draw_scene *s, draw_canvas *c) {
     TRY(ensure_device(s->device));
     if (s->geometry_dirty) TRY(upload_geometry(s));
+    TRY(ensure_tile_state(c));
     FrameUniforms U{};
     fill_uniforms(s, c, U);
     if (U.tiles_x >= MAX_TILES_X || U.tiles_y >= MAX_TILES_Y)
@@ -731,10 +797,16 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     s->launches += 2 + (s->dev.n_transparent ? 1 : 0) + (tile_grid_items(U) ? 1 : 0);
     CU(cudaGetLastError());
     c->host_dirty = true;
+    // whole canvas, empty tiles written: the colour buffer is this render's and nothing else's
+    c->frame_clean = c->stripe_y1 == 0 && U.row_step == 1u && c->empty_tile_color && !c->ext_color;
+    int mirror_path = 0;
+    if (c->host_mirror && !c->ext_color) // the frame follows its render to the host without waiting for the host to ask (map_host then only waits)
+        TRY(refresh_mirror(c, st, U.status_host + CNT_MIRROR_TILES, &mirror_path));
     {
         draw_canvas::FrameInputs in;
         in.scene = s;
         in.status_slot = c->next_status_slot;
+        in.mirror_path = mirror_path;
         in.camera = s->camera;
         in.light = s->light;
         in.off_x = c->off_x; in.off_y = c->off_y;
@@ -742,16 +814,9 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
         in.row_step = c->row_step; in.row_phase = c->row_phase;
         in.depth_max = c->depth_max;
         if (!c->slot_event[in.status_slot]) CU(cudaEventCreateWithFlags(&c->slot_event[in.status_slot], cudaEventDisableTiming));
-        CU(cudaEventRecord(c->slot_event[in.status_slot], st));
+        CU(cudaEventRecord(c->slot_event[in.status_slot], st)); // behind the frame and its way to the host
         c->pending.push_back(in);
         c->next_status_slot = (c->next_status_slot + 1) % draw_canvas::STATUS_SLOTS;
-    }
-    if (c->host_mirror && !c->ext_color) {
-        // the frame follows its render to the host without waiting for the host to ask (map_host then only waits)
-        const size_t bytes = c->width * c->height * 4;
-        TRY(ensure_host_mirror(c, bytes));
-        CU(cudaMemcpyAsync(c->h_color, c->color(), bytes, cudaMemcpyDeviceToHost, st));
-        c->host_dirty = false;
     }
     return DRAW_OK;
 }
@@ -767,6 +832,7 @@ void record_stats(draw_canvas *c, const draw_canvas::FrameInputs &frame) {
     c->stats.tile_refs = c->stats.large_refs + c->stats.medium_refs + c->stats.small_refs + c->stats.transparent_refs;
     c->stats.empty_tiles = st[CNT_EMPTY];
     c->stats.work_items = st[CNT_ITEMS];
+    c->stats.mirror_tiles = frame.mirror_path == 2 ? st[CNT_MIRROR_TILES] : frame.mirror_path == 1 ? (uint32_t)c->state_tiles : 0u;
     for (int i = 0; i < 5; i++) c->stats.front_phase_ns[i] = st[CNT_PHASE_NS + i + 1] - st[CNT_PHASE_NS + i];
     c->stats.front_phase_ns[5] = st[CNT_PHASE_NS + 6] - st[CNT_PHASE_NS + 2];                              // triangle phase, slowest CTA
     c->stats.front_phase_ns[6] = st[CNT_PHASE_NS + 7] ? st[CNT_PHASE_NS + 7] - st[CNT_PHASE_NS + 6] : 0u; // huge-record phase (after the barrier)
@@ -1353,7 +1419,7 @@ int draw_canvas_resize(draw_canvas *canvas, size_t width, size_t height) {
     canvas->stripe_y0 = canvas->stripe_y1 = 0;
     canvas->row_step = 1;
     canvas->row_phase = 0;
-    canvas->host_dirty = true;
+    touch_frame(canvas);
     // self.init_depth(self.depth_max), canvas.rs:392 — allocates the depth buffer even if none existed
     return draw_canvas_init_depth(canvas, canvas->depth_max);
     GUARD_END
@@ -1365,7 +1431,7 @@ int draw_canvas_clear(draw_canvas *canvas) {
     TRY(ensure_device(canvas->device));
     CU(launch_clear(canvas->color(), canvas->has_depth ? canvas->depth() : nullptr, canvas->width * canvas->height,
                     canvas->depth_max, canvas->stream, &canvas->launches));
-    canvas->host_dirty = true;
+    touch_frame(canvas);
     return DRAW_OK;
     GUARD_END
 }
@@ -1454,7 +1520,7 @@ int draw_canvas_draw_triangles(draw_canvas *canvas, const draw_vertex2d *vertice
         P.bin_any = canvas->ov_any.ptr;
         CU(launch_overlay(P, canvas->stream, &canvas->launches));
     }
-    if (n_triangles) canvas->host_dirty = true;
+    if (n_triangles) touch_frame(canvas);
     return DRAW_OK;
     GUARD_END
 }
@@ -1473,9 +1539,8 @@ int draw_canvas_map_host(draw_canvas *canvas, const uint8_t **out_bytes, size_t 
     const size_t bytes = canvas->width * canvas->height * 4;
     TRY(ensure_host_mirror(canvas, bytes));
     if (canvas->host_dirty) {
-        CU(cudaMemcpyAsync(canvas->h_color, canvas->color(), bytes, cudaMemcpyDeviceToHost, canvas->stream));
+        TRY(refresh_mirror(canvas, canvas->stream, nullptr, nullptr));
         CU(cudaStreamSynchronize(canvas->stream));
-        canvas->host_dirty = false;
     }
     *out_bytes = canvas->h_color;
     if (out_len) *out_len = bytes;
@@ -1536,7 +1601,7 @@ int draw_canvas_bind_external(draw_canvas *canvas, void *color_dev, void *depth_
     canvas->ext_color = static_cast<uint8_t *>(color_dev);
     canvas->ext_depth = static_cast<float *>(depth_dev);
     if (depth_dev) canvas->has_depth = true;
-    canvas->host_dirty = true;
+    touch_frame(canvas);
     return DRAW_OK;
     GUARD_END
 }

@@ -99,6 +99,8 @@ typedef struct draw_frame_stats {
     uint32_t overflow;          /* non-zero: a device buffer was too small, frame was re-rendered */
     uint32_t empty_tiles;       /* tiles of this render's rows nothing was binned to (they only get the clear colour and depth) */
     uint32_t work_items;        /* k_tile work items: non-empty tiles, dense ones cut into windows */
+    uint32_t mirror_tiles;      /* tiles of the frame copied to the pinned host mirror behind the render (draw_canvas_enable_host_mirror):
+                                   all of them for a whole-frame copy, the changed ones for an incremental one; 0 without the mirror */
     uint32_t front_phase_ns[7]; /* k_front, CTA 0: vertex phase, barrier, triangle phase, barrier (+ huge-record phase), tile phase;
                                    then the triangle phase of the slowest CTA and the huge-record phase */
     uint32_t front_block_ns[5]; /* k_front, first 256-triangle block: set-up, slot scan, record write, binning, clip path */
@@ -185,10 +187,13 @@ int draw_canvas_size(const draw_canvas *canvas, size_t *width, size_t *height);
  * pinned host mirror if it changed, and returns that mirror: width*height*4 bytes, B,G,R,pad
  * per pixel, row 0 = top.  Valid until the next render / resize / destroy on this canvas. */
 int draw_canvas_map_host(draw_canvas *canvas, const uint8_t **out_bytes, size_t *out_len);
-/* The reference's frame always lives in host memory (Canvas::frame, canvas.rs:353).  With the host
- * mirror enabled every draw_scene_render also enqueues the device-to-host copy of the frame behind
- * its kernels, so the PCIe transfer of frame k overlaps the rendering of frame k+1 on another canvas
- * and draw_canvas_map_host only waits.  Off by default (the copy costs 4*W*H bytes of PCIe per frame). */
+/* The reference's frame always lives in host memory (Canvas::frame, canvas.rs:353).  With the host mirror enabled every
+ * draw_scene_render also brings the pinned mirror up to date behind its kernels, so the PCIe transfer of frame k overlaps
+ * the rendering of frame k+1 on another canvas and draw_canvas_map_host only waits.  The refresh is a copy of the whole
+ * frame (4*W*H bytes) or — when the frame is a whole-canvas render, most of it is clear colour and the mirror's content is
+ * known — of the tiles that differ from what the mirror holds: drawn in this frame, or drawn in the mirror's frame and
+ * cleared since (k_mirror.cu; draw_frame_stats.mirror_tiles says how many).  Either way the mirror is byte-identical to
+ * the device frame.  Off by default. */
 int draw_canvas_enable_host_mirror(draw_canvas *canvas, int enabled);
 /* depth_frame (get_pixel_depth :413): width*height floats, row index = canvas y (not flipped). */
 int draw_canvas_read_depth(draw_canvas *canvas, float *dst, size_t n_floats);

@@ -1,7 +1,11 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_paths.py -x -q 2>&1 | tail -3
-for r in 1 2; do
-for c in c3 c4 c5 c2; do
-    python bench.py --config $c --steps 100 --warmup 20 --quick 2>/dev/null | python -c "
+for d in 3 4 6 8; do
+  DRAW_BENCH_E2E_DEPTH=$d timeout 400 python bench.py --config c3 --steps 20 --warmup 5 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('  $c fps', round(d['value'],1), 'us', round(d['us_per_frame'],2), 'lone', round(d['lone_frame_us_median'],1))"
-done; done
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); e=d['e2e']; print('depth $d c3', 'fps', round(d['value'],1), 'e2e', round(e['value'],1), 'serial', round(e['serial_value'],1), 'achieved', round(e['d2h_achieved_gbs'],2))"
+done
+DRAW_BENCH_E2E_DEPTH=6 timeout 400 python bench.py --config c2 --steps 20 --warmup 5 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); e=d['e2e']; print('depth 6 c2', 'e2e', round(e['value'],1), 'serial', round(e['serial_value'],1), 'achieved', round(e['d2h_achieved_gbs'],2))"
+DRAW_BENCH_E2E_DEPTH=6 timeout 400 python bench.py --config c4 --steps 20 --warmup 5 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); e=d['e2e']; print('depth 6 c4', 'e2e', round(e['value'],1), 'serial', round(e['serial_value'],1), 'achieved', round(e['d2h_achieved_gbs'],2))"
