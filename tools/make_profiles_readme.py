@@ -43,7 +43,7 @@ w("All numbers were taken on the pool's B200 (148 SMs, 1965 MHz max SM clock, no
   "write-up: `r01_README.md`.\n")
 
 w("## 1. bench.py, N = 1 (files `r02_bench_*_n1.json`, one JSON line each; `--steps 20 --warmup 5`, the driver's flags)\n")
-w("| cfg | workload | frames/s | Mtri/s | us/frame (frames back to back) | us, lone frame, L2 flushed | e2e frames/s (3 in flight / serial) | "
+w("| cfg | workload | frames/s | Mtri/s | us/frame (frames back to back) | us, lone frame, L2 flushed | e2e frames/s (6 in flight / serial) | "
   "k_front / k_raster / k_tile us (evented, one frame at a time) | k_tile HBM frac | frame HBM frac | frame fill frac | CPU oracle frames/s (1 thread) |")
 w("|---|---|---|---|---|---|---|---|---|---|---|---|")
 r1 = {"c2": 60164, "c3": 25416, "c4": 3522, "c5": 496}
@@ -65,8 +65,12 @@ if d3:
     w(f"- C3 is the bench's default workload (BASELINE.json `configs[2]`).  The driver-protocol line (`--steps 20 --warmup 5`: 20 steps of "
       f"128 frames, {d3['clocks']['samples']} clock samples) and a 200-step run agree within 1 %.  `--impl reference` "
       f"(`r02_bench_c3_reference.json`): {line('r02_bench_c3_reference.json')['value']:.1f} frames/s, same `config` object.")
-    w(f"- e2e is at the PCIe / host-memory ceiling: {d3['e2e']['d2h_achieved_gbs']:.1f} GB/s of frame read-backs against "
-      f"{d3['e2e']['d2h_ceiling_gbs']:.1f} GB/s for a plain `cudaMemcpyAsync` of the same bytes.")
+    e = d3["e2e"]
+    w(f"- e2e: {e['value']:.0f} frames/s with six canvases in flight, {e['serial_value']:.0f} for the reference's serial loop (one canvas: render, read, repeat).  "
+      f"{e['d2h_bytes_per_step'] / d3['config']['frames_per_step'] / 1e6:.2f} MB per frame crossed PCIe instead of {e.get('d2h_frame_bytes', 0) / 1e6:.1f} MB: the host mirror is "
+      f"refreshed by the tiles that differ from the frame it holds (`k_mirror`, posted writes from the SMs: {e['d2h_achieved_gbs']:.1f} GB/s; the copy engine's ceiling for "
+      f"whole frames is {e['d2h_ceiling_gbs']:.1f} GB/s = {e['d2h_ceiling_gbs'] * 1e9 / max(1, e.get('d2h_frame_bytes', 1)):.0f} frames/s, which is where e2e sat before: 1 622 frames/s).  "
+      f"`DRAW_B200_MIRROR_TILES=0` restores whole-frame copies; pipeline depth 3 / 4 / 6 / 8 gives 8.3 / 9.6 / 11.1 / 11.9 k frames/s (`DRAW_BENCH_E2E_DEPTH`).")
     w(f"- `k_front` phases on C3 (CTA 0's global-timer stamps, us): vertex {ph['vertex']:.1f}, barrier {ph['barrier1']:.1f}, triangle "
       f"{ph['triangle']:.1f} (slowest CTA {ph['triangle_slowest_cta']:.1f}), barrier (+ huge-record phase) {ph['barrier2_and_huge']:.1f}, "
       f"tile {ph['tile']:.1f}.  Round 1's seven launches for the same work: 108 us.")
@@ -86,9 +90,9 @@ if rows:
     for n, d, f in rows:
         w(f"| {n} | {d['value']:.0f} | {d['value'] / base:.2f} | {d['e2e']['value']:.0f} | {d['e2e']['d2h_achieved_gbs']:.0f} / {d['e2e']['d2h_ceiling_gbs']:.0f} | `{f}` |")
     w("")
-    w("e2e does not scale with N because the box's host side does not: the plain-copy ceiling (all ranks copying 33 MB frames to pinned "
-      "memory at once, no renderer involved) is ~57 GB/s for one GPU and 70-140 GB/s for 2, 4 or 8 depending on the box the call landed on "
-      "(one NUMA node, 32 vCPUs: `nvidia-smi topo`), and the renderer's read-backs sit at that ceiling at every N.\n")
+    w("The host side of the box does not scale with N: the plain-copy ceiling (all ranks copying whole 33 MB frames to pinned memory at once, no "
+      "renderer involved) is ~57 GB/s for one GPU and 70-140 GB/s for 2, 4 or 8 depending on the box the call landed on (one NUMA node, 32 vCPUs: "
+      "`nvidia-smi topo`).  With the incremental mirror the ranks move a tenth of those bytes, so e2e is no longer pinned to that ceiling.\n")
     w("Sort-first, ONE frame across the ranks (`sort_first` in the same lines; CUDA events around all frames, no host synchronisation in the "
       "loop; every entry `bit_exact: true` = composed frame equals the single-GPU frame):\n")
     w("| N | config | 1 GPU, frames back to back ms | 1 GPU, lone frame ms | p2p interleaved ms (x back-to-back / x lone) | NCCL interleaved | p2p stripes | NCCL stripes |")
