@@ -2,7 +2,7 @@
 """Renders a few small frames through libdraw_b200.so and compares them with the oracle; run it under
 compute-sanitizer (tools/sanitize.sh).  Scenes: C1 (textured + transparent, 800x600), C3 at 1280x720 (thousands of small
 triangles: key pages, k_raster atomics), C4 frame 60 at 960x544 (near-plane clipping, records covering hundreds of
-tiles: k_front's huge-record phase, tile windows), each rendered twice on two canvases (frames in flight); then a GUI
+tiles: k_front's huge-record phase, tile windows), each rendered three times on two canvases with the host mirror on (frames in flight, k_mirror); then a GUI
 command list over a rendered frame (k_overlay: bin masks, ordered blend)."""
 import os
 import sys
@@ -28,10 +28,13 @@ for name, (W, H), cam in (("c1_lemur_airplane", (800, 600), None), ("c3_trio", (
     for _ in range(2):
         c = draw_b200.Canvas(W, H)
         c.init_depth(100000.0)
+        c.enable_host_mirror(True)  # the frame's way to the host: whole-frame copy first, k_mirror's changed tiles after
         cs.append(c)
-    for k in range(4):
+    for k in range(6):
         s.render(cs[k % 2])
-    want = render_oracle(objs, W, H, cam=cam, frames=2)
+        if k >= 2:
+            cs[k % 2].as_bytes_slice(copy=False)
+    want = render_oracle(objs, W, H, cam=cam, frames=3)
     for c in cs:
         assert_frames_equal((c.as_bytes_slice(), c.depth()), want, name)
     print(name, W, H, "ok", c.last_frame_stats()["setup_records"], "records", flush=True)
