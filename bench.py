@@ -449,12 +449,10 @@ def run_ours(args, cfg):
         pair[k % N_E2E].as_bytes_slice(copy=False)
     n_e2e = frames_rank
     # bytes that actually cross PCIe per frame: the library copies a frame to its pinned host mirror whole (4*W*H), or — when
-    # most of it is clear colour and was clear colour in the frame the mirror holds — only the tiles that differ
-    # (draw_frame_stats.mirror_tiles; the mirror is byte-identical to the device frame either way: tests/test_gpu_mirror.py)
-    total_tiles = ((W + 63) // 64) * ((H + 31) // 32)
-
+    # most of it is clear colour and was clear colour in the frame the mirror holds — only the 64x8-pixel strips that differ
+    # (draw_frame_stats.mirror_kbytes; the mirror is byte-identical to the device frame either way: tests/test_gpu_mirror.py)
     def mirrored_bytes(canvas):
-        return 4 * W * H * min(canvas.last_frame_stats()["mirror_tiles"], total_tiles) // total_tiles
+        return min(4 * W * H, 1024 * canvas.last_frame_stats()["mirror_kbytes"])
 
     barrier()
     t0 = time.perf_counter()

@@ -132,7 +132,7 @@ pub struct draw_frame_stats {
     pub overflow: u32,
     pub empty_tiles: u32,
     pub work_items: u32,
-    pub mirror_tiles: u32,
+    pub mirror_kbytes: u32,
     pub front_phase_ns: [u32; 7],
     pub front_block_ns: [u32; 5],
 }

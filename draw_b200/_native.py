@@ -47,7 +47,7 @@ class Rect(C.Structure):  # draw_rect
 
 class FrameStats(C.Structure):
     _NAMES = ("input_triangles", "setup_records", "tile_refs", "large_refs", "medium_refs", "small_refs", "transparent_refs",
-              "overflow", "empty_tiles", "work_items", "mirror_tiles")
+              "overflow", "empty_tiles", "work_items", "mirror_kbytes")
     _fields_ = [(n, C.c_uint32) for n in _NAMES] + [("front_phase_ns", C.c_uint32 * 7), ("front_block_ns", C.c_uint32 * 5)]
 
     def as_dict(self):

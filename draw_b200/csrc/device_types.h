@@ -30,6 +30,10 @@ constexpr int TILE_W = DRAW_TILE_W, TILE_H = DRAW_TILE_H, REGION = 16;
 #endif
 constexpr int SMALL_AREA = DRAW_SMALL_AREA, MEDIUM_AREA = DRAW_MEDIUM_AREA;
 constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
+// k_mirror's granularity: a tile is TILE_H / 8 strips of TILE_W x 8 pixels (whole rows of the tile: 256-byte PCIe writes)
+constexpr int TILE_STRIP_H = 8, TILE_STRIPS = TILE_H / TILE_STRIP_H;
+constexpr uint32_t TILE_STRIPS_ALL = (1u << TILE_STRIPS) - 1u;
+static_assert(TILE_STRIPS <= 8, "one state byte per tile");
 // Opaque records: slot number = block * SLOT_STRIDE + number inside k_front's 128-triangle block (at most 4 records per
 // triangle); storage index = FrameDev::block_loc[block] + number inside the block (record_index, device_math.cuh).
 constexpr uint32_t SLOT_SHIFT = 9, SLOT_STRIDE = 1u << SLOT_SHIFT;
@@ -96,7 +100,7 @@ struct FrameUniforms {
     uint32_t empty_tile_color;         // 0: tiles nothing is binned to keep their colour bytes (the caller has cleared the buffer: draw_canvas_set_empty_tile_color)
     uint32_t sort_large;               // k_tile: a tile's large references are tested nearest first
     uint32_t clear_first;              // k_tile: a CTA writes its share of the empty tiles before its raster item (else after it)
-    uint8_t *tile_state;               // canvas-owned, one byte per tile: k_tile writes 1 where it rasterised, 0 where it only cleared (k_mirror.cu)
+    uint8_t *tile_state;               // canvas-owned, one byte per tile: k_tile's mask of the 64x8 strips that hold something else than the clear colour (k_mirror.cu)
     uint32_t *status_host;             // pinned host memory of the canvas (device-mapped): k_tile copies counters[0..31] there
     uint8_t *color;                    // the canvas: BGRA8, row 0 = top (canvas.rs:955-956)
     float *depth;                      // depth buffer, row 0 = y 0 (canvas.rs:413-423)
@@ -225,7 +229,7 @@ enum : int {
     CNT_HUGE = 30,      // 64-bit (8-byte aligned): huge records queued << 32 | their tile rows
     CNT_PHASE_NS = 16,  // 6 words: global-timer stamps of k_front's phases (block 0), low 32 bits; + 8: durations of the first block's sub-phases
     CNT_BUCKETS = 32,   // COST_BUCKETS words
-    CNT_MIRROR_TILES = 29, // status word only: tiles k_mirror copied to the host mirror (posted by k_mirror, after k_tile's block)
+    CNT_MIRROR_STRIPS = 29, // status word only: strips k_mirror copied to the host mirror (posted by k_mirror, after k_tile's block)
     CNT_ITEM_CURSOR = 96, // k_tile's item cursor, in a 128-byte line of its own
     CNT_BARRIER = 128,    // k_front's grid barrier, in a line of its own; never reset (FrameUniforms::bar_base)
     N_COUNTERS = 160, N_STATUS_WORDS = 32

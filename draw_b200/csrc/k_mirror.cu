@@ -3,12 +3,13 @@
 //
 // A full read-back is 4*W*H bytes over PCIe per frame — 33 MB at 4K, which caps the renderer at ~1 700 frames/s
 // whatever the GPU does.  Most of a frame is usually the clear colour, and it was the clear colour in the frame
-// the host mirror already holds: those tiles need not cross the bus again.  k_tile records per tile whether it
-// rasterised something into it (1) or only wrote the clear colour (0) (FrameUniforms::tile_state); the canvas
-// remembers the same for the frame its pinned host mirror holds (mirror_state).  k_mirror copies the tiles that are
-// 1 in either — drawn now, or drawn then and cleared since — from the device frame to the mirror through its
-// device-mapped address (posted PCIe writes, whole 256-byte rows), and brings mirror_state up to date.  The mirror
-// ends up byte-identical to the device frame.  The number of tiles copied is posted to the frame's status block.
+// the host mirror already holds: those pixels need not cross the bus again.  k_tile records per tile which of its
+// 64x8-pixel strips hold anything else than the clear colour (one bit each, FrameUniforms::tile_state; 0 for a tile
+// it only cleared); the canvas remembers the same for the frame its pinned host mirror holds (mirror_state).
+// k_mirror copies the strips that are set in either — drawn now, or drawn then and clear since — from the device
+// frame to the mirror through its device-mapped address (posted PCIe writes, whole 256-byte rows), and brings
+// mirror_state up to date.  The mirror ends up byte-identical to the device frame.  The number of strips copied is
+// posted to the frame's status block.
 #include "device_math.cuh"
 
 namespace drawb200 {
@@ -24,23 +25,26 @@ __global__ void __launch_bounds__(MIRROR_THREADS) k_mirror(const uint8_t *__rest
     const int tid = threadIdx.x;
     uint32_t copied = 0; // CTA-uniform
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint32_t now = tile_state[tile], was = mirror_state[tile];
-        if (!(now | was)) continue; // clear colour on both sides
-        ++copied;
-        const int x = (tile % tiles_x) * TILE_W + (tid % QPR) * 4, y0 = (tile / tiles_x) * TILE_H + tid / QPR;
+        const uint32_t now = tile_state[tile], m = now | mirror_state[tile];
+        if (!m) continue; // clear colour on both sides
+        copied += (uint32_t)__popc(m);
+        const int x = (tile % tiles_x) * TILE_W + (tid % QPR) * 4, r0 = tid / QPR, y0 = (tile / tiles_x) * TILE_H + r0;
         if ((W_ & 3) == 0) {
             if (x < W_) {
                 const size_t at = ((size_t)(H_ - 1 - y0) * W_ + x) * 4; // colour rows are y-flipped; both buffers alike
                 const ptrdiff_t step = (ptrdiff_t)ROWS_PER_STEP * W_ * 4;
                 uint4 q[STEPS];
+                bool take[STEPS];
+#pragma unroll
+                for (int k = 0; k < STEPS; k++) {
+                    take[k] = y0 + k * ROWS_PER_STEP < H_ && ((m >> ((r0 + k * ROWS_PER_STEP) / TILE_STRIP_H)) & 1u);
+                    if (take[k]) q[k] = __ldcs(reinterpret_cast<const uint4 *>(color + at - k * step));
+                }
 #pragma unroll
                 for (int k = 0; k < STEPS; k++)
-                    if (y0 + k * ROWS_PER_STEP < H_) q[k] = __ldcs(reinterpret_cast<const uint4 *>(color + at - k * step));
-#pragma unroll
-                for (int k = 0; k < STEPS; k++)
-                    if (y0 + k * ROWS_PER_STEP < H_) *reinterpret_cast<uint4 *>(host_color + at - k * step) = q[k];
+                    if (take[k]) *reinterpret_cast<uint4 *>(host_color + at - k * step) = q[k];
             }
-        } else {
+        } else { // k_tile reports whole tiles for such canvases
             for (int p = tid; p < TILE_W * TILE_H; p += MIRROR_THREADS) {
                 const int px = (tile % tiles_x) * TILE_W + (p & (TILE_W - 1)), py = (tile / tiles_x) * TILE_H + p / TILE_W;
                 if (px >= W_ || py >= H_) continue;

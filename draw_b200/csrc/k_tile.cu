@@ -174,7 +174,7 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
     __shared__ __align__(16) uint32_t colour[TILE_PIXELS];         // r | g << 8 | b << 16 | pad << 24
     __shared__ float staged[CHUNK][STAGE_STRIDE];
     __shared__ uint32_t cand[CAND_CAP];
-    __shared__ uint32_t s_cand_count, s_min, s_max, s_warp_sum[TILE_THREADS / 32];
+    __shared__ uint32_t s_cand_count, s_min, s_max, s_warp_sum[TILE_THREADS / 32], s_strips;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W_ = (int)U.canvas_w, H_ = (int)U.canvas_h;
     const float depth_max = U.depth_max;
@@ -404,6 +404,7 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
     if (W.tile_cycles && tid == 0) atomicMax(&W.tile_cycles[TAP_A * U.n_coarse + tile], (uint32_t)(clock64() - t_start));
 
     // ---- phase C: deferred shading, fused clear ----------------------------------------------------
+    if (tid == 0) s_strips = 0; // phase E: which 64x8 strips of the tile hold something else than the clear colour (ordered by the barriers between)
     // The records of all the lane's winners are requested first (prefetch into L1: no registers held), so
     // that the pixel loop below pays the L2 round trip once and not once per pixel.
     // (Measured alternatives that did not pay: two pixels per lane as independent streams; per-warp staging of the
@@ -547,17 +548,23 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
 #pragma unroll 1
         for (int q = tid; q < (n_win >> 2); q += TILE_THREADS) {
             const int x = wx0 + ((q & (qpr - 1)) << 2), y = wy0 + (q >> qpr_shift);
-            if (x >= W_ || y >= H_) continue;
-            const int p = (y - ty0) * TILE_W + (x - tx0);
-            const uint4 c4 = *reinterpret_cast<const uint4 *>(&colour[p]); // r g b pad -> memory order b g r pad
-            const ulonglong2 k01 = *reinterpret_cast<const ulonglong2 *>(&keys[p]), k23 = *reinterpret_cast<const ulonglong2 *>(&keys[p + 2]);
-            uint4 o;
-            o.x = __byte_perm(c4.x, 0, 0x3012); o.y = __byte_perm(c4.y, 0, 0x3012);
-            o.z = __byte_perm(c4.z, 0, 0x3012); o.w = __byte_perm(c4.w, 0, 0x3012);
-            __stcs(reinterpret_cast<uint4 *>(color + ((size_t)(H_ - 1 - y) * W_ + x) * 4), o);
-            __stcs(reinterpret_cast<float4 *>(depth + (size_t)y * W_ + x),
-                   make_float4(__uint_as_float((uint32_t)(k01.x >> 32)), __uint_as_float((uint32_t)(k01.y >> 32)),
-                               __uint_as_float((uint32_t)(k23.x >> 32)), __uint_as_float((uint32_t)(k23.y >> 32))));
+            bool content = false;
+            if (x < W_ && y < H_) {
+                const int p = (y - ty0) * TILE_W + (x - tx0);
+                const uint4 c4 = *reinterpret_cast<const uint4 *>(&colour[p]); // r g b pad -> memory order b g r pad
+                const ulonglong2 k01 = *reinterpret_cast<const ulonglong2 *>(&keys[p]), k23 = *reinterpret_cast<const ulonglong2 *>(&keys[p + 2]);
+                uint4 o;
+                o.x = __byte_perm(c4.x, 0, 0x3012); o.y = __byte_perm(c4.y, 0, 0x3012);
+                o.z = __byte_perm(c4.z, 0, 0x3012); o.w = __byte_perm(c4.w, 0, 0x3012);
+                __stcs(reinterpret_cast<uint4 *>(color + ((size_t)(H_ - 1 - y) * W_ + x) * 4), o);
+                __stcs(reinterpret_cast<float4 *>(depth + (size_t)y * W_ + x),
+                       make_float4(__uint_as_float((uint32_t)(k01.x >> 32)), __uint_as_float((uint32_t)(k01.y >> 32)),
+                                   __uint_as_float((uint32_t)(k23.x >> 32)), __uint_as_float((uint32_t)(k23.y >> 32))));
+                constexpr uint32_t CLEAR = 155u | (186u << 8) | (255u << 16) | (255u << 24); // phase C's value for a pixel nothing covers
+                content = c4.x != CLEAR || c4.y != CLEAR || c4.z != CLEAR || c4.w != CLEAR;
+            }
+            // a whole tile: every thread makes the same number of steps and a warp's 32 quads are two rows of one strip
+            if (!windowed && __any_sync(0xFFFFFFFFu, content) && lane == 0) atomicOr(&s_strips, 1u << ((y - ty0) >> 3));
         }
     } else {
 #pragma unroll 1
@@ -574,7 +581,12 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
         __syncthreads();
         if (tid == 0) atomicMax(&W.tile_cycles[TAP_TOTAL * U.n_coarse + tile], (uint32_t)(clock64() - t_start));
     }
-    if (tid == 0 && U.tile_state) U.tile_state[tile] = 1; // rasterised content (every window of a split tile says so)
+    // What k_mirror needs to know about the tile (k_mirror.cu): one bit per 64x8 strip that holds something else than the
+    // clear colour.  Windows of a split tile, and canvases whose rows are not 16-byte multiples, say "all of it".
+    if (U.tile_state) {
+        __syncthreads();
+        if (tid == 0) U.tile_state[tile] = (windowed || (W_ & 3) != 0) ? (uint8_t)TILE_STRIPS_ALL : (uint8_t)s_strips;
+    }
 }
 
 // One empty tile written by the whole CTA: 16 bytes of colour and 16 of depth per thread, fire-and-forget

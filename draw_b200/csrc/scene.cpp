@@ -223,8 +223,8 @@ struct draw_canvas {
     size_t h_color_cap = 0;
     bool host_dirty = true;
     bool host_mirror = false;   // every render also refreshes the pinned mirror (draw_canvas_enable_host_mirror)
-    // Incremental read-back (k_mirror.cu).  tile_state: per tile, 1 = the last render rasterised into it, 0 = it only wrote
-    // the clear colour (written by k_tile); mirror_state: the same for the frame the host mirror holds.
+    // Incremental read-back (k_mirror.cu).  tile_state: per tile, the mask of its 64x8 strips that hold something else than
+    // the clear colour after the last render (written by k_tile); mirror_state: the same for the frame the host mirror holds.
     uint8_t *h_color_dev = nullptr;     // the mirror's device-side address
     DevBuf<uint8_t> tile_state, mirror_state;
     DevBuf<uint32_t> mirror_counters;
@@ -589,8 +589,8 @@ int ensure_tile_state(draw_canvas *c) {
     TRY(c->tile_state.reserve(n));
     TRY(c->mirror_state.reserve(n));
     TRY(c->mirror_counters.reserve(2));
-    CU(cudaMemsetAsync(c->tile_state.ptr, 1, n, c->stream));
-    CU(cudaMemsetAsync(c->mirror_state.ptr, 1, n, c->stream));
+    CU(cudaMemsetAsync(c->tile_state.ptr, (int)TILE_STRIPS_ALL, n, c->stream)); // unknown content: every strip
+    CU(cudaMemsetAsync(c->mirror_state.ptr, (int)TILE_STRIPS_ALL, n, c->stream));
     CU(cudaMemsetAsync(c->mirror_counters.ptr, 0, 2 * sizeof(uint32_t), c->stream));
     c->state_tiles = n;
     c->frame_clean = false;
@@ -801,7 +801,7 @@ int enqueue_frame(draw_scene *s, draw_canvas *c) {
     c->frame_clean = c->stripe_y1 == 0 && U.row_step == 1u && c->empty_tile_color && !c->ext_color;
     int mirror_path = 0;
     if (c->host_mirror && !c->ext_color) // the frame follows its render to the host without waiting for the host to ask (map_host then only waits)
-        TRY(refresh_mirror(c, st, U.status_host + CNT_MIRROR_TILES, &mirror_path));
+        TRY(refresh_mirror(c, st, U.status_host + CNT_MIRROR_STRIPS, &mirror_path));
     {
         draw_canvas::FrameInputs in;
         in.scene = s;
@@ -832,7 +832,9 @@ void record_stats(draw_canvas *c, const draw_canvas::FrameInputs &frame) {
     c->stats.tile_refs = c->stats.large_refs + c->stats.medium_refs + c->stats.small_refs + c->stats.transparent_refs;
     c->stats.empty_tiles = st[CNT_EMPTY];
     c->stats.work_items = st[CNT_ITEMS];
-    c->stats.mirror_tiles = frame.mirror_path == 2 ? st[CNT_MIRROR_TILES] : frame.mirror_path == 1 ? (uint32_t)c->state_tiles : 0u;
+    // KiB that went to the host mirror: strips of TILE_W x 8 pixels x 4 bytes, or the whole frame
+    c->stats.mirror_kbytes = frame.mirror_path == 2 ? st[CNT_MIRROR_STRIPS] * (uint32_t)(TILE_W * TILE_STRIP_H * 4 / 1024)
+                             : frame.mirror_path == 1 ? (uint32_t)((c->width * c->height * 4 + 1023) / 1024) : 0u;
     for (int i = 0; i < 5; i++) c->stats.front_phase_ns[i] = st[CNT_PHASE_NS + i + 1] - st[CNT_PHASE_NS + i];
     c->stats.front_phase_ns[5] = st[CNT_PHASE_NS + 6] - st[CNT_PHASE_NS + 2];                              // triangle phase, slowest CTA
     c->stats.front_phase_ns[6] = st[CNT_PHASE_NS + 7] ? st[CNT_PHASE_NS + 7] - st[CNT_PHASE_NS + 6] : 0u; // huge-record phase (after the barrier)

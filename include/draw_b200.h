@@ -99,8 +99,8 @@ typedef struct draw_frame_stats {
     uint32_t overflow;          /* non-zero: a device buffer was too small, frame was re-rendered */
     uint32_t empty_tiles;       /* tiles of this render's rows nothing was binned to (they only get the clear colour and depth) */
     uint32_t work_items;        /* k_tile work items: non-empty tiles, dense ones cut into windows */
-    uint32_t mirror_tiles;      /* tiles of the frame copied to the pinned host mirror behind the render (draw_canvas_enable_host_mirror):
-                                   all of them for a whole-frame copy, the changed ones for an incremental one; 0 without the mirror */
+    uint32_t mirror_kbytes;     /* KiB of the frame copied to the pinned host mirror behind the render (draw_canvas_enable_host_mirror):
+                                   the whole frame, or the 64x8-pixel strips that changed; 0 without the mirror */
     uint32_t front_phase_ns[7]; /* k_front, CTA 0: vertex phase, barrier, triangle phase, barrier (+ huge-record phase), tile phase;
                                    then the triangle phase of the slowest CTA and the huge-record phase */
     uint32_t front_block_ns[5]; /* k_front, first 256-triangle block: set-up, slot scan, record write, binning, clip path */
@@ -192,7 +192,7 @@ int draw_canvas_map_host(draw_canvas *canvas, const uint8_t **out_bytes, size_t 
  * the rendering of frame k+1 on another canvas and draw_canvas_map_host only waits.  The refresh is a copy of the whole
  * frame (4*W*H bytes) or — when the frame is a whole-canvas render, most of it is clear colour and the mirror's content is
  * known — of the tiles that differ from what the mirror holds: drawn in this frame, or drawn in the mirror's frame and
- * cleared since (k_mirror.cu; draw_frame_stats.mirror_tiles says how many).  Either way the mirror is byte-identical to
+ * cleared since (k_mirror.cu, in strips of 64x8 pixels; draw_frame_stats.mirror_kbytes says how much).  Either way the mirror is byte-identical to
  * the device frame.  Off by default. */
 int draw_canvas_enable_host_mirror(draw_canvas *canvas, int enabled);
 /* depth_frame (get_pixel_depth :413): width*height floats, row index = canvas y (not flipped). */

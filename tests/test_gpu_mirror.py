@@ -35,7 +35,7 @@ def test_incremental_mirror_follows_a_moving_camera():
         ring.append(c)
     plain = draw_b200.Canvas(W, H)
     plain.init_depth(DEPTH_MAX)
-    total_tiles = ((W + 63) // 64) * ((H + 31) // 32)
+    whole_kb = (4 * W * H + 1023) // 1024
     copied = []
     for k in range(16):
         cam = cams[(4 * k) % len(cams)]
@@ -49,10 +49,10 @@ def test_incremental_mirror_follows_a_moving_camera():
                 s.render(plain)
                 got = ring[j % 3].as_bytes_slice()
                 assert np.array_equal(got, plain.as_bytes_slice()), f"frame {j}"
-                copied.append(ring[j % 3].last_frame_stats()["mirror_tiles"])
-    assert copied[0] == total_tiles                     # the first refresh of a mirror is a whole-frame copy
-    assert 0 < min(copied) < total_tiles // 2, copied   # later ones are incremental
-    assert (np.array(copied) <= total_tiles).all()
+                copied.append(ring[j % 3].last_frame_stats()["mirror_kbytes"])
+    assert copied[0] == whole_kb                       # the first refresh of a mirror is a whole-frame copy
+    assert 0 < min(copied) < whole_kb // 4, copied     # later ones are incremental
+    assert (np.array(copied) <= whole_kb).all()
 
 
 def test_mirror_survives_everything_else_that_writes_the_frame():
@@ -83,7 +83,7 @@ def test_mirror_survives_everything_else_that_writes_the_frame():
     for k in range(4):  # warm the incremental path
         both_render()
         check(f"render {k}")
-    assert c.last_frame_stats()["mirror_tiles"] < ((W + 63) // 64) * ((H + 31) // 32)
+    assert c.last_frame_stats()["mirror_kbytes"] < 4 * W * H // 1024 // 2
     c.disable_depth_update()
     oc.disable_depth_update()
     for clip, v in cmds:  # overlay on top of the rendered frame
@@ -133,7 +133,7 @@ def test_mirror_paths_agree(monkeypatch):
         "for k in range(10):\n"
         "    s.camera = draw_b200.Camera.new(cams[5 * k][:3], cams[5 * k][3:]); s.render(c)\n"
         "    a = c.as_bytes_slice(); h = (h * 1000003 + int(a.astype(np.uint64).sum()) + int(a[::7, ::5].astype(np.uint64).sum())) % (1 << 61)\n"
-        "print('HASH', h, c.last_frame_stats()['mirror_tiles'])\n")
+        "print('HASH', h, c.last_frame_stats()['mirror_kbytes'])\n")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = {}
     for mode in ("0", "1"):
@@ -143,4 +143,4 @@ def test_mirror_paths_agree(monkeypatch):
         line = [ln for ln in r.stdout.splitlines() if ln.startswith("HASH")][0].split()
         out[mode] = (line[1], int(line[2]))
     assert out["0"][0] == out["1"][0]
-    assert out["1"][1] < out["0"][1]  # fewer tiles crossed the bus
+    assert out["1"][1] < out["0"][1]  # fewer bytes crossed the bus
