@@ -68,9 +68,11 @@ if d3:
     e = d3["e2e"]
     w(f"- e2e: {e['value']:.0f} frames/s with six canvases in flight, {e['serial_value']:.0f} for the reference's serial loop (one canvas: render, read, repeat).  "
       f"{e['d2h_bytes_per_step'] / d3['config']['frames_per_step'] / 1e6:.2f} MB per frame crossed PCIe instead of {e.get('d2h_frame_bytes', 0) / 1e6:.1f} MB: the host mirror is "
-      f"refreshed by the tiles that differ from the frame it holds (`k_mirror`, posted writes from the SMs: {e['d2h_achieved_gbs']:.1f} GB/s; the copy engine's ceiling for "
+      f"refreshed by the 64x8-pixel strips that differ from the frame it holds (`k_mirror`, posted writes from the SMs: {e['d2h_achieved_gbs']:.1f} GB/s; the copy engine's ceiling for "
       f"whole frames is {e['d2h_ceiling_gbs']:.1f} GB/s = {e['d2h_ceiling_gbs'] * 1e9 / max(1, e.get('d2h_frame_bytes', 1)):.0f} frames/s, which is where e2e sat before: 1 622 frames/s).  "
-      f"`DRAW_B200_MIRROR_TILES=0` restores whole-frame copies; pipeline depth 3 / 4 / 6 / 8 gives 8.3 / 9.6 / 11.1 / 11.9 k frames/s (`DRAW_BENCH_E2E_DEPTH`).")
+      f"`DRAW_B200_MIRROR_TILES=0` restores whole-frame copies; pipeline depth 3 / 4 / 6 / 8 / 12 gives 8.3 / 9.6 / 11.6 / 11.9 / 12.4 k frames/s (`DRAW_BENCH_E2E_DEPTH`).  "
+      f"With `k_mirror` pointed at device memory instead of the mirror the same loop runs at 22.6 k frames/s: e2e is bound by the SM-initiated PCIe writes "
+      f"(plain stores, streaming / write-through hints and `cp.async.bulk` rows all give ~33 GB/s).")
     w(f"- `k_front` phases on C3 (CTA 0's global-timer stamps, us): vertex {ph['vertex']:.1f}, barrier {ph['barrier1']:.1f}, triangle "
       f"{ph['triangle']:.1f} (slowest CTA {ph['triangle_slowest_cta']:.1f}), barrier (+ huge-record phase) {ph['barrier2_and_huge']:.1f}, "
       f"tile {ph['tile']:.1f}.  Round 1's seven launches for the same work: 108 us.")
