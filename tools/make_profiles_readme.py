@@ -94,7 +94,8 @@ if rows:
     w("")
     w("The host side of the box does not scale with N: the plain-copy ceiling (all ranks copying whole 33 MB frames to pinned memory at once, no "
       "renderer involved) is ~57 GB/s for one GPU and 70-140 GB/s for 2, 4 or 8 depending on the box the call landed on (one NUMA node, 32 vCPUs: "
-      "`nvidia-smi topo`).  With the incremental mirror the ranks move a tenth of those bytes, so e2e is no longer pinned to that ceiling.\n")
+      "`nvidia-smi topo`).  With the incremental mirror a frame costs a tenth of those bytes: one and two GPUs are bound by their own SM-initiated "
+      "PCIe writes (~33 GB/s each), four and eight together reach the box's ceiling again — at 28-35 k frames/s instead of 2.9-4.2 k.\n")
     w("Sort-first, ONE frame across the ranks (`sort_first` in the same lines; CUDA events around all frames, no host synchronisation in the "
       "loop; every entry `bit_exact: true` = composed frame equals the single-GPU frame):\n")
     w("| N | config | 1 GPU, frames back to back ms | 1 GPU, lone frame ms | p2p interleaved ms (x back-to-back / x lone) | NCCL interleaved | p2p stripes | NCCL stripes |")
