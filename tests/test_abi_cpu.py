@@ -71,3 +71,31 @@ def test_product_does_not_import_the_oracle():
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "oracle/" not in src and "liboracle" not in src, f
+
+
+def test_struct_layouts_agree_across_the_bindings(tmp_path):
+    """The header compiled as C says how big its structs are and where draw_frame_stats' fields sit; the ctypes mirrors
+    (draw_b200/_native.py, draw_b200.api.VERTEX2D) and the Rust sys crate's field lists must agree with it."""
+    import subprocess
+    from draw_b200 import _native
+    from draw_b200.synthetic import _VERTEX2D
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "draw_b200.h"\nint main(void) {\n'
+                   '  printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(draw_frame_stats), offsetof(draw_frame_stats, mirror_kbytes),\n'
+                   '         offsetof(draw_frame_stats, front_phase_ns), offsetof(draw_frame_stats, front_block_ns), sizeof(draw_vertex2d),\n'
+                   '         sizeof(draw_rect), sizeof(draw_texture_map));\n  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    S = _native.FrameStats
+    assert got == [ctypes.sizeof(S), S.mirror_kbytes.offset, S.front_phase_ns.offset, S.front_block_ns.offset, _VERTEX2D.itemsize,
+                   ctypes.sizeof(_native.Rect), ctypes.sizeof(_native.TextureMap)]
+    # field order of draw_frame_stats: header == ctypes == Rust
+    header = open(os.path.join(ROOT, "include", "draw_b200.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", header[header.index("typedef struct draw_frame_stats {"):header.index("} draw_frame_stats;")], flags=re.S)
+    c_fields = [n for decl in re.findall(r"uint32_t\s+([^;]+);", body) for n in re.findall(r"([a-z_0-9]+)(?:\[\d+\])?\s*(?:,|$)", decl.strip())]
+    assert c_fields == [n for n, _ in S._fields_]
+    rust = open(os.path.join(ROOT, "bindings", "draw-b200-sys", "src", "lib.rs")).read()
+    rbody = rust[rust.index("pub struct draw_frame_stats {"):]
+    rbody = rbody[:rbody.index("}")]
+    assert re.findall(r"pub ([a-z_0-9]+):", rbody) == c_fields
