@@ -98,7 +98,7 @@ struct FrameUniforms {
     uint32_t split_min_cost, split_div, split_max; // k_front's tile splitting policy (defaults: TILE_SPLIT_*)
     uint32_t bar_base;                 // value of the work set's grid-barrier counter when k_front starts (host-tracked)
     uint32_t empty_tile_color;         // 0: tiles nothing is binned to keep their colour bytes (the caller has cleared the buffer: draw_canvas_set_empty_tile_color)
-    uint32_t sort_large;               // k_tile: a tile's large references are tested nearest first
+    uint32_t sort_large;               // k_tile: a tile's large references are tested nearest first when there are at least this many (0: never)
     uint32_t clear_first;              // k_tile: a CTA writes its share of the empty tiles before its raster item (else after it)
     uint8_t *tile_state;               // canvas-owned, one byte per tile: k_tile's mask of the 64x8 strips that hold something else than the clear colour (k_mirror.cu)
     uint32_t *status_host;             // pinned host memory of the canvas (device-mapped): k_tile copies counters[0..31] there

@@ -99,7 +99,6 @@ __device__ __forceinline__ uint32_t filter_refs(const uint32_t *__restrict__ lis
 // nearest triangles first, most of the others are turned away per block instead of per pixel.  Key = the smallest
 // vertex depth of the record (a lower bound of its depths) over the slot; bitonic sort in `scratch` (the tile's key
 // array, not in use before the end of phase A); the slots come back in cand[].  Ends with a barrier.
-constexpr uint32_t SORT_MIN_REFS = 16;
 __device__ __forceinline__ void sort_refs_front_to_back(const uint32_t *refs, uint32_t n, const PrepRec *__restrict__ prep,
                                                         const uint32_t *__restrict__ block_loc, unsigned long long *scratch, uint32_t *cand,
                                                         int tid) {
@@ -277,7 +276,7 @@ __device__ __forceinline__ void tile_item(const uint32_t item, const FrameUnifor
                 n_refs = filter_refs(refs, 1u, seg_n, prep, W.block_loc, cand, &s_cand_count, wx0f, wx1f, wy0f, wy1f, tid);
                 refs = cand;
             }
-            if (n_refs >= SORT_MIN_REFS && U.sort_large) {
+            if (U.sort_large && n_refs >= U.sort_large) {
                 sort_refs_front_to_back(refs, n_refs, prep, W.block_loc, keys, cand, tid);
                 refs = cand;
             }

@@ -294,7 +294,7 @@ struct Config {
     int front_cps = std::max(0, env_int("DRAW_B200_FRONT_CPS", 0)); // k_front CTAs per SM
     int raster_ctas = std::max(0, env_int("DRAW_B200_RASTER_CTAS", 0));
     int mirror_tiles = env_int("DRAW_B200_MIRROR_TILES", 1); // host mirror: copy only the tiles that changed when most of the frame is clear colour (k_mirror.cu)
-    int sort_large = env_int("DRAW_B200_SORT_LARGE", 1);   // k_tile: a tile's large references front to back (the early depth rejects bite sooner)
+    int sort_large = std::max(0, env_int("DRAW_B200_SORT_LARGE", 16)); // k_tile: lists of at least this many large references are tested front to back (0: never)
     int clear_first = env_int("DRAW_B200_CLEAR_FIRST", 0); // k_tile: empty-tile stores before (1) or after (0) a CTA's raster item
     int rec_cap = std::max(0, env_int("DRAW_B200_REC_CAP", 0));   // initial record / reference capacities (tests force overflows)
     int refs_cap = std::max(0, env_int("DRAW_B200_REFS_CAP", 0));
