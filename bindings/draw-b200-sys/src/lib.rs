@@ -69,6 +69,14 @@ pub struct draw_rect {
     pub x1: u64,
     pub y1: u64,
 }
+/// One draw command of Gui::render (src/app/gui.rs:397-481): a run of triangles and its clipping rectangle.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct draw_command2d {
+    pub n_triangles: usize,
+    pub has_clip: c_int,
+    pub clip: draw_rect,
+}
 /// TextureMap (scene/mod.rs:102-110); `pixels == NULL` is TextureMap::default() (1x1x3 white).
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -200,6 +208,8 @@ extern "C" {
     pub fn draw_texture_destroy(texture: *mut draw_texture);
     pub fn draw_canvas_draw_triangles(canvas: *mut draw_canvas, vertices: *const draw_vertex2d, n_triangles: usize,
                                       texture: *const draw_texture, clipping_rect: *const draw_rect) -> c_int;
+    pub fn draw_canvas_draw_commands(canvas: *mut draw_canvas, vertices: *const draw_vertex2d, n_triangles: usize,
+                                     commands: *const draw_command2d, n_commands: usize, texture: *const draw_texture) -> c_int;
 
     // ---- device-side plumbing (multi-GPU drivers)
     pub fn draw_canvas_device_ptrs(canvas: *mut draw_canvas, out_color: *mut *mut c_void, out_depth: *mut *mut c_void) -> c_int;

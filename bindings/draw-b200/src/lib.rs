@@ -388,6 +388,26 @@ impl Canvas {
         let rect_ptr = rect.as_ref().map_or(std::ptr::null(), |r| r as *const sys::draw_rect);
         check(unsafe { sys::draw_canvas_draw_triangles(self.h, v.as_ptr(), v.len() / 3, texture.h, rect_ptr) })
     }
+    /// A whole GUI frame in one submission (src/app/gui.rs:389-485): `commands` are consecutive runs of `vertices`'
+    /// triangles, each (number of triangles, clipping rectangle), drawn in order with one texture.
+    pub fn draw_commands(&mut self, vertices: &[VertexSimpleAttributes], commands: &[(usize, Option<Rectangle>)], texture: &DeviceTexture) {
+        let v: Vec<sys::draw_vertex2d> = vertices
+            .iter()
+            .map(|a| sys::draw_vertex2d {
+                x: a.screen_coord[0], y: a.screen_coord[1], u: a.texture_coord[0], v: a.texture_coord[1],
+                r: a.color[0], g: a.color[1], b: a.color[2], pad: 0, alpha: a.alpha,
+            })
+            .collect();
+        let table: Vec<sys::draw_command2d> = commands
+            .iter()
+            .map(|(n, r)| sys::draw_command2d {
+                n_triangles: *n,
+                has_clip: r.is_some() as c_int,
+                clip: r.map_or(sys::draw_rect::default(), |r| sys::draw_rect { x0: r.x0 as u64, y0: r.y0 as u64, x1: r.x1 as u64, y1: r.y1 as u64 }),
+            })
+            .collect();
+        check(unsafe { sys::draw_canvas_draw_commands(self.h, v.as_ptr(), v.len() / 3, table.as_ptr(), table.len(), texture.h) })
+    }
     /// Application::export_frame_as(Png) (app/mod.rs:316-360)
     pub fn export_png(&self, path: &str) {
         let c = CString::new(path).unwrap();

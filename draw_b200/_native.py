@@ -45,6 +45,10 @@ class Rect(C.Structure):  # draw_rect
     _fields_ = [("x0", C.c_uint64), ("y0", C.c_uint64), ("x1", C.c_uint64), ("y1", C.c_uint64)]
 
 
+class Command2D(C.Structure):  # draw_command2d
+    _fields_ = [("n_triangles", C.c_size_t), ("has_clip", C.c_int), ("clip", Rect)]
+
+
 class FrameStats(C.Structure):
     _NAMES = ("input_triangles", "setup_records", "tile_refs", "large_refs", "medium_refs", "small_refs", "transparent_refs",
               "overflow", "empty_tiles", "work_items", "mirror_kbytes")
@@ -110,6 +114,7 @@ SIGNATURES = {
     "draw_texture_create": (C.c_int, [C.POINTER(TextureMap), C.POINTER(C.c_void_p)]),
     "draw_texture_destroy": (None, [C.c_void_p]),
     "draw_canvas_draw_triangles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(Rect)]),
+    "draw_canvas_draw_commands": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Command2D), C.c_size_t, C.c_void_p]),
     "draw_device_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "draw_device_free": (C.c_int, [C.c_void_p]),
     "draw_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),

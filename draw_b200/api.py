@@ -137,6 +137,22 @@ class Canvas:
         rect = None if clipping_rect is None else C.byref(N.Rect(*[int(c) for c in clipping_rect]))
         N.check(N.lib().draw_canvas_draw_triangles(self._h, v.ctypes.data, v.size // 3, tex._h, rect))
 
+    def draw_commands(self, commands, texture):
+        """A whole GUI frame (src/app/gui.rs:389-485) in one submission: `commands` is a sequence of (clipping_rect or None,
+        VERTEX2D array) pairs, drawn in order with one texture — the result of one draw_triangles call per pair."""
+        commands = [(clip, np.ascontiguousarray(v, VERTEX2D)) for clip, v in commands]
+        if any(v.ndim != 1 or v.size % 3 for _, v in commands):
+            raise ValueError("vertices hold three VERTEX2D entries per triangle")
+        verts = np.concatenate([v for _, v in commands]) if commands else np.zeros(0, VERTEX2D)
+        table = (N.Command2D * max(1, len(commands)))()
+        for k, (clip, v) in enumerate(commands):
+            table[k].n_triangles = v.size // 3
+            table[k].has_clip = 0 if clip is None else 1
+            if clip is not None:
+                table[k].clip = N.Rect(*[int(c) for c in clip])
+        tex = texture if isinstance(texture, DeviceTexture) else DeviceTexture(texture)
+        N.check(N.lib().draw_canvas_draw_commands(self._h, verts.ctypes.data, verts.size // 3, table, len(commands), tex._h))
+
     def draw_triangle(self, a_vertex, b_vertex, c_vertex, texture, clipping_rect=None):
         """One Canvas::draw_triangle call; each vertex is (x, y, u, v, (r, g, b), alpha)."""
         v = np.zeros(3, VERTEX2D)

@@ -244,6 +244,10 @@ constexpr int N_FRAME_KERNELS = 4; // k_sort_transparent k_front k_raster k_tile
 constexpr int OVERLAY_BIN = 64;             // pixels per bin edge
 constexpr size_t OVERLAY_REC_BYTES = 80;    // per triangle, written by k_overlay_setup
 constexpr uint32_t OVERLAY_MAX_BATCH = 32768; // triangles per launch pair (sizes the bin masks)
+struct OverlayClip {
+    unsigned long long c[4]; // x0, y0, x1, y1 as given to Rectangle::from_coords
+    unsigned long long has;  // 0: Option::None (the whole screen)
+};
 struct OverlayParams {
     const void *verts; // 3 draw_vertex2d per triangle
     void *recs;        // n x OVERLAY_REC_BYTES
@@ -251,8 +255,12 @@ struct OverlayParams {
     uint32_t *bin_any; // [bins_x * bins_y]
     uint32_t n, words, bins_x, bins_y;
     uint32_t width, height;
-    unsigned long long clip[4]; // x0, y0, x1, y1 as given to Rectangle::from_coords
-    uint32_t has_clip;
+    // the draw commands of the submission: command c owns the triangles [cmd_first[c], cmd_first[c + 1]) (numbered over the
+    // whole submission) and clips them to cmd_clip[c]
+    const unsigned long long *cmd_first; // [n_cmds + 1]
+    const OverlayClip *cmd_clip;         // [n_cmds]
+    uint32_t n_cmds;
+    uint32_t first;                      // number of this batch's first triangle in the submission
     const void *texels; // RGBA8, row 0 = top
     uint32_t tex_w, tex_h;
     uint32_t *color;

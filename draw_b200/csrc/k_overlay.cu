@@ -3,7 +3,8 @@
 // written over the frame in SUBMISSION ORDER with a depth of 0.0.
 //
 // The reference walks every triangle's clipped bounding box pixel by pixel, one triangle after the other.  Here a
-// batch of triangles (one draw command: one texture, one clipping rectangle) is two launches:
+// submission — the draw commands of a GUI frame that share a texture, each with its own clipping rectangle — is two
+// launches per 32 768 triangles:
 //
 //   k_overlay_setup  one thread per triangle: snapped vertices, the three literal edge functions, their values at
 //                    the opposite vertex and at (-1,-1), the clipped pixel rectangle (Rectangle::from_coords / clip
@@ -96,7 +97,15 @@ __global__ void __launch_bounds__(128) k_overlay_setup(const OverlayParams P) {
     RectU64 drawable = rect_from_coords(sat_usize_nan0(min3_ref(px[0], px[1], px[2])), sat_usize_nan0(min3_ref(py[0], py[1], py[2])),
                                         sat_usize_nan0(max3_ref(px[0], px[1], px[2])), sat_usize_nan0(max3_ref(py[0], py[1], py[2])));
     drawable = rect_clip(drawable, screen);
-    const RectU64 valid = rect_clip(P.has_clip ? rect_from_coords(P.clip[0], P.clip[1], P.clip[2], P.clip[3]) : screen, drawable);
+    // the triangle's draw command (commands own consecutive ranges of the submission): its clipping rectangle
+    uint32_t lo = 0, hi = P.n_cmds; // largest c with cmd_first[c] <= number of the triangle
+    const unsigned long long number = (unsigned long long)P.first + i;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(P.cmd_first + mid) <= number) lo = mid; else hi = mid;
+    }
+    const OverlayClip cl = P.cmd_clip[lo];
+    const RectU64 valid = rect_clip(cl.has ? rect_from_coords(cl.c[0], cl.c[1], cl.c[2], cl.c[3]) : screen, drawable);
     const uint32_t x0 = (uint32_t)valid.x, y0 = (uint32_t)valid.y, x1 = (uint32_t)(valid.x + valid.w), y1 = (uint32_t)(valid.y + valid.h);
     r.x01 = x0 | x1 << 16;
     r.y01 = y0 | y1 << 16;

@@ -258,7 +258,7 @@ struct draw_canvas {
     };
     std::vector<FrameInputs> pending;
     // draw_canvas_draw_triangles scratch: the batch's vertices, its records, the bin masks and the per-bin flags
-    DevBuf<uint8_t> ov_verts, ov_recs;
+    DevBuf<uint8_t> ov_verts, ov_recs, ov_cmds;
     DevBuf<uint32_t> ov_masks, ov_any;
     draw_frame_stats stats{};
     uint64_t launches = 0;
@@ -1477,12 +1477,23 @@ void draw_texture_destroy(draw_texture *texture) {
     delete texture;
 }
 
-int draw_canvas_draw_triangles(draw_canvas *canvas, const draw_vertex2d *vertices, size_t n_triangles, const draw_texture *texture,
-                               const draw_rect *clipping_rect) {
+int draw_canvas_draw_commands(draw_canvas *canvas, const draw_vertex2d *vertices, size_t n_triangles, const draw_command2d *commands,
+                              size_t n_commands, const draw_texture *texture) {
     GUARD_BEGIN
-    if (!canvas || !texture || (!vertices && n_triangles)) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!canvas || !texture || (!vertices && n_triangles) || (!commands && n_commands)) return fail(DRAW_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!canvas->has_depth) return fail(DRAW_ERR_INVALID_ARGUMENT, "Depth not initialized"); // get_pixel_depth indexes an empty Vec
     if (texture->device != canvas->device) return fail(DRAW_ERR_INVALID_ARGUMENT, "texture and canvas live on different devices");
+    // the commands own consecutive triangle ranges, in submission order
+    std::vector<unsigned long long> first(n_commands + 1, 0);
+    std::vector<OverlayClip> clips(std::max<size_t>(n_commands, 1));
+    for (size_t k = 0; k < n_commands; k++) {
+        first[k + 1] = first[k] + commands[k].n_triangles;
+        clips[k].has = commands[k].has_clip ? 1u : 0u;
+        clips[k].c[0] = commands[k].clip.x0; clips[k].c[1] = commands[k].clip.y0;
+        clips[k].c[2] = commands[k].clip.x1; clips[k].c[3] = commands[k].clip.y1;
+    }
+    if (first[n_commands] != n_triangles) return fail(DRAW_ERR_INVALID_ARGUMENT, "the commands' triangle counts must add up to n_triangles");
+    if (n_triangles == 0) return DRAW_OK;
     TRY(ensure_device(canvas->device));
     // A frame still in flight may have to be rendered again (overflow); the triangles go on top of the settled frame.
     TRY(finish_frame(canvas));
@@ -1491,30 +1502,32 @@ int draw_canvas_draw_triangles(draw_canvas *canvas, const draw_vertex2d *vertice
     P.height = (uint32_t)canvas->height;
     P.bins_x = (P.width + OVERLAY_BIN - 1) / OVERLAY_BIN;
     P.bins_y = (P.height + OVERLAY_BIN - 1) / OVERLAY_BIN;
-    if (clipping_rect) {
-        P.has_clip = 1;
-        P.clip[0] = clipping_rect->x0;
-        P.clip[1] = clipping_rect->y0;
-        P.clip[2] = clipping_rect->x1;
-        P.clip[3] = clipping_rect->y1;
-    }
     P.texels = texture->texels.ptr;
     P.tex_w = texture->width;
     P.tex_h = texture->height;
     P.color = reinterpret_cast<uint32_t *>(canvas->color());
     P.depth = canvas->depth();
     P.depth_update = canvas->depth_update ? 1u : 0u;
+    // the command table: [n_commands + 1] first-triangle numbers, then the clipping rectangles (pageable sources: the copies
+    // have left these vectors when cudaMemcpyAsync returns)
+    const size_t first_bytes = (n_commands + 1) * sizeof(unsigned long long);
+    TRY(canvas->ov_cmds.reserve(first_bytes + n_commands * sizeof(OverlayClip)));
+    CU(cudaMemcpyAsync(canvas->ov_cmds.ptr, first.data(), first_bytes, cudaMemcpyHostToDevice, canvas->stream));
+    CU(cudaMemcpyAsync(canvas->ov_cmds.ptr + first_bytes, clips.data(), n_commands * sizeof(OverlayClip), cudaMemcpyHostToDevice, canvas->stream));
+    P.cmd_first = reinterpret_cast<const unsigned long long *>(canvas->ov_cmds.ptr);
+    P.cmd_clip = reinterpret_cast<const OverlayClip *>(canvas->ov_cmds.ptr + first_bytes);
+    P.n_cmds = (uint32_t)n_commands;
     const size_t n_bins = (size_t)P.bins_x * P.bins_y;
-    for (size_t first = 0; first < n_triangles; first += OVERLAY_MAX_BATCH) { // batches keep submission order on the stream
-        const uint32_t n = (uint32_t)std::min<size_t>(OVERLAY_MAX_BATCH, n_triangles - first);
+    for (size_t at = 0; at < n_triangles; at += OVERLAY_MAX_BATCH) { // batches keep submission order on the stream
+        const uint32_t n = (uint32_t)std::min<size_t>(OVERLAY_MAX_BATCH, n_triangles - at);
         P.n = n;
+        P.first = (uint32_t)at;
         P.words = (n + 31) / 32;
         TRY(canvas->ov_verts.reserve((size_t)n * 3 * sizeof(draw_vertex2d)));
         TRY(canvas->ov_recs.reserve((size_t)n * OVERLAY_REC_BYTES));
         TRY(canvas->ov_masks.reserve(n_bins * P.words));
         TRY(canvas->ov_any.reserve(n_bins));
-        // pageable source: the copy has left the caller's buffer when this returns
-        CU(cudaMemcpyAsync(canvas->ov_verts.ptr, vertices + first * 3, (size_t)n * 3 * sizeof(draw_vertex2d), cudaMemcpyHostToDevice,
+        CU(cudaMemcpyAsync(canvas->ov_verts.ptr, vertices + at * 3, (size_t)n * 3 * sizeof(draw_vertex2d), cudaMemcpyHostToDevice,
                            canvas->stream));
         P.verts = canvas->ov_verts.ptr;
         P.recs = canvas->ov_recs.ptr;
@@ -1522,9 +1535,18 @@ int draw_canvas_draw_triangles(draw_canvas *canvas, const draw_vertex2d *vertice
         P.bin_any = canvas->ov_any.ptr;
         CU(launch_overlay(P, canvas->stream, &canvas->launches));
     }
-    if (n_triangles) touch_frame(canvas);
+    touch_frame(canvas);
     return DRAW_OK;
     GUARD_END
+}
+
+int draw_canvas_draw_triangles(draw_canvas *canvas, const draw_vertex2d *vertices, size_t n_triangles, const draw_texture *texture,
+                               const draw_rect *clipping_rect) {
+    draw_command2d cmd{};
+    cmd.n_triangles = n_triangles;
+    cmd.has_clip = clipping_rect ? 1 : 0;
+    if (clipping_rect) cmd.clip = *clipping_rect;
+    return draw_canvas_draw_commands(canvas, vertices, n_triangles, &cmd, 1, texture);
 }
 
 int draw_canvas_size(const draw_canvas *canvas, size_t *width, size_t *height) {

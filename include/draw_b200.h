@@ -226,6 +226,19 @@ void draw_texture_destroy(draw_texture *texture);
  * (draw_canvas_init_depth), as the reference's depth test does. */
 int draw_canvas_draw_triangles(draw_canvas *canvas, const draw_vertex2d *vertices, size_t n_triangles, const draw_texture *texture,
                                const draw_rect *clipping_rect);
+/* One draw command of Gui::render (src/app/gui.rs:397-481, ig::DrawCmd::Elements): n_triangles consecutive triangles of a
+ * submission and the clipping rectangle they are drawn with (has_clip == 0: None). */
+typedef struct draw_command2d {
+    size_t n_triangles;
+    int has_clip;
+    draw_rect clip;
+} draw_command2d;
+/* A whole GUI frame at once: the draw commands of src/app/gui.rs:389-485 that share a texture (ImGui's font atlas), in
+ * submission order — command k draws the next commands[k].n_triangles triangles of `vertices` with its own clipping
+ * rectangle; the counts must add up to n_triangles.  Same result as one draw_canvas_draw_triangles call per command, in two
+ * kernel launches per 32 768 triangles instead of two per command. */
+int draw_canvas_draw_commands(draw_canvas *canvas, const draw_vertex2d *vertices, size_t n_triangles, const draw_command2d *commands,
+                              size_t n_commands, const draw_texture *texture);
 
 /* ---- device-side plumbing (not in the reference; used by the multi-GPU drivers) ------ */
 /* Device pointers of the colour (BGRA8, y-flipped rows) and depth (f32) buffers. */

@@ -214,6 +214,27 @@ class Canvas {
         if (clipping_rect) r = {clipping_rect->x0, clipping_rect->y0, clipping_rect->x1, clipping_rect->y1};
         check(draw_canvas_draw_triangles(h_, v.data(), n_triangles, texture.handle(), clipping_rect ? &r : nullptr));
     }
+    // a whole GUI frame: consecutive runs of triangles, each with its own clipping rectangle (src/app/gui.rs:389-485)
+    struct Command {
+        size_t n_triangles;
+        const Rectangle *clipping_rect; // nullptr is None
+    };
+    void draw_commands(const VertexSimpleAttributes *vertices, const std::vector<Command> &commands, const DeviceTexture &texture) {
+        size_t n_triangles = 0;
+        std::vector<draw_command2d> table(commands.size());
+        for (size_t k = 0; k < commands.size(); k++) {
+            table[k].n_triangles = commands[k].n_triangles;
+            table[k].has_clip = commands[k].clipping_rect ? 1 : 0;
+            if (const Rectangle *r = commands[k].clipping_rect) table[k].clip = {r->x0, r->y0, r->x1, r->y1};
+            n_triangles += commands[k].n_triangles;
+        }
+        std::vector<draw_vertex2d> v(3 * n_triangles);
+        for (size_t i = 0; i < v.size(); i++) {
+            const VertexSimpleAttributes &a = vertices[i];
+            v[i] = {a.screen_coord[0], a.screen_coord[1], a.texture_coord[0], a.texture_coord[1], a.color[0], a.color[1], a.color[2], 0, a.alpha};
+        }
+        check(draw_canvas_draw_commands(h_, v.data(), n_triangles, table.data(), table.size(), texture.handle()));
+    }
     void export_jpeg(const std::string &path) { check(draw_canvas_export_jpeg(h_, path.c_str())); } // app/mod.rs:316, Jpeg
     void export_png(const std::string &path) { check(draw_canvas_export_png(h_, path.c_str())); } // app/mod.rs:316
     void sync() { check(draw_canvas_sync(h_)); }

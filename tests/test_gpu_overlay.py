@@ -162,3 +162,29 @@ def test_errors():
     with pytest.raises(ValueError):
         c.draw_triangles(v[:2], atlas)
     c.draw_triangles(v[:0], atlas)  # nothing to draw is not an error
+
+
+def test_whole_gui_frame_in_one_submission():
+    """draw_canvas_draw_commands: the commands of a GUI frame, each with its own clipping rectangle (None, inside, swapped
+    corners), in one submission — the frame one draw_triangles call per command gives, and the oracle's."""
+    import draw_b200
+    from draw_b200 import synthetic
+    W, H = 1280, 720
+    atlas = synthetic.font_atlas()
+    tex = draw_b200.DeviceTexture(atlas)
+    cmds = synthetic.gui_command_list(W, H, n_commands=9, quads_per_command=40, seed=21)
+    c, oc = _pair(W, H)
+    c.clear()
+    oc.clear()
+    c.draw_commands(cmds, tex)
+    for clip, v in cmds:
+        oc.draw_triangles(v, atlas, clip)
+    _check(c, oc, "one submission")
+    c2, _ = _pair(W, H)
+    c2.clear()
+    for clip, v in cmds:
+        c2.draw_triangles(v, tex, clip)
+    assert np.array_equal(c2.as_bytes_slice(), c.as_bytes_slice())
+    c.draw_commands([], tex)  # nothing to draw
+    with pytest.raises(ValueError):
+        c.draw_commands([(None, cmds[0][1][:4])], tex)
