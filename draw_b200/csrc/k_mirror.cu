@@ -54,18 +54,14 @@ __global__ void __launch_bounds__(MIRROR_THREADS) k_mirror(const uint8_t *__rest
         }
         if (tid == 0) mirror_state[tile] = (uint8_t)now;
     }
-    // the last CTA to finish posts the frame's total and re-arms the counters
+    // The last CTA to finish posts the frame's total and re-arms the counter.  One 64-bit word (CTAs done << 32 | strips)
+    // and one atomic per CTA: no fence — a fence here would make every CTA wait for its PCIe writes to land.
     if (tid == 0) {
-        if (copied) atomicAdd(&counters[0], copied);
-        __threadfence();
-        if (atomicAdd(&counters[1], 1u) == gridDim.x - 1u) {
-            __threadfence();
-            const uint32_t total = atomicExch(&counters[0], 0u);
-            counters[1] = 0u;
-            if (status_word) {
-                *status_word = total;
-                __threadfence_system();
-            }
+        unsigned long long *word = reinterpret_cast<unsigned long long *>(counters);
+        const unsigned long long old = atomicAdd(word, (1ull << 32) | copied);
+        if ((uint32_t)(old >> 32) == gridDim.x - 1u) {
+            *word = 0ull; // every CTA of this launch has added; the next launch follows in stream order
+            if (status_word) *status_word = (uint32_t)old + copied;
         }
     }
 }

@@ -185,6 +185,10 @@ w("""Reading them:
   0.77 GB read + 1.6 GB written (304 B per surviving record) = 2.2 TB/s; top stalls are the index / vertex gathers (`long_scoreboard`)
   and the per-block barriers of the binning.  Keeping a ticket and the next block's index lines in flight ahead was measured: C5 +2 %,
   C3 -1 %, not kept.  **k_raster, C5**: issue-bound (66 %), 0.29 ms.
+- **k_mirror, C3** (`r02_ncu_full_c3_k_mirror.md`, captured inside the bench's e2e loop): 57.6 us alone for ~2.5 MB of changed strips
+  (~44 GB/s over PCIe when nothing else uses the link), 1.2 M warp instructions, 3 % issue-active: the kernel is the PCIe write path.
+  The capture predates the removal of the `__threadfence()` pair at its end (`membar` 28 per issue in the stall list: every CTA waited for
+  its own posted writes to land before it could leave); with one 64-bit atomic instead the serial loop gained 1 %, the pipelined one nothing.
 """)
 w("## 5. compute-sanitizer (`tools/sanitize.sh`; `r02_sanitizer_*.log`)\n")
 for tool in ("memcheck", "racecheck", "synccheck"):
