@@ -101,6 +101,9 @@ def ring_size(cfg):
     return max(2, int(np.ceil(160e6 / (8 * cfg["W"] * cfg["H"]))) + 1)
 
 
+UNIFORM_BYTES = 296  # sizeof(FrameUniforms), draw_b200/csrc/device_types.h: the per-frame host-to-device copy (camera, light, canvas state)
+
+
 def workload_config(cfg, world):
     """The `config` object of the JSON line — the same in both arms (--impl ours / reference)."""
     W, H = cfg["W"], cfg["H"]
@@ -550,7 +553,7 @@ def run_ours(args, cfg):
                            "frame_frac": cfg["algo_bytes_frame"] / (lone_ms * 1e-3) / 1e9 / peak,
                            "protocol": "one frame at a time: 256 MB fill (L2 flushed), device idle, CUDA events around the frame, median of 32"},
             "clocks": clocks,
-            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 220 * FPS,
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": UNIFORM_BYTES * FPS,
                     "d2h_bytes_per_step": (d2h_bytes // max(1, n_e2e * world) + 128) * FPS,
                     "d2h_frame_bytes": 4 * W * H,
                     "serial_value": serial_fps, "d2h_ceiling_gbs": d2h_ceiling,

@@ -99,3 +99,15 @@ def test_struct_layouts_agree_across_the_bindings(tmp_path):
     rbody = rust[rust.index("pub struct draw_frame_stats {"):]
     rbody = rbody[:rbody.index("}")]
     assert re.findall(r"pub ([a-z_0-9]+):", rbody) == c_fields
+
+
+def test_bench_counts_the_uniform_upload_it_really_makes(tmp_path):
+    """bench.py's h2d_bytes_per_step is frames x sizeof(FrameUniforms): the constant must follow the struct."""
+    import subprocess
+    import bench
+    src = tmp_path / "sz.cpp"
+    src.write_text('#include <cstdio>\n#include "device_types.h"\nint main() { std::printf("%zu\\n", sizeof(drawb200::FrameUniforms)); }\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["g++", "-std=c++17", "-I", os.path.join(ROOT, "draw_b200", "csrc"), "-I", "/usr/local/cuda/include", str(src), "-o", str(exe)],
+                   check=True)
+    assert int(subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout) == bench.UNIFORM_BYTES
