@@ -645,9 +645,9 @@ void set_launch_grids(const draw_scene *s) {
     const bool small_scene = s->dev.n_triangles <= 200000u;
     const int cps = std::min(front_cap, g_cfg.front_cps ? g_cfg.front_cps : (small_scene ? 1 : 8)); // CTAs of 128 threads
     g_front_ctas = (unsigned)(n_sm * std::max(1, cps));
-    // k_raster (128-thread CTAs): three per SM for small scenes (measured on C3: 296 / 444 / 592 / 740 CTAs give 28.1 / 27.8 / 27.6 / 27.5 k
-    // frames/s and 112 / 108 / 107 / 106 us for a lone frame), sixteen for large ones
-    g_raster_ctas = g_cfg.raster_ctas ? (unsigned)g_cfg.raster_ctas : (small_scene ? 444u : 2368u);
+    // k_raster (128-thread CTAs): four per SM for small scenes (measured on C3: 296 / 444 / 592 / 740 CTAs give 28.1 / 27.8 / 27.6 / 27.5 k
+    // frames/s back to back; fewer CTAs cost a lone frame its raster warps: C4's k_raster alone 50 -> 71 us at 444), sixteen for large ones
+    g_raster_ctas = g_cfg.raster_ctas ? (unsigned)g_cfg.raster_ctas : (small_scene ? 592u : 2368u);
     g_tile_ctas = (unsigned)g_cfg.tile_ctas;
 }
 

@@ -87,7 +87,7 @@ for n, f in ((2, "r02_bench_c3_n2.json"), (4, "r02_bench_c3_n4.json"), (8, "r02_
 if rows:
     base = d3["value"] if d3 else None
     w("Frame-parallel (the bench's `value` at N > 1; no collective) and end-to-end.  (These three lines, the launch list and the ncu captures below were "
-      "taken one commit before `k_raster` went from 256- to 128-thread CTAs, which is worth +4 % on C3's frames back to back; the N = 1 lines above are "
+      "taken one commit before `k_raster` went from 256- to 128-thread CTAs, which is worth +3.5 % on C3's frames back to back and costs a lone frame ~3 us of raster warps; the N = 1 lines above are "
       "from the final build.)\n")
     w("| N | frames/s | x N=1 | e2e frames/s | D2H achieved / ceiling GB/s (all ranks) | file |")
     w("|---|---|---|---|---|---|")
