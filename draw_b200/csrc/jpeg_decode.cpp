@@ -453,6 +453,7 @@ struct Decoder {
         img_x = u16();
         n_comp = u8();
         if (img_x == 0 || img_y == 0) bad("empty image");
+        if ((unsigned long long)img_x * (unsigned long long)img_y > (1ull << 28)) bad("image too large (more than 2^28 pixels)");
         if (n_comp == 1) bad("greyscale JPEG: one native channel (the reference accepts 3 or 4, scene/mod.rs:185-189)");
         if (n_comp != 3) bad("only three-component JPEG files are decoded");
         if (len != 6 + 3 * n_comp) bad("bad SOF length");

@@ -153,3 +153,32 @@ def test_writer_quality_argument(tmp_path):
     draw_b200.write_jpg(str(tmp_path / "q.jpg"), src, quality=95)
     q = PIL_Image.open(str(tmp_path / "q.jpg")).quantization
     assert q[0][0] == (16 * 10 + 50) // 100 and max(q[1]) == (99 * 10 + 50) // 100  # the IJG scale: 200 - 2 * 95 = 10
+
+
+def test_decoder_survives_damaged_files(tmp_path):
+    """Truncations and random byte damage anywhere in baseline and progressive files: the decoder either returns an image
+    of the announced size or fails with an error — it does not crash, hang or read outside the file."""
+    import draw_b200
+    rng = np.random.default_rng(3)
+    src = _picture(40, 56)
+    n_ok = n_err = 0
+    for progressive in (False, True):
+        good = str(tmp_path / "good.jpg")
+        PIL_Image.fromarray(src).save(good, quality=85, subsampling=2, progressive=progressive, restart_marker_rows=1)
+        data = bytearray(open(good, "rb").read())
+        for trial in range(150):
+            bad = bytearray(data)
+            if trial % 3 == 0:
+                bad = bad[:int(rng.integers(2, len(bad)))]
+            else:
+                for _ in range(int(rng.integers(1, 6))):
+                    bad[int(rng.integers(2, len(bad)))] = int(rng.integers(0, 256))
+            p = str(tmp_path / "bad.jpg")
+            open(p, "wb").write(bytes(bad))
+            try:
+                a = draw_b200.load_image(p)
+                assert a.ndim == 3 and a.shape[2] == 3 and a.dtype == np.uint8
+                n_ok += 1
+            except draw_b200.DrawError:
+                n_err += 1
+    assert n_ok + n_err == 300 and n_err > 0
