@@ -110,3 +110,28 @@ def test_png_writer_round_trips(tmp_path, c):
     api.write_png(p, a)
     assert np.array_equal(np.asarray(PIL.open(p)), a)
     assert np.array_equal(api.load_image(p), a)
+
+
+def test_png_decoder_survives_damaged_files(tmp_path):
+    """Truncated and randomly damaged PNG files: an image of the announced shape or an error, never a crash."""
+    import draw_b200._native as N
+    rng = np.random.default_rng(4)
+    good = tmp_path / "good.png"
+    PIL.fromarray(_noise(24, 40, 4, 5), "RGBA").save(str(good))
+    data = good.read_bytes()
+    n_err = 0
+    for trial in range(200):
+        bad = bytearray(data)
+        if trial % 3 == 0:
+            bad = bad[:int(rng.integers(1, len(bad)))]
+        else:
+            for _ in range(int(rng.integers(1, 5))):
+                bad[int(rng.integers(8, len(bad)))] = int(rng.integers(0, 256))
+        p = tmp_path / "bad.png"
+        p.write_bytes(bytes(bad))
+        try:
+            a = _lib_decode(str(p))
+            assert a.ndim == 3 and a.shape[2] in (3, 4)
+        except N.DrawError:
+            n_err += 1
+    assert n_err > 0
