@@ -99,3 +99,36 @@ def test_missing_file_is_an_error_not_a_crash(tmp_path):
 def test_reference_models(rel):
     path = os.path.join(REF_MODELS, rel)
     _same(api.load_obj(path), obj_loader.load_from_file(path))
+
+
+def test_damaged_obj_and_mtl_text_is_an_error_or_an_object(tmp_path):
+    """Tokens dropped, swapped for garbage or for out-of-range indices, lines cut: the C++ loader returns an Object or fails
+    with an error (the reference panics on most of these, object.rs:106-454) — no crash."""
+    rng = np.random.default_rng(6)
+    junk = ["", "x", "-", "1e999", "nan", "99999999999", "-7", "0", "1/", "/1", "1//", "//", "a/b/c", "3/99/1", "3/1/99"]
+    n_err = 0
+    for trial in range(250):
+        obj_lines, mtl_lines = SYNTH_OBJ.splitlines(), SYNTH_MTL.splitlines()
+        for lines in (obj_lines, mtl_lines):
+            for _ in range(int(rng.integers(1, 4))):
+                k = int(rng.integers(0, len(lines)))
+                tok = lines[k].split(" ")
+                j = int(rng.integers(0, len(tok)))
+                what = rng.random()
+                if what < 0.5:
+                    tok[j] = junk[int(rng.integers(0, len(junk)))]
+                elif what < 0.75:
+                    del tok[j]
+                else:
+                    tok = tok[:j]
+                lines[k] = " ".join(tok)
+        (tmp_path / "synth.obj").write_text("\n".join(obj_lines) + "\n")
+        (tmp_path / "synth.mtl").write_text("\n".join(mtl_lines) + "\n")
+        try:
+            o = api.load_obj(str(tmp_path / "synth.obj"))
+            assert o.vertices.ndim == 2 and all(m.triangles.shape[1] == 9 for m in o.meshes)
+            for m in o.meshes:  # what comes back is indexable
+                assert m.triangles[:, 0:3].max(initial=0) < len(o.vertices)
+        except draw_b200.DrawError:
+            n_err += 1
+    assert n_err > 0
